@@ -1,0 +1,87 @@
+// Internal C++ launch API (host side).  Every function enqueues work on `st` and returns 0 or a
+// negative error code with the message in cvb_last_error(); nothing here synchronises the device.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cvb {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- tensor-core GEMM (gemm_tcgen05.cuh) -------------------------------------------------------
+struct GemmCall {
+  const bf16* A = nullptr;  // [M, K], leading dim lda
+  long lda = 0;
+  const bf16* W = nullptr;  // [N, K], leading dim ldw   (nn.Linear weight layout)
+  long ldw = 0;
+  int M = 0, N = 0, K = 0;
+  int epi = 0;  // EpiKind
+  void* C = nullptr;
+  long ldc = 0;
+  const void* bias = nullptr;
+  int bias_is_f32 = 0;
+  const void* resid = nullptr;  // bf16, or fp32 when resid_is_f32
+  int resid_is_f32 = 0;
+  long ldr = 0;
+  int n_out = 0;               // EPI_GEGLU: intermediate size
+  const int* m_dev = nullptr;  // optional device-side row count
+  int force_bn = 0;            // 0 = heuristic, else 64 / 128 / 256
+};
+int gemm_bf16(cudaStream_t st, const GemmCall& c);
+
+// ---- fp32 SIMT GEMM (sgemm.cuh): C = act(A[M,K] * W[N,K]^T + bias) (+ resid) -------------------
+enum SgemmAct : int { SACT_NONE = 0, SACT_RELU = 1, SACT_GELU_ERF = 2, SACT_SILU = 3 };
+struct SgemmCall {
+  const float* A = nullptr;
+  long lda = 0;
+  const float* W = nullptr;
+  long ldw = 0;
+  int M = 0, N = 0, K = 0;
+  float* C = nullptr;
+  long ldc = 0;
+  const float* bias = nullptr;
+  const float* resid = nullptr;  // added after activation
+  long ldr = 0;
+  int act = 0;
+  const float* row_bias = nullptr;  // optional second bias [N] (e.g. the per-step time vector)
+};
+int sgemm_f32(cudaStream_t st, const SgemmCall& c);
+
+// ---- normalisation ------------------------------------------------------------------------------
+// Gemma RMSNorm: y = bf16( x * rsqrt(mean(x^2) + eps) * (1 + w) ), statistics in fp32.
+int rmsnorm(cudaStream_t st, const void* x, int x_is_f32, long ldx, const void* w, int w_is_f32,
+            bf16* y, long ldy, int rows, int width, float eps, const int* rows_dev);
+// LayerNorm on bf16 rows (fp32 statistics), bf16 affine.
+int layernorm_bf16(cudaStream_t st, const bf16* x, long ldx, const bf16* w, const bf16* b, bf16* y,
+                   long ldy, int rows, int width, float eps);
+// LayerNorm on fp32 rows, fp32 affine (verifier heads); optional residual added BEFORE the norm.
+int layernorm_f32(cudaStream_t st, const float* x, const float* resid, const float* w,
+                  const float* b, float* y, int rows, int width, float eps);
+
+// ---- attention (attention.cuh) -----------------------------------------------------------------
+struct AttnCall {
+  // Q rows for batch b, head h, token t:  q + (b*q_batch_stride + t*q_row_stride + h*head_dim)
+  const bf16* q = nullptr;
+  long q_batch_stride = 0, q_row_stride = 0;
+  // key/value segment 0 (shared per kv-batch): k0 + (kvb*kv0_batch_stride + j*kv0_row_stride + kvh*head_dim)
+  const bf16* k0 = nullptr;
+  const bf16* v0 = nullptr;
+  long kv0_batch_stride = 0, kv0_row_stride = 0;
+  const int* kv0_len_dev = nullptr;  // [kv batches] valid keys in segment 0 (nullptr -> kv0_len)
+  int kv0_len = 0;
+  int q_per_kv_batch = 1;  // kv batch index = b / q_per_kv_batch
+  // optional segment 1 (per q-batch, e.g. the suffix tokens' own keys): tq1 keys
+  const bf16* k1 = nullptr;
+  const bf16* v1 = nullptr;
+  long kv1_batch_stride = 0, kv1_row_stride = 0;
+  int kv1_len = 0;
+  int suffix_mask = 0;  // 1: query token 0 only sees segment-1 key 0 (pi0 suffix att mask)
+  bf16* out = nullptr;  // out + (b*o_batch_stride + t*o_row_stride + h*head_dim)
+  long o_batch_stride = 0, o_row_stride = 0;
+  int batches = 0, heads = 0, kv_heads = 0, tq = 0, head_dim = 0;
+  float scale = 1.f;
+};
+int attention(cudaStream_t st, const AttnCall& c);
+
+}  // namespace cvb

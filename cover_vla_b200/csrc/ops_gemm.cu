@@ -1,0 +1,136 @@
+// Host dispatch for the tcgen05 GEMM: tensor-map construction (cached), tile-shape heuristic, launch.
+#include <mutex>
+#include <unordered_map>
+
+#include "gemm_tcgen05.cuh"
+#include "host_common.h"
+#include "ops.h"
+
+namespace cvb {
+
+namespace {
+
+struct TmapKey {
+  const void* ptr;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h ^= k.rows * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h ^= k.cols * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+    h ^= k.ld * 0x165667B19E3779F9ull + (h << 6) + (h >> 2);
+    h ^= k.box_rows + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
+
+int get_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+             CUtensorMap* out) {
+  TmapKey key{ptr, rows, cols, ld, box_rows};
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  auto it = g_tmaps.find(key);
+  if (it != g_tmaps.end()) {
+    *out = it->second;
+    return 0;
+  }
+  CUtensorMap tm;
+  CVB_TRY(make_tmap_2d(&tm, ptr, rows, cols, ld, box_rows, GEMM_BK, 2));
+  g_tmaps.emplace(key, tm);
+  *out = tm;
+  return 0;
+}
+
+template <int BN, int STAGES, int EPI>
+int launch(cudaStream_t st, const GemmCall& c, int grid) {
+  using S = GemmSmem<BN, STAGES>;
+  CUtensorMap tmA, tmB;
+  CVB_TRY(get_tmap(c.A, c.M, c.K, c.lda, GEMM_BM, &tmA));
+  CVB_TRY(get_tmap(c.W, c.N, c.K, c.ldw, BN, &tmB));
+  GemmArgs g;
+  g.C = c.C;
+  g.ldc = c.ldc;
+  g.bias = c.bias;
+  g.bias_is_f32 = c.bias_is_f32;
+  g.resid = c.resid;
+  g.resid_is_f32 = c.resid_is_f32;
+  g.ldr = c.ldr;
+  g.M = c.M;
+  g.N = c.N;
+  g.K = c.K;
+  g.n_out = c.n_out;
+  g.m_dev = c.m_dev;
+  auto kern = gemm_bf16_tcgen05<BN, STAGES, EPI>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_set = true;
+  }
+  kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(tmA, tmB, g);
+  CVB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int EPI>
+int launch_bn(cudaStream_t st, const GemmCall& c, int bn, int grid) {
+  switch (bn) {
+    case 256:
+      return launch<256, 4, EPI>(st, c, grid);
+    case 128:
+      return launch<128, 6, EPI>(st, c, grid);
+    default:
+      return launch<64, 8, EPI>(st, c, grid);
+  }
+}
+
+}  // namespace
+
+int gemm_bf16(cudaStream_t st, const GemmCall& c) {
+  CVB_REQUIRE(c.M > 0 && c.N > 0 && c.K > 0, "empty GEMM");
+  CVB_REQUIRE(c.K % 8 == 0, "K must be a multiple of 8 (16-byte TMA rows)");
+  CVB_REQUIRE(c.N % 8 == 0, "N must be a multiple of 8 (16-byte vector epilogue)");
+  CVB_REQUIRE(c.ldc % 8 == 0 || c.epi == EPI_F32, "ldc must be a multiple of 8");
+  const int sms = device_sm_count();
+  const int m_tiles = (c.M + GEMM_BM - 1) / GEMM_BM;
+  auto tiles = [&](int bn) { return m_tiles * ((c.N + bn - 1) / bn); };
+  int bn = c.force_bn;
+  if (c.epi == EPI_GEGLU) {
+    CVB_REQUIRE(c.N % 256 == 0, "EPI_GEGLU expects 256-row packed gate|up blocks");
+    bn = 256;
+  } else if (bn == 0) {
+    if (tiles(256) >= sms)
+      bn = 256;
+    else if (tiles(128) >= sms)
+      bn = 128;
+    else
+      bn = 64;
+  }
+  CVB_REQUIRE(bn == 64 || bn == 128 || bn == 256, "BN must be 64, 128 or 256");
+  int grid = tiles(bn);
+  if (grid > sms) grid = sms;
+  switch (c.epi) {
+    case EPI_STORE:
+      return launch_bn<EPI_STORE>(st, c, bn, grid);
+    case EPI_GELU:
+      return launch_bn<EPI_GELU>(st, c, bn, grid);
+    case EPI_RESID:
+      CVB_REQUIRE(c.resid != nullptr, "EPI_RESID needs a residual pointer");
+      return launch_bn<EPI_RESID>(st, c, bn, grid);
+    case EPI_GEGLU:
+      return launch<256, 4, EPI_GEGLU>(st, c, grid);
+    case EPI_F32:
+      return launch_bn<EPI_F32>(st, c, bn, grid);
+    default:
+      set_last_error("unknown GEMM epilogue kind");
+      return -1;
+  }
+}
+
+}  // namespace cvb

@@ -1,0 +1,177 @@
+// C-ABI entry points of the engine (handle lifetime, weight binding, pi0 sampling, verifier scoring).
+#include <cmath>
+#include <cstring>
+
+#include "engine.h"
+
+namespace cvb {
+
+static bool replace_first(std::string& s, const std::string& from, const std::string& to) {
+  const size_t p = s.find(from);
+  if (p == std::string::npos) return false;
+  s.replace(p, from.size(), to);
+  return true;
+}
+
+// Accept PI0Policy.state_dict() names ("model." prefix) and both transformers module layouts
+// (SURVEY.md Appendix C): canonical = the 4.48.3 layout the published checkpoints use.
+std::string canonical_key(const std::string& k_in) {
+  std::string k = k_in;
+  if (k.rfind("model.", 0) == 0) k = k.substr(6);
+  replace_first(k, "paligemma.model.vision_tower.", "paligemma.vision_tower.");
+  replace_first(k, "paligemma.model.multi_modal_projector.", "paligemma.multi_modal_projector.");
+  replace_first(k, "paligemma.model.language_model.", "paligemma.language_model.model.");
+  return k;
+}
+
+int dalloc(cvb_handle* h, void** p, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  CVB_CUDA(cudaMalloc(p, bytes));
+  h->owned.push_back(*p);
+  return 0;
+}
+
+int get_weight(cvb_handle* h, const std::string& key, int dtype, int64_t numel, const void** out) {
+  auto it = h->weights.find(key);
+  if (it == h->weights.end()) {
+    set_last_error("weight not bound: " + key);
+    return -3;
+  }
+  if (it->second.dtype != dtype) {
+    set_last_error("weight has wrong dtype: " + key);
+    return -3;
+  }
+  if (numel >= 0 && it->second.numel() != numel) {
+    set_last_error("weight has wrong element count: " + key + " (got " +
+                   std::to_string(it->second.numel()) + ", want " + std::to_string(numel) + ")");
+    return -3;
+  }
+  *out = it->second.ptr;
+  return 0;
+}
+
+}  // namespace cvb
+
+extern "C" {
+
+int cvb_create(const cvb_config* cfg, cvb_handle** out) {
+  CVB_REQUIRE(cfg != nullptr && out != nullptr, "null argument");
+  CVB_REQUIRE(cfg->struct_size == (int32_t)sizeof(cvb_config), "cvb_config size mismatch (ABI)");
+  CVB_REQUIRE(cfg->max_rephrases >= 1 && cfg->max_samples >= 1, "max_rephrases / max_samples must be >= 1");
+  cvb_handle* h = new cvb_handle();
+  h->cfg = *cfg;
+  cvb::pi0_required_weights(h->cfg, &h->required);
+  if (cfg->vf_members > 0) cvb::verifier_required_weights(h->cfg, &h->required);
+  *out = h;
+  return 0;
+}
+
+void cvb_destroy(cvb_handle* h) {
+  if (h == nullptr) return;
+  for (auto& g : h->pi0.graphs) cudaGraphExecDestroy(g.second);
+  cvb::verifier_destroy(h);
+  for (void* p : h->owned) cudaFree(p);
+  delete h;
+}
+
+int cvb_bind_weight(cvb_handle* h, const char* key, const void* dev_ptr, int dtype, int ndim,
+                    const int64_t* shape) {
+  CVB_REQUIRE(h != nullptr && key != nullptr && dev_ptr != nullptr, "null argument");
+  CVB_REQUIRE(!h->finalized, "handle already finalized");
+  cvb::Weight w;
+  w.ptr = dev_ptr;
+  w.dtype = dtype;
+  w.shape.assign(shape, shape + ndim);
+  h->weights[cvb::canonical_key(key)] = std::move(w);
+  return 0;
+}
+
+int cvb_required_weight_count(cvb_handle* h) { return h ? (int)h->required.size() : 0; }
+
+const char* cvb_required_weight_name(cvb_handle* h, int index) {
+  if (h == nullptr || index < 0 || index >= (int)h->required.size()) return nullptr;
+  return h->required[index].key.c_str();
+}
+
+int cvb_finalize(cvb_handle* h, void* stream) {
+  CVB_REQUIRE(h != nullptr, "null handle");
+  CVB_REQUIRE(!h->finalized, "handle already finalized");
+  for (const auto& spec : h->required) {
+    auto it = h->weights.find(spec.key);
+    if (it == h->weights.end()) {
+      cvb::set_last_error("missing weight: " + spec.key);
+      return -3;
+    }
+    if (it->second.dtype != spec.dtype) {
+      cvb::set_last_error("wrong dtype for weight: " + spec.key);
+      return -3;
+    }
+    int64_t want = 1;
+    for (auto d : spec.shape) want *= d;
+    if (it->second.numel() != want) {
+      cvb::set_last_error("wrong shape for weight: " + spec.key);
+      return -3;
+    }
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  CVB_TRY(cvb::pi0_finalize(h, st));
+  if (h->cfg.vf_members > 0) CVB_TRY(cvb::verifier_finalize(h, st));
+  CVB_CUDA(cudaStreamSynchronize(st));
+  h->finalized = true;
+  return 0;
+}
+
+int cvb_pi0_sample(cvb_handle* h, const float* image, const int64_t* lang_tokens,
+                   const int32_t* lang_len, const float* state, const float* noise, int R, int K,
+                   float* actions, void* stream) {
+  CVB_REQUIRE(h != nullptr, "null handle");
+  return cvb::pi0_sample(h, image, lang_tokens, lang_len, state, noise, R, K, actions,
+                         (cudaStream_t)stream);
+}
+
+int64_t cvb_debug_copy(cvb_handle* h, const char* name, void* dst, int64_t max_bytes, void* stream) {
+  if (h == nullptr || name == nullptr) return -1;
+  return cvb::pi0_debug_copy(h, name, dst, max_bytes, (cudaStream_t)stream);
+}
+
+// ---- host-only constants of the denoise loop (modeling_pi0.py:697-714 and :71-89)
+int cvb_denoise_times_host(int num_steps, float* times_out, int max_out, float* dt_out) {
+  if (num_steps <= 0) return 0;
+  const float dt = static_cast<float>(-1.0 / num_steps);
+  float t = 1.0f;
+  int n = 0;
+  while (t >= -dt / 2) {
+    if (times_out != nullptr && n < max_out) times_out[n] = t;
+    ++n;
+    t = t + dt;
+    if (n > 100000) break;
+  }
+  if (dt_out != nullptr) *dt_out = dt;
+  return n;
+}
+
+static uint16_t f32_to_bf16_rne(float f) {
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  if ((x & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((x >> 16) | 0x40);
+  const uint32_t lsb = (x >> 16) & 1u;
+  x += 0x7fffu + lsb;
+  return static_cast<uint16_t>(x >> 16);
+}
+
+void cvb_time_embedding_host(float t, int dim, double min_period, double max_period,
+                             uint16_t* out_bf16) {
+  const int half = dim / 2;
+  const double step = half > 1 ? (1.0 - 0.0) / static_cast<double>(half - 1) : 0.0;
+  for (int i = 0; i < half; ++i) {
+    // torch.linspace(float64): start + step*i in the first half, end - step*(n-1-i) in the second
+    const double fraction = (i < half / 2) ? 0.0 + step * i : 1.0 - step * (half - 1 - i);
+    const double period = min_period * std::pow(max_period / min_period, fraction);
+    const double scaling = 1.0 / period * 2 * M_PI;
+    const double x = scaling * static_cast<double>(t);
+    out_bf16[i] = f32_to_bf16_rne(static_cast<float>(std::sin(x)));
+    out_bf16[half + i] = f32_to_bf16_rne(static_cast<float>(std::cos(x)));
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+// Engine internals shared by engine_pi0.cu / engine_verifier.cu / api_engine.cu.
+#pragma once
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/coverb200.h"
+#include "host_common.h"
+#include "ops.h"
+
+namespace cvb {
+
+struct Weight {
+  const void* ptr = nullptr;
+  int dtype = 0;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+struct WeightSpec {
+  std::string key;
+  int dtype;
+  std::vector<int64_t> shape;
+};
+
+struct VisLayer {
+  const bf16 *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+  bf16* wqkv;  // owned [3W, W]
+  bf16* bqkv;  // owned [3W]
+  const bf16 *wo, *bo, *w1, *b1, *w2, *b2;
+};
+struct GemmaLayer {
+  const bf16 *in_norm, *post_norm;
+  bf16* wqkv;  // owned [(H+2)*hd, D]
+  const bf16* wo;
+  bf16* wgu;  // owned packed [256*ceil(I/128), D]
+  const bf16* wd;
+};
+
+struct Pi0State {
+  // packed / derived weights
+  bf16* w_patch = nullptr;  // [Wv, kpad]
+  int kpad = 0;
+  std::vector<VisLayer> vis;
+  std::vector<GemmaLayer> lm, ex;
+  float* rope_timescale = nullptr;  // [hd/2]
+  float* time_vec = nullptr;        // [steps, We] = W_in[:, We:] . bf16(time_emb[s])
+  float* time_emb_f32 = nullptr;    // [steps, We] (bf16-rounded values)
+  std::vector<float> times;
+  float dt = 0.f;
+  // inputs (staged copies so the captured graph only touches internal memory)
+  float* in_image = nullptr;
+  int64_t* in_tokens = nullptr;
+  int* in_lang_len = nullptr;
+  float* in_state = nullptr;
+  float* x_t = nullptr;
+  int* plen = nullptr;
+  // workspace
+  bf16 *patches = nullptr, *hv = nullptr, *xv = nullptr, *qkv_v = nullptr, *attn_v = nullptr,
+       *mlp_v = nullptr, *proj_out = nullptr;
+  bf16 *hp = nullptr, *xp = nullptr, *qkv_p = nullptr, *attn_p = nullptr, *act_p = nullptr;
+  bf16 *kcache = nullptr, *vcache = nullptr;
+  float *state_emb = nullptr, *a1 = nullptr, *a2 = nullptr, *suffix = nullptr, *v0 = nullptr;
+  bf16 *he = nullptr, *xe = nullptr, *qkv_e = nullptr, *attn_e = nullptr, *act_e = nullptr;
+  std::unordered_map<long, cudaGraphExec_t> graphs;  // key = R * 65536 + K
+  std::unordered_map<long, int> warm;                // eager runs done per key
+};
+
+struct VerifierState;  // engine_verifier.cu
+
+}  // namespace cvb
+
+struct cvb_handle {
+  cvb_config cfg;
+  std::unordered_map<std::string, cvb::Weight> weights;
+  std::vector<cvb::WeightSpec> required;
+  std::vector<void*> owned;
+  bool finalized = false;
+  cvb::Pi0State pi0;
+  cvb::VerifierState* vf = nullptr;
+
+  int n_img() const { return (cfg.vis_image / cfg.vis_patch) * (cfg.vis_image / cfg.vis_patch); }
+  int prefix_len() const { return n_img() + cfg.max_lang_len; }
+  int suffix_len() const { return 1 + cfg.chunk_size; }
+};
+
+namespace cvb {
+
+std::string canonical_key(const std::string& k);
+int dalloc(cvb_handle* h, void** p, size_t bytes);
+template <typename T>
+int dalloc_t(cvb_handle* h, T** p, size_t count) {
+  return dalloc(h, reinterpret_cast<void**>(p), count * sizeof(T));
+}
+// fetch a bound weight, checking dtype and element count
+int get_weight(cvb_handle* h, const std::string& key, int dtype, int64_t numel, const void** out);
+
+void pi0_required_weights(const cvb_config& c, std::vector<WeightSpec>* out);
+int pi0_finalize(cvb_handle* h, cudaStream_t st);
+int pi0_sample(cvb_handle* h, const float* image, const int64_t* tokens, const int32_t* lang_len,
+               const float* state, const float* noise, int R, int K, float* actions, cudaStream_t st);
+int64_t pi0_debug_copy(cvb_handle* h, const std::string& name, void* dst, int64_t max_bytes,
+                       cudaStream_t st);
+
+void verifier_required_weights(const cvb_config& c, std::vector<WeightSpec>* out);
+int verifier_finalize(cvb_handle* h, cudaStream_t st);
+void verifier_destroy(cvb_handle* h);
+
+}  // namespace cvb

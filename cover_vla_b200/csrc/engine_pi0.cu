@@ -1,0 +1,533 @@
+// pi0 sampling pipeline: SigLIP tower (once per observation) -> PaliGemma prefix (once per unique
+// rephrase) -> 10-step action-expert denoise loop over all N = R*K candidates.  Host code only
+// sequences kernels on one stream; the whole sequence is captured into a CUDA graph per (R, K).
+//
+// Reference: PI0FlowMatching.sample_actions, modeling_pi0.py:672-715 and everything it calls
+// (embed_prefix :517-567, PaliGemmaWithExpertModel.forward paligemma_with_expert.py:236-360,
+// embed_suffix :569-629, denoise_step :717-752).  De-duplication per SURVEY.md F1/F2.
+#include <cmath>
+
+#include "engine.h"
+#include "gemm_tcgen05.cuh"
+#include "pi0_kernels.h"
+
+namespace cvb {
+
+namespace {
+
+const std::string PW = "paligemma_with_expert.";
+const std::string VT = PW + "paligemma.vision_tower.vision_model.";
+const std::string MM = PW + "paligemma.multi_modal_projector.linear.";
+const std::string LM = PW + "paligemma.language_model.model.";
+const std::string EX = PW + "gemma_expert.model.";
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+template <typename T>
+int W(cvb_handle* h, const std::string& key, int dtype, int64_t numel, const T** out) {
+  const void* p = nullptr;
+  CVB_TRY(get_weight(h, key, dtype, numel, &p));
+  *out = reinterpret_cast<const T*>(p);
+  return 0;
+}
+
+// concat row-major matrices along rows into an owned buffer
+int concat_rows(cvb_handle* h, cudaStream_t st, std::vector<std::pair<const bf16*, int64_t>> parts,
+                int64_t cols, bf16** out) {
+  int64_t rows = 0;
+  for (auto& p : parts) rows += p.second;
+  CVB_TRY(dalloc_t(h, out, rows * cols));
+  int64_t off = 0;
+  for (auto& p : parts) {
+    CVB_CUDA(cudaMemcpyAsync(*out + off * cols, p.first, p.second * cols * sizeof(bf16),
+                             cudaMemcpyDeviceToDevice, st));
+    off += p.second;
+  }
+  return 0;
+}
+
+// gate/up -> [128 gate rows | 128 up rows] per 128-feature block (zero padded)
+int pack_gate_up(cvb_handle* h, cudaStream_t st, const bf16* wg, const bf16* wu, int I, int D,
+                 bf16** out) {
+  const int blocks = (I + 127) / 128;
+  CVB_TRY(dalloc_t(h, out, static_cast<size_t>(blocks) * 256 * D));
+  CVB_CUDA(cudaMemsetAsync(*out, 0, static_cast<size_t>(blocks) * 256 * D * sizeof(bf16), st));
+  for (int b = 0; b < blocks; ++b) {
+    const int rows = std::min(128, I - b * 128);
+    CVB_CUDA(cudaMemcpyAsync(*out + (static_cast<size_t>(b) * 256) * D, wg + static_cast<size_t>(b) * 128 * D,
+                             static_cast<size_t>(rows) * D * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+    CVB_CUDA(cudaMemcpyAsync(*out + (static_cast<size_t>(b) * 256 + 128) * D,
+                             wu + static_cast<size_t>(b) * 128 * D,
+                             static_cast<size_t>(rows) * D * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+int gemm(cudaStream_t st, const bf16* A, long lda, const bf16* Wt, long ldw, int M, int N, int K,
+         int epi, void* C, long ldc, const void* bias = nullptr, const void* resid = nullptr,
+         long ldr = 0, int resid_f32 = 0, int n_out = 0) {
+  GemmCall c;
+  c.A = A, c.lda = lda, c.W = Wt, c.ldw = ldw, c.M = M, c.N = N, c.K = K, c.epi = epi;
+  c.C = C, c.ldc = ldc, c.bias = bias, c.bias_is_f32 = 0, c.resid = resid, c.ldr = ldr;
+  c.resid_is_f32 = resid_f32, c.n_out = n_out;
+  return gemm_bf16(st, c);
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------------------------------
+void pi0_required_weights(const cvb_config& c, std::vector<WeightSpec>* out) {
+  auto add = [&](const std::string& k, int dt, std::vector<int64_t> shape) {
+    out->push_back(WeightSpec{k, dt, std::move(shape)});
+  };
+  const int n_img = (c.vis_image / c.vis_patch) * (c.vis_image / c.vis_patch);
+  add(VT + "embeddings.patch_embedding.weight", CVB_BF16, {c.vis_width, 3, c.vis_patch, c.vis_patch});
+  add(VT + "embeddings.patch_embedding.bias", CVB_BF16, {c.vis_width});
+  add(VT + "embeddings.position_embedding.weight", CVB_BF16, {n_img, c.vis_width});
+  for (int l = 0; l < c.vis_layers; ++l) {
+    const std::string p = VT + "encoder.layers." + std::to_string(l) + ".";
+    for (const char* ln : {"layer_norm1", "layer_norm2"}) {
+      add(p + ln + ".weight", CVB_BF16, {c.vis_width});
+      add(p + ln + ".bias", CVB_BF16, {c.vis_width});
+    }
+    for (const char* nm : {"q_proj", "k_proj", "v_proj", "out_proj"}) {
+      add(p + "self_attn." + nm + ".weight", CVB_BF16, {c.vis_width, c.vis_width});
+      add(p + "self_attn." + nm + ".bias", CVB_BF16, {c.vis_width});
+    }
+    add(p + "mlp.fc1.weight", CVB_BF16, {c.vis_mlp, c.vis_width});
+    add(p + "mlp.fc1.bias", CVB_BF16, {c.vis_mlp});
+    add(p + "mlp.fc2.weight", CVB_BF16, {c.vis_width, c.vis_mlp});
+    add(p + "mlp.fc2.bias", CVB_BF16, {c.vis_width});
+  }
+  add(VT + "post_layernorm.weight", CVB_BF16, {c.vis_width});
+  add(VT + "post_layernorm.bias", CVB_BF16, {c.vis_width});
+  add(MM + "weight", CVB_BF16, {c.lm_width, c.vis_width});
+  add(MM + "bias", CVB_BF16, {c.lm_width});
+  add(LM + "embed_tokens.weight", CVB_BF16, {c.vocab, c.lm_width});
+  const int qd = c.heads * c.head_dim;
+  for (int t = 0; t < 2; ++t) {
+    const std::string& base = t == 0 ? LM : EX;
+    const int D = t == 0 ? c.lm_width : c.ex_width, I = t == 0 ? c.lm_mlp : c.ex_mlp;
+    for (int l = 0; l < c.layers; ++l) {
+      const std::string p = base + "layers." + std::to_string(l) + ".";
+      add(p + "self_attn.q_proj.weight", CVB_BF16, {qd, D});
+      add(p + "self_attn.k_proj.weight", CVB_BF16, {c.head_dim, D});
+      add(p + "self_attn.v_proj.weight", CVB_BF16, {c.head_dim, D});
+      add(p + "self_attn.o_proj.weight", CVB_BF16, {D, qd});
+      add(p + "mlp.gate_proj.weight", CVB_BF16, {I, D});
+      add(p + "mlp.up_proj.weight", CVB_BF16, {I, D});
+      add(p + "mlp.down_proj.weight", CVB_BF16, {D, I});
+      add(p + "input_layernorm.weight", CVB_BF16, {D});
+      add(p + "post_attention_layernorm.weight", CVB_BF16, {D});
+    }
+  }
+  add(EX + "norm.weight", CVB_F32, {c.ex_width});
+  add("state_proj.weight", CVB_F32, {c.ex_width, c.max_state_dim});
+  add("state_proj.bias", CVB_F32, {c.ex_width});
+  add("action_in_proj.weight", CVB_F32, {c.ex_width, c.max_action_dim});
+  add("action_in_proj.bias", CVB_F32, {c.ex_width});
+  add("action_out_proj.weight", CVB_F32, {c.max_action_dim, c.ex_width});
+  add("action_out_proj.bias", CVB_F32, {c.max_action_dim});
+  add("action_time_mlp_in.weight", CVB_F32, {c.ex_width, 2 * c.ex_width});
+  add("action_time_mlp_in.bias", CVB_F32, {c.ex_width});
+  add("action_time_mlp_out.weight", CVB_F32, {c.ex_width, c.ex_width});
+  add("action_time_mlp_out.bias", CVB_F32, {c.ex_width});
+}
+
+// --------------------------------------------------------------------------------------------------
+int pi0_finalize(cvb_handle* h, cudaStream_t st) {
+  const cvb_config& c = h->cfg;
+  Pi0State& s = h->pi0;
+  CVB_REQUIRE(c.vis_width % 8 == 0 && c.vis_mlp % 8 == 0 && c.lm_width % 8 == 0 && c.ex_width % 8 == 0 &&
+                  c.lm_mlp % 8 == 0 && c.ex_mlp % 8 == 0,
+              "layer widths must be multiples of 8");
+  CVB_REQUIRE(c.vis_width % c.vis_heads == 0 && (c.vis_width / c.vis_heads) % 8 == 0,
+              "vision head_dim must be a multiple of 8");
+  CVB_REQUIRE(c.head_dim % 16 == 0 && c.head_dim <= 256, "head_dim must be a multiple of 16, <= 256");
+  CVB_REQUIRE(c.vis_image % c.vis_patch == 0, "image size must be a multiple of the patch size");
+  const int T = h->n_img(), P = h->prefix_len(), S = h->suffix_len();
+  const int Wv = c.vis_width, D = c.lm_width, We = c.ex_width;
+  const int qd = c.heads * c.head_dim, qkvw = qd + 2 * c.head_dim;
+  const int Rm = c.max_rephrases, Nm = c.max_rephrases * c.max_samples;
+
+  // ---- patch embedding weight, K padded to a multiple of 8 (TMA rows are 16-byte multiples)
+  const int kreal = 3 * c.vis_patch * c.vis_patch;
+  s.kpad = round_up(kreal, 8);
+  const bf16* wp = nullptr;
+  CVB_TRY(W(h, VT + "embeddings.patch_embedding.weight", CVB_BF16, (int64_t)Wv * kreal, &wp));
+  CVB_TRY(dalloc_t(h, &s.w_patch, (size_t)Wv * s.kpad));
+  CVB_CUDA(cudaMemsetAsync(s.w_patch, 0, (size_t)Wv * s.kpad * sizeof(bf16), st));
+  CVB_CUDA(cudaMemcpy2DAsync(s.w_patch, s.kpad * sizeof(bf16), wp, kreal * sizeof(bf16),
+                             kreal * sizeof(bf16), Wv, cudaMemcpyDeviceToDevice, st));
+
+  // ---- vision layers
+  s.vis.resize(c.vis_layers);
+  for (int l = 0; l < c.vis_layers; ++l) {
+    const std::string p = VT + "encoder.layers." + std::to_string(l) + ".";
+    VisLayer& L = s.vis[l];
+    CVB_TRY(W(h, p + "layer_norm1.weight", CVB_BF16, Wv, &L.ln1_w));
+    CVB_TRY(W(h, p + "layer_norm1.bias", CVB_BF16, Wv, &L.ln1_b));
+    CVB_TRY(W(h, p + "layer_norm2.weight", CVB_BF16, Wv, &L.ln2_w));
+    CVB_TRY(W(h, p + "layer_norm2.bias", CVB_BF16, Wv, &L.ln2_b));
+    const bf16 *wq, *wk, *wv, *bq, *bk, *bv;
+    CVB_TRY(W(h, p + "self_attn.q_proj.weight", CVB_BF16, (int64_t)Wv * Wv, &wq));
+    CVB_TRY(W(h, p + "self_attn.k_proj.weight", CVB_BF16, (int64_t)Wv * Wv, &wk));
+    CVB_TRY(W(h, p + "self_attn.v_proj.weight", CVB_BF16, (int64_t)Wv * Wv, &wv));
+    CVB_TRY(W(h, p + "self_attn.q_proj.bias", CVB_BF16, Wv, &bq));
+    CVB_TRY(W(h, p + "self_attn.k_proj.bias", CVB_BF16, Wv, &bk));
+    CVB_TRY(W(h, p + "self_attn.v_proj.bias", CVB_BF16, Wv, &bv));
+    CVB_TRY(concat_rows(h, st, {{wq, Wv}, {wk, Wv}, {wv, Wv}}, Wv, &L.wqkv));
+    CVB_TRY(concat_rows(h, st, {{bq, 1}, {bk, 1}, {bv, 1}}, Wv, &L.bqkv));
+    CVB_TRY(W(h, p + "self_attn.out_proj.weight", CVB_BF16, (int64_t)Wv * Wv, &L.wo));
+    CVB_TRY(W(h, p + "self_attn.out_proj.bias", CVB_BF16, Wv, &L.bo));
+    CVB_TRY(W(h, p + "mlp.fc1.weight", CVB_BF16, (int64_t)c.vis_mlp * Wv, &L.w1));
+    CVB_TRY(W(h, p + "mlp.fc1.bias", CVB_BF16, c.vis_mlp, &L.b1));
+    CVB_TRY(W(h, p + "mlp.fc2.weight", CVB_BF16, (int64_t)c.vis_mlp * Wv, &L.w2));
+    CVB_TRY(W(h, p + "mlp.fc2.bias", CVB_BF16, Wv, &L.b2));
+  }
+
+  // ---- Gemma towers
+  for (int t = 0; t < 2; ++t) {
+    const std::string& base = t == 0 ? LM : EX;
+    const int Dt = t == 0 ? D : We, I = t == 0 ? c.lm_mlp : c.ex_mlp;
+    std::vector<GemmaLayer>& layers = t == 0 ? s.lm : s.ex;
+    layers.resize(c.layers);
+    for (int l = 0; l < c.layers; ++l) {
+      const std::string p = base + "layers." + std::to_string(l) + ".";
+      GemmaLayer& L = layers[l];
+      const bf16 *wq, *wk, *wv, *wg, *wu;
+      CVB_TRY(W(h, p + "self_attn.q_proj.weight", CVB_BF16, (int64_t)qd * Dt, &wq));
+      CVB_TRY(W(h, p + "self_attn.k_proj.weight", CVB_BF16, (int64_t)c.head_dim * Dt, &wk));
+      CVB_TRY(W(h, p + "self_attn.v_proj.weight", CVB_BF16, (int64_t)c.head_dim * Dt, &wv));
+      CVB_TRY(concat_rows(h, st, {{wq, qd}, {wk, c.head_dim}, {wv, c.head_dim}}, Dt, &L.wqkv));
+      CVB_TRY(W(h, p + "self_attn.o_proj.weight", CVB_BF16, (int64_t)qd * Dt, &L.wo));
+      CVB_TRY(W(h, p + "mlp.gate_proj.weight", CVB_BF16, (int64_t)I * Dt, &wg));
+      CVB_TRY(W(h, p + "mlp.up_proj.weight", CVB_BF16, (int64_t)I * Dt, &wu));
+      CVB_TRY(pack_gate_up(h, st, wg, wu, I, Dt, &L.wgu));
+      CVB_TRY(W(h, p + "mlp.down_proj.weight", CVB_BF16, (int64_t)I * Dt, &L.wd));
+      CVB_TRY(W(h, p + "input_layernorm.weight", CVB_BF16, Dt, &L.in_norm));
+      CVB_TRY(W(h, p + "post_attention_layernorm.weight", CVB_BF16, Dt, &L.post_norm));
+    }
+  }
+
+  // ---- constants: RoPE timescale (paligemma_with_expert.py:43-44), denoise times, time embeddings
+  {
+    const int half = c.head_dim / 2;
+    std::vector<float> ts(half);
+    const float coef = static_cast<float>(2.0 / c.head_dim);
+    for (int i = 0; i < half; ++i) ts[i] = powf(10000.0f, coef * static_cast<float>(i));
+    CVB_TRY(dalloc_t(h, &s.rope_timescale, half));
+    CVB_CUDA(cudaMemcpyAsync(s.rope_timescale, ts.data(), half * sizeof(float), cudaMemcpyHostToDevice, st));
+    CVB_CUDA(cudaStreamSynchronize(st));  // ts is a stack-lifetime host buffer
+  }
+  {
+    s.times.resize(256);
+    int n = cvb_denoise_times_host(c.num_steps, s.times.data(), 256, &s.dt);
+    CVB_REQUIRE(n > 0, "denoise time schedule is empty");
+    s.times.resize(n);
+    std::vector<float> temb((size_t)n * We);
+    std::vector<uint16_t> row(We);
+    for (int i = 0; i < n; ++i) {
+      cvb_time_embedding_host(s.times[i], We, 4e-3, 4.0, row.data());
+      for (int j = 0; j < We; ++j) {
+        uint32_t bits = static_cast<uint32_t>(row[j]) << 16;
+        float f;
+        memcpy(&f, &bits, 4);
+        temb[(size_t)i * We + j] = f;
+      }
+    }
+    CVB_TRY(dalloc_t(h, &s.time_emb_f32, (size_t)n * We));
+    CVB_TRY(dalloc_t(h, &s.time_vec, (size_t)n * We));
+    CVB_CUDA(cudaMemcpyAsync(s.time_emb_f32, temb.data(), temb.size() * sizeof(float),
+                             cudaMemcpyHostToDevice, st));
+    CVB_CUDA(cudaStreamSynchronize(st));
+    // time_vec[s] = W_in[:, We:2We] . time_emb[s]   (the time half of action_time_mlp_in, constant per step)
+    const float* w_in = nullptr;
+    CVB_TRY(W(h, "action_time_mlp_in.weight", CVB_F32, (int64_t)We * 2 * We, &w_in));
+    SgemmCall g;
+    g.A = s.time_emb_f32, g.lda = We, g.W = w_in + We, g.ldw = 2 * We, g.M = n, g.N = We, g.K = We;
+    g.C = s.time_vec, g.ldc = We;
+    CVB_TRY(sgemm_f32(st, g));
+  }
+
+  // ---- workspace
+  CVB_TRY(dalloc_t(h, &s.in_image, (size_t)3 * c.vis_image * c.vis_image));
+  CVB_TRY(dalloc_t(h, &s.in_tokens, (size_t)Rm * c.max_lang_len));
+  CVB_TRY(dalloc_t(h, &s.in_lang_len, Rm));
+  CVB_TRY(dalloc_t(h, &s.plen, Rm));
+  CVB_TRY(dalloc_t(h, &s.in_state, c.max_state_dim));
+  CVB_TRY(dalloc_t(h, &s.x_t, (size_t)Nm * c.chunk_size * c.max_action_dim));
+  CVB_TRY(dalloc_t(h, &s.v0, (size_t)Nm * c.chunk_size * c.max_action_dim));
+  CVB_TRY(dalloc_t(h, &s.patches, (size_t)T * s.kpad));
+  CVB_TRY(dalloc_t(h, &s.hv, (size_t)T * Wv));
+  CVB_TRY(dalloc_t(h, &s.xv, (size_t)T * Wv));
+  CVB_TRY(dalloc_t(h, &s.qkv_v, (size_t)T * 3 * Wv));
+  CVB_TRY(dalloc_t(h, &s.attn_v, (size_t)T * Wv));
+  CVB_TRY(dalloc_t(h, &s.mlp_v, (size_t)T * c.vis_mlp));
+  CVB_TRY(dalloc_t(h, &s.proj_out, (size_t)T * D));
+  const size_t Mp = (size_t)Rm * P;
+  CVB_TRY(dalloc_t(h, &s.hp, Mp * D));
+  CVB_TRY(dalloc_t(h, &s.xp, Mp * D));
+  CVB_TRY(dalloc_t(h, &s.qkv_p, Mp * qkvw));
+  CVB_TRY(dalloc_t(h, &s.attn_p, Mp * qd));
+  CVB_TRY(dalloc_t(h, &s.act_p, Mp * c.lm_mlp));
+  CVB_TRY(dalloc_t(h, &s.kcache, (size_t)c.layers * Mp * c.head_dim));
+  CVB_TRY(dalloc_t(h, &s.vcache, (size_t)c.layers * Mp * c.head_dim));
+  const size_t Me = (size_t)Nm * S, Ma = (size_t)Nm * c.chunk_size;
+  CVB_TRY(dalloc_t(h, &s.state_emb, We));
+  CVB_TRY(dalloc_t(h, &s.a1, Ma * We));
+  CVB_TRY(dalloc_t(h, &s.a2, Ma * We));
+  CVB_TRY(dalloc_t(h, &s.suffix, Me * We));
+  CVB_TRY(dalloc_t(h, &s.he, Me * We));
+  CVB_TRY(dalloc_t(h, &s.xe, Me * We));
+  CVB_TRY(dalloc_t(h, &s.qkv_e, Me * qkvw));
+  CVB_TRY(dalloc_t(h, &s.attn_e, Me * qd));
+  CVB_TRY(dalloc_t(h, &s.act_e, Me * c.ex_mlp));
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------
+static int run_vision(cvb_handle* h, cudaStream_t st) {
+  const cvb_config& c = h->cfg;
+  Pi0State& s = h->pi0;
+  const int T = h->n_img(), Wv = c.vis_width, hd = Wv / c.vis_heads, D = c.lm_width;
+  const bf16 *b_patch, *pos, *post_w, *post_b, *w_proj, *b_proj;
+  CVB_TRY(W(h, VT + "embeddings.patch_embedding.bias", CVB_BF16, Wv, &b_patch));
+  CVB_TRY(W(h, VT + "embeddings.position_embedding.weight", CVB_BF16, (int64_t)T * Wv, &pos));
+  CVB_TRY(W(h, VT + "post_layernorm.weight", CVB_BF16, Wv, &post_w));
+  CVB_TRY(W(h, VT + "post_layernorm.bias", CVB_BF16, Wv, &post_b));
+  CVB_TRY(W(h, MM + "weight", CVB_BF16, (int64_t)D * Wv, &w_proj));
+  CVB_TRY(W(h, MM + "bias", CVB_BF16, D, &b_proj));
+
+  CVB_TRY(im2col_patches(st, s.in_image, s.patches, 3, c.vis_image, c.vis_image, c.vis_patch, s.kpad));
+  // hv = bf16(bf16(conv + bias) + pos_emb)
+  CVB_TRY(gemm(st, s.patches, s.kpad, s.w_patch, s.kpad, T, Wv, s.kpad, EPI_RESID, s.hv, Wv, b_patch, pos, Wv));
+  for (int l = 0; l < c.vis_layers; ++l) {
+    const VisLayer& L = s.vis[l];
+    CVB_TRY(layernorm_bf16(st, s.hv, Wv, L.ln1_w, L.ln1_b, s.xv, Wv, T, Wv, 1e-6f));
+    CVB_TRY(gemm(st, s.xv, Wv, L.wqkv, Wv, T, 3 * Wv, Wv, EPI_STORE, s.qkv_v, 3 * Wv, L.bqkv));
+    AttnCall a;
+    a.q = s.qkv_v, a.q_batch_stride = 0, a.q_row_stride = 3 * Wv;
+    a.k0 = s.qkv_v + Wv, a.v0 = s.qkv_v + 2 * Wv, a.kv0_batch_stride = 0, a.kv0_row_stride = 3 * Wv;
+    a.kv0_len = T, a.q_per_kv_batch = 1;
+    a.out = s.attn_v, a.o_batch_stride = 0, a.o_row_stride = Wv;
+    a.batches = 1, a.heads = c.vis_heads, a.kv_heads = c.vis_heads, a.tq = T, a.head_dim = hd;
+    a.scale = 1.0f / sqrtf(static_cast<float>(hd));
+    CVB_TRY(attention(st, a));
+    CVB_TRY(gemm(st, s.attn_v, Wv, L.wo, Wv, T, Wv, Wv, EPI_RESID, s.hv, Wv, L.bo, s.hv, Wv));
+    CVB_TRY(layernorm_bf16(st, s.hv, Wv, L.ln2_w, L.ln2_b, s.xv, Wv, T, Wv, 1e-6f));
+    CVB_TRY(gemm(st, s.xv, Wv, L.w1, Wv, T, c.vis_mlp, Wv, EPI_GELU, s.mlp_v, c.vis_mlp, L.b1));
+    CVB_TRY(gemm(st, s.mlp_v, c.vis_mlp, L.w2, c.vis_mlp, T, Wv, c.vis_mlp, EPI_RESID, s.hv, Wv, L.b2, s.hv, Wv));
+  }
+  CVB_TRY(layernorm_bf16(st, s.hv, Wv, post_w, post_b, s.xv, Wv, T, Wv, 1e-6f));
+  CVB_TRY(gemm(st, s.xv, Wv, w_proj, Wv, T, D, Wv, EPI_STORE, s.proj_out, D, b_proj));
+  return 0;
+}
+
+static int run_prefix(cvb_handle* h, cudaStream_t st, int R) {
+  const cvb_config& c = h->cfg;
+  Pi0State& s = h->pi0;
+  const int T = h->n_img(), P = h->prefix_len(), D = c.lm_width, hd = c.head_dim;
+  const int qd = c.heads * hd, qkvw = qd + 2 * hd, M = R * P;
+  const bf16* embed;
+  CVB_TRY(W(h, LM + "embed_tokens.weight", CVB_BF16, (int64_t)c.vocab * D, &embed));
+  CVB_TRY(build_prefix(st, s.proj_out, embed, s.in_tokens, s.hp, R, T, c.max_lang_len, D));
+  CVB_TRY(prefix_lengths(st, s.in_lang_len, s.plen, R, T));
+  const long layer_stride = (long)c.max_rephrases * P * hd;
+  for (int l = 0; l < c.layers; ++l) {
+    const GemmaLayer& L = s.lm[l];
+    bf16* kc = s.kcache + l * layer_stride;
+    bf16* vc = s.vcache + l * layer_stride;
+    CVB_TRY(rmsnorm(st, s.hp, 0, D, L.in_norm, 0, s.xp, D, M, D, 1e-6f, nullptr));
+    CVB_TRY(gemm(st, s.xp, D, L.wqkv, D, M, qkvw, D, EPI_STORE, s.qkv_p, qkvw));
+    CVB_TRY(rope_qkv(st, s.qkv_p, qkvw, s.rope_timescale, M, c.heads, hd, P, nullptr, 1, kc, vc,
+                     (long)P * hd, hd));
+    if (l == c.layers - 1) break;  // only this layer's K/V are consumed (modeling_pi0.py:688-695)
+    AttnCall a;
+    a.q = s.qkv_p, a.q_batch_stride = (long)P * qkvw, a.q_row_stride = qkvw;
+    a.k0 = kc, a.v0 = vc, a.kv0_batch_stride = (long)P * hd, a.kv0_row_stride = hd;
+    a.kv0_len_dev = s.plen, a.q_per_kv_batch = 1;
+    a.out = s.attn_p, a.o_batch_stride = (long)P * qd, a.o_row_stride = qd;
+    a.batches = R, a.heads = c.heads, a.kv_heads = 1, a.tq = P, a.head_dim = hd;
+    a.scale = 1.0f / sqrtf(static_cast<float>(hd));
+    CVB_TRY(attention(st, a));
+    CVB_TRY(gemm(st, s.attn_p, qd, L.wo, qd, M, D, qd, EPI_RESID, s.hp, D, nullptr, s.hp, D));
+    CVB_TRY(rmsnorm(st, s.hp, 0, D, L.post_norm, 0, s.xp, D, M, D, 1e-6f, nullptr));
+    const int packed = ((c.lm_mlp + 127) / 128) * 256;
+    CVB_TRY(gemm(st, s.xp, D, L.wgu, D, M, packed, D, EPI_GEGLU, s.act_p, c.lm_mlp, nullptr, nullptr, 0, 0, c.lm_mlp));
+    CVB_TRY(gemm(st, s.act_p, c.lm_mlp, L.wd, c.lm_mlp, M, D, c.lm_mlp, EPI_RESID, s.hp, D, nullptr, s.hp, D));
+  }
+  return 0;
+}
+
+static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
+  const cvb_config& c = h->cfg;
+  Pi0State& s = h->pi0;
+  const int P = h->prefix_len(), S = h->suffix_len(), We = c.ex_width, hd = c.head_dim;
+  const int qd = c.heads * hd, qkvw = qd + 2 * hd, N = R * K, M = N * S, Ma = N * c.chunk_size;
+  const float *w_state, *b_state, *w_ain, *b_ain, *w_in, *b_in, *w_out, *b_out, *w_aout, *b_aout, *w_norm;
+  CVB_TRY(W(h, "state_proj.weight", CVB_F32, (int64_t)We * c.max_state_dim, &w_state));
+  CVB_TRY(W(h, "state_proj.bias", CVB_F32, We, &b_state));
+  CVB_TRY(W(h, "action_in_proj.weight", CVB_F32, (int64_t)We * c.max_action_dim, &w_ain));
+  CVB_TRY(W(h, "action_in_proj.bias", CVB_F32, We, &b_ain));
+  CVB_TRY(W(h, "action_time_mlp_in.weight", CVB_F32, (int64_t)We * 2 * We, &w_in));
+  CVB_TRY(W(h, "action_time_mlp_in.bias", CVB_F32, We, &b_in));
+  CVB_TRY(W(h, "action_time_mlp_out.weight", CVB_F32, (int64_t)We * We, &w_out));
+  CVB_TRY(W(h, "action_time_mlp_out.bias", CVB_F32, We, &b_out));
+  CVB_TRY(W(h, "action_out_proj.weight", CVB_F32, (int64_t)We * c.max_action_dim, &w_aout));
+  CVB_TRY(W(h, "action_out_proj.bias", CVB_F32, c.max_action_dim, &b_aout));
+  CVB_TRY(W(h, EX + "norm.weight", CVB_F32, We, &w_norm));
+
+  // state token (identical for every candidate and every step)
+  {
+    SgemmCall g;
+    g.A = s.in_state, g.lda = c.max_state_dim, g.W = w_state, g.ldw = c.max_state_dim;
+    g.M = 1, g.N = We, g.K = c.max_state_dim, g.C = s.state_emb, g.ldc = We, g.bias = b_state;
+    CVB_TRY(sgemm_f32(st, g));
+    CVB_TRY(fill_state_rows(st, s.state_emb, s.suffix, N, We, S));
+  }
+  const long layer_stride = (long)c.max_rephrases * P * hd;
+  const int packed = ((c.ex_mlp + 127) / 128) * 256;
+  for (size_t step = 0; step < s.times.size(); ++step) {
+    {  // embed_suffix (modeling_pi0.py:598-609), time half of mlp_in folded into time_vec[step]
+      SgemmCall g;
+      g.A = s.x_t, g.lda = c.max_action_dim, g.W = w_ain, g.ldw = c.max_action_dim;
+      g.M = Ma, g.N = We, g.K = c.max_action_dim, g.C = s.a1, g.ldc = We, g.bias = b_ain;
+      CVB_TRY(sgemm_f32(st, g));
+      SgemmCall g2;
+      g2.A = s.a1, g2.lda = We, g2.W = w_in, g2.ldw = 2 * We, g2.M = Ma, g2.N = We, g2.K = We;
+      g2.C = s.a2, g2.ldc = We, g2.bias = b_in, g2.row_bias = s.time_vec + step * We, g2.act = SACT_SILU;
+      CVB_TRY(sgemm_f32(st, g2));
+      SgemmCall g3;
+      g3.A = s.a2, g3.lda = We, g3.W = w_out, g3.ldw = We, g3.M = Ma, g3.N = We, g3.K = We;
+      g3.C = s.suffix, g3.ldc = We, g3.bias = b_out, g3.out_group = c.chunk_size;
+      CVB_TRY(sgemm_f32(st, g3));
+    }
+    for (int l = 0; l < c.layers; ++l) {
+      const GemmaLayer& L = s.ex[l];
+      const void* resid = l == 0 ? static_cast<const void*>(s.suffix) : static_cast<const void*>(s.he);
+      const int resid_f32 = l == 0 ? 1 : 0;
+      CVB_TRY(rmsnorm(st, resid, resid_f32, We, L.in_norm, 0, s.xe, We, M, We, 1e-6f, nullptr));
+      CVB_TRY(gemm(st, s.xe, We, L.wqkv, We, M, qkvw, We, EPI_STORE, s.qkv_e, qkvw));
+      CVB_TRY(rope_qkv(st, s.qkv_e, qkvw, s.rope_timescale, M, c.heads, hd, S, s.plen, K, nullptr,
+                       nullptr, 0, 0));
+      AttnCall a;
+      a.q = s.qkv_e, a.q_batch_stride = (long)S * qkvw, a.q_row_stride = qkvw;
+      a.k0 = s.kcache + l * layer_stride, a.v0 = s.vcache + l * layer_stride;
+      a.kv0_batch_stride = (long)P * hd, a.kv0_row_stride = hd, a.kv0_len_dev = s.plen;
+      a.q_per_kv_batch = K;
+      a.k1 = s.qkv_e + qd, a.v1 = s.qkv_e + qd + hd, a.kv1_batch_stride = (long)S * qkvw;
+      a.kv1_row_stride = qkvw, a.kv1_len = S, a.suffix_mask = 1;
+      a.out = s.attn_e, a.o_batch_stride = (long)S * qd, a.o_row_stride = qd;
+      a.batches = N, a.heads = c.heads, a.kv_heads = 1, a.tq = S, a.head_dim = hd;
+      a.scale = 1.0f / sqrtf(static_cast<float>(hd));
+      CVB_TRY(attention(st, a));
+      CVB_TRY(gemm(st, s.attn_e, qd, L.wo, qd, M, We, qd, EPI_RESID, s.he, We, nullptr, resid, We, resid_f32));
+      CVB_TRY(rmsnorm(st, s.he, 0, We, L.post_norm, 0, s.xe, We, M, We, 1e-6f, nullptr));
+      CVB_TRY(gemm(st, s.xe, We, L.wgu, We, M, packed, We, EPI_GEGLU, s.act_e, c.ex_mlp, nullptr, nullptr, 0, 0, c.ex_mlp));
+      CVB_TRY(gemm(st, s.act_e, c.ex_mlp, L.wd, c.ex_mlp, M, We, c.ex_mlp, EPI_RESID, s.he, We, nullptr, s.he, We));
+    }
+    CVB_TRY(rmsnorm(st, s.he, 0, We, w_norm, 1, s.xe, We, M, We, 1e-6f, nullptr));
+    CVB_TRY(action_out_euler(st, s.xe, We, w_aout, b_aout, s.x_t, step == 0 ? s.v0 : nullptr, N, We,
+                             c.max_action_dim, c.chunk_size, S, s.dt));
+  }
+  return 0;
+}
+
+static int run_all(cvb_handle* h, cudaStream_t st, int R, int K) {
+  CVB_TRY(run_vision(h, st));
+  CVB_TRY(run_prefix(h, st, R));
+  CVB_TRY(run_denoise(h, st, R, K));
+  return 0;
+}
+
+int pi0_sample(cvb_handle* h, const float* image, const int64_t* tokens, const int32_t* lang_len,
+               const float* state, const float* noise, int R, int K, float* actions, cudaStream_t st) {
+  const cvb_config& c = h->cfg;
+  Pi0State& s = h->pi0;
+  CVB_REQUIRE(h->finalized, "cvb_finalize() has not been called");
+  CVB_REQUIRE(R >= 1 && R <= c.max_rephrases, "R out of range (max_rephrases)");
+  CVB_REQUIRE(K >= 1 && K <= c.max_samples, "K out of range (max_samples)");
+  const int N = R * K;
+  const size_t act_bytes = (size_t)N * c.chunk_size * c.max_action_dim * sizeof(float);
+  CVB_CUDA(cudaMemcpyAsync(s.in_image, image, (size_t)3 * c.vis_image * c.vis_image * sizeof(float),
+                           cudaMemcpyDeviceToDevice, st));
+  CVB_CUDA(cudaMemcpyAsync(s.in_tokens, tokens, (size_t)R * c.max_lang_len * sizeof(int64_t),
+                           cudaMemcpyDeviceToDevice, st));
+  CVB_CUDA(cudaMemcpyAsync(s.in_lang_len, lang_len, R * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  CVB_CUDA(cudaMemcpyAsync(s.in_state, state, c.max_state_dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CVB_CUDA(cudaMemcpyAsync(s.x_t, noise, act_bytes, cudaMemcpyDeviceToDevice, st));
+
+  const long key = (long)R * 65536 + K;
+  if (!c.use_cuda_graph) {
+    CVB_TRY(run_all(h, st, R, K));
+  } else {
+    auto it = s.graphs.find(key);
+    if (it == s.graphs.end()) {
+      if (s.warm[key] == 0) {
+        // first call for this shape runs eagerly: sets kernel attributes, fills the tensor-map cache
+        s.warm[key] = 1;
+        CVB_TRY(run_all(h, st, R, K));
+      } else {
+        cudaGraph_t graph = nullptr;
+        CVB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = run_all(h, st, R, K);
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (rc != 0) {
+          if (graph) cudaGraphDestroy(graph);
+          return rc;
+        }
+        CVB_CUDA(e);
+        cudaGraphExec_t exec = nullptr;
+        CVB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        s.graphs[key] = exec;
+        CVB_CUDA(cudaGraphLaunch(exec, st));
+      }
+    } else {
+      CVB_CUDA(cudaGraphLaunch(it->second, st));
+    }
+  }
+  CVB_CUDA(cudaMemcpyAsync(actions, s.x_t, act_bytes, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int64_t pi0_debug_copy(cvb_handle* h, const std::string& name, void* dst, int64_t max_bytes,
+                       cudaStream_t st) {
+  const cvb_config& c = h->cfg;
+  Pi0State& s = h->pi0;
+  const int T = h->n_img(), P = h->prefix_len();
+  const void* src = nullptr;
+  int64_t bytes = 0;
+  const int64_t layer_bytes = (int64_t)c.max_rephrases * P * c.head_dim * sizeof(bf16);
+  if (name == "image_emb") {
+    src = s.proj_out, bytes = (int64_t)T * c.lm_width * sizeof(bf16);
+  } else if (name == "vision_hidden") {
+    src = s.xv, bytes = (int64_t)T * c.vis_width * sizeof(bf16);
+  } else if (name == "prefix_k0") {
+    src = s.kcache, bytes = layer_bytes;
+  } else if (name == "prefix_v0") {
+    src = s.vcache, bytes = layer_bytes;
+  } else if (name == "prefix_klast") {
+    src = s.kcache + (int64_t)(c.layers - 1) * (layer_bytes / sizeof(bf16)), bytes = layer_bytes;
+  } else if (name == "prefix_vlast") {
+    src = s.vcache + (int64_t)(c.layers - 1) * (layer_bytes / sizeof(bf16)), bytes = layer_bytes;
+  } else if (name == "v0") {
+    src = s.v0, bytes = (int64_t)c.max_rephrases * c.max_samples * c.chunk_size * c.max_action_dim * sizeof(float);
+  } else if (name == "time_emb") {
+    src = s.time_emb_f32, bytes = (int64_t)s.times.size() * c.ex_width * sizeof(float);
+  } else if (name == "suffix") {
+    src = s.suffix, bytes = (int64_t)c.max_rephrases * c.max_samples * h->suffix_len() * c.ex_width * sizeof(float);
+  } else {
+    set_last_error("unknown debug buffer: " + name);
+    return -1;
+  }
+  if (bytes > max_bytes) bytes = max_bytes;
+  if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+    set_last_error("debug copy failed");
+    return -2;
+  }
+  return bytes;
+}
+
+}  // namespace cvb

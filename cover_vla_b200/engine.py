@@ -1,0 +1,194 @@
+"""Python handle on the engine-level C ABI (cvb_create / cvb_bind_weight / cvb_finalize / cvb_pi0_sample /
+cvb_verifier_score ...).  PyTorch is used for device memory and streams only."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, fields
+
+import torch
+
+from . import _lib
+
+_CFG_FIELDS = [
+    "struct_size",
+    "vis_layers", "vis_width", "vis_heads", "vis_mlp", "vis_patch", "vis_image",
+    "layers", "lm_width", "lm_mlp", "heads", "head_dim", "ex_width", "ex_mlp", "vocab",
+    "max_state_dim", "max_action_dim", "chunk_size", "max_lang_len", "num_steps",
+    "max_rephrases", "max_samples",
+    "vf_image", "vf_patch", "vf_width", "vf_layers", "vf_heads", "vf_mlp",
+    "vf_text_layers", "vf_text_ctx", "vf_vocab",
+    "vf_members", "vf_embed", "vf_pool_heads", "vf_pool_layers", "vf_traj_layers", "vf_traj_ff",
+    "vf_history", "vf_action_dim",
+    "use_cuda_graph",
+]
+
+
+class CvbConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in _CFG_FIELDS]
+
+
+@dataclass
+class EngineConfig:
+    """Mirror of cvb_config (include/coverb200.h).  Defaults = the Bridge pi0 checkpoint
+    (INT-ACT/config/models/pi0_finetune_bridge.json) and the CoVer-BridgeV2 verifier."""
+    vis_layers: int = 27
+    vis_width: int = 1152
+    vis_heads: int = 16
+    vis_mlp: int = 4304
+    vis_patch: int = 14
+    vis_image: int = 224
+    layers: int = 18
+    lm_width: int = 2048
+    lm_mlp: int = 16384
+    heads: int = 8
+    head_dim: int = 256
+    ex_width: int = 1024
+    ex_mlp: int = 4096
+    vocab: int = 257152
+    max_state_dim: int = 32
+    max_action_dim: int = 32
+    chunk_size: int = 4
+    max_lang_len: int = 72
+    num_steps: int = 10
+    max_rephrases: int = 8
+    max_samples: int = 5
+    vf_image: int = 384
+    vf_patch: int = 16
+    vf_width: int = 1024
+    vf_layers: int = 24
+    vf_heads: int = 16
+    vf_mlp: int = 4096
+    vf_text_layers: int = 24
+    vf_text_ctx: int = 64
+    vf_vocab: int = 256000
+    vf_members: int = 0
+    vf_embed: int = 512
+    vf_pool_heads: int = 8
+    vf_pool_layers: int = 4
+    vf_traj_layers: int = 4
+    vf_traj_ff: int = 1024
+    vf_history: int = 10
+    vf_action_dim: int = 7
+    use_cuda_graph: int = 1
+
+    def to_c(self) -> CvbConfig:
+        c = CvbConfig()
+        c.struct_size = C.sizeof(CvbConfig)
+        for f in fields(self):
+            setattr(c, f.name, int(getattr(self, f.name)))
+        return c
+
+    @property
+    def n_img_tokens(self) -> int:
+        return (self.vis_image // self.vis_patch) ** 2
+
+
+_DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.int64: 2, torch.int32: 3, torch.uint8: 4}
+
+
+class Engine:
+    """Owns one cvb_handle on the current CUDA device."""
+
+    def __init__(self, cfg: EngineConfig, device: str | torch.device = "cuda"):
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.CvbError("coverb200 has no CPU path: the engine needs a CUDA device")
+        self._declare()
+        self._h = C.c_void_p()
+        ccfg = cfg.to_c()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cvb_create(C.byref(ccfg), C.byref(self._h)))
+        self._keep = {}  # tensors whose memory the handle borrows
+        self.finalized = False
+
+    def _declare(self):
+        L = self.lib
+        L.cvb_create.argtypes = [C.POINTER(CvbConfig), C.POINTER(C.c_void_p)]
+        L.cvb_destroy.argtypes = [C.c_void_p]
+        L.cvb_destroy.restype = None
+        L.cvb_bind_weight.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+        L.cvb_required_weight_count.argtypes = [C.c_void_p]
+        L.cvb_required_weight_name.argtypes = [C.c_void_p, C.c_int]
+        L.cvb_required_weight_name.restype = C.c_char_p
+        L.cvb_finalize.argtypes = [C.c_void_p, C.c_void_p]
+        L.cvb_pi0_sample.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.cvb_debug_copy.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.cvb_debug_copy.restype = C.c_int64
+
+    # ------------------------------------------------------------------ weights
+    def required_weights(self) -> list[str]:
+        n = self.lib.cvb_required_weight_count(self._h)
+        return [self.lib.cvb_required_weight_name(self._h, i).decode() for i in range(n)]
+
+    def bind(self, key: str, t: torch.Tensor):
+        if t.device != self.device and not (t.is_cuda and self.device.index is None):
+            t = t.to(self.device)
+        t = t.contiguous()
+        if t.dtype not in _DTYPES:
+            raise _lib.CvbError(f"unsupported dtype for {key}: {t.dtype}")
+        shape = (C.c_int64 * max(1, t.dim()))(*t.shape)
+        _lib.check(self.lib.cvb_bind_weight(self._h, key.encode(), _lib.ptr(t), _DTYPES[t.dtype], t.dim(), shape))
+        self._keep[key] = t
+
+    def load_state_dict(self, sd: dict, strict_unused: bool = False):
+        """Bind every tensor of a reference state dict (names unchanged)."""
+        for k, v in sd.items():
+            if isinstance(v, torch.Tensor):
+                self.bind(k, v)
+
+    def finalize(self, release_repacked: bool = True):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cvb_finalize(self._h, _lib.stream_ptr()))
+            torch.cuda.synchronize()
+        self.finalized = True
+        if release_repacked:
+            # q/k/v, gate/up and the patch embedding were repacked into library-owned memory
+            for k in list(self._keep):
+                if any(s in k for s in ("q_proj.weight", "k_proj.weight", "v_proj.weight", "gate_proj.weight",
+                                        "up_proj.weight", "patch_embedding.weight")) and "verifier." not in k:
+                    del self._keep[k]
+                elif ("q_proj.bias" in k or "k_proj.bias" in k or "v_proj.bias" in k) and "verifier." not in k:
+                    del self._keep[k]
+
+    # ------------------------------------------------------------------ pi0
+    def pi0_sample(self, image, lang_tokens, lang_len, state, noise, K: int, out=None):
+        """image f32 [3,H,W]; lang_tokens i64 [R,L]; lang_len i32 [R]; state f32 [max_state_dim];
+        noise f32 [R*K, chunk, max_action_dim] -> actions f32 (same shape).  Asynchronous."""
+        cfg = self.cfg
+        R = lang_tokens.shape[0]
+        assert image.dtype == torch.float32 and image.numel() == 3 * cfg.vis_image ** 2
+        assert lang_tokens.dtype == torch.int64 and lang_tokens.shape[1] == cfg.max_lang_len
+        assert lang_len.dtype == torch.int32 and lang_len.numel() == R
+        assert state.dtype == torch.float32 and state.numel() == cfg.max_state_dim
+        assert noise.dtype == torch.float32 and tuple(noise.shape) == (R * K, cfg.chunk_size, cfg.max_action_dim)
+        for t in (image, lang_tokens, lang_len, state, noise):
+            assert t.is_cuda and t.is_contiguous()
+        if out is None:
+            out = torch.empty_like(noise)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cvb_pi0_sample(self._h, _lib.ptr(image), _lib.ptr(lang_tokens), _lib.ptr(lang_len),
+                                               _lib.ptr(state), _lib.ptr(noise), R, K, _lib.ptr(out),
+                                               _lib.stream_ptr()))
+        return out
+
+    def debug(self, name: str, shape, dtype) -> torch.Tensor:
+        out = torch.zeros(shape, dtype=dtype, device=self.device)
+        n = self.lib.cvb_debug_copy(self._h, name.encode(), _lib.ptr(out), out.numel() * out.element_size(),
+                                    _lib.stream_ptr())
+        if n < 0:
+            _lib.check(int(n))
+        torch.cuda.synchronize()
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.cvb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

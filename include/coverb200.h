@@ -44,6 +44,71 @@ CVB_API int cvb_op_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
                      const void* resid, int resid_is_f32, int64_t ldr, int n_out,
                      const int32_t* m_dev, int force_bn, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Engine level.  One handle per (device, stream); a handle is not thread-safe, the library is
+ * re-entrant across handles.  All sizes are configuration, nothing is hard-coded to the Bridge
+ * checkpoint (chunk_size 4, 72 language tokens, 10 steps) - see SURVEY.md section 8.
+ */
+typedef struct cvb_config {
+  int32_t struct_size; /* = sizeof(cvb_config), ABI guard */
+  /* pi0: SigLIP tower (paligemma_with_expert.py:103-115) */
+  int32_t vis_layers, vis_width, vis_heads, vis_mlp, vis_patch, vis_image;
+  /* pi0: PaliGemma LM + action expert (paligemma_with_expert.py:91-102,127-150) */
+  int32_t layers, lm_width, lm_mlp, heads, head_dim, ex_width, ex_mlp, vocab;
+  /* pi0: PI0Config (configuration_pi0.py:27-80) */
+  int32_t max_state_dim, max_action_dim, chunk_size, max_lang_len, num_steps;
+  /* workspace sizing: calls may use any R <= max_rephrases, K <= max_samples */
+  int32_t max_rephrases, max_samples;
+  /* verifier trunk (SigLIP2 ViT-L/16-384 + text tower) and heads; vf_members == 0 disables it */
+  int32_t vf_image, vf_patch, vf_width, vf_layers, vf_heads, vf_mlp;
+  int32_t vf_text_layers, vf_text_ctx, vf_vocab;
+  int32_t vf_members, vf_embed, vf_pool_heads, vf_pool_layers, vf_traj_layers, vf_traj_ff;
+  int32_t vf_history, vf_action_dim;
+  int32_t use_cuda_graph; /* capture the per-(R,K) launch sequence once and replay it */
+} cvb_config;
+
+typedef struct cvb_handle cvb_handle;
+
+enum { CVB_F32 = 0, CVB_BF16 = 1, CVB_I64 = 2, CVB_I32 = 3, CVB_U8 = 4 };
+
+CVB_API int cvb_create(const cvb_config* cfg, cvb_handle** out);
+CVB_API void cvb_destroy(cvb_handle* h);
+
+/* Borrow a weight: `key` is the reference state-dict name (PI0Policy.state_dict() with or without the
+ * leading "model.", transformers 4.48.3 or >=4.52 module layout - SURVEY.md Appendix C; verifier
+ * tensors as "verifier.<member>.<component>.<name>" and trunk tensors as "verifier.trunk.<name>").
+ * The pointer must stay valid until cvb_finalize() for tensors that get repacked (q/k/v, gate/up,
+ * patch embedding) and until cvb_destroy() for all others. */
+CVB_API int cvb_bind_weight(cvb_handle* h, const char* key, const void* dev_ptr, int dtype, int ndim,
+                            const int64_t* shape);
+/* Number of weights the configuration requires; names retrievable one by one (for loaders / tests). */
+CVB_API int cvb_required_weight_count(cvb_handle* h);
+CVB_API const char* cvb_required_weight_name(cvb_handle* h, int index);
+/* Validate that every required weight is bound, repack, allocate the workspace. */
+CVB_API int cvb_finalize(cvb_handle* h, void* stream);
+
+/* Sample N = R*K action chunks for ONE observation (replaces PI0FlowMatching.sample_actions,
+ * modeling_pi0.py:672-715, for the batch run_simpler_eval_with_openpi.py:305-319 builds).
+ *   image      f32 [3, vis_image, vis_image] in [-1, 1]      (identical for all candidates)
+ *   lang_tokens i64 [R, max_lang_len], lang_len i32 [R]       (right-padded; valid prefix length)
+ *   state      f32 [max_state_dim]
+ *   noise      f32 [R*K, chunk_size, max_action_dim]          (rephrase-major, as the reference batches)
+ *   actions    f32 [R*K, chunk_size, max_action_dim]          (output x_0)
+ */
+CVB_API int cvb_pi0_sample(cvb_handle* h, const float* image, const int64_t* lang_tokens,
+                           const int32_t* lang_len, const float* state, const float* noise, int R,
+                           int K, float* actions, void* stream);
+
+/* Test/diagnostic tap: copy an internal buffer ("image_emb", "prefix_k0", "prefix_vlast", "v0",
+ * "time_emb", ...) to dst (device).  Returns the number of bytes copied or a negative error. */
+CVB_API int64_t cvb_debug_copy(cvb_handle* h, const char* name, void* dst, int64_t max_bytes,
+                               void* stream);
+
+/* Host-only helpers (no CUDA calls): the constants of the denoise loop, for tests and hosts. */
+CVB_API int cvb_denoise_times_host(int num_steps, float* times_out, int max_out, float* dt_out);
+CVB_API void cvb_time_embedding_host(float t, int dim, double min_period, double max_period,
+                                     uint16_t* out_bf16);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,452 @@
+"""TEST INFRASTRUCTURE (oracle) - CPU restatement of the reference pi0 sampling path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import
+this module; the product (cover_vla_b200/) never does and has no CPU fallback.
+
+Restates, op for op and with the same dtype/rounding ledger:
+  PI0FlowMatching.sample_actions      lerobot_custom/lerobot/common/policies/pi0/modeling_pi0.py:672-715
+  PI0FlowMatching.embed_prefix        modeling_pi0.py:517-567
+  PI0FlowMatching.embed_suffix        modeling_pi0.py:569-629
+  PI0FlowMatching.denoise_step        modeling_pi0.py:717-752
+  create_sinusoidal_pos_embedding     modeling_pi0.py:71-89
+  make_att_2d_masks                   modeling_pi0.py:98-128
+  PaliGemmaWithExpertModel.forward    pi0/paligemma_with_expert.py:236-360
+  apply_rope / eager_attention        paligemma_with_expert.py:34-57, :376-434
+Third-party arithmetic the reference reaches (not vendored under /root/reference; pinned
+transformers==4.48.3, CoVer_VLA/scripts/env_simpler_pi.sh:83) is restated from its published
+definition: GemmaRMSNorm ((1+w), fp32 statistics), GemmaMLP (down(gelu_tanh(gate)*up)),
+SiglipVisionModel (pre-LN blocks, learned position embedding, gelu_tanh MLP, SDPA attention, post
+layernorm, no head), PaliGemmaMultiModalProjector + get_image_features (/sqrt(hidden)).
+
+PINNING: the reference ships no golden vectors or tests for this path.  The
+oracle is pinned against outputs of the reference's own files executed in the authoring container
+through oracle/ref_shim.py: tests/golden/pi0_*.pt (made by oracle/make_golden.py) and, when
+/root/reference is present, live in tests/test_oracle_vs_reference.py.
+"""
+from __future__ import annotations
+
+import hashlib
+import math
+from dataclasses import asdict, dataclass
+
+import torch
+import torch.nn.functional as F
+
+
+@dataclass
+class PI0Dims:
+    vis_layers: int = 27
+    vis_width: int = 1152
+    vis_heads: int = 16
+    vis_mlp: int = 4304
+    vis_patch: int = 14
+    vis_image: int = 224
+    layers: int = 18
+    lm_width: int = 2048
+    lm_mlp: int = 16384
+    heads: int = 8
+    head_dim: int = 256
+    ex_width: int = 1024
+    ex_mlp: int = 4096
+    vocab: int = 257152
+    max_state_dim: int = 32
+    max_action_dim: int = 32
+    chunk_size: int = 4
+    max_lang_len: int = 72
+    num_steps: int = 10
+
+    @property
+    def n_img_tokens(self) -> int:
+        return (self.vis_image // self.vis_patch) ** 2
+
+    def as_dict(self):
+        return asdict(self)
+
+
+FULL = PI0Dims()
+TINY = PI0Dims(vis_layers=2, vis_width=128, vis_heads=2, vis_mlp=256, vis_patch=14, vis_image=56,
+               layers=3, lm_width=128, lm_mlp=512, heads=2, head_dim=64, ex_width=64, ex_mlp=256,
+               vocab=1000, max_lang_len=16)
+# mid-size: every awkward property of the full model (head_dim 72 in the tower, K tails, 256-d heads)
+# at a size the CPU oracle finishes in seconds
+MID = PI0Dims(vis_layers=3, vis_width=288, vis_heads=4, vis_mlp=1072, vis_patch=14, vis_image=224,
+              layers=4, lm_width=512, lm_mlp=2048, heads=8, head_dim=256, ex_width=256, ex_mlp=1024,
+              vocab=4096, max_lang_len=72)
+
+PW = "paligemma_with_expert."
+VT = PW + "paligemma.vision_tower.vision_model."
+MM = PW + "paligemma.multi_modal_projector.linear."
+LM = PW + "paligemma.language_model.model."
+EX = PW + "gemma_expert.model."
+
+
+# ------------------------------------------------------------------------------------------------
+# deterministic synthetic weights (canonical = transformers-4.48.3 key names, no "model." prefix)
+# ------------------------------------------------------------------------------------------------
+def _gen(name: str, seed: int, shape, std: float, dtype, mean: float = 0.0):
+    h = int.from_bytes(hashlib.sha256(f"{seed}:{name}".encode()).digest()[:8], "little") % (2 ** 62)
+    g = torch.Generator(device="cpu").manual_seed(h)
+    n = 1
+    for s in shape:
+        n *= s
+    if n > (1 << 26):  # huge tables (token embedding): tile a 4M-element random block
+        blk = torch.empty(1 << 22, dtype=torch.float32).normal_(0.0, std, generator=g)
+        t = blk.repeat((n + blk.numel() - 1) // blk.numel())[:n].reshape(shape)
+    else:
+        t = torch.empty(shape, dtype=torch.float32).normal_(0.0, std, generator=g)
+    if mean != 0.0:
+        t = t + mean
+    return t.to(dtype)
+
+
+def weight_specs(d: PI0Dims):
+    """(key, shape, std, mean, dtype) for every tensor the sampling path reads."""
+    bf, f32 = torch.bfloat16, torch.float32
+    out = []
+
+    def lin(key, o, i, dtype=bf, bias=False):
+        out.append((key + ".weight", (o, i), 1.0 / math.sqrt(i), 0.0, dtype))
+        if bias:
+            out.append((key + ".bias", (o,), 0.05, 0.0, dtype))
+
+    out.append((VT + "embeddings.patch_embedding.weight", (d.vis_width, 3, d.vis_patch, d.vis_patch),
+                1.0 / math.sqrt(3 * d.vis_patch ** 2), 0.0, bf))
+    out.append((VT + "embeddings.patch_embedding.bias", (d.vis_width,), 0.05, 0.0, bf))
+    out.append((VT + "embeddings.position_embedding.weight", (d.n_img_tokens, d.vis_width), 0.5, 0.0, bf))
+    for l in range(d.vis_layers):
+        p = VT + f"encoder.layers.{l}."
+        for ln in ("layer_norm1", "layer_norm2"):
+            out.append((p + ln + ".weight", (d.vis_width,), 0.1, 1.0, bf))
+            out.append((p + ln + ".bias", (d.vis_width,), 0.1, 0.0, bf))
+        for nm in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            lin(p + "self_attn." + nm, d.vis_width, d.vis_width, bias=True)
+        lin(p + "mlp.fc1", d.vis_mlp, d.vis_width, bias=True)
+        lin(p + "mlp.fc2", d.vis_width, d.vis_mlp, bias=True)
+    out.append((VT + "post_layernorm.weight", (d.vis_width,), 0.1, 1.0, bf))
+    out.append((VT + "post_layernorm.bias", (d.vis_width,), 0.1, 0.0, bf))
+    lin(MM[:-1], d.lm_width, d.vis_width, bias=True)
+    out.append((LM + "embed_tokens.weight", (d.vocab, d.lm_width), 1.0 / math.sqrt(d.lm_width), 0.0, bf))
+    qd = d.heads * d.head_dim
+    for l in range(d.layers):
+        p = LM + f"layers.{l}."
+        lin(p + "self_attn.q_proj", qd, d.lm_width)
+        lin(p + "self_attn.k_proj", d.head_dim, d.lm_width)
+        lin(p + "self_attn.v_proj", d.head_dim, d.lm_width)
+        lin(p + "self_attn.o_proj", d.lm_width, qd)
+        lin(p + "mlp.gate_proj", d.lm_mlp, d.lm_width)
+        lin(p + "mlp.up_proj", d.lm_mlp, d.lm_width)
+        lin(p + "mlp.down_proj", d.lm_width, d.lm_mlp)
+        out.append((p + "input_layernorm.weight", (d.lm_width,), 0.1, 0.0, bf))
+        out.append((p + "post_attention_layernorm.weight", (d.lm_width,), 0.1, 0.0, bf))
+        p = EX + f"layers.{l}."
+        lin(p + "self_attn.q_proj", qd, d.ex_width)
+        lin(p + "self_attn.k_proj", d.head_dim, d.ex_width)
+        lin(p + "self_attn.v_proj", d.head_dim, d.ex_width)
+        lin(p + "self_attn.o_proj", d.ex_width, qd)
+        lin(p + "mlp.gate_proj", d.ex_mlp, d.ex_width)
+        lin(p + "mlp.up_proj", d.ex_mlp, d.ex_width)
+        lin(p + "mlp.down_proj", d.ex_width, d.ex_mlp)
+        out.append((p + "input_layernorm.weight", (d.ex_width,), 0.1, 0.0, bf))
+        out.append((p + "post_attention_layernorm.weight", (d.ex_width,), 0.1, 0.0, bf))
+    out.append((EX + "norm.weight", (d.ex_width,), 0.1, 0.0, f32))
+    lin("state_proj", d.ex_width, d.max_state_dim, f32, bias=True)
+    lin("action_in_proj", d.ex_width, d.max_action_dim, f32, bias=True)
+    lin("action_out_proj", d.max_action_dim, d.ex_width, f32, bias=True)
+    lin("action_time_mlp_in", d.ex_width, 2 * d.ex_width, f32, bias=True)
+    lin("action_time_mlp_out", d.ex_width, d.ex_width, f32, bias=True)
+    return out
+
+
+def make_pi0_weights(d: PI0Dims, seed: int = 0) -> dict:
+    return {k: _gen(k, seed, shape, std, dtype, mean) for k, shape, std, mean, dtype in weight_specs(d)}
+
+
+def to_hf5_key(k: str) -> str:
+    """canonical (4.48.3) -> transformers>=4.52 module layout (what the shim-built reference uses)."""
+    k = k.replace("paligemma.vision_tower.", "paligemma.model.vision_tower.")
+    k = k.replace("paligemma.multi_modal_projector.", "paligemma.model.multi_modal_projector.")
+    k = k.replace("paligemma.language_model.model.", "paligemma.model.language_model.")
+    return k
+
+
+def canonical_key(k: str) -> str:
+    """accept 'model.'-prefixed PI0Policy keys and either transformers layout."""
+    if k.startswith("model."):
+        k = k[len("model."):]
+    k = k.replace("paligemma.model.vision_tower.", "paligemma.vision_tower.")
+    k = k.replace("paligemma.model.multi_modal_projector.", "paligemma.multi_modal_projector.")
+    k = k.replace("paligemma.model.language_model.", "paligemma.language_model.model.")
+    return k
+
+
+# ------------------------------------------------------------------------------------------------
+# building blocks
+# ------------------------------------------------------------------------------------------------
+def gemma_rmsnorm(x, w, eps=1e-6):
+    # transformers GemmaRMSNorm: _norm(x.float()) * (1 + w.float()), cast back to x.dtype
+    xf = x.float()
+    out = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+    out = out * (1.0 + w.float())
+    return out.type_as(x)
+
+
+def gemma_mlp(x, wg, wu, wd):
+    return F.linear(F.gelu(F.linear(x, wg), approximate="tanh") * F.linear(x, wu), wd)
+
+
+def apply_rope(x, positions, max_wavelength=10_000):
+    # paligemma_with_expert.py:34-57
+    d_half = x.shape[-1] // 2
+    dtype = x.dtype
+    x = x.to(torch.float32)
+    freq_exponents = (2.0 / x.shape[-1]) * torch.arange(d_half, dtype=torch.float32)
+    timescale = max_wavelength ** freq_exponents
+    radians = positions[..., None].to(torch.float32) / timescale[None, None, :].to(torch.float32)
+    radians = radians[..., None, :]
+    sin, cos = torch.sin(radians), torch.cos(radians)
+    x1, x2 = x.split(d_half, dim=-1)
+    res = torch.empty_like(x)
+    res[..., :d_half] = x1 * cos - x2 * sin
+    res[..., d_half:] = x2 * cos + x1 * sin
+    return res.to(dtype)
+
+
+def eager_attention(mask, q, k, v, heads, head_dim):
+    # paligemma_with_expert.py:376-434 ; q [B,Lq,H,D] bf16, k/v [B,Lk,1,D] bf16, mask [B,Lq,Lk] bool
+    B, Lk = k.shape[0], k.shape[1]
+    k = k[:, :, :, None, :].expand(B, Lk, 1, heads, head_dim).reshape(B, Lk, heads, head_dim)
+    v = v[:, :, :, None, :].expand(B, Lk, 1, heads, head_dim).reshape(B, Lk, heads, head_dim)
+    qf = q.to(torch.float32).transpose(1, 2)
+    kf = k.to(torch.float32).transpose(1, 2)
+    att = torch.matmul(qf, kf.transpose(2, 3))
+    att *= head_dim ** -0.5
+    big_neg = -2.3819763e38
+    att = torch.where(mask[:, None, :, :], att, big_neg)
+    probs = F.softmax(att, dim=-1).to(dtype=v.dtype)
+    out = torch.matmul(probs, v.permute(0, 2, 1, 3))
+    out = out.permute(0, 2, 1, 3)
+    return out.reshape(B, -1, heads * head_dim)
+
+
+def make_att_2d_masks(pad_masks, att_masks):
+    cumsum = torch.cumsum(att_masks, dim=1)
+    att_2d = cumsum[:, None, :] <= cumsum[:, :, None]
+    pad_2d = pad_masks[:, None, :] * pad_masks[:, :, None]
+    return att_2d & pad_2d
+
+
+def sinusoidal_time_embedding(time, dimension, min_period=4e-3, max_period=4.0):
+    # modeling_pi0.py:71-89 (float64 math)
+    fraction = torch.linspace(0.0, 1.0, dimension // 2, dtype=torch.float64)
+    period = min_period * (max_period / min_period) ** fraction
+    scaling = 1.0 / period * 2 * math.pi
+    sin_input = scaling[None, :] * time[:, None]
+    return torch.cat([torch.sin(sin_input), torch.cos(sin_input)], dim=1)
+
+
+def denoise_times(num_steps: int):
+    """The fp32 time values the reference loop visits (modeling_pi0.py:697-714)."""
+    dt = torch.tensor(-1.0 / num_steps, dtype=torch.float32)
+    time = torch.tensor(1.0, dtype=torch.float32)
+    out = []
+    while time >= -dt / 2:
+        out.append(float(time))
+        time = time + dt
+    return out, float(dt)
+
+
+# ------------------------------------------------------------------------------------------------
+# SigLIP tower + projector  (transformers SiglipVisionModel, PaliGemma get_image_features @4.48.3)
+# ------------------------------------------------------------------------------------------------
+def siglip_tower(w, d: PI0Dims, pixel_values):
+    x = pixel_values.to(torch.bfloat16)
+    pe = F.conv2d(x, w[VT + "embeddings.patch_embedding.weight"], w[VT + "embeddings.patch_embedding.bias"],
+                  stride=d.vis_patch)
+    h = pe.flatten(2).transpose(1, 2)
+    h = h + w[VT + "embeddings.position_embedding.weight"][None]
+    B, T, W = h.shape
+    hd = d.vis_width // d.vis_heads
+    for l in range(d.vis_layers):
+        p = VT + f"encoder.layers.{l}."
+        r = h
+        y = F.layer_norm(h, (W,), w[p + "layer_norm1.weight"], w[p + "layer_norm1.bias"], 1e-6)
+        q = F.linear(y, w[p + "self_attn.q_proj.weight"], w[p + "self_attn.q_proj.bias"])
+        k = F.linear(y, w[p + "self_attn.k_proj.weight"], w[p + "self_attn.k_proj.bias"])
+        v = F.linear(y, w[p + "self_attn.v_proj.weight"], w[p + "self_attn.v_proj.bias"])
+        q, k, v = (t.view(B, T, d.vis_heads, hd).transpose(1, 2) for t in (q, k, v))
+        a = F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False,
+                                           scale=hd ** -0.5)
+        a = a.transpose(1, 2).reshape(B, T, W).contiguous()
+        a = F.linear(a, w[p + "self_attn.out_proj.weight"], w[p + "self_attn.out_proj.bias"])
+        h = r + a
+        r = h
+        y = F.layer_norm(h, (W,), w[p + "layer_norm2.weight"], w[p + "layer_norm2.bias"], 1e-6)
+        y = F.linear(y, w[p + "mlp.fc1.weight"], w[p + "mlp.fc1.bias"])
+        y = F.gelu(y, approximate="tanh")
+        y = F.linear(y, w[p + "mlp.fc2.weight"], w[p + "mlp.fc2.bias"])
+        h = r + y
+    return F.layer_norm(h, (W,), w[VT + "post_layernorm.weight"], w[VT + "post_layernorm.bias"], 1e-6)
+
+
+def embed_image(w, d: PI0Dims, pixel_values):
+    feats = siglip_tower(w, d, pixel_values)
+    feats = F.linear(feats, w[MM + "weight"], w[MM + "bias"])
+    return feats / (d.lm_width ** 0.5)
+
+
+def embed_prefix(w, d: PI0Dims, image, lang_tokens, lang_masks):
+    # modeling_pi0.py:517-567 (one camera, img_mask all True)
+    img_emb = embed_image(w, d, image).to(torch.bfloat16)
+    img_emb = img_emb * torch.tensor(img_emb.shape[-1] ** 0.5, dtype=img_emb.dtype)
+    B, n_img = img_emb.shape[:2]
+    lang_emb = F.embedding(lang_tokens, w[LM + "embed_tokens.weight"])
+    lang_emb = lang_emb * math.sqrt(lang_emb.shape[-1])
+    embs = torch.cat([img_emb, lang_emb], dim=1)
+    pad = torch.cat([torch.ones(B, n_img, dtype=torch.bool), lang_masks], dim=1)
+    att = torch.zeros(B, pad.shape[1], dtype=torch.bool)
+    return embs, pad, att
+
+
+# ------------------------------------------------------------------------------------------------
+# dual-tower layer loop  (paligemma_with_expert.py:236-360)
+# ------------------------------------------------------------------------------------------------
+def _tower_forward(w, d: PI0Dims, prefix: str, x, mask, pos, cache, fill, last_layer_kv_only=False):
+    """One tower alone (the reference only ever runs one at a time on the sampling path)."""
+    B = x.shape[0]
+    new_cache = {}
+    for l in range(d.layers):
+        p = prefix + f"layers.{l}."
+        y = gemma_rmsnorm(x, w[p + "input_layernorm.weight"])
+        y = y.to(torch.bfloat16)
+        shp = (*y.shape[:-1], -1, d.head_dim)
+        q = F.linear(y, w[p + "self_attn.q_proj.weight"]).view(shp)
+        k = F.linear(y, w[p + "self_attn.k_proj.weight"]).view(shp)
+        v = F.linear(y, w[p + "self_attn.v_proj.weight"]).view(shp)
+        q = apply_rope(q, pos)
+        k = apply_rope(k, pos)
+        if fill:
+            new_cache[l] = {"key_states": k, "value_states": v}
+            if last_layer_kv_only and l == d.layers - 1:
+                break
+        else:
+            k = torch.cat([cache[l]["key_states"], k], dim=1)
+            v = torch.cat([cache[l]["value_states"], v], dim=1)
+        a = eager_attention(mask, q, k, v, d.heads, d.head_dim).to(torch.bfloat16)
+        out = F.linear(a, w[p + "self_attn.o_proj.weight"])
+        out += x  # in place: the result keeps out's dtype (bf16) even when x is fp32 (layer 0 of the suffix)
+        res = out.clone()
+        out = gemma_rmsnorm(out, w[p + "post_attention_layernorm.weight"])
+        out = gemma_mlp(out, w[p + "mlp.gate_proj.weight"], w[p + "mlp.up_proj.weight"], w[p + "mlp.down_proj.weight"])
+        out += res
+        x = out
+    return x, new_cache
+
+
+def embed_suffix(w, d: PI0Dims, state, x_t, timestep):
+    # modeling_pi0.py:569-629
+    state_emb = F.linear(state, w["state_proj.weight"], w["state_proj.bias"]).to(torch.bfloat16)
+    time_emb = sinusoidal_time_embedding(timestep, d.ex_width).type(dtype=torch.bfloat16)
+    action_emb = F.linear(x_t, w["action_in_proj.weight"], w["action_in_proj.bias"])
+    time_emb = time_emb[:, None, :].expand_as(action_emb)
+    at = torch.cat([action_emb, time_emb], dim=2)
+    at = F.linear(at, w["action_time_mlp_in.weight"], w["action_time_mlp_in.bias"])
+    at = F.silu(at)
+    at = F.linear(at, w["action_time_mlp_out.weight"], w["action_time_mlp_out.bias"])
+    embs = torch.cat([state_emb[:, None, :], at], dim=1)  # promotes to fp32
+    B = state.shape[0]
+    pad = torch.ones(B, 1 + d.chunk_size, dtype=torch.bool)
+    att = torch.tensor([1, 1] + [0] * (d.chunk_size - 1), dtype=embs.dtype)[None].expand(B, -1)
+    return embs, pad, att
+
+
+def denoise_step(w, d: PI0Dims, state, prefix_pad, cache, x_t, timestep):
+    # modeling_pi0.py:717-752
+    suf, suf_pad, suf_att = embed_suffix(w, d, state, x_t, timestep)
+    B, S = suf_pad.shape
+    P = prefix_pad.shape[1]
+    prefix_2d = prefix_pad[:, None, :].expand(B, S, P)
+    suf_2d = make_att_2d_masks(suf_pad, suf_att)
+    full = torch.cat([prefix_2d, suf_2d], dim=2)
+    offsets = torch.sum(prefix_pad, dim=-1)[:, None]
+    pos = offsets + torch.cumsum(suf_pad, dim=1) - 1
+    out, _ = _tower_forward(w, d, EX, suf, full, pos, cache, fill=False)
+    out = gemma_rmsnorm(out, w[EX + "norm.weight"])
+    out = out[:, -d.chunk_size:].to(torch.float32)
+    return F.linear(out, w["action_out_proj.weight"], w["action_out_proj.bias"])
+
+
+def prefix_cache(w, d: PI0Dims, image, lang_tokens, lang_masks, last_layer_kv_only=False):
+    embs, pad, att = embed_prefix(w, d, image, lang_tokens, lang_masks)
+    mask = make_att_2d_masks(pad, att)
+    pos = torch.cumsum(pad, dim=1) - 1
+    _, cache = _tower_forward(w, d, LM, embs, mask, pos, None, fill=True, last_layer_kv_only=last_layer_kv_only)
+    return cache, pad
+
+
+@torch.no_grad()
+def sample_actions(w, d: PI0Dims, image, lang_tokens, lang_masks, state, noise, trace=None):
+    """Exactly the reference batch layout: every argument has leading dim B (= N candidates)."""
+    cache, pad = prefix_cache(w, d, image, lang_tokens, lang_masks)
+    if trace is not None:
+        trace["k0"] = cache[0]["key_states"].clone()
+        trace["v_last"] = cache[d.layers - 1]["value_states"].clone()
+    B = state.shape[0]
+    dt = torch.tensor(-1.0 / d.num_steps, dtype=torch.float32)
+    x_t = noise.clone()
+    time = torch.tensor(1.0, dtype=torch.float32)
+    step = 0
+    while time >= -dt / 2:
+        v_t = denoise_step(w, d, state, pad, cache, x_t, time.expand(B))
+        if trace is not None and step == 0:
+            trace["v0"] = v_t.clone()
+        x_t += dt * v_t
+        time += dt
+        step += 1
+    return x_t
+
+
+@torch.no_grad()
+def sample_actions_dedup(w, d: PI0Dims, image1, lang_tokens_r, lang_masks_r, state1, noise, K):
+    """Same arithmetic, de-duplicated the way the CUDA path schedules it: vision
+    tower once, prefix once per rephrase (padded tokens kept), K samples share their rephrase's cache."""
+    R = lang_tokens_r.shape[0]
+    img = image1.expand(R, -1, -1, -1)
+    cache, pad = prefix_cache(w, d, img, lang_tokens_r, lang_masks_r, last_layer_kv_only=True)
+    rep = torch.arange(R).repeat_interleave(K)
+    cache = {l: {k: v[rep] for k, v in c.items()} for l, c in cache.items()}
+    pad = pad[rep]
+    N = R * K
+    state = state1.expand(N, -1)
+    dt = torch.tensor(-1.0 / d.num_steps, dtype=torch.float32)
+    x_t = noise.clone()
+    time = torch.tensor(1.0, dtype=torch.float32)
+    while time >= -dt / 2:
+        v_t = denoise_step(w, d, state, pad, cache, x_t, time.expand(N))
+        x_t += dt * v_t
+        time += dt
+    return x_t
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs
+# ------------------------------------------------------------------------------------------------
+def make_inputs(d: PI0Dims, R: int, K: int, seed: int = 0, noise_std: float = 1.0):
+    g = torch.Generator().manual_seed(1000 + seed)
+    image = torch.rand(1, 3, d.vis_image, d.vis_image, generator=g) * 2 - 1
+    lens = torch.randint(min(8, d.max_lang_len), min(24, d.max_lang_len) + 1, (R,), generator=g)
+    tokens = torch.randint(3, d.vocab - 1, (R, d.max_lang_len), generator=g)
+    masks = torch.arange(d.max_lang_len)[None, :] < lens[:, None]
+    tokens = torch.where(masks, tokens, torch.zeros_like(tokens))
+    state = torch.zeros(1, d.max_state_dim)
+    state[0, :7] = torch.randn(7, generator=g)
+    noise = torch.randn(R * K, d.chunk_size, d.max_action_dim, generator=g) * noise_std
+    return dict(image=image, tokens=tokens, masks=masks, state=state, noise=noise, lens=lens)
+
+
+def expand_to_batch(inp, K):
+    """What run_simpler_eval_with_openpi.py:305-319 hands to select_action (rephrase-major)."""
+    R = inp["tokens"].shape[0]
+    N = R * K
+    rep = torch.arange(R).repeat_interleave(K)
+    return dict(image=inp["image"].repeat(N, 1, 1, 1), tokens=inp["tokens"][rep], masks=inp["masks"][rep],
+                state=inp["state"].repeat(N, 1), noise=inp["noise"])

@@ -174,6 +174,12 @@ def build_pi0(dims: dict, chunk_size=4, tokenizer_max_length=72, num_steps=10):
         model = M.PI0FlowMatching(cfg)
     finally:
         M.PaliGemmaWithExpertConfig = orig
+    # transformers >= 4.5x made Gemma's embed_tokens a *scaled* embedding (x sqrt(hidden)); the
+    # reference targets 4.48.3 where it is a plain nn.Embedding and modeling_pi0.py:553 applies the
+    # scale itself.  Neutralise the built-in scale so the 4.48.3 arithmetic is what runs.
+    et = model.paligemma_with_expert.paligemma.model.language_model.embed_tokens
+    if hasattr(et, "embed_scale"):
+        et.embed_scale = torch.ones_like(et.embed_scale)
     return model.eval(), cfg
 
 

@@ -1,0 +1,76 @@
+"""pi0 sampling parity: CUDA engine (through the C ABI) vs the CPU oracle at the reference batch layout.
+
+Tolerances: north_star asks max-abs <= 1e-2 on actions; SURVEY.md F10 shows the reference's own bf16
+result moves by ~1e-2 when only the batch size changes, so intermediate tensors are checked by
+relative L2 (bf16 rounding noise ~2e-3..1e-2) and the final actions by max-abs.
+"""
+import pytest
+import torch
+
+from oracle import pi0_oracle as O
+from tests.helpers import build_pi0_engine, max_abs, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+ACTION_TOL = 1e-2
+
+
+def _run(d, R, K, seed=0, graph=1):
+    torch.manual_seed(0)
+    w = O.make_pi0_weights(d, seed=seed)
+    inp = O.make_inputs(d, R, K, seed=seed)
+    b = O.expand_to_batch(inp, K)
+    trace = {}
+    ref = O.sample_actions(w, d, b["image"], b["tokens"], b["masks"], b["state"], b["noise"], trace=trace)
+    eng = build_pi0_engine(d, w, R, K, use_cuda_graph=graph)
+    args = (inp["image"][0].cuda().contiguous(), inp["tokens"].cuda(), inp["lens"].to(torch.int32).cuda(),
+            inp["state"][0].cuda().contiguous(), inp["noise"].cuda())
+    outs = [eng.pi0_sample(*args, K=K).cpu() for _ in range(3 if graph else 1)]
+    torch.cuda.synchronize()
+    return w, inp, ref, trace, eng, outs
+
+
+@pytest.mark.parametrize("name,R,K", [("TINY", 2, 2), ("TINY", 3, 1), ("MID", 2, 2), ("MID", 1, 5)])
+def test_pi0_sample_matches_oracle(name, R, K):
+    d = getattr(O, name)
+    w, inp, ref, trace, eng, outs = _run(d, R, K)
+    T, P = d.n_img_tokens, d.n_img_tokens + d.max_lang_len
+    # stage 1: image embedding (SigLIP tower + projector), before the /sqrt(d) rescale
+    img_ref = O.embed_image(w, d, inp["image"])[0].float() * (d.lm_width ** 0.5)
+    img = eng.debug("image_emb", (T, d.lm_width), torch.bfloat16)
+    assert rel_l2(img, img_ref) < 2e-2, ("image_emb", rel_l2(img, img_ref))
+    # stage 2: prefix KV cache, first and last layer, valid tokens only
+    k0 = eng.debug("prefix_k0", (R, P, d.head_dim), torch.bfloat16)
+    vl = eng.debug("prefix_vlast", (R, P, d.head_dim), torch.bfloat16)
+    for r in range(R):
+        n = T + int(inp["lens"][r])
+        kr = trace["k0"][r * K, :n, 0]
+        assert rel_l2(k0[r, :n], kr) < 2e-2, ("k0", r, rel_l2(k0[r, :n], kr))
+        vr = trace["v_last"][r * K, :n, 0]
+        assert rel_l2(vl[r, :n], vr) < 5e-2, ("v_last", r, rel_l2(vl[r, :n], vr))
+    # stage 3: first velocity
+    v0 = eng.debug("v0", (R * K, d.chunk_size, d.max_action_dim), torch.float32)
+    assert rel_l2(v0, trace["v0"]) < 5e-2, ("v0", rel_l2(v0, trace["v0"]))
+    # final actions; graph replay must reproduce the eager first call bit for bit
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    err = max_abs(outs[0], ref)
+    effect = (ref - inp["noise"]).abs().max().item()
+    print(f"{name} R={R} K={K}: actions max-abs {err:.3e} (effect size {effect:.2f})")
+    assert err <= ACTION_TOL * max(1.0, effect), err
+    eng.close()
+
+
+def test_pi0_candidates_of_one_rephrase_share_prefix():
+    """K samples of one rephrase with identical noise must be bit-identical."""
+    d = O.TINY
+    w = O.make_pi0_weights(d, seed=1)
+    inp = O.make_inputs(d, 2, 3, seed=1)
+    inp["noise"][1] = inp["noise"][0]
+    inp["noise"][2] = inp["noise"][0]
+    eng = build_pi0_engine(d, w, 2, 3)
+    out = eng.pi0_sample(inp["image"][0].cuda().contiguous(), inp["tokens"].cuda(), inp["lens"].to(torch.int32).cuda(),
+                         inp["state"][0].cuda().contiguous(), inp["noise"].cuda(), K=3).cpu()
+    assert torch.equal(out[0], out[1]) and torch.equal(out[0], out[2])
+    assert not torch.equal(out[0], out[3])
+    eng.close()

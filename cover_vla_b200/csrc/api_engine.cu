@@ -69,6 +69,7 @@ int cvb_create(const cvb_config* cfg, cvb_handle** out) {
 void cvb_destroy(cvb_handle* h) {
   if (h == nullptr) return;
   for (auto& g : h->pi0.graphs) cudaGraphExecDestroy(g.second);
+  if (h->pi0.cap_stream) cudaStreamDestroy(h->pi0.cap_stream);
   cvb::verifier_destroy(h);
   for (void* p : h->owned) cudaFree(p);
   delete h;

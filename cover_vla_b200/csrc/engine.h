@@ -68,6 +68,7 @@ struct Pi0State {
   bf16 *he = nullptr, *xe = nullptr, *qkv_e = nullptr, *attn_e = nullptr, *act_e = nullptr;
   std::unordered_map<long, cudaGraphExec_t> graphs;  // key = R * 65536 + K
   std::unordered_map<long, int> warm;                // eager runs done per key
+  cudaStream_t cap_stream = nullptr;
 };
 
 struct VerifierState;  // engine_verifier.cu

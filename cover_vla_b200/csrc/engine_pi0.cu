@@ -469,10 +469,14 @@ int pi0_sample(cvb_handle* h, const float* image, const int64_t* tokens, const i
         s.warm[key] = 1;
         CVB_TRY(run_all(h, st, R, K));
       } else {
+        // capture on a private stream (the caller's may be the legacy default stream, which cannot
+        // be captured); the instantiated graph is then launched on the caller's stream
+        if (s.cap_stream == nullptr)
+          CVB_CUDA(cudaStreamCreateWithFlags(&s.cap_stream, cudaStreamNonBlocking));
         cudaGraph_t graph = nullptr;
-        CVB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        int rc = run_all(h, st, R, K);
-        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        CVB_CUDA(cudaStreamBeginCapture(s.cap_stream, cudaStreamCaptureModeThreadLocal));
+        int rc = run_all(h, s.cap_stream, R, K);
+        cudaError_t e = cudaStreamEndCapture(s.cap_stream, &graph);
         if (rc != 0) {
           if (graph) cudaGraphDestroy(graph);
           return rc;

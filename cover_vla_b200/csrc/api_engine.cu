@@ -3,6 +3,7 @@
 #include <cstring>
 
 #include "engine.h"
+#include "verifier_kernels.h"
 
 namespace cvb {
 
@@ -132,7 +133,29 @@ int cvb_pi0_sample(cvb_handle* h, const float* image, const int64_t* lang_tokens
 
 int64_t cvb_debug_copy(cvb_handle* h, const char* name, void* dst, int64_t max_bytes, void* stream) {
   if (h == nullptr || name == nullptr) return -1;
+  if (std::string(name).rfind("vf_", 0) == 0)
+    return cvb::verifier_debug_copy(h, name, dst, max_bytes, (cudaStream_t)stream);
   return cvb::pi0_debug_copy(h, name, dst, max_bytes, (cudaStream_t)stream);
+}
+
+int cvb_verifier_score(cvb_handle* h, const float* image, const int64_t* text_tokens, const float* traj, int N,
+                       int R, int K, float* scores, float* group_mean, int32_t* best_idx, float* best_score,
+                       int recompute_context, void* stream) {
+  CVB_REQUIRE(h != nullptr, "null handle");
+  return cvb::verifier_score(h, image, text_tokens, traj, N, R, K, scores, group_mean, best_idx, best_score,
+                             recompute_context, (cudaStream_t)stream);
+}
+
+int cvb_verifier_set_features(cvb_handle* h, const float* patch, const float* text, void* stream) {
+  CVB_REQUIRE(h != nullptr, "null handle");
+  return cvb::verifier_set_features(h, patch, text, (cudaStream_t)stream);
+}
+
+int cvb_select(const float* scores, int R, int K, float* group_mean, int32_t* best_idx, float* best_score,
+               void* stream) {
+  CVB_REQUIRE(scores != nullptr && best_idx != nullptr && best_score != nullptr, "null argument");
+  CVB_REQUIRE(R >= 1 && K >= 1, "R and K must be >= 1");
+  return cvb::select_best((cudaStream_t)stream, scores, R, K, group_mean, best_idx, best_score);
 }
 
 // ---- host-only constants of the denoise loop (modeling_pi0.py:697-714 and :71-89)

@@ -110,5 +110,10 @@ int64_t pi0_debug_copy(cvb_handle* h, const std::string& name, void* dst, int64_
 void verifier_required_weights(const cvb_config& c, std::vector<WeightSpec>* out);
 int verifier_finalize(cvb_handle* h, cudaStream_t st);
 void verifier_destroy(cvb_handle* h);
+int verifier_score(cvb_handle* h, const float* image, const int64_t* tokens, const float* traj, int N, int R, int K,
+                   float* scores, float* group_mean, int32_t* best_idx, float* best_score, int recompute_context,
+                   cudaStream_t st);
+int64_t verifier_debug_copy(cvb_handle* h, const std::string& name, void* dst, int64_t max_bytes, cudaStream_t st);
+int verifier_set_features(cvb_handle* h, const float* patch, const float* text, cudaStream_t st);
 
 }  // namespace cvb

@@ -1,11 +1,522 @@
+// CoVer verifier pipeline: SigLIP2 trunk (bf16 tcgen05 GEMMs, up to the two hook points) -> fp32 heads
+// of every ensemble member -> fused score / group-mean / argmax.
+//
+// Reference: EfficientEnsembleMerged.compute_max_similarity_scores_batch (efficient_ensemble_merged.py:309-454),
+// get_embeddings_from_model_batch (:194-247), VLA_SigLIP2_Bridge.extract_features
+// (finetune_trajectory_bridge_ddp.py:297-355).  De-duplication per SURVEY.md F3-F5: the image/text side
+// is computed once per call (not N times), the last vision block stops after attn.proj, the text
+// tower applies ln_final + text_projection to every token.
+#include <cmath>
+
 #include "engine.h"
+#include "gemm_tcgen05.cuh"
+#include "pi0_kernels.h"
+#include "verifier_kernels.h"
 
 namespace cvb {
-struct VerifierState {};
-void verifier_required_weights(const cvb_config&, std::vector<WeightSpec>*) {}
-int verifier_finalize(cvb_handle*, cudaStream_t) {
-  set_last_error("verifier not built yet");
-  return -1;
+
+struct TrunkBlock {
+  const bf16 *ln1_w, *ln1_b, *wqkv, *bqkv, *wo, *bo, *ln2_w, *ln2_b, *w1, *b1, *w2, *b2;
+};
+struct TrajLayer {
+  const float *w_in, *b_in, *wo, *bo, *w1, *b1, *w2, *b2, *n1w, *n1b, *n2w, *n2b;
+};
+struct MemberW {
+  const float *temp, *pos_emb, *w_ss, *b_ss;
+  float* wkv_v;  // owned [L*2E, W] (vision pooling K/V projections of all blocks)
+  float* bkv_v;  // owned [L*2E]
+  std::vector<TrajLayer> traj;
+};
+
+struct VerifierState {
+  std::vector<TrunkBlock> vis, txt;
+  const bf16 *patch_b, *pos_embed, *tok_emb, *txt_pos, *lnf_w, *lnf_b, *wproj, *bproj;
+  bf16* w_patch = nullptr;
+  int kpad = 0;
+  std::vector<MemberW> mem;
+  float* wkv_t = nullptr;  // owned [M*L*2E, W] text pooling K/V projections of all members
+  float* bkv_t = nullptr;
+  PoolChain* chains = nullptr;  // device [2*M]
+  ItFinal* itf = nullptr;       // device [M]
+  // inputs
+  float* in_image = nullptr;
+  int64_t* in_tokens = nullptr;
+  float* in_traj = nullptr;
+  // trunk workspace
+  bf16 *patches = nullptr, *hv = nullptr, *xv = nullptr, *qkv = nullptr, *att = nullptr, *mlp = nullptr,
+       *pfeat = nullptr, *ht = nullptr, *tfeat = nullptr;
+  // head workspace
+  float *Pn = nullptr, *Tn = nullptr, *sim = nullptr, *pe = nullptr, *taf = nullptr, *kv_v = nullptr,
+        *kv_t = nullptr, *vtok = nullptr, *ttok = nullptr, *it = nullptr;
+  float *tx = nullptr, *tqkv = nullptr, *tatt = nullptr, *ty = nullptr, *tff = nullptr, *act = nullptr;
+  float* scores = nullptr;
+  bool context_valid = false;
+};
+
+namespace {
+const std::string TRK = "verifier.trunk.";
+
+template <typename T>
+int W(cvb_handle* h, const std::string& key, int dtype, int64_t numel, const T** out) {
+  const void* p = nullptr;
+  CVB_TRY(get_weight(h, key, dtype, numel, &p));
+  *out = reinterpret_cast<const T*>(p);
+  return 0;
 }
-void verifier_destroy(cvb_handle*) {}
+int gemm(cudaStream_t st, const bf16* A, long lda, const bf16* Wt, long ldw, int M, int N, int K, int epi, void* C,
+         long ldc, const void* bias = nullptr, const void* resid = nullptr, long ldr = 0) {
+  GemmCall c;
+  c.A = A, c.lda = lda, c.W = Wt, c.ldw = ldw, c.M = M, c.N = N, c.K = K, c.epi = epi;
+  c.C = C, c.ldc = ldc, c.bias = bias, c.resid = resid, c.ldr = ldr;
+  return gemm_bf16(st, c);
+}
+int sg(cudaStream_t st, const float* A, long lda, const float* Wt, long ldw, int M, int N, int K, float* C, long ldc,
+       const float* bias = nullptr, int act = 0, const float* resid = nullptr, long ldr = 0, int w_kn = 0) {
+  SgemmCall c;
+  c.A = A, c.lda = lda, c.W = Wt, c.ldw = ldw, c.M = M, c.N = N, c.K = K, c.C = C, c.ldc = ldc;
+  c.bias = bias, c.act = act, c.resid = resid, c.ldr = ldr, c.w_kn = w_kn;
+  return sgemm_f32(st, c);
+}
+}  // namespace
+
+void verifier_required_weights(const cvb_config& c, std::vector<WeightSpec>* out) {
+  auto add = [&](const std::string& k, int dt, std::vector<int64_t> shape) {
+    out->push_back(WeightSpec{k, dt, std::move(shape)});
+  };
+  const int Wd = c.vf_width, E = c.vf_embed, Np = (c.vf_image / c.vf_patch) * (c.vf_image / c.vf_patch);
+  const std::string v = TRK + "visual.trunk.";
+  add(v + "patch_embed.proj.weight", CVB_BF16, {Wd, 3, c.vf_patch, c.vf_patch});
+  add(v + "patch_embed.proj.bias", CVB_BF16, {Wd});
+  add(v + "pos_embed", CVB_BF16, {1, Np, Wd});
+  for (int l = 0; l < c.vf_layers; ++l) {
+    const std::string p = v + "blocks." + std::to_string(l) + ".";
+    add(p + "norm1.weight", CVB_BF16, {Wd});
+    add(p + "norm1.bias", CVB_BF16, {Wd});
+    add(p + "attn.qkv.weight", CVB_BF16, {3 * Wd, Wd});
+    add(p + "attn.qkv.bias", CVB_BF16, {3 * Wd});
+    add(p + "attn.proj.weight", CVB_BF16, {Wd, Wd});
+    add(p + "attn.proj.bias", CVB_BF16, {Wd});
+    if (l < c.vf_layers - 1) {
+      add(p + "norm2.weight", CVB_BF16, {Wd});
+      add(p + "norm2.bias", CVB_BF16, {Wd});
+      add(p + "mlp.fc1.weight", CVB_BF16, {c.vf_mlp, Wd});
+      add(p + "mlp.fc1.bias", CVB_BF16, {c.vf_mlp});
+      add(p + "mlp.fc2.weight", CVB_BF16, {Wd, c.vf_mlp});
+      add(p + "mlp.fc2.bias", CVB_BF16, {Wd});
+    }
+  }
+  const std::string t = TRK + "text.";
+  add(t + "token_embedding.weight", CVB_BF16, {c.vf_vocab, Wd});
+  add(t + "positional_embedding", CVB_BF16, {c.vf_text_ctx, Wd});
+  for (int l = 0; l < c.vf_text_layers; ++l) {
+    const std::string p = t + "transformer.resblocks." + std::to_string(l) + ".";
+    add(p + "ln_1.weight", CVB_BF16, {Wd});
+    add(p + "ln_1.bias", CVB_BF16, {Wd});
+    add(p + "attn.in_proj_weight", CVB_BF16, {3 * Wd, Wd});
+    add(p + "attn.in_proj_bias", CVB_BF16, {3 * Wd});
+    add(p + "attn.out_proj.weight", CVB_BF16, {Wd, Wd});
+    add(p + "attn.out_proj.bias", CVB_BF16, {Wd});
+    add(p + "ln_2.weight", CVB_BF16, {Wd});
+    add(p + "ln_2.bias", CVB_BF16, {Wd});
+    add(p + "mlp.c_fc.weight", CVB_BF16, {c.vf_mlp, Wd});
+    add(p + "mlp.c_fc.bias", CVB_BF16, {c.vf_mlp});
+    add(p + "mlp.c_proj.weight", CVB_BF16, {Wd, c.vf_mlp});
+    add(p + "mlp.c_proj.bias", CVB_BF16, {Wd});
+  }
+  add(t + "ln_final.weight", CVB_BF16, {Wd});
+  add(t + "ln_final.bias", CVB_BF16, {Wd});
+  add(t + "text_projection.weight", CVB_BF16, {Wd, Wd});
+  add(t + "text_projection.bias", CVB_BF16, {Wd});
+  for (int m = 0; m < c.vf_members; ++m) {
+    const std::string b = "verifier." + std::to_string(m) + ".";
+    add(b + "text_aware_visual_extraction.temperature", CVB_F32, {});
+    add(b + "text_aware_visual_extraction.pos_emb", CVB_F32, {Np, Wd});
+    for (const char* pool : {"vision_poolings", "text_pooling"}) {
+      const std::string p = b + pool + ".";
+      add(p + "query", CVB_F32, {1, 1, E});
+      add(p + "layer_norm.weight", CVB_F32, {E});
+      add(p + "layer_norm.bias", CVB_F32, {E});
+      for (int i = 0; i < c.vf_pool_layers; ++i) {
+        const std::string q = p + "blocks." + std::to_string(i) + ".";
+        add(q + "attention.q_proj_weight", CVB_F32, {E, E});
+        add(q + "attention.k_proj_weight", CVB_F32, {E, Wd});
+        add(q + "attention.v_proj_weight", CVB_F32, {E, Wd});
+        add(q + "attention.in_proj_bias", CVB_F32, {3 * E});
+        add(q + "attention.out_proj.weight", CVB_F32, {E, E});
+        add(q + "attention.out_proj.bias", CVB_F32, {E});
+        add(q + "mlp.fc1.weight", CVB_F32, {E, E});
+        add(q + "mlp.fc1.bias", CVB_F32, {E});
+        add(q + "mlp.fc2.weight", CVB_F32, {E, E});
+        add(q + "mlp.fc2.bias", CVB_F32, {E});
+        for (const char* nm : {"q_layer_norm", "layer_norm"}) {
+          add(q + nm + ".weight", CVB_F32, {E});
+          add(q + nm + ".bias", CVB_F32, {E});
+        }
+      }
+    }
+    add(b + "input_projection.weight", CVB_F32, {E, 2 * E});
+    add(b + "input_projection.bias", CVB_F32, {E});
+    add(b + "single_step_action_encoder.weight", CVB_F32, {E, c.vf_action_dim});
+    add(b + "single_step_action_encoder.bias", CVB_F32, {E});
+    for (int i = 0; i < c.vf_traj_layers; ++i) {
+      const std::string q = b + "trajectory_encoder.layers." + std::to_string(i) + ".";
+      add(q + "self_attn.in_proj_weight", CVB_F32, {3 * E, E});
+      add(q + "self_attn.in_proj_bias", CVB_F32, {3 * E});
+      add(q + "self_attn.out_proj.weight", CVB_F32, {E, E});
+      add(q + "self_attn.out_proj.bias", CVB_F32, {E});
+      add(q + "linear1.weight", CVB_F32, {c.vf_traj_ff, E});
+      add(q + "linear1.bias", CVB_F32, {c.vf_traj_ff});
+      add(q + "linear2.weight", CVB_F32, {E, c.vf_traj_ff});
+      add(q + "linear2.bias", CVB_F32, {E});
+      for (const char* nm : {"norm1", "norm2"}) {
+        add(q + nm + ".weight", CVB_F32, {E});
+        add(q + nm + ".bias", CVB_F32, {E});
+      }
+    }
+  }
+}
+
+int verifier_finalize(cvb_handle* h, cudaStream_t st) {
+  const cvb_config& c = h->cfg;
+  h->vf = new VerifierState();
+  VerifierState& s = *h->vf;
+  const int Wd = c.vf_width, E = c.vf_embed, L = c.vf_pool_layers, M = c.vf_members;
+  const int Np = (c.vf_image / c.vf_patch) * (c.vf_image / c.vf_patch), Tt = c.vf_text_ctx;
+  const int Nm = c.max_rephrases * c.max_samples, S = c.vf_history;
+  CVB_REQUIRE(Wd % 8 == 0 && c.vf_mlp % 8 == 0 && (Wd / c.vf_heads) % 8 == 0, "verifier trunk widths must be multiples of 8");
+  CVB_REQUIRE(L <= kMaxPoolLayers, "too many pooling layers");
+  CVB_REQUIRE(E % c.vf_pool_heads == 0, "embed must divide by pool heads");
+  const std::string v = TRK + "visual.trunk.", t = TRK + "text.";
+  // ---- trunk
+  const int kreal = 3 * c.vf_patch * c.vf_patch;
+  s.kpad = (kreal + 7) / 8 * 8;
+  const bf16* wp;
+  CVB_TRY(W(h, v + "patch_embed.proj.weight", CVB_BF16, (int64_t)Wd * kreal, &wp));
+  CVB_TRY(dalloc_t(h, &s.w_patch, (size_t)Wd * s.kpad));
+  CVB_CUDA(cudaMemsetAsync(s.w_patch, 0, (size_t)Wd * s.kpad * sizeof(bf16), st));
+  CVB_CUDA(cudaMemcpy2DAsync(s.w_patch, s.kpad * sizeof(bf16), wp, kreal * sizeof(bf16), kreal * sizeof(bf16), Wd,
+                             cudaMemcpyDeviceToDevice, st));
+  CVB_TRY(W(h, v + "patch_embed.proj.bias", CVB_BF16, Wd, &s.patch_b));
+  CVB_TRY(W(h, v + "pos_embed", CVB_BF16, (int64_t)Np * Wd, &s.pos_embed));
+  s.vis.resize(c.vf_layers);
+  for (int l = 0; l < c.vf_layers; ++l) {
+    const std::string p = v + "blocks." + std::to_string(l) + ".";
+    TrunkBlock& B = s.vis[l];
+    memset(&B, 0, sizeof(B));
+    CVB_TRY(W(h, p + "norm1.weight", CVB_BF16, Wd, &B.ln1_w));
+    CVB_TRY(W(h, p + "norm1.bias", CVB_BF16, Wd, &B.ln1_b));
+    CVB_TRY(W(h, p + "attn.qkv.weight", CVB_BF16, (int64_t)3 * Wd * Wd, &B.wqkv));
+    CVB_TRY(W(h, p + "attn.qkv.bias", CVB_BF16, 3 * Wd, &B.bqkv));
+    CVB_TRY(W(h, p + "attn.proj.weight", CVB_BF16, (int64_t)Wd * Wd, &B.wo));
+    CVB_TRY(W(h, p + "attn.proj.bias", CVB_BF16, Wd, &B.bo));
+    if (l < c.vf_layers - 1) {
+      CVB_TRY(W(h, p + "norm2.weight", CVB_BF16, Wd, &B.ln2_w));
+      CVB_TRY(W(h, p + "norm2.bias", CVB_BF16, Wd, &B.ln2_b));
+      CVB_TRY(W(h, p + "mlp.fc1.weight", CVB_BF16, (int64_t)c.vf_mlp * Wd, &B.w1));
+      CVB_TRY(W(h, p + "mlp.fc1.bias", CVB_BF16, c.vf_mlp, &B.b1));
+      CVB_TRY(W(h, p + "mlp.fc2.weight", CVB_BF16, (int64_t)c.vf_mlp * Wd, &B.w2));
+      CVB_TRY(W(h, p + "mlp.fc2.bias", CVB_BF16, Wd, &B.b2));
+    }
+  }
+  CVB_TRY(W(h, t + "token_embedding.weight", CVB_BF16, (int64_t)c.vf_vocab * Wd, &s.tok_emb));
+  CVB_TRY(W(h, t + "positional_embedding", CVB_BF16, (int64_t)Tt * Wd, &s.txt_pos));
+  s.txt.resize(c.vf_text_layers);
+  for (int l = 0; l < c.vf_text_layers; ++l) {
+    const std::string p = t + "transformer.resblocks." + std::to_string(l) + ".";
+    TrunkBlock& B = s.txt[l];
+    CVB_TRY(W(h, p + "ln_1.weight", CVB_BF16, Wd, &B.ln1_w));
+    CVB_TRY(W(h, p + "ln_1.bias", CVB_BF16, Wd, &B.ln1_b));
+    CVB_TRY(W(h, p + "attn.in_proj_weight", CVB_BF16, (int64_t)3 * Wd * Wd, &B.wqkv));
+    CVB_TRY(W(h, p + "attn.in_proj_bias", CVB_BF16, 3 * Wd, &B.bqkv));
+    CVB_TRY(W(h, p + "attn.out_proj.weight", CVB_BF16, (int64_t)Wd * Wd, &B.wo));
+    CVB_TRY(W(h, p + "attn.out_proj.bias", CVB_BF16, Wd, &B.bo));
+    CVB_TRY(W(h, p + "ln_2.weight", CVB_BF16, Wd, &B.ln2_w));
+    CVB_TRY(W(h, p + "ln_2.bias", CVB_BF16, Wd, &B.ln2_b));
+    CVB_TRY(W(h, p + "mlp.c_fc.weight", CVB_BF16, (int64_t)c.vf_mlp * Wd, &B.w1));
+    CVB_TRY(W(h, p + "mlp.c_fc.bias", CVB_BF16, c.vf_mlp, &B.b1));
+    CVB_TRY(W(h, p + "mlp.c_proj.weight", CVB_BF16, (int64_t)c.vf_mlp * Wd, &B.w2));
+    CVB_TRY(W(h, p + "mlp.c_proj.bias", CVB_BF16, Wd, &B.b2));
+  }
+  CVB_TRY(W(h, t + "ln_final.weight", CVB_BF16, Wd, &s.lnf_w));
+  CVB_TRY(W(h, t + "ln_final.bias", CVB_BF16, Wd, &s.lnf_b));
+  CVB_TRY(W(h, t + "text_projection.weight", CVB_BF16, (int64_t)Wd * Wd, &s.wproj));
+  CVB_TRY(W(h, t + "text_projection.bias", CVB_BF16, Wd, &s.bproj));
+
+  // ---- workspace (trunk)
+  const int Tmax = std::max(Np, Tt);
+  CVB_TRY(dalloc_t(h, &s.in_image, (size_t)3 * c.vf_image * c.vf_image));
+  CVB_TRY(dalloc_t(h, &s.in_tokens, Tt));
+  CVB_TRY(dalloc_t(h, &s.in_traj, (size_t)Nm * S * c.vf_action_dim));
+  CVB_TRY(dalloc_t(h, &s.patches, (size_t)Np * s.kpad));
+  CVB_TRY(dalloc_t(h, &s.hv, (size_t)Tmax * Wd));
+  CVB_TRY(dalloc_t(h, &s.xv, (size_t)Tmax * Wd));
+  CVB_TRY(dalloc_t(h, &s.qkv, (size_t)Tmax * 3 * Wd));
+  CVB_TRY(dalloc_t(h, &s.att, (size_t)Tmax * Wd));
+  CVB_TRY(dalloc_t(h, &s.mlp, (size_t)Tmax * c.vf_mlp));
+  CVB_TRY(dalloc_t(h, &s.pfeat, (size_t)Np * Wd));
+  CVB_TRY(dalloc_t(h, &s.ht, (size_t)Tt * Wd));
+  CVB_TRY(dalloc_t(h, &s.tfeat, (size_t)Tt * Wd));
+  // ---- workspace (heads)
+  CVB_TRY(dalloc_t(h, &s.Pn, (size_t)Np * Wd));
+  CVB_TRY(dalloc_t(h, &s.Tn, (size_t)Tt * Wd));
+  CVB_TRY(dalloc_t(h, &s.sim, (size_t)Tt * Np));
+  CVB_TRY(dalloc_t(h, &s.pe, (size_t)Np * Wd));
+  CVB_TRY(dalloc_t(h, &s.taf, (size_t)M * Tt * Wd));
+  CVB_TRY(dalloc_t(h, &s.kv_v, (size_t)M * Tt * L * 2 * E));
+  CVB_TRY(dalloc_t(h, &s.kv_t, (size_t)Tt * M * L * 2 * E));
+  CVB_TRY(dalloc_t(h, &s.vtok, (size_t)M * E));
+  CVB_TRY(dalloc_t(h, &s.ttok, (size_t)M * E));
+  CVB_TRY(dalloc_t(h, &s.it, (size_t)M * E));
+  const size_t rows = (size_t)Nm * S;
+  CVB_TRY(dalloc_t(h, &s.tx, rows * E));
+  CVB_TRY(dalloc_t(h, &s.tqkv, rows * 3 * E));
+  CVB_TRY(dalloc_t(h, &s.tatt, rows * E));
+  CVB_TRY(dalloc_t(h, &s.ty, rows * E));
+  CVB_TRY(dalloc_t(h, &s.tff, rows * c.vf_traj_ff));
+  CVB_TRY(dalloc_t(h, &s.act, (size_t)M * Nm * E));
+  CVB_TRY(dalloc_t(h, &s.scores, Nm));
+
+  // ---- heads: pack K/V projections of all pooling blocks (they only depend on the kv input)
+  s.mem.resize(M);
+  CVB_TRY(dalloc_t(h, &s.wkv_t, (size_t)M * L * 2 * E * Wd));
+  CVB_TRY(dalloc_t(h, &s.bkv_t, (size_t)M * L * 2 * E));
+  std::vector<PoolChain> chains(2 * M);
+  std::vector<ItFinal> itf(M);
+  for (int m = 0; m < M; ++m) {
+    const std::string b = "verifier." + std::to_string(m) + ".";
+    MemberW& Mw = s.mem[m];
+    CVB_TRY(W(h, b + "text_aware_visual_extraction.temperature", CVB_F32, 1, &Mw.temp));
+    CVB_TRY(W(h, b + "text_aware_visual_extraction.pos_emb", CVB_F32, (int64_t)Np * Wd, &Mw.pos_emb));
+    CVB_TRY(W(h, b + "single_step_action_encoder.weight", CVB_F32, (int64_t)E * c.vf_action_dim, &Mw.w_ss));
+    CVB_TRY(W(h, b + "single_step_action_encoder.bias", CVB_F32, E, &Mw.b_ss));
+    CVB_TRY(dalloc_t(h, &Mw.wkv_v, (size_t)L * 2 * E * Wd));
+    CVB_TRY(dalloc_t(h, &Mw.bkv_v, (size_t)L * 2 * E));
+    for (int pi = 0; pi < 2; ++pi) {
+      const std::string p = b + (pi == 0 ? "vision_poolings." : "text_pooling.");
+      PoolChain& ch = chains[m * 2 + pi];
+      memset(&ch, 0, sizeof(ch));
+      CVB_TRY(W(h, p + "query", CVB_F32, E, &ch.query));
+      CVB_TRY(W(h, p + "layer_norm.weight", CVB_F32, E, &ch.fin_w));
+      CVB_TRY(W(h, p + "layer_norm.bias", CVB_F32, E, &ch.fin_b));
+      ch.embed = E, ch.heads = c.vf_pool_heads, ch.tokens = Tt, ch.layers = L;
+      float* wdst = pi == 0 ? Mw.wkv_v : s.wkv_t + (size_t)m * L * 2 * E * Wd;
+      float* bdst = pi == 0 ? Mw.bkv_v : s.bkv_t + (size_t)m * L * 2 * E;
+      if (pi == 0) {
+        ch.kv = s.kv_v + (size_t)m * Tt * L * 2 * E, ch.kv_ld = L * 2 * E, ch.out = s.vtok + (size_t)m * E;
+      } else {
+        ch.kv = s.kv_t + (size_t)m * L * 2 * E, ch.kv_ld = M * L * 2 * E, ch.out = s.ttok + (size_t)m * E;
+      }
+      for (int i = 0; i < L; ++i) {
+        const std::string q = p + "blocks." + std::to_string(i) + ".";
+        PoolBlockW& bw = ch.blk[i];
+        const float *wk, *wv;
+        CVB_TRY(W(h, q + "attention.q_proj_weight", CVB_F32, (int64_t)E * E, &bw.wq));
+        CVB_TRY(W(h, q + "attention.k_proj_weight", CVB_F32, (int64_t)E * Wd, &wk));
+        CVB_TRY(W(h, q + "attention.v_proj_weight", CVB_F32, (int64_t)E * Wd, &wv));
+        CVB_TRY(W(h, q + "attention.in_proj_bias", CVB_F32, 3 * E, &bw.b_in));
+        CVB_TRY(W(h, q + "attention.out_proj.weight", CVB_F32, (int64_t)E * E, &bw.wo));
+        CVB_TRY(W(h, q + "attention.out_proj.bias", CVB_F32, E, &bw.bo));
+        CVB_TRY(W(h, q + "mlp.fc1.weight", CVB_F32, (int64_t)E * E, &bw.fc1_w));
+        CVB_TRY(W(h, q + "mlp.fc1.bias", CVB_F32, E, &bw.fc1_b));
+        CVB_TRY(W(h, q + "mlp.fc2.weight", CVB_F32, (int64_t)E * E, &bw.fc2_w));
+        CVB_TRY(W(h, q + "mlp.fc2.bias", CVB_F32, E, &bw.fc2_b));
+        CVB_TRY(W(h, q + "q_layer_norm.weight", CVB_F32, E, &bw.qln_w));
+        CVB_TRY(W(h, q + "q_layer_norm.bias", CVB_F32, E, &bw.qln_b));
+        CVB_TRY(W(h, q + "layer_norm.weight", CVB_F32, E, &bw.ln_w));
+        CVB_TRY(W(h, q + "layer_norm.bias", CVB_F32, E, &bw.ln_b));
+        CVB_CUDA(cudaMemcpyAsync(wdst + (size_t)(i * 2) * E * Wd, wk, (size_t)E * Wd * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st));
+        CVB_CUDA(cudaMemcpyAsync(wdst + (size_t)(i * 2 + 1) * E * Wd, wv, (size_t)E * Wd * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st));
+        CVB_CUDA(cudaMemcpyAsync(bdst + (size_t)(i * 2) * E, bw.b_in + E, (size_t)2 * E * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st));
+      }
+    }
+    ItFinal& f = itf[m];
+    f.text_tok = s.ttok + (size_t)m * E, f.vision_tok = s.vtok + (size_t)m * E, f.out = s.it + (size_t)m * E;
+    CVB_TRY(W(h, b + "input_projection.weight", CVB_F32, (int64_t)E * 2 * E, &f.w));
+    CVB_TRY(W(h, b + "input_projection.bias", CVB_F32, E, &f.b));
+    Mw.traj.resize(c.vf_traj_layers);
+    for (int i = 0; i < c.vf_traj_layers; ++i) {
+      const std::string q = b + "trajectory_encoder.layers." + std::to_string(i) + ".";
+      TrajLayer& T = Mw.traj[i];
+      CVB_TRY(W(h, q + "self_attn.in_proj_weight", CVB_F32, (int64_t)3 * E * E, &T.w_in));
+      CVB_TRY(W(h, q + "self_attn.in_proj_bias", CVB_F32, 3 * E, &T.b_in));
+      CVB_TRY(W(h, q + "self_attn.out_proj.weight", CVB_F32, (int64_t)E * E, &T.wo));
+      CVB_TRY(W(h, q + "self_attn.out_proj.bias", CVB_F32, E, &T.bo));
+      CVB_TRY(W(h, q + "linear1.weight", CVB_F32, (int64_t)c.vf_traj_ff * E, &T.w1));
+      CVB_TRY(W(h, q + "linear1.bias", CVB_F32, c.vf_traj_ff, &T.b1));
+      CVB_TRY(W(h, q + "linear2.weight", CVB_F32, (int64_t)c.vf_traj_ff * E, &T.w2));
+      CVB_TRY(W(h, q + "linear2.bias", CVB_F32, E, &T.b2));
+      CVB_TRY(W(h, q + "norm1.weight", CVB_F32, E, &T.n1w));
+      CVB_TRY(W(h, q + "norm1.bias", CVB_F32, E, &T.n1b));
+      CVB_TRY(W(h, q + "norm2.weight", CVB_F32, E, &T.n2w));
+      CVB_TRY(W(h, q + "norm2.bias", CVB_F32, E, &T.n2b));
+    }
+  }
+  CVB_TRY(dalloc_t(h, &s.chains, chains.size()));
+  CVB_TRY(dalloc_t(h, &s.itf, itf.size()));
+  CVB_CUDA(cudaMemcpyAsync(s.chains, chains.data(), chains.size() * sizeof(PoolChain), cudaMemcpyHostToDevice, st));
+  CVB_CUDA(cudaMemcpyAsync(s.itf, itf.data(), itf.size() * sizeof(ItFinal), cudaMemcpyHostToDevice, st));
+  CVB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+void verifier_destroy(cvb_handle* h) {
+  delete h->vf;
+  h->vf = nullptr;
+}
+
+// pre-norm transformer block stack on bf16 rows; `stop_after_attn_proj` implements the hook on
+// visual.trunk.blocks[-1].attn (the last block's attention output BEFORE the residual).
+static int run_blocks(cudaStream_t st, VerifierState& s, const std::vector<TrunkBlock>& blocks, bf16* hbuf, int T,
+                      int Wd, int heads, int mlp, bool last_is_attn_only, bf16* attn_only_out) {
+  const int hd = Wd / heads;
+  for (size_t l = 0; l < blocks.size(); ++l) {
+    const TrunkBlock& B = blocks[l];
+    const bool last = last_is_attn_only && l + 1 == blocks.size();
+    CVB_TRY(layernorm_bf16(st, hbuf, Wd, B.ln1_w, B.ln1_b, s.xv, Wd, T, Wd, 1e-6f));
+    CVB_TRY(gemm(st, s.xv, Wd, B.wqkv, Wd, T, 3 * Wd, Wd, EPI_STORE, s.qkv, 3 * Wd, B.bqkv));
+    AttnCall a;
+    a.q = s.qkv, a.q_row_stride = 3 * Wd;
+    a.k0 = s.qkv + Wd, a.v0 = s.qkv + 2 * Wd, a.kv0_row_stride = 3 * Wd, a.kv0_len = T;
+    a.out = s.att, a.o_row_stride = Wd;
+    a.batches = 1, a.heads = heads, a.kv_heads = heads, a.tq = T, a.head_dim = hd;
+    a.scale = 1.0f / sqrtf(static_cast<float>(hd));
+    CVB_TRY(attention(st, a));
+    if (last) {
+      CVB_TRY(gemm(st, s.att, Wd, B.wo, Wd, T, Wd, Wd, EPI_STORE, attn_only_out, Wd, B.bo));
+      break;
+    }
+    CVB_TRY(gemm(st, s.att, Wd, B.wo, Wd, T, Wd, Wd, EPI_RESID, hbuf, Wd, B.bo, hbuf, Wd));
+    CVB_TRY(layernorm_bf16(st, hbuf, Wd, B.ln2_w, B.ln2_b, s.xv, Wd, T, Wd, 1e-6f));
+    CVB_TRY(gemm(st, s.xv, Wd, B.w1, Wd, T, mlp, Wd, EPI_GELU, s.mlp, mlp, B.b1));
+    CVB_TRY(gemm(st, s.mlp, mlp, B.w2, mlp, T, Wd, mlp, EPI_RESID, hbuf, Wd, B.b2, hbuf, Wd));
+  }
+  return 0;
+}
+
+// image-text heads of every member (N-independent: SURVEY.md F4) from the normalised features Pn / Tn
+static int run_heads_context(cvb_handle* h, cudaStream_t st) {
+  const cvb_config& c = h->cfg;
+  VerifierState& s = *h->vf;
+  const int Wd = c.vf_width, E = c.vf_embed, L = c.vf_pool_layers, M = c.vf_members;
+  const int Np = (c.vf_image / c.vf_patch) * (c.vf_image / c.vf_patch), Tt = c.vf_text_ctx;
+  CVB_TRY(sg(st, s.Tn, Wd, s.wkv_t, Wd, Tt, M * L * 2 * E, Wd, s.kv_t, M * L * 2 * E, s.bkv_t));
+  for (int m = 0; m < M; ++m) {
+    const MemberW& Mw = s.mem[m];
+    float* taf = s.taf + (size_t)m * Tt * Wd;
+    CVB_TRY(sg(st, s.Tn, Wd, s.Pn, Wd, Tt, Np, Wd, s.sim, Np));
+    CVB_TRY(softmax_rows_temp(st, s.sim, Tt, Np, Mw.temp));
+    CVB_TRY(add_f32(st, s.Pn, Mw.pos_emb, s.pe, (long)Np * Wd));
+    CVB_TRY(sg(st, s.sim, Np, s.pe, Wd, Tt, Wd, Np, taf, Wd, nullptr, 0, nullptr, 0, /*w_kn=*/1));
+    CVB_TRY(sg(st, taf, Wd, Mw.wkv_v, Wd, Tt, L * 2 * E, Wd, s.kv_v + (size_t)m * Tt * L * 2 * E, L * 2 * E, Mw.bkv_v));
+  }
+  CVB_TRY(pool_chains(st, s.chains, 2 * M, E, c.vf_pool_heads, Tt));
+  CVB_TRY(it_finalize(st, s.itf, M, E));
+  return 0;
+}
+
+static int run_context(cvb_handle* h, cudaStream_t st) {
+  const cvb_config& c = h->cfg;
+  VerifierState& s = *h->vf;
+  const int Wd = c.vf_width, E = c.vf_embed, L = c.vf_pool_layers, M = c.vf_members;
+  const int Np = (c.vf_image / c.vf_patch) * (c.vf_image / c.vf_patch), Tt = c.vf_text_ctx;
+  // image tower -> patch features (hook output), text tower -> per-token projected features
+  CVB_TRY(im2col_patches(st, s.in_image, s.patches, 3, c.vf_image, c.vf_image, c.vf_patch, s.kpad));
+  CVB_TRY(gemm(st, s.patches, s.kpad, s.w_patch, s.kpad, Np, Wd, s.kpad, EPI_RESID, s.hv, Wd, s.patch_b, s.pos_embed, Wd));
+  CVB_TRY(run_blocks(st, s, s.vis, s.hv, Np, Wd, c.vf_heads, c.vf_mlp, true, s.pfeat));
+  CVB_TRY(embed_tokens_pos(st, s.tok_emb, s.txt_pos, s.in_tokens, s.ht, Tt, Wd));
+  CVB_TRY(run_blocks(st, s, s.txt, s.ht, Tt, Wd, c.vf_heads, c.vf_mlp, false, nullptr));
+  CVB_TRY(layernorm_bf16(st, s.ht, Wd, s.lnf_w, s.lnf_b, s.xv, Wd, Tt, Wd, 1e-6f));
+  CVB_TRY(gemm(st, s.xv, Wd, s.wproj, Wd, Tt, Wd, Wd, EPI_STORE, s.tfeat, Wd, s.bproj));
+  CVB_TRY(l2norm_rows_bf16_to_f32(st, s.pfeat, Wd, s.Pn, Np, Wd));
+  CVB_TRY(l2norm_rows_bf16_to_f32(st, s.tfeat, Wd, s.Tn, Tt, Wd));
+  CVB_TRY(run_heads_context(h, st));
+  return 0;
+}
+
+static int run_trajectories(cvb_handle* h, cudaStream_t st, int N) {
+  const cvb_config& c = h->cfg;
+  VerifierState& s = *h->vf;
+  const int E = c.vf_embed, M = c.vf_members, S = c.vf_history, A = c.vf_action_dim, FF = c.vf_traj_ff;
+  const int rows = N * S;
+  for (int m = 0; m < M; ++m) {
+    const MemberW& Mw = s.mem[m];
+    CVB_TRY(sg(st, s.in_traj, A, Mw.w_ss, A, rows, E, A, s.tx, E, Mw.b_ss));
+    for (const TrajLayer& T : Mw.traj) {
+      CVB_TRY(sg(st, s.tx, E, T.w_in, E, rows, 3 * E, E, s.tqkv, 3 * E, T.b_in));
+      CVB_TRY(traj_attention(st, s.tqkv, s.in_traj, s.tatt, N, S, E, c.vf_pool_heads, A, -5.0f));
+      CVB_TRY(sg(st, s.tatt, E, T.wo, E, rows, E, E, s.ty, E, T.bo));
+      CVB_TRY(layernorm_f32(st, s.ty, s.tx, T.n1w, T.n1b, s.tx, rows, E, 1e-5f));
+      CVB_TRY(sg(st, s.tx, E, T.w1, E, rows, FF, E, s.tff, FF, T.b1, SACT_RELU));
+      CVB_TRY(sg(st, s.tff, FF, T.w2, FF, rows, E, FF, s.ty, E, T.b2));
+      CVB_TRY(layernorm_f32(st, s.ty, s.tx, T.n2w, T.n2b, s.tx, rows, E, 1e-5f));
+    }
+    CVB_TRY(masked_mean_l2norm(st, s.tx, s.in_traj, s.act + (size_t)m * N * E, N, S, E, A, -5.0f));
+  }
+  return 0;
+}
+
+int verifier_score(cvb_handle* h, const float* image, const int64_t* tokens, const float* traj, int N, int R, int K,
+                   float* scores, float* group_mean, int32_t* best_idx, float* best_score, int recompute_context,
+                   cudaStream_t st) {
+  const cvb_config& c = h->cfg;
+  CVB_REQUIRE(h->finalized && h->vf != nullptr, "verifier not configured (vf_members == 0?) or not finalized");
+  VerifierState& s = *h->vf;
+  CVB_REQUIRE(N >= 1 && N <= c.max_rephrases * c.max_samples, "N out of range");
+  CVB_REQUIRE(R == 0 || R * K == N, "R*K must equal N");
+  if (recompute_context || !s.context_valid) {
+    CVB_REQUIRE(image != nullptr && tokens != nullptr, "image / tokens required to compute the context");
+    CVB_CUDA(cudaMemcpyAsync(s.in_image, image, (size_t)3 * c.vf_image * c.vf_image * sizeof(float),
+                             cudaMemcpyDeviceToDevice, st));
+    CVB_CUDA(cudaMemcpyAsync(s.in_tokens, tokens, c.vf_text_ctx * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    CVB_TRY(run_context(h, st));
+    s.context_valid = true;
+  }
+  CVB_CUDA(cudaMemcpyAsync(s.in_traj, traj, (size_t)N * c.vf_history * c.vf_action_dim * sizeof(float),
+                           cudaMemcpyDeviceToDevice, st));
+  CVB_TRY(run_trajectories(h, st, N));
+  CVB_TRY(fuse_score_select(st, s.it, s.act, c.vf_members, N, c.vf_embed, scores, R, K, group_mean, best_idx,
+                            best_score, R > 0 ? 1 : 0));
+  return 0;
+}
+
+int64_t verifier_debug_copy(cvb_handle* h, const std::string& name, void* dst, int64_t max_bytes, cudaStream_t st) {
+  if (h->vf == nullptr) return -1;
+  const cvb_config& c = h->cfg;
+  VerifierState& s = *h->vf;
+  const int Np = (c.vf_image / c.vf_patch) * (c.vf_image / c.vf_patch);
+  const void* src = nullptr;
+  int64_t bytes = 0;
+  if (name == "vf_patch_features") {
+    src = s.Pn, bytes = (int64_t)Np * c.vf_width * 4;
+  } else if (name == "vf_text_features") {
+    src = s.Tn, bytes = (int64_t)c.vf_text_ctx * c.vf_width * 4;
+  } else if (name == "vf_it_emb") {
+    src = s.it, bytes = (int64_t)c.vf_members * c.vf_embed * 4;
+  } else if (name == "vf_act_emb") {
+    src = s.act, bytes = (int64_t)c.vf_members * c.max_rephrases * c.max_samples * c.vf_embed * 4;
+  } else {
+    return -1;
+  }
+  if (bytes > max_bytes) bytes = max_bytes;
+  if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return -2;
+  return bytes;
+}
+
+// test hook: overwrite the normalised trunk features (lets tests check the heads in isolation)
+int verifier_set_features(cvb_handle* h, const float* patch, const float* text, cudaStream_t st) {
+  CVB_REQUIRE(h->vf != nullptr, "verifier not configured");
+  const cvb_config& c = h->cfg;
+  VerifierState& s = *h->vf;
+  const int Wd = c.vf_width;
+  const int Np = (c.vf_image / c.vf_patch) * (c.vf_image / c.vf_patch), Tt = c.vf_text_ctx;
+  CVB_CUDA(cudaMemcpyAsync(s.Pn, patch, (size_t)Np * Wd * 4, cudaMemcpyDeviceToDevice, st));
+  CVB_CUDA(cudaMemcpyAsync(s.Tn, text, (size_t)Tt * Wd * 4, cudaMemcpyDeviceToDevice, st));
+  CVB_TRY(run_heads_context(h, st));
+  s.context_valid = true;
+  return 0;
+}
+
 }  // namespace cvb

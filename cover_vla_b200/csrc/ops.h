@@ -45,6 +45,7 @@ struct SgemmCall {
   long ldr = 0;
   int act = 0;
   const float* row_bias = nullptr;  // optional second bias [N] (e.g. the per-step time vector)
+  int w_kn = 0;       // 1: W is [K, N] row-major (C = A @ W) instead of [N, K]
   int out_group = 0;  // >0: output row m lands at (m / g) * (g + 1) + 1 + m % g (suffix layout)
 };
 int sgemm_f32(cudaStream_t st, const SgemmCall& c);

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
                                                     const float* __restrict__ bias,
                                                     const float* __restrict__ row_bias,
                                                     const float* __restrict__ resid, long ldr,
-                                                    int act, int out_group) {
+                                                    int act, int out_group, int w_kn) {
   __shared__ float As[TK][TM + 4];
   __shared__ float Ws[TK][TN + 4];
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
@@ -54,7 +54,13 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
           if (kk + e < K) av[e] = A[am * lda + kk + e];
       }
     }
-    if (wn < N) {
+    if (w_kn) {
+      // W given as [K, N] row-major (plain A @ B): this thread loads 4 consecutive n of one k
+      const int wk = k0 + threadIdx.x / 16, wn4 = n0 + (threadIdx.x % 16) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (wk < K && wn4 + e < N) wv[e] = W[wk * ldw + wn4 + e];
+    } else if (wn < N) {
       if (vec_ok && kk + 3 < K) {
         const float4 t = *reinterpret_cast<const float4*>(W + wn * ldw + kk);
         wv[0] = t.x, wv[1] = t.y, wv[2] = t.z, wv[3] = t.w;
@@ -68,7 +74,10 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       As[lc + e][lr] = av[e];
-      Ws[lc + e][lr] = wv[e];
+      if (w_kn)
+        Ws[threadIdx.x / 16][(threadIdx.x % 16) * 4 + e] = wv[e];
+      else
+        Ws[lc + e][lr] = wv[e];
     }
     __syncthreads();
 #pragma unroll
@@ -107,7 +116,7 @@ int sgemm_f32(cudaStream_t st, const SgemmCall& c) {
   CVB_REQUIRE(c.M > 0 && c.N > 0 && c.K > 0, "empty sgemm");
   dim3 grid((c.N + TN - 1) / TN, (c.M + TM - 1) / TM);
   sgemm_kernel<<<grid, 256, 0, st>>>(c.A, c.lda, c.W, c.ldw, c.M, c.N, c.K, c.C, c.ldc, c.bias,
-                                     c.row_bias, c.resid, c.ldr, c.act, c.out_group);
+                                     c.row_bias, c.resid, c.ldr, c.act, c.out_group, c.w_kn);
   CVB_CUDA(cudaGetLastError());
   return 0;
 }

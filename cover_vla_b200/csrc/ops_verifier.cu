@@ -1,0 +1,401 @@
+// Verifier-specific kernels (all fp32, as the reference keeps everything after the trunk hooks in
+// float32 - finetune_trajectory_bridge_ddp.py:329,352).  See verifier_kernels.h for reference lines.
+#include "host_common.h"
+#include "ptx.cuh"
+#include "verifier_kernels.h"
+
+namespace cvb {
+
+namespace {
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float wmax(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float bsum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = wsum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float t = (lane < nw) ? red[lane] : 0.f;
+  return wsum(t);
+}
+__device__ __forceinline__ float bmax(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = wmax(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float t = (lane < nw) ? red[lane] : -INFINITY;
+  return wmax(t);
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+__global__ void embed_tokens_pos_kernel(const bf16* __restrict__ table, const bf16* __restrict__ pos,
+                                        const int64_t* __restrict__ tok, bf16* __restrict__ out, int width) {
+  const int t = blockIdx.x;
+  const bf16* src = table + tok[t] * width;
+  const bf16* pp = pos + static_cast<long>(t) * width;
+  for (int i = threadIdx.x; i < width; i += blockDim.x)
+    out[static_cast<long>(t) * width + i] =
+        __float2bfloat16_rn(__bfloat162float(src[i]) + __bfloat162float(pp[i]));
+}
+int embed_tokens_pos(cudaStream_t st, const bf16* table, const bf16* pos, const int64_t* tok, bf16* out,
+                     int tokens, int width) {
+  embed_tokens_pos_kernel<<<tokens, 256, 0, st>>>(table, pos, tok, out, width);
+  CVB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// y[r,:] = float(x[r,:]) / ||float(x[r,:])||_2
+__global__ void l2norm_bf16_kernel(const bf16* __restrict__ x, long ldx, float* __restrict__ y, int width) {
+  __shared__ float red[32];
+  const bf16* xr = x + blockIdx.x * ldx;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < width; i += blockDim.x) {
+    const float v = __bfloat162float(xr[i]);
+    ss += v * v;
+  }
+  const float nrm = sqrtf(bsum(ss, red));
+  for (int i = threadIdx.x; i < width; i += blockDim.x)
+    y[static_cast<long>(blockIdx.x) * width + i] = __bfloat162float(xr[i]) / nrm;
+}
+int l2norm_rows_bf16_to_f32(cudaStream_t st, const bf16* x, long ldx, float* y, int rows, int width) {
+  l2norm_bf16_kernel<<<rows, 256, 0, st>>>(x, ldx, y, width);
+  CVB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// in-place row softmax of x / clamp(*temp, 0, 100)
+__global__ void softmax_temp_kernel(float* __restrict__ x, int cols, const float* __restrict__ temp) {
+  __shared__ float red[32];
+  float* xr = x + static_cast<long>(blockIdx.x) * cols;
+  const float t = fminf(fmaxf(*temp, 0.f), 100.f);
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) m = fmaxf(m, xr[i] / t);
+  m = bmax(m, red);
+  float s = 0.f;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) s += expf(xr[i] / t - m);
+  s = bsum(s, red);
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) xr[i] = expf(xr[i] / t - m) / s;
+}
+int softmax_rows_temp(cudaStream_t st, float* x, int rows, int cols, const float* temp_dev) {
+  softmax_temp_kernel<<<rows, 256, 0, st>>>(x, cols, temp_dev);
+  CVB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, long n) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a[i] + b[i];
+}
+int add_f32(cudaStream_t st, const float* a, const float* b, float* y, long n) {
+  add_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b, y, n);
+  CVB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// AttentionPooling with one learned query (model.py:76-112): the whole 4-block chain for one pooling
+// in ONE CTA (K/V projections of all blocks are precomputed by one GEMM since they do not depend on q).
+namespace {
+__device__ void matvec(float* __restrict__ out, const float* __restrict__ W, const float* __restrict__ in,
+                       const float* __restrict__ bias, int n_out, int n_in) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int o = warp; o < n_out; o += nw) {
+    const float* wr = W + static_cast<long>(o) * n_in;
+    float acc = 0.f;
+    for (int i = lane; i < n_in; i += 32) acc = fmaf(wr[i], in[i], acc);
+    acc = wsum(acc);
+    if (lane == 0) out[o] = acc + (bias != nullptr ? bias[o] : 0.f);
+  }
+  __syncthreads();
+}
+__device__ void layernorm_vec(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ w,
+                              const float* __restrict__ b, int n, float* red) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += in[i];
+  const float mean = bsum(s, red) / n;
+  float vs = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) vs += (in[i] - mean) * (in[i] - mean);
+  const float rstd = 1.0f / sqrtf(bsum(vs, red) / n + 1e-5f);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = (in[i] - mean) * rstd * w[i] + b[i];
+  __syncthreads();
+}
+}  // namespace
+
+__global__ void __launch_bounds__(512) pool_chain_kernel(const PoolChain* __restrict__ chains) {
+  extern __shared__ float sm[];
+  __shared__ float red[32];
+  const PoolChain& c = chains[blockIdx.x];
+  const int E = c.embed, H = c.heads, hd = E / H, T = c.tokens;
+  float* q = sm;             // [E]
+  float* a = q + E;          // [E]
+  float* b = a + E;          // [E]
+  float* prob = b + E;       // [H * T]
+  for (int i = threadIdx.x; i < E; i += blockDim.x) q[i] = c.query[i];
+  __syncthreads();
+  const float qscale = sqrtf(1.0f / static_cast<float>(hd));
+  for (int l = 0; l < c.layers; ++l) {
+    const PoolBlockW& w = c.blk[l];
+    layernorm_vec(q, q, w.qln_w, w.qln_b, E, red);         // q = q_layer_norm(q)
+    matvec(a, w.wq, q, w.b_in, E, E);                       // a = Wq q + bq
+    for (int i = threadIdx.x; i < E; i += blockDim.x) a[i] *= qscale;
+    __syncthreads();
+    const float* Kp = c.kv + static_cast<long>(l) * 2 * E;  // K_l at cols [l*2E, l*2E+E), V_l after it
+    const float* Vp = Kp + E;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int h = warp; h < H; h += nw) {
+      float mx = -INFINITY;
+      for (int j = lane; j < T; j += 32) {
+        const float* kr = Kp + static_cast<long>(j) * c.kv_ld + h * hd;
+        float s = 0.f;
+        for (int d = 0; d < hd; ++d) s = fmaf(a[h * hd + d], kr[d], s);
+        prob[h * T + j] = s;
+        mx = fmaxf(mx, s);
+      }
+      mx = wmax(mx);
+      float sum = 0.f;
+      for (int j = lane; j < T; j += 32) {
+        const float e = expf(prob[h * T + j] - mx);
+        prob[h * T + j] = e;
+        sum += e;
+      }
+      sum = wsum(sum);
+      __syncwarp();
+      for (int d = lane; d < hd; d += 32) {
+        float o = 0.f;
+        for (int j = 0; j < T; ++j) o = fmaf(prob[h * T + j] / sum, Vp[static_cast<long>(j) * c.kv_ld + h * hd + d], o);
+        b[h * hd + d] = o;
+      }
+    }
+    __syncthreads();
+    matvec(a, w.wo, b, w.bo, E, E);                         // attn_out
+    for (int i = threadIdx.x; i < E; i += blockDim.x) q[i] = q[i] + a[i];
+    __syncthreads();
+    layernorm_vec(q, q, w.ln_w, w.ln_b, E, red);            // q = layer_norm(q + attn)
+    matvec(a, w.fc1_w, q, w.fc1_b, E, E);
+    for (int i = threadIdx.x; i < E; i += blockDim.x)
+      a[i] = 0.5f * a[i] * (1.0f + erff(a[i] * 0.70710678118654752440f));
+    __syncthreads();
+    matvec(b, w.fc2_w, a, w.fc2_b, E, E);
+    for (int i = threadIdx.x; i < E; i += blockDim.x) q[i] = q[i] + b[i];
+    __syncthreads();
+  }
+  layernorm_vec(a, q, c.fin_w, c.fin_b, E, red);
+  for (int i = threadIdx.x; i < E; i += blockDim.x) c.out[i] = a[i];
+}
+
+int pool_chains(cudaStream_t st, const PoolChain* chains_dev, int n_chains, int embed, int heads, int tokens) {
+  const size_t smem = (3 * embed + heads * tokens) * sizeof(float);
+  pool_chain_kernel<<<n_chains, 512, smem, st>>>(chains_dev);
+  CVB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// it[m] = normalize(W_ip . cat[text_tok[m], vision_tok[m]] + b_ip)      (efficient_ensemble_merged.py:220-223)
+__global__ void __launch_bounds__(256) it_finalize_kernel(const ItFinal* __restrict__ items, int E) {
+  extern __shared__ float sm[];
+  __shared__ float red[32];
+  const ItFinal& f = items[blockIdx.x];
+  float* in = sm;       // [2E]
+  float* out = sm + 2 * E;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    in[i] = f.text_tok[i];
+    in[E + i] = f.vision_tok[i];
+  }
+  __syncthreads();
+  matvec(out, f.w, in, f.b, E, 2 * E);
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) ss += out[i] * out[i];
+  const float nrm = sqrtf(bsum(ss, red));
+  for (int i = threadIdx.x; i < E; i += blockDim.x) f.out[i] = out[i] / nrm;
+}
+int it_finalize(cudaStream_t st, const ItFinal* items_dev, int members, int embed) {
+  it_finalize_kernel<<<members, 256, 3 * embed * sizeof(float), st>>>(items_dev, embed);
+  CVB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// nn.TransformerEncoderLayer self-attention over a <=32-step action history with key-padding mask
+// (efficient_ensemble_merged.py:229-235): one CTA per candidate, one warp per head, lane = query step.
+__global__ void __launch_bounds__(256) traj_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ traj,
+                                                             float* __restrict__ out, int S, int E, int H, int adim,
+                                                             float pad_value) {
+  const int n = blockIdx.x, hd = E / H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  for (int h = warp; h < H; h += nw) {
+    if (lane < S) {
+      const float* qr = qkv + (static_cast<long>(n) * S + lane) * 3 * E + h * hd;
+      float sc[32];
+      float mx = -INFINITY;
+      for (int j = 0; j < S; ++j) {
+        const bool pad = traj[(static_cast<long>(n) * S + j) * adim] == pad_value;
+        const float* kr = qkv + (static_cast<long>(n) * S + j) * 3 * E + E + h * hd;
+        float s = 0.f;
+        for (int d = 0; d < hd; ++d) s = fmaf(qr[d], kr[d], s);
+        s = pad ? -INFINITY : s * scale;
+        sc[j] = s;
+        mx = fmaxf(mx, s);
+      }
+      float sum = 0.f;
+      for (int j = 0; j < S; ++j) {
+        sc[j] = sc[j] == -INFINITY ? 0.f : expf(sc[j] - mx);
+        sum += sc[j];
+      }
+      float* orow = out + (static_cast<long>(n) * S + lane) * E + h * hd;
+      for (int d = 0; d < hd; ++d) {
+        float o = 0.f;
+        for (int j = 0; j < S; ++j)
+          o = fmaf(sc[j] / sum, qkv[(static_cast<long>(n) * S + j) * 3 * E + 2 * E + h * hd + d], o);
+        orow[d] = o;
+      }
+    }
+  }
+}
+int traj_attention(cudaStream_t st, const float* qkv, const float* traj, float* out, int n_cand, int S, int E, int H,
+                   int adim, float pad_value) {
+  CVB_REQUIRE(S <= 32, "history length must be <= 32");
+  traj_attention_kernel<<<n_cand, 256, 0, st>>>(qkv, traj, out, S, E, H, adim, pad_value);
+  CVB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// masked mean over non-padded steps, then L2 normalise        (efficient_ensemble_merged.py:236-245)
+__global__ void __launch_bounds__(256) masked_mean_l2_kernel(const float* __restrict__ x, const float* __restrict__ traj,
+                                                             float* __restrict__ out, int S, int E, int adim,
+                                                             float pad_value) {
+  __shared__ float red[32];
+  const int n = blockIdx.x;
+  float cnt = 0.f;
+  for (int j = 0; j < S; ++j) cnt += (traj[(static_cast<long>(n) * S + j) * adim] == pad_value) ? 0.f : 1.f;
+  cnt = fmaxf(cnt, 1e-9f);
+  float ss = 0.f;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < S; ++j) {
+      const float keep = (traj[(static_cast<long>(n) * S + j) * adim] == pad_value) ? 0.f : 1.f;
+      s += x[(static_cast<long>(n) * S + j) * E + e] * keep;
+    }
+    s = s / cnt;
+    out[static_cast<long>(n) * E + e] = s;
+    ss += s * s;
+  }
+  const float nrm = sqrtf(bsum(ss, red));
+  for (int e = threadIdx.x; e < E; e += blockDim.x) out[static_cast<long>(n) * E + e] /= nrm;
+}
+int masked_mean_l2norm(cudaStream_t st, const float* x, const float* traj, float* out, int n_cand, int S, int E,
+                       int adim, float pad_value) {
+  masked_mean_l2_kernel<<<n_cand, 256, 0, st>>>(x, traj, out, S, E, adim, pad_value);
+  CVB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused ensemble fusion + scores (efficient_ensemble_merged.py:404-414): one warp per candidate,
+// warp-shuffle reductions; then (optionally) group-mean / argmax selection in the same launch.
+__device__ void select_block(const float* __restrict__ scores, int R, int K, float* __restrict__ group_mean,
+                             int* __restrict__ best_idx, float* __restrict__ best_score, float* sh_mean) {
+  // group means (efficient_ensemble_merged.py:427-431)
+  for (int g = threadIdx.x; g < R; g += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s += scores[g * K + k];
+    const float m = s / static_cast<float>(K);
+    sh_mean[g] = m;
+    if (group_mean != nullptr) group_mean[g] = m;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int bg = 0;
+    for (int g = 1; g < R; ++g)
+      if (sh_mean[g] > sh_mean[bg]) bg = g;  // first maximum wins ties, like torch.max
+    int bk = 0;
+    for (int k = 1; k < K; ++k)
+      if (scores[bg * K + k] > scores[bg * K + bk]) bk = k;
+    *best_idx = bg * K + bk;
+    *best_score = scores[bg * K + bk];
+  }
+}
+
+__global__ void __launch_bounds__(1024) fuse_score_select_kernel(const float* __restrict__ it, const float* __restrict__ act,
+                                                                 int M, int N, int E, float* __restrict__ scores, int R,
+                                                                 int K, float* __restrict__ group_mean,
+                                                                 int* __restrict__ best_idx, float* __restrict__ best_score,
+                                                                 int do_select) {
+  extern __shared__ float sm[];
+  __shared__ float red[32];
+  float* fit = sm;          // [E]
+  float* sh_mean = sm + E;  // [R]
+  float ss = 0.f;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    float s = 0.f;
+    for (int m = 0; m < M; ++m) s += it[static_cast<long>(m) * E + e];
+    s = s / static_cast<float>(M);
+    fit[e] = s;
+    ss += s * s;
+  }
+  const float nrm = sqrtf(bsum(ss, red));
+  __syncthreads();
+  for (int e = threadIdx.x; e < E; e += blockDim.x) fit[e] = fit[e] / nrm;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int n = warp; n < N; n += nw) {
+    float an = 0.f;
+    for (int e = lane; e < E; e += 32) {
+      float s = 0.f;
+      for (int m = 0; m < M; ++m) s += act[(static_cast<long>(m) * N + n) * E + e];
+      s = s / static_cast<float>(M);
+      an += s * s;
+    }
+    an = sqrtf(wsum(an));
+    float dot = 0.f;
+    for (int e = lane; e < E; e += 32) {
+      float s = 0.f;
+      for (int m = 0; m < M; ++m) s += act[(static_cast<long>(m) * N + n) * E + e];
+      s = s / static_cast<float>(M);
+      dot = fmaf(fit[e], s / an, dot);
+    }
+    dot = wsum(dot);
+    if (lane == 0) scores[n] = dot;
+  }
+  __syncthreads();
+  if (do_select) {
+    __threadfence_block();
+    select_block(scores, R, K, group_mean, best_idx, best_score, sh_mean);
+  }
+}
+int fuse_score_select(cudaStream_t st, const float* it, const float* act, int M, int N, int E, float* scores, int R,
+                      int K, float* group_mean, int* best_idx, float* best_score, int do_select) {
+  CVB_REQUIRE(!do_select || R * K == N, "R*K must equal the number of candidates");
+  fuse_score_select_kernel<<<1, 1024, (E + R + 1) * sizeof(float), st>>>(it, act, M, N, E, scores, R, K, group_mean,
+                                                                         best_idx, best_score, do_select);
+  CVB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ scores, int R, int K,
+                                                     float* __restrict__ group_mean, int* __restrict__ best_idx,
+                                                     float* __restrict__ best_score) {
+  extern __shared__ float sm[];
+  select_block(scores, R, K, group_mean, best_idx, best_score, sm);
+}
+int select_best(cudaStream_t st, const float* scores, int R, int K, float* group_mean, int* best_idx,
+                float* best_score) {
+  select_kernel<<<1, 256, (R + 1) * sizeof(float), st>>>(scores, R, K, group_mean, best_idx, best_score);
+  CVB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cvb

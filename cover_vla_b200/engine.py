@@ -116,6 +116,9 @@ class Engine:
         L.cvb_pi0_sample.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.cvb_debug_copy.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.cvb_debug_copy.restype = C.c_int64
+        L.cvb_verifier_score.argtypes = [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
+        L.cvb_verifier_set_features.argtypes = [C.c_void_p] * 4
+        L.cvb_select.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 
     # ------------------------------------------------------------------ weights
     def required_weights(self) -> list[str]:
@@ -172,6 +175,45 @@ class Engine:
                                                _lib.ptr(state), _lib.ptr(noise), R, K, _lib.ptr(out),
                                                _lib.stream_ptr()))
         return out
+
+    # ------------------------------------------------------------------ verifier
+    def verifier_score(self, image, text_tokens, traj, R: int, K: int, recompute_context: bool = True):
+        """image f32 [3,S,S] (or None to reuse the context); text_tokens i64 [ctx]; traj f32 [N,H,A] left-padded
+        with -5.  Returns device tensors (scores [N], group_mean [R], best_idx i32 [1], best_score [1]).
+        R == 0: scores only."""
+        cfg = self.cfg
+        N = traj.shape[0]
+        assert traj.dtype == torch.float32 and tuple(traj.shape[1:]) == (cfg.vf_history, cfg.vf_action_dim)
+        assert traj.is_cuda and traj.is_contiguous()
+        if image is not None:
+            assert image.dtype == torch.float32 and image.numel() == 3 * cfg.vf_image ** 2 and image.is_contiguous()
+            assert text_tokens.dtype == torch.int64 and text_tokens.numel() == cfg.vf_text_ctx
+        scores = torch.empty(N, dtype=torch.float32, device=self.device)
+        gmean = torch.empty(max(R, 1), dtype=torch.float32, device=self.device)
+        bidx = torch.zeros(1, dtype=torch.int32, device=self.device)
+        bscore = torch.zeros(1, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cvb_verifier_score(self._h, _lib.ptr(image), _lib.ptr(text_tokens), _lib.ptr(traj),
+                                                   N, R, K, _lib.ptr(scores), _lib.ptr(gmean), _lib.ptr(bidx),
+                                                   _lib.ptr(bscore), int(recompute_context), _lib.stream_ptr()))
+        return scores, gmean, bidx, bscore
+
+    def verifier_set_features(self, patch, text):
+        assert patch.dtype == torch.float32 and text.dtype == torch.float32 and patch.is_cuda and text.is_cuda
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cvb_verifier_set_features(self._h, _lib.ptr(patch.contiguous()),
+                                                          _lib.ptr(text.contiguous()), _lib.stream_ptr()))
+
+    def select(self, scores, R: int, K: int):
+        """group-mean -> argmax group -> argmax inside it over a (gathered) fp32 score vector."""
+        assert scores.dtype == torch.float32 and scores.is_cuda and scores.numel() == R * K
+        gmean = torch.empty(R, dtype=torch.float32, device=scores.device)
+        bidx = torch.zeros(1, dtype=torch.int32, device=scores.device)
+        bscore = torch.zeros(1, dtype=torch.float32, device=scores.device)
+        with torch.cuda.device(scores.device):
+            _lib.check(self.lib.cvb_select(_lib.ptr(scores.contiguous()), R, K, _lib.ptr(gmean), _lib.ptr(bidx),
+                                           _lib.ptr(bscore), _lib.stream_ptr()))
+        return gmean, bidx, bscore
 
     def debug(self, name: str, shape, dtype) -> torch.Tensor:
         out = torch.zeros(shape, dtype=dtype, device=self.device)

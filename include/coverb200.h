@@ -99,6 +99,25 @@ CVB_API int cvb_pi0_sample(cvb_handle* h, const float* image, const int64_t* lan
                            const int32_t* lang_len, const float* state, const float* noise, int R,
                            int K, float* actions, void* stream);
 
+/* Score N = R*K candidate action histories against ONE (image, instruction) pair and select
+ * (replaces EfficientEnsembleMerged.compute_max_similarity_scores_batch, efficient_ensemble_merged.py:309-454;
+ * the fast path of :330-347 - pair 0 only - is the only one whose result the reference consumes, :422-425).
+ *   image       f32 [3, vf_image, vf_image]  (open_clip-preprocessed, normalised)
+ *   text_tokens i64 [vf_text_ctx]
+ *   traj        f32 [N, vf_history, vf_action_dim], left-padded with -5 rows (:379-390)
+ *   scores f32 [N]; group_mean f32 [R] (may be NULL); best_idx i32 [1]; best_score f32 [1]
+ * With R == 0 only the scores are produced (multi-GPU: gather them, then call cvb_select).
+ * recompute_context = 0 reuses the image/text side (trunk + image-text heads) of the previous call. */
+CVB_API int cvb_verifier_score(cvb_handle* h, const float* image, const int64_t* text_tokens, const float* traj,
+                               int N, int R, int K, float* scores, float* group_mean, int32_t* best_idx,
+                               float* best_score, int recompute_context, void* stream);
+/* Test hook: inject normalised trunk features (patch f32 [Np, W], text f32 [ctx, W]) and recompute the
+ * image-text heads, so the fp32 heads can be checked in isolation from the bf16 trunk. */
+CVB_API int cvb_verifier_set_features(cvb_handle* h, const float* patch, const float* text, void* stream);
+/* group-mean -> argmax group -> argmax inside the group over a (gathered) score vector (:417-447). */
+CVB_API int cvb_select(const float* scores, int R, int K, float* group_mean, int32_t* best_idx, float* best_score,
+                       void* stream);
+
 /* Test/diagnostic tap: copy an internal buffer ("image_emb", "prefix_k0", "prefix_vlast", "v0",
  * "time_emb", ...) to dst (device).  Returns the number of bytes copied or a negative error. */
 CVB_API int64_t cvb_debug_copy(cvb_handle* h, const char* name, void* dst, int64_t max_bytes,

@@ -32,3 +32,22 @@ def rel_l2(x, y):
 
 def max_abs(x, y):
     return (x.float().cpu() - y.float().cpu()).abs().max().item()
+
+
+def verifier_config_kwargs(v):
+    return dict(vf_image=v.image, vf_patch=v.patch, vf_width=v.width, vf_layers=v.layers, vf_heads=v.heads,
+                vf_mlp=v.mlp, vf_text_layers=v.text_layers, vf_text_ctx=v.text_ctx, vf_vocab=v.vocab,
+                vf_members=v.members, vf_embed=v.embed, vf_pool_heads=v.pool_heads, vf_pool_layers=v.pool_layers,
+                vf_traj_layers=v.traj_layers, vf_traj_ff=v.traj_ff, vf_history=v.history, vf_action_dim=v.action_dim)
+
+
+def build_full_engine(d, w, v, vw, max_R, max_K, **kw):
+    """pi0 + verifier in one handle."""
+    from cover_vla_b200.engine import Engine
+    eng = Engine(engine_config_from_dims(d, max_R, max_K, **verifier_config_kwargs(v), **kw))
+    for k, t in w.items():
+        eng.bind("model." + k, t.cuda())
+    for k, t in vw.items():
+        eng.bind(k, t.cuda())
+    eng.finalize()
+    return eng

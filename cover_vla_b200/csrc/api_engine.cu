@@ -131,6 +131,11 @@ int cvb_pi0_sample(cvb_handle* h, const float* image, const int64_t* lang_tokens
                          (cudaStream_t)stream);
 }
 
+int cvb_pi0_run_phase(cvb_handle* h, int phase, int R, int K, void* stream) {
+  CVB_REQUIRE(h != nullptr, "null handle");
+  return cvb::pi0_run_phase(h, phase, R, K, (cudaStream_t)stream);
+}
+
 int64_t cvb_debug_copy(cvb_handle* h, const char* name, void* dst, int64_t max_bytes, void* stream) {
   if (h == nullptr || name == nullptr) return -1;
   if (std::string(name).rfind("vf_", 0) == 0)

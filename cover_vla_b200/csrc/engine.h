@@ -104,6 +104,7 @@ void pi0_required_weights(const cvb_config& c, std::vector<WeightSpec>* out);
 int pi0_finalize(cvb_handle* h, cudaStream_t st);
 int pi0_sample(cvb_handle* h, const float* image, const int64_t* tokens, const int32_t* lang_len,
                const float* state, const float* noise, int R, int K, float* actions, cudaStream_t st);
+int pi0_run_phase(cvb_handle* h, int phase, int R, int K, cudaStream_t st);
 int64_t pi0_debug_copy(cvb_handle* h, const std::string& name, void* dst, int64_t max_bytes,
                        cudaStream_t st);
 

@@ -496,6 +496,23 @@ int pi0_sample(cvb_handle* h, const float* image, const int64_t* tokens, const i
   return 0;
 }
 
+// profiling hook: run one phase eagerly on the staged inputs of the last cvb_pi0_sample call
+int pi0_run_phase(cvb_handle* h, int phase, int R, int K, cudaStream_t st) {
+  CVB_REQUIRE(h->finalized, "cvb_finalize() has not been called");
+  CVB_REQUIRE(R >= 1 && R <= h->cfg.max_rephrases && K >= 1 && K <= h->cfg.max_samples, "R/K out of range");
+  switch (phase) {
+    case 0:
+      return run_vision(h, st);
+    case 1:
+      return run_prefix(h, st, R);
+    case 2:
+      return run_denoise(h, st, R, K);
+    default:
+      set_last_error("phase must be 0 (vision), 1 (prefix) or 2 (denoise)");
+      return -1;
+  }
+}
+
 int64_t pi0_debug_copy(cvb_handle* h, const std::string& name, void* dst, int64_t max_bytes,
                        cudaStream_t st) {
   const cvb_config& c = h->cfg;

@@ -114,6 +114,7 @@ class Engine:
         L.cvb_required_weight_name.restype = C.c_char_p
         L.cvb_finalize.argtypes = [C.c_void_p, C.c_void_p]
         L.cvb_pi0_sample.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.cvb_pi0_run_phase.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.cvb_debug_copy.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.cvb_debug_copy.restype = C.c_int64
         L.cvb_verifier_score.argtypes = [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
@@ -175,6 +176,10 @@ class Engine:
                                                _lib.ptr(state), _lib.ptr(noise), R, K, _lib.ptr(out),
                                                _lib.stream_ptr()))
         return out
+
+    def pi0_run_phase(self, phase: int, R: int, K: int):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cvb_pi0_run_phase(self._h, phase, R, K, _lib.stream_ptr()))
 
     # ------------------------------------------------------------------ verifier
     def verifier_score(self, image, text_tokens, traj, R: int, K: int, recompute_context: bool = True):

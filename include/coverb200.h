@@ -99,6 +99,10 @@ CVB_API int cvb_pi0_sample(cvb_handle* h, const float* image, const int64_t* lan
                            const int32_t* lang_len, const float* state, const float* noise, int R,
                            int K, float* actions, void* stream);
 
+/* Profiling hook: re-run one phase (0 vision tower, 1 prefix, 2 denoise loop) eagerly on the inputs staged by
+ * the last cvb_pi0_sample call, so a host can time the phases separately with CUDA events. */
+CVB_API int cvb_pi0_run_phase(cvb_handle* h, int phase, int R, int K, void* stream);
+
 /* Score N = R*K candidate action histories against ONE (image, instruction) pair and select
  * (replaces EfficientEnsembleMerged.compute_max_similarity_scores_batch, efficient_ensemble_merged.py:309-454;
  * the fast path of :330-347 - pair 0 only - is the only one whose result the reference consumes, :422-425).

@@ -50,7 +50,7 @@ def pi0_golden(name: str, R: int, K: int, seed: int = 0):
                image_emb_slice=img_emb[0, ::37, ::29].clone(),
                k0_slice=cache[0]["key_states"][::K, ::11, 0, ::7].clone(),
                vlast_slice=cache[L]["value_states"][::K, ::11, 0, ::7].clone(),
-               lens=inp["lens"], torch_version=torch.__version__)
+               lens=inp["lens"], torch_version=str(torch.__version__))
     OUT.mkdir(parents=True, exist_ok=True)
     torch.save(fix, OUT / f"pi0_{name}_R{R}K{K}.pt")
     print(f"pi0 {name} R={R} K={K}: {time.time() - t0:.1f}s  |actions-noise|max="

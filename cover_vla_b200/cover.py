@@ -1,0 +1,151 @@
+"""One CoVer decision on the device: sample N = R*K action chunks (pi0) -> verifier-format trajectories ->
+ensemble scores -> group-mean / argmax, with no host round trip in between.
+
+This is the body of run_simpler_eval_with_openpi.py:322-409 minus the simulator: `select_action` (:324),
+`process_inputs(verifier_action=True)` (:338), the 1-candidate gate (:344-352) and the N-candidate call
+(:355-363).  The gate needs no second pass: its score is scores[0] of the same launch.
+
+Multi-GPU: candidates shard by REPHRASE - rank g owns rephrases
+[g*R/G, (g+1)*R/G) and all their K samples, so every prefix is computed exactly once globally and group
+means stay rank-local.  The only exchange is an all-gather of N/G fp32 scores (+ the N/G x chunk x 7
+actions so every rank can return the winner); every rank then runs the same select kernel.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import ctypes as C
+import torch
+
+from . import _lib
+from .engine import Engine
+
+# INT-ACT/config/dataset/bridge_statistics.json "action" p01 / p99 (first 6 dims; the gripper is not scaled)
+BRIDGE_ACTION_P01 = (-0.02872725307941437, -0.04170349963009357, -0.026093858778476715,
+                     -0.08092105075716972, -0.09288699507713317, -0.20718276381492615)
+BRIDGE_ACTION_P99 = (0.028309678435325586, 0.040855254605412394, 0.040161586627364146,
+                     0.08192047759890528, 0.07792850524187081, 0.20382574498653397)
+
+
+def format_trajectories(actions, past, history: int, n_future: int, p01=BRIDGE_ACTION_P01, p99=BRIDGE_ACTION_P99,
+                        out=None):
+    """actions f32 [N, chunk, stride>=7] (device) -> verifier trajectories f32 [N, history, 7] (device)."""
+    lib = _lib.load()
+    N, chunk, stride = actions.shape
+    num_past = 0 if past is None else past.shape[0]
+    if out is None:
+        out = torch.empty(N, history, 7, dtype=torch.float32, device=actions.device)
+    a = (C.c_double * 6)(*p01)
+    b = (C.c_double * 6)(*p99)
+    lib.cvb_format_trajectories.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                            C.POINTER(C.c_double), C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_void_p]
+    with torch.cuda.device(actions.device):
+        _lib.check(lib.cvb_format_trajectories(_lib.ptr(actions), N, chunk, stride, a, b, _lib.ptr(past), num_past,
+                                               history, n_future, _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+@dataclass
+class CoverInputs:
+    """Device-resident inputs of one decision."""
+    image: torch.Tensor        # f32 [3, 224, 224] in [-1, 1]
+    lang_tokens: torch.Tensor  # i64 [R, L] (one row per unique rephrase)
+    lang_len: torch.Tensor     # i32 [R]
+    state: torch.Tensor        # f32 [max_state_dim]
+    noise: torch.Tensor        # f32 [R*K, chunk, max_action_dim]
+    vf_image: torch.Tensor     # f32 [3, 384, 384] (verifier preprocessing)
+    vf_tokens: torch.Tensor    # i64 [ctx] (the CURRENT task description)
+    past: torch.Tensor | None = None  # f32 [num_past, 7] verifier-format action history tail
+
+
+class CoverStep:
+    def __init__(self, engine: Engine, samples_per_rephrase: int, n_future: int | None = None,
+                 p01=BRIDGE_ACTION_P01, p99=BRIDGE_ACTION_P99):
+        self.engine = engine
+        self.K = samples_per_rephrase
+        self.n_future = n_future or engine.cfg.chunk_size
+        self.p01, self.p99 = p01, p99
+
+    def sample_and_score(self, x: CoverInputs, select: bool = True):
+        """Asynchronous; returns device tensors (actions, traj, scores, group_mean, best_idx, best_score)."""
+        e = self.engine
+        actions = e.pi0_sample(x.image, x.lang_tokens, x.lang_len, x.state, x.noise, K=self.K)
+        traj = format_trajectories(actions, x.past, e.cfg.vf_history, self.n_future, self.p01, self.p99)
+        R = x.lang_tokens.shape[0]
+        scores, gmean, bidx, bscore = e.verifier_score(x.vf_image, x.vf_tokens, traj, R if select else 0, self.K)
+        return actions, traj, scores, gmean, bidx, bscore
+
+    def __call__(self, x: CoverInputs, gate_threshold: float = 0.1):
+        """Full decision incl. the one D2H read the caller needs: (best_idx, best_score, winner actions [chunk, 7])."""
+        actions, traj, scores, gmean, bidx, bscore = self.sample_and_score(x)
+        # gate (run_simpler_eval_with_openpi.py:344-363): keep candidate 0 when its score clears the threshold
+        use0 = scores[0] >= gate_threshold
+        idx = torch.where(use0, torch.zeros_like(bidx[0]), bidx[0])
+        score = torch.where(use0, scores[0], bscore[0])
+        winner = actions.index_select(0, idx.to(torch.int64).reshape(1))[0, :, :7]
+        packed = torch.cat([idx.to(torch.float32).reshape(1), score.reshape(1), winner.reshape(-1)]).cpu()
+        return int(packed[0]), float(packed[1]), packed[2:].reshape(-1, 7)
+
+
+# ----------------------------------------------------------------------------------------------------
+# rephrase sharding across ranks
+# ----------------------------------------------------------------------------------------------------
+def rephrase_shard(R: int, world_size: int, rank: int) -> tuple[int, int]:
+    """[start, stop) of the rephrases rank owns; contiguous, sizes differ by at most one."""
+    base, rem = divmod(R, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_inputs(x: CoverInputs, K: int, world_size: int, rank: int) -> CoverInputs:
+    R = x.lang_tokens.shape[0]
+    a, b = rephrase_shard(R, world_size, rank)
+    return CoverInputs(image=x.image, lang_tokens=x.lang_tokens[a:b].contiguous(), lang_len=x.lang_len[a:b].contiguous(),
+                       state=x.state, noise=x.noise[a * K:b * K].contiguous(), vf_image=x.vf_image,
+                       vf_tokens=x.vf_tokens, past=x.past)
+
+
+def gather_and_select(local_scores, local_actions, R: int, K: int, select_fn, group=None):
+    """All-gather the per-rank score / action slices (rephrase-major order is preserved because shards are
+    contiguous) and run the same selection on every rank.  Returns (scores [N], actions [N,...], gmean, idx, score)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1:
+        scores, actions = local_scores, local_actions
+    else:
+        sizes = [(rephrase_shard(R, world, r)[1] - rephrase_shard(R, world, r)[0]) * K for r in range(world)]
+        if len(set(sizes)) == 1:
+            scores = torch.empty(R * K, dtype=local_scores.dtype, device=local_scores.device)
+            dist.all_gather_into_tensor(scores, local_scores.contiguous(), group=group)
+            actions = torch.empty((R * K, *local_actions.shape[1:]), dtype=local_actions.dtype, device=local_actions.device)
+            dist.all_gather_into_tensor(actions, local_actions.contiguous(), group=group)
+        else:  # ragged shards (R not divisible by the world size)
+            sl = [torch.empty(s, dtype=local_scores.dtype, device=local_scores.device) for s in sizes]
+            dist.all_gather(sl, local_scores.contiguous(), group=group)
+            scores = torch.cat(sl)
+            al = [torch.empty((s, *local_actions.shape[1:]), dtype=local_actions.dtype, device=local_actions.device) for s in sizes]
+            dist.all_gather(al, local_actions.contiguous(), group=group)
+            actions = torch.cat(al)
+    gmean, idx, score = select_fn(scores, R, K)
+    return scores, actions, gmean, idx, score
+
+
+class ShardedCoverStep:
+    """CoverStep over torch.distributed (one process per GPU, NCCL): each rank samples and scores its own
+    rephrase slice; a single small all-gather collects the scores for the global argmax."""
+
+    def __init__(self, engine: Engine, samples_per_rephrase: int, group=None, **kw):
+        import torch.distributed as dist
+        self.step = CoverStep(engine, samples_per_rephrase, **kw)
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def __call__(self, x: CoverInputs):
+        R, K = x.lang_tokens.shape[0], self.step.K
+        mine = shard_inputs(x, K, self.world, self.rank)
+        if mine.lang_tokens.shape[0] == 0:
+            raise ValueError("more ranks than rephrases: shrink the process group for this decision")
+        actions, traj, scores, *_ = self.step.sample_and_score(mine, select=False)
+        return gather_and_select(scores, actions[:, :, :7].contiguous(), R, K, self.step.engine.select, self.group)

@@ -61,7 +61,7 @@ int cvb_create(const cvb_config* cfg, cvb_handle** out) {
   CVB_REQUIRE(cfg->max_rephrases >= 1 && cfg->max_samples >= 1, "max_rephrases / max_samples must be >= 1");
   cvb_handle* h = new cvb_handle();
   h->cfg = *cfg;
-  cvb::pi0_required_weights(h->cfg, &h->required);
+  if (cfg->layers > 0) cvb::pi0_required_weights(h->cfg, &h->required);
   if (cfg->vf_members > 0) cvb::verifier_required_weights(h->cfg, &h->required);
   *out = h;
   return 0;
@@ -116,7 +116,7 @@ int cvb_finalize(cvb_handle* h, void* stream) {
     }
   }
   cudaStream_t st = (cudaStream_t)stream;
-  CVB_TRY(cvb::pi0_finalize(h, st));
+  if (h->cfg.layers > 0) CVB_TRY(cvb::pi0_finalize(h, st));
   if (h->cfg.vf_members > 0) CVB_TRY(cvb::verifier_finalize(h, st));
   CVB_CUDA(cudaStreamSynchronize(st));
   h->finalized = true;
@@ -154,6 +154,17 @@ int cvb_verifier_score(cvb_handle* h, const float* image, const int64_t* text_to
 int cvb_verifier_set_features(cvb_handle* h, const float* patch, const float* text, void* stream) {
   CVB_REQUIRE(h != nullptr, "null handle");
   return cvb::verifier_set_features(h, patch, text, (cudaStream_t)stream);
+}
+
+int cvb_format_trajectories(const float* actions, int n_cand, int chunk, int action_stride,
+                            const double* p01_host, const double* p99_host, const float* past, int num_past,
+                            int history, int n_future, float* traj, void* stream) {
+  CVB_REQUIRE(actions != nullptr && traj != nullptr && p01_host != nullptr && p99_host != nullptr, "null argument");
+  CVB_REQUIRE(num_past == 0 || past != nullptr, "past actions pointer required when num_past > 0");
+  cvb::FormatStats st;
+  for (int i = 0; i < 6; ++i) st.p01[i] = p01_host[i], st.p99[i] = p99_host[i];
+  return cvb::format_trajectories((cudaStream_t)stream, actions, n_cand, chunk, action_stride, st, past, num_past,
+                                  history, n_future, traj);
 }
 
 int cvb_select(const float* scores, int R, int K, float* group_mean, int32_t* best_idx, float* best_score,

@@ -446,6 +446,7 @@ int pi0_sample(cvb_handle* h, const float* image, const int64_t* tokens, const i
   const cvb_config& c = h->cfg;
   Pi0State& s = h->pi0;
   CVB_REQUIRE(h->finalized, "cvb_finalize() has not been called");
+  CVB_REQUIRE(c.layers > 0, "this handle was created without the pi0 model (layers == 0)");
   CVB_REQUIRE(R >= 1 && R <= c.max_rephrases, "R out of range (max_rephrases)");
   CVB_REQUIRE(K >= 1 && K <= c.max_samples, "K out of range (max_samples)");
   const int N = R * K;

@@ -398,4 +398,50 @@ int select_best(cudaStream_t st, const float* scores, int R, int K, float* group
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Sampler -> verifier action formatting on the device: replaces, per decision,
+// process_inputs(verifier_action=True) (eval_utils.py:172-221) -> BridgeSimplerAdapter.postprocess_verifier
+// (INT-ACT/src/experiments/env_adapters/simpler.py:96-121, denormalize_bound base.py:20-31, gripper
+// :221-225) and the left-padding with -5 of efficient_ensemble_merged.py:379-390.  Arithmetic mirrors
+// numpy's promotion: (x + 1) / 2 in float32, then * (p99 - p01) + p01 in float64, rounded to float32.
+__global__ void format_traj_kernel(const float* __restrict__ actions, int chunk, int adim_stride,
+                                   FormatStats st, const float* __restrict__ past, int num_past, int history,
+                                   int n_future, float* __restrict__ traj) {
+  const int n = blockIdx.x;
+  const int A = 7;
+  const int used = num_past + n_future;
+  const int lead = history - used;  // rows of -5 padding (>= 0, checked on the host)
+  for (int idx = threadIdx.x; idx < history * A; idx += blockDim.x) {
+    const int row = idx / A, col = idx % A;
+    float v;
+    if (row < lead) {
+      v = -5.0f;
+    } else if (row < lead + num_past) {
+      v = past[(row - lead) * A + col];
+    } else {
+      const int j = row - lead - num_past;
+      const float x = actions[(static_cast<long>(n) * chunk + j) * adim_stride + col];
+      if (col < 6) {
+        const float t = (x - (-1.0f)) / 2.0f;
+        v = static_cast<float>(static_cast<double>(t) * (st.p99[col] - st.p01[col]) + st.p01[col]);
+      } else {
+        v = x < 0.5f ? 0.0f : 1.0f;
+      }
+    }
+    traj[(static_cast<long>(n) * history + row) * A + col] = v;
+  }
+}
+int format_trajectories(cudaStream_t stream, const float* actions, int n_cand, int chunk, int adim_stride,
+                        const FormatStats& st, const float* past, int num_past, int history, int n_future,
+                        float* traj) {
+  CVB_REQUIRE(n_future >= 1 && n_future <= chunk, "n_future must be in [1, chunk]");
+  CVB_REQUIRE(num_past >= 0 && num_past + n_future <= history, "history too short for past + future actions");
+  CVB_REQUIRE(adim_stride >= 7, "action stride must be >= 7");
+  format_traj_kernel<<<n_cand, 96, 0, stream>>>(actions, chunk, adim_stride, st, past, num_past, history, n_future,
+                                                traj);
+  CVB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace cvb

@@ -6,6 +6,7 @@
 //   it_finalize               efficient_ensemble_merged.py:220-223
 //   traj_attention            nn.TransformerEncoderLayer self-attention with key padding, efficient_ensemble_merged.py:229-235
 //   masked_mean_l2norm        efficient_ensemble_merged.py:236-245
+//   format_trajectories       eval_utils.py:172-221 + INT-ACT simpler.py:96-121 + efficient_ensemble_merged.py:379-390
 //   fuse_score_select         efficient_ensemble_merged.py:404-447 (fuse, scores, group mean, argmax)
 #pragma once
 #include "ops.h"
@@ -29,6 +30,13 @@ struct ItFinal {
   const float *text_tok, *vision_tok, *w, *b;
   float* out;
 };
+
+struct FormatStats {
+  double p01[6], p99[6];
+};
+int format_trajectories(cudaStream_t stream, const float* actions, int n_cand, int chunk, int adim_stride,
+                        const FormatStats& st, const float* past, int num_past, int history, int n_future,
+                        float* traj);
 
 int embed_tokens_pos(cudaStream_t st, const bf16* table, const bf16* pos, const int64_t* tok, bf16* out,
                      int tokens, int width);

@@ -115,6 +115,16 @@ CVB_API int cvb_pi0_run_phase(cvb_handle* h, int phase, int R, int K, void* stre
 CVB_API int cvb_verifier_score(cvb_handle* h, const float* image, const int64_t* text_tokens, const float* traj,
                                int N, int R, int K, float* scores, float* group_mean, int32_t* best_idx,
                                float* best_score, int recompute_context, void* stream);
+/* Sampler -> verifier action formatting on the device (replaces process_inputs(verifier_action=True),
+ * eval_utils.py:172-221, BridgeSimplerAdapter.postprocess_verifier, INT-ACT/src/experiments/env_adapters/
+ * simpler.py:96-121, and the -5 left-padding of efficient_ensemble_merged.py:379-390).
+ *   actions f32 [n_cand, chunk, action_stride] (policy output, dims 0..6 used; first n_future steps)
+ *   p01_host / p99_host: HOST double[6] action statistics (bridge_statistics.json "action" p01 / p99)
+ *   past    f32 [num_past, 7] already in verifier format (the caller's action_history tail)
+ *   traj    f32 [n_cand, history, 7] */
+CVB_API int cvb_format_trajectories(const float* actions, int n_cand, int chunk, int action_stride,
+                                    const double* p01_host, const double* p99_host, const float* past,
+                                    int num_past, int history, int n_future, float* traj, void* stream);
 /* Test hook: inject normalised trunk features (patch f32 [Np, W], text f32 [ctx, W]) and recompute the
  * image-text heads, so the fp32 heads can be checked in isolation from the bf16 trunk. */
 CVB_API int cvb_verifier_set_features(cvb_handle* h, const float* patch, const float* text, void* stream);

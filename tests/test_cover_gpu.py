@@ -1,0 +1,127 @@
+"""Whole CoVer decision on the GPU through the public host surfaces vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pi0_oracle as O
+from oracle import verifier_oracle as V
+from tests.helpers import build_full_engine, max_abs
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_traj(actions, past, history, p01, p99):
+    """numpy restatement of eval_utils.process_inputs(verifier_action=True) + postprocess_verifier + padding."""
+    a = actions[:, :, :7].cpu().numpy().astype(np.float32)
+    fut = np.zeros(a.shape, dtype=np.float64)
+    t = (a[:, :, :6] - (-1)) / 2
+    fut[:, :, :6] = t * (np.array(p99) - np.array(p01)) + np.array(p01)
+    fut[:, :, 6] = np.where(a[:, :, 6] < 0.5, 0, 1)
+    hist = []
+    for n in range(a.shape[0]):
+        rows = fut[n] if past is None else np.concatenate([past.cpu().numpy().astype(np.float64), fut[n]], axis=0)
+        hist.append(rows)
+    return V.pad_histories(hist, history)
+
+
+def test_cover_step_matches_oracle():
+    from cover_vla_b200.cover import BRIDGE_ACTION_P01, BRIDGE_ACTION_P99, CoverInputs, CoverStep
+    d, v = O.TINY, V.VTINY
+    R, K = 4, 3
+    w, vw = O.make_pi0_weights(d, 0), V.make_verifier_weights(v, 0)
+    eng = build_full_engine(d, w, v, vw, R, K)
+    inp = O.make_inputs(d, R, K, seed=5)
+    vin = V.make_inputs(v, 1, seed=5)
+    past = torch.tensor([[0.01, -0.02, 0.0, 0.03, 0.0, -0.05, 1.0], [0.0, 0.01, 0.02, 0.0, 0.0, 0.1, 0.0]])
+    x = CoverInputs(image=inp["image"][0].cuda().contiguous(), lang_tokens=inp["tokens"].cuda(),
+                    lang_len=inp["lens"].to(torch.int32).cuda(), state=inp["state"][0].cuda().contiguous(),
+                    noise=inp["noise"].cuda(), vf_image=vin["image"][0].cuda().contiguous(),
+                    vf_tokens=vin["tokens"][0].cuda(), past=past.cuda())
+    step = CoverStep(eng, K)
+    actions, traj, scores, gmean, bidx, bscore = step.sample_and_score(x)
+    torch.cuda.synchronize()
+    # formatting kernel == numpy restatement, bit for bit (given the same actions)
+    ref_traj = _oracle_traj(actions, past, v.history, BRIDGE_ACTION_P01, BRIDGE_ACTION_P99)
+    assert torch.equal(traj.cpu(), ref_traj)
+    # verifier on those trajectories
+    patch, text = V.extract_features(vw, v, vin["image"], vin["tokens"])
+    ref_scores = V.scores_from_features(vw, v, patch, text, ref_traj)
+    best, idx, gi, means = V.select(ref_scores, K)
+    err = max_abs(scores, ref_scores)
+    print(f"cover step: score err {err:.2e}, best idx {int(bidx.item())} (oracle {idx})")
+    assert err < 5e-3
+    # gate (run_simpler_eval_with_openpi.py:344-363): candidate 0 is kept iff its score >= threshold
+    i2, s2, win = step(x, gate_threshold=10.0)   # score < 10 -> the N-candidate selection is used
+    assert i2 == idx and win.shape == (d.chunk_size, 7) and abs(s2 - best) < 5e-3
+    assert torch.equal(win, actions[idx, :, :7].cpu())
+    i3, s3, win3 = step(x, gate_threshold=-1e9)  # always confident -> candidate 0
+    assert i3 == 0 and abs(s3 - float(ref_scores[0])) < 5e-3
+    eng.close()
+
+
+def test_policy_and_ensemble_surfaces():
+    """The two reference-facing objects, used the way run_simpler_eval_with_openpi.py uses them."""
+    from cover_vla_b200.pi0 import PI0Config, PI0Policy, PolicyFeature
+    from cover_vla_b200.verifier import EfficientEnsembleMerged
+    d, v = O.TINY, V.VTINY
+    R, K = 3, 2
+    N = R * K
+    w, vw = O.make_pi0_weights(d, 0), V.make_verifier_weights(v, 0)
+    cfg = PI0Config(chunk_size=d.chunk_size, n_action_steps=d.chunk_size, tokenizer_max_length=d.max_lang_len,
+                    proj_width=d.ex_width, num_steps=d.num_steps, vis_layers=d.vis_layers, vis_width=d.vis_width,
+                    vis_heads=d.vis_heads, vis_mlp=d.vis_mlp, vis_patch=d.vis_patch, vis_image=d.vis_image,
+                    layers=d.layers, lm_width=d.lm_width, lm_mlp=d.lm_mlp, heads=d.heads, head_dim=d.head_dim,
+                    ex_mlp=d.ex_mlp, vocab=d.vocab, max_rephrases=R, max_samples=K,
+                    resize_imgs_with_padding=(d.vis_image, d.vis_image),
+                    input_features={"observation.images.top": PolicyFeature("VISUAL", (3, d.vis_image, d.vis_image)),
+                                    "observation.state": PolicyFeature("STATE", (7,))})
+    policy = PI0Policy(cfg, state_dict={"model." + k: t for k, t in w.items()})
+    inp = O.make_inputs(d, R, K, seed=7)
+    b = O.expand_to_batch(inp, K)
+    obs = {"observation.images.top": b["image"].cuda(), "observation.state": b["state"][:, :7].cuda(),
+           "lang_tokens": b["tokens"].cuda(), "lang_masks": b["masks"].cuda(), "task": ["x"] * N}
+    q = policy.select_action(obs, noise=b["noise"].cuda())
+    assert len(q) == cfg.n_action_steps and q[0].shape == (N, 7)
+    queue = q.copy()
+    q.clear()
+    ref = O.sample_actions(w, d, b["image"], b["tokens"], b["masks"], b["state"], b["noise"])
+    got = torch.stack(list(queue), dim=1).cpu()  # [N, steps, 7]
+    assert max_abs(got, ref[:, :, :7]) < 0.06
+    # a second call with an empty queue samples again; with a non-empty queue it must not
+    q2 = policy.select_action(obs, noise=b["noise"].cuda())
+    assert len(q2) == cfg.n_action_steps
+    q3 = policy.select_action(obs, noise=torch.zeros_like(b["noise"]).cuda())
+    assert torch.equal(torch.stack(list(q3)), torch.stack(list(q2)))
+
+    comps = []
+    for m in range(v.members):
+        c = {}
+        for k, t in vw.items():
+            pre = f"verifier.{m}."
+            if k.startswith(pre):
+                comp, name = k[len(pre):].split(".", 1)
+                c.setdefault(comp, {})[name] = t
+        c["action_padding_value"] = -5.0
+        comps.append(c)
+    trunk = {k: t for k, t in vw.items() if k.startswith("verifier.trunk.")}
+    vf_cfg = dict(vf_image=v.image, vf_patch=v.patch, vf_width=v.width, vf_layers=v.layers, vf_heads=v.heads,
+                  vf_mlp=v.mlp, vf_text_layers=v.text_layers, vf_text_ctx=v.text_ctx, vf_vocab=v.vocab,
+                  vf_embed=v.embed, vf_pool_heads=v.pool_heads, vf_pool_layers=v.pool_layers,
+                  vf_traj_layers=v.traj_layers, vf_traj_ff=v.traj_ff)
+    ens = EfficientEnsembleMerged(ensemble_components=comps, trunk_state_dict=trunk, vf_config=vf_cfg,
+                                  preprocess=lambda im: im, max_candidates=N)
+    vin = V.make_inputs(v, N, seed=7)
+    imgs = [vin["image"][0]] * N
+    instr = [vin["tokens"][0]] * N
+    ms, mi, mh, gi = ens.compute_max_similarity_scores_batch(imgs, instr, vin["histories"], cfg_repeat_language_instructions=K)
+    best, idx, ref_scores, means = V.compute_max_similarity_scores(vw, v, vin["image"], vin["tokens"], vin["histories"], K)
+    assert isinstance(ms, float) and gi.dtype == torch.int64 and gi.ndim == 0
+    assert abs(ms - best) < 5e-3
+    assert mh is vin["histories"][int(gi)]
+    # the 1-candidate gate call reuses the context and equals scores[0]
+    ms1, _, _, gi1 = ens.compute_max_similarity_scores_batch(imgs[:1], instr[:1], vin["histories"][:1], cfg_repeat_language_instructions=1)
+    assert int(gi1) == 0 and abs(ms1 - float(ref_scores[0])) < 5e-3
+    hist, sc = ens.predict(vin["image"][0], vin["tokens"][0], vin["histories"])
+    assert len(sc) == N and abs(sc["0"] - float(ref_scores[0])) < 5e-3
+    policy.engine.close()
+    ens.engine.close()

@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py - CoVer-VLA sample-and-verify on B200 (contract: see the task statement / DESIGN.md section 5).
+
+One "step" = one CoVer decision: pi0 samples N = R*K = 8*5 = 40 action chunks for one observation
+(SigLIP tower once, PaliGemma prefix once per unique rephrase, 10 denoise steps over all candidates), the
+candidates are formatted for the verifier on the device, scored by the 3-member bridge_verifier ensemble
+(SigLIP2 ViT-L trunk + text tower + fp32 heads) and the group-mean / argmax rule picks the winner
+(BASELINE.json configs[2]: "full CoVer step ... simpler_widowx shapes, 1 B200").  Full-size models,
+random-init weights, synthetic inputs.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (weak scaling:
+        every rank runs its own observation - episode-parallel, BASELINE.json configs[4] - no data-path collective)
+    python bench.py --impl reference ...      (the reference algorithm on the host CPU: oracle port, rank 0 only)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+R_DEFAULT, K_DEFAULT = 8, 5
+METRIC = "verified_candidates_per_sec"
+UNIT = "candidates/s"
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def algorithmic_flops(R: int, K: int) -> dict:
+    """De-duplicated algorithmic FLOPs per decision."""
+    N = R * K
+    return {"vision": 220.2e9, "prefix": 1315.9e9 * R, "denoise": 33.6e9 * N, "verifier_trunk": 420.6e9,
+            "verifier_heads": 3.7e9 + 20.2e9 * N / 40}
+
+
+def make_device_inputs(S, d, v, R, K, seed, device):
+    import torch
+    from cover_vla_b200.cover import CoverInputs
+    inp = S.make_inputs(d, R, K, seed=seed)
+    vin = S.make_verifier_inputs(v, 1, seed=seed)
+    past = torch.tensor([[0.004, -0.011, 0.002, 0.01, -0.02, 0.03, 1.0],
+                         [0.001, 0.006, -0.003, 0.0, 0.01, -0.04, 1.0],
+                         [-0.002, 0.003, 0.007, 0.02, 0.0, 0.05, 0.0]])
+    host = dict(image=inp["image"][0].contiguous(), lang_tokens=inp["tokens"].contiguous(),
+                lang_len=inp["lens"].to(torch.int32).contiguous(), state=inp["state"][0].contiguous(),
+                noise=inp["noise"].contiguous(), vf_image=vin["image"][0].contiguous(),
+                vf_tokens=vin["tokens"][0].contiguous(), past=past)
+    host = {k: t.pin_memory() for k, t in host.items()}
+    dev = CoverInputs(**{k: t.to(device) for k, t in host.items()})
+    return host, dev
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from cover_vla_b200 import _lib, synthetic as S
+    from cover_vla_b200 import build as cvb_build
+    from cover_vla_b200.cover import CoverInputs, CoverStep
+    from cover_vla_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    if not _lib.LIB_PATH.exists():
+        cvb_build.build()
+    lib = _lib.load()
+    lib.cvb_launch_count.restype = __import__("ctypes").c_int64
+
+    R, K = args.rephrases, args.samples
+    N = R * K
+    d, v = S.FULL, S.VFULL
+    t0 = time.time()
+    w = S.make_pi0_weights(d, seed=0)
+    vw = S.make_verifier_weights(v, seed=0)
+    eng = S.build_engine(d, w, v, vw, R, K, device=device)
+    t_build = time.time() - t0
+    host, x = make_device_inputs(S, d, v, R, K, seed=100 + rank, device=device)
+    step = CoverStep(eng, K)
+
+    def one_step():
+        return step.sample_and_score(x)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (first calls run eagerly, then the CUDA graph is captured)
+    for _ in range(max(3, args.warmup)):
+        out = one_step()
+    torch.cuda.synchronize()
+    l0 = lib.cvb_launch_count()
+    eng_eager = None  # launches per step = what one eager pass enqueues (graph replay enqueues the same kernels)
+    # count by replaying the phases eagerly once
+    eng.pi0_run_phase(0, R, K)
+    eng.pi0_run_phase(1, R, K)
+    eng.pi0_run_phase(2, R, K)
+    pi0_launches = lib.cvb_launch_count() - l0
+    l1 = lib.cvb_launch_count()
+    one_step()
+    torch.cuda.synchronize()
+    other_launches = lib.cvb_launch_count() - l1  # format + verifier (eager) [+ 0 for the replayed pi0 graph]
+    launches_per_step = int(pi0_launches + other_launches)
+
+    # ---- timed region: K steps, device-resident inputs, CUDA events, max over ranks
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        out = one_step()
+        ev[i + 1].record()
+    barrier()
+    clk = clocks.stop()
+    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[-1])
+    if world > 1:
+        t = torch.tensor([total_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = N * world / (ms_per_step / 1e3)
+
+    # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
+    def e2e_step():
+        xin = CoverInputs(**{k: t.to(device, non_blocking=True) for k, t in host.items()})
+        return step(xin)  # returns python (idx, score, winner actions): includes the D2H read
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t_e2e = []
+    for _ in range(args.steps):
+        t1 = time.perf_counter()
+        idx, score, winner = e2e_step()
+        t_e2e.append((time.perf_counter() - t1) * 1e3)
+    barrier()
+    e2e_ms = sum(t_e2e) / len(t_e2e)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+    d2h = (2 + d.chunk_size * 7) * 4
+
+    line = None
+    if rank == 0:
+        peaks, peak_src = _peaks()
+        # ---- phase breakdown (eager, CUDA events) and the roofline of the dominant kernel
+        def ev_ms(fn, iters=3):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+            a.record()
+            for _ in range(iters):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / iters
+        phases = {nm: ev_ms(lambda p=p: eng.pi0_run_phase(p, R, K)) for p, nm in enumerate(["vision", "prefix", "denoise"])}
+        traj = out[1]
+        phases["verifier"] = ev_ms(lambda: eng.verifier_score(x.vf_image, x.vf_tokens, traj, R, K))
+        fl = algorithmic_flops(R, K)
+        total_flops = sum(fl.values())
+
+        # dominant kernel: the prefix gate/up GeGLU GEMM (tcgen05), M = R*328, N = 2*16384 packed, K = 2048.
+        # Timed alone, cycling through 6 different weight matrices (6 x 134 MB >> 126 MB L2).
+        M_, Kd, I_ = R * (d.n_img_tokens + d.max_lang_len), d.lm_width, d.lm_mlp
+        a_ = torch.randn(M_, Kd, device=device, dtype=torch.bfloat16)
+        ws = [(torch.randn(2 * I_, Kd, device=device) * 0.02).to(torch.bfloat16) for _ in range(6)]
+        o_ = torch.empty(M_, I_, device=device, dtype=torch.bfloat16)
+        for wgt in ws:
+            ops.gemm_bf16(a_, wgt, epilogue=ops.EPI_GEGLU, n_out=I_, out=o_)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        reps = 5
+        a.record()
+        for _ in range(reps):
+            for wgt in ws:
+                ops.gemm_bf16(a_, wgt, epilogue=ops.EPI_GEGLU, n_out=I_, out=o_)
+        b.record()
+        torch.cuda.synchronize()
+        gemm_ms = a.elapsed_time(b) / (reps * len(ws))
+        gemm_flops = 2.0 * M_ * (2 * I_) * Kd
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        peak = float(peaks["bf16_tflops"])
+        roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05<256,4,EPI_GEGLU> (prefix gate/up, M=%d N=%d K=%d)" % (M_, 2 * I_, Kd),
+                    "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+                    "traffic": None, "peak_source": peak_src + ", burst figure (kernel timed alone)",
+                    "launch_ms": round(gemm_ms, 4), "launches_per_step": d.layers - 1,
+                    "step_frac_of_sustained_peak": round(total_flops / (ms_per_step * 1e-3) / 1e12 / float(peaks["bf16_tflops_sustained"]), 4)}
+        del a_, ws, o_
+
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_sample(seconds_hint=20)
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[2]: full CoVer step, pi0 %d rephrases x %d samples (%d candidates) "
+                                   "+ 3-member verifier argmax, simpler_widowx shapes, full-size random-init models" % (R, K, N),
+                       "rephrases": R, "samples_per_rephrase": K, "candidates_per_step_per_gpu": N,
+                       "parallelism": "episode-parallel: 1 observation per GPU per step, no data-path collective" if world > 1 else "1 GPU",
+                       "l2": "no flush needed: every step streams ~8.6 GB of weights from HBM (>> 126 MB L2)",
+                       "cuda_graph": bool(eng.cfg.use_cuda_graph)},
+            "p50_ms": round(statistics.median(per_step), 3),
+            "phases_ms": {k: round(val, 3) for k, val in phases.items()},
+            "algorithmic_tflop_per_step": round(total_flops / 1e12, 3),
+            "clocks": clk,
+            "e2e": {"value": round(N * world / (e2e_ms / 1e3), 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 3),
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": launches_per_step,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "build_s": round(t_build, 1),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU legs: the oracle (bit-exact restatement of the reference) on the host cores
+# ----------------------------------------------------------------------------------------------------
+_CPU_STATE = {}
+
+
+def _cpu_setup():
+    """Full-size weights + oracle modules (test infrastructure; only the CPU legs import oracle/)."""
+    if _CPU_STATE:
+        return _CPU_STATE
+    import torch
+    from cover_vla_b200 import synthetic as S
+    from oracle import pi0_oracle as O
+    from oracle import verifier_oracle as V
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    _CPU_STATE.update(S=S, O=O, V=V, cores=cores, w=S.make_pi0_weights(S.FULL, 0), vw=S.make_verifier_weights(S.VFULL, 0))
+    return _CPU_STATE
+
+
+def cpu_decision(R: int, K: int, seed: int):
+    """One CoVer decision for R*K candidates exactly as the reference executes it (batch layout N, no
+    de-duplication): sample_actions at B = N, verifier-format, ensemble scores, selection."""
+    import numpy as np
+    import torch
+    st = _cpu_setup()
+    S, O, V = st["S"], st["O"], st["V"]
+    d, v = S.FULL, S.VFULL
+    inp = S.make_inputs(d, R, K, seed=seed)
+    b = S.expand_to_batch(inp, K)
+    vin = S.make_verifier_inputs(v, 1, seed=seed)
+    t0 = time.perf_counter()
+    actions = O.sample_actions(st["w"], d, b["image"], b["tokens"], b["masks"], b["state"], b["noise"])
+    from cover_vla_b200.cover import BRIDGE_ACTION_P01, BRIDGE_ACTION_P99
+    a = actions[:, :, :7].numpy().astype(np.float32)
+    fut = np.zeros(a.shape, dtype=np.float64)
+    fut[:, :, :6] = (a[:, :, :6] + 1) / 2 * (np.array(BRIDGE_ACTION_P99) - np.array(BRIDGE_ACTION_P01)) + np.array(BRIDGE_ACTION_P01)
+    fut[:, :, 6] = np.where(a[:, :, 6] < 0.5, 0, 1)
+    best, idx, scores, means = V.compute_max_similarity_scores(st["vw"], v, vin["image"], vin["tokens"],
+                                                               [fut[n] for n in range(R * K)], K)
+    return time.perf_counter() - t0, idx
+
+
+def cpu_baseline_sample(seconds_hint=20):
+    st = _cpu_setup()
+    R, K = 1, 2
+    cpu_decision(1, 1, seed=1)  # warm-up (thread pools, allocator)
+    t, _ = cpu_decision(R, K, seed=2)
+    return {"value": round(R * K / t, 4), "unit": UNIT, "cores": st["cores"], "kind": "port",
+            "sample": "full-size models, one decision over %d of the 40 candidates (R=%d, K=%d) in the reference's batch "
+                      "layout incl. verifier; oracle port (bit-exact vs the reference files in the authoring container); "
+                      "%.1f s of CPU work" % (R * K, R, K, t)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    st = _cpu_setup()
+    R, K = 1, 2
+    # bounded sample: each step = one decision over 2 candidates (B = 2 in the reference's batch layout)
+    for i in range(max(1, min(args.warmup, 1))):
+        cpu_decision(R, K, seed=10 + i)
+    times = []
+    budget = 240.0
+    t_start = time.perf_counter()
+    for i in range(args.steps):
+        t, _ = cpu_decision(R, K, seed=20 + i)
+        times.append(t)
+        if time.perf_counter() - t_start > budget:
+            break
+    ms = 1e3 * sum(times) / len(times)
+    value = R * K / (ms / 1e3)
+    sample = ("each step = one full-size CoVer decision over %d of the 40 candidates (R=%d, K=%d, reference batch layout, "
+              "no de-duplication, incl. verifier trunk + heads + selection) on %d host threads; %d of %d steps run inside "
+              "the %.0f s budget" % (R * K, R, K, st["cores"], len(times), args.steps, budget))
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world,
+            "steps": len(times), "warmup": args.warmup, "ms_per_step": round(ms, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[2] (bounded sample): full CoVer step on the host CPU",
+                       "rephrases": R, "samples_per_rephrase": K},
+            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": st["cores"], "kind": "port", "sample": sample},
+            "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rephrases", type=int, default=R_DEFAULT)
+    ap.add_argument("--samples", type=int, default=K_DEFAULT)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

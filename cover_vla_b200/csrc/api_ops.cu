@@ -15,6 +15,8 @@ const char* cvb_last_error(void) { return cvb::get_last_error(); }
 
 int cvb_abi_version(void) { return CVB_ABI_VERSION; }
 
+int64_t cvb_launch_count(void) { return cvb::launch_count(); }
+
 int cvb_op_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
                      int epilogue, void* C, int64_t ldc, const void* bias, int bias_is_f32,
                      const void* resid, int resid_is_f32, int64_t ldr, int n_out,

@@ -1,5 +1,6 @@
 #include "host_common.h"
 
+#include <atomic>
 #include <mutex>
 
 namespace cvb {
@@ -49,6 +50,10 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols
   }
   return 0;
 }
+
+static std::atomic<long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int device_sm_count() {
   static int sms = 0;

@@ -47,4 +47,14 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols
 
 int device_sm_count();
 
+// number of kernel launches enqueued by this library (bench.py reports it as gpu_launches)
+void count_launch();
+long launch_count();
+
+#define CVB_LAUNCHED()                \
+  do {                                \
+    ::cvb::count_launch();            \
+    CVB_CUDA(cudaGetLastError());     \
+  } while (0)
+
 }  // namespace cvb

@@ -261,7 +261,7 @@ int launch_attn(cudaStream_t st, const AttnParams& p, dim3 grid) {
     attr_set = true;
   }
   kern<<<grid, ATT_THREADS, SMEM, st>>>(p);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 

@@ -74,7 +74,7 @@ int launch(cudaStream_t st, const GemmCall& c, int grid) {
     attr_set = true;
   }
   kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(tmA, tmB, g);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 

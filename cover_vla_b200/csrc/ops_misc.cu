@@ -108,7 +108,7 @@ int rmsnorm(cudaStream_t st, const void* x, int x_is_f32, long ldx, const void* 
     rmsnorm_kernel<false, true><<<rows, threads, 0, st>>>(x, ldx, w, y, ldy, rows, width, eps, rows_dev);
   else
     rmsnorm_kernel<false, false><<<rows, threads, 0, st>>>(x, ldx, w, y, ldy, rows, width, eps, rows_dev);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 
@@ -166,7 +166,7 @@ int layernorm_bf16(cudaStream_t st, const bf16* x, long ldx, const bf16* w, cons
   CVB_REQUIRE(width % 8 == 0, "layernorm width must be a multiple of 8");
   const int threads = width >= 1024 ? 128 : 64;
   layernorm_bf16_kernel<<<rows, threads, 0, st>>>(x, ldx, w, b, y, ldy, width, eps);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(128) layernorm_f32_kernel(const float* __restr
 int layernorm_f32(cudaStream_t st, const float* x, const float* resid, const float* w,
                   const float* b, float* y, int rows, int width, float eps) {
   layernorm_f32_kernel<<<rows, 128, width * sizeof(float), st>>>(x, resid, w, b, y, width, eps);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 

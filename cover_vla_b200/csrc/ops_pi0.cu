@@ -29,7 +29,7 @@ int im2col_patches(cudaStream_t st, const float* img, bf16* out, int C, int H, i
                    int kpad) {
   const int tokens = (H / P) * (W / P);
   im2col_kernel<<<tokens, 128, 0, st>>>(img, out, C, H, W, P, kpad);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 
@@ -79,7 +79,7 @@ int build_prefix(cudaStream_t st, const bf16* proj, const bf16* embed, const int
   const float sb = __bfloat162float(__float2bfloat16_rn(s));
   dim3 grid(n_img + n_lang, R);
   build_prefix_kernel<<<grid, 128, 0, st>>>(proj, embed, tok, prefix, n_img, n_lang, D, s, sb);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 
@@ -146,7 +146,7 @@ int rope_qkv(cudaStream_t st, bf16* qkv, long ld, const float* timescale, int ro
   if (threads < 32) threads = 32;
   rope_kernel<<<rows, threads, 0, st>>>(qkv, ld, timescale, heads, hd, rows_per_batch, pos_base_dev,
                                         q_per_kv_batch, kcache, vcache, cache_bs, cache_rs);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 
@@ -182,7 +182,7 @@ int action_out_euler(cudaStream_t st, const bf16* hn, long ld, const float* w, c
                      int suffix_len, float dt) {
   action_out_euler_kernel<<<n_cand * chunk, 256, 0, st>>>(hn, ld, w, bias, x_t, v_out, width, adim,
                                                          chunk, suffix_len, dt);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 
@@ -197,7 +197,7 @@ __global__ void fill_state_rows_kernel(const float* __restrict__ state_emb, floa
 int fill_state_rows(cudaStream_t st, const float* state_emb, float* suffix, int n_cand, int width,
                     int suffix_len) {
   fill_state_rows_kernel<<<n_cand, 256, 0, st>>>(state_emb, suffix, width, suffix_len);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 
@@ -210,7 +210,7 @@ __global__ void prefix_len_kernel(const int* __restrict__ lang_len, int* __restr
 
 int prefix_lengths(cudaStream_t st, const int* lang_len, int* plen, int R, int n_img) {
   prefix_len_kernel<<<(R + 63) / 64, 64, 0, st>>>(lang_len, plen, R, n_img);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 
@@ -220,7 +220,7 @@ __global__ void bf16_table_to_f32_kernel(const bf16* __restrict__ src, float* __
 }
 int bf16_to_f32(cudaStream_t st, const bf16* src, float* dst, long n) {
   bf16_table_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 

@@ -117,7 +117,7 @@ int sgemm_f32(cudaStream_t st, const SgemmCall& c) {
   dim3 grid((c.N + TN - 1) / TN, (c.M + TM - 1) / TM);
   sgemm_kernel<<<grid, 256, 0, st>>>(c.A, c.lda, c.W, c.ldw, c.M, c.N, c.K, c.C, c.ldc, c.bias,
                                      c.row_bias, c.resid, c.ldr, c.act, c.out_group, c.w_kn);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 

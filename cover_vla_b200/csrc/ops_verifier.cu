@@ -52,7 +52,7 @@ __global__ void embed_tokens_pos_kernel(const bf16* __restrict__ table, const bf
 int embed_tokens_pos(cudaStream_t st, const bf16* table, const bf16* pos, const int64_t* tok, bf16* out,
                      int tokens, int width) {
   embed_tokens_pos_kernel<<<tokens, 256, 0, st>>>(table, pos, tok, out, width);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 
@@ -71,7 +71,7 @@ __global__ void l2norm_bf16_kernel(const bf16* __restrict__ x, long ldx, float* 
 }
 int l2norm_rows_bf16_to_f32(cudaStream_t st, const bf16* x, long ldx, float* y, int rows, int width) {
   l2norm_bf16_kernel<<<rows, 256, 0, st>>>(x, ldx, y, width);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 
@@ -90,7 +90,7 @@ __global__ void softmax_temp_kernel(float* __restrict__ x, int cols, const float
 }
 int softmax_rows_temp(cudaStream_t st, float* x, int rows, int cols, const float* temp_dev) {
   softmax_temp_kernel<<<rows, 256, 0, st>>>(x, cols, temp_dev);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 
@@ -100,7 +100,7 @@ __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restr
 }
 int add_f32(cudaStream_t st, const float* a, const float* b, float* y, long n) {
   add_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b, y, n);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(512) pool_chain_kernel(const PoolChain* __rest
 int pool_chains(cudaStream_t st, const PoolChain* chains_dev, int n_chains, int embed, int heads, int tokens) {
   const size_t smem = (3 * embed + heads * tokens) * sizeof(float);
   pool_chain_kernel<<<n_chains, 512, smem, st>>>(chains_dev);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256) it_finalize_kernel(const ItFinal* __restr
 }
 int it_finalize(cudaStream_t st, const ItFinal* items_dev, int members, int embed) {
   it_finalize_kernel<<<members, 256, 3 * embed * sizeof(float), st>>>(items_dev, embed);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 
@@ -269,7 +269,7 @@ int traj_attention(cudaStream_t st, const float* qkv, const float* traj, float* 
                    int adim, float pad_value) {
   CVB_REQUIRE(S <= 32, "history length must be <= 32");
   traj_attention_kernel<<<n_cand, 256, 0, st>>>(qkv, traj, out, S, E, H, adim, pad_value);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) masked_mean_l2_kernel(const float* __rest
 int masked_mean_l2norm(cudaStream_t st, const float* x, const float* traj, float* out, int n_cand, int S, int E,
                        int adim, float pad_value) {
   masked_mean_l2_kernel<<<n_cand, 256, 0, st>>>(x, traj, out, S, E, adim, pad_value);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 
@@ -381,7 +381,7 @@ int fuse_score_select(cudaStream_t st, const float* it, const float* act, int M,
   CVB_REQUIRE(!do_select || R * K == N, "R*K must equal the number of candidates");
   fuse_score_select_kernel<<<1, 1024, (E + R + 1) * sizeof(float), st>>>(it, act, M, N, E, scores, R, K, group_mean,
                                                                          best_idx, best_score, do_select);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ s
 int select_best(cudaStream_t st, const float* scores, int R, int K, float* group_mean, int* best_idx,
                 float* best_score) {
   select_kernel<<<1, 256, (R + 1) * sizeof(float), st>>>(scores, R, K, group_mean, best_idx, best_score);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 
@@ -440,7 +440,7 @@ int format_trajectories(cudaStream_t stream, const float* actions, int n_cand, i
   CVB_REQUIRE(adim_stride >= 7, "action stride must be >= 7");
   format_traj_kernel<<<n_cand, 96, 0, stream>>>(actions, chunk, adim_stride, st, past, num_past, history, n_future,
                                                 traj);
-  CVB_CUDA(cudaGetLastError());
+  CVB_LAUNCHED();
   return 0;
 }
 

@@ -31,6 +31,8 @@ extern "C" {
 
 CVB_API const char* cvb_last_error(void);
 CVB_API int cvb_abi_version(void);
+/* Kernels enqueued by this library so far (launches recorded into a CUDA graph count once, at capture). */
+CVB_API int64_t cvb_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Operator level (one launch each).  GEMM epilogue kinds:

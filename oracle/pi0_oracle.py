@@ -25,158 +25,13 @@ through oracle/ref_shim.py: tests/golden/pi0_*.pt (made by oracle/make_golden.py
 """
 from __future__ import annotations
 
-import hashlib
 import math
-from dataclasses import asdict, dataclass
 
 import torch
 import torch.nn.functional as F
 
-
-@dataclass
-class PI0Dims:
-    vis_layers: int = 27
-    vis_width: int = 1152
-    vis_heads: int = 16
-    vis_mlp: int = 4304
-    vis_patch: int = 14
-    vis_image: int = 224
-    layers: int = 18
-    lm_width: int = 2048
-    lm_mlp: int = 16384
-    heads: int = 8
-    head_dim: int = 256
-    ex_width: int = 1024
-    ex_mlp: int = 4096
-    vocab: int = 257152
-    max_state_dim: int = 32
-    max_action_dim: int = 32
-    chunk_size: int = 4
-    max_lang_len: int = 72
-    num_steps: int = 10
-
-    @property
-    def n_img_tokens(self) -> int:
-        return (self.vis_image // self.vis_patch) ** 2
-
-    def as_dict(self):
-        return asdict(self)
-
-
-FULL = PI0Dims()
-TINY = PI0Dims(vis_layers=2, vis_width=128, vis_heads=2, vis_mlp=256, vis_patch=14, vis_image=56,
-               layers=3, lm_width=128, lm_mlp=512, heads=2, head_dim=64, ex_width=64, ex_mlp=256,
-               vocab=1000, max_lang_len=16)
-# mid-size: every awkward property of the full model (head_dim 72 in the tower, K tails, 256-d heads)
-# at a size the CPU oracle finishes in seconds
-MID = PI0Dims(vis_layers=3, vis_width=288, vis_heads=4, vis_mlp=1072, vis_patch=14, vis_image=224,
-              layers=4, lm_width=512, lm_mlp=2048, heads=8, head_dim=256, ex_width=256, ex_mlp=1024,
-              vocab=4096, max_lang_len=72)
-
-PW = "paligemma_with_expert."
-VT = PW + "paligemma.vision_tower.vision_model."
-MM = PW + "paligemma.multi_modal_projector.linear."
-LM = PW + "paligemma.language_model.model."
-EX = PW + "gemma_expert.model."
-
-
-# ------------------------------------------------------------------------------------------------
-# deterministic synthetic weights (canonical = transformers-4.48.3 key names, no "model." prefix)
-# ------------------------------------------------------------------------------------------------
-def _gen(name: str, seed: int, shape, std: float, dtype, mean: float = 0.0):
-    h = int.from_bytes(hashlib.sha256(f"{seed}:{name}".encode()).digest()[:8], "little") % (2 ** 62)
-    g = torch.Generator(device="cpu").manual_seed(h)
-    n = 1
-    for s in shape:
-        n *= s
-    if n > (1 << 26):  # huge tables (token embedding): tile a 4M-element random block
-        blk = torch.empty(1 << 22, dtype=torch.float32).normal_(0.0, std, generator=g)
-        t = blk.repeat((n + blk.numel() - 1) // blk.numel())[:n].reshape(shape)
-    else:
-        t = torch.empty(shape, dtype=torch.float32).normal_(0.0, std, generator=g)
-    if mean != 0.0:
-        t = t + mean
-    return t.to(dtype)
-
-
-def weight_specs(d: PI0Dims):
-    """(key, shape, std, mean, dtype) for every tensor the sampling path reads."""
-    bf, f32 = torch.bfloat16, torch.float32
-    out = []
-
-    def lin(key, o, i, dtype=bf, bias=False):
-        out.append((key + ".weight", (o, i), 1.0 / math.sqrt(i), 0.0, dtype))
-        if bias:
-            out.append((key + ".bias", (o,), 0.05, 0.0, dtype))
-
-    out.append((VT + "embeddings.patch_embedding.weight", (d.vis_width, 3, d.vis_patch, d.vis_patch),
-                1.0 / math.sqrt(3 * d.vis_patch ** 2), 0.0, bf))
-    out.append((VT + "embeddings.patch_embedding.bias", (d.vis_width,), 0.05, 0.0, bf))
-    out.append((VT + "embeddings.position_embedding.weight", (d.n_img_tokens, d.vis_width), 0.5, 0.0, bf))
-    for l in range(d.vis_layers):
-        p = VT + f"encoder.layers.{l}."
-        for ln in ("layer_norm1", "layer_norm2"):
-            out.append((p + ln + ".weight", (d.vis_width,), 0.1, 1.0, bf))
-            out.append((p + ln + ".bias", (d.vis_width,), 0.1, 0.0, bf))
-        for nm in ("q_proj", "k_proj", "v_proj", "out_proj"):
-            lin(p + "self_attn." + nm, d.vis_width, d.vis_width, bias=True)
-        lin(p + "mlp.fc1", d.vis_mlp, d.vis_width, bias=True)
-        lin(p + "mlp.fc2", d.vis_width, d.vis_mlp, bias=True)
-    out.append((VT + "post_layernorm.weight", (d.vis_width,), 0.1, 1.0, bf))
-    out.append((VT + "post_layernorm.bias", (d.vis_width,), 0.1, 0.0, bf))
-    lin(MM[:-1], d.lm_width, d.vis_width, bias=True)
-    out.append((LM + "embed_tokens.weight", (d.vocab, d.lm_width), 1.0 / math.sqrt(d.lm_width), 0.0, bf))
-    qd = d.heads * d.head_dim
-    for l in range(d.layers):
-        p = LM + f"layers.{l}."
-        lin(p + "self_attn.q_proj", qd, d.lm_width)
-        lin(p + "self_attn.k_proj", d.head_dim, d.lm_width)
-        lin(p + "self_attn.v_proj", d.head_dim, d.lm_width)
-        lin(p + "self_attn.o_proj", d.lm_width, qd)
-        lin(p + "mlp.gate_proj", d.lm_mlp, d.lm_width)
-        lin(p + "mlp.up_proj", d.lm_mlp, d.lm_width)
-        lin(p + "mlp.down_proj", d.lm_width, d.lm_mlp)
-        out.append((p + "input_layernorm.weight", (d.lm_width,), 0.1, 0.0, bf))
-        out.append((p + "post_attention_layernorm.weight", (d.lm_width,), 0.1, 0.0, bf))
-        p = EX + f"layers.{l}."
-        lin(p + "self_attn.q_proj", qd, d.ex_width)
-        lin(p + "self_attn.k_proj", d.head_dim, d.ex_width)
-        lin(p + "self_attn.v_proj", d.head_dim, d.ex_width)
-        lin(p + "self_attn.o_proj", d.ex_width, qd)
-        lin(p + "mlp.gate_proj", d.ex_mlp, d.ex_width)
-        lin(p + "mlp.up_proj", d.ex_mlp, d.ex_width)
-        lin(p + "mlp.down_proj", d.ex_width, d.ex_mlp)
-        out.append((p + "input_layernorm.weight", (d.ex_width,), 0.1, 0.0, bf))
-        out.append((p + "post_attention_layernorm.weight", (d.ex_width,), 0.1, 0.0, bf))
-    out.append((EX + "norm.weight", (d.ex_width,), 0.1, 0.0, f32))
-    lin("state_proj", d.ex_width, d.max_state_dim, f32, bias=True)
-    lin("action_in_proj", d.ex_width, d.max_action_dim, f32, bias=True)
-    lin("action_out_proj", d.max_action_dim, d.ex_width, f32, bias=True)
-    lin("action_time_mlp_in", d.ex_width, 2 * d.ex_width, f32, bias=True)
-    lin("action_time_mlp_out", d.ex_width, d.ex_width, f32, bias=True)
-    return out
-
-
-def make_pi0_weights(d: PI0Dims, seed: int = 0) -> dict:
-    return {k: _gen(k, seed, shape, std, dtype, mean) for k, shape, std, mean, dtype in weight_specs(d)}
-
-
-def to_hf5_key(k: str) -> str:
-    """canonical (4.48.3) -> transformers>=4.52 module layout (what the shim-built reference uses)."""
-    k = k.replace("paligemma.vision_tower.", "paligemma.model.vision_tower.")
-    k = k.replace("paligemma.multi_modal_projector.", "paligemma.model.multi_modal_projector.")
-    k = k.replace("paligemma.language_model.model.", "paligemma.model.language_model.")
-    return k
-
-
-def canonical_key(k: str) -> str:
-    """accept 'model.'-prefixed PI0Policy keys and either transformers layout."""
-    if k.startswith("model."):
-        k = k[len("model."):]
-    k = k.replace("paligemma.model.vision_tower.", "paligemma.vision_tower.")
-    k = k.replace("paligemma.model.multi_modal_projector.", "paligemma.multi_modal_projector.")
-    k = k.replace("paligemma.model.language_model.", "paligemma.language_model.model.")
-    return k
+from cover_vla_b200.synthetic import (EX, FULL, LM, MID, MM, PW, TINY, VT, PI0Dims, canonical_key, expand_to_batch,  # noqa: F401
+                                      make_inputs, make_pi0_weights, to_hf5_key, weight_specs)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -427,26 +282,3 @@ def sample_actions_dedup(w, d: PI0Dims, image1, lang_tokens_r, lang_masks_r, sta
     return x_t
 
 
-# ------------------------------------------------------------------------------------------------
-# synthetic inputs
-# ------------------------------------------------------------------------------------------------
-def make_inputs(d: PI0Dims, R: int, K: int, seed: int = 0, noise_std: float = 1.0):
-    g = torch.Generator().manual_seed(1000 + seed)
-    image = torch.rand(1, 3, d.vis_image, d.vis_image, generator=g) * 2 - 1
-    lens = torch.randint(min(8, d.max_lang_len), min(24, d.max_lang_len) + 1, (R,), generator=g)
-    tokens = torch.randint(3, d.vocab - 1, (R, d.max_lang_len), generator=g)
-    masks = torch.arange(d.max_lang_len)[None, :] < lens[:, None]
-    tokens = torch.where(masks, tokens, torch.zeros_like(tokens))
-    state = torch.zeros(1, d.max_state_dim)
-    state[0, :7] = torch.randn(7, generator=g)
-    noise = torch.randn(R * K, d.chunk_size, d.max_action_dim, generator=g) * noise_std
-    return dict(image=image, tokens=tokens, masks=masks, state=state, noise=noise, lens=lens)
-
-
-def expand_to_batch(inp, K):
-    """What run_simpler_eval_with_openpi.py:305-319 hands to select_action (rephrase-major)."""
-    R = inp["tokens"].shape[0]
-    N = R * K
-    rep = torch.arange(R).repeat_interleave(K)
-    return dict(image=inp["image"].repeat(N, 1, 1, 1), tokens=inp["tokens"][rep], masks=inp["masks"][rep],
-                state=inp["state"].repeat(N, 1), noise=inp["noise"])

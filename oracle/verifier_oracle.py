@@ -26,162 +26,14 @@ golden vector or source pins it, and with random-init weights this restatement D
 from __future__ import annotations
 
 import math
-from dataclasses import asdict, dataclass
 
-import numpy as np
+import numpy as np  # noqa: F401
 import torch
 import torch.nn.functional as F
 
-from oracle.pi0_oracle import _gen
-
-
-@dataclass
-class VerifierDims:
-    image: int = 384
-    patch: int = 16
-    width: int = 1024
-    layers: int = 24
-    heads: int = 16
-    mlp: int = 4096
-    text_layers: int = 24
-    text_ctx: int = 64
-    vocab: int = 256000
-    members: int = 3
-    embed: int = 512
-    pool_heads: int = 8
-    pool_layers: int = 4
-    traj_layers: int = 4
-    traj_ff: int = 1024
-    history: int = 10
-    action_dim: int = 7
-
-    @property
-    def n_patches(self) -> int:
-        return (self.image // self.patch) ** 2
-
-    def as_dict(self):
-        return asdict(self)
-
-
-VFULL = VerifierDims()
-VTINY = VerifierDims(image=64, patch=16, width=128, layers=2, heads=2, mlp=256, text_layers=2, text_ctx=16,
-                     vocab=500, members=2, embed=64, pool_heads=2, pool_layers=2, traj_layers=2, traj_ff=128)
-VMID = VerifierDims(image=192, patch=16, width=256, layers=3, heads=4, mlp=1024, text_layers=3, text_ctx=64,
-                    vocab=2000, members=3, embed=512, pool_heads=8, pool_layers=4, traj_layers=4, traj_ff=1024)
-
-TR = "verifier.trunk."
-
-
-def trunk_specs(d: VerifierDims):
-    bf = torch.bfloat16
-    out = []
-
-    def lin(key, o, i, wname="weight", bname="bias"):
-        out.append((key + wname, (o, i), 1.0 / math.sqrt(i), 0.0, bf))
-        out.append((key + bname, (o,), 0.05, 0.0, bf))
-
-    def ln(key):
-        out.append((key + "weight", (d.width,), 0.1, 1.0, bf))
-        out.append((key + "bias", (d.width,), 0.1, 0.0, bf))
-
-    v = TR + "visual.trunk."
-    out.append((v + "patch_embed.proj.weight", (d.width, 3, d.patch, d.patch), 1.0 / math.sqrt(3 * d.patch ** 2), 0.0, bf))
-    out.append((v + "patch_embed.proj.bias", (d.width,), 0.05, 0.0, bf))
-    out.append((v + "pos_embed", (1, d.n_patches, d.width), 0.5, 0.0, bf))
-    for l in range(d.layers):
-        p = v + f"blocks.{l}."
-        ln(p + "norm1.")
-        lin(p + "attn.qkv.", 3 * d.width, d.width)
-        lin(p + "attn.proj.", d.width, d.width)
-        if l < d.layers - 1:  # the last block's MLP is computed by the reference but never read
-            ln(p + "norm2.")
-            lin(p + "mlp.fc1.", d.mlp, d.width)
-            lin(p + "mlp.fc2.", d.width, d.mlp)
-    t = TR + "text."
-    out.append((t + "token_embedding.weight", (d.vocab, d.width), 0.7, 0.0, bf))
-    out.append((t + "positional_embedding", (d.text_ctx, d.width), 0.5, 0.0, bf))
-    for l in range(d.text_layers):
-        p = t + f"transformer.resblocks.{l}."
-        ln(p + "ln_1.")
-        lin(p + "attn.", 3 * d.width, d.width, "in_proj_weight", "in_proj_bias")
-        lin(p + "attn.out_proj.", d.width, d.width)
-        ln(p + "ln_2.")
-        lin(p + "mlp.c_fc.", d.mlp, d.width)
-        lin(p + "mlp.c_proj.", d.width, d.mlp)
-    ln(t + "ln_final.")
-    lin(t + "text_projection.", d.width, d.width)
-    return out
-
-
-def head_specs(d: VerifierDims):
-    """Names = 'verifier.<m>.<component>.<state-dict key>' with the component / key names of the merged
-    checkpoint (efficient_ensemble_merged.py:94-160)."""
-    f32 = torch.float32
-    E, Wd = d.embed, d.width
-    out = []
-    for m in range(d.members):
-        b = f"verifier.{m}."
-        out.append((b + "text_aware_visual_extraction.temperature", (), 0.0, 0.07, f32))
-        out.append((b + "text_aware_visual_extraction.pos_emb", (d.n_patches, Wd), None, None, f32))  # sincos buffer
-        for pool in ("vision_poolings", "text_pooling"):
-            p = b + pool + "."
-            out.append((p + "query", (1, 1, E), 1.0, 0.0, f32))
-            out.append((p + "layer_norm.weight", (E,), 0.1, 1.0, f32))
-            out.append((p + "layer_norm.bias", (E,), 0.1, 0.0, f32))
-            for i in range(d.pool_layers):
-                q = p + f"blocks.{i}."
-                out.append((q + "attention.q_proj_weight", (E, E), 1.0 / math.sqrt(E), 0.0, f32))
-                out.append((q + "attention.k_proj_weight", (E, Wd), 4.0 / math.sqrt(Wd), 0.0, f32))
-                out.append((q + "attention.v_proj_weight", (E, Wd), 4.0 / math.sqrt(Wd), 0.0, f32))
-                out.append((q + "attention.in_proj_bias", (3 * E,), 0.05, 0.0, f32))
-                out.append((q + "attention.out_proj.weight", (E, E), 1.0 / math.sqrt(E), 0.0, f32))
-                out.append((q + "attention.out_proj.bias", (E,), 0.05, 0.0, f32))
-                out.append((q + "mlp.fc1.weight", (E, E), 1.0 / math.sqrt(E), 0.0, f32))
-                out.append((q + "mlp.fc1.bias", (E,), 0.05, 0.0, f32))
-                out.append((q + "mlp.fc2.weight", (E, E), 1.0 / math.sqrt(E), 0.0, f32))
-                out.append((q + "mlp.fc2.bias", (E,), 0.05, 0.0, f32))
-                for nm in ("q_layer_norm", "layer_norm"):
-                    out.append((q + nm + ".weight", (E,), 0.1, 1.0, f32))
-                    out.append((q + nm + ".bias", (E,), 0.1, 0.0, f32))
-        out.append((b + "input_projection.weight", (E, 2 * E), 1.0 / math.sqrt(2 * E), 0.0, f32))
-        out.append((b + "input_projection.bias", (E,), 0.05, 0.0, f32))
-        out.append((b + "single_step_action_encoder.weight", (E, d.action_dim), 1.0 / math.sqrt(d.action_dim), 0.0, f32))
-        out.append((b + "single_step_action_encoder.bias", (E,), 0.05, 0.0, f32))
-        for i in range(d.traj_layers):
-            q = b + f"trajectory_encoder.layers.{i}."
-            out.append((q + "self_attn.in_proj_weight", (3 * E, E), 1.0 / math.sqrt(E), 0.0, f32))
-            out.append((q + "self_attn.in_proj_bias", (3 * E,), 0.05, 0.0, f32))
-            out.append((q + "self_attn.out_proj.weight", (E, E), 1.0 / math.sqrt(E), 0.0, f32))
-            out.append((q + "self_attn.out_proj.bias", (E,), 0.05, 0.0, f32))
-            out.append((q + "linear1.weight", (d.traj_ff, E), 1.0 / math.sqrt(E), 0.0, f32))
-            out.append((q + "linear1.bias", (d.traj_ff,), 0.05, 0.0, f32))
-            out.append((q + "linear2.weight", (E, d.traj_ff), 1.0 / math.sqrt(d.traj_ff), 0.0, f32))
-            out.append((q + "linear2.bias", (E,), 0.05, 0.0, f32))
-            for nm in ("norm1", "norm2"):
-                out.append((q + nm + ".weight", (E,), 0.1, 1.0, f32))
-                out.append((q + nm + ".bias", (E,), 0.1, 0.0, f32))
-    return out
-
-
-def sincos_position_embedding(seq_len: int, dim: int) -> torch.Tensor:
-    # model.py:40-47
-    pos = torch.arange(seq_len).float()
-    inv_freq = 1.0 / (10000 ** (torch.arange(0, dim, 2).float() / dim))
-    sinusoid_inp = torch.einsum("i,j->ij", pos, inv_freq)
-    return torch.cat((sinusoid_inp.sin(), sinusoid_inp.cos()), dim=-1)
-
-
-def make_verifier_weights(d: VerifierDims, seed: int = 0, trunk: bool = True) -> dict:
-    w = {}
-    specs = head_specs(d) + (trunk_specs(d) if trunk else [])
-    for k, shape, std, mean, dtype in specs:
-        if k.endswith("text_aware_visual_extraction.pos_emb"):
-            w[k] = sincos_position_embedding(d.n_patches, d.width)
-        elif shape == ():
-            w[k] = torch.tensor(mean, dtype=dtype)
-        else:
-            w[k] = _gen(k, seed + 77, shape, std, dtype, mean)
-    return w
+from cover_vla_b200.synthetic import (TR, VFULL, VMID, VTINY, VerifierDims, head_specs, make_verifier_weights,  # noqa: F401
+                                      pad_histories, sincos_position_embedding, trunk_specs)
+from cover_vla_b200.synthetic import make_verifier_inputs as make_inputs  # noqa: F401
 
 
 # ------------------------------------------------------------------------------------------------
@@ -332,17 +184,6 @@ def trajectory_embedding(w, m: int, d: VerifierDims, traj, pad_value=-5.0):
     return t / t.norm(dim=-1, keepdim=True)
 
 
-def pad_histories(histories, history: int = 10):
-    # efficient_ensemble_merged.py:379-390 (left-pad with -5 to 10 steps)
-    out = []
-    for ah in histories:
-        ah = np.asarray(ah)
-        if len(ah) < history:
-            ah = np.vstack([np.ones((history - len(ah), ah.shape[1])) * -5, ah])
-        out.append(ah)
-    return torch.tensor(np.array(out), dtype=torch.float32)
-
-
 @torch.no_grad()
 def scores_from_features(w, d: VerifierDims, patch, text, traj):
     """fused scores [N] for ONE (image, instruction) against N trajectories (row 0 of the matrix)."""
@@ -375,16 +216,3 @@ def compute_max_similarity_scores(w, d: VerifierDims, image, tokens, histories, 
     return best, idx, scores, means
 
 
-# ------------------------------------------------------------------------------------------------
-def make_inputs(d: VerifierDims, N: int, seed: int = 0):
-    g = torch.Generator().manual_seed(2000 + seed)
-    image = torch.rand(1, 3, d.image, d.image, generator=g) * 2 - 1
-    tokens = torch.randint(1, d.vocab - 1, (1, d.text_ctx), generator=g)
-    hist = []
-    for n in range(N):
-        T = int(torch.randint(4, d.history + 1, (1,), generator=g))
-        a = torch.rand(T, d.action_dim, generator=g) * 2 - 1
-        a[:, :6] *= 0.05
-        a[:, 6] = (a[:, 6] > 0).float()
-        hist.append(a.numpy())
-    return dict(image=image, tokens=tokens, histories=hist)

@@ -43,4 +43,22 @@ int cvb_op_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int
   return cvb::gemm_bf16((cudaStream_t)stream, c);
 }
 
+
+int cvb_op_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k0, const void* v0, int64_t kv0_bs,
+                     int64_t kv0_rs, const int32_t* kv0_len_dev, int kv0_len, int kv0_max, int q_per_kv_batch,
+                     const void* k1, const void* v1, int64_t kv1_bs, int64_t kv1_rs, int kv1_len, int suffix_mask,
+                     void* out, int64_t o_bs, int64_t o_rs, int batches, int heads, int kv_heads, int tq,
+                     int head_dim, float scale, int force_two_pass, void* stream) {
+  cvb::AttnCall c;
+  c.q = (const cvb::bf16*)q, c.q_batch_stride = q_bs, c.q_row_stride = q_rs;
+  c.k0 = (const cvb::bf16*)k0, c.v0 = (const cvb::bf16*)v0, c.kv0_batch_stride = kv0_bs, c.kv0_row_stride = kv0_rs;
+  c.kv0_len_dev = kv0_len_dev, c.kv0_len = kv0_len, c.kv0_max = kv0_max, c.q_per_kv_batch = q_per_kv_batch;
+  c.k1 = (const cvb::bf16*)k1, c.v1 = (const cvb::bf16*)v1, c.kv1_batch_stride = kv1_bs, c.kv1_row_stride = kv1_rs;
+  c.kv1_len = kv1_len, c.suffix_mask = suffix_mask;
+  c.out = (cvb::bf16*)out, c.o_batch_stride = o_bs, c.o_row_stride = o_rs;
+  c.batches = batches, c.heads = heads, c.kv_heads = kv_heads, c.tq = tq, c.head_dim = head_dim, c.scale = scale;
+  c.force_two_pass = force_two_pass;
+  return cvb::attention((cudaStream_t)stream, c);
+}
+
 }  // extern "C"

@@ -346,7 +346,7 @@ static int run_prefix(cvb_handle* h, cudaStream_t st, int R) {
     AttnCall a;
     a.q = s.qkv_p, a.q_batch_stride = (long)P * qkvw, a.q_row_stride = qkvw;
     a.k0 = kc, a.v0 = vc, a.kv0_batch_stride = (long)P * hd, a.kv0_row_stride = hd;
-    a.kv0_len_dev = s.plen, a.q_per_kv_batch = 1;
+    a.kv0_len_dev = s.plen, a.kv0_max = P, a.q_per_kv_batch = 1;
     a.out = s.attn_p, a.o_batch_stride = (long)P * qd, a.o_row_stride = qd;
     a.batches = R, a.heads = c.heads, a.kv_heads = 1, a.tq = P, a.head_dim = hd;
     a.scale = 1.0f / sqrtf(static_cast<float>(hd));
@@ -414,7 +414,7 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
       AttnCall a;
       a.q = s.qkv_e, a.q_batch_stride = (long)S * qkvw, a.q_row_stride = qkvw;
       a.k0 = s.kcache + l * layer_stride, a.v0 = s.vcache + l * layer_stride;
-      a.kv0_batch_stride = (long)P * hd, a.kv0_row_stride = hd, a.kv0_len_dev = s.plen;
+      a.kv0_batch_stride = (long)P * hd, a.kv0_row_stride = hd, a.kv0_len_dev = s.plen, a.kv0_max = P;
       a.q_per_kv_batch = K;
       a.k1 = s.qkv_e + qd, a.v1 = s.qkv_e + qd + hd, a.kv1_batch_stride = (long)S * qkvw;
       a.kv1_row_stride = qkvw, a.kv1_len = S, a.suffix_mask = 1;

@@ -72,6 +72,8 @@ struct AttnCall {
   long kv0_batch_stride = 0, kv0_row_stride = 0;
   const int* kv0_len_dev = nullptr;  // [kv batches] valid keys in segment 0 (nullptr -> kv0_len)
   int kv0_len = 0;
+  int kv0_max = 0;  // upper bound of kv0_len_dev[] (sizes the logits buffer of the fast path)
+  int force_two_pass = 0;
   int q_per_kv_batch = 1;  // kv batch index = b / q_per_kv_batch
   // optional segment 1 (per q-batch, e.g. the suffix tokens' own keys): tq1 keys
   const bf16* k1 = nullptr;

@@ -251,6 +251,199 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_kernel(const AttnParams p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Fast path: K and V each stream through shared memory ONCE (cp.async, double buffered); the scaled and
+// masked logits of the whole row are parked in shared memory in each thread's own mma-fragment order, so
+// the exact softmax statistics are known before P is rounded to bf16 and no Q.K^T is recomputed.
+// Used whenever the logits fit (keys <= ~384 at head_dim 256, ~900 at head_dim 64).
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int HDP>
+__device__ __forceinline__ void issue_tile(const AttnParams& p, bf16* dst, int tile, bool is_v, int n0, int nk,
+                                           int b, int kvb, int kvh) {
+  constexpr int LDS = HDP + 8;
+  constexpr int CH = HDP / 8;
+  for (int idx = threadIdx.x; idx < BKV * CH; idx += ATT_THREADS) {
+    const int r = idx / CH, c = (idx % CH) * 8;
+    const int j = tile * BKV + r;
+    const bool valid = j < nk && c < p.head_dim;
+    const bf16* src = p.q;
+    if (valid) {
+      if (j < n0)
+        src = (is_v ? p.v0 : p.k0) + kvb * p.kv0_bs + j * p.kv0_rs + kvh * p.head_dim + c;
+      else
+        src = (is_v ? p.v1 : p.k1) + b * p.kv1_bs + (j - n0) * p.kv1_rs + kvh * p.head_dim + c;
+    }
+    cp_async16(smem_u32(dst + r * LDS + c), src, valid);
+  }
+}
+
+template <int HDP>
+__global__ void __launch_bounds__(ATT_THREADS) attn_smem_kernel(const AttnParams p) {
+  constexpr int LDS = HDP + 8;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
+  bf16* KV = Qs + BQ * LDS;                                   // 2 stages of [64][LDS]
+  float* Sp = reinterpret_cast<float*>(KV + 2 * BKV * LDS);   // [tile][32][128] thread-private logits
+
+  const int b = blockIdx.z, kvh = blockIdx.y, qt = blockIdx.x;
+  const int G = p.heads / p.kv_heads;
+  const int rows_total = G * p.tq;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kvb = b / p.q_per_kv_batch;
+  const int n0 = p.kv0_len_dev != nullptr ? p.kv0_len_dev[kvb] : p.kv0_len;
+  const int nk = n0 + p.kv1_len;
+  const int n_tiles = (nk + BKV - 1) / BKV;
+
+  {  // Q tile + first K tile
+    constexpr int CH = HDP / 8;
+    for (int idx = threadIdx.x; idx < BQ * CH; idx += ATT_THREADS) {
+      const int r = idx / CH, c = (idx % CH) * 8;
+      const int i = qt * BQ + r;
+      const bool valid = i < rows_total && c < p.head_dim;
+      const bf16* src = p.q;
+      if (valid) src = p.q + b * p.q_bs + (i % p.tq) * p.q_rs + (kvh * G + i / p.tq) * p.head_dim + c;
+      cp_async16(smem_u32(Qs + r * LDS + c), src, valid);
+    }
+    issue_tile<HDP>(p, KV, 0, false, n0, nk, b, kvb, kvh);
+    cp_async_commit();
+  }
+
+  const int r_lo = qt * BQ + warp * 16 + (lane >> 2);
+  const int r_hi = r_lo + 8;
+  const int t_lo = r_lo % p.tq, t_hi = r_hi % p.tq;
+  auto key_ok = [&](int j, int t) -> bool {
+    if (j >= nk) return false;
+    if (p.suffix_mask && j >= n0 && t == 0) return (j - n0) == 0;
+    return true;
+  };
+
+  float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+  float o[HDP / 8][4];
+#pragma unroll
+  for (int dt = 0; dt < HDP / 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+  float inv_lo = 0.f, inv_hi = 0.f;
+  const int mi = lane >> 3, ri = lane & 7;
+
+  // items 0..n_tiles-1 = K tiles (logits), n_tiles..2*n_tiles-1 = V tiles (P @ V)
+  for (int it = 0; it < 2 * n_tiles; ++it) {
+    const int nxt = it + 1;
+    if (nxt < 2 * n_tiles)
+      issue_tile<HDP>(p, KV + (nxt & 1) * BKV * LDS, nxt % n_tiles, nxt >= n_tiles, n0, nk, b, kvb, kvh);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const bf16* buf = KV + (it & 1) * BKV * LDS;
+    if (it < n_tiles) {
+      const int tile = it;
+      float s[8][4];
+      qk_tile<HDP>(Qs, buf, warp, lane, s);
+      float tm_lo = -INFINITY, tm_hi = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = tile * BKV + nt * 8 + (lane & 3) * 2 + e;
+          s[nt][e] = key_ok(j, t_lo) ? s[nt][e] * p.scale : -INFINITY;
+          s[nt][2 + e] = key_ok(j, t_hi) ? s[nt][2 + e] * p.scale : -INFINITY;
+          tm_lo = fmaxf(tm_lo, s[nt][e]);
+          tm_hi = fmaxf(tm_hi, s[nt][2 + e]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) Sp[((tile * 8 + nt) * 4 + e) * ATT_THREADS + threadIdx.x] = s[nt][e];
+      }
+      tm_lo = fmaxf(tm_lo, __shfl_xor_sync(0xffffffffu, tm_lo, 1));
+      tm_lo = fmaxf(tm_lo, __shfl_xor_sync(0xffffffffu, tm_lo, 2));
+      tm_hi = fmaxf(tm_hi, __shfl_xor_sync(0xffffffffu, tm_hi, 1));
+      tm_hi = fmaxf(tm_hi, __shfl_xor_sync(0xffffffffu, tm_hi, 2));
+      const float nm_lo = fmaxf(m_lo, tm_lo), nm_hi = fmaxf(m_hi, tm_hi);
+      float ts_lo = 0.f, ts_hi = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          ts_lo += (s[nt][e] == -INFINITY) ? 0.f : expf(s[nt][e] - nm_lo);
+          ts_hi += (s[nt][2 + e] == -INFINITY) ? 0.f : expf(s[nt][2 + e] - nm_hi);
+        }
+      }
+      ts_lo += __shfl_xor_sync(0xffffffffu, ts_lo, 1);
+      ts_lo += __shfl_xor_sync(0xffffffffu, ts_lo, 2);
+      ts_hi += __shfl_xor_sync(0xffffffffu, ts_hi, 1);
+      ts_hi += __shfl_xor_sync(0xffffffffu, ts_hi, 2);
+      l_lo = (m_lo == -INFINITY ? 0.f : l_lo * expf(m_lo - nm_lo)) + ts_lo;
+      l_hi = (m_hi == -INFINITY ? 0.f : l_hi * expf(m_hi - nm_hi)) + ts_hi;
+      m_lo = nm_lo, m_hi = nm_hi;
+      if (it == n_tiles - 1) {
+        inv_lo = l_lo > 0.f ? 1.0f / l_lo : 0.f;
+        inv_hi = l_hi > 0.f ? 1.0f / l_hi : 0.f;
+      }
+    } else {
+      const int tile = it - n_tiles;
+      uint32_t pa[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        float sv[4], pv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sv[e] = Sp[((tile * 8 + nt) * 4 + e) * ATT_THREADS + threadIdx.x];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          pv[e] = sv[e] == -INFINITY ? 0.f : expf(sv[e] - m_lo) * inv_lo;
+          pv[2 + e] = sv[2 + e] == -INFINITY ? 0.f : expf(sv[2 + e] - m_hi) * inv_hi;
+        }
+        pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(pv[0], pv[1]);
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(pv[2], pv[3]);
+      }
+      const uint32_t v_base = smem_u32(buf + ((mi & 1) * 8 + ri) * LDS + (mi >> 1) * 8);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int dp = 0; dp < HDP / 16; ++dp) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_t(v_base + (kk * 16 * LDS) * 2 + dp * 32, b0, b1, b2, b3);
+          mma_bf16(o[2 * dp], pa[kk][0], pa[kk][1], pa[kk][2], pa[kk][3], b0, b1);
+          mma_bf16(o[2 * dp + 1], pa[kk][0], pa[kk][1], pa[kk][2], pa[kk][3], b2, b3);
+        }
+      }
+    }
+    __syncthreads();  // the buffer just consumed is refilled by the next iteration's prefetch
+  }
+
+  const bool ok_lo = r_lo < rows_total, ok_hi = r_hi < rows_total;
+  bf16* o_lo = p.out + b * p.o_bs + t_lo * p.o_rs + (kvh * G + r_lo / p.tq) * p.head_dim;
+  bf16* o_hi = p.out + b * p.o_bs + t_hi * p.o_rs + (kvh * G + r_hi / p.tq) * p.head_dim;
+#pragma unroll
+  for (int dt = 0; dt < HDP / 8; ++dt) {
+    const int d = dt * 8 + (lane & 3) * 2;
+    if (d < p.head_dim) {
+      if (ok_lo) *reinterpret_cast<uint32_t*>(o_lo + d) = pack_bf16x2(o[dt][0], o[dt][1]);
+      if (ok_hi) *reinterpret_cast<uint32_t*>(o_hi + d) = pack_bf16x2(o[dt][2], o[dt][3]);
+    }
+  }
+}
+
+template <int HDP>
+int launch_attn_smem(cudaStream_t st, const AttnParams& p, dim3 grid, int max_tiles) {
+  const int smem = (BQ + 2 * BKV) * (HDP + 8) * 2 + max_tiles * 32 * ATT_THREADS * 4;
+  auto kern = attn_smem_kernel<HDP>;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  kern<<<grid, ATT_THREADS, smem, st>>>(p);
+  CVB_LAUNCHED();
+  return 0;
+}
+
 template <int HDP>
 int launch_attn(cudaStream_t st, const AttnParams& p, dim3 grid) {
   constexpr int SMEM = (BQ + 2 * BKV) * (HDP + 8) * 2;
@@ -283,9 +476,21 @@ int attention(cudaStream_t st, const AttnCall& c) {
   p.scale = c.scale;
   const int G = c.heads / c.kv_heads;
   dim3 grid((G * c.tq + BQ - 1) / BQ, c.kv_heads, c.batches);
-  if (c.head_dim <= 64) return launch_attn<64>(st, p, grid);
-  if (c.head_dim <= 80) return launch_attn<80>(st, p, grid);
-  if (c.head_dim <= 128) return launch_attn<128>(st, p, grid);
+  // logits-in-smem fast path when the whole key range fits next to the Q / K / V tiles
+  const int hdp = c.head_dim <= 64 ? 64 : c.head_dim <= 80 ? 80 : c.head_dim <= 128 ? 128 : 256;
+  const int max_keys = (c.kv0_len_dev != nullptr ? c.kv0_max : c.kv0_len) + p.kv1_len;
+  const int max_tiles = (max_keys + BKV - 1) / BKV;
+  const long smem_fast = (long)(BQ + 2 * BKV) * (hdp + 8) * 2 + (long)max_tiles * 32 * ATT_THREADS * 4;
+  if (c.kv0_len_dev != nullptr) CVB_REQUIRE(c.kv0_max > 0, "kv0_max (upper bound of the device-side length) is required");
+  if (smem_fast <= 220 * 1024 && !c.force_two_pass) {
+    if (hdp == 64) return launch_attn_smem<64>(st, p, grid, max_tiles);
+    if (hdp == 80) return launch_attn_smem<80>(st, p, grid, max_tiles);
+    if (hdp == 128) return launch_attn_smem<128>(st, p, grid, max_tiles);
+    return launch_attn_smem<256>(st, p, grid, max_tiles);
+  }
+  if (hdp == 64) return launch_attn<64>(st, p, grid);
+  if (hdp == 80) return launch_attn<80>(st, p, grid);
+  if (hdp == 128) return launch_attn<128>(st, p, grid);
   return launch_attn<256>(st, p, grid);
 }
 

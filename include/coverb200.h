@@ -46,6 +46,17 @@ CVB_API int cvb_op_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
                      const void* resid, int resid_is_f32, int64_t ldr, int n_out,
                      const int32_t* m_dev, int force_bn, void* stream);
 
+/* Exact-softmax attention with the reference's rounding ledger (eager_attention_forward,
+ * paligemma_with_expert.py:376-434): q [batches, tq, heads*head_dim] (strides q_bs / q_rs in elements), keys in two
+ * segments - segment 0 shared per kv batch (kv batch = batch / q_per_kv_batch; length from kv0_len_dev[kv batch] or
+ * kv0_len), segment 1 per batch (e.g. the suffix tokens' own keys) with the pi0 suffix mask when suffix_mask = 1. */
+CVB_API int cvb_op_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k0, const void* v0, int64_t kv0_bs,
+                             int64_t kv0_rs, const int32_t* kv0_len_dev, int kv0_len, int kv0_max,
+                             int q_per_kv_batch, const void* k1, const void* v1, int64_t kv1_bs, int64_t kv1_rs,
+                             int kv1_len, int suffix_mask, void* out, int64_t o_bs, int64_t o_rs, int batches,
+                             int heads, int kv_heads, int tq, int head_dim, float scale, int force_two_pass,
+                             void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Engine level.  One handle per (device, stream); a handle is not thread-safe, the library is
  * re-entrant across handles.  All sizes are configuration, nothing is hard-coded to the Bridge

@@ -1,0 +1,63 @@
+"""Attention kernels (fast logits-in-smem path and two-pass fallback) vs a plain PyTorch fp32 reference."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(q, k, v, heads, kv_heads, hd, mask):
+    B, Tq, _ = q.shape
+    Tk = k.shape[1]
+    g = heads // kv_heads
+    qf = q.float().view(B, Tq, heads, hd).transpose(1, 2)
+    kf = k.float().view(B, Tk, kv_heads, hd).transpose(1, 2).repeat_interleave(g, dim=1)
+    vf = v.float().view(B, Tk, kv_heads, hd).transpose(1, 2).repeat_interleave(g, dim=1)
+    att = qf @ kf.transpose(-1, -2) * hd ** -0.5
+    att = att.masked_fill(~mask[:, None], float("-inf"))
+    p = torch.softmax(att, dim=-1).to(torch.bfloat16).float()
+    return (p @ vf).transpose(1, 2).reshape(B, Tq, heads * hd)
+
+
+@pytest.mark.parametrize("two_pass", [False, True])
+@pytest.mark.parametrize("B,Tq,Tk,heads,kvh,hd", [(1, 256, 256, 16, 16, 72), (3, 328, 328, 8, 1, 256),
+                                                   (1, 576, 576, 16, 16, 64), (2, 64, 64, 4, 4, 64), (2, 100, 77, 2, 1, 128)])
+def test_self_attention(B, Tq, Tk, heads, kvh, hd, two_pass):
+    from cover_vla_b200 import ops
+    torch.manual_seed(B * 1000 + Tq + hd)
+    q = torch.randn(B, Tq, heads * hd, device="cuda").to(torch.bfloat16)
+    k = torch.randn(B, Tk, kvh * hd, device="cuda").to(torch.bfloat16)
+    v = torch.randn(B, Tk, kvh * hd, device="cuda").to(torch.bfloat16)
+    lens = torch.randint(Tk // 2, Tk + 1, (B,), device="cuda", dtype=torch.int32)
+    out = ops.attention(q, k, v, heads=heads, kv_heads=kvh, head_dim=hd, kv0_len_dev=lens, force_two_pass=two_pass)
+    mask = (torch.arange(Tk, device="cuda")[None, :] < lens[:, None])[:, None, :].expand(B, Tq, Tk)
+    ref = _ref(q, k, v, heads, kvh, hd, mask)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2, err
+    assert ((out.float() - ref).norm() / ref.norm()).item() < 5e-3
+
+
+@pytest.mark.parametrize("two_pass", [False, True])
+def test_denoise_attention_two_segments(two_pass):
+    """N candidates x 5 suffix tokens against the rephrase's prefix cache + own suffix keys (pi0 mask)."""
+    from cover_vla_b200 import ops
+    torch.manual_seed(7)
+    R, K, S, P, heads, hd = 3, 4, 5, 328, 8, 256
+    N = R * K
+    q = torch.randn(N, S, heads * hd, device="cuda").to(torch.bfloat16)
+    k0 = torch.randn(R, P, hd, device="cuda").to(torch.bfloat16)
+    v0 = torch.randn(R, P, hd, device="cuda").to(torch.bfloat16)
+    k1 = torch.randn(N, S, hd, device="cuda").to(torch.bfloat16)
+    v1 = torch.randn(N, S, hd, device="cuda").to(torch.bfloat16)
+    lens = torch.tensor([270, 328, 300], device="cuda", dtype=torch.int32)
+    out = ops.attention(q, k0, v0, heads=heads, kv_heads=1, head_dim=hd, kv0_len_dev=lens, q_per_kv_batch=K,
+                        k1=k1, v1=v1, suffix_mask=True, force_two_pass=two_pass)
+    for n in range(N):
+        r = n // K
+        L = int(lens[r])
+        kk = torch.cat([k0[r, :L], k1[n]])[None]
+        vv = torch.cat([v0[r, :L], v1[n]])[None]
+        mask = torch.ones(1, S, L + S, dtype=torch.bool, device="cuda")
+        mask[0, 0, L + 1:] = False  # the state token only sees itself among the suffix keys
+        ref = _ref(q[n:n + 1], kk, vv, heads, 1, hd, mask)
+        err = (out[n:n + 1].float() - ref).abs().max().item()
+        assert err < 2e-2, (n, err)

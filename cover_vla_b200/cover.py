@@ -66,14 +66,30 @@ class CoverStep:
         self.K = samples_per_rephrase
         self.n_future = n_future or engine.cfg.chunk_size
         self.p01, self.p99 = p01, p99
+        # the verifier's image/text side does not depend on the sampled actions: it runs on a second stream,
+        # concurrently with the (latency-bound, SM-underfilling) denoise loop of the sampler
+        self.overlap_context = True
+        self._side = torch.cuda.Stream(device=engine.device)
 
     def sample_and_score(self, x: CoverInputs, select: bool = True):
         """Asynchronous; returns device tensors (actions, traj, scores, group_mean, best_idx, best_score)."""
         e = self.engine
-        actions = e.pi0_sample(x.image, x.lang_tokens, x.lang_len, x.state, x.noise, K=self.K)
-        traj = format_trajectories(actions, x.past, e.cfg.vf_history, self.n_future, self.p01, self.p99)
         R = x.lang_tokens.shape[0]
-        scores, gmean, bidx, bscore = e.verifier_score(x.vf_image, x.vf_tokens, traj, R if select else 0, self.K)
+        if self.overlap_context:
+            cur = torch.cuda.current_stream(e.device)
+            self._side.wait_stream(cur)
+            # critical path first: one graph launch for the whole sampler, then the side work
+            actions = e.pi0_sample(x.image, x.lang_tokens, x.lang_len, x.state, x.noise, K=self.K)
+            with torch.cuda.stream(self._side):
+                e.verifier_context(x.vf_image, x.vf_tokens)
+            traj = format_trajectories(actions, x.past, e.cfg.vf_history, self.n_future, self.p01, self.p99)
+            cur.wait_stream(self._side)
+            scores, gmean, bidx, bscore = e.verifier_score(None, None, traj, R if select else 0, self.K,
+                                                           recompute_context=False)
+        else:
+            actions = e.pi0_sample(x.image, x.lang_tokens, x.lang_len, x.state, x.noise, K=self.K)
+            traj = format_trajectories(actions, x.past, e.cfg.vf_history, self.n_future, self.p01, self.p99)
+            scores, gmean, bidx, bscore = e.verifier_score(x.vf_image, x.vf_tokens, traj, R if select else 0, self.K)
         return actions, traj, scores, gmean, bidx, bscore
 
     def __call__(self, x: CoverInputs, gate_threshold: float = 0.1):

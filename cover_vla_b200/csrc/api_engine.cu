@@ -69,8 +69,7 @@ int cvb_create(const cvb_config* cfg, cvb_handle** out) {
 
 void cvb_destroy(cvb_handle* h) {
   if (h == nullptr) return;
-  for (auto& g : h->pi0.graphs) cudaGraphExecDestroy(g.second);
-  if (h->pi0.cap_stream) cudaStreamDestroy(h->pi0.cap_stream);
+  h->pi0.graphs.destroy();
   cvb::verifier_destroy(h);
   for (void* p : h->owned) cudaFree(p);
   delete h;
@@ -149,6 +148,11 @@ int cvb_verifier_score(cvb_handle* h, const float* image, const int64_t* text_to
   CVB_REQUIRE(h != nullptr, "null handle");
   return cvb::verifier_score(h, image, text_tokens, traj, N, R, K, scores, group_mean, best_idx, best_score,
                              recompute_context, (cudaStream_t)stream);
+}
+
+int cvb_verifier_context(cvb_handle* h, const float* image, const int64_t* text_tokens, void* stream) {
+  CVB_REQUIRE(h != nullptr, "null handle");
+  return cvb::verifier_context(h, image, text_tokens, (cudaStream_t)stream);
 }
 
 int cvb_verifier_set_features(cvb_handle* h, const float* patch, const float* text, void* stream) {

@@ -41,6 +41,50 @@ struct GemmaLayer {
   const bf16* wd;
 };
 
+// Per-shape CUDA-graph cache: the first call of a shape runs eagerly (sets kernel attributes, fills the
+// tensor-map cache), the second is captured on a private stream (the caller's may be the legacy default
+// stream, which cannot be captured), later calls replay the instantiated graph on the caller's stream.
+struct GraphCache {
+  std::unordered_map<long, cudaGraphExec_t> graphs;
+  std::unordered_map<long, int> warm;
+  cudaStream_t cap_stream = nullptr;
+  template <typename F>
+  int run(bool enabled, long key, cudaStream_t st, F&& body) {
+    if (!enabled) return body(st);
+    auto it = graphs.find(key);
+    if (it != graphs.end()) {
+      CVB_CUDA(cudaGraphLaunch(it->second, st));
+      return 0;
+    }
+    if (warm[key] == 0) {
+      warm[key] = 1;
+      return body(st);
+    }
+    if (cap_stream == nullptr) CVB_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    CVB_CUDA(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = body(cap_stream);
+    const cudaError_t e = cudaStreamEndCapture(cap_stream, &graph);
+    if (rc != 0) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    CVB_CUDA(e);
+    cudaGraphExec_t exec = nullptr;
+    CVB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    graphs[key] = exec;
+    CVB_CUDA(cudaGraphLaunch(exec, st));
+    return 0;
+  }
+  void destroy() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+    graphs.clear();
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+    cap_stream = nullptr;
+  }
+};
+
 struct Pi0State {
   // packed / derived weights
   bf16* w_patch = nullptr;  // [Wv, kpad]
@@ -66,9 +110,7 @@ struct Pi0State {
   bf16 *kcache = nullptr, *vcache = nullptr;
   float *state_emb = nullptr, *a1 = nullptr, *a2 = nullptr, *suffix = nullptr, *v0 = nullptr;
   bf16 *he = nullptr, *xe = nullptr, *qkv_e = nullptr, *attn_e = nullptr, *act_e = nullptr;
-  std::unordered_map<long, cudaGraphExec_t> graphs;  // key = R * 65536 + K
-  std::unordered_map<long, int> warm;                // eager runs done per key
-  cudaStream_t cap_stream = nullptr;
+  GraphCache graphs;  // key = R * 65536 + K
 };
 
 struct VerifierState;  // engine_verifier.cu
@@ -114,6 +156,7 @@ void verifier_destroy(cvb_handle* h);
 int verifier_score(cvb_handle* h, const float* image, const int64_t* tokens, const float* traj, int N, int R, int K,
                    float* scores, float* group_mean, int32_t* best_idx, float* best_score, int recompute_context,
                    cudaStream_t st);
+int verifier_context(cvb_handle* h, const float* image, const int64_t* tokens, cudaStream_t st);
 int64_t verifier_debug_copy(cvb_handle* h, const std::string& name, void* dst, int64_t max_bytes, cudaStream_t st);
 int verifier_set_features(cvb_handle* h, const float* patch, const float* text, cudaStream_t st);
 

@@ -460,39 +460,7 @@ int pi0_sample(cvb_handle* h, const float* image, const int64_t* tokens, const i
   CVB_CUDA(cudaMemcpyAsync(s.x_t, noise, act_bytes, cudaMemcpyDeviceToDevice, st));
 
   const long key = (long)R * 65536 + K;
-  if (!c.use_cuda_graph) {
-    CVB_TRY(run_all(h, st, R, K));
-  } else {
-    auto it = s.graphs.find(key);
-    if (it == s.graphs.end()) {
-      if (s.warm[key] == 0) {
-        // first call for this shape runs eagerly: sets kernel attributes, fills the tensor-map cache
-        s.warm[key] = 1;
-        CVB_TRY(run_all(h, st, R, K));
-      } else {
-        // capture on a private stream (the caller's may be the legacy default stream, which cannot
-        // be captured); the instantiated graph is then launched on the caller's stream
-        if (s.cap_stream == nullptr)
-          CVB_CUDA(cudaStreamCreateWithFlags(&s.cap_stream, cudaStreamNonBlocking));
-        cudaGraph_t graph = nullptr;
-        CVB_CUDA(cudaStreamBeginCapture(s.cap_stream, cudaStreamCaptureModeThreadLocal));
-        int rc = run_all(h, s.cap_stream, R, K);
-        cudaError_t e = cudaStreamEndCapture(s.cap_stream, &graph);
-        if (rc != 0) {
-          if (graph) cudaGraphDestroy(graph);
-          return rc;
-        }
-        CVB_CUDA(e);
-        cudaGraphExec_t exec = nullptr;
-        CVB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-        cudaGraphDestroy(graph);
-        s.graphs[key] = exec;
-        CVB_CUDA(cudaGraphLaunch(exec, st));
-      }
-    } else {
-      CVB_CUDA(cudaGraphLaunch(it->second, st));
-    }
-  }
+  CVB_TRY(s.graphs.run(c.use_cuda_graph != 0, key, st, [&](cudaStream_t cs) { return run_all(h, cs, R, K); }));
   CVB_CUDA(cudaMemcpyAsync(actions, s.x_t, act_bytes, cudaMemcpyDeviceToDevice, st));
   return 0;
 }

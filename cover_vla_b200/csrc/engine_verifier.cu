@@ -50,7 +50,11 @@ struct VerifierState {
         *kv_t = nullptr, *vtok = nullptr, *ttok = nullptr, *it = nullptr;
   float *tx = nullptr, *tqkv = nullptr, *tatt = nullptr, *ty = nullptr, *tff = nullptr, *act = nullptr;
   float* scores = nullptr;
+  float* gmean = nullptr;
+  int* bidx = nullptr;
+  float* bscore = nullptr;
   bool context_valid = false;
+  GraphCache ctx_graph, traj_graph;
 };
 
 namespace {
@@ -275,6 +279,9 @@ int verifier_finalize(cvb_handle* h, cudaStream_t st) {
   CVB_TRY(dalloc_t(h, &s.tff, rows * c.vf_traj_ff));
   CVB_TRY(dalloc_t(h, &s.act, (size_t)M * Nm * E));
   CVB_TRY(dalloc_t(h, &s.scores, Nm));
+  CVB_TRY(dalloc_t(h, &s.gmean, Nm));
+  CVB_TRY(dalloc_t(h, &s.bidx, 1));
+  CVB_TRY(dalloc_t(h, &s.bscore, 1));
 
   // ---- heads: pack K/V projections of all pooling blocks (they only depend on the kv input)
   s.mem.resize(M);
@@ -363,6 +370,10 @@ int verifier_finalize(cvb_handle* h, cudaStream_t st) {
 }
 
 void verifier_destroy(cvb_handle* h) {
+  if (h->vf != nullptr) {
+    h->vf->ctx_graph.destroy();
+    h->vf->traj_graph.destroy();
+  }
   delete h->vf;
   h->vf = nullptr;
 }
@@ -471,14 +482,37 @@ int verifier_score(cvb_handle* h, const float* image, const int64_t* tokens, con
     CVB_CUDA(cudaMemcpyAsync(s.in_image, image, (size_t)3 * c.vf_image * c.vf_image * sizeof(float),
                              cudaMemcpyDeviceToDevice, st));
     CVB_CUDA(cudaMemcpyAsync(s.in_tokens, tokens, c.vf_text_ctx * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
-    CVB_TRY(run_context(h, st));
+    CVB_TRY(s.ctx_graph.run(c.use_cuda_graph != 0, 0, st, [&](cudaStream_t cs) { return run_context(h, cs); }));
     s.context_valid = true;
   }
   CVB_CUDA(cudaMemcpyAsync(s.in_traj, traj, (size_t)N * c.vf_history * c.vf_action_dim * sizeof(float),
                            cudaMemcpyDeviceToDevice, st));
-  CVB_TRY(run_trajectories(h, st, N));
-  CVB_TRY(fuse_score_select(st, s.it, s.act, c.vf_members, N, c.vf_embed, scores, R, K, group_mean, best_idx,
-                            best_score, R > 0 ? 1 : 0));
+  const long key = ((long)N << 32) | ((long)R << 16) | (long)K;
+  CVB_TRY(s.traj_graph.run(c.use_cuda_graph != 0, key, st, [&](cudaStream_t cs) {
+    CVB_TRY(run_trajectories(h, cs, N));
+    return fuse_score_select(cs, s.it, s.act, c.vf_members, N, c.vf_embed, s.scores, R, K, s.gmean, s.bidx, s.bscore,
+                             R > 0 ? 1 : 0);
+  }));
+  CVB_CUDA(cudaMemcpyAsync(scores, s.scores, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (R > 0) {
+    if (group_mean != nullptr)
+      CVB_CUDA(cudaMemcpyAsync(group_mean, s.gmean, R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CVB_CUDA(cudaMemcpyAsync(best_idx, s.bidx, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    CVB_CUDA(cudaMemcpyAsync(best_score, s.bscore, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+int verifier_context(cvb_handle* h, const float* image, const int64_t* tokens, cudaStream_t st) {
+  const cvb_config& c = h->cfg;
+  CVB_REQUIRE(h->finalized && h->vf != nullptr, "verifier not configured (vf_members == 0?) or not finalized");
+  CVB_REQUIRE(image != nullptr && tokens != nullptr, "image / tokens required");
+  VerifierState& s = *h->vf;
+  CVB_CUDA(cudaMemcpyAsync(s.in_image, image, (size_t)3 * c.vf_image * c.vf_image * sizeof(float),
+                           cudaMemcpyDeviceToDevice, st));
+  CVB_CUDA(cudaMemcpyAsync(s.in_tokens, tokens, c.vf_text_ctx * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  CVB_TRY(s.ctx_graph.run(c.use_cuda_graph != 0, 0, st, [&](cudaStream_t cs) { return run_context(h, cs); }));
+  s.context_valid = true;
   return 0;
 }
 

@@ -111,12 +111,34 @@ namespace {
 __device__ void matvec(float* __restrict__ out, const float* __restrict__ W, const float* __restrict__ in,
                        const float* __restrict__ bias, int n_out, int n_in) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int o = warp; o < n_out; o += nw) {
-    const float* wr = W + static_cast<long>(o) * n_in;
-    float acc = 0.f;
-    for (int i = lane; i < n_in; i += 32) acc = fmaf(wr[i], in[i], acc);
-    acc = wsum(acc);
-    if (lane == 0) out[o] = acc + (bias != nullptr ? bias[o] : 0.f);
+  if ((n_in & 127) == 0) {
+    // two output rows per warp iteration, float4 loads: 8+ independent 16-byte loads in flight per lane
+    for (int o = warp * 2; o < n_out; o += nw * 2) {
+      const float4* w0 = reinterpret_cast<const float4*>(W + static_cast<long>(o) * n_in);
+      const float4* w1 = reinterpret_cast<const float4*>(W + static_cast<long>(min(o + 1, n_out - 1)) * n_in);
+      const float4* x4 = reinterpret_cast<const float4*>(in);
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+      for (int i = lane; i < n_in / 4; i += 32) {
+        const float4 a = w0[i], b = w1[i], x = x4[i];
+        a0 = fmaf(a.x, x.x, fmaf(a.y, x.y, fmaf(a.z, x.z, fmaf(a.w, x.w, a0))));
+        a1 = fmaf(b.x, x.x, fmaf(b.y, x.y, fmaf(b.z, x.z, fmaf(b.w, x.w, a1))));
+      }
+      a0 = wsum(a0);
+      a1 = wsum(a1);
+      if (lane == 0) {
+        out[o] = a0 + (bias != nullptr ? bias[o] : 0.f);
+        if (o + 1 < n_out) out[o + 1] = a1 + (bias != nullptr ? bias[o + 1] : 0.f);
+      }
+    }
+  } else {
+    for (int o = warp; o < n_out; o += nw) {
+      const float* wr = W + static_cast<long>(o) * n_in;
+      float acc = 0.f;
+      for (int i = lane; i < n_in; i += 32) acc = fmaf(wr[i], in[i], acc);
+      acc = wsum(acc);
+      if (lane == 0) out[o] = acc + (bias != nullptr ? bias[o] : 0.f);
+    }
   }
   __syncthreads();
 }
@@ -233,42 +255,66 @@ int it_finalize(cudaStream_t st, const ItFinal* items_dev, int members, int embe
 __global__ void __launch_bounds__(256) traj_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ traj,
                                                              float* __restrict__ out, int S, int E, int H, int adim,
                                                              float pad_value) {
+  // one CTA per candidate: stage its [S, 3E] q/k/v rows in shared memory (coalesced), then one warp per
+  // head; lane = (query step, 1/2..1/8 slice of head_dim) so all 32 lanes work and reads stay conflict-light.
+  extern __shared__ float sm[];
+  float* sq = sm;                       // [S][3E]
+  float* sp = sm + S * 3 * E;           // [H][S][S] probabilities
+  __shared__ int spad[32];
   const int n = blockIdx.x, hd = E / H;
+  const float* src = qkv + static_cast<long>(n) * S * 3 * E;
+  for (int i = threadIdx.x * 4; i < S * 3 * E; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(sq + i) = *reinterpret_cast<const float4*>(src + i);
+  if (threadIdx.x < S) spad[threadIdx.x] = traj[(static_cast<long>(n) * S + threadIdx.x) * adim] == pad_value;
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   for (int h = warp; h < H; h += nw) {
+    float* ph = sp + h * S * S;
+    // scores: S*S entries spread over the 32 lanes
+    for (int e = lane; e < S * S; e += 32) {
+      const int i = e / S, j = e % S;
+      const float* qr = sq + i * 3 * E + h * hd;
+      const float* kr = sq + j * 3 * E + E + h * hd;
+      float s = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < hd; ++d) s = fmaf(qr[d], kr[d], s);
+      ph[e] = spad[j] ? -INFINITY : s * scale;
+    }
+    __syncwarp();
     if (lane < S) {
-      const float* qr = qkv + (static_cast<long>(n) * S + lane) * 3 * E + h * hd;
-      float sc[32];
       float mx = -INFINITY;
-      for (int j = 0; j < S; ++j) {
-        const bool pad = traj[(static_cast<long>(n) * S + j) * adim] == pad_value;
-        const float* kr = qkv + (static_cast<long>(n) * S + j) * 3 * E + E + h * hd;
-        float s = 0.f;
-        for (int d = 0; d < hd; ++d) s = fmaf(qr[d], kr[d], s);
-        s = pad ? -INFINITY : s * scale;
-        sc[j] = s;
-        mx = fmaxf(mx, s);
-      }
+      for (int j = 0; j < S; ++j) mx = fmaxf(mx, ph[lane * S + j]);
       float sum = 0.f;
       for (int j = 0; j < S; ++j) {
-        sc[j] = sc[j] == -INFINITY ? 0.f : expf(sc[j] - mx);
-        sum += sc[j];
+        const float v = ph[lane * S + j];
+        const float e = v == -INFINITY ? 0.f : expf(v - mx);
+        ph[lane * S + j] = e;
+        sum += e;
       }
-      float* orow = out + (static_cast<long>(n) * S + lane) * E + h * hd;
-      for (int d = 0; d < hd; ++d) {
-        float o = 0.f;
-        for (int j = 0; j < S; ++j)
-          o = fmaf(sc[j] / sum, qkv[(static_cast<long>(n) * S + j) * 3 * E + 2 * E + h * hd + d], o);
-        orow[d] = o;
-      }
+      for (int j = 0; j < S; ++j) ph[lane * S + j] = ph[lane * S + j] / sum;
+    }
+    __syncwarp();
+    // output: S*hd entries over the lanes, d fastest (coalesced stores, conflict-free V reads)
+    for (int e = lane; e < S * hd; e += 32) {
+      const int i = e / hd, d = e % hd;
+      float o = 0.f;
+      for (int j = 0; j < S; ++j) o = fmaf(ph[i * S + j], sq[j * 3 * E + 2 * E + h * hd + d], o);
+      out[(static_cast<long>(n) * S + i) * E + h * hd + d] = o;
     }
   }
 }
 int traj_attention(cudaStream_t st, const float* qkv, const float* traj, float* out, int n_cand, int S, int E, int H,
                    int adim, float pad_value) {
   CVB_REQUIRE(S <= 32, "history length must be <= 32");
-  traj_attention_kernel<<<n_cand, 256, 0, st>>>(qkv, traj, out, S, E, H, adim, pad_value);
+  CVB_REQUIRE((3 * E) % 4 == 0, "embed must be a multiple of 4");
+  const size_t smem = (static_cast<size_t>(S) * 3 * E + static_cast<size_t>(H) * S * S) * sizeof(float);
+  static size_t attr = 0;
+  if (smem > attr) {
+    CVB_CUDA(cudaFuncSetAttribute(traj_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  traj_attention_kernel<<<n_cand, 256, smem, st>>>(qkv, traj, out, S, E, H, adim, pad_value);
   CVB_LAUNCHED();
   return 0;
 }

@@ -119,6 +119,7 @@ class Engine:
         L.cvb_debug_copy.restype = C.c_int64
         L.cvb_verifier_score.argtypes = [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
         L.cvb_verifier_set_features.argtypes = [C.c_void_p] * 4
+        L.cvb_verifier_context.argtypes = [C.c_void_p] * 4
         L.cvb_select.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 
     # ------------------------------------------------------------------ weights
@@ -202,6 +203,15 @@ class Engine:
                                                    N, R, K, _lib.ptr(scores), _lib.ptr(gmean), _lib.ptr(bidx),
                                                    _lib.ptr(bscore), int(recompute_context), _lib.stream_ptr()))
         return scores, gmean, bidx, bscore
+
+    def verifier_context(self, image, text_tokens):
+        """Image/text side only (trunk + image-text heads) on the current stream; pair with
+        verifier_score(None, None, traj, ..., recompute_context=False)."""
+        cfg = self.cfg
+        assert image.dtype == torch.float32 and image.numel() == 3 * cfg.vf_image ** 2 and image.is_contiguous()
+        assert text_tokens.dtype == torch.int64 and text_tokens.numel() == cfg.vf_text_ctx
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cvb_verifier_context(self._h, _lib.ptr(image), _lib.ptr(text_tokens), _lib.stream_ptr()))
 
     def verifier_set_features(self, patch, text):
         assert patch.dtype == torch.float32 and text.dtype == torch.float32 and patch.is_cuda and text.is_cuda

@@ -128,6 +128,11 @@ CVB_API int cvb_pi0_run_phase(cvb_handle* h, int phase, int R, int K, void* stre
 CVB_API int cvb_verifier_score(cvb_handle* h, const float* image, const int64_t* text_tokens, const float* traj,
                                int N, int R, int K, float* scores, float* group_mean, int32_t* best_idx,
                                float* best_score, int recompute_context, void* stream);
+/* Only the image/text side of cvb_verifier_score (trunk + image-text heads of every member).  It does not depend
+ * on the sampled actions, so a host can enqueue it on a second stream while cvb_pi0_sample runs, then call
+ * cvb_verifier_score(..., recompute_context = 0) after joining the streams. */
+CVB_API int cvb_verifier_context(cvb_handle* h, const float* image, const int64_t* text_tokens, void* stream);
+
 /* Sampler -> verifier action formatting on the device (replaces process_inputs(verifier_action=True),
  * eval_utils.py:172-221, BridgeSimplerAdapter.postprocess_verifier, INT-ACT/src/experiments/env_adapters/
  * simpler.py:96-121, and the -5 left-padding of efficient_ensemble_merged.py:379-390).

@@ -136,13 +136,18 @@ def gather_and_select(local_scores, local_actions, R: int, K: int, select_fn, gr
             dist.all_gather_into_tensor(scores, local_scores.contiguous(), group=group)
             actions = torch.empty((R * K, *local_actions.shape[1:]), dtype=local_actions.dtype, device=local_actions.device)
             dist.all_gather_into_tensor(actions, local_actions.contiguous(), group=group)
-        else:  # ragged shards (R not divisible by the world size)
-            sl = [torch.empty(s, dtype=local_scores.dtype, device=local_scores.device) for s in sizes]
-            dist.all_gather(sl, local_scores.contiguous(), group=group)
-            scores = torch.cat(sl)
-            al = [torch.empty((s, *local_actions.shape[1:]), dtype=local_actions.dtype, device=local_actions.device) for s in sizes]
-            dist.all_gather(al, local_actions.contiguous(), group=group)
-            actions = torch.cat(al)
+        else:  # ragged shards (R not divisible by the world size): pad every slice to the largest, gather, compact
+            mx = max(sizes)
+
+            def gather_padded(local):
+                pad = torch.zeros((mx, *local.shape[1:]), dtype=local.dtype, device=local.device)
+                pad[:local.shape[0]] = local
+                buf = torch.empty((world * mx, *local.shape[1:]), dtype=local.dtype, device=local.device)
+                dist.all_gather_into_tensor(buf, pad, group=group)
+                return torch.cat([buf[r * mx:r * mx + s] for r, s in enumerate(sizes)])
+
+            scores = gather_padded(local_scores)
+            actions = gather_padded(local_actions)
     gmean, idx, score = select_fn(scores, R, K)
     return scores, actions, gmean, idx, score
 

@@ -7,6 +7,7 @@
 
 namespace cvb {
 const char* get_last_error();
+extern unsigned long long* g_skinny_ts;
 }
 
 extern "C" {
@@ -16,6 +17,8 @@ const char* cvb_last_error(void) { return cvb::get_last_error(); }
 int cvb_abi_version(void) { return CVB_ABI_VERSION; }
 
 int64_t cvb_launch_count(void) { return cvb::launch_count(); }
+
+void cvb_debug_set_timestamps(void* dev_u64) { cvb::g_skinny_ts = (unsigned long long*)dev_u64; }
 
 int cvb_op_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
                      int epilogue, void* C, int64_t ldc, const void* bias, int bias_is_f32,
@@ -48,7 +51,7 @@ int cvb_op_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k0, 
                      int64_t kv0_rs, const int32_t* kv0_len_dev, int kv0_len, int kv0_max, int q_per_kv_batch,
                      const void* k1, const void* v1, int64_t kv1_bs, int64_t kv1_rs, int kv1_len, int suffix_mask,
                      void* out, int64_t o_bs, int64_t o_rs, int batches, int heads, int kv_heads, int tq,
-                     int head_dim, float scale, int force_two_pass, void* stream) {
+                     int head_dim, float scale, int force_two_pass, const float* rope_cos_sin, void* stream) {
   cvb::AttnCall c;
   c.q = (const cvb::bf16*)q, c.q_batch_stride = q_bs, c.q_row_stride = q_rs;
   c.k0 = (const cvb::bf16*)k0, c.v0 = (const cvb::bf16*)v0, c.kv0_batch_stride = kv0_bs, c.kv0_row_stride = kv0_rs;
@@ -58,6 +61,7 @@ int cvb_op_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k0, 
   c.out = (cvb::bf16*)out, c.o_batch_stride = o_bs, c.o_row_stride = o_rs;
   c.batches = batches, c.heads = heads, c.kv_heads = kv_heads, c.tq = tq, c.head_dim = head_dim, c.scale = scale;
   c.force_two_pass = force_two_pass;
+  c.rope = reinterpret_cast<const float2*>(rope_cos_sin);
   return cvb::attention((cudaStream_t)stream, c);
 }
 

@@ -92,6 +92,7 @@ struct Pi0State {
   std::vector<VisLayer> vis;
   std::vector<GemmaLayer> lm, ex;
   float* rope_timescale = nullptr;  // [hd/2]
+  float2* rope_tab = nullptr;       // [max_rephrases][suffix_len][hd/2] (cos, sin) of the suffix positions
   float* time_vec = nullptr;        // [steps, We] = W_in[:, We:] . bf16(time_emb[s])
   float* time_emb_f32 = nullptr;    // [steps, We] (bf16-rounded values)
   std::vector<float> times;

@@ -13,6 +13,8 @@
 
 namespace cvb {
 
+bool attention_decode_eligible(const AttnCall& c);
+
 namespace {
 
 const std::string PW = "paligemma_with_expert.";
@@ -255,6 +257,7 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
   CVB_TRY(dalloc_t(h, &s.in_tokens, (size_t)Rm * c.max_lang_len));
   CVB_TRY(dalloc_t(h, &s.in_lang_len, Rm));
   CVB_TRY(dalloc_t(h, &s.plen, Rm));
+  CVB_TRY(dalloc_t(h, &s.rope_tab, (size_t)Rm * S * (c.head_dim / 2)));
   CVB_TRY(dalloc_t(h, &s.in_state, c.max_state_dim));
   CVB_TRY(dalloc_t(h, &s.x_t, (size_t)Nm * c.chunk_size * c.max_action_dim));
   CVB_TRY(dalloc_t(h, &s.v0, (size_t)Nm * c.chunk_size * c.max_action_dim));
@@ -388,6 +391,13 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
   }
   const long layer_stride = (long)c.max_rephrases * P * hd;
   const int packed = ((c.ex_mlp + 127) / 128) * 256;
+  // RoPE of the suffix is applied inside the cluster decode attention (from a table built once per sample) when the
+  // shape is eligible; otherwise by the standalone kernel
+  AttnCall probe;
+  probe.k1 = s.qkv_e, probe.kv1_len = S, probe.kv0_len_dev = s.plen, probe.kv0_max = P;
+  probe.heads = c.heads, probe.kv_heads = 1, probe.tq = S, probe.head_dim = hd;
+  const bool fused_rope = attention_decode_eligible(probe);
+  if (fused_rope) CVB_TRY(rope_table(st, s.rope_timescale, s.plen, R, S, hd / 2, s.rope_tab));
   for (size_t step = 0; step < s.times.size(); ++step) {
     {  // embed_suffix (modeling_pi0.py:598-609), time half of mlp_in folded into time_vec[step]
       SgemmCall g;
@@ -409,9 +419,10 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
       const int resid_f32 = l == 0 ? 1 : 0;
       CVB_TRY(rmsnorm(st, resid, resid_f32, We, L.in_norm, 0, s.xe, We, M, We, 1e-6f, nullptr));
       CVB_TRY(gemm(st, s.xe, We, L.wqkv, We, M, qkvw, We, EPI_STORE, s.qkv_e, qkvw));
-      CVB_TRY(rope_qkv(st, s.qkv_e, qkvw, s.rope_timescale, M, c.heads, hd, S, s.plen, K, nullptr,
-                       nullptr, 0, 0));
+      if (!fused_rope)
+        CVB_TRY(rope_qkv(st, s.qkv_e, qkvw, s.rope_timescale, M, c.heads, hd, S, s.plen, K, nullptr, nullptr, 0, 0));
       AttnCall a;
+      a.rope = fused_rope ? s.rope_tab : nullptr;
       a.q = s.qkv_e, a.q_batch_stride = (long)S * qkvw, a.q_row_stride = qkvw;
       a.k0 = s.kcache + l * layer_stride, a.v0 = s.vcache + l * layer_stride;
       a.kv0_batch_stride = (long)P * hd, a.kv0_row_stride = hd, a.kv0_len_dev = s.plen, a.kv0_max = P;

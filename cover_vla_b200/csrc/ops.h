@@ -85,6 +85,9 @@ struct AttnCall {
   long o_batch_stride = 0, o_row_stride = 0;
   int batches = 0, heads = 0, kv_heads = 0, tq = 0, head_dim = 0;
   float scale = 1.f;
+  // optional (cos, sin) table [kv batches][tq][head_dim/2] for positions kv0_len + t: RoPE is applied to q and to
+  // the segment-1 keys while staging (cluster decode kernel only; requires k1)
+  const float2* rope = nullptr;
 };
 int attention(cudaStream_t st, const AttnCall& c);
 

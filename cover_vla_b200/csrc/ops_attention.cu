@@ -15,6 +15,7 @@
 #include "host_common.h"
 #include "ops.h"
 #include "ptx.cuh"
+#include "attn_common.cuh"
 
 namespace cvb {
 
@@ -40,28 +41,6 @@ struct AttnParams {
   float scale;
 };
 
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
-                                        uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-               : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
-                                          uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-               : "r"(addr));
-}
-__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
-                                         uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
-      "{%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
-constexpr int BQ = 64, BKV = 64, ATT_THREADS = 128;
 
 template <int HDP>
 __device__ __forceinline__ void load_kv_tile(const AttnParams& p, bf16* Ks, bf16* Vs, int tile,
@@ -86,30 +65,6 @@ __device__ __forceinline__ void load_kv_tile(const AttnParams& p, bf16* Ks, bf16
     }
     *reinterpret_cast<uint4*>(Ks + r * LDS + c) = kv;
     if (want_v) *reinterpret_cast<uint4*>(Vs + r * LDS + c) = vv;
-  }
-}
-
-// S[16 x 64] (per warp) = Q_warp[16 x HDP] * K_tile[64 x HDP]^T
-template <int HDP>
-__device__ __forceinline__ void qk_tile(const bf16* Qs, const bf16* Ks, int warp, int lane,
-                                        float (&s)[8][4]) {
-  constexpr int LDS = HDP + 8;
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-  const uint32_t q_base = smem_u32(Qs + (warp * 16 + (lane & 15)) * LDS + (lane >> 4) * 8);
-  const int mi = lane >> 3, ri = lane & 7;
-  const uint32_t k_base = smem_u32(Ks + ((mi >> 1) * 8 + ri) * LDS + (mi & 1) * 8);
-#pragma unroll 4
-  for (int ks = 0; ks < HDP / 16; ++ks) {
-    uint32_t a0, a1, a2, a3;
-    ldsm_x4(q_base + ks * 32, a0, a1, a2, a3);
-#pragma unroll
-    for (int np = 0; np < 4; ++np) {
-      uint32_t b0, b1, b2, b3;
-      ldsm_x4(k_base + (np * 16 * LDS) * 2 + ks * 32, b0, b1, b2, b3);
-      mma_bf16(s[2 * np], a0, a1, a2, a3, b0, b1);
-      mma_bf16(s[2 * np + 1], a0, a1, a2, a3, b2, b3);
-    }
   }
 }
 
@@ -257,16 +212,6 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_kernel(const AttnParams p) {
 // masked logits of the whole row are parked in shared memory in each thread's own mma-fragment order, so
 // the exact softmax statistics are known before P is rounded to bf16 and no Q.K^T is recomputed.
 // Used whenever the logits fit (keys <= ~384 at head_dim 256, ~900 at head_dim 64).
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-  const int sz = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
 template <int HDP>
 __device__ __forceinline__ void issue_tile(const AttnParams& p, bf16* dst, int tile, bool is_v, int n0, int nk,
                                            int b, int kvb, int kvh) {
@@ -460,8 +405,14 @@ int launch_attn(cudaStream_t st, const AttnParams& p, dim3 grid) {
 
 }  // namespace
 
+bool attention_decode_eligible(const AttnCall& c);
+int attention_decode(cudaStream_t st, const AttnCall& c, const float2* rope);
+
 int attention(cudaStream_t st, const AttnCall& c) {
   CVB_REQUIRE(c.head_dim % 8 == 0 && c.head_dim <= 256, "head_dim must be a multiple of 8, <= 256");
+  CVB_REQUIRE(c.heads % c.kv_heads == 0, "heads must be a multiple of kv_heads");
+  if (c.k1 != nullptr && attention_decode_eligible(c)) return attention_decode(st, c, c.rope);
+  CVB_REQUIRE(c.rope == nullptr, "fused RoPE needs the cluster decode attention (shape not eligible)");
   CVB_REQUIRE(c.heads % c.kv_heads == 0, "heads must be a multiple of kv_heads");
   CVB_REQUIRE(c.batches > 0 && c.tq > 0, "empty attention");
   AttnParams p;

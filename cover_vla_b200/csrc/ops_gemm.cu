@@ -48,6 +48,16 @@ int get_tmap(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_
   return 0;
 }
 
+}  // namespace
+
+int get_tmap_cached(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, CUtensorMap* out) {
+  return get_tmap(ptr, rows, cols, ld, box_rows, out);
+}
+bool skinny_eligible(const GemmCall& c);
+int gemm_skinny(cudaStream_t st, const GemmCall& c, int force_split);
+
+namespace {
+
 template <int BN, int STAGES, int EPI>
 int launch(cudaStream_t st, const GemmCall& c, int grid) {
   using S = GemmSmem<BN, STAGES>;
@@ -94,6 +104,10 @@ int launch_bn(cudaStream_t st, const GemmCall& c, int bn, int grid) {
 
 int gemm_bf16(cudaStream_t st, const GemmCall& c) {
   CVB_REQUIRE(c.M > 0 && c.N > 0 && c.K > 0, "empty GEMM");
+  // force_bn: 0 = auto, 64/128/256 = general kernel with that tile, -100 = skinny auto, -1..-16 = skinny with that split
+  if (c.force_bn < 0) return gemm_skinny(st, c, c.force_bn == -100 ? 0 : -c.force_bn);
+  if (c.epi == 5) return gemm_skinny(st, c, 0);
+  if (c.force_bn == 0 && skinny_eligible(c)) return gemm_skinny(st, c, 0);
   CVB_REQUIRE(c.K % 8 == 0, "K must be a multiple of 8 (16-byte TMA rows)");
   CVB_REQUIRE(c.N % 8 == 0, "N must be a multiple of 8 (16-byte vector epilogue)");
   CVB_REQUIRE(c.ldc % 8 == 0 || c.epi == EPI_F32, "ldc must be a multiple of 8");

@@ -1,0 +1,117 @@
+// Host dispatch for the skinny (swap-AB, cluster split-K) GEMM: split heuristic, tensor maps, cluster launch.
+#include <mutex>
+#include <unordered_map>
+
+#include "gemm_skinny.cuh"
+#include "host_common.h"
+#include "ops.h"
+
+namespace cvb {
+
+int get_tmap_cached(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, CUtensorMap* out);
+
+unsigned long long* g_skinny_ts = nullptr;  // diagnostics: cvb_debug_set_timestamps
+
+namespace {
+
+constexpr int kSmemBudget = 200 * 1024;  // ring / receive buffer (barriers + alignment slack come on top)
+
+template <int EPI>
+int launch_skinny(cudaStream_t st, const GemmCall& c, const SkinnyArgs& g, int n_tiles) {
+  CUtensorMap tmW, tmA;
+  CVB_TRY(get_tmap_cached(c.W, c.N, c.K, c.ldw, 128, &tmW));
+  CVB_TRY(get_tmap_cached(c.A, c.M, c.K, c.lda, g.Mp, &tmA));
+  const uint32_t stage_bytes = SK_W_BYTES + g.Mp * 128;
+  const uint32_t recv_bytes = (uint32_t)g.S * g.slice * 512u;
+  const uint32_t body = std::max<uint32_t>(g.stages * stage_bytes, recv_bytes);
+  const int smem = 1024 + ((body + 15) & ~15u) + (2 * g.stages + 1) * 8 + 16;
+  auto kern = gemm_skinny_tcgen05<EPI>;
+  static int attr_smem = 0;
+  static bool nonportable = false;
+  if (smem > attr_smem) {
+    CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  if (g.S > 8 && !nonportable) {
+    CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    nonportable = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(n_tiles * g.S, 1, 1);
+  cfg.blockDim = dim3(SK_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = g.S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CVB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmW, tmA, g));
+  CVB_LAUNCHED();
+  return 0;
+}
+
+}  // namespace
+
+// Auto policy (measured, tools/skinny_bench.py): the cluster split-K kernel wins where the general kernel has few
+// tiles AND a long K walk (o_proj / down / fc2: N <= 1152, K >= 2048); elsewhere its DSMEM reduction costs more than it saves.
+bool skinny_eligible(const GemmCall& c) {
+  if (c.M > 256 || c.m_dev != nullptr || c.epi == EPI_GEGLU) return false;
+  const int tiles64 = ((c.M + 127) / 128) * ((c.N + 63) / 64);
+  return tiles64 <= 40 && c.K >= 2048;
+}
+
+int gemm_skinny(cudaStream_t st, const GemmCall& c, int force_split) {
+  CVB_REQUIRE(c.M > 0 && c.M <= 256, "skinny GEMM handles 1..256 activation rows");
+  CVB_REQUIRE(c.K % 8 == 0, "K must be a multiple of 8 (16-byte TMA rows)");
+  CVB_REQUIRE(c.m_dev == nullptr, "skinny GEMM has no device-side row count");
+  if (c.epi == EPI_GEGLU64) CVB_REQUIRE(c.N % 128 == 0, "EPI_GEGLU64 expects 128-row packed [64 gate | 64 up] blocks");
+  SkinnyArgs g;
+  g.C = c.C, g.ldc = c.ldc, g.bias = c.bias, g.bias_is_f32 = c.bias_is_f32;
+  g.resid = c.resid, g.resid_is_f32 = c.resid_is_f32, g.ldr = c.ldr;
+  g.M = c.M, g.Mp = (c.M + 15) / 16 * 16, g.N = c.N, g.K = c.K, g.n_out = c.n_out;
+  const int n_tiles = (c.N + 127) / 128;
+  const int kb_total = (c.K + 63) / 64;
+  int S = force_split;
+  if (S <= 0) {
+    // aim at ~128 co-resident CTAs; clusters of up to 8 are portable
+    S = (128 + n_tiles / 2) / n_tiles;
+    if (S < 1) S = 1;
+    if (S > 8) S = 8;
+  }
+  if (S > 16) S = 16;
+  if (S > kb_total) S = kb_total;
+  g.kbs = (kb_total + S - 1) / S;
+  S = (kb_total + g.kbs - 1) / g.kbs;  // drop splits that would own no k-block
+  g.S = S;
+  g.slice = ((g.Mp + S - 1) / S + 3) / 4 * 4;
+  const int stage_bytes = SK_W_BYTES + g.Mp * 128;
+  int stages = kSmemBudget / stage_bytes;
+  if (stages > g.kbs) stages = g.kbs;
+  if (stages > 8) stages = 8;
+  if (stages < 1) stages = 1;
+  g.stages = stages;
+  CVB_REQUIRE((long)g.S * g.slice * 512 <= kSmemBudget, "split-K receive buffer does not fit shared memory");
+  g.ts = g_skinny_ts;
+  g.tmem_cols = g.Mp <= 32 ? 32 : g.Mp <= 64 ? 64 : g.Mp <= 128 ? 128 : 256;
+  switch (c.epi) {
+    case EPI_STORE:
+      return launch_skinny<EPI_STORE>(st, c, g, n_tiles);
+    case EPI_GELU:
+      return launch_skinny<EPI_GELU>(st, c, g, n_tiles);
+    case EPI_RESID:
+      CVB_REQUIRE(c.resid != nullptr, "EPI_RESID needs a residual pointer");
+      return launch_skinny<EPI_RESID>(st, c, g, n_tiles);
+    case EPI_F32:
+      return launch_skinny<EPI_F32>(st, c, g, n_tiles);
+    case EPI_GEGLU64:
+      return launch_skinny<EPI_GEGLU64>(st, c, g, n_tiles);
+    default:
+      set_last_error("epilogue kind not supported by the skinny GEMM");
+      return -1;
+  }
+}
+
+}  // namespace cvb

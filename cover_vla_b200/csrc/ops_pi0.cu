@@ -150,6 +150,26 @@ int rope_qkv(cudaStream_t st, bf16* qkv, long ld, const float* timescale, int ro
   return 0;
 }
 
+// (cos, sin) of the suffix positions: tab[b][t][i] = sincos((pos_base[b] + t) / timescale[i]) - computed once per sample
+// so the denoise attention applies RoPE while staging Q / K (same sincosf as rope_kernel: bit-identical rotation)
+__global__ void rope_table_kernel(const float* __restrict__ timescale, const int* __restrict__ pos_base_dev,
+                                  int tq, int half, float2* __restrict__ tab) {
+  const int b = blockIdx.x / tq, t = blockIdx.x % tq;
+  const float pos = static_cast<float>(pos_base_dev[b] + t);
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    float sn, cs;
+    sincosf(pos / timescale[i], &sn, &cs);
+    tab[(static_cast<long>(b) * tq + t) * half + i] = make_float2(cs, sn);
+  }
+}
+
+int rope_table(cudaStream_t st, const float* timescale, const int* pos_base_dev, int batches, int tq, int half,
+               float2* tab) {
+  rope_table_kernel<<<batches * tq, 128, 0, st>>>(timescale, pos_base_dev, tq, half, tab);
+  CVB_LAUNCHED();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // v = action_out_proj(float(h_norm[last chunk tokens]));  x_t += dt * v      (modeling_pi0.py:748-752,713)
 __global__ void __launch_bounds__(256) action_out_euler_kernel(const bf16* __restrict__ hn, long ld,

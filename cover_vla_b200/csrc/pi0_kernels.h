@@ -20,6 +20,8 @@ int action_out_euler(cudaStream_t st, const bf16* hn, long ld, const float* w, c
                      int suffix_len, float dt);
 int fill_state_rows(cudaStream_t st, const float* state_emb, float* suffix, int n_cand, int width,
                     int suffix_len);
+int rope_table(cudaStream_t st, const float* timescale, const int* pos_base_dev, int batches, int tq, int half,
+               float2* tab);
 int prefix_lengths(cudaStream_t st, const int* lang_len, int* plen, int R, int n_img);
 int bf16_to_f32(cudaStream_t st, const bf16* src, float* dst, long n);
 

@@ -7,7 +7,8 @@ import torch
 
 from . import _lib
 
-EPI_STORE, EPI_GELU, EPI_RESID, EPI_GEGLU, EPI_F32 = range(5)
+EPI_STORE, EPI_GELU, EPI_RESID, EPI_GEGLU, EPI_F32, EPI_GEGLU64 = range(6)
+SKINNY_AUTO = -100  # force_bn value: skinny (swap-AB, cluster split-K) GEMM with the split heuristic; -S forces S splits
 
 
 def _i64(v):
@@ -22,7 +23,7 @@ def gemm_bf16(a, w, *, epilogue=EPI_STORE, bias=None, resid=None, out=None, n_ou
     assert a.stride(-1) == 1 and w.stride(-1) == 1
     M, K = a.shape
     N = w.shape[0]
-    cols = n_out if epilogue == EPI_GEGLU else N
+    cols = n_out if epilogue in (EPI_GEGLU, EPI_GEGLU64) else N
     if out is None:
         out = torch.empty(M, cols, device=a.device,
                           dtype=torch.float32 if epilogue == EPI_F32 else torch.bfloat16)
@@ -38,7 +39,7 @@ def gemm_bf16(a, w, *, epilogue=EPI_STORE, bias=None, resid=None, out=None, n_ou
 
 
 def attention(q, k0, v0, *, heads, kv_heads, head_dim, kv0_len=None, kv0_len_dev=None, q_per_kv_batch=1,
-              k1=None, v1=None, suffix_mask=False, scale=None, force_two_pass=False):
+              k1=None, v1=None, suffix_mask=False, scale=None, force_two_pass=False, rope=None):
     """q [B, Tq, heads*hd]; k0/v0 [Bkv, T0, kv_heads*hd]; optional k1/v1 [B, T1, kv_heads*hd] (bf16, CUDA)."""
     lib = _lib.load()
     B, Tq, _ = q.shape
@@ -48,12 +49,12 @@ def attention(q, k0, v0, *, heads, kv_heads, head_dim, kv0_len=None, kv0_len_dev
     lib.cvb_op_attention.argtypes = ([C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                       C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64] + [C.c_int] * 5 +
-                                     [C.c_float, C.c_int, C.c_void_p])
+                                     [C.c_float, C.c_int, C.c_void_p, C.c_void_p])
     rc = lib.cvb_op_attention(
         _lib.ptr(q), q.stride(0), q.stride(1), _lib.ptr(k0), _lib.ptr(v0), k0.stride(0), k0.stride(1),
         _lib.ptr(kv0_len_dev), int(kv0_len if kv0_len is not None else T0), T0, q_per_kv_batch,
         _lib.ptr(k1), _lib.ptr(v1), k1.stride(0) if k1 is not None else 0, k1.stride(1) if k1 is not None else 0,
         k1.shape[1] if k1 is not None else 0, int(suffix_mask), _lib.ptr(out), out.stride(0), out.stride(1),
-        B, heads, kv_heads, Tq, head_dim, scale, int(force_two_pass), _lib.stream_ptr())
+        B, heads, kv_heads, Tq, head_dim, scale, int(force_two_pass), _lib.ptr(rope), _lib.stream_ptr())
     _lib.check(rc)
     return out

@@ -49,13 +49,14 @@ CVB_API int cvb_op_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
 /* Exact-softmax attention with the reference's rounding ledger (eager_attention_forward,
  * paligemma_with_expert.py:376-434): q [batches, tq, heads*head_dim] (strides q_bs / q_rs in elements), keys in two
  * segments - segment 0 shared per kv batch (kv batch = batch / q_per_kv_batch; length from kv0_len_dev[kv batch] or
- * kv0_len), segment 1 per batch (e.g. the suffix tokens' own keys) with the pi0 suffix mask when suffix_mask = 1. */
+ * kv0_len), segment 1 per batch (e.g. the suffix tokens' own keys) with the pi0 suffix mask when suffix_mask = 1.
+ * rope_cos_sin (optional, f32 [kv batches, tq, head_dim/2, 2]): RoPE applied to q and the segment-1 keys while staging. */
 CVB_API int cvb_op_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k0, const void* v0, int64_t kv0_bs,
                              int64_t kv0_rs, const int32_t* kv0_len_dev, int kv0_len, int kv0_max,
                              int q_per_kv_batch, const void* k1, const void* v1, int64_t kv1_bs, int64_t kv1_rs,
                              int kv1_len, int suffix_mask, void* out, int64_t o_bs, int64_t o_rs, int batches,
                              int heads, int kv_heads, int tq, int head_dim, float scale, int force_two_pass,
-                             void* stream);
+                             const float* rope_cos_sin, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Engine level.  One handle per (device, stream); a handle is not thread-safe, the library is
@@ -154,6 +155,9 @@ CVB_API int cvb_select(const float* scores, int R, int K, float* group_mean, int
  * "time_emb", ...) to dst (device).  Returns the number of bytes copied or a negative error. */
 CVB_API int64_t cvb_debug_copy(cvb_handle* h, const char* name, void* dst, int64_t max_bytes,
                                void* stream);
+
+/* Diagnostics: when non-NULL, every CTA of the skinny GEMM writes 8 globaltimer phase stamps to dev_u64[cta * 8 + i]. */
+CVB_API void cvb_debug_set_timestamps(void* dev_u64);
 
 /* Host-only helpers (no CUDA calls): the constants of the denoise loop, for tests and hosts. */
 CVB_API int cvb_denoise_times_host(int num_steps, float* times_out, int max_out, float* dt_out);

@@ -61,3 +61,52 @@ def test_denoise_attention_two_segments(two_pass):
         ref = _ref(q[n:n + 1], kk, vv, heads, 1, hd, mask)
         err = (out[n:n + 1].float() - ref).abs().max().item()
         assert err < 2e-2, (n, err)
+
+
+def _rope(x, pos, hd):
+    """apply_rope (paligemma_with_expert.py:34-57) on [..., T, H, hd] bf16 with positions [..., T]."""
+    half = hd // 2
+    ts = 10000.0 ** ((2.0 / hd) * torch.arange(half, dtype=torch.float32, device=x.device))
+    rad = pos[..., None].float() / ts
+    sin, cos = torch.sin(rad)[..., None, :], torch.cos(rad)[..., None, :]
+    xf = x.float()
+    x1, x2 = xf[..., :half], xf[..., half:]
+    return torch.cat([x1 * cos - x2 * sin, x2 * cos + x1 * sin], dim=-1).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("R,K,S,P,heads,hd,lens", [(3, 4, 5, 328, 8, 256, [270, 328, 300]), (2, 3, 5, 32, 2, 64, [20, 32]),
+                                                    (2, 2, 8, 500, 8, 128, [130, 499]), (1, 5, 5, 328, 8, 256, [61])])
+def test_cluster_decode_attention_with_fused_rope(R, K, S, P, heads, hd, lens):
+    """Cluster split-KV kernel: RoPE on q / suffix keys fused into staging, exact softmax over DSMEM statistics."""
+    from cover_vla_b200 import ops
+    torch.manual_seed(11)
+    N = R * K
+    q = torch.randn(N, S, heads * hd, device="cuda").to(torch.bfloat16)
+    k0 = torch.randn(R, P, hd, device="cuda").to(torch.bfloat16)
+    v0 = torch.randn(R, P, hd, device="cuda").to(torch.bfloat16)
+    k1 = torch.randn(N, S, hd, device="cuda").to(torch.bfloat16)
+    v1 = torch.randn(N, S, hd, device="cuda").to(torch.bfloat16)
+    lens_t = torch.tensor(lens, device="cuda", dtype=torch.int32)
+    pos = lens_t[:, None] + torch.arange(S, device="cuda")[None, :]           # [R, S]
+    half = hd // 2
+    ts = 10000.0 ** ((2.0 / hd) * torch.arange(half, dtype=torch.float32, device="cuda"))
+    rad = pos[..., None].float() / ts
+    tab = torch.stack([torch.cos(rad), torch.sin(rad)], dim=-1).contiguous()   # [R, S, half, 2]
+    out = ops.attention(q, k0, v0, heads=heads, kv_heads=1, head_dim=hd, kv0_len_dev=lens_t, q_per_kv_batch=K,
+                        k1=k1, v1=v1, suffix_mask=True, rope=tab)
+    out2 = ops.attention(q, k0, v0, heads=heads, kv_heads=1, head_dim=hd, kv0_len_dev=lens_t, q_per_kv_batch=K,
+                         k1=k1, v1=v1, suffix_mask=True, rope=tab)
+    assert torch.equal(out, out2)  # rank-ordered DSMEM reduction: deterministic
+    posn = pos.repeat_interleave(K, dim=0)                                     # [N, S]
+    qr = _rope(q.view(N, S, heads, hd), posn, hd).view(N, S, heads * hd)
+    k1r = _rope(k1.view(N, S, 1, hd), posn, hd).view(N, S, hd)
+    for n in range(N):
+        r = n // K
+        L = int(lens[r])
+        kk = torch.cat([k0[r, :L], k1r[n]])[None]
+        vv = torch.cat([v0[r, :L], v1[n]])[None]
+        mask = torch.ones(1, S, L + S, dtype=torch.bool, device="cuda")
+        mask[0, 0, L + 1:] = False
+        ref = _ref(qr[n:n + 1], kk, vv, heads, 1, hd, mask)
+        err = (out[n:n + 1].float() - ref).abs().max().item()
+        assert err < 2e-2, (n, err)

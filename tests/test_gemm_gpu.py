@@ -97,3 +97,85 @@ def test_gemm_device_side_rows():
     ref = _ref(a, w)
     assert _rel_err(out[:300], ref[:300]) < 4e-3
     assert out[300:].abs().max().item() == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# skinny (swap-AB, cluster split-K through distributed shared memory) GEMM: M <= 256
+# ---------------------------------------------------------------------------------------------------------------
+SKINNY_SHAPES = [
+    (200, 2560, 1024), (200, 1024, 2048), (200, 1024, 4096), (256, 3456, 1152), (256, 1152, 4304),
+    (256, 4304, 1152), (64, 1024, 1024), (64, 3072, 1024), (5, 64, 64), (130, 72, 200), (16, 128, 64), (1, 256, 128),
+    (255, 136, 72),
+]
+
+
+@pytest.mark.parametrize("M,N,K", SKINNY_SHAPES)
+@pytest.mark.parametrize("split", [-100, -1, -2, -3, -8])
+def test_skinny_gemm_store(M, N, K, split):
+    from cover_vla_b200 import ops
+    torch.manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", dtype=torch.bfloat16)
+    y = ops.gemm_bf16(a, w, bias=bias, force_bn=split)
+    torch.cuda.synchronize()
+    ref = _ref(a, w, bias)
+    assert _rel_err(y, ref) < 4e-3, (M, N, K, split, _rel_err(y, ref))
+    assert (y.float() - ref).abs().max().item() < 0.06
+    # deterministic: the cluster reduction sums partials in rank order
+    y2 = ops.gemm_bf16(a, w, bias=bias, force_bn=split)
+    assert torch.equal(y, y2)
+
+
+def test_skinny_matches_general_kernel_bitwise_when_unsplit():
+    """S = 1: one fp32 accumulator over the whole K, same rounding points -> same bf16 bits as the general kernel."""
+    from cover_vla_b200 import ops
+    torch.manual_seed(3)
+    M, N, K = 200, 1024, 1024
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    y0 = ops.gemm_bf16(a, w, force_bn=64)
+    y1 = ops.gemm_bf16(a, w, force_bn=-1)
+    assert (y0.float() - y1.float()).abs().max().item() <= 2 ** -6  # accumulation order inside the tensor core may differ
+    assert (y0 != y1).float().mean().item() < 0.02
+
+
+def test_skinny_epilogues():
+    from cover_vla_b200 import ops
+    torch.manual_seed(0)
+    M, N, K = 200, 512, 1024
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", dtype=torch.float32)
+    ref = _ref(a, w, bias)
+    y = ops.gemm_bf16(a, w, bias=bias, epilogue=ops.EPI_F32, force_bn=ops.SKINNY_AUTO)
+    assert _rel_err(y, ref) < 1e-5
+    bias16 = bias.to(torch.bfloat16)
+    ref16 = _ref(a, w, bias16).to(torch.bfloat16)
+    y = ops.gemm_bf16(a, w, bias=bias16, epilogue=ops.EPI_GELU, force_bn=ops.SKINNY_AUTO)
+    assert _rel_err(y, torch.nn.functional.gelu(ref16, approximate="tanh")) < 4e-3
+    r = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+    y = ops.gemm_bf16(a, w, bias=bias16, epilogue=ops.EPI_RESID, resid=r, force_bn=ops.SKINNY_AUTO)
+    assert _rel_err(y, (ref16.float() + r.float()).to(torch.bfloat16)) < 4e-3
+    r32 = torch.randn(M, N, device="cuda", dtype=torch.float32)
+    y = ops.gemm_bf16(a, w, bias=bias16, epilogue=ops.EPI_RESID, resid=r32, force_bn=ops.SKINNY_AUTO)
+    assert _rel_err(y, (ref16.float() + r32).to(torch.bfloat16)) < 4e-3
+    r2 = r.clone()
+    ops.gemm_bf16(a, w, bias=bias16, epilogue=ops.EPI_RESID, resid=r2, out=r2, force_bn=ops.SKINNY_AUTO)
+    assert _rel_err(r2, (ref16.float() + r.float()).to(torch.bfloat16)) < 4e-3
+
+
+@pytest.mark.parametrize("M,I,K", [(200, 4096, 1024), (37, 320, 256), (256, 1024, 2048)])
+def test_skinny_geglu64(M, I, K):
+    from cover_vla_b200 import ops
+    torch.manual_seed(1)
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    wg = (torch.randn(I, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    wu = (torch.randn(I, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    packed = torch.stack([wg.view(I // 64, 64, K), wu.view(I // 64, 64, K)], dim=1).reshape(2 * I, K).contiguous()
+    y = ops.gemm_bf16(a, packed, epilogue=ops.EPI_GEGLU64, n_out=I)
+    g = (a.float() @ wg.float().t()).to(torch.bfloat16)
+    u = (a.float() @ wu.float().t()).to(torch.bfloat16)
+    ref = torch.nn.functional.gelu(g, approximate="tanh") * u
+    assert y.shape == (M, I)
+    assert _rel_err(y, ref) < 6e-3

@@ -423,6 +423,7 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
         CVB_TRY(rope_qkv(st, s.qkv_e, qkvw, s.rope_timescale, M, c.heads, hd, S, s.plen, K, nullptr, nullptr, 0, 0));
       AttnCall a;
       a.rope = fused_rope ? s.rope_tab : nullptr;
+      a.kv0_static = 1;
       a.q = s.qkv_e, a.q_batch_stride = (long)S * qkvw, a.q_row_stride = qkvw;
       a.k0 = s.kcache + l * layer_stride, a.v0 = s.vcache + l * layer_stride;
       a.kv0_batch_stride = (long)P * hd, a.kv0_row_stride = hd, a.kv0_len_dev = s.plen, a.kv0_max = P;

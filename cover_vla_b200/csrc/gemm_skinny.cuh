@@ -153,12 +153,28 @@ gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   SK_TS(1);
 
+  pdl_launch();
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      // weight tiles first (independent of the preceding kernel), activations after the dependency resolves
+      const int pre = min(nkb, g.stages);
+      for (int i = 0; i < pre; ++i) {
+        mbar_arrive_expect_tx(&full_bar[i], stage_bytes);
+        tma_load_2d_hint(smem + i * stage_bytes, &tmW, &full_bar[i], (kb0 + i) * 64, tile * 128, kEvictFirst);
+      }
+      pdl_wait();
       for (int i = 0; i < nkb; ++i) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sw = smem + stage * stage_bytes;
+        if (i < pre) {
+          tma_load_2d_hint(sw + SK_W_BYTES, &tmA, &full_bar[stage], (kb0 + i) * 64, 0, kEvictLast);
+          if (++stage == static_cast<uint32_t>(g.stages)) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
+        }
+        mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
         tma_load_2d_hint(sw, &tmW, &full_bar[stage], (kb0 + i) * 64, tile * 128, kEvictFirst);
         tma_load_2d_hint(sw + SK_W_BYTES, &tmA, &full_bar[stage], (kb0 + i) * 64, 0, kEvictLast);
@@ -191,6 +207,7 @@ gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     }
     __syncwarp();
   } else {
+    pdl_wait();  // residual reads / C writes must not overtake the preceding kernel
     if (nkb > 0) {
       mbar_wait(tfull_bar, 0);
       tc_fence_after();

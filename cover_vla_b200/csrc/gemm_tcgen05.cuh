@@ -84,7 +84,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int lane = threadIdx.x & 31;
 
   int M = g.M;
-  if (g.m_dev != nullptr) M = min(M, *g.m_dev);
+  if (g.m_dev != nullptr) {
+    pdl_wait();  // the device-side row count may come from the preceding kernel
+    M = min(M, *g.m_dev);
+  }
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
   const int n_tiles = (g.N + BN - 1) / BN;
   const int k_blocks = (g.K + GEMM_BK - 1) / GEMM_BK;
@@ -115,17 +118,38 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch();  // the next kernel may start its prologue (and its own weight prefetch) now
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      // Weights (operand B) never depend on the preceding kernel: put the first ring-full of weight tiles in flight
+      // BEFORE waiting for it (programmatic dependent launch), then add the activation tiles.
+      int pre = 0;
+      if (static_cast<int>(blockIdx.x) < num_tiles) {
+        const int nt0 = blockIdx.x / m_tiles;
+        pre = min(STAGES, k_blocks);
+        for (int kb = 0; kb < pre; ++kb) {
+          mbar_arrive_expect_tx(&full_bar[kb], S::STAGE_BYTES);
+          tma_load_2d(smem + kb * S::STAGE_BYTES + S::A_BYTES, &tmB, &full_bar[kb], kb * GEMM_BK, nt0 * BN);
+        }
+      }
+      pdl_wait();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile % m_tiles, nt = tile / m_tiles;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
           uint8_t* sb = sa + S::A_BYTES;
+          if (tile == static_cast<int>(blockIdx.x) && kb < pre) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, mt * GEMM_BM);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, mt * GEMM_BM);
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, nt * BN);
@@ -168,6 +192,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ------------------------------------------------------------ epilogue (4 warps, 128 rows)
+    pdl_wait();  // residual reads / C writes must not overtake the preceding kernel
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row_in_tile = q * 32 + lane;
     uint32_t acc = 0, acc_phase = 0;

@@ -1,6 +1,7 @@
 #include "host_common.h"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 namespace cvb {
@@ -54,6 +55,15 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols
 static std::atomic<long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CVB_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 int device_sm_count() {
   static int sms = 0;

@@ -10,6 +10,7 @@
 #include <map>
 #include <string>
 #include <tuple>
+#include <utility>
 
 namespace cvb {
 
@@ -50,6 +51,36 @@ int device_sm_count();
 // number of kernel launches enqueued by this library (bench.py reports it as gpu_launches)
 void count_launch();
 long launch_count();
+
+// Launch with programmatic stream serialization (PDL) and an optional cluster dimension.  CVB_PDL=0 in the
+// environment disables the attribute (kernels then serialise fully; their griddepcontrol instructions are no-ops).
+bool pdl_enabled();
+template <typename... P, typename... A>
+int launch_pdl(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  CVB_CUDA(cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...));
+  return 0;
+}
 
 #define CVB_LAUNCHED()                \
   do {                                \

@@ -88,6 +88,9 @@ struct AttnCall {
   // optional (cos, sin) table [kv batches][tq][head_dim/2] for positions kv0_len + t: RoPE is applied to q and to
   // the segment-1 keys while staging (cluster decode kernel only; requires k1)
   const float2* rope = nullptr;
+  // segment 0 (and kv0_len_dev) is NOT written by the kernel launched just before this one: its tiles may be
+  // prefetched before the programmatic-dependency wait (the prefix KV cache during the denoise loop)
+  int kv0_static = 0;
 };
 int attention(cudaStream_t st, const AttnCall& c);
 

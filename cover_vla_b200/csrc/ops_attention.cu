@@ -70,6 +70,8 @@ __device__ __forceinline__ void load_kv_tile(const AttnParams& p, bf16* Ks, bf16
 
 template <int HDP>
 __global__ void __launch_bounds__(ATT_THREADS) attn_kernel(const AttnParams p) {
+  pdl_wait();
+  pdl_launch();
   constexpr int LDS = HDP + 8;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
@@ -234,6 +236,8 @@ __device__ __forceinline__ void issue_tile(const AttnParams& p, bf16* dst, int t
 
 template <int HDP>
 __global__ void __launch_bounds__(ATT_THREADS) attn_smem_kernel(const AttnParams p) {
+  pdl_wait();
+  pdl_launch();
   constexpr int LDS = HDP + 8;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
@@ -384,7 +388,7 @@ int launch_attn_smem(cudaStream_t st, const AttnParams& p, dim3 grid, int max_ti
     CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
-  kern<<<grid, ATT_THREADS, smem, st>>>(p);
+  CVB_TRY(launch_pdl(kern, dim3(grid), dim3(ATT_THREADS), smem, st, 1, p));
   CVB_LAUNCHED();
   return 0;
 }
@@ -398,7 +402,7 @@ int launch_attn(cudaStream_t st, const AttnParams& p, dim3 grid) {
     CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
-  kern<<<grid, ATT_THREADS, SMEM, st>>>(p);
+  CVB_TRY(launch_pdl(kern, dim3(grid), dim3(ATT_THREADS), SMEM, st, 1, p));
   CVB_LAUNCHED();
   return 0;
 }

@@ -19,6 +19,8 @@
 
 namespace cvb {
 
+extern unsigned long long* g_skinny_ts;
+
 namespace {
 
 struct DecodeParams {
@@ -39,10 +41,18 @@ struct DecodeParams {
   long o_bs, o_rs;
   int heads, kv_heads, tq, head_dim;
   float scale;
+  int kv0_static;      // segment 0 and its length are not produced by the preceding kernel (PDL prefetch allowed)
   const float2* rope;  // [kv batches][tq][head_dim/2] (cos, sin) of position kv0_len + t, or nullptr (no RoPE)
   int C;               // cluster size = key tiles
   int rows_per;        // query rows finalised per CTA
+  unsigned long long* ts;  // diagnostics (cvb_debug_set_timestamps) or nullptr
 };
+
+#define AD_TS(i)                                                                                   \
+  do {                                                                                             \
+    if (p.ts != nullptr && threadIdx.x == 0)                                                       \
+      p.ts[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (i)] = gtimer(); \
+  } while (0)
 
 __device__ __forceinline__ void st_cluster_v2f(uint32_t addr, float a, float b) {
   asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
@@ -86,12 +96,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const DecodePa
   const int rows_total = G * p.tq;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kvb = b / p.q_per_kv_batch;
-  const int n0 = p.kv0_len_dev != nullptr ? p.kv0_len_dev[kvb] : p.kv0_len;
-  const int nk = n0 + p.kv1_len;
   const int tile = rank;
   const float2* rope = p.rope != nullptr ? p.rope + static_cast<long>(kvb) * p.tq * HALF : nullptr;
+  AD_TS(0);
 
-  // ---- stage K (prefix rows by cp.async, own suffix rows through registers with RoPE), then V, then Q
+  // ---- stage K / V prefix rows by cp.async.  With kv0_static the prefix cache (and its length) does not depend on the
+  // preceding kernel, so these loads are put in flight BEFORE the programmatic-dependency wait.
+  pdl_launch();
+  if (!p.kv0_static) pdl_wait();
+  const int n0 = p.kv0_len_dev != nullptr ? p.kv0_len_dev[kvb] : p.kv0_len;
+  const int nk = n0 + p.kv1_len;
   {
     constexpr int CH = HD / 8;
     for (int idx = threadIdx.x; idx < BKV * CH; idx += ATT_THREADS) {
@@ -105,13 +119,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const DecodePa
     for (int idx = threadIdx.x; idx < BKV * CH; idx += ATT_THREADS) {
       const int r = idx / CH, c = (idx % CH) * 8;
       const int j = tile * BKV + r;
-      const bool valid = j < nk;
-      const bf16* src = p.q;
-      if (valid) src = j < n0 ? p.v0 + kvb * p.kv0_bs + j * p.kv0_rs + kvh * HD + c
-                              : p.v1 + b * p.kv1_bs + (j - n0) * p.kv1_rs + kvh * HD + c;
-      cp_async16(smem_u32(Vs + r * LDS + c), src, valid);
+      const bool pre = j < n0;
+      const bf16* src = pre ? p.v0 + kvb * p.kv0_bs + j * p.kv0_rs + kvh * HD + c : p.q;
+      cp_async16(smem_u32(Vs + r * LDS + c), src, pre);
     }
     cp_async_commit();
+    if (p.kv0_static) pdl_wait();
     // Q rows (+ RoPE): work item = (row, 8-wide chunk of the first half)
     constexpr int CH2 = HALF / 8;
     for (int idx = threadIdx.x; idx < BQ * CH2; idx += ATT_THREADS) {
@@ -142,9 +155,17 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const DecodePa
       *reinterpret_cast<uint4*>(Ks + r * LDS + c) = v1;
       *reinterpret_cast<uint4*>(Ks + r * LDS + HALF + c) = v2;
     }
+    cp_async_wait<0>();  // V zero-fill of the suffix rows has landed before they are overwritten
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < max(0, j_hi - j_lo) * (HD / 8); idx += ATT_THREADS) {
+      const int j = j_lo + idx / (HD / 8), c = (idx % (HD / 8)) * 8;
+      const bf16* vp = p.v1 + b * p.kv1_bs + (j - n0) * p.kv1_rs + kvh * HD + c;
+      *reinterpret_cast<uint4*>(Vs + (j - tile * BKV) * LDS + c) = *reinterpret_cast<const uint4*>(vp);
+    }
     __syncthreads();
   }
 
+  AD_TS(1);
   const int r_lo = warp * 16 + (lane >> 2);
   const int r_hi = r_lo + 8;
   const int t_lo = r_lo % p.tq, t_hi = r_hi % p.tq;
@@ -195,9 +216,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const DecodePa
       st_cluster_v2f(dst + r_hi * 8, m_hi, l_hi);
     }
   }
+  AD_TS(2);
   cluster_sync_all();  // statistics visible everywhere; every CTA is past Q.K^T, so Q / K may be overwritten (orecv)
 
   // ---- exact softmax with the global statistics, P -> bf16, O_partial = P V
+  AD_TS(3);
   float o[HD / 8][4];
   cp_async_wait<0>();
   __syncthreads();  // every thread's V chunks are in shared memory
@@ -266,7 +289,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const DecodePa
       }
     }
   }
+  AD_TS(4);
   cluster_sync_all();
+  AD_TS(5);
 
   // ---- final: sum the C partial rows I own, round to bf16, store
   {
@@ -285,6 +310,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const DecodePa
       *reinterpret_cast<uint2*>(op) = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
     }
   }
+  AD_TS(6);
 }
 
 template <int HD>
@@ -296,19 +322,7 @@ int launch_decode(cudaStream_t st, const DecodeParams& p, dim3 grid) {
     CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(ATT_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = p.C;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  CVB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  CVB_TRY(launch_pdl(kern, grid, dim3(ATT_THREADS), smem, st, p.C, p));
   CVB_LAUNCHED();
   return 0;
 }
@@ -336,6 +350,8 @@ int attention_decode(cudaStream_t st, const AttnCall& c, const float2* rope) {
   p.out = c.out, p.o_bs = c.o_batch_stride, p.o_rs = c.o_row_stride;
   p.heads = c.heads, p.kv_heads = c.kv_heads, p.tq = c.tq, p.head_dim = c.head_dim, p.scale = c.scale;
   p.rope = rope;
+  p.kv0_static = c.kv0_static;
+  p.ts = g_skinny_ts;
   const int G = c.heads / c.kv_heads;
   const int max_keys = (c.kv0_len_dev != nullptr ? c.kv0_max : c.kv0_len) + p.kv1_len;
   p.C = (max_keys + BKV - 1) / BKV;

@@ -83,7 +83,7 @@ int launch(cudaStream_t st, const GemmCall& c, int grid) {
     CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
-  kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(tmA, tmB, g);
+  CVB_TRY(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), S::TOTAL, st, 1, tmA, tmB, g));
   CVB_LAUNCHED();
   return 0;
 }

@@ -36,19 +36,7 @@ int launch_skinny(cudaStream_t st, const GemmCall& c, const SkinnyArgs& g, int n
     CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     nonportable = true;
   }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(n_tiles * g.S, 1, 1);
-  cfg.blockDim = dim3(SK_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = g.S;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  CVB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmW, tmA, g));
+  CVB_TRY(launch_pdl(kern, dim3(n_tiles * g.S), dim3(SK_THREADS), smem, st, g.S, tmW, tmA, g));
   CVB_LAUNCHED();
   return 0;
 }

@@ -33,6 +33,8 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const void* __restrict__ x
                                                       bf16* __restrict__ y, long ldy, int rows,
                                                       int width, float eps,
                                                       const int* __restrict__ rows_dev) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float red[32];
   const int row = blockIdx.x;
   if (rows_dev != nullptr && row >= *rows_dev) return;
@@ -101,13 +103,13 @@ int rmsnorm(cudaStream_t st, const void* x, int x_is_f32, long ldx, const void* 
   CVB_REQUIRE(width % 8 == 0, "rmsnorm width must be a multiple of 8");
   const int threads = width >= 2048 ? 256 : (width >= 512 ? 128 : 64);
   if (x_is_f32 && w_is_f32)
-    rmsnorm_kernel<true, true><<<rows, threads, 0, st>>>(x, ldx, w, y, ldy, rows, width, eps, rows_dev);
+    CVB_TRY(launch_pdl(rmsnorm_kernel<true, true>, dim3(rows), dim3(threads), 0, st, 1, x, ldx, w, y, ldy, rows, width, eps, rows_dev));
   else if (x_is_f32)
-    rmsnorm_kernel<true, false><<<rows, threads, 0, st>>>(x, ldx, w, y, ldy, rows, width, eps, rows_dev);
+    CVB_TRY(launch_pdl(rmsnorm_kernel<true, false>, dim3(rows), dim3(threads), 0, st, 1, x, ldx, w, y, ldy, rows, width, eps, rows_dev));
   else if (w_is_f32)
-    rmsnorm_kernel<false, true><<<rows, threads, 0, st>>>(x, ldx, w, y, ldy, rows, width, eps, rows_dev);
+    CVB_TRY(launch_pdl(rmsnorm_kernel<false, true>, dim3(rows), dim3(threads), 0, st, 1, x, ldx, w, y, ldy, rows, width, eps, rows_dev));
   else
-    rmsnorm_kernel<false, false><<<rows, threads, 0, st>>>(x, ldx, w, y, ldy, rows, width, eps, rows_dev);
+    CVB_TRY(launch_pdl(rmsnorm_kernel<false, false>, dim3(rows), dim3(threads), 0, st, 1, x, ldx, w, y, ldy, rows, width, eps, rows_dev));
   CVB_LAUNCHED();
   return 0;
 }
@@ -119,6 +121,8 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const bf16* __restr
                                                              const bf16* __restrict__ b,
                                                              bf16* __restrict__ y, long ldy,
                                                              int width, float eps) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float red[32];
   const bf16* xr = x + blockIdx.x * ldx;
   float s = 0.f;
@@ -165,7 +169,7 @@ int layernorm_bf16(cudaStream_t st, const bf16* x, long ldx, const bf16* w, cons
                    long ldy, int rows, int width, float eps) {
   CVB_REQUIRE(width % 8 == 0, "layernorm width must be a multiple of 8");
   const int threads = width >= 1024 ? 128 : 64;
-  layernorm_bf16_kernel<<<rows, threads, 0, st>>>(x, ldx, w, b, y, ldy, width, eps);
+  CVB_TRY(launch_pdl(layernorm_bf16_kernel, dim3(rows), dim3(threads), 0, st, 1, x, ldx, w, b, y, ldy, width, eps));
   CVB_LAUNCHED();
   return 0;
 }
@@ -177,6 +181,8 @@ __global__ void __launch_bounds__(128) layernorm_f32_kernel(const float* __restr
                                                             const float* __restrict__ b,
                                                             float* __restrict__ y, int width,
                                                             float eps) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float red[32];
   extern __shared__ float rowbuf[];
   const long off = static_cast<long>(blockIdx.x) * width;
@@ -201,7 +207,7 @@ __global__ void __launch_bounds__(128) layernorm_f32_kernel(const float* __restr
 
 int layernorm_f32(cudaStream_t st, const float* x, const float* resid, const float* w,
                   const float* b, float* y, int rows, int width, float eps) {
-  layernorm_f32_kernel<<<rows, 128, width * sizeof(float), st>>>(x, resid, w, b, y, width, eps);
+  CVB_TRY(launch_pdl(layernorm_f32_kernel, dim3(rows), dim3(128), width * sizeof(float), st, 1, x, resid, w, b, y, width, eps));
   CVB_LAUNCHED();
   return 0;
 }

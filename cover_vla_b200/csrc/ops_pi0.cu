@@ -10,6 +10,8 @@ namespace cvb {
 // conv(patch, stride patch) as GEMM: patches[t, c*P*P + ky*P + kx] = bf16(img[c, py*P+ky, px*P+kx])
 __global__ void im2col_kernel(const float* __restrict__ img, bf16* __restrict__ out, int C, int H,
                               int W, int P, int kpad) {
+  pdl_wait();
+  pdl_launch();
   const int t = blockIdx.x;
   const int gw = W / P;
   const int py = t / gw, px = t % gw;
@@ -28,7 +30,7 @@ __global__ void im2col_kernel(const float* __restrict__ img, bf16* __restrict__ 
 int im2col_patches(cudaStream_t st, const float* img, bf16* out, int C, int H, int W, int P,
                    int kpad) {
   const int tokens = (H / P) * (W / P);
-  im2col_kernel<<<tokens, 128, 0, st>>>(img, out, C, H, W, P, kpad);
+  CVB_TRY(launch_pdl(im2col_kernel, dim3(tokens), dim3(128), 0, st, 1, img, out, C, H, W, P, kpad));
   CVB_LAUNCHED();
   return 0;
 }
@@ -39,6 +41,8 @@ int im2col_patches(cudaStream_t st, const float* img, bf16* out, int C, int H, i
 __global__ void build_prefix_kernel(const bf16* __restrict__ proj, const bf16* __restrict__ embed,
                                     const int64_t* __restrict__ tok, bf16* __restrict__ prefix,
                                     int n_img, int n_lang, int D, float sqrt_d, float sqrt_d_bf16) {
+  pdl_wait();
+  pdl_launch();
   const int t = blockIdx.x, r = blockIdx.y;
   const int P = n_img + n_lang;
   bf16* dst = prefix + (static_cast<long>(r) * P + t) * D;
@@ -78,7 +82,7 @@ int build_prefix(cudaStream_t st, const bf16* proj, const bf16* embed, const int
   const float s = static_cast<float>(sqrt(static_cast<double>(D)));  // (float)(D ** 0.5)
   const float sb = __bfloat162float(__float2bfloat16_rn(s));
   dim3 grid(n_img + n_lang, R);
-  build_prefix_kernel<<<grid, 128, 0, st>>>(proj, embed, tok, prefix, n_img, n_lang, D, s, sb);
+  CVB_TRY(launch_pdl(build_prefix_kernel, dim3(grid), dim3(128), 0, st, 1, proj, embed, tok, prefix, n_img, n_lang, D, s, sb));
   CVB_LAUNCHED();
   return 0;
 }
@@ -91,6 +95,8 @@ __global__ void rope_kernel(bf16* __restrict__ qkv, long ld, const float* __rest
                             int heads, int hd, int rows_per_batch, const int* __restrict__ pos_base_dev,
                             int q_per_kv_batch, bf16* __restrict__ kcache, bf16* __restrict__ vcache,
                             long cache_bs, long cache_rs) {
+  pdl_wait();
+  pdl_launch();
   const int row = blockIdx.x;
   const int b = row / rows_per_batch, t = row % rows_per_batch;
   const int base = pos_base_dev != nullptr ? pos_base_dev[b / q_per_kv_batch] : 0;
@@ -144,8 +150,8 @@ int rope_qkv(cudaStream_t st, bf16* qkv, long ld, const float* timescale, int ro
   int threads = ((work + 31) / 32) * 32;
   if (threads > 256) threads = 256;
   if (threads < 32) threads = 32;
-  rope_kernel<<<rows, threads, 0, st>>>(qkv, ld, timescale, heads, hd, rows_per_batch, pos_base_dev,
-                                        q_per_kv_batch, kcache, vcache, cache_bs, cache_rs);
+  CVB_TRY(launch_pdl(rope_kernel, dim3(rows), dim3(threads), 0, st, 1, qkv, ld, timescale, heads, hd, rows_per_batch, pos_base_dev,
+                                        q_per_kv_batch, kcache, vcache, cache_bs, cache_rs));
   CVB_LAUNCHED();
   return 0;
 }
@@ -154,6 +160,8 @@ int rope_qkv(cudaStream_t st, bf16* qkv, long ld, const float* timescale, int ro
 // so the denoise attention applies RoPE while staging Q / K (same sincosf as rope_kernel: bit-identical rotation)
 __global__ void rope_table_kernel(const float* __restrict__ timescale, const int* __restrict__ pos_base_dev,
                                   int tq, int half, float2* __restrict__ tab) {
+  pdl_wait();
+  pdl_launch();
   const int b = blockIdx.x / tq, t = blockIdx.x % tq;
   const float pos = static_cast<float>(pos_base_dev[b] + t);
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
@@ -165,7 +173,7 @@ __global__ void rope_table_kernel(const float* __restrict__ timescale, const int
 
 int rope_table(cudaStream_t st, const float* timescale, const int* pos_base_dev, int batches, int tq, int half,
                float2* tab) {
-  rope_table_kernel<<<batches * tq, 128, 0, st>>>(timescale, pos_base_dev, tq, half, tab);
+  CVB_TRY(launch_pdl(rope_table_kernel, dim3(batches * tq), dim3(128), 0, st, 1, timescale, pos_base_dev, tq, half, tab));
   CVB_LAUNCHED();
   return 0;
 }
@@ -179,6 +187,8 @@ __global__ void __launch_bounds__(256) action_out_euler_kernel(const bf16* __res
                                                                float* __restrict__ v_out, int width,
                                                                int adim, int chunk, int suffix_len,
                                                                float dt) {
+  pdl_wait();
+  pdl_launch();
   const int n = blockIdx.x / chunk, j = blockIdx.x % chunk;
   const bf16* h = hn + (static_cast<long>(n) * suffix_len + (suffix_len - chunk) + j) * ld;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -200,8 +210,8 @@ __global__ void __launch_bounds__(256) action_out_euler_kernel(const bf16* __res
 int action_out_euler(cudaStream_t st, const bf16* hn, long ld, const float* w, const float* bias,
                      float* x_t, float* v_out, int n_cand, int width, int adim, int chunk,
                      int suffix_len, float dt) {
-  action_out_euler_kernel<<<n_cand * chunk, 256, 0, st>>>(hn, ld, w, bias, x_t, v_out, width, adim,
-                                                         chunk, suffix_len, dt);
+  CVB_TRY(launch_pdl(action_out_euler_kernel, dim3(n_cand * chunk), dim3(256), 0, st, 1, hn, ld, w, bias, x_t, v_out, width, adim,
+                                                         chunk, suffix_len, dt));
   CVB_LAUNCHED();
   return 0;
 }
@@ -210,13 +220,15 @@ int action_out_euler(cudaStream_t st, const bf16* hn, long ld, const float* w, c
 // suffix[n, 0, :] = float(bf16(state_emb))  (the state row never changes across denoise steps)
 __global__ void fill_state_rows_kernel(const float* __restrict__ state_emb, float* __restrict__ suffix,
                                        int width, int suffix_len) {
+  pdl_wait();
+  pdl_launch();
   float* dst = suffix + static_cast<long>(blockIdx.x) * suffix_len * width;
   for (int i = threadIdx.x; i < width; i += blockDim.x) dst[i] = bf16_round(state_emb[i]);
 }
 
 int fill_state_rows(cudaStream_t st, const float* state_emb, float* suffix, int n_cand, int width,
                     int suffix_len) {
-  fill_state_rows_kernel<<<n_cand, 256, 0, st>>>(state_emb, suffix, width, suffix_len);
+  CVB_TRY(launch_pdl(fill_state_rows_kernel, dim3(n_cand), dim3(256), 0, st, 1, state_emb, suffix, width, suffix_len));
   CVB_LAUNCHED();
   return 0;
 }
@@ -224,22 +236,26 @@ int fill_state_rows(cudaStream_t st, const float* state_emb, float* suffix, int 
 // plen[r] = n_img + lang_len[r]; rows_valid = sum (unused for now)
 __global__ void prefix_len_kernel(const int* __restrict__ lang_len, int* __restrict__ plen, int R,
                                   int n_img) {
+  pdl_wait();
+  pdl_launch();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < R) plen[r] = n_img + lang_len[r];
 }
 
 int prefix_lengths(cudaStream_t st, const int* lang_len, int* plen, int R, int n_img) {
-  prefix_len_kernel<<<(R + 63) / 64, 64, 0, st>>>(lang_len, plen, R, n_img);
+  CVB_TRY(launch_pdl(prefix_len_kernel, dim3((R + 63) / 64), dim3(64), 0, st, 1, lang_len, plen, R, n_img));
   CVB_LAUNCHED();
   return 0;
 }
 
 __global__ void bf16_table_to_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long n) {
+  pdl_wait();
+  pdl_launch();
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __bfloat162float(src[i]);
 }
 int bf16_to_f32(cudaStream_t st, const bf16* src, float* dst, long n) {
-  bf16_table_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n);
+  CVB_TRY(launch_pdl(bf16_table_to_f32_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, 1, src, dst, n));
   CVB_LAUNCHED();
   return 0;
 }

@@ -4,6 +4,7 @@
 // relative, so these stay true-fp32 FFMA (no TF32): 64x64 tile, 16-deep k slices, 4x4 per thread.
 #include "host_common.h"
 #include "ops.h"
+#include "ptx.cuh"
 
 namespace cvb {
 
@@ -31,6 +32,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
                                                     const float* __restrict__ row_bias,
                                                     const float* __restrict__ resid, long ldr,
                                                     int act, int out_group, int w_kn) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float As[TK][TM + 4];
   __shared__ float Ws[TK][TN + 4];
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
@@ -115,8 +118,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
 int sgemm_f32(cudaStream_t st, const SgemmCall& c) {
   CVB_REQUIRE(c.M > 0 && c.N > 0 && c.K > 0, "empty sgemm");
   dim3 grid((c.N + TN - 1) / TN, (c.M + TM - 1) / TM);
-  sgemm_kernel<<<grid, 256, 0, st>>>(c.A, c.lda, c.W, c.ldw, c.M, c.N, c.K, c.C, c.ldc, c.bias,
-                                     c.row_bias, c.resid, c.ldr, c.act, c.out_group, c.w_kn);
+  CVB_TRY(launch_pdl(sgemm_kernel, dim3(grid), dim3(256), 0, st, 1, c.A, c.lda, c.W, c.ldw, c.M, c.N, c.K, c.C, c.ldc, c.bias,
+                                     c.row_bias, c.resid, c.ldr, c.act, c.out_group, c.w_kn));
   CVB_LAUNCHED();
   return 0;
 }

@@ -42,6 +42,8 @@ __device__ __forceinline__ float bmax(float v, float* red) {
 // ---------------------------------------------------------------------------------------------
 __global__ void embed_tokens_pos_kernel(const bf16* __restrict__ table, const bf16* __restrict__ pos,
                                         const int64_t* __restrict__ tok, bf16* __restrict__ out, int width) {
+  pdl_wait();
+  pdl_launch();
   const int t = blockIdx.x;
   const bf16* src = table + tok[t] * width;
   const bf16* pp = pos + static_cast<long>(t) * width;
@@ -51,13 +53,15 @@ __global__ void embed_tokens_pos_kernel(const bf16* __restrict__ table, const bf
 }
 int embed_tokens_pos(cudaStream_t st, const bf16* table, const bf16* pos, const int64_t* tok, bf16* out,
                      int tokens, int width) {
-  embed_tokens_pos_kernel<<<tokens, 256, 0, st>>>(table, pos, tok, out, width);
+  CVB_TRY(launch_pdl(embed_tokens_pos_kernel, dim3(tokens), dim3(256), 0, st, 1, table, pos, tok, out, width));
   CVB_LAUNCHED();
   return 0;
 }
 
 // y[r,:] = float(x[r,:]) / ||float(x[r,:])||_2
 __global__ void l2norm_bf16_kernel(const bf16* __restrict__ x, long ldx, float* __restrict__ y, int width) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float red[32];
   const bf16* xr = x + blockIdx.x * ldx;
   float ss = 0.f;
@@ -70,13 +74,15 @@ __global__ void l2norm_bf16_kernel(const bf16* __restrict__ x, long ldx, float* 
     y[static_cast<long>(blockIdx.x) * width + i] = __bfloat162float(xr[i]) / nrm;
 }
 int l2norm_rows_bf16_to_f32(cudaStream_t st, const bf16* x, long ldx, float* y, int rows, int width) {
-  l2norm_bf16_kernel<<<rows, 256, 0, st>>>(x, ldx, y, width);
+  CVB_TRY(launch_pdl(l2norm_bf16_kernel, dim3(rows), dim3(256), 0, st, 1, x, ldx, y, width));
   CVB_LAUNCHED();
   return 0;
 }
 
 // in-place row softmax of x / clamp(*temp, 0, 100)
 __global__ void softmax_temp_kernel(float* __restrict__ x, int cols, const float* __restrict__ temp) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float red[32];
   float* xr = x + static_cast<long>(blockIdx.x) * cols;
   const float t = fminf(fmaxf(*temp, 0.f), 100.f);
@@ -89,17 +95,19 @@ __global__ void softmax_temp_kernel(float* __restrict__ x, int cols, const float
   for (int i = threadIdx.x; i < cols; i += blockDim.x) xr[i] = expf(xr[i] / t - m) / s;
 }
 int softmax_rows_temp(cudaStream_t st, float* x, int rows, int cols, const float* temp_dev) {
-  softmax_temp_kernel<<<rows, 256, 0, st>>>(x, cols, temp_dev);
+  CVB_TRY(launch_pdl(softmax_temp_kernel, dim3(rows), dim3(256), 0, st, 1, x, cols, temp_dev));
   CVB_LAUNCHED();
   return 0;
 }
 
 __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, long n) {
+  pdl_wait();
+  pdl_launch();
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) y[i] = a[i] + b[i];
 }
 int add_f32(cudaStream_t st, const float* a, const float* b, float* y, long n) {
-  add_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b, y, n);
+  CVB_TRY(launch_pdl(add_f32_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, 1, a, b, y, n));
   CVB_LAUNCHED();
   return 0;
 }
@@ -157,6 +165,8 @@ __device__ void layernorm_vec(float* __restrict__ out, const float* __restrict__
 }  // namespace
 
 __global__ void __launch_bounds__(512) pool_chain_kernel(const PoolChain* __restrict__ chains) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float sm[];
   __shared__ float red[32];
   const PoolChain& c = chains[blockIdx.x];
@@ -220,13 +230,15 @@ __global__ void __launch_bounds__(512) pool_chain_kernel(const PoolChain* __rest
 
 int pool_chains(cudaStream_t st, const PoolChain* chains_dev, int n_chains, int embed, int heads, int tokens) {
   const size_t smem = (3 * embed + heads * tokens) * sizeof(float);
-  pool_chain_kernel<<<n_chains, 512, smem, st>>>(chains_dev);
+  CVB_TRY(launch_pdl(pool_chain_kernel, dim3(n_chains), dim3(512), smem, st, 1, chains_dev));
   CVB_LAUNCHED();
   return 0;
 }
 
 // it[m] = normalize(W_ip . cat[text_tok[m], vision_tok[m]] + b_ip)      (efficient_ensemble_merged.py:220-223)
 __global__ void __launch_bounds__(256) it_finalize_kernel(const ItFinal* __restrict__ items, int E) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float sm[];
   __shared__ float red[32];
   const ItFinal& f = items[blockIdx.x];
@@ -244,7 +256,7 @@ __global__ void __launch_bounds__(256) it_finalize_kernel(const ItFinal* __restr
   for (int i = threadIdx.x; i < E; i += blockDim.x) f.out[i] = out[i] / nrm;
 }
 int it_finalize(cudaStream_t st, const ItFinal* items_dev, int members, int embed) {
-  it_finalize_kernel<<<members, 256, 3 * embed * sizeof(float), st>>>(items_dev, embed);
+  CVB_TRY(launch_pdl(it_finalize_kernel, dim3(members), dim3(256), 3 * embed * sizeof(float), st, 1, items_dev, embed));
   CVB_LAUNCHED();
   return 0;
 }
@@ -255,6 +267,8 @@ int it_finalize(cudaStream_t st, const ItFinal* items_dev, int members, int embe
 __global__ void __launch_bounds__(256) traj_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ traj,
                                                              float* __restrict__ out, int S, int E, int H, int adim,
                                                              float pad_value) {
+  pdl_wait();
+  pdl_launch();
   // one CTA per candidate: stage its [S, 3E] q/k/v rows in shared memory (coalesced), then one warp per
   // head; lane = (query step, 1/2..1/8 slice of head_dim) so all 32 lanes work and reads stay conflict-light.
   extern __shared__ float sm[];
@@ -314,7 +328,7 @@ int traj_attention(cudaStream_t st, const float* qkv, const float* traj, float* 
     CVB_CUDA(cudaFuncSetAttribute(traj_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  traj_attention_kernel<<<n_cand, 256, smem, st>>>(qkv, traj, out, S, E, H, adim, pad_value);
+  CVB_TRY(launch_pdl(traj_attention_kernel, dim3(n_cand), dim3(256), smem, st, 1, qkv, traj, out, S, E, H, adim, pad_value));
   CVB_LAUNCHED();
   return 0;
 }
@@ -323,6 +337,8 @@ int traj_attention(cudaStream_t st, const float* qkv, const float* traj, float* 
 __global__ void __launch_bounds__(256) masked_mean_l2_kernel(const float* __restrict__ x, const float* __restrict__ traj,
                                                              float* __restrict__ out, int S, int E, int adim,
                                                              float pad_value) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float red[32];
   const int n = blockIdx.x;
   float cnt = 0.f;
@@ -344,7 +360,7 @@ __global__ void __launch_bounds__(256) masked_mean_l2_kernel(const float* __rest
 }
 int masked_mean_l2norm(cudaStream_t st, const float* x, const float* traj, float* out, int n_cand, int S, int E,
                        int adim, float pad_value) {
-  masked_mean_l2_kernel<<<n_cand, 256, 0, st>>>(x, traj, out, S, E, adim, pad_value);
+  CVB_TRY(launch_pdl(masked_mean_l2_kernel, dim3(n_cand), dim3(256), 0, st, 1, x, traj, out, S, E, adim, pad_value));
   CVB_LAUNCHED();
   return 0;
 }
@@ -380,6 +396,8 @@ __global__ void __launch_bounds__(1024) fuse_score_select_kernel(const float* __
                                                                  int K, float* __restrict__ group_mean,
                                                                  int* __restrict__ best_idx, float* __restrict__ best_score,
                                                                  int do_select) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float sm[];
   __shared__ float red[32];
   float* fit = sm;          // [E]
@@ -425,8 +443,8 @@ __global__ void __launch_bounds__(1024) fuse_score_select_kernel(const float* __
 int fuse_score_select(cudaStream_t st, const float* it, const float* act, int M, int N, int E, float* scores, int R,
                       int K, float* group_mean, int* best_idx, float* best_score, int do_select) {
   CVB_REQUIRE(!do_select || R * K == N, "R*K must equal the number of candidates");
-  fuse_score_select_kernel<<<1, 1024, (E + R + 1) * sizeof(float), st>>>(it, act, M, N, E, scores, R, K, group_mean,
-                                                                         best_idx, best_score, do_select);
+  CVB_TRY(launch_pdl(fuse_score_select_kernel, dim3(1), dim3(1024), (E + R + 1) * sizeof(float), st, 1, it, act, M, N, E, scores, R, K, group_mean,
+                                                                         best_idx, best_score, do_select));
   CVB_LAUNCHED();
   return 0;
 }
@@ -434,12 +452,14 @@ int fuse_score_select(cudaStream_t st, const float* it, const float* act, int M,
 __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ scores, int R, int K,
                                                      float* __restrict__ group_mean, int* __restrict__ best_idx,
                                                      float* __restrict__ best_score) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float sm[];
   select_block(scores, R, K, group_mean, best_idx, best_score, sm);
 }
 int select_best(cudaStream_t st, const float* scores, int R, int K, float* group_mean, int* best_idx,
                 float* best_score) {
-  select_kernel<<<1, 256, (R + 1) * sizeof(float), st>>>(scores, R, K, group_mean, best_idx, best_score);
+  CVB_TRY(launch_pdl(select_kernel, dim3(1), dim3(256), (R + 1) * sizeof(float), st, 1, scores, R, K, group_mean, best_idx, best_score));
   CVB_LAUNCHED();
   return 0;
 }
@@ -454,6 +474,8 @@ int select_best(cudaStream_t st, const float* scores, int R, int K, float* group
 __global__ void format_traj_kernel(const float* __restrict__ actions, int chunk, int adim_stride,
                                    FormatStats st, const float* __restrict__ past, int num_past, int history,
                                    int n_future, float* __restrict__ traj) {
+  pdl_wait();
+  pdl_launch();
   const int n = blockIdx.x;
   const int A = 7;
   const int used = num_past + n_future;
@@ -484,8 +506,8 @@ int format_trajectories(cudaStream_t stream, const float* actions, int n_cand, i
   CVB_REQUIRE(n_future >= 1 && n_future <= chunk, "n_future must be in [1, chunk]");
   CVB_REQUIRE(num_past >= 0 && num_past + n_future <= history, "history too short for past + future actions");
   CVB_REQUIRE(adim_stride >= 7, "action stride must be >= 7");
-  format_traj_kernel<<<n_cand, 96, 0, stream>>>(actions, chunk, adim_stride, st, past, num_past, history, n_future,
-                                                traj);
+  CVB_TRY(launch_pdl(format_traj_kernel, dim3(n_cand), dim3(96), 0, stream, 1, actions, chunk, adim_stride, st, past, num_past, history, n_future,
+                                                traj));
   CVB_LAUNCHED();
   return 0;
 }

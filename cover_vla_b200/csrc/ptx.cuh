@@ -21,6 +21,14 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the library is launched with programmatic stream serialization (host_common.h: launch_pdl): the
+// next kernel's CTAs may be scheduled while this one still runs.  pdl_wait() blocks until the preceding kernel has
+// completed and flushed its memory (no-op without the launch attribute); nothing that depends on - or overwrites data
+// read by - an earlier kernel may happen before it.  pdl_launch() lets the dependent grid start its prologue.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -6,7 +6,8 @@ from cover_vla_b200 import synthetic as S
 from cover_vla_b200.cover import CoverInputs, CoverStep
 R, K = 8, 5
 d, v = S.FULL, S.VFULL
-eng = S.build_engine(d, S.make_pi0_weights(d, 0), v, S.make_verifier_weights(v, 0), R, K)
+import os
+eng = S.build_engine(d, S.make_pi0_weights(d, 0), v, S.make_verifier_weights(v, 0), R, K, use_cuda_graph=int(os.environ.get("CVB_GRAPH", "1")))
 inp = S.make_inputs(d, R, K, seed=3); vin = S.make_verifier_inputs(v, 1, seed=3)
 x = CoverInputs(image=inp["image"][0].cuda().contiguous(), lang_tokens=inp["tokens"].cuda(),
                 lang_len=inp["lens"].to(torch.int32).cuda(), state=inp["state"][0].cuda().contiguous(),

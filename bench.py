@@ -107,8 +107,10 @@ def make_device_inputs(S, d, v, R, K, seed, device):
                 noise=inp["noise"].contiguous(), vf_image=vin["image"][0].contiguous(),
                 vf_tokens=vin["tokens"][0].contiguous(), past=past)
     host = {k: t.pin_memory() for k, t in host.items()}
-    dev = CoverInputs(**{k: t.to(device) for k, t in host.items()})
-    return host, dev
+    # the host tokenised the prompts, so it knows the longest one without a device round trip
+    lmax = int(inp["lens"].max())
+    dev = CoverInputs(**{k: t.to(device) for k, t in host.items()}, lang_len_max=lmax)
+    return host, dev, lmax
 
 
 def run_gpu(args):
@@ -141,7 +143,7 @@ def run_gpu(args):
     vw = S.make_verifier_weights(v, seed=0)
     eng = S.build_engine(d, w, v, vw, R, K, device=device)
     t_build = time.time() - t0
-    host, x = make_device_inputs(S, d, v, R, K, seed=100 + rank, device=device)
+    host, x, lmax = make_device_inputs(S, d, v, R, K, seed=100 + rank, device=device)
     step = CoverStep(eng, K)
 
     def one_step():
@@ -191,7 +193,7 @@ def run_gpu(args):
 
     # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
     def e2e_step():
-        xin = CoverInputs(**{k: t.to(device, non_blocking=True) for k, t in host.items()})
+        xin = CoverInputs(**{k: t.to(device, non_blocking=True) for k, t in host.items()}, lang_len_max=lmax)
         return step(xin)  # returns python (idx, score, winner actions): includes the D2H read
 
     for _ in range(3):

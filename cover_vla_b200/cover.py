@@ -57,6 +57,7 @@ class CoverInputs:
     vf_image: torch.Tensor     # f32 [3, 384, 384] (verifier preprocessing)
     vf_tokens: torch.Tensor    # i64 [ctx] (the CURRENT task description)
     past: torch.Tensor | None = None  # f32 [num_past, 7] verifier-format action history tail
+    lang_len_max: int | None = None   # host-known bound on valid tokens per prompt (lets the prefix skip padding rows)
 
 
 class CoverStep:
@@ -79,7 +80,7 @@ class CoverStep:
             cur = torch.cuda.current_stream(e.device)
             self._side.wait_stream(cur)
             # critical path first: one graph launch for the whole sampler, then the side work
-            actions = e.pi0_sample(x.image, x.lang_tokens, x.lang_len, x.state, x.noise, K=self.K)
+            actions = e.pi0_sample(x.image, x.lang_tokens, x.lang_len, x.state, x.noise, K=self.K, lang_len_max=x.lang_len_max)
             with torch.cuda.stream(self._side):
                 e.verifier_context(x.vf_image, x.vf_tokens)
             traj = format_trajectories(actions, x.past, e.cfg.vf_history, self.n_future, self.p01, self.p99)
@@ -87,7 +88,7 @@ class CoverStep:
             scores, gmean, bidx, bscore = e.verifier_score(None, None, traj, R if select else 0, self.K,
                                                            recompute_context=False)
         else:
-            actions = e.pi0_sample(x.image, x.lang_tokens, x.lang_len, x.state, x.noise, K=self.K)
+            actions = e.pi0_sample(x.image, x.lang_tokens, x.lang_len, x.state, x.noise, K=self.K, lang_len_max=x.lang_len_max)
             traj = format_trajectories(actions, x.past, e.cfg.vf_history, self.n_future, self.p01, self.p99)
             scores, gmean, bidx, bscore = e.verifier_score(x.vf_image, x.vf_tokens, traj, R if select else 0, self.K)
         return actions, traj, scores, gmean, bidx, bscore
@@ -119,7 +120,7 @@ def shard_inputs(x: CoverInputs, K: int, world_size: int, rank: int) -> CoverInp
     a, b = rephrase_shard(R, world_size, rank)
     return CoverInputs(image=x.image, lang_tokens=x.lang_tokens[a:b].contiguous(), lang_len=x.lang_len[a:b].contiguous(),
                        state=x.state, noise=x.noise[a * K:b * K].contiguous(), vf_image=x.vf_image,
-                       vf_tokens=x.vf_tokens, past=x.past)
+                       vf_tokens=x.vf_tokens, past=x.past, lang_len_max=x.lang_len_max)
 
 
 def gather_and_select(local_scores, local_actions, R: int, K: int, select_fn, group=None):

@@ -130,6 +130,13 @@ int cvb_pi0_sample(cvb_handle* h, const float* image, const int64_t* lang_tokens
                          (cudaStream_t)stream);
 }
 
+int cvb_pi0_set_lang_len_hint(cvb_handle* h, int max_valid_tokens) {
+  CVB_REQUIRE(h != nullptr, "null handle");
+  CVB_REQUIRE(max_valid_tokens >= 0, "hint must be >= 0 (0 = no hint)");
+  h->pi0.lang_hint = max_valid_tokens;
+  return 0;
+}
+
 int cvb_pi0_run_phase(cvb_handle* h, int phase, int R, int K, void* stream) {
   CVB_REQUIRE(h != nullptr, "null handle");
   return cvb::pi0_run_phase(h, phase, R, K, (cudaStream_t)stream);

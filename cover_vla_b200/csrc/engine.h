@@ -111,7 +111,8 @@ struct Pi0State {
   bf16 *kcache = nullptr, *vcache = nullptr;
   float *state_emb = nullptr, *a1 = nullptr, *a2 = nullptr, *suffix = nullptr, *v0 = nullptr;
   bf16 *he = nullptr, *xe = nullptr, *qkv_e = nullptr, *attn_e = nullptr, *act_e = nullptr;
-  GraphCache graphs;  // key = R * 65536 + K
+  int lang_hint = 0;  // caller's bound on valid language tokens per prompt (0 = max_lang_len), cvb_pi0_set_lang_len_hint
+  GraphCache graphs;  // key = (lang rows << 40) | R << 16 | K
 };
 
 struct VerifierState;  // engine_verifier.cu
@@ -130,6 +131,12 @@ struct cvb_handle {
   int n_img() const { return (cfg.vis_image / cfg.vis_patch) * (cfg.vis_image / cfg.vis_patch); }
   int prefix_len() const { return n_img() + cfg.max_lang_len; }
   int suffix_len() const { return 1 + cfg.chunk_size; }
+  // language rows actually processed per prompt: the caller's hint rounded up to 8 (bounds the number of graphs)
+  int lang_rows() const {
+    const int hint = pi0.lang_hint > 0 ? pi0.lang_hint : cfg.max_lang_len;
+    const int r = (hint + 7) / 8 * 8;
+    return r < cfg.max_lang_len ? r : cfg.max_lang_len;
+  }
 };
 
 namespace cvb {

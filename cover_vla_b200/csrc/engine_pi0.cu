@@ -330,12 +330,15 @@ static int run_vision(cvb_handle* h, cudaStream_t st) {
 static int run_prefix(cvb_handle* h, cudaStream_t st, int R) {
   const cvb_config& c = h->cfg;
   Pi0State& s = h->pi0;
-  const int T = h->n_img(), P = h->prefix_len(), D = c.lm_width, hd = c.head_dim;
-  const int qd = c.heads * hd, qkvw = qd + 2 * hd, M = R * P;
+  // Right-padded language tokens are masked as keys and their own rows are never read (dropping them
+  // is bit-exact on the reference), so only Pe = image tokens + lang_rows() rows per prompt are processed; the KV
+  // cache keeps the full-P layout the denoise attention indexes.
+  const int T = h->n_img(), P = h->prefix_len(), Le = h->lang_rows(), Pe = T + Le, D = c.lm_width, hd = c.head_dim;
+  const int qd = c.heads * hd, qkvw = qd + 2 * hd, M = R * Pe;
   const bf16* embed;
   CVB_TRY(W(h, LM + "embed_tokens.weight", CVB_BF16, (int64_t)c.vocab * D, &embed));
-  CVB_TRY(build_prefix(st, s.proj_out, embed, s.in_tokens, s.hp, R, T, c.max_lang_len, D));
-  CVB_TRY(prefix_lengths(st, s.in_lang_len, s.plen, R, T));
+  CVB_TRY(build_prefix(st, s.proj_out, embed, s.in_tokens, s.hp, R, T, Le, c.max_lang_len, D));
+  CVB_TRY(prefix_lengths(st, s.in_lang_len, s.plen, R, T, Le));
   const long layer_stride = (long)c.max_rephrases * P * hd;
   for (int l = 0; l < c.layers; ++l) {
     const GemmaLayer& L = s.lm[l];
@@ -343,15 +346,15 @@ static int run_prefix(cvb_handle* h, cudaStream_t st, int R) {
     bf16* vc = s.vcache + l * layer_stride;
     CVB_TRY(rmsnorm(st, s.hp, 0, D, L.in_norm, 0, s.xp, D, M, D, 1e-6f, nullptr));
     CVB_TRY(gemm(st, s.xp, D, L.wqkv, D, M, qkvw, D, EPI_STORE, s.qkv_p, qkvw));
-    CVB_TRY(rope_qkv(st, s.qkv_p, qkvw, s.rope_timescale, M, c.heads, hd, P, nullptr, 1, kc, vc,
+    CVB_TRY(rope_qkv(st, s.qkv_p, qkvw, s.rope_timescale, M, c.heads, hd, Pe, nullptr, 1, kc, vc,
                      (long)P * hd, hd));
     if (l == c.layers - 1) break;  // only this layer's K/V are consumed (modeling_pi0.py:688-695)
     AttnCall a;
-    a.q = s.qkv_p, a.q_batch_stride = (long)P * qkvw, a.q_row_stride = qkvw;
+    a.q = s.qkv_p, a.q_batch_stride = (long)Pe * qkvw, a.q_row_stride = qkvw;
     a.k0 = kc, a.v0 = vc, a.kv0_batch_stride = (long)P * hd, a.kv0_row_stride = hd;
-    a.kv0_len_dev = s.plen, a.kv0_max = P, a.q_per_kv_batch = 1;
-    a.out = s.attn_p, a.o_batch_stride = (long)P * qd, a.o_row_stride = qd;
-    a.batches = R, a.heads = c.heads, a.kv_heads = 1, a.tq = P, a.head_dim = hd;
+    a.kv0_len_dev = s.plen, a.kv0_max = Pe, a.q_per_kv_batch = 1;
+    a.out = s.attn_p, a.o_batch_stride = (long)Pe * qd, a.o_row_stride = qd;
+    a.batches = R, a.heads = c.heads, a.kv_heads = 1, a.tq = Pe, a.head_dim = hd;
     a.scale = 1.0f / sqrtf(static_cast<float>(hd));
     CVB_TRY(attention(st, a));
     CVB_TRY(gemm(st, s.attn_p, qd, L.wo, qd, M, D, qd, EPI_RESID, s.hp, D, nullptr, s.hp, D));
@@ -394,7 +397,7 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
   // RoPE of the suffix is applied inside the cluster decode attention (from a table built once per sample) when the
   // shape is eligible; otherwise by the standalone kernel
   AttnCall probe;
-  probe.k1 = s.qkv_e, probe.kv1_len = S, probe.kv0_len_dev = s.plen, probe.kv0_max = P;
+  probe.k1 = s.qkv_e, probe.kv1_len = S, probe.kv0_len_dev = s.plen, probe.kv0_max = h->n_img() + h->lang_rows();
   probe.heads = c.heads, probe.kv_heads = 1, probe.tq = S, probe.head_dim = hd;
   const bool fused_rope = attention_decode_eligible(probe);
   if (fused_rope) CVB_TRY(rope_table(st, s.rope_timescale, s.plen, R, S, hd / 2, s.rope_tab));
@@ -426,7 +429,7 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
       a.kv0_static = 1;
       a.q = s.qkv_e, a.q_batch_stride = (long)S * qkvw, a.q_row_stride = qkvw;
       a.k0 = s.kcache + l * layer_stride, a.v0 = s.vcache + l * layer_stride;
-      a.kv0_batch_stride = (long)P * hd, a.kv0_row_stride = hd, a.kv0_len_dev = s.plen, a.kv0_max = P;
+      a.kv0_batch_stride = (long)P * hd, a.kv0_row_stride = hd, a.kv0_len_dev = s.plen, a.kv0_max = h->n_img() + h->lang_rows();
       a.q_per_kv_batch = K;
       a.k1 = s.qkv_e + qd, a.v1 = s.qkv_e + qd + hd, a.kv1_batch_stride = (long)S * qkvw;
       a.kv1_row_stride = qkvw, a.kv1_len = S, a.suffix_mask = 1;
@@ -471,7 +474,7 @@ int pi0_sample(cvb_handle* h, const float* image, const int64_t* tokens, const i
   CVB_CUDA(cudaMemcpyAsync(s.in_state, state, c.max_state_dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
   CVB_CUDA(cudaMemcpyAsync(s.x_t, noise, act_bytes, cudaMemcpyDeviceToDevice, st));
 
-  const long key = (long)R * 65536 + K;
+  const long key = ((long)h->lang_rows() << 40) | ((long)R << 16) | (long)K;
   CVB_TRY(s.graphs.run(c.use_cuda_graph != 0, key, st, [&](cudaStream_t cs) { return run_all(h, cs, R, K); }));
   CVB_CUDA(cudaMemcpyAsync(actions, s.x_t, act_bytes, cudaMemcpyDeviceToDevice, st));
   return 0;

@@ -40,7 +40,7 @@ int im2col_patches(cudaStream_t st, const float* img, bf16* out, int C, int H, i
 //                             : bf16(embed[tok[r, t-n_img], :] * sqrt(D))               + HF get_image_features, :549-553)
 __global__ void build_prefix_kernel(const bf16* __restrict__ proj, const bf16* __restrict__ embed,
                                     const int64_t* __restrict__ tok, bf16* __restrict__ prefix,
-                                    int n_img, int n_lang, int D, float sqrt_d, float sqrt_d_bf16) {
+                                    int n_img, int n_lang, int tok_stride, int D, float sqrt_d, float sqrt_d_bf16) {
   pdl_wait();
   pdl_launch();
   const int t = blockIdx.x, r = blockIdx.y;
@@ -60,7 +60,7 @@ __global__ void build_prefix_kernel(const bf16* __restrict__ proj, const bf16* _
       *reinterpret_cast<uint4*>(dst + i) = make_uint4(o[0], o[1], o[2], o[3]);
     }
   } else {
-    const int64_t id = tok[static_cast<long>(r) * n_lang + (t - n_img)];
+    const int64_t id = tok[static_cast<long>(r) * tok_stride + (t - n_img)];
     const bf16* src = embed + id * D;
     for (int i = threadIdx.x * 8; i < D; i += blockDim.x * 8) {
       const uint4 v = *reinterpret_cast<const uint4*>(src + i);
@@ -77,12 +77,12 @@ __global__ void build_prefix_kernel(const bf16* __restrict__ proj, const bf16* _
 }
 
 int build_prefix(cudaStream_t st, const bf16* proj, const bf16* embed, const int64_t* tok,
-                 bf16* prefix, int R, int n_img, int n_lang, int D) {
+                 bf16* prefix, int R, int n_img, int n_lang, int tok_stride, int D) {
   CVB_REQUIRE(D % 8 == 0, "lm width must be a multiple of 8");
   const float s = static_cast<float>(sqrt(static_cast<double>(D)));  // (float)(D ** 0.5)
   const float sb = __bfloat162float(__float2bfloat16_rn(s));
   dim3 grid(n_img + n_lang, R);
-  CVB_TRY(launch_pdl(build_prefix_kernel, dim3(grid), dim3(128), 0, st, 1, proj, embed, tok, prefix, n_img, n_lang, D, s, sb));
+  CVB_TRY(launch_pdl(build_prefix_kernel, dim3(grid), dim3(128), 0, st, 1, proj, embed, tok, prefix, n_img, n_lang, tok_stride, D, s, sb));
   CVB_LAUNCHED();
   return 0;
 }
@@ -235,15 +235,15 @@ int fill_state_rows(cudaStream_t st, const float* state_emb, float* suffix, int 
 
 // plen[r] = n_img + lang_len[r]; rows_valid = sum (unused for now)
 __global__ void prefix_len_kernel(const int* __restrict__ lang_len, int* __restrict__ plen, int R,
-                                  int n_img) {
+                                  int n_img, int max_lang) {
   pdl_wait();
   pdl_launch();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < R) plen[r] = n_img + lang_len[r];
+  if (r < R) plen[r] = n_img + min(max(lang_len[r], 0), max_lang);
 }
 
-int prefix_lengths(cudaStream_t st, const int* lang_len, int* plen, int R, int n_img) {
-  CVB_TRY(launch_pdl(prefix_len_kernel, dim3((R + 63) / 64), dim3(64), 0, st, 1, lang_len, plen, R, n_img));
+int prefix_lengths(cudaStream_t st, const int* lang_len, int* plen, int R, int n_img, int max_lang) {
+  CVB_TRY(launch_pdl(prefix_len_kernel, dim3((R + 63) / 64), dim3(64), 0, st, 1, lang_len, plen, R, n_img, max_lang));
   CVB_LAUNCHED();
   return 0;
 }

@@ -11,7 +11,7 @@ namespace cvb {
 
 int im2col_patches(cudaStream_t st, const float* img, bf16* out, int C, int H, int W, int P, int kpad);
 int build_prefix(cudaStream_t st, const bf16* proj, const bf16* embed, const int64_t* tok,
-                 bf16* prefix, int R, int n_img, int n_lang, int D);
+                 bf16* prefix, int R, int n_img, int n_lang, int tok_stride, int D);
 int rope_qkv(cudaStream_t st, bf16* qkv, long ld, const float* timescale, int rows, int heads,
              int hd, int rows_per_batch, const int* pos_base_dev, int q_per_kv_batch, bf16* kcache,
              bf16* vcache, long cache_bs, long cache_rs);
@@ -22,7 +22,7 @@ int fill_state_rows(cudaStream_t st, const float* state_emb, float* suffix, int 
                     int suffix_len);
 int rope_table(cudaStream_t st, const float* timescale, const int* pos_base_dev, int batches, int tq, int half,
                float2* tab);
-int prefix_lengths(cudaStream_t st, const int* lang_len, int* plen, int R, int n_img);
+int prefix_lengths(cudaStream_t st, const int* lang_len, int* plen, int R, int n_img, int max_lang);
 int bf16_to_f32(cudaStream_t st, const bf16* src, float* dst, long n);
 
 }  // namespace cvb

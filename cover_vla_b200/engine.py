@@ -114,6 +114,7 @@ class Engine:
         L.cvb_required_weight_name.restype = C.c_char_p
         L.cvb_finalize.argtypes = [C.c_void_p, C.c_void_p]
         L.cvb_pi0_sample.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.cvb_pi0_set_lang_len_hint.argtypes = [C.c_void_p, C.c_int]
         L.cvb_pi0_run_phase.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.cvb_debug_copy.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.cvb_debug_copy.restype = C.c_int64
@@ -158,7 +159,15 @@ class Engine:
                     del self._keep[k]
 
     # ------------------------------------------------------------------ pi0
-    def pi0_sample(self, image, lang_tokens, lang_len, state, noise, K: int, out=None):
+    def set_lang_len_hint(self, max_valid_tokens: int | None):
+        """Bound on valid language tokens per prompt (None / 0 = none).  The host that tokenised the prompts knows it
+        without a device sync; the prefix then skips the right-padding rows (exact: SURVEY.md F11)."""
+        n = int(max_valid_tokens or 0)
+        if n != getattr(self, "_lang_hint", 0):
+            _lib.check(self.lib.cvb_pi0_set_lang_len_hint(self._h, n))
+            self._lang_hint = n
+
+    def pi0_sample(self, image, lang_tokens, lang_len, state, noise, K: int, out=None, lang_len_max: int | None = None):
         """image f32 [3,H,W]; lang_tokens i64 [R,L]; lang_len i32 [R]; state f32 [max_state_dim];
         noise f32 [R*K, chunk, max_action_dim] -> actions f32 (same shape).  Asynchronous."""
         cfg = self.cfg
@@ -172,6 +181,7 @@ class Engine:
             assert t.is_cuda and t.is_contiguous()
         if out is None:
             out = torch.empty_like(noise)
+        self.set_lang_len_hint(lang_len_max)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.cvb_pi0_sample(self._h, _lib.ptr(image), _lib.ptr(lang_tokens), _lib.ptr(lang_len),
                                                _lib.ptr(state), _lib.ptr(noise), R, K, _lib.ptr(out),

@@ -72,6 +72,9 @@ class PI0FlowMatching:
         # rows, K samples per rephrase): skips the two device->host checks below
         self.assume_cover_layout = False
         self.samples_per_rephrase: int | None = None
+        # bound on valid language tokens per prompt known WITHOUT a device sync (set by PI0Policy.prepare_language from
+        # the tokenizer's host output); None = process all tokenizer_max_length rows
+        self.lang_len_hint: int | None = None
 
     def sample_noise(self, shape, device, noise_std=1.0):
         return torch.normal(mean=0.0, std=noise_std, size=shape, dtype=torch.float32, device=device)
@@ -119,6 +122,7 @@ class PI0FlowMatching:
             prefix_ok = lang_masks == (torch.arange(lang_masks.shape[1], device=device)[None, :] < lang_len[:, None])
             same_obs = (img == img[:1]).all() & (state == state[:1]).all()
             prefix_ok, same_obs = bool(prefix_ok.all()), bool(same_obs)
+            hint = int(lang_len.max())  # these checks already synchronise: the exact bound is free here
             if not prefix_ok:
                 raise NotImplementedError("language masks must be right-padded (tokenizer padding_side='right')")
             if not same_obs:
@@ -128,12 +132,14 @@ class PI0FlowMatching:
                                                           lang_len[i:i + 1].contiguous(), state[i].contiguous(),
                                                           noise[i:i + 1].contiguous(), K=1)
                 return out
+        else:
+            hint = self.lang_len_hint
         R, K = self._layout(images, lang_tokens)
         if R > self.engine.cfg.max_rephrases or K > self.engine.cfg.max_samples:
             raise ValueError(f"batch layout R={R}, K={K} exceeds the engine workspace "
                              f"(max_rephrases={self.engine.cfg.max_rephrases}, max_samples={self.engine.cfg.max_samples})")
         return self.engine.pi0_sample(img[0].contiguous(), lang_tokens[::K].contiguous(), lang_len[::K].contiguous(),
-                                      state[0].contiguous(), noise.contiguous(), K=K)
+                                      state[0].contiguous(), noise.contiguous(), K=K, lang_len_max=hint)
 
 
 class _Normalize:
@@ -273,4 +279,5 @@ class PI0Policy:
         tok = self.language_tokenizer.__call__(tasks, padding="max_length", padding_side="right",
                                                max_length=self.config.tokenizer_max_length, return_tensors="pt",
                                                truncation=True)
+        self.model.lang_len_hint = int(tok["attention_mask"].sum(dim=1).max())  # host tensor: no device sync
         return tok["input_ids"].to(device=device), tok["attention_mask"].to(device=device, dtype=torch.bool)

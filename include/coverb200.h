@@ -113,6 +113,12 @@ CVB_API int cvb_pi0_sample(cvb_handle* h, const float* image, const int64_t* lan
                            const int32_t* lang_len, const float* state, const float* noise, int R,
                            int K, float* actions, void* stream);
 
+/* Optional bound on the number of VALID language tokens per prompt for the following cvb_pi0_sample calls (0 = none:
+ * max_lang_len rows are processed).  Right-padded tokens are masked as keys and never read (exact),
+ * so a host that knows its tokenizer output (it produced it) lets the prefix skip them; longer prompts are truncated
+ * to the hint, as the reference truncates at tokenizer_max_length (modeling_pi0.py:389-409). */
+CVB_API int cvb_pi0_set_lang_len_hint(cvb_handle* h, int max_valid_tokens);
+
 /* Profiling hook: re-run one phase (0 vision tower, 1 prefix, 2 denoise loop) eagerly on the inputs staged by
  * the last cvb_pi0_sample call, so a host can time the phases separately with CUDA events. */
 CVB_API int cvb_pi0_run_phase(cvb_handle* h, int phase, int R, int K, void* stream);

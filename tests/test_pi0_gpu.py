@@ -74,3 +74,27 @@ def test_pi0_candidates_of_one_rephrase_share_prefix():
     assert torch.equal(out[0], out[1]) and torch.equal(out[0], out[2])
     assert not torch.equal(out[0], out[3])
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["TINY", "MID"])
+def test_lang_len_hint_is_exact(name):
+    """Skipping the right-padding rows of the prefix (host-known bound on valid tokens) must not change a single bit:
+    padded tokens are masked as keys and their own rows are never read."""
+    d = getattr(O, name)
+    R, K = 3, 2
+    w = O.make_pi0_weights(d, seed=2)
+    inp = O.make_inputs(d, R, K, seed=2)
+    eng = build_pi0_engine(d, w, R, K)
+    args = (inp["image"][0].cuda().contiguous(), inp["tokens"].cuda(), inp["lens"].to(torch.int32).cuda(),
+            inp["state"][0].cuda().contiguous(), inp["noise"].cuda())
+    full = eng.pi0_sample(*args, K=K).cpu()
+    lmax = int(inp["lens"].max())
+    for _ in range(3):  # eager, capture, replay
+        hinted = eng.pi0_sample(*args, K=K, lang_len_max=lmax).cpu()
+        assert torch.equal(hinted, full)
+    # a hint shorter than a prompt truncates it (like the tokenizer's max_length) - results must then differ
+    short = eng.pi0_sample(*args, K=K, lang_len_max=max(1, int(inp["lens"].min()) - 2)).cpu()
+    assert not torch.equal(short, full)
+    again = eng.pi0_sample(*args, K=K, lang_len_max=None).cpu()
+    assert torch.equal(again, full)
+    eng.close()

@@ -70,12 +70,18 @@ class CoverStep:
         # the verifier's image/text side does not depend on the sampled actions: it runs on a second stream,
         # concurrently with the (latency-bound, SM-underfilling) denoise loop of the sampler
         self.overlap_context = True
+        # default: the whole decision is one C-ABI call / one CUDA graph (cvb_cover_step) with the verifier context forked
+        # after the prefix; False = three calls (cvb_pi0_sample, cvb_format_trajectories, cvb_verifier_score)
+        self.fused = True
         self._side = torch.cuda.Stream(device=engine.device)
 
     def sample_and_score(self, x: CoverInputs, select: bool = True):
         """Asynchronous; returns device tensors (actions, traj, scores, group_mean, best_idx, best_score)."""
         e = self.engine
         R = x.lang_tokens.shape[0]
+        if self.fused:
+            return e.cover_step(x.image, x.lang_tokens, x.lang_len, x.state, x.noise, self.K, x.vf_image, x.vf_tokens,
+                                self.p01, self.p99, past=x.past, n_future=self.n_future, lang_len_max=x.lang_len_max)
         if self.overlap_context:
             cur = torch.cuda.current_stream(e.device)
             self._side.wait_stream(cur)

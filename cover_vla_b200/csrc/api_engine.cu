@@ -70,6 +70,7 @@ int cvb_create(const cvb_config* cfg, cvb_handle** out) {
 void cvb_destroy(cvb_handle* h) {
   if (h == nullptr) return;
   h->pi0.graphs.destroy();
+  cvb::cover_destroy(h);
   cvb::verifier_destroy(h);
   for (void* p : h->owned) cudaFree(p);
   delete h;
@@ -176,6 +177,17 @@ int cvb_format_trajectories(const float* actions, int n_cand, int chunk, int act
   for (int i = 0; i < 6; ++i) st.p01[i] = p01_host[i], st.p99[i] = p99_host[i];
   return cvb::format_trajectories((cudaStream_t)stream, actions, n_cand, chunk, action_stride, st, past, num_past,
                                   history, n_future, traj);
+}
+
+int cvb_cover_step(cvb_handle* h, const float* image, const int64_t* lang_tokens, const int32_t* lang_len,
+                   const float* state, const float* noise, int R, int K, const float* vf_image,
+                   const int64_t* vf_text_tokens, const double* p01_host, const double* p99_host, const float* past,
+                   int num_past, int n_future, float* actions, float* traj, float* scores, float* group_mean,
+                   int32_t* best_idx, float* best_score, void* stream) {
+  CVB_REQUIRE(h != nullptr, "null handle");
+  return cvb::cover_step(h, image, lang_tokens, lang_len, state, noise, R, K, vf_image, vf_text_tokens, p01_host,
+                         p99_host, past, num_past, n_future, actions, traj, scores, group_mean, best_idx, best_score,
+                         (cudaStream_t)stream);
 }
 
 int cvb_select(const float* scores, int R, int K, float* group_mean, int32_t* best_idx, float* best_score,

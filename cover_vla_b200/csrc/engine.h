@@ -117,6 +117,16 @@ struct Pi0State {
 
 struct VerifierState;  // engine_verifier.cu
 
+// fused decision (engine_cover.cu): one CUDA graph with a forked branch for the verifier's image/text side
+struct CoverState {
+  GraphCache graphs;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  float* past = nullptr;  // staged copy of the caller's action-history tail [vf_history, 7]
+  double stats[12] = {0};
+  bool stats_set = false;
+};
+
 }  // namespace cvb
 
 struct cvb_handle {
@@ -127,6 +137,7 @@ struct cvb_handle {
   bool finalized = false;
   cvb::Pi0State pi0;
   cvb::VerifierState* vf = nullptr;
+  cvb::CoverState cover;
 
   int n_img() const { return (cfg.vis_image / cfg.vis_patch) * (cfg.vis_image / cfg.vis_patch); }
   int prefix_len() const { return n_img() + cfg.max_lang_len; }
@@ -165,6 +176,23 @@ int verifier_score(cvb_handle* h, const float* image, const int64_t* tokens, con
                    float* scores, float* group_mean, int32_t* best_idx, float* best_score, int recompute_context,
                    cudaStream_t st);
 int verifier_context(cvb_handle* h, const float* image, const int64_t* tokens, cudaStream_t st);
+// building blocks of the fused decision (engine_cover.cu)
+int pi0_stage_inputs(cvb_handle* h, const float* image, const int64_t* tokens, const int32_t* lang_len,
+                     const float* state, const float* noise, int R, int K, cudaStream_t st);
+int pi0_enqueue(cvb_handle* h, cudaStream_t st, int R, int K, int part);  // 0 = vision + prefix, 1 = denoise loop
+float* pi0_actions_buffer(cvb_handle* h);
+int verifier_stage_context_inputs(cvb_handle* h, const float* image, const int64_t* tokens, cudaStream_t st);
+int verifier_enqueue_context(cvb_handle* h, cudaStream_t st);
+int verifier_enqueue_score(cvb_handle* h, cudaStream_t st, int N, int R, int K);
+float* verifier_traj_buffer(cvb_handle* h);
+int verifier_copy_results(cvb_handle* h, int N, int R, float* scores, float* group_mean, int32_t* best_idx,
+                          float* best_score, cudaStream_t st);
+int cover_step(cvb_handle* h, const float* image, const int64_t* lang_tokens, const int32_t* lang_len,
+               const float* state, const float* noise, int R, int K, const float* vf_image, const int64_t* vf_tokens,
+               const double* p01_host, const double* p99_host, const float* past, int num_past, int n_future,
+               float* actions, float* traj, float* scores, float* group_mean, int32_t* best_idx, float* best_score,
+               cudaStream_t st);
+void cover_destroy(cvb_handle* h);
 int64_t verifier_debug_copy(cvb_handle* h, const std::string& name, void* dst, int64_t max_bytes, cudaStream_t st);
 int verifier_set_features(cvb_handle* h, const float* patch, const float* text, cudaStream_t st);
 

@@ -456,16 +456,17 @@ static int run_all(cvb_handle* h, cudaStream_t st, int R, int K) {
   return 0;
 }
 
-int pi0_sample(cvb_handle* h, const float* image, const int64_t* tokens, const int32_t* lang_len,
-               const float* state, const float* noise, int R, int K, float* actions, cudaStream_t st) {
+int pi0_stage_inputs(cvb_handle* h, const float* image, const int64_t* tokens, const int32_t* lang_len,
+                     const float* state, const float* noise, int R, int K, cudaStream_t st) {
   const cvb_config& c = h->cfg;
   Pi0State& s = h->pi0;
   CVB_REQUIRE(h->finalized, "cvb_finalize() has not been called");
   CVB_REQUIRE(c.layers > 0, "this handle was created without the pi0 model (layers == 0)");
   CVB_REQUIRE(R >= 1 && R <= c.max_rephrases, "R out of range (max_rephrases)");
   CVB_REQUIRE(K >= 1 && K <= c.max_samples, "K out of range (max_samples)");
-  const int N = R * K;
-  const size_t act_bytes = (size_t)N * c.chunk_size * c.max_action_dim * sizeof(float);
+  CVB_REQUIRE(image != nullptr && tokens != nullptr && lang_len != nullptr && state != nullptr && noise != nullptr,
+              "null input");
+  const size_t act_bytes = (size_t)R * K * c.chunk_size * c.max_action_dim * sizeof(float);
   CVB_CUDA(cudaMemcpyAsync(s.in_image, image, (size_t)3 * c.vis_image * c.vis_image * sizeof(float),
                            cudaMemcpyDeviceToDevice, st));
   CVB_CUDA(cudaMemcpyAsync(s.in_tokens, tokens, (size_t)R * c.max_lang_len * sizeof(int64_t),
@@ -473,7 +474,25 @@ int pi0_sample(cvb_handle* h, const float* image, const int64_t* tokens, const i
   CVB_CUDA(cudaMemcpyAsync(s.in_lang_len, lang_len, R * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   CVB_CUDA(cudaMemcpyAsync(s.in_state, state, c.max_state_dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
   CVB_CUDA(cudaMemcpyAsync(s.x_t, noise, act_bytes, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
 
+int pi0_enqueue(cvb_handle* h, cudaStream_t st, int R, int K, int part) {
+  if (part == 0) {
+    CVB_TRY(run_vision(h, st));
+    return run_prefix(h, st, R);
+  }
+  return run_denoise(h, st, R, K);
+}
+
+float* pi0_actions_buffer(cvb_handle* h) { return h->pi0.x_t; }
+
+int pi0_sample(cvb_handle* h, const float* image, const int64_t* tokens, const int32_t* lang_len,
+               const float* state, const float* noise, int R, int K, float* actions, cudaStream_t st) {
+  const cvb_config& c = h->cfg;
+  Pi0State& s = h->pi0;
+  CVB_TRY(pi0_stage_inputs(h, image, tokens, lang_len, state, noise, R, K, st));
+  const size_t act_bytes = (size_t)R * K * c.chunk_size * c.max_action_dim * sizeof(float);
   const long key = ((long)h->lang_rows() << 40) | ((long)R << 16) | (long)K;
   CVB_TRY(s.graphs.run(c.use_cuda_graph != 0, key, st, [&](cudaStream_t cs) { return run_all(h, cs, R, K); }));
   CVB_CUDA(cudaMemcpyAsync(actions, s.x_t, act_bytes, cudaMemcpyDeviceToDevice, st));

@@ -503,6 +503,49 @@ int verifier_score(cvb_handle* h, const float* image, const int64_t* tokens, con
   return 0;
 }
 
+int verifier_stage_context_inputs(cvb_handle* h, const float* image, const int64_t* tokens, cudaStream_t st) {
+  const cvb_config& c = h->cfg;
+  CVB_REQUIRE(h->finalized && h->vf != nullptr, "verifier not configured (vf_members == 0?) or not finalized");
+  CVB_REQUIRE(image != nullptr && tokens != nullptr, "image / tokens required");
+  VerifierState& s = *h->vf;
+  CVB_CUDA(cudaMemcpyAsync(s.in_image, image, (size_t)3 * c.vf_image * c.vf_image * sizeof(float),
+                           cudaMemcpyDeviceToDevice, st));
+  CVB_CUDA(cudaMemcpyAsync(s.in_tokens, tokens, c.vf_text_ctx * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int verifier_enqueue_context(cvb_handle* h, cudaStream_t st) {
+  CVB_TRY(run_context(h, st));
+  h->vf->context_valid = true;
+  return 0;
+}
+
+int verifier_enqueue_score(cvb_handle* h, cudaStream_t st, int N, int R, int K) {
+  const cvb_config& c = h->cfg;
+  VerifierState& s = *h->vf;
+  CVB_REQUIRE(N >= 1 && N <= c.max_rephrases * c.max_samples, "N out of range");
+  CVB_REQUIRE(R == 0 || R * K == N, "R*K must equal N");
+  CVB_TRY(run_trajectories(h, st, N));
+  return fuse_score_select(st, s.it, s.act, c.vf_members, N, c.vf_embed, s.scores, R, K, s.gmean, s.bidx, s.bscore,
+                           R > 0 ? 1 : 0);
+}
+
+float* verifier_traj_buffer(cvb_handle* h) { return h->vf->in_traj; }
+
+int verifier_copy_results(cvb_handle* h, int N, int R, float* scores, float* group_mean, int32_t* best_idx,
+                          float* best_score, cudaStream_t st) {
+  VerifierState& s = *h->vf;
+  if (scores != nullptr) CVB_CUDA(cudaMemcpyAsync(scores, s.scores, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (R > 0) {
+    if (group_mean != nullptr)
+      CVB_CUDA(cudaMemcpyAsync(group_mean, s.gmean, R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (best_idx != nullptr) CVB_CUDA(cudaMemcpyAsync(best_idx, s.bidx, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    if (best_score != nullptr)
+      CVB_CUDA(cudaMemcpyAsync(best_score, s.bscore, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
 int verifier_context(cvb_handle* h, const float* image, const int64_t* tokens, cudaStream_t st) {
   const cvb_config& c = h->cfg;
   CVB_REQUIRE(h->finalized && h->vf != nullptr, "verifier not configured (vf_members == 0?) or not finalized");

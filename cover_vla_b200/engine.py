@@ -121,6 +121,8 @@ class Engine:
         L.cvb_verifier_score.argtypes = [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
         L.cvb_verifier_set_features.argtypes = [C.c_void_p] * 4
         L.cvb_verifier_context.argtypes = [C.c_void_p] * 4
+        L.cvb_cover_step.argtypes = ([C.c_void_p] * 6 + [C.c_int, C.c_int] + [C.c_void_p] * 2 +
+                                     [C.POINTER(C.c_double)] * 2 + [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7)
         L.cvb_select.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 
     # ------------------------------------------------------------------ weights
@@ -213,6 +215,38 @@ class Engine:
                                                    N, R, K, _lib.ptr(scores), _lib.ptr(gmean), _lib.ptr(bidx),
                                                    _lib.ptr(bscore), int(recompute_context), _lib.stream_ptr()))
         return scores, gmean, bidx, bscore
+
+    def cover_step(self, image, lang_tokens, lang_len, state, noise, K: int, vf_image, vf_tokens, p01, p99, past=None,
+                   n_future: int | None = None, lang_len_max: int | None = None, select: bool = True):
+        """One whole decision (cvb_cover_step): sample -> format -> score -> select in one graph.  Returns device
+        tensors (actions [N,chunk,A], traj [N,H,7], scores [N], group_mean [R], best_idx i32 [1], best_score [1])."""
+        cfg = self.cfg
+        R = lang_tokens.shape[0]
+        N = R * K
+        assert tuple(noise.shape) == (N, cfg.chunk_size, cfg.max_action_dim) and noise.dtype == torch.float32
+        for t in (image, lang_tokens, lang_len, state, noise, vf_image, vf_tokens):
+            assert t.is_cuda and t.is_contiguous()
+        assert lang_tokens.dtype == torch.int64 and lang_len.dtype == torch.int32 and vf_tokens.dtype == torch.int64
+        num_past = 0 if past is None else int(past.shape[0])
+        if past is not None:
+            assert past.dtype == torch.float32 and past.is_cuda and past.is_contiguous() and past.shape[1] == 7
+        n_future = n_future or cfg.chunk_size
+        actions = torch.empty_like(noise)
+        traj = torch.empty(N, cfg.vf_history, 7, dtype=torch.float32, device=self.device)
+        scores = torch.empty(N, dtype=torch.float32, device=self.device)
+        gmean = torch.empty(R, dtype=torch.float32, device=self.device)
+        bidx = torch.zeros(1, dtype=torch.int32, device=self.device)
+        bscore = torch.zeros(1, dtype=torch.float32, device=self.device)
+        a = (C.c_double * 6)(*p01)
+        b = (C.c_double * 6)(*p99)
+        self.set_lang_len_hint(lang_len_max)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cvb_cover_step(self._h, _lib.ptr(image), _lib.ptr(lang_tokens), _lib.ptr(lang_len),
+                                               _lib.ptr(state), _lib.ptr(noise), R if select else R, K, _lib.ptr(vf_image),
+                                               _lib.ptr(vf_tokens), a, b, _lib.ptr(past), num_past, n_future,
+                                               _lib.ptr(actions), _lib.ptr(traj), _lib.ptr(scores), _lib.ptr(gmean),
+                                               _lib.ptr(bidx), _lib.ptr(bscore), _lib.stream_ptr()))
+        return actions, traj, scores, gmean, bidx, bscore
 
     def verifier_context(self, image, text_tokens):
         """Image/text side only (trunk + image-text heads) on the current stream; pair with

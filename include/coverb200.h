@@ -150,6 +150,18 @@ CVB_API int cvb_verifier_context(cvb_handle* h, const float* image, const int64_
 CVB_API int cvb_format_trajectories(const float* actions, int n_cand, int chunk, int action_stride,
                                     const double* p01_host, const double* p99_host, const float* past,
                                     int num_past, int history, int n_future, float* traj, void* stream);
+/* One whole CoVer decision in one call / one CUDA graph: cvb_pi0_sample -> cvb_format_trajectories ->
+ * cvb_verifier_score for N = R*K candidates (the body of run_simpler_eval_with_openpi.py:322-363 on the device, no host
+ * round trip in between).  The verifier's image/text side is forked onto an internal stream after the prefix and runs
+ * concurrently with the denoise loop.  Arguments as in the three calls it fuses; past f32 [num_past, 7] (may be NULL
+ * when num_past == 0); outputs actions [N, chunk, max_action_dim], traj [N, vf_history, 7], scores [N],
+ * group_mean [R], best_idx, best_score - any output pointer may be NULL. */
+CVB_API int cvb_cover_step(cvb_handle* h, const float* image, const int64_t* lang_tokens, const int32_t* lang_len,
+                           const float* state, const float* noise, int R, int K, const float* vf_image,
+                           const int64_t* vf_text_tokens, const double* p01_host, const double* p99_host,
+                           const float* past, int num_past, int n_future, float* actions, float* traj, float* scores,
+                           float* group_mean, int32_t* best_idx, float* best_score, void* stream);
+
 /* Test hook: inject normalised trunk features (patch f32 [Np, W], text f32 [ctx, W]) and recompute the
  * image-text heads, so the fp32 heads can be checked in isolation from the bf16 trunk. */
 CVB_API int cvb_verifier_set_features(cvb_handle* h, const float* patch, const float* text, void* stream);

@@ -125,3 +125,31 @@ def test_policy_and_ensemble_surfaces():
     assert len(sc) == N and abs(sc["0"] - float(ref_scores[0])) < 5e-3
     policy.engine.close()
     ens.engine.close()
+
+
+@pytest.mark.parametrize("with_past", [True, False])
+def test_fused_cover_step_equals_three_calls(with_past):
+    """cvb_cover_step (one graph, verifier context forked after the prefix) == cvb_pi0_sample + cvb_format_trajectories
+    + cvb_verifier_score, bit for bit, eagerly and on graph replay."""
+    from cover_vla_b200.cover import CoverInputs, CoverStep
+    d, v = O.MID, V.VMID
+    R, K = 3, 2
+    w, vw = O.make_pi0_weights(d, 0), V.make_verifier_weights(v, 0)
+    eng = build_full_engine(d, w, v, vw, R, K)
+    inp = O.make_inputs(d, R, K, seed=9)
+    vin = V.make_inputs(v, 1, seed=9)
+    past = torch.tensor([[0.01, -0.02, 0.0, 0.03, 0.0, -0.05, 1.0]] * 3).cuda() if with_past else None
+    x = CoverInputs(image=inp["image"][0].cuda().contiguous(), lang_tokens=inp["tokens"].cuda(),
+                    lang_len=inp["lens"].to(torch.int32).cuda(), state=inp["state"][0].cuda().contiguous(),
+                    noise=inp["noise"].cuda(), vf_image=vin["image"][0].cuda().contiguous(),
+                    vf_tokens=vin["tokens"][0].cuda(), past=past, lang_len_max=int(inp["lens"].max()))
+    step = CoverStep(eng, K)
+    step.fused = False
+    ref = [t.clone() for t in step.sample_and_score(x)]
+    step.fused = True
+    for _ in range(4):  # eager, capture, replay, replay
+        out = step.sample_and_score(x)
+        torch.cuda.synchronize()
+        for a, b in zip(out, ref):
+            assert torch.equal(a, b)
+    eng.close()

@@ -60,7 +60,8 @@ int cvb_op_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k0, 
   c.kv1_len = kv1_len, c.suffix_mask = suffix_mask;
   c.out = (cvb::bf16*)out, c.o_batch_stride = o_bs, c.o_row_stride = o_rs;
   c.batches = batches, c.heads = heads, c.kv_heads = kv_heads, c.tq = tq, c.head_dim = head_dim, c.scale = scale;
-  c.force_two_pass = force_two_pass;
+  c.force_two_pass = force_two_pass == 1;
+  c.algo = force_two_pass == 2 ? 1 : force_two_pass == 3 ? 2 : 0;
   c.rope = reinterpret_cast<const float2*>(rope_cos_sin);
   return cvb::attention((cudaStream_t)stream, c);
 }

@@ -14,6 +14,7 @@
 namespace cvb {
 
 bool attention_decode_eligible(const AttnCall& c);
+bool attention_group_eligible(const AttnCall& c);
 
 namespace {
 
@@ -399,7 +400,8 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
   AttnCall probe;
   probe.k1 = s.qkv_e, probe.kv1_len = S, probe.kv0_len_dev = s.plen, probe.kv0_max = h->n_img() + h->lang_rows();
   probe.heads = c.heads, probe.kv_heads = 1, probe.tq = S, probe.head_dim = hd;
-  const bool fused_rope = attention_decode_eligible(probe);
+  probe.q_per_kv_batch = K, probe.batches = N;
+  const bool fused_rope = attention_group_eligible(probe) || attention_decode_eligible(probe);
   if (fused_rope) CVB_TRY(rope_table(st, s.rope_timescale, s.plen, R, S, hd / 2, s.rope_tab));
   for (size_t step = 0; step < s.times.size(); ++step) {
     {  // embed_suffix (modeling_pi0.py:598-609), time half of mlp_in folded into time_vec[step]

@@ -55,6 +55,10 @@ struct VerifierState {
   float* bscore = nullptr;
   bool context_valid = false;
   GraphCache ctx_graph, traj_graph;
+  // the ensemble members' trajectory encoders are independent until the fused score: one branch (stream) per member
+  std::vector<cudaStream_t> mstream;
+  std::vector<cudaEvent_t> mevent;
+  cudaEvent_t ev_fork = nullptr;
 };
 
 namespace {
@@ -272,11 +276,18 @@ int verifier_finalize(cvb_handle* h, cudaStream_t st) {
   CVB_TRY(dalloc_t(h, &s.ttok, (size_t)M * E));
   CVB_TRY(dalloc_t(h, &s.it, (size_t)M * E));
   const size_t rows = (size_t)Nm * S;
-  CVB_TRY(dalloc_t(h, &s.tx, rows * E));
-  CVB_TRY(dalloc_t(h, &s.tqkv, rows * 3 * E));
-  CVB_TRY(dalloc_t(h, &s.tatt, rows * E));
-  CVB_TRY(dalloc_t(h, &s.ty, rows * E));
-  CVB_TRY(dalloc_t(h, &s.tff, rows * c.vf_traj_ff));
+  CVB_TRY(dalloc_t(h, &s.tx, rows * E * M));
+  CVB_TRY(dalloc_t(h, &s.tqkv, rows * 3 * E * M));
+  CVB_TRY(dalloc_t(h, &s.tatt, rows * E * M));
+  CVB_TRY(dalloc_t(h, &s.ty, rows * E * M));
+  CVB_TRY(dalloc_t(h, &s.tff, rows * c.vf_traj_ff * M));
+  s.mstream.assign(M, nullptr);
+  s.mevent.assign(M, nullptr);
+  for (int m = 1; m < M; ++m) {
+    CVB_CUDA(cudaStreamCreateWithFlags(&s.mstream[m], cudaStreamNonBlocking));
+    CVB_CUDA(cudaEventCreateWithFlags(&s.mevent[m], cudaEventDisableTiming));
+  }
+  CVB_CUDA(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
   CVB_TRY(dalloc_t(h, &s.act, (size_t)M * Nm * E));
   CVB_TRY(dalloc_t(h, &s.scores, Nm));
   CVB_TRY(dalloc_t(h, &s.gmean, Nm));
@@ -373,6 +384,11 @@ void verifier_destroy(cvb_handle* h) {
   if (h->vf != nullptr) {
     h->vf->ctx_graph.destroy();
     h->vf->traj_graph.destroy();
+    for (cudaStream_t st : h->vf->mstream)
+      if (st) cudaStreamDestroy(st);
+    for (cudaEvent_t e : h->vf->mevent)
+      if (e) cudaEventDestroy(e);
+    if (h->vf->ev_fork) cudaEventDestroy(h->vf->ev_fork);
   }
   delete h->vf;
   h->vf = nullptr;
@@ -447,26 +463,45 @@ static int run_context(cvb_handle* h, cudaStream_t st) {
   return 0;
 }
 
-static int run_trajectories(cvb_handle* h, cudaStream_t st, int N) {
+static int run_member_trajectories(cvb_handle* h, cudaStream_t st, int N, int m) {
   const cvb_config& c = h->cfg;
   VerifierState& s = *h->vf;
-  const int E = c.vf_embed, M = c.vf_members, S = c.vf_history, A = c.vf_action_dim, FF = c.vf_traj_ff;
+  const int E = c.vf_embed, S = c.vf_history, A = c.vf_action_dim, FF = c.vf_traj_ff;
   const int rows = N * S;
-  for (int m = 0; m < M; ++m) {
-    const MemberW& Mw = s.mem[m];
-    CVB_TRY(sg(st, s.in_traj, A, Mw.w_ss, A, rows, E, A, s.tx, E, Mw.b_ss));
-    for (const TrajLayer& T : Mw.traj) {
-      CVB_TRY(sg(st, s.tx, E, T.w_in, E, rows, 3 * E, E, s.tqkv, 3 * E, T.b_in));
-      CVB_TRY(traj_attention(st, s.tqkv, s.in_traj, s.tatt, N, S, E, c.vf_pool_heads, A, -5.0f));
-      CVB_TRY(sg(st, s.tatt, E, T.wo, E, rows, E, E, s.ty, E, T.bo));
-      CVB_TRY(layernorm_f32(st, s.ty, s.tx, T.n1w, T.n1b, s.tx, rows, E, 1e-5f));
-      CVB_TRY(sg(st, s.tx, E, T.w1, E, rows, FF, E, s.tff, FF, T.b1, SACT_RELU));
-      CVB_TRY(sg(st, s.tff, FF, T.w2, FF, rows, E, FF, s.ty, E, T.b2));
-      CVB_TRY(layernorm_f32(st, s.ty, s.tx, T.n2w, T.n2b, s.tx, rows, E, 1e-5f));
-    }
-    CVB_TRY(masked_mean_l2norm(st, s.tx, s.in_traj, s.act + (size_t)m * N * E, N, S, E, A, -5.0f));
+  const size_t cap = (size_t)c.max_rephrases * c.max_samples * S;  // rows of workspace per member
+  float* tx = s.tx + (size_t)m * cap * E;
+  float* tqkv = s.tqkv + (size_t)m * cap * 3 * E;
+  float* tatt = s.tatt + (size_t)m * cap * E;
+  float* ty = s.ty + (size_t)m * cap * E;
+  float* tff = s.tff + (size_t)m * cap * FF;
+  const MemberW& Mw = s.mem[m];
+  CVB_TRY(sg(st, s.in_traj, A, Mw.w_ss, A, rows, E, A, tx, E, Mw.b_ss));
+  for (const TrajLayer& T : Mw.traj) {
+    CVB_TRY(sg(st, tx, E, T.w_in, E, rows, 3 * E, E, tqkv, 3 * E, T.b_in));
+    CVB_TRY(traj_attention(st, tqkv, s.in_traj, tatt, N, S, E, c.vf_pool_heads, A, -5.0f));
+    CVB_TRY(sg(st, tatt, E, T.wo, E, rows, E, E, ty, E, T.bo));
+    CVB_TRY(layernorm_f32(st, ty, tx, T.n1w, T.n1b, tx, rows, E, 1e-5f));
+    CVB_TRY(sg(st, tx, E, T.w1, E, rows, FF, E, tff, FF, T.b1, SACT_RELU));
+    CVB_TRY(sg(st, tff, FF, T.w2, FF, rows, E, FF, ty, E, T.b2));
+    CVB_TRY(layernorm_f32(st, ty, tx, T.n2w, T.n2b, tx, rows, E, 1e-5f));
   }
-  return 0;
+  return masked_mean_l2norm(st, tx, s.in_traj, s.act + (size_t)m * N * E, N, S, E, A, -5.0f);
+}
+
+// One branch per ensemble member (forked from / joined back into `st`; plain parallel graph branches under capture).
+static int run_trajectories(cvb_handle* h, cudaStream_t st, int N) {
+  VerifierState& s = *h->vf;
+  const int M = h->cfg.vf_members;
+  if (M > 1) CVB_CUDA(cudaEventRecord(s.ev_fork, st));
+  int rc = 0;
+  for (int m = 1; m < M; ++m) {
+    CVB_CUDA(cudaStreamWaitEvent(s.mstream[m], s.ev_fork, 0));
+    if (rc == 0) rc = run_member_trajectories(h, s.mstream[m], N, m);
+    CVB_CUDA(cudaEventRecord(s.mevent[m], s.mstream[m]));  // always rejoin so a stream capture can end cleanly
+  }
+  if (rc == 0) rc = run_member_trajectories(h, st, N, 0);
+  for (int m = 1; m < M; ++m) CVB_CUDA(cudaStreamWaitEvent(st, s.mevent[m], 0));
+  return rc;
 }
 
 int verifier_score(cvb_handle* h, const float* image, const int64_t* tokens, const float* traj, int N, int R, int K,

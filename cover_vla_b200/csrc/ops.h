@@ -91,6 +91,7 @@ struct AttnCall {
   // segment 0 (and kv0_len_dev) is NOT written by the kernel launched just before this one: its tiles may be
   // prefetched before the programmatic-dependency wait (the prefix KV cache during the denoise loop)
   int kv0_static = 0;
+  int algo = 0;  // two-segment calls: 0 auto, 1 rephrase-grouped kernel only, 2 cluster decode kernel only
 };
 int attention(cudaStream_t st, const AttnCall& c);
 

@@ -125,20 +125,46 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const DecodePa
     }
     cp_async_commit();
     if (p.kv0_static) pdl_wait();
-    // Q rows (+ RoPE): work item = (row, 8-wide chunk of the first half)
+    // Q rows (+ RoPE): work item = (row, 8-wide chunk of the first half).  All global loads of a batch of items are
+    // issued before any is consumed (the items are independent: one exposed L2 round trip per batch, not per item).
     constexpr int CH2 = HALF / 8;
-    for (int idx = threadIdx.x; idx < BQ * CH2; idx += ATT_THREADS) {
-      const int r = idx / CH2, c = (idx % CH2) * 8;
-      uint4 v1 = make_uint4(0, 0, 0, 0), v2 = v1;
-      if (r < rows_total) {
-        const int hl = r / p.tq, t = r % p.tq;
-        const bf16* qp = p.q + b * p.q_bs + t * p.q_rs + (kvh * G + hl) * HD + c;
-        v1 = *reinterpret_cast<const uint4*>(qp);
-        v2 = *reinterpret_cast<const uint4*>(qp + HALF);
-        if (rope != nullptr) rope8(v1, v2, rope + t * HALF + c);
+    constexpr int QB = 4;
+    const int q_items = rows_total * CH2;
+    for (int base = 0; base < q_items; base += QB * ATT_THREADS) {
+      uint4 v1[QB], v2[QB];
+      float4 cs[QB][4];
+#pragma unroll
+      for (int u = 0; u < QB; ++u) {
+        const int idx = base + u * ATT_THREADS + threadIdx.x;
+        if (idx < q_items) {
+          const int r = idx / CH2, c = (idx % CH2) * 8;
+          const int hl = r / p.tq, t = r % p.tq;
+          const bf16* qp = p.q + b * p.q_bs + t * p.q_rs + (kvh * G + hl) * HD + c;
+          v1[u] = *reinterpret_cast<const uint4*>(qp);
+          v2[u] = *reinterpret_cast<const uint4*>(qp + HALF);
+          if (rope != nullptr) {
+            const float4* tp = reinterpret_cast<const float4*>(rope + t * HALF + c);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cs[u][e] = tp[e];
+          }
+        }
       }
-      *reinterpret_cast<uint4*>(Qs + r * LDS + c) = v1;
-      *reinterpret_cast<uint4*>(Qs + r * LDS + HALF + c) = v2;
+#pragma unroll
+      for (int u = 0; u < QB; ++u) {
+        const int idx = base + u * ATT_THREADS + threadIdx.x;
+        if (idx < q_items) {
+          const int r = idx / CH2, c = (idx % CH2) * 8;
+          if (rope != nullptr) rope8(v1[u], v2[u], reinterpret_cast<const float2*>(cs[u]));
+          *reinterpret_cast<uint4*>(Qs + r * LDS + c) = v1[u];
+          *reinterpret_cast<uint4*>(Qs + r * LDS + HALF + c) = v2[u];
+        }
+      }
+    }
+    // padding rows of the 64-row tile
+    for (int idx = q_items + threadIdx.x; idx < BQ * CH2; idx += ATT_THREADS) {
+      const int r = idx / CH2, c = (idx % CH2) * 8;
+      *reinterpret_cast<uint4*>(Qs + r * LDS + c) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(Qs + r * LDS + HALF + c) = make_uint4(0, 0, 0, 0);
     }
     cp_async_wait<1>();  // this thread's K chunks have landed; the suffix rows it overwrites are its own or ordered below
     __syncthreads();

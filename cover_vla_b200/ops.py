@@ -39,7 +39,7 @@ def gemm_bf16(a, w, *, epilogue=EPI_STORE, bias=None, resid=None, out=None, n_ou
 
 
 def attention(q, k0, v0, *, heads, kv_heads, head_dim, kv0_len=None, kv0_len_dev=None, q_per_kv_batch=1,
-              k1=None, v1=None, suffix_mask=False, scale=None, force_two_pass=False, rope=None):
+              k1=None, v1=None, suffix_mask=False, scale=None, force_two_pass=False, rope=None, algo=0):
     """q [B, Tq, heads*hd]; k0/v0 [Bkv, T0, kv_heads*hd]; optional k1/v1 [B, T1, kv_heads*hd] (bf16, CUDA)."""
     lib = _lib.load()
     B, Tq, _ = q.shape
@@ -55,6 +55,6 @@ def attention(q, k0, v0, *, heads, kv_heads, head_dim, kv0_len=None, kv0_len_dev
         _lib.ptr(kv0_len_dev), int(kv0_len if kv0_len is not None else T0), T0, q_per_kv_batch,
         _lib.ptr(k1), _lib.ptr(v1), k1.stride(0) if k1 is not None else 0, k1.stride(1) if k1 is not None else 0,
         k1.shape[1] if k1 is not None else 0, int(suffix_mask), _lib.ptr(out), out.stride(0), out.stride(1),
-        B, heads, kv_heads, Tq, head_dim, scale, int(force_two_pass), _lib.ptr(rope), _lib.stream_ptr())
+        B, heads, kv_heads, Tq, head_dim, scale, (int(algo) + 1 if algo else int(force_two_pass)), _lib.ptr(rope), _lib.stream_ptr())
     _lib.check(rc)
     return out

@@ -76,8 +76,10 @@ def _rope(x, pos, hd):
 
 @pytest.mark.parametrize("R,K,S,P,heads,hd,lens", [(3, 4, 5, 328, 8, 256, [270, 328, 300]), (2, 3, 5, 32, 2, 64, [20, 32]),
                                                     (2, 2, 8, 500, 8, 128, [130, 499]), (1, 5, 5, 328, 8, 256, [61])])
-def test_cluster_decode_attention_with_fused_rope(R, K, S, P, heads, hd, lens):
-    """Cluster split-KV kernel: RoPE on q / suffix keys fused into staging, exact softmax over DSMEM statistics."""
+@pytest.mark.parametrize("algo", [1, 2])
+def test_denoise_attention_with_fused_rope(R, K, S, P, heads, hd, lens, algo):
+    """Rephrase-grouped kernel (algo 1) and cluster split-KV kernel (algo 2): RoPE on q / suffix keys fused into
+    staging, exact softmax (logits parked in smem / statistics exchanged over DSMEM)."""
     from cover_vla_b200 import ops
     torch.manual_seed(11)
     N = R * K
@@ -93,9 +95,9 @@ def test_cluster_decode_attention_with_fused_rope(R, K, S, P, heads, hd, lens):
     rad = pos[..., None].float() / ts
     tab = torch.stack([torch.cos(rad), torch.sin(rad)], dim=-1).contiguous()   # [R, S, half, 2]
     out = ops.attention(q, k0, v0, heads=heads, kv_heads=1, head_dim=hd, kv0_len_dev=lens_t, q_per_kv_batch=K,
-                        k1=k1, v1=v1, suffix_mask=True, rope=tab)
+                        k1=k1, v1=v1, suffix_mask=True, rope=tab, algo=algo)
     out2 = ops.attention(q, k0, v0, heads=heads, kv_heads=1, head_dim=hd, kv0_len_dev=lens_t, q_per_kv_batch=K,
-                         k1=k1, v1=v1, suffix_mask=True, rope=tab)
+                         k1=k1, v1=v1, suffix_mask=True, rope=tab, algo=algo)
     assert torch.equal(out, out2)  # rank-ordered DSMEM reduction: deterministic
     posn = pos.repeat_interleave(K, dim=0)                                     # [N, S]
     qr = _rope(q.view(N, S, heads, hd), posn, hd).view(N, S, heads * hd)

@@ -19,9 +19,12 @@ kw = dict(heads=heads, kv_heads=1, head_dim=hd, kv0_len_dev=lens, q_per_kv_batch
 for _ in range(3):
     ops.attention(q, k0, v0, **kw)
 torch.cuda.synchronize()
-ts = torch.zeros(4096 * 8, dtype=torch.int64, device="cuda")
-lib.cvb_debug_set_timestamps(C.c_void_p(ts.data_ptr()))
-for rep in range(2):
+import os
+if os.environ.get("TS"):
+  kw["algo"] = 2
+  ts = torch.zeros(4096 * 8, dtype=torch.int64, device="cuda")
+  lib.cvb_debug_set_timestamps(C.c_void_p(ts.data_ptr()))
+  for rep in range(2):
     ts.zero_()
     ops.attention(q, k0, v0, **kw)
     torch.cuda.synchronize()
@@ -33,12 +36,15 @@ for rep in range(2):
     for i, n in enumerate(["start", "staged", "qk+stats", "bar1", "pv+sent", "bar2", "final"]):
         c = rel[:, i]
         print(f"  {n:9s} {c.min():7.2f} {c.median():7.2f} {c.max():7.2f}")
-lib.cvb_debug_set_timestamps(C.c_void_p(0))
-e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-g = torch.cuda.CUDAGraph()
-with torch.cuda.graph(g):
-    for _ in range(20):
-        ops.attention(q, k0, v0, **kw)
-g.replay(); torch.cuda.synchronize()
-e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
-print("graph avg us per launch:", e0.elapsed_time(e1) / 20 * 1e3)
+  lib.cvb_debug_set_timestamps(C.c_void_p(0))
+for algo in (1, 2):
+  kw["algo"] = algo
+  e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+  g = torch.cuda.CUDAGraph()
+  with torch.cuda.graph(g):
+      for _ in range(20):
+          ops.attention(q, k0, v0, **kw)
+  g.replay(); torch.cuda.synchronize()
+  e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+  print("algo", algo, "graph avg us per launch:", e0.elapsed_time(e1) / 20 * 1e3)
+  

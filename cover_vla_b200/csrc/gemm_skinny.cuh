@@ -101,6 +101,26 @@ __device__ __forceinline__ unsigned long long gtimer() {
     if (g.ts != nullptr && threadIdx.x == 64 + 128) g.ts[blockIdx.x * 8 + (i)] = gtimer(); \
   } while (0)
 
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// shared::cta -> shared::cluster bulk copy (copy engine, asynchronous); completion = complete_tx on the DESTINATION's mbarrier
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
+                                                  uint32_t mbar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   dst_cluster_addr),
+               "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// Shared-memory map (after 1024-byte alignment):
+//   [0, body)            TMA ring (stages x (16 KB weights + Mp x 128 B activations)); once this CTA's MMAs have retired
+//                        the same bytes hold `stage_out`: its fp32 partial tile as [Mp/4 column quads][128 features][4]
+//   [body, body + recv)  partial slices received from the S-1 peers: [slot][slice/4][128][4]
+//   barriers
 template <int EPI>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA,
@@ -110,14 +130,15 @@ gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_consta
                                              ~static_cast<uintptr_t>(1023));
   const uint32_t a_bytes = static_cast<uint32_t>(g.Mp) * 128u;
   const uint32_t stage_bytes = SK_W_BYTES + a_bytes;
-  const uint32_t recv_bytes = static_cast<uint32_t>(g.S) * g.slice * 512u;
   const uint32_t ring_bytes = static_cast<uint32_t>(g.stages) * stage_bytes;
-  const uint32_t bar_off = (max(ring_bytes, recv_bytes) + 15u) & ~15u;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + bar_off);
+  const uint32_t body = (max(ring_bytes, static_cast<uint32_t>(g.Mp) * 512u) + 1023u) & ~1023u;
+  const uint32_t recv_bytes = static_cast<uint32_t>(g.S - 1) * g.slice * 512u;
+  uint8_t* recv = smem + body;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(recv + recv_bytes);
   uint64_t* empty_bar = full_bar + g.stages;
   uint64_t* tfull_bar = empty_bar + g.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
-  float* recv = reinterpret_cast<float*>(smem);  // [S][slice][128], aliases the ring once every MMA has retired
+  uint64_t* recv_bar = tfull_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(recv_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -127,6 +148,8 @@ gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   const int kb_total = (g.K + 63) / 64;
   const int kb0 = rank * g.kbs;
   const int nkb = max(0, min(kb0 + g.kbs, kb_total) - kb0);
+  const int s_act = (kb_total + g.kbs - 1) / g.kbs;  // splits that own k-blocks (a prefix of the ranks)
+  const int my_cols = max(0, min(g.slice, g.Mp - rank * g.slice));
   SK_TS(0);
 
   if (warp == 0 && lane == 0) {
@@ -140,8 +163,12 @@ gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         mbar_init(&empty_bar[s], 1);
       }
       mbar_init(tfull_bar, 1);
+      mbar_init(recv_bar, 1);
       fence_barrier_init();
       fence_proxy_async();
+      // bytes this CTA will receive: its column slice from every OTHER split that owns k-blocks
+      const int senders = s_act - (rank < s_act ? 1 : 0);
+      mbar_arrive_expect_tx(recv_bar, static_cast<uint32_t>(senders) * my_cols * 512u);
     }
     __syncwarp();
     tmem_alloc(tmem_slot, g.tmem_cols);
@@ -151,6 +178,8 @@ gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // every CTA's recv_bar is initialised before any peer may complete_tx on it (waited on just before the sends)
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   SK_TS(1);
 
   pdl_launch();
@@ -168,16 +197,12 @@ gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         uint8_t* sw = smem + stage * stage_bytes;
         if (i < pre) {
           tma_load_2d_hint(sw + SK_W_BYTES, &tmA, &full_bar[stage], (kb0 + i) * 64, 0, kEvictLast);
-          if (++stage == static_cast<uint32_t>(g.stages)) {
-            stage = 0;
-            phase ^= 1;
-          }
-          continue;
+        } else {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+          tma_load_2d_hint(sw, &tmW, &full_bar[stage], (kb0 + i) * 64, tile * 128, kEvictFirst);
+          tma_load_2d_hint(sw + SK_W_BYTES, &tmA, &full_bar[stage], (kb0 + i) * 64, 0, kEvictLast);
         }
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-        tma_load_2d_hint(sw, &tmW, &full_bar[stage], (kb0 + i) * 64, tile * 128, kEvictFirst);
-        tma_load_2d_hint(sw + SK_W_BYTES, &tmA, &full_bar[stage], (kb0 + i) * 64, 0, kEvictLast);
         if (++stage == static_cast<uint32_t>(g.stages)) {
           stage = 0;
           phase ^= 1;
@@ -209,67 +234,70 @@ gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   } else {
     pdl_wait();  // residual reads / C writes must not overtake the preceding kernel
     if (nkb > 0) {
-      mbar_wait(tfull_bar, 0);
+      mbar_wait(tfull_bar, 0);  // this CTA's MMAs have retired: the ring is dead and becomes stage_out
       tc_fence_after();
     }
     SK_TS(2);
   }
-
-  // every MMA of every CTA in the cluster has retired -> the rings are dead, recv may be written remotely
-  cluster_sync_relaxed();
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   SK_TS(3);
 
-  // recv layout: [source rank][column quad c/4][128 features][4 columns] fp32, so a thread ships 4 activation rows of
-  // its feature with one 16-byte remote store and a warp covers 512 contiguous bytes
   const int half = (warp - 2) >> 2;  // which of the two epilogue warps of this lane quarter
-  if (warp >= 2 && nkb > 0) {
-    const int q = warp & 3;
-    const int L = q * 32 + lane;  // feature row inside the weight tile
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t my_base = smem_u32(recv) + (static_cast<uint32_t>(rank) * g.slice * 128u + L * 4u) * 4u;
-    const int squads = g.slice >> 2;
-    for (int c0 = half * 32; c0 < g.Mp; c0 += 64) {
-      uint32_t r[32];
-      const bool wide = c0 + 32 <= g.Mp;  // Mp is a multiple of 16: the last chunk may be 16 columns
-      if (wide) {
-        tmem_ld_x32(taddr + c0, r);
-      } else {
-        uint32_t r16[16];
-        tmem_ld_x16(taddr + c0, r16);
+  const uint32_t so_base = smem_u32(smem);
+  const uint32_t rv_base = smem_u32(recv);
+  const int squads = g.slice >> 2;
+  if (warp >= 2) {
+    if (nkb > 0) {
+      // ---- TMEM -> registers -> stage_out[quad][feature][4]
+      const int q = warp & 3;
+      const int L = q * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      for (int c0 = half * 32; c0 < g.Mp; c0 += 64) {
+        uint32_t r[32];
+        const bool wide = c0 + 32 <= g.Mp;  // Mp is a multiple of 16: the last chunk may be 16 columns
+        if (wide) {
+          tmem_ld_x32(taddr + c0, r);
+        } else {
+          uint32_t r16[16];
+          tmem_ld_x16(taddr + c0, r16);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] = r16[i];
-      }
-      tmem_wait_ld();
-      int quad = c0 >> 2;
-      int j = quad / squads;
-      int off = quad - j * squads;
-      uint32_t dst = mapa_shared(my_base, j);
-#pragma unroll
-      for (int v = 0; v < 8; ++v) {
-        if (v < 4 || wide) {
-          st_cluster_v4(dst + static_cast<uint32_t>(off) * 2048u, r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
-          if (++off == squads) {
-            off = 0;
-            ++j;
-            dst = mapa_shared(my_base, j < S ? j : 0);
-          }
+          for (int i = 0; i < 16; ++i) r[i] = r16[i];
         }
+        tmem_wait_ld();
+        const uint32_t dst = so_base + (static_cast<uint32_t>(c0 >> 2) * 128u + L) * 16u;
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+          if (v < 4 || wide) sts_v4(dst + v * 2048u, r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+      }
+      tc_fence_before();
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the copy engine
+    }
+    named_bar_sync(1, SK_THREADS - 64);
+    if (nkb > 0 && warp == 2 && lane == 0) {
+      // ---- ship every peer its column slice of my partial tile (copy engine; lands with complete_tx on the peer)
+      const int slot = rank;  // my slot in peer j: sources ordered by rank, the peer itself skipped
+      for (int j = 0; j < S; ++j) {
+        const int cols = max(0, min(g.slice, g.Mp - j * g.slice));
+        if (j == rank || cols == 0) continue;
+        const uint32_t dst = mapa_shared(rv_base + static_cast<uint32_t>((slot > j ? slot - 1 : slot) * squads) * 2048u, j);
+        bulk_copy_to_peer(dst, so_base + static_cast<uint32_t>(j * squads) * 2048u, static_cast<uint32_t>(cols) * 512u,
+                          mapa_shared(smem_u32(recv_bar), j));
       }
     }
-    tc_fence_before();
-  }
+    SK_TS(4);
+    mbar_wait(recv_bar, 0);
+    SK_TS(5);
 
-  SK_TS(4);
-  cluster_sync_all();  // partial sums are visible in their owners' shared memory
-  SK_TS(5);
-
-  if (warp >= 2) {
+    // ---- final: sum the partial slices in rank order, fused epilogue, store
     const int e = (warp & 3) * 32 + lane;  // feature inside the tile, 0..127
     const int c_begin = rank * g.slice;
     const int c_end = min(min(c_begin + g.slice, g.Mp), g.M);
-    const int squads = g.slice >> 2;
-    const int s_act = (kb_total + g.kbs - 1) / g.kbs;  // splits that own k-blocks (a prefix of the ranks)
-    const uint32_t rbase = smem_u32(recv);
+    // address of source s's copy of (my quad `quad`, feature f)
+    auto src_addr = [&](int s, int quad, int f) -> uint32_t {
+      if (s == rank) return so_base + static_cast<uint32_t>((rank * squads + quad) * 128 + f) * 16u;
+      const int slot = s > rank ? s - 1 : s;
+      return rv_base + static_cast<uint32_t>((slot * squads + quad) * 128 + f) * 16u;
+    };
     if constexpr (EPI == EPI_GEGLU64) {
       // lanes 0..63 of the tile hold gate features, 64..127 the matching up features
       const int fl = e & 63;
@@ -280,8 +308,7 @@ gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           const int quad = (m0 - c_begin) >> 2;
           float4 gt = make_float4(0.f, 0.f, 0.f, 0.f), up = gt;
           for (int s = 0; s < s_act; ++s) {
-            const uint32_t a0 = rbase + static_cast<uint32_t>((s * squads + quad) * 128 + fl) * 16u;
-            const float4 a = lds_f4(a0), b = lds_f4(a0 + 64u * 16u);
+            const float4 a = lds_f4(src_addr(s, quad, fl)), b = lds_f4(src_addr(s, quad, fl + 64));
             gt.x += a.x, gt.y += a.y, gt.z += a.z, gt.w += a.w;
             up.x += b.x, up.y += b.y, up.z += b.z, up.w += b.w;
           }
@@ -302,14 +329,8 @@ gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         const float b = load_bias(g.bias, g.bias_is_f32, n);
         for (int m0 = c_begin + 4 * half; m0 < c_end; m0 += 8) {
           const int quad = (m0 - c_begin) >> 2;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int s = 0; s < s_act; ++s) {
-            const float4 a = lds_f4(rbase + static_cast<uint32_t>((s * squads + quad) * 128 + e) * 16u);
-            acc.x += a.x, acc.y += a.y, acc.z += a.z, acc.w += a.w;
-          }
-          const float av[4] = {acc.x, acc.y, acc.z, acc.w};
           float rr[4] = {0.f, 0.f, 0.f, 0.f};
-          if constexpr (EPI == EPI_RESID) {
+          if constexpr (EPI == EPI_RESID) {  // issue the residual loads before the smem reduction
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               if (m0 + i < c_end) {
@@ -319,6 +340,12 @@ gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_consta
               }
             }
           }
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int s = 0; s < s_act; ++s) {
+            const float4 a = lds_f4(src_addr(s, quad, e));
+            acc.x += a.x, acc.y += a.y, acc.z += a.z, acc.w += a.w;
+          }
+          const float av[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int m = m0 + i;
@@ -345,6 +372,9 @@ gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_base, g.tmem_cols);
   }
+  // nobody may exit while a peer's copy engine could still be reading its stage_out: every CTA got here only after all
+  // bytes addressed to it (ours included) have landed
+  cluster_sync_relaxed();
 }
 
 }  // namespace cvb

@@ -14,7 +14,7 @@ unsigned long long* g_skinny_ts = nullptr;  // diagnostics: cvb_debug_set_timest
 
 namespace {
 
-constexpr int kSmemBudget = 200 * 1024;  // ring / receive buffer (barriers + alignment slack come on top)
+constexpr int kSmemBudget = 222 * 1024;  // ring (= staging) + receive buffers (barriers + alignment slack come on top)
 
 template <int EPI>
 int launch_skinny(cudaStream_t st, const GemmCall& c, const SkinnyArgs& g, int n_tiles) {
@@ -22,9 +22,9 @@ int launch_skinny(cudaStream_t st, const GemmCall& c, const SkinnyArgs& g, int n
   CVB_TRY(get_tmap_cached(c.W, c.N, c.K, c.ldw, 128, &tmW));
   CVB_TRY(get_tmap_cached(c.A, c.M, c.K, c.lda, g.Mp, &tmA));
   const uint32_t stage_bytes = SK_W_BYTES + g.Mp * 128;
-  const uint32_t recv_bytes = (uint32_t)g.S * g.slice * 512u;
-  const uint32_t body = std::max<uint32_t>(g.stages * stage_bytes, recv_bytes);
-  const int smem = 1024 + ((body + 15) & ~15u) + (2 * g.stages + 1) * 8 + 16;
+  const uint32_t recv_bytes = (uint32_t)(g.S - 1) * g.slice * 512u;
+  const uint32_t body = (std::max<uint32_t>(g.stages * stage_bytes, g.Mp * 512u) + 1023u) & ~1023u;
+  const int smem = 1024 + body + recv_bytes + (2 * g.stages + 2) * 8 + 16;
   auto kern = gemm_skinny_tcgen05<EPI>;
   static int attr_smem = 0;
   static bool nonportable = false;
@@ -43,12 +43,14 @@ int launch_skinny(cudaStream_t st, const GemmCall& c, const SkinnyArgs& g, int n
 
 }  // namespace
 
-// Auto policy (measured, tools/skinny_bench.py): the cluster split-K kernel wins where the general kernel has few
-// tiles AND a long K walk (o_proj / down / fc2: N <= 1152, K >= 2048); elsewhere its DSMEM reduction costs more than it saves.
+// Auto policy (measured, tools/skinny_bench.py, profiles/r1_skinny_gemm.md): the split-K reduction moves
+// (S-1) x M x N x 4 bytes over the SM-to-SM network, which sustains only ~2.4 TB/s in aggregate, so the cluster kernel
+// wins only where the general kernel has few tiles AND a very long K walk (expert down-projection 4096 -> 1024: 18.0 ->
+// 12.8 us; text-tower fc2 at M = 64: 17.7 -> 6.5 us); elsewhere the general kernel with PDL weight prefetch is as fast.
 bool skinny_eligible(const GemmCall& c) {
-  if (c.M > 256 || c.m_dev != nullptr || c.epi == EPI_GEGLU) return false;
+  if (c.M > 208 || c.m_dev != nullptr || c.epi == EPI_GEGLU) return false;
   const int tiles64 = ((c.M + 127) / 128) * ((c.N + 63) / 64);
-  return tiles64 <= 40 && c.K >= 2048;
+  return tiles64 <= 40 && c.K >= 4096;
 }
 
 int gemm_skinny(cudaStream_t st, const GemmCall& c, int force_split) {
@@ -68,20 +70,29 @@ int gemm_skinny(cudaStream_t st, const GemmCall& c, int force_split) {
     S = (128 + n_tiles / 2) / n_tiles;
     if (S < 1) S = 1;
     if (S > 8) S = 8;
+    if (S > 6 && g.Mp > 128) S = 6;  // measured: beyond 6 the reduction traffic outgrows the shorter K walk
   }
   if (S > 16) S = 16;
   if (S > kb_total) S = kb_total;
-  g.kbs = (kb_total + S - 1) / S;
-  S = (kb_total + g.kbs - 1) / g.kbs;  // drop splits that would own no k-block
-  g.S = S;
-  g.slice = ((g.Mp + S - 1) / S + 3) / 4 * 4;
   const int stage_bytes = SK_W_BYTES + g.Mp * 128;
-  int stages = kSmemBudget / stage_bytes;
-  if (stages > g.kbs) stages = g.kbs;
-  if (stages > 8) stages = 8;
-  if (stages < 1) stages = 1;
-  g.stages = stages;
-  CVB_REQUIRE((long)g.S * g.slice * 512 <= kSmemBudget, "split-K receive buffer does not fit shared memory");
+  // the staging tile (Mp x 512 B, aliased with the TMA ring) and the S-1 received slices must fit shared memory:
+  // take the largest feasible split <= the requested one
+  for (;; --S) {
+    g.kbs = (kb_total + S - 1) / S;
+    const int s_eff = (kb_total + g.kbs - 1) / g.kbs;  // drop splits that would own no k-block
+    g.S = s_eff;
+    g.slice = ((g.Mp + s_eff - 1) / s_eff + 3) / 4 * 4;
+    const long recv_bytes = (long)(s_eff - 1) * g.slice * 512;
+    if (recv_bytes + std::max(stage_bytes, g.Mp * 512) + 2048 <= kSmemBudget) {
+      int stages = (int)((kSmemBudget - recv_bytes) / stage_bytes);
+      if (stages > g.kbs) stages = g.kbs;
+      if (stages > 8) stages = 8;
+      if (stages < 1) stages = 1;
+      g.stages = stages;
+      break;
+    }
+    CVB_REQUIRE(S > 1, "skinny GEMM staging buffers do not fit shared memory");
+  }
   g.ts = g_skinny_ts;
   g.tmem_cols = g.Mp <= 32 ? 32 : g.Mp <= 64 ? 64 : g.Mp <= 128 ? 128 : 256;
   switch (c.epi) {

@@ -118,7 +118,7 @@ def run_gpu(args):
     import torch.distributed as dist
     from cover_vla_b200 import _lib, synthetic as S
     from cover_vla_b200 import build as cvb_build
-    from cover_vla_b200.cover import CoverInputs, CoverStep
+    from cover_vla_b200.cover import CoverInputs, CoverStep, ShardedCoverStep, rephrase_shard
     from cover_vla_b200 import ops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -137,16 +137,30 @@ def run_gpu(args):
 
     R, K = args.rephrases, args.samples
     N = R * K
+    sharded = args.mode == "sharded"
+    if sharded and world > R:
+        raise SystemExit("--mode sharded needs at least one rephrase per rank")
     d, v = S.FULL, S.VFULL
     t0 = time.time()
     w = S.make_pi0_weights(d, seed=0)
     vw = S.make_verifier_weights(v, seed=0)
-    eng = S.build_engine(d, w, v, vw, R, K, device=device)
+    if sharded:
+        a_, b_ = rephrase_shard(R, world, rank)
+        R_loc = b_ - a_
+        R_max = max(rephrase_shard(R, world, r)[1] - rephrase_shard(R, world, r)[0] for r in range(world))
+    else:
+        R_loc = R_max = R
+    eng = S.build_engine(d, w, v, vw, R_max, K, device=device)
+    del w, vw
     t_build = time.time() - t0
-    host, x, lmax = make_device_inputs(S, d, v, R, K, seed=100 + rank, device=device)
+    # episode mode: every rank has its own observation; sharded mode: all ranks see the SAME observation
+    host, x, lmax = make_device_inputs(S, d, v, R, K, seed=100 + (0 if sharded else rank), device=device)
     step = CoverStep(eng, K)
+    sstep = ShardedCoverStep(eng, K) if sharded and world > 1 else None
 
     def one_step():
+        if sstep is not None:
+            return sstep(x)
         return step.sample_and_score(x)
 
     def barrier():
@@ -154,24 +168,18 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (first calls run eagerly, then the CUDA graph is captured)
-    for _ in range(max(3, args.warmup)):
+    # ---- warm-up: the first call of a shape runs every kernel eagerly (this is where the launches of one decision are
+    # counted), the second is captured into the CUDA graph, later ones replay it
+    l0 = lib.cvb_launch_count()
+    out = one_step()
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.cvb_launch_count() - l0)
+    for _ in range(max(3, args.warmup) - 1):
         out = one_step()
     torch.cuda.synchronize()
-    l0 = lib.cvb_launch_count()
-    eng_eager = None  # launches per step = what one eager pass enqueues (graph replay enqueues the same kernels)
-    # count by replaying the phases eagerly once
-    eng.pi0_run_phase(0, R, K)
-    eng.pi0_run_phase(1, R, K)
-    eng.pi0_run_phase(2, R, K)
-    pi0_launches = lib.cvb_launch_count() - l0
-    l1 = lib.cvb_launch_count()
-    one_step()
-    torch.cuda.synchronize()
-    other_launches = lib.cvb_launch_count() - l1  # format + verifier (eager) [+ 0 for the replayed pi0 graph]
-    launches_per_step = int(pi0_launches + other_launches)
+    traj0 = out[1] if sstep is None else step.sample_and_score(sstep_inputs(x, K, world, rank))[1]
 
-    # ---- timed region: K steps, device-resident inputs, CUDA events, max over ranks
+    # ---- timed region: `steps` decisions, device-resident inputs, CUDA events, max over ranks
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
@@ -189,11 +197,17 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = N * world / (ms_per_step / 1e3)
+    cands_per_step = N if sharded else N * world
+    value = cands_per_step / (ms_per_step / 1e3)
 
     # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
     def e2e_step():
         xin = CoverInputs(**{k: t.to(device, non_blocking=True) for k, t in host.items()}, lang_len_max=lmax)
+        if sstep is not None:
+            scores, actions, gmean, idx, score = sstep(xin)
+            winner = actions.index_select(0, idx.to(torch.int64).reshape(1))[0]
+            packed = torch.cat([idx.to(torch.float32).reshape(1), score.reshape(1), winner.reshape(-1)]).cpu()
+            return int(packed[0]), float(packed[1]), packed[2:].reshape(-1, 7)
         return step(xin)  # returns python (idx, score, winner actions): includes the D2H read
 
     for _ in range(3):
@@ -206,19 +220,22 @@ def run_gpu(args):
         t_e2e.append((time.perf_counter() - t1) * 1e3)
     barrier()
     e2e_ms = sum(t_e2e) / len(t_e2e)
+    e2e_p50 = statistics.median(t_e2e)
     if world > 1:
-        t = torch.tensor([e2e_ms], device=device, dtype=torch.float64)
+        t = torch.tensor([e2e_ms, e2e_p50], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+        e2e_ms, e2e_p50 = float(t[0].item()), float(t[1].item())
     h2d = sum(t.numel() * t.element_size() for t in host.values())
     d2h = (2 + d.chunk_size * 7) * 4
 
     line = None
     if rank == 0:
         peaks, peak_src = _peaks()
-        # ---- phase breakdown (eager, CUDA events) and the roofline of the dominant kernel
-        def ev_ms(fn, iters=3):
-            fn()
+
+        # ---- phase breakdown (CUDA events) and the roofline of the dominant kernel
+        def ev_ms(fn, iters=5, warm=3):
+            for _ in range(warm):
+                fn()
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(True), torch.cuda.Event(True)
             a.record()
@@ -227,15 +244,16 @@ def run_gpu(args):
             b.record()
             torch.cuda.synchronize()
             return a.elapsed_time(b) / iters
-        phases = {nm: ev_ms(lambda p=p: eng.pi0_run_phase(p, R, K)) for p, nm in enumerate(["vision", "prefix", "denoise"])}
-        traj = out[1]
-        phases["verifier"] = ev_ms(lambda: eng.verifier_score(x.vf_image, x.vf_tokens, traj, R, K))
+        phases = {nm: ev_ms(lambda p=p: eng.pi0_run_phase(p, R_loc, K)) for p, nm in enumerate(["vision", "prefix", "denoise"])}
+        phases["verifier_context"] = ev_ms(lambda: eng.verifier_context(x.vf_image, x.vf_tokens))
+        phases["verifier_trajectories_select"] = ev_ms(lambda: eng.verifier_score(None, None, traj0, R_loc, K, recompute_context=False))
         fl = algorithmic_flops(R, K)
         total_flops = sum(fl.values())
 
-        # dominant kernel: the prefix gate/up GeGLU GEMM (tcgen05), M = R*328, N = 2*16384 packed, K = 2048.
-        # Timed alone, cycling through 6 different weight matrices (6 x 134 MB >> 126 MB L2).
-        M_, Kd, I_ = R * (d.n_img_tokens + d.max_lang_len), d.lm_width, d.lm_mlp
+        # dominant kernel: the prefix gate/up GeGLU GEMM (tcgen05), M = R*(256 + language rows), N = 2*16384 packed,
+        # K = 2048.  Timed alone, cycling through 6 different weight matrices (6 x 134 MB >> 126 MB L2).
+        lang_rows = min(d.max_lang_len, (lmax + 7) // 8 * 8)
+        M_, Kd, I_ = R_loc * (d.n_img_tokens + lang_rows), d.lm_width, d.lm_mlp
         a_ = torch.randn(M_, Kd, device=device, dtype=torch.bfloat16)
         ws = [(torch.randn(2 * I_, Kd, device=device) * 0.02).to(torch.bfloat16) for _ in range(6)]
         o_ = torch.empty(M_, I_, device=device, dtype=torch.bfloat16)
@@ -256,30 +274,37 @@ def run_gpu(args):
         peak = float(peaks["bf16_tflops"])
         roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05<256,4,EPI_GEGLU> (prefix gate/up, M=%d N=%d K=%d)" % (M_, 2 * I_, Kd),
                     "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-                    "traffic": None, "peak_source": peak_src + ", burst figure (kernel timed alone)",
+                    "traffic": NCU_TRAFFIC_BYTES, "algorithmic_bytes": int((M_ * Kd + 2 * I_ * Kd + M_ * I_) * 2),
+                    "peak_source": peak_src + ", burst figure (kernel timed alone)",
                     "launch_ms": round(gemm_ms, 4), "launches_per_step": d.layers - 1,
                     "step_frac_of_sustained_peak": round(total_flops / (ms_per_step * 1e-3) / 1e12 / float(peaks["bf16_tflops_sustained"]), 4)}
         del a_, ws, o_
 
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline_sample(seconds_hint=20)
+            cpu = cpu_baseline_sample()
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
+            "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "BASELINE.json configs[2]: full CoVer step, pi0 %d rephrases x %d samples (%d candidates) "
-                                   "+ 3-member verifier argmax, simpler_widowx shapes, full-size random-init models" % (R, K, N),
-                       "rephrases": R, "samples_per_rephrase": K, "candidates_per_step_per_gpu": N,
-                       "parallelism": "episode-parallel: 1 observation per GPU per step, no data-path collective" if world > 1 else "1 GPU",
+            "config": {"workload": ("BASELINE.json configs[3]: ONE observation, %d rephrases x %d samples (%d candidates) sharded by "
+                                    "rephrase over the ranks, NCCL all-gather of scores/actions, full-size random-init models" % (R, K, N))
+                       if sharded else
+                       ("BASELINE.json configs[2]: full CoVer step, pi0 %d rephrases x %d samples (%d candidates) "
+                        "+ 3-member verifier argmax, simpler_widowx shapes, full-size random-init models" % (R, K, N)),
+                       "rephrases": R, "samples_per_rephrase": K, "candidates_per_step": cands_per_step,
+                       "parallelism": ("rephrase-sharded over %d ranks + score all-gather" % world) if sharded else
+                       ("episode-parallel: 1 observation per GPU per step, no data-path collective" if world > 1 else "1 GPU"),
                        "l2": "no flush needed: every step streams ~8.6 GB of weights from HBM (>> 126 MB L2)",
+                       "max_valid_language_tokens": lmax,
                        "cuda_graph": bool(eng.cfg.use_cuda_graph)},
             "p50_ms": round(statistics.median(per_step), 3),
             "phases_ms": {k: round(val, 3) for k, val in phases.items()},
             "algorithmic_tflop_per_step": round(total_flops / 1e12, 3),
             "clocks": clk,
-            "e2e": {"value": round(N * world / (e2e_ms / 1e3), 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 3),
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": round(cands_per_step / (e2e_ms / 1e3), 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 3),
+                    "p50_ms": round(e2e_p50, 3), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "roofline": roofline,
@@ -291,6 +316,16 @@ def run_gpu(args):
         dist.barrier()
         dist.destroy_process_group()
     return line
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel, from the committed
+# `ncu --set full` capture (profiles/r1_gateup_gemm_ncu.txt); None until a capture exists
+NCU_TRAFFIC_BYTES = None
+
+
+def sstep_inputs(x, K, world, rank):
+    from cover_vla_b200.cover import shard_inputs
+    return shard_inputs(x, K, world, rank)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -336,9 +371,12 @@ def cpu_decision(R: int, K: int, seed: int):
     return time.perf_counter() - t0, idx
 
 
-def cpu_baseline_sample(seconds_hint=20):
+CPU_SAMPLE_R, CPU_SAMPLE_K = 4, 5  # bounded sample: 20 of the 40 candidates, reference batch layout (B = 20)
+
+
+def cpu_baseline_sample():
     st = _cpu_setup()
-    R, K = 1, 2
+    R, K = CPU_SAMPLE_R, CPU_SAMPLE_K
     cpu_decision(1, 1, seed=1)  # warm-up (thread pools, allocator)
     t, _ = cpu_decision(R, K, seed=2)
     return {"value": round(R * K / t, 4), "unit": UNIT, "cores": st["cores"], "kind": "port",
@@ -353,8 +391,8 @@ def run_reference(args):
     if rank != 0:
         return
     st = _cpu_setup()
-    R, K = 1, 2
-    # bounded sample: each step = one decision over 2 candidates (B = 2 in the reference's batch layout)
+    R, K = CPU_SAMPLE_R, CPU_SAMPLE_K
+    # bounded sample: each step = one decision over R*K = 20 candidates (B = 20 in the reference's batch layout)
     for i in range(max(1, min(args.warmup, 1))):
         cpu_decision(R, K, seed=10 + i)
     times = []
@@ -390,6 +428,10 @@ def main():
     ap.add_argument("--rephrases", type=int, default=R_DEFAULT)
     ap.add_argument("--samples", type=int, default=K_DEFAULT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="episode", choices=["episode", "sharded"],
+                    help="episode: every rank decides its own observation (weak scaling, BASELINE configs[2]/[4]); "
+                         "sharded: ONE observation, rephrases sharded over the ranks + NCCL score all-gather "
+                         "(strong scaling, BASELINE configs[3]; use --rephrases 16 --samples 16)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -319,8 +319,9 @@ def run_gpu(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel, from the committed
-# `ncu --set full` capture (profiles/r1_gateup_gemm_ncu.txt); None until a capture exists
-NCU_TRAFFIC_BYTES = None
+# `ncu --set full` capture (profiles/r1b_gateup_gemm_ncu.txt: 145.3 MB read + 60.7 MB written at M=2624, i.e. the
+# full 328-row prefix of tools/gateup_one.py; algorithmic bytes at that M are 231 MB - part of A/W hits L2)
+NCU_TRAFFIC_BYTES = 206.0e6
 
 
 def sstep_inputs(x, K, world, rank):

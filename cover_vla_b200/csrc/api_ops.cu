@@ -46,6 +46,15 @@ int cvb_op_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int
   return cvb::gemm_bf16((cudaStream_t)stream, c);
 }
 
+int cvb_op_sgemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, int M, int N, int K, float* C,
+                     int64_t ldc, const float* bias, const float* row_bias, const float* resid, int64_t ldr, int act,
+                     void* stream) {
+  cvb::SgemmCall c;
+  c.A = A, c.lda = lda, c.W = W, c.ldw = ldw, c.M = M, c.N = N, c.K = K, c.C = C, c.ldc = ldc;
+  c.bias = bias, c.row_bias = row_bias, c.resid = resid, c.ldr = ldr, c.act = act;
+  c.w_dynamic = 1;  // operator level: W may have been produced by the caller's previous launch
+  return cvb::sgemm_f32((cudaStream_t)stream, c);
+}
 
 int cvb_op_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k0, const void* v0, int64_t kv0_bs,
                      int64_t kv0_rs, const int32_t* kv0_len_dev, int kv0_len, int kv0_max, int q_per_kv_batch,

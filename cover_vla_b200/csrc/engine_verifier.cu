@@ -79,10 +79,11 @@ int gemm(cudaStream_t st, const bf16* A, long lda, const bf16* Wt, long ldw, int
   return gemm_bf16(st, c);
 }
 int sg(cudaStream_t st, const float* A, long lda, const float* Wt, long ldw, int M, int N, int K, float* C, long ldc,
-       const float* bias = nullptr, int act = 0, const float* resid = nullptr, long ldr = 0, int w_kn = 0) {
+       const float* bias = nullptr, int act = 0, const float* resid = nullptr, long ldr = 0, int w_kn = 0,
+       int w_dynamic = 0) {
   SgemmCall c;
   c.A = A, c.lda = lda, c.W = Wt, c.ldw = ldw, c.M = M, c.N = N, c.K = K, c.C = C, c.ldc = ldc;
-  c.bias = bias, c.act = act, c.resid = resid, c.ldr = ldr, c.w_kn = w_kn;
+  c.bias = bias, c.act = act, c.resid = resid, c.ldr = ldr, c.w_kn = w_kn, c.w_dynamic = w_dynamic;
   return sgemm_f32(st, c);
 }
 }  // namespace
@@ -433,7 +434,7 @@ static int run_heads_context(cvb_handle* h, cudaStream_t st) {
   for (int m = 0; m < M; ++m) {
     const MemberW& Mw = s.mem[m];
     float* taf = s.taf + (size_t)m * Tt * Wd;
-    CVB_TRY(sg(st, s.Tn, Wd, s.Pn, Wd, Tt, Np, Wd, s.sim, Np));
+    CVB_TRY(sg(st, s.Tn, Wd, s.Pn, Wd, Tt, Np, Wd, s.sim, Np, nullptr, 0, nullptr, 0, 0, /*w_dynamic=*/1));
     CVB_TRY(softmax_rows_temp(st, s.sim, Tt, Np, Mw.temp));
     CVB_TRY(add_f32(st, s.Pn, Mw.pos_emb, s.pe, (long)Np * Wd));
     CVB_TRY(sg(st, s.sim, Np, s.pe, Wd, Tt, Wd, Np, taf, Wd, nullptr, 0, nullptr, 0, /*w_kn=*/1));

@@ -47,6 +47,7 @@ struct SgemmCall {
   const float* row_bias = nullptr;  // optional second bias [N] (e.g. the per-step time vector)
   int w_kn = 0;       // 1: W is [K, N] row-major (C = A @ W) instead of [N, K]
   int out_group = 0;  // >0: output row m lands at (m / g) * (g + 1) + 1 + m % g (suffix layout)
+  int w_dynamic = 0;  // 1: W is produced on the stream (not a weight): never read it ahead of the dependency wait
 };
 int sgemm_f32(cudaStream_t st, const SgemmCall& c);
 

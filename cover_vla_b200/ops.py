@@ -58,3 +58,25 @@ def attention(q, k0, v0, *, heads, kv_heads, head_dim, kv0_len=None, kv0_len_dev
         B, heads, kv_heads, Tq, head_dim, scale, (int(algo) + 1 if algo else int(force_two_pass)), _lib.ptr(rope), _lib.stream_ptr())
     _lib.check(rc)
     return out
+
+
+SACT_NONE, SACT_RELU, SACT_GELU_ERF, SACT_SILU = range(4)
+
+
+def sgemm_f32(a, w, *, bias=None, row_bias=None, resid=None, act=SACT_NONE, out=None):
+    """out[M, N] = act(a[M, K] @ w[N, K]^T + bias + row_bias) + resid, all float32 CUDA (true-fp32 accumulation)."""
+    lib = _lib.load()
+    assert a.dtype == torch.float32 and w.dtype == torch.float32
+    assert a.stride(-1) == 1 and w.stride(-1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    lib.cvb_op_sgemm_f32.argtypes = ([C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                      C.c_void_p])
+    rc = lib.cvb_op_sgemm_f32(_lib.ptr(a), _i64(a.stride(0)), _lib.ptr(w), _i64(w.stride(0)), M, N, K, _lib.ptr(out),
+                              _i64(out.stride(0)), _lib.ptr(bias), _lib.ptr(row_bias), _lib.ptr(resid),
+                              _i64(resid.stride(0) if resid is not None else 0), int(act), _lib.stream_ptr())
+    _lib.check(rc)
+    return out

@@ -46,6 +46,13 @@ CVB_API int cvb_op_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
                      const void* resid, int resid_is_f32, int64_t ldr, int n_out,
                      const int32_t* m_dev, int force_bn, void* stream);
 
+/* fp32 linear for the parts of the path the reference keeps in float32 (modeling_pi0.py:598-609 suffix MLP,
+ * efficient_ensemble_merged.py:194-247 verifier heads): C = act(A[M,K] . W[N,K]^T + bias + row_bias) + resid, true-fp32
+ * FFMA accumulation (no TF32).  act: 0 none | 1 relu | 2 gelu(erf) | 3 silu.  Any pointer but A / W / C may be NULL. */
+CVB_API int cvb_op_sgemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, int M, int N, int K, float* C,
+                             int64_t ldc, const float* bias, const float* row_bias, const float* resid, int64_t ldr,
+                             int act, void* stream);
+
 /* Exact-softmax attention with the reference's rounding ledger (eager_attention_forward,
  * paligemma_with_expert.py:376-434): q [batches, tq, heads*head_dim] (strides q_bs / q_rs in elements), keys in two
  * segments - segment 0 shared per kv batch (kv batch = batch / q_per_kv_batch; length from kv0_len_dev[kv batch] or

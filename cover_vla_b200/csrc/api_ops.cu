@@ -46,6 +46,13 @@ int cvb_op_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int
   return cvb::gemm_bf16((cudaStream_t)stream, c);
 }
 
+int cvb_op_rmsnorm_reduce(const float* P, int S, int64_t split_stride, int64_t ldp, const void* resid, int resid_is_f32,
+                          int64_t ldr, const void* w, int w_is_f32, void* h_out, int64_t ldh, void* y, int64_t ldy,
+                          int rows, int width, float eps, void* stream) {
+  return cvb::rmsnorm_reduce((cudaStream_t)stream, P, S, split_stride, ldp, resid, resid_is_f32, ldr, w, w_is_f32,
+                             (cvb::bf16*)h_out, ldh, (cvb::bf16*)y, ldy, rows, width, eps);
+}
+
 int cvb_op_sgemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, int M, int N, int K, float* C,
                      int64_t ldc, const float* bias, const float* row_bias, const float* resid, int64_t ldr, int act,
                      void* stream) {

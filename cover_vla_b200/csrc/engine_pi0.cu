@@ -5,7 +5,9 @@
 // Reference: PI0FlowMatching.sample_actions, modeling_pi0.py:672-715 and everything it calls
 // (embed_prefix :517-567, PaliGemmaWithExpertModel.forward paligemma_with_expert.py:236-360,
 // embed_suffix :569-629, denoise_step :717-752).  De-duplication per SURVEY.md F1/F2.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "engine.h"
 #include "gemm_tcgen05.cuh"
@@ -25,6 +27,7 @@ const std::string LM = PW + "paligemma.language_model.model.";
 const std::string EX = PW + "gemma_expert.model.";
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
+constexpr int kMaxSplitK = 16;
 
 template <typename T>
 int W(cvb_handle* h, const std::string& key, int dtype, int64_t numel, const T** out) {
@@ -287,6 +290,21 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
   CVB_TRY(dalloc_t(h, &s.qkv_e, Me * qkvw));
   CVB_TRY(dalloc_t(h, &s.attn_e, Me * qd));
   CVB_TRY(dalloc_t(h, &s.act_e, Me * c.ex_mlp));
+  // Denoise-loop o_proj / down_proj as split-K partials reduced inside the following RMSNorm (ops_misc.cu
+  // rmsnorm_reduce_kernel).  The rows of one denoise step must fit one UMMA N (<= 256); larger candidate counts keep
+  // the fused-epilogue GEMMs.  CVB_SPLITK_O / CVB_SPLITK_D override the split counts (0 disables).
+  if (Me <= 256) {
+    auto pick = [&](const char* env, int kdim) {
+      const int kb = (kdim + 63) / 64, tiles = (We + 127) / 128;
+      // measured (tools/splitk_bench.py): 8 splits beat 4 / 12 / 16 at both shapes (more splits = more partial traffic)
+      int sp = std::min(std::min(8, std::max(1, device_sm_count() / tiles)), std::max(1, kb / 2));
+      if (const char* e = getenv(env)) sp = std::max(0, std::min(atoi(e), std::min(kMaxSplitK, kb)));
+      return sp;
+    };
+    s.splitk_o = pick("CVB_SPLITK_O", qd);
+    s.splitk_d = pick("CVB_SPLITK_D", c.ex_mlp);
+    CVB_TRY(dalloc_t(h, &s.part_e, (size_t)kMaxSplitK * Me * We));
+  }
   return 0;
 }
 
@@ -418,11 +436,23 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
       g3.C = s.suffix, g3.ldc = We, g3.bias = b_out, g3.out_group = c.chunk_size;
       CVB_TRY(sgemm_f32(st, g3));
     }
+    // pending = split-K partials of the previous down_proj still to be folded into he by the next norm
+    int pending = 0;
+    auto gemm_part = [&](const bf16* A, long lda, const bf16* Wt, int Kd, int splits, int* used) {
+      GemmCall g;
+      g.A = A, g.lda = lda, g.W = Wt, g.ldw = Kd, g.M = M, g.N = We, g.K = Kd, g.C = s.part_e, g.ldc = We;
+      return gemm_splitk_partial(st, g, splits, used);
+    };
     for (int l = 0; l < c.layers; ++l) {
       const GemmaLayer& L = s.ex[l];
       const void* resid = l == 0 ? static_cast<const void*>(s.suffix) : static_cast<const void*>(s.he);
       const int resid_f32 = l == 0 ? 1 : 0;
-      CVB_TRY(rmsnorm(st, resid, resid_f32, We, L.in_norm, 0, s.xe, We, M, We, 1e-6f, nullptr));
+      if (pending > 0)  // he = he + down_proj(l-1), xe = input_layernorm(he)
+        CVB_TRY(rmsnorm_reduce(st, s.part_e, pending, (long)M * We, We, s.he, 0, We, L.in_norm, 0, s.he, We, s.xe, We, M,
+                               We, 1e-6f));
+      else
+        CVB_TRY(rmsnorm(st, resid, resid_f32, We, L.in_norm, 0, s.xe, We, M, We, 1e-6f, nullptr));
+      pending = 0;
       CVB_TRY(gemm(st, s.xe, We, L.wqkv, We, M, qkvw, We, EPI_STORE, s.qkv_e, qkvw));
       if (!fused_rope)
         CVB_TRY(rope_qkv(st, s.qkv_e, qkvw, s.rope_timescale, M, c.heads, hd, S, s.plen, K, nullptr, nullptr, 0, 0));
@@ -439,12 +469,26 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
       a.batches = N, a.heads = c.heads, a.kv_heads = 1, a.tq = S, a.head_dim = hd;
       a.scale = 1.0f / sqrtf(static_cast<float>(hd));
       CVB_TRY(attention(st, a));
-      CVB_TRY(gemm(st, s.attn_e, qd, L.wo, qd, M, We, qd, EPI_RESID, s.he, We, nullptr, resid, We, resid_f32));
-      CVB_TRY(rmsnorm(st, s.he, 0, We, L.post_norm, 0, s.xe, We, M, We, 1e-6f, nullptr));
+      if (s.splitk_o > 0) {
+        int used = 0;
+        CVB_TRY(gemm_part(s.attn_e, qd, L.wo, qd, s.splitk_o, &used));
+        CVB_TRY(rmsnorm_reduce(st, s.part_e, used, (long)M * We, We, resid, resid_f32, We, L.post_norm, 0, s.he, We,
+                               s.xe, We, M, We, 1e-6f));
+      } else {
+        CVB_TRY(gemm(st, s.attn_e, qd, L.wo, qd, M, We, qd, EPI_RESID, s.he, We, nullptr, resid, We, resid_f32));
+        CVB_TRY(rmsnorm(st, s.he, 0, We, L.post_norm, 0, s.xe, We, M, We, 1e-6f, nullptr));
+      }
       CVB_TRY(gemm(st, s.xe, We, L.wgu, We, M, packed, We, EPI_GEGLU, s.act_e, c.ex_mlp, nullptr, nullptr, 0, 0, c.ex_mlp));
-      CVB_TRY(gemm(st, s.act_e, c.ex_mlp, L.wd, c.ex_mlp, M, We, c.ex_mlp, EPI_RESID, s.he, We, nullptr, s.he, We));
+      if (s.splitk_d > 0)
+        CVB_TRY(gemm_part(s.act_e, c.ex_mlp, L.wd, c.ex_mlp, s.splitk_d, &pending));
+      else
+        CVB_TRY(gemm(st, s.act_e, c.ex_mlp, L.wd, c.ex_mlp, M, We, c.ex_mlp, EPI_RESID, s.he, We, nullptr, s.he, We));
     }
-    CVB_TRY(rmsnorm(st, s.he, 0, We, w_norm, 1, s.xe, We, M, We, 1e-6f, nullptr));
+    if (pending > 0)
+      CVB_TRY(rmsnorm_reduce(st, s.part_e, pending, (long)M * We, We, s.he, 0, We, w_norm, 1, s.he, We, s.xe, We, M, We,
+                             1e-6f));
+    else
+      CVB_TRY(rmsnorm(st, s.he, 0, We, w_norm, 1, s.xe, We, M, We, 1e-6f, nullptr));
     CVB_TRY(action_out_euler(st, s.xe, We, w_aout, b_aout, s.x_t, step == 0 ? s.v0 : nullptr, N, We,
                              c.max_action_dim, c.chunk_size, S, s.dt));
   }

@@ -377,4 +377,159 @@ gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   cluster_sync_relaxed();
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Split-K variant WITHOUT a cluster: CTA (tile, split) streams its K-slice of one 128-row weight tile and stores its
+// fp32 partial accumulator to P[split][m][n] (coalesced 128-byte rows).  The consumer (rmsnorm_reduce_kernel,
+// ops_misc.cu) sums the S partials in split order (deterministic), applies the residual and the norm that follows the
+// linear layer anyway - so the reduction costs no extra launch and no SM-to-SM traffic (measured: the DSMEM
+// reduce-scatter above takes 4-5 us of a 10-13 us launch at the expert's o_proj / down_proj shapes; an L2 round trip
+// of the same partials takes ~1 us).
+constexpr int EPI_PARTIAL = 6;
+
+struct SplitKArgs {
+  float* P;
+  long ldp;           // row stride of one partial (elements)
+  long split_stride;  // elements between partials
+  int M, Mp, N, K;
+  int S;       // K-splits (grid = n_tiles * S)
+  int stages;  // smem ring depth
+  int tmem_cols;
+};
+
+template <int UNUSED>  // (template only so that the header may be included by several translation units)
+__global__ void __launch_bounds__(SK_THREADS, 1)
+gemm_splitk_partial_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA,
+                            const SplitKArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const uint32_t a_bytes = static_cast<uint32_t>(g.Mp) * 128u;
+  const uint32_t stage_bytes = SK_W_BYTES + a_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + static_cast<uint32_t>(g.stages) * stage_bytes);
+  uint64_t* empty_bar = full_bar + g.stages;
+  uint64_t* tfull_bar = empty_bar + g.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / g.S;
+  const int split = blockIdx.x % g.S;
+  const int kb_total = (g.K + 63) / 64;
+  // balanced k-block ranges: every split owns >= 1 block (host guarantees S <= kb_total)
+  const int kb0 = static_cast<int>(static_cast<long>(split) * kb_total / g.S);
+  const int kb1 = static_cast<int>(static_cast<long>(split + 1) * kb_total / g.S);
+  const int nkb = kb1 - kb0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmA);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < g.stages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tfull_bar, 1);
+      fence_barrier_init();
+      fence_proxy_async();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, g.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  pdl_launch();
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      // weight tiles first (independent of the preceding kernel), activations after the dependency resolves
+      const int pre = min(nkb, g.stages);
+      for (int i = 0; i < pre; ++i) {
+        mbar_arrive_expect_tx(&full_bar[i], stage_bytes);
+        tma_load_2d_hint(smem + i * stage_bytes, &tmW, &full_bar[i], (kb0 + i) * 64, tile * 128, kEvictFirst);
+      }
+      pdl_wait();
+      for (int i = 0; i < nkb; ++i) {
+        uint8_t* sw = smem + stage * stage_bytes;
+        if (i < pre) {
+          tma_load_2d_hint(sw + SK_W_BYTES, &tmA, &full_bar[stage], (kb0 + i) * 64, 0, kEvictLast);
+        } else {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+          tma_load_2d_hint(sw, &tmW, &full_bar[stage], (kb0 + i) * 64, tile * 128, kEvictFirst);
+          tma_load_2d_hint(sw + SK_W_BYTES, &tmA, &full_bar[stage], (kb0 + i) * 64, 0, kEvictLast);
+        }
+        if (++stage == static_cast<uint32_t>(g.stages)) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_rt(1, 128, g.Mp);
+      uint32_t stage = 0, phase = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t w_addr = smem_u32(smem + stage * stage_bytes);
+        const uint64_t wdesc = make_desc_kmajor_sw128(w_addr);
+        const uint64_t adesc = make_desc_kmajor_sw128(w_addr + SK_W_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, wdesc + 2 * k, adesc + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+        if (++stage == static_cast<uint32_t>(g.stages)) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tfull_bar);
+    }
+    __syncwarp();
+  } else {
+    pdl_wait();  // P may still be read by the kernel that consumed the previous partials
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    // TMEM lane = feature, column = activation row: lane L of the warp's quarter stores P[split][m][tile*128 + L]
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int n = tile * 128 + q * 32 + lane;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float* pp = g.P + static_cast<long>(split) * g.split_stride + n;
+    for (int c0 = half * 32; c0 < g.Mp; c0 += 64) {
+      uint32_t r[32];
+      const bool wide = c0 + 32 <= g.Mp;  // Mp is a multiple of 16: the last chunk may be 16 columns
+      if (wide) {
+        tmem_ld_x32(taddr + c0, r);
+      } else {
+        uint32_t r16[16];
+        tmem_ld_x16(taddr + c0, r16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = r16[i];
+      }
+      tmem_wait_ld();
+      if (n < g.N) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int m = c0 + i;
+          if ((i < 16 || wide) && m < g.M) pp[static_cast<long>(m) * g.ldp] = __uint_as_float(r[i]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, g.tmem_cols);
+  }
+}
+
 }  // namespace cvb

@@ -29,6 +29,9 @@ struct GemmCall {
   int force_bn = 0;            // 0 = heuristic, else 64 / 128 / 256
 };
 int gemm_bf16(cudaStream_t st, const GemmCall& c);
+// Split-K GEMM (M <= 256) that leaves S fp32 partial products in C = float[S][M][ldc] (epi / bias / resid unused);
+// splits <= 0 picks S so that n_tiles * S fills the SMs once.  The partials are consumed by rmsnorm_reduce().
+int gemm_splitk_partial(cudaStream_t st, const GemmCall& c, int splits, int* splits_out);
 
 // ---- fp32 SIMT GEMM (sgemm.cuh): C = act(A[M,K] * W[N,K]^T + bias) (+ resid) -------------------
 enum SgemmAct : int { SACT_NONE = 0, SACT_RELU = 1, SACT_GELU_ERF = 2, SACT_SILU = 3 };
@@ -55,6 +58,12 @@ int sgemm_f32(cudaStream_t st, const SgemmCall& c);
 // Gemma RMSNorm: y = bf16( x * rsqrt(mean(x^2) + eps) * (1 + w) ), statistics in fp32.
 int rmsnorm(cudaStream_t st, const void* x, int x_is_f32, long ldx, const void* w, int w_is_f32,
             bf16* y, long ldy, int rows, int width, float eps, const int* rows_dev);
+// Linear-layer tail + Gemma RMSNorm in one pass over the split-K partials of gemm_splitk_partial():
+//   h = bf16( bf16(sum_s P[s]) + resid )   (the EPI_RESID ledger; h_out may alias resid)
+//   y = bf16( h * rsqrt(mean(h^2) + eps) * (1 + w) )
+int rmsnorm_reduce(cudaStream_t st, const float* P, int S, long split_stride, long ldp, const void* resid,
+                   int resid_is_f32, long ldr, const void* w, int w_is_f32, bf16* h_out, long ldh, bf16* y, long ldy,
+                   int rows, int width, float eps);
 // LayerNorm on bf16 rows (fp32 statistics), bf16 affine.
 int layernorm_bf16(cudaStream_t st, const bf16* x, long ldx, const bf16* w, const bf16* b, bf16* y,
                    long ldy, int rows, int width, float eps);

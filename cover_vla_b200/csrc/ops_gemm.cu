@@ -105,8 +105,9 @@ int launch_bn(cudaStream_t st, const GemmCall& c, int bn, int grid) {
 int gemm_bf16(cudaStream_t st, const GemmCall& c) {
   CVB_REQUIRE(c.M > 0 && c.N > 0 && c.K > 0, "empty GEMM");
   // force_bn: 0 = auto, 64/128/256 = general kernel with that tile, -100 = skinny auto, -1..-16 = skinny with that split
-  if (c.force_bn < 0) return gemm_skinny(st, c, c.force_bn == -100 ? 0 : -c.force_bn);
+  if (c.force_bn < 0 && c.epi != 6) return gemm_skinny(st, c, c.force_bn == -100 ? 0 : -c.force_bn);
   if (c.epi == 5) return gemm_skinny(st, c, 0);
+  if (c.epi == 6) return gemm_splitk_partial(st, c, c.force_bn < 0 ? -c.force_bn : 0, nullptr);  // EPI_PARTIAL
   if (c.force_bn == 0 && skinny_eligible(c)) return gemm_skinny(st, c, 0);
   CVB_REQUIRE(c.K % 8 == 0, "K must be a multiple of 8 (16-byte TMA rows)");
   CVB_REQUIRE(c.N % 8 == 0, "N must be a multiple of 8 (16-byte vector epilogue)");

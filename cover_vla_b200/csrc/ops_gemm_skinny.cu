@@ -1,4 +1,5 @@
 // Host dispatch for the skinny (swap-AB, cluster split-K) GEMM: split heuristic, tensor maps, cluster launch.
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 
@@ -111,6 +112,44 @@ int gemm_skinny(cudaStream_t st, const GemmCall& c, int force_split) {
       set_last_error("epilogue kind not supported by the skinny GEMM");
       return -1;
   }
+}
+
+// Split-K GEMM with fp32 partials in global memory (no cluster): C = fp32 [S][M][ldc], consumed by rmsnorm_reduce().
+// Returns the number of splits actually used through *splits_out (<= requested; every split owns >= 1 k-block).
+int gemm_splitk_partial(cudaStream_t st, const GemmCall& c, int splits, int* splits_out) {
+  CVB_REQUIRE(c.M > 0 && c.M <= 256, "split-K partial GEMM handles 1..256 activation rows");
+  CVB_REQUIRE(c.K % 8 == 0, "K must be a multiple of 8 (16-byte TMA rows)");
+  CVB_REQUIRE(c.m_dev == nullptr && c.bias == nullptr && c.resid == nullptr,
+              "split-K partial GEMM has no fused epilogue (bias / residual belong to the reducing kernel)");
+  SplitKArgs g;
+  g.P = reinterpret_cast<float*>(c.C), g.ldp = c.ldc, g.split_stride = static_cast<long>(c.M) * c.ldc;
+  g.M = c.M, g.Mp = (c.M + 15) / 16 * 16, g.N = c.N, g.K = c.K;
+  const int n_tiles = (c.N + 127) / 128;
+  const int kb_total = (c.K + 63) / 64;
+  int S = splits;
+  if (S <= 0) {  // fill the SMs once: n_tiles * S <= #SMs, at least 2 k-blocks per split
+    S = std::max(1, device_sm_count() / n_tiles);
+    S = std::min(S, std::max(1, kb_total / 2));
+  }
+  S = std::max(1, std::min(S, kb_total));
+  g.S = S;
+  const int stage_bytes = SK_W_BYTES + g.Mp * 128;
+  const int kbs = (kb_total + S - 1) / S;
+  g.stages = std::max(1, std::min(std::min(kbs, 5), (kSmemBudget - 1024) / stage_bytes));
+  g.tmem_cols = g.Mp <= 32 ? 32 : g.Mp <= 64 ? 64 : g.Mp <= 128 ? 128 : 256;
+  CUtensorMap tmW, tmA;
+  CVB_TRY(get_tmap_cached(c.W, c.N, c.K, c.ldw, 128, &tmW));
+  CVB_TRY(get_tmap_cached(c.A, c.M, c.K, c.lda, g.Mp, &tmA));
+  const int smem = 1024 + g.stages * stage_bytes + (2 * g.stages + 1) * 8 + 16;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    CVB_CUDA(cudaFuncSetAttribute(gemm_splitk_partial_tcgen05<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  CVB_TRY(launch_pdl(gemm_splitk_partial_tcgen05<0>, dim3(n_tiles * S), dim3(SK_THREADS), smem, st, 1, tmW, tmA, g));
+  CVB_LAUNCHED();
+  if (splits_out != nullptr) *splits_out = S;
+  return 0;
 }
 
 }  // namespace cvb

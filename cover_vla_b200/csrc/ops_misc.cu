@@ -115,6 +115,99 @@ int rmsnorm(cudaStream_t st, const void* x, int x_is_f32, long ldx, const void* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tail of a split-K linear layer fused with the Gemma RMSNorm that follows it (o_proj -> post_attention_layernorm,
+// down_proj -> next input_layernorm / final norm; paligemma_with_expert.py:327-355).  One CTA per row sums the S fp32
+// partials of gemm_splitk_partial_tcgen05 in split order, applies the reference's rounding points
+// (bf16(acc), + residual, bf16) and normalises the new residual-stream row.
+template <bool R_F32, bool W_F32>
+__global__ void __launch_bounds__(256) rmsnorm_reduce_kernel(const float* __restrict__ P, int S, long split_stride,
+                                                             long ldp, const void* resid, long ldr,
+                                                             const void* __restrict__ w, bf16* h_out, long ldh,
+                                                             bf16* __restrict__ y, long ldy, int width, float eps) {
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ float hrow[];  // the new residual row (bf16 values held as fp32)
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const float* pr = P + row * ldp;
+  float ss = 0.f;
+  for (int i = threadIdx.x * 4; i < width; i += blockDim.x * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = 0;
+    for (; s + 4 <= S; s += 4) {  // four independent loads in flight, summed in split order
+      const float4 a0 = *reinterpret_cast<const float4*>(pr + (s + 0) * split_stride + i);
+      const float4 a1 = *reinterpret_cast<const float4*>(pr + (s + 1) * split_stride + i);
+      const float4 a2 = *reinterpret_cast<const float4*>(pr + (s + 2) * split_stride + i);
+      const float4 a3 = *reinterpret_cast<const float4*>(pr + (s + 3) * split_stride + i);
+      acc.x = (((acc.x + a0.x) + a1.x) + a2.x) + a3.x;
+      acc.y = (((acc.y + a0.y) + a1.y) + a2.y) + a3.y;
+      acc.z = (((acc.z + a0.z) + a1.z) + a2.z) + a3.z;
+      acc.w = (((acc.w + a0.w) + a1.w) + a2.w) + a3.w;
+    }
+    for (; s < S; ++s) {
+      const float4 a = *reinterpret_cast<const float4*>(pr + s * split_stride + i);
+      acc.x += a.x, acc.y += a.y, acc.z += a.z, acc.w += a.w;
+    }
+    float rr[4];
+    if constexpr (R_F32) {
+      const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(resid) + row * ldr + i);
+      rr[0] = v.x, rr[1] = v.y, rr[2] = v.z, rr[3] = v.w;
+    } else {
+      const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(resid) + row * ldr + i);
+      const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y);
+      rr[0] = f0.x, rr[1] = f0.y, rr[2] = f1.x, rr[3] = f1.y;
+    }
+    const float hv[4] = {bf16_round(bf16_round(acc.x) + rr[0]), bf16_round(bf16_round(acc.y) + rr[1]),
+                         bf16_round(bf16_round(acc.z) + rr[2]), bf16_round(bf16_round(acc.w) + rr[3])};
+    *reinterpret_cast<uint2*>(h_out + row * ldh + i) = make_uint2(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]));
+    *reinterpret_cast<float4*>(hrow + i) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+    ss += hv[0] * hv[0] + hv[1] * hv[1] + hv[2] * hv[2] + hv[3] * hv[3];
+  }
+  ss = block_sum(ss, red);
+  const float r = 1.0f / sqrtf(ss / static_cast<float>(width) + eps);
+  bf16* yr = y + row * ldy;
+  for (int i = threadIdx.x * 4; i < width; i += blockDim.x * 4) {  // each thread re-reads its own hrow entries
+    const float4 hv = *reinterpret_cast<const float4*>(hrow + i);
+    float wv[4];
+    if constexpr (W_F32) {
+      const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(w) + i);
+      wv[0] = v.x, wv[1] = v.y, wv[2] = v.z, wv[3] = v.w;
+    } else {
+      const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(w) + i);
+      const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y);
+      wv[0] = f0.x, wv[1] = f0.y, wv[2] = f1.x, wv[3] = f1.y;
+    }
+    *reinterpret_cast<uint2*>(yr + i) =
+        make_uint2(pack_bf16x2((hv.x * r) * (1.0f + wv[0]), (hv.y * r) * (1.0f + wv[1])),
+                   pack_bf16x2((hv.z * r) * (1.0f + wv[2]), (hv.w * r) * (1.0f + wv[3])));
+  }
+}
+
+int rmsnorm_reduce(cudaStream_t st, const float* P, int S, long split_stride, long ldp, const void* resid,
+                   int resid_is_f32, long ldr, const void* w, int w_is_f32, bf16* h_out, long ldh, bf16* y, long ldy,
+                   int rows, int width, float eps) {
+  CVB_REQUIRE(width % 4 == 0 && ldp % 4 == 0 && split_stride % 4 == 0 && ldr % 4 == 0 && ldh % 4 == 0 && ldy % 4 == 0,
+              "rmsnorm_reduce needs 4-element aligned rows");
+  CVB_REQUIRE(S >= 1 && resid != nullptr, "rmsnorm_reduce needs >= 1 partial and a residual");
+  const int threads = width >= 1024 ? 256 : 128;
+  const size_t smem = static_cast<size_t>(width) * sizeof(float);
+#define CVB_RR(RF, WF)                                                                                             \
+  CVB_TRY(launch_pdl(rmsnorm_reduce_kernel<RF, WF>, dim3(rows), dim3(threads), smem, st, 1, P, S, split_stride, ldp, \
+                     resid, ldr, w, h_out, ldh, y, ldy, width, eps))
+  if (resid_is_f32 && w_is_f32)
+    CVB_RR(true, true);
+  else if (resid_is_f32)
+    CVB_RR(true, false);
+  else if (w_is_f32)
+    CVB_RR(false, true);
+  else
+    CVB_RR(false, false);
+#undef CVB_RR
+  CVB_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // LayerNorm over bf16 rows (SigLIP / ViT-L / text tower blocks).  fp32 statistics (two-pass).
 __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const bf16* __restrict__ x, long ldx,
                                                              const bf16* __restrict__ w,

@@ -7,7 +7,7 @@ import torch
 
 from . import _lib
 
-EPI_STORE, EPI_GELU, EPI_RESID, EPI_GEGLU, EPI_F32, EPI_GEGLU64 = range(6)
+EPI_STORE, EPI_GELU, EPI_RESID, EPI_GEGLU, EPI_F32, EPI_GEGLU64, EPI_PARTIAL = range(7)
 SKINNY_AUTO = -100  # force_bn value: skinny (swap-AB, cluster split-K) GEMM with the split heuristic; -S forces S splits
 
 
@@ -36,6 +36,38 @@ def gemm_bf16(a, w, *, epilogue=EPI_STORE, bias=None, resid=None, out=None, n_ou
         int(force_bn), _lib.stream_ptr())
     _lib.check(rc)
     return out
+
+
+def gemm_splitk_partial(a, w, splits):
+    """fp32 partial products [S, M, N] of a[M, K] @ w[N, K]^T, K split into S balanced runs of 64-wide blocks."""
+    M, K = a.shape
+    N = w.shape[0]
+    S = max(1, min(int(splits), (K + 63) // 64))
+    out = torch.empty(S, M, N, device=a.device, dtype=torch.float32)
+    lib = _lib.load()
+    rc = lib.cvb_op_gemm_bf16(
+        _lib.ptr(a), _i64(a.stride(0)), _lib.ptr(w), _i64(w.stride(0)), M, N, K, EPI_PARTIAL,
+        _lib.ptr(out), _i64(N), None, 0, None, 0, _i64(0), 0, None, -S, _lib.stream_ptr())
+    _lib.check(rc)
+    return out
+
+
+def rmsnorm_reduce(partials, resid, w, eps=1e-6):
+    """(h, y): h = bf16(bf16(sum_s partials[s]) + resid), y = GemmaRMSNorm(h) with weight w (bf16 or fp32)."""
+    lib = _lib.load()
+    S, M, N = partials.shape
+    assert partials.dtype == torch.float32 and partials.is_contiguous()
+    h = torch.empty(M, N, device=partials.device, dtype=torch.bfloat16)
+    y = torch.empty_like(h)
+    lib.cvb_op_rmsnorm_reduce.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int64,
+                                          C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                          C.c_int, C.c_int, C.c_float, C.c_void_p]
+    rc = lib.cvb_op_rmsnorm_reduce(_lib.ptr(partials), S, M * N, N, _lib.ptr(resid),
+                                   int(resid.dtype == torch.float32), resid.stride(0), _lib.ptr(w),
+                                   int(w.dtype == torch.float32), _lib.ptr(h), N, _lib.ptr(y), N, M, N, float(eps),
+                                   _lib.stream_ptr())
+    _lib.check(rc)
+    return h, y
 
 
 def attention(q, k0, v0, *, heads, kv_heads, head_dim, kv0_len=None, kv0_len_dev=None, q_per_kv_batch=1,

@@ -38,6 +38,9 @@ CVB_API int64_t cvb_launch_count(void);
  * Operator level (one launch each).  GEMM epilogue kinds:
  *   0 store bf16(acc+bias) | 1 bf16(gelu_tanh(bf16(acc+bias))) | 2 bf16(bf16(acc+bias)+resid)
  *   3 GeGLU on packed [128 gate | 128 up] weight rows | 4 store fp32(acc+bias)
+ *   5 GeGLU on packed [64 gate | 64 up] rows (skinny kernel, M <= 256)
+ *   6 split-K partials (M <= 256): C = fp32 [S][M][ldc], S = -force_bn clamped to ceil(K/64) (0: fill the SMs once);
+ *     no bias / resid - the S partials are summed by cvb_op_rmsnorm_reduce
  * Replaces nn.Linear (+ the elementwise op that follows it) wherever it appears on the path, e.g.
  * paligemma_with_expert.py:273-276 (q/k/v), :327-333 (o_proj + residual), :335-341 (MLP + residual).
  */
@@ -45,6 +48,14 @@ CVB_API int cvb_op_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
                      int epilogue, void* C, int64_t ldc, const void* bias, int bias_is_f32,
                      const void* resid, int resid_is_f32, int64_t ldr, int n_out,
                      const int32_t* m_dev, int force_bn, void* stream);
+
+/* Tail of a split-K linear layer fused with the Gemma RMSNorm that follows it (paligemma_with_expert.py:327-355:
+ * o_proj + residual -> post_attention_layernorm, down_proj + residual -> next input_layernorm):
+ *   h = bf16(bf16(sum_s P[s]) + resid)  (summed in split order; h_out may alias resid),  y = bf16(h * rsqrt(mean(h^2) + eps) * (1 + w)).
+ * P = fp32 [S][rows][ldp] written by cvb_op_gemm_bf16(epilogue 6); resid bf16 or fp32; w bf16 or fp32 [width]. */
+CVB_API int cvb_op_rmsnorm_reduce(const float* P, int S, int64_t split_stride, int64_t ldp, const void* resid,
+                                  int resid_is_f32, int64_t ldr, const void* w, int w_is_f32, void* h_out, int64_t ldh,
+                                  void* y, int64_t ldy, int rows, int width, float eps, void* stream);
 
 /* fp32 linear for the parts of the path the reference keeps in float32 (modeling_pi0.py:598-609 suffix MLP,
  * efficient_ensemble_merged.py:194-247 verifier heads): C = act(A[M,K] . W[N,K]^T + bias + row_bias) + resid, true-fp32

@@ -1,0 +1,81 @@
+"""Split-K partial GEMM (cvb_op_gemm_bf16 epilogue 6) + cvb_op_rmsnorm_reduce against torch.
+
+The pair replaces `o_proj -> + residual -> post_attention_layernorm` and `down_proj -> + residual -> next input_layernorm`
+of the action expert (paligemma_with_expert.py:327-355) during PI0FlowMatching.denoise_step (modeling_pi0.py:717-752).
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemma_rmsnorm(h, w, eps=1e-6):
+    x = h.float()
+    x = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps)
+    return (x * (1.0 + w.float())).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K,S", [(200, 1024, 2048, 8), (200, 1024, 2048, 16), (200, 1024, 4096, 16),
+                                     (200, 1024, 4096, 5), (40, 1024, 4096, 12), (5, 128, 64, 4), (256, 1152, 4304, 9),
+                                     (20, 64, 200, 2), (200, 1024, 2048, 1)])
+def test_partials_sum_to_the_product(M, N, K, S):
+    from cover_vla_b200 import ops
+    torch.manual_seed(M + N + K + S)
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    p = ops.gemm_splitk_partial(a, w, S)
+    torch.cuda.synchronize()
+    kb = (K + 63) // 64
+    S_eff = min(S, kb)
+    assert p.shape == (S_eff, M, N)
+    # every partial is the product over its own balanced run of 64-wide k-blocks (fp32 accumulation of bf16 products)
+    for s in range(S_eff):
+        k0, k1 = (s * kb // S_eff) * 64, min(((s + 1) * kb // S_eff) * 64, K)
+        ref = a[:, k0:k1].float() @ w[:, k0:k1].float().t()
+        err = (p[s] - ref).abs().max().item()
+        assert err < 2e-4 * max(1.0, ref.abs().max().item()), (s, err)
+    ref = a.float() @ w.float().t()
+    assert ((p.sum(0) - ref).norm() / ref.norm()).item() < 1e-5
+
+
+@pytest.mark.parametrize("resid_dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("w_dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,N,S", [(200, 1024, 16), (200, 1024, 7), (3, 64, 1), (40, 2048, 4)])
+def test_rmsnorm_reduce_matches_the_ledger(M, N, S, resid_dtype, w_dtype):
+    from cover_vla_b200 import ops
+    torch.manual_seed(M + N + S)
+    p = torch.randn(S, M, N, device="cuda", dtype=torch.float32)
+    resid = torch.randn(M, N, device="cuda").to(resid_dtype)
+    w = (0.1 * torch.randn(N, device="cuda")).to(w_dtype)
+    h, y = ops.rmsnorm_reduce(p, resid, w)
+    torch.cuda.synchronize()
+    acc = torch.zeros(M, N, device="cuda")
+    for s in range(S):  # split order, fp32
+        acc = acc + p[s]
+    h_ref = (acc.to(torch.bfloat16).float() + resid.float()).to(torch.bfloat16)
+    assert torch.equal(h, h_ref)
+    y_ref = _gemma_rmsnorm(h_ref, w)
+    # statistics are fp32 in both; the block reduction order differs from torch's -> allow one bf16 ulp
+    diff = (y.float() - y_ref.float()).abs()
+    assert (diff <= 2.0 ** -7 * y_ref.float().abs() + 1e-6).all()
+    assert (diff > 0).float().mean().item() < 0.02
+
+
+def test_pair_matches_fused_epilogue_gemm():
+    """o_proj/down_proj through partials + reduce == the EPI_RESID GEMM followed by rmsnorm, up to accumulation order."""
+    from cover_vla_b200 import ops
+    torch.manual_seed(3)
+    M, N, K = 200, 1024, 4096
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    resid = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+    g = (0.1 * torch.randn(N, device="cuda")).to(torch.bfloat16)
+    h_fused = ops.gemm_bf16(a, w, epilogue=ops.EPI_RESID, resid=resid, force_bn=64)
+    h, y = ops.rmsnorm_reduce(ops.gemm_splitk_partial(a, w, 16), resid, g)
+    torch.cuda.synchronize()
+    d = (h.float() - h_fused.float()).abs()
+    # <= 1 bf16 ulp of bf16(acc) (accumulation order differs), then <= 1 ulp of the rounded sum
+    mag = (h_fused.float() - resid.float()).abs() + h_fused.float().abs()
+    assert (d <= 2.0 ** -6 * mag + 1e-6).all()
+    assert (d > 0).float().mean().item() < 0.05
+    assert ((y.float() - _gemma_rmsnorm(h, g).float()).abs() <= 2.0 ** -7 * y.float().abs() + 1e-6).all()

@@ -82,4 +82,17 @@ int cvb_op_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k0, 
   return cvb::attention((cudaStream_t)stream, c);
 }
 
+int cvb_op_attention_umma(const void* q, int64_t q_ld, int64_t q_total_rows, int64_t q_rows_per_batch, const void* k,
+                          int64_t k_total_rows, int64_t k_rows_per_batch, const void* vt, int64_t vt_ld,
+                          const int32_t* klen_dev, int klen, int kmax, void* out, int64_t o_bs, int64_t o_rs, int batches,
+                          int tq, int heads, int head_dim, float scale, void* stream) {
+  cvb::UmmaAttnCall c;
+  c.q = (const cvb::bf16*)q, c.q_ld = q_ld, c.q_total_rows = q_total_rows, c.q_rows_per_batch = q_rows_per_batch;
+  c.k = (const cvb::bf16*)k, c.k_total_rows = k_total_rows, c.k_rows_per_batch = k_rows_per_batch;
+  c.vt = (const cvb::bf16*)vt, c.vt_ld = vt_ld, c.klen_dev = klen_dev, c.klen = klen, c.kmax = kmax;
+  c.out = (cvb::bf16*)out, c.o_batch_stride = o_bs, c.o_row_stride = o_rs;
+  c.batches = batches, c.tq = tq, c.heads = heads, c.head_dim = head_dim, c.scale = scale;
+  return cvb::attention_umma((cudaStream_t)stream, c);
+}
+
 }  // extern "C"

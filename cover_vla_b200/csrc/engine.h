@@ -111,6 +111,8 @@ struct Pi0State {
   bf16 *kcache = nullptr, *vcache = nullptr;
   float *state_emb = nullptr, *a1 = nullptr, *a2 = nullptr, *suffix = nullptr, *v0 = nullptr;
   bf16 *he = nullptr, *xe = nullptr, *qkv_e = nullptr, *attn_e = nullptr, *act_e = nullptr;
+  bf16* vt_p = nullptr;  // V^T of the current prefix layer: [max_rephrases][head_dim][vt_ld] (tcgen05 prefix attention)
+  long vt_ld = 0;
   float* part_e = nullptr;  // split-K partials of the expert's o_proj / down_proj: [kMaxSplitK][N*S][ex_width] fp32
   int splitk_o = 0, splitk_d = 0;  // K-splits of o_proj / down_proj in the denoise loop (0 = fused-epilogue GEMMs)
   int lang_hint = 0;  // caller's bound on valid language tokens per prompt (0 = max_lang_len), cvb_pi0_set_lang_len_hint

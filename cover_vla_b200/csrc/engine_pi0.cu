@@ -280,6 +280,9 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
   CVB_TRY(dalloc_t(h, &s.act_p, Mp * c.lm_mlp));
   CVB_TRY(dalloc_t(h, &s.kcache, (size_t)c.layers * Mp * c.head_dim));
   CVB_TRY(dalloc_t(h, &s.vcache, (size_t)c.layers * Mp * c.head_dim));
+  s.vt_ld = round_up(P, 64);
+  CVB_TRY(dalloc_t(h, &s.vt_p, (size_t)Rm * c.head_dim * s.vt_ld));
+  CVB_CUDA(cudaMemsetAsync(s.vt_p, 0, (size_t)Rm * c.head_dim * s.vt_ld * sizeof(bf16), st));  // padding keys stay finite
   const size_t Me = (size_t)Nm * S, Ma = (size_t)Nm * c.chunk_size;
   CVB_TRY(dalloc_t(h, &s.state_emb, We));
   CVB_TRY(dalloc_t(h, &s.a1, Ma * We));
@@ -365,17 +368,30 @@ static int run_prefix(cvb_handle* h, cudaStream_t st, int R) {
     bf16* vc = s.vcache + l * layer_stride;
     CVB_TRY(rmsnorm(st, s.hp, 0, D, L.in_norm, 0, s.xp, D, M, D, 1e-6f, nullptr));
     CVB_TRY(gemm(st, s.xp, D, L.wqkv, D, M, qkvw, D, EPI_STORE, s.qkv_p, qkvw));
-    CVB_TRY(rope_qkv(st, s.qkv_p, qkvw, s.rope_timescale, M, c.heads, hd, Pe, nullptr, 1, kc, vc,
-                     (long)P * hd, hd));
+    // tcgen05 attention (8 heads folded into UMMA rows, V^T written by the RoPE kernel) when the shape allows it
+    UmmaAttnCall u;
+    u.q = s.qkv_p, u.q_ld = qkvw, u.q_total_rows = M, u.q_rows_per_batch = Pe;
+    u.k = kc, u.k_total_rows = (long)c.max_rephrases * P, u.k_rows_per_batch = P;
+    u.vt = s.vt_p, u.vt_ld = s.vt_ld, u.klen_dev = s.plen, u.kmax = Pe;
+    u.out = s.attn_p, u.o_batch_stride = (long)Pe * qd, u.o_row_stride = qd;
+    u.batches = R, u.tq = Pe, u.heads = c.heads, u.head_dim = hd, u.scale = 1.0f / sqrtf(static_cast<float>(hd));
+    static const bool umma_off = getenv("CVB_NO_UMMA_ATTN") != nullptr;
+    const bool use_umma = !umma_off && l != c.layers - 1 && attention_umma_eligible(u);
+    CVB_TRY(rope_qkv(st, s.qkv_p, qkvw, s.rope_timescale, M, c.heads, hd, Pe, nullptr, 1, kc, vc, (long)P * hd, hd,
+                     use_umma ? s.vt_p : nullptr, (long)hd * s.vt_ld, s.vt_ld));
     if (l == c.layers - 1) break;  // only this layer's K/V are consumed (modeling_pi0.py:688-695)
-    AttnCall a;
-    a.q = s.qkv_p, a.q_batch_stride = (long)Pe * qkvw, a.q_row_stride = qkvw;
-    a.k0 = kc, a.v0 = vc, a.kv0_batch_stride = (long)P * hd, a.kv0_row_stride = hd;
-    a.kv0_len_dev = s.plen, a.kv0_max = Pe, a.q_per_kv_batch = 1;
-    a.out = s.attn_p, a.o_batch_stride = (long)Pe * qd, a.o_row_stride = qd;
-    a.batches = R, a.heads = c.heads, a.kv_heads = 1, a.tq = Pe, a.head_dim = hd;
-    a.scale = 1.0f / sqrtf(static_cast<float>(hd));
-    CVB_TRY(attention(st, a));
+    if (use_umma) {
+      CVB_TRY(attention_umma(st, u));
+    } else {
+      AttnCall a;
+      a.q = s.qkv_p, a.q_batch_stride = (long)Pe * qkvw, a.q_row_stride = qkvw;
+      a.k0 = kc, a.v0 = vc, a.kv0_batch_stride = (long)P * hd, a.kv0_row_stride = hd;
+      a.kv0_len_dev = s.plen, a.kv0_max = Pe, a.q_per_kv_batch = 1;
+      a.out = s.attn_p, a.o_batch_stride = (long)Pe * qd, a.o_row_stride = qd;
+      a.batches = R, a.heads = c.heads, a.kv_heads = 1, a.tq = Pe, a.head_dim = hd;
+      a.scale = 1.0f / sqrtf(static_cast<float>(hd));
+      CVB_TRY(attention(st, a));
+    }
     CVB_TRY(gemm(st, s.attn_p, qd, L.wo, qd, M, D, qd, EPI_RESID, s.hp, D, nullptr, s.hp, D));
     CVB_TRY(rmsnorm(st, s.hp, 0, D, L.post_norm, 0, s.xp, D, M, D, 1e-6f, nullptr));
     const int packed = ((c.lm_mlp + 127) / 128) * 256;

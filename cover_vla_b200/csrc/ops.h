@@ -105,4 +105,26 @@ struct AttnCall {
 };
 int attention(cudaStream_t st, const AttnCall& c);
 
+// ---- tcgen05 prefix attention (ops_attention_umma.cu): MQA, 8 query heads x head_dim 256, <= 384 keys ----------
+struct UmmaAttnCall {
+  // q rows: token (b * q_rows_per_batch + t) at q + row * q_ld, head h at column h * head_dim
+  const bf16* q = nullptr;
+  long q_ld = 0, q_total_rows = 0, q_rows_per_batch = 0;
+  // keys: [k_total_rows, head_dim] row-major, batch b starts at row b * k_rows_per_batch
+  const bf16* k = nullptr;
+  long k_total_rows = 0, k_rows_per_batch = 0;
+  // values TRANSPOSED: vt[(b * head_dim + d) * vt_ld + key]; columns >= the valid length must be finite
+  const bf16* vt = nullptr;
+  long vt_ld = 0;
+  const int* klen_dev = nullptr;  // [batches] valid keys (nullptr -> klen)
+  int klen = 0;
+  int kmax = 0;  // upper bound of the valid key count (the kernel processes round_up(kmax, 16) keys)
+  bf16* out = nullptr;  // out + b * o_batch_stride + t * o_row_stride + h * head_dim
+  long o_batch_stride = 0, o_row_stride = 0;
+  int batches = 0, tq = 0, heads = 0, head_dim = 0;
+  float scale = 1.f;
+};
+bool attention_umma_eligible(const UmmaAttnCall& c);
+int attention_umma(cudaStream_t st, const UmmaAttnCall& c);
+
 }  // namespace cvb

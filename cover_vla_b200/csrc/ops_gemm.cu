@@ -1,4 +1,5 @@
 // Host dispatch for the tcgen05 GEMM: tensor-map construction (cached), tile-shape heuristic, launch.
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -120,7 +121,10 @@ int gemm_bf16(cudaStream_t st, const GemmCall& c) {
     CVB_REQUIRE(c.N % 256 == 0, "EPI_GEGLU expects 256-row packed gate|up blocks");
     bn = 256;
   } else if (bn == 0) {
-    if (tiles(256) >= sms)
+    // a 256-wide tile does twice the math per shared-memory byte of a 128-wide one: prefer it as soon as it fills
+    // ~90% of one wave (e.g. the prefix o_proj / down_proj: 18 x 8 = 144 tiles on 148 SMs); CVB_GEMM_BN256_PCT overrides
+    static const int pct = getenv("CVB_GEMM_BN256_PCT") != nullptr ? atoi(getenv("CVB_GEMM_BN256_PCT")) : 90;
+    if (tiles(256) * 100 >= sms * pct)
       bn = 256;
     else if (tiles(128) >= sms)
       bn = 128;

@@ -94,7 +94,7 @@ int build_prefix(cudaStream_t st, const bf16* proj, const bf16* embed, const int
 __global__ void rope_kernel(bf16* __restrict__ qkv, long ld, const float* __restrict__ timescale,
                             int heads, int hd, int rows_per_batch, const int* __restrict__ pos_base_dev,
                             int q_per_kv_batch, bf16* __restrict__ kcache, bf16* __restrict__ vcache,
-                            long cache_bs, long cache_rs) {
+                            long cache_bs, long cache_rs, bf16* __restrict__ vt, long vt_bs, long vt_ld) {
   pdl_wait();
   pdl_launch();
   const int row = blockIdx.x;
@@ -140,18 +140,23 @@ __global__ void rope_kernel(bf16* __restrict__ qkv, long ld, const float* __rest
     for (int i = threadIdx.x * 8; i < hd; i += blockDim.x * 8)
       *reinterpret_cast<uint4*>(vc + i) = *reinterpret_cast<const uint4*>(vp + i);
   }
+  if (vt != nullptr) {  // V^T[b][d][t]: the K-major "B" operand of the tcgen05 P.V GEMM (ops_attention_umma.cu)
+    const bf16* vp = rp + (heads + 1) * hd;
+    bf16* vtp = vt + b * vt_bs + t;
+    for (int d = threadIdx.x; d < hd; d += blockDim.x) vtp[d * vt_ld] = vp[d];
+  }
 }
 
 int rope_qkv(cudaStream_t st, bf16* qkv, long ld, const float* timescale, int rows, int heads,
              int hd, int rows_per_batch, const int* pos_base_dev, int q_per_kv_batch, bf16* kcache,
-             bf16* vcache, long cache_bs, long cache_rs) {
+             bf16* vcache, long cache_bs, long cache_rs, bf16* vt, long vt_bs, long vt_ld) {
   CVB_REQUIRE(hd % 16 == 0, "head_dim must be a multiple of 16 for the vectorised RoPE");
   const int work = (heads + 1) * (hd / 16);
   int threads = ((work + 31) / 32) * 32;
   if (threads > 256) threads = 256;
   if (threads < 32) threads = 32;
   CVB_TRY(launch_pdl(rope_kernel, dim3(rows), dim3(threads), 0, st, 1, qkv, ld, timescale, heads, hd, rows_per_batch, pos_base_dev,
-                                        q_per_kv_batch, kcache, vcache, cache_bs, cache_rs));
+                                        q_per_kv_batch, kcache, vcache, cache_bs, cache_rs, vt, vt_bs, vt_ld));
   CVB_LAUNCHED();
   return 0;
 }

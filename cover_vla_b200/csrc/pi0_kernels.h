@@ -14,7 +14,7 @@ int build_prefix(cudaStream_t st, const bf16* proj, const bf16* embed, const int
                  bf16* prefix, int R, int n_img, int n_lang, int tok_stride, int D);
 int rope_qkv(cudaStream_t st, bf16* qkv, long ld, const float* timescale, int rows, int heads,
              int hd, int rows_per_batch, const int* pos_base_dev, int q_per_kv_batch, bf16* kcache,
-             bf16* vcache, long cache_bs, long cache_rs);
+             bf16* vcache, long cache_bs, long cache_rs, bf16* vt = nullptr, long vt_bs = 0, long vt_ld = 0);
 int action_out_euler(cudaStream_t st, const bf16* hn, long ld, const float* w, const float* bias,
                      float* x_t, float* v_out, int n_cand, int width, int adim, int chunk,
                      int suffix_len, float dt);

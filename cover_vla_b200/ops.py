@@ -92,6 +92,28 @@ def attention(q, k0, v0, *, heads, kv_heads, head_dim, kv0_len=None, kv0_len_dev
     return out
 
 
+def attention_umma(q, k, v, *, lens=None, kmax=None, scale=None):
+    """tcgen05 prefix attention: q [B, Tq, 8*256], k / v [B, Tk, 256] (bf16, CUDA); lens int32 [B] valid keys."""
+    lib = _lib.load()
+    B, Tq, qw = q.shape
+    Tk = k.shape[1]
+    hd, heads = 256, qw // 256
+    assert q.is_contiguous() and k.is_contiguous()
+    vt_ld = (Tk + 63) // 64 * 64
+    vt = torch.zeros(B, hd, vt_ld, device=q.device, dtype=torch.bfloat16)
+    vt[:, :, :Tk] = v.transpose(1, 2)
+    out = torch.empty(B, Tq, heads * hd, device=q.device, dtype=torch.bfloat16)
+    lib.cvb_op_attention_umma.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                          C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]
+    rc = lib.cvb_op_attention_umma(_lib.ptr(q), qw, B * Tq, Tq, _lib.ptr(k), B * Tk, Tk, _lib.ptr(vt), vt_ld,
+                                   _lib.ptr(lens), Tk, int(kmax if kmax is not None else Tk), _lib.ptr(out),
+                                   out.stride(0), out.stride(1), B, Tq, heads, hd,
+                                   float(scale if scale is not None else hd ** -0.5), _lib.stream_ptr())
+    _lib.check(rc)
+    return out
+
+
 SACT_NONE, SACT_RELU, SACT_GELU_ERF, SACT_SILU = range(4)
 
 

@@ -77,6 +77,17 @@ CVB_API int cvb_op_attention(const void* q, int64_t q_bs, int64_t q_rs, const vo
                              int heads, int kv_heads, int tq, int head_dim, float scale, int force_two_pass,
                              const float* rope_cos_sin, void* stream);
 
+/* tcgen05 / TMEM prefix attention (PaliGemma prefix pass, paligemma_with_expert.py:236-360, eager_attention_forward
+ * :376-434): multi-query, heads = 8, head_dim = 256, <= 384 keys, every query token of a batch attends the first
+ * klen_dev[b] (or klen) keys.  q: token (b * q_rows_per_batch + t) at q + row * q_ld, head h at column h * 256;
+ * k: [k_total_rows, 256] row-major, batch b from row b * k_rows_per_batch; vt = V transposed, vt[(b * 256 + d) * vt_ld +
+ * key] (columns past the valid length must be finite); out + b * o_bs + t * o_rs + h * 256.  Returns -1 (with
+ * cvb_last_error) for shapes outside these limits. */
+CVB_API int cvb_op_attention_umma(const void* q, int64_t q_ld, int64_t q_total_rows, int64_t q_rows_per_batch,
+                                  const void* k, int64_t k_total_rows, int64_t k_rows_per_batch, const void* vt,
+                                  int64_t vt_ld, const int32_t* klen_dev, int klen, int kmax, void* out, int64_t o_bs,
+                                  int64_t o_rs, int batches, int tq, int heads, int head_dim, float scale, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Engine level.  One handle per (device, stream); a handle is not thread-safe, the library is
  * re-entrant across handles.  All sizes are configuration, nothing is hard-coded to the Bridge

@@ -112,3 +112,34 @@ def test_denoise_attention_with_fused_rope(R, K, S, P, heads, hd, lens, algo):
         ref = _ref(qr[n:n + 1], kk, vv, heads, 1, hd, mask)
         err = (out[n:n + 1].float() - ref).abs().max().item()
         assert err < 2e-2, (n, err)
+
+
+@pytest.mark.parametrize("B,T", [(8, 280), (3, 300), (2, 100), (1, 16), (2, 37), (1, 320), (2, 257), (3, 328), (1, 384)])
+def test_prefix_attention_tcgen05(B, T):
+    """tcgen05/TMEM prefix attention (MQA 8 x 256, heads folded into UMMA rows) vs the eager ledger in fp32."""
+    from cover_vla_b200 import ops
+    torch.manual_seed(B * 100 + T)
+    heads, hd = 8, 256
+    q = torch.randn(B, T, heads * hd, device="cuda").to(torch.bfloat16)
+    k = torch.randn(B, T, hd, device="cuda").to(torch.bfloat16)
+    v = torch.randn(B, T, hd, device="cuda").to(torch.bfloat16)
+    lens = torch.randint(max(1, T // 2), T + 1, (B,), device="cuda", dtype=torch.int32)
+    lens[0] = T
+    out = ops.attention_umma(q, k, v, lens=lens)
+    torch.cuda.synchronize()
+    mask = (torch.arange(T, device="cuda")[None, :] < lens[:, None])[:, None, :].expand(B, T, T)
+    ref = _ref(q, k, v, heads, 1, hd, mask)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2, err
+    assert ((out.float() - ref).norm() / ref.norm()).item() < 5e-3
+    # and against the mma.sync kernel it replaces (same ledger, different accumulation order / exp implementation)
+    old = ops.attention(q, k, v, heads=heads, kv_heads=1, head_dim=hd, kv0_len_dev=lens)
+    assert (out.float() - old.float()).abs().max().item() < 2e-2
+
+
+def test_prefix_attention_tcgen05_rejects_unsupported_shapes():
+    from cover_vla_b200 import ops, _lib
+    q = torch.randn(1, 392, 8 * 256, device="cuda").to(torch.bfloat16)
+    k = torch.randn(1, 392, 256, device="cuda").to(torch.bfloat16)
+    with pytest.raises(_lib.CvbError):
+        ops.attention_umma(q, k, k)

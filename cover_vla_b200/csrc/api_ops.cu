@@ -63,11 +63,12 @@ int cvb_op_sgemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, i
   return cvb::sgemm_f32((cudaStream_t)stream, c);
 }
 
-int cvb_op_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k0, const void* v0, int64_t kv0_bs,
-                     int64_t kv0_rs, const int32_t* kv0_len_dev, int kv0_len, int kv0_max, int q_per_kv_batch,
-                     const void* k1, const void* v1, int64_t kv1_bs, int64_t kv1_rs, int kv1_len, int suffix_mask,
-                     void* out, int64_t o_bs, int64_t o_rs, int batches, int heads, int kv_heads, int tq,
-                     int head_dim, float scale, int force_two_pass, const float* rope_cos_sin, void* stream) {
+int cvb_op_attention_tc(const void* q, int64_t q_bs, int64_t q_rs, const void* k0, const void* v0, int64_t kv0_bs,
+                        int64_t kv0_rs, const int32_t* kv0_len_dev, int kv0_len, int kv0_max, int q_per_kv_batch,
+                        const void* k1, const void* v1, int64_t kv1_bs, int64_t kv1_rs, int kv1_len, int suffix_mask,
+                        void* out, int64_t o_bs, int64_t o_rs, int batches, int heads, int kv_heads, int tq,
+                        int head_dim, float scale, int force_two_pass, const float* rope_cos_sin, const void* vt0,
+                        int64_t vt0_ld, void* stream) {
   cvb::AttnCall c;
   c.q = (const cvb::bf16*)q, c.q_batch_stride = q_bs, c.q_row_stride = q_rs;
   c.k0 = (const cvb::bf16*)k0, c.v0 = (const cvb::bf16*)v0, c.kv0_batch_stride = kv0_bs, c.kv0_row_stride = kv0_rs;
@@ -77,9 +78,20 @@ int cvb_op_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k0, 
   c.out = (cvb::bf16*)out, c.o_batch_stride = o_bs, c.o_row_stride = o_rs;
   c.batches = batches, c.heads = heads, c.kv_heads = kv_heads, c.tq = tq, c.head_dim = head_dim, c.scale = scale;
   c.force_two_pass = force_two_pass == 1;
-  c.algo = force_two_pass == 2 ? 1 : force_two_pass == 3 ? 2 : 0;
+  c.algo = force_two_pass == 2 ? 1 : force_two_pass == 3 ? 2 : force_two_pass == 4 ? 3 : 0;
   c.rope = reinterpret_cast<const float2*>(rope_cos_sin);
+  c.vt0 = (const cvb::bf16*)vt0, c.vt0_ld = vt0_ld;
   return cvb::attention((cudaStream_t)stream, c);
+}
+
+int cvb_op_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k0, const void* v0, int64_t kv0_bs,
+                     int64_t kv0_rs, const int32_t* kv0_len_dev, int kv0_len, int kv0_max, int q_per_kv_batch,
+                     const void* k1, const void* v1, int64_t kv1_bs, int64_t kv1_rs, int kv1_len, int suffix_mask,
+                     void* out, int64_t o_bs, int64_t o_rs, int batches, int heads, int kv_heads, int tq,
+                     int head_dim, float scale, int force_two_pass, const float* rope_cos_sin, void* stream) {
+  return cvb_op_attention_tc(q, q_bs, q_rs, k0, v0, kv0_bs, kv0_rs, kv0_len_dev, kv0_len, kv0_max, q_per_kv_batch, k1,
+                             v1, kv1_bs, kv1_rs, kv1_len, suffix_mask, out, o_bs, o_rs, batches, heads, kv_heads, tq,
+                             head_dim, scale, force_two_pass, rope_cos_sin, nullptr, 0, stream);
 }
 
 int cvb_op_attention_umma(const void* q, int64_t q_ld, int64_t q_total_rows, int64_t q_rows_per_batch, const void* k,

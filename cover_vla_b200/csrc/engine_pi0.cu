@@ -17,6 +17,7 @@ namespace cvb {
 
 bool attention_decode_eligible(const AttnCall& c);
 bool attention_group_eligible(const AttnCall& c);
+bool attention_decode_umma_eligible(const AttnCall& c);
 
 namespace {
 
@@ -281,8 +282,9 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
   CVB_TRY(dalloc_t(h, &s.kcache, (size_t)c.layers * Mp * c.head_dim));
   CVB_TRY(dalloc_t(h, &s.vcache, (size_t)c.layers * Mp * c.head_dim));
   s.vt_ld = round_up(P, 64);
-  CVB_TRY(dalloc_t(h, &s.vt_p, (size_t)Rm * c.head_dim * s.vt_ld));
-  CVB_CUDA(cudaMemsetAsync(s.vt_p, 0, (size_t)Rm * c.head_dim * s.vt_ld * sizeof(bf16), st));  // padding keys stay finite
+  // transposed V cache [layer][rephrase][head_dim][vt_ld]: the K-major "B" operand of the tcgen05 P.V GEMMs
+  CVB_TRY(dalloc_t(h, &s.vt_p, (size_t)c.layers * Rm * c.head_dim * s.vt_ld));
+  CVB_CUDA(cudaMemsetAsync(s.vt_p, 0, (size_t)c.layers * Rm * c.head_dim * s.vt_ld * sizeof(bf16), st));  // padding keys stay finite
   const size_t Me = (size_t)Nm * S, Ma = (size_t)Nm * c.chunk_size;
   CVB_TRY(dalloc_t(h, &s.state_emb, We));
   CVB_TRY(dalloc_t(h, &s.a1, Ma * We));
@@ -372,13 +374,15 @@ static int run_prefix(cvb_handle* h, cudaStream_t st, int R) {
     UmmaAttnCall u;
     u.q = s.qkv_p, u.q_ld = qkvw, u.q_total_rows = M, u.q_rows_per_batch = Pe;
     u.k = kc, u.k_total_rows = (long)c.max_rephrases * P, u.k_rows_per_batch = P;
-    u.vt = s.vt_p, u.vt_ld = s.vt_ld, u.klen_dev = s.plen, u.kmax = Pe;
+    bf16* vt = s.vt_p + (size_t)l * c.max_rephrases * hd * s.vt_ld;
+    u.vt = vt, u.vt_ld = s.vt_ld, u.klen_dev = s.plen, u.kmax = Pe;
     u.out = s.attn_p, u.o_batch_stride = (long)Pe * qd, u.o_row_stride = qd;
     u.batches = R, u.tq = Pe, u.heads = c.heads, u.head_dim = hd, u.scale = 1.0f / sqrtf(static_cast<float>(hd));
     static const bool umma_off = getenv("CVB_NO_UMMA_ATTN") != nullptr;
-    const bool use_umma = !umma_off && l != c.layers - 1 && attention_umma_eligible(u);
+    const bool use_umma = !umma_off && attention_umma_eligible(u);
+    // V^T is written for every layer (the last one included: the denoise attention reads all 18 caches)
     CVB_TRY(rope_qkv(st, s.qkv_p, qkvw, s.rope_timescale, M, c.heads, hd, Pe, nullptr, 1, kc, vc, (long)P * hd, hd,
-                     use_umma ? s.vt_p : nullptr, (long)hd * s.vt_ld, s.vt_ld));
+                     umma_off ? nullptr : vt, (long)hd * s.vt_ld, s.vt_ld));
     if (l == c.layers - 1) break;  // only this layer's K/V are consumed (modeling_pi0.py:688-695)
     if (use_umma) {
       CVB_TRY(attention_umma(st, u));
@@ -435,7 +439,9 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
   probe.k1 = s.qkv_e, probe.kv1_len = S, probe.kv0_len_dev = s.plen, probe.kv0_max = h->n_img() + h->lang_rows();
   probe.heads = c.heads, probe.kv_heads = 1, probe.tq = S, probe.head_dim = hd;
   probe.q_per_kv_batch = K, probe.batches = N;
-  const bool fused_rope = attention_group_eligible(probe) || attention_decode_eligible(probe);
+  probe.kv0_row_stride = hd, probe.kv0_batch_stride = (long)P * hd, probe.vt0 = getenv("CVB_NO_UMMA_ATTN") == nullptr ? s.vt_p : nullptr, probe.vt0_ld = s.vt_ld;
+  const bool fused_rope = attention_group_eligible(probe) || attention_decode_eligible(probe) ||
+                          attention_decode_umma_eligible(probe);
   if (fused_rope) CVB_TRY(rope_table(st, s.rope_timescale, s.plen, R, S, hd / 2, s.rope_tab));
   for (size_t step = 0; step < s.times.size(); ++step) {
     {  // embed_suffix (modeling_pi0.py:598-609), time half of mlp_in folded into time_vec[step]
@@ -479,6 +485,7 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
       a.k0 = s.kcache + l * layer_stride, a.v0 = s.vcache + l * layer_stride;
       a.kv0_batch_stride = (long)P * hd, a.kv0_row_stride = hd, a.kv0_len_dev = s.plen, a.kv0_max = h->n_img() + h->lang_rows();
       a.q_per_kv_batch = K;
+      if (getenv("CVB_NO_UMMA_ATTN") == nullptr) a.vt0 = s.vt_p + (size_t)l * c.max_rephrases * hd * s.vt_ld, a.vt0_ld = s.vt_ld;
       a.k1 = s.qkv_e + qd, a.v1 = s.qkv_e + qd + hd, a.kv1_batch_stride = (long)S * qkvw;
       a.kv1_row_stride = qkvw, a.kv1_len = S, a.suffix_mask = 1;
       a.out = s.attn_e, a.o_batch_stride = (long)S * qd, a.o_row_stride = qd;

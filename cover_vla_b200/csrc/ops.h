@@ -101,7 +101,11 @@ struct AttnCall {
   // segment 0 (and kv0_len_dev) is NOT written by the kernel launched just before this one: its tiles may be
   // prefetched before the programmatic-dependency wait (the prefix KV cache during the denoise loop)
   int kv0_static = 0;
-  int algo = 0;  // two-segment calls: 0 auto, 1 rephrase-grouped kernel only, 2 cluster decode kernel only
+  int algo = 0;  // two-segment calls: 0 auto, 1 rephrase-grouped kernel only, 2 cluster decode kernel only, 3 tcgen05 only
+  // optional TRANSPOSED copy of segment-0 values, vt0[(kv batch * head_dim + d) * vt0_ld + key] (finite past the valid
+  // length): enables the tcgen05 decode kernel (ops_attention_umma.cu) for MQA / head_dim 256 shapes
+  const bf16* vt0 = nullptr;
+  long vt0_ld = 0;
 };
 int attention(cudaStream_t st, const AttnCall& c);
 

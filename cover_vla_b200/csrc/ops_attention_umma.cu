@@ -29,9 +29,12 @@ int get_tmap_cached(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, 
 int make_tmap_3d_heads(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t heads, uint64_t hd, uint64_t ld,
                        uint32_t box_rows);
 
+extern unsigned long long* g_skinny_ts;
+
 namespace {
 
-constexpr int UA_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: softmax / epilogue
+constexpr int UA_THREADS = 320;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..9: softmax / epilogue
+constexpr int UA_SOFT = 256;     // two warps per TMEM lane quarter, even / odd 16-column chunks
 constexpr int UA_HD = 256;
 constexpr int UA_TOK = 16;     // query tokens per CTA
 constexpr int UA_HEADS = 8;    // query heads folded into rows: 16 x 8 = 128 UMMA rows
@@ -40,7 +43,7 @@ constexpr int UA_VBLK = UA_HD * 128;    // one key-block of V^T: 256 rows x 64 k
 constexpr int UA_PBLK = 128 * 128;      // one key-block of P: 128 rows x 64 keys
 constexpr int UA_VSLOTS = 4;
 constexpr int UA_MAX_KEYS = 384;
-constexpr int UA_BODY_MAX = 224 * 1024;  // operand bytes per CTA (barriers and the alignment slack come on top)
+constexpr int UA_BODY_MAX = 222 * 1024;  // operand bytes per CTA (barriers and the alignment slack come on top)
 
 struct UmmaAttnParams {
   const int* klen_dev;
@@ -60,6 +63,59 @@ __device__ __forceinline__ uint32_t make_idesc_n(int n) {  // bf16 x bf16 -> fp3
 
 __device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// Softmax building blocks on one 16-column chunk of a TMEM row whose first nv (1..16) columns are valid keys.
+// exp(x * scale - m * scale) is evaluated as 2^(x * c2 - m * c2), c2 = scale * log2(e): one FFMA + one ex2 per element.
+// (1) online update of the running (raw max, sum of exponentials relative to it)
+__device__ __forceinline__ void online_chunk(const uint32_t (&rr)[16], int nv, float c2, float& m, float& l) {
+  float cm = -INFINITY;
+  if (nv == 16) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) cm = fmaxf(cm, __uint_as_float(rr[i]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nv) cm = fmaxf(cm, __uint_as_float(rr[i]));
+  }
+  const float mn = fmaxf(m, cm);
+  const float mc = mn * c2;
+  float acc = 0.f;
+  if (nv == 16) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc += ex2_approx(fmaf(__uint_as_float(rr[i]), c2, -mc));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nv) acc += ex2_approx(fmaf(__uint_as_float(rr[i]), c2, -mc));
+  }
+  l = l * ex2_approx((m - mn) * c2) + acc;  // first chunk: m = -inf -> factor 0
+  m = mn;
+}
+// (2) normalised probabilities, rounded to bf16 and packed in key order (invalid columns -> 0)
+__device__ __forceinline__ void prob_chunk(const uint32_t (&rr)[16], int nv, float c2, float Mc, float inv, uint32_t (&pk)[8]) {
+  if (nv == 16) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      pk[i] = pack_bf16x2(ex2_approx(fmaf(__uint_as_float(rr[2 * i]), c2, -Mc)) * inv,
+                          ex2_approx(fmaf(__uint_as_float(rr[2 * i + 1]), c2, -Mc)) * inv);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a = 2 * i < nv ? ex2_approx(fmaf(__uint_as_float(rr[2 * i]), c2, -Mc)) * inv : 0.f;
+      const float bb = 2 * i + 1 < nv ? ex2_approx(fmaf(__uint_as_float(rr[2 * i + 1]), c2, -Mc)) * inv : 0.f;
+      pk[i] = pack_bf16x2(a, bb);
+    }
+  }
 }
 
 // r[0..31] <- 32 (or 16) consecutive fp32 columns of this thread's TMEM lane
@@ -85,7 +141,7 @@ attn_prefix_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const int tk_pad = p.tk_pad;
   const uint32_t kblk = static_cast<uint32_t>(tk_pad) * 128u;  // one hd-block of K: tk_pad rows x 64 bf16
   const int nkb = (tk_pad + 63) / 64;                          // key blocks of P / V^T
-  const int nslots = min(nkb, UA_VSLOTS);
+  const int nslots = min(min(nkb, UA_VSLOTS), (UA_BODY_MAX - nkb * UA_PBLK) / UA_VBLK);
   // all four hd-blocks of K stay resident when they fit; otherwise the last one reuses the slot of the first once its
   // MMAs have retired (only for > 320 keys)
   const int kslots = 4u * UA_QBLK + 4u * kblk <= static_cast<uint32_t>(UA_BODY_MAX) ? 4 : 3;
@@ -104,6 +160,7 @@ attn_prefix_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* o_full = v_empty + UA_VSLOTS;
   uint64_t* k0_free = o_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k0_free + 1);
+  float2* red2 = reinterpret_cast<float2*>(k0_free + 3);  // [2][128] (max, sum) of the two column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, b = blockIdx.y;
@@ -117,7 +174,7 @@ attn_prefix_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     if (lane == 0) {
       for (int c = 0; c < 4; ++c) mbar_init(&qk_full[c], 1);
       mbar_init(s_full, 1);
-      mbar_init(p_ready, 128);
+      mbar_init(p_ready, UA_SOFT);
       for (int s = 0; s < UA_VSLOTS; ++s) {
         mbar_init(&v_full[s], 1);
         mbar_init(&v_empty[s], 1);
@@ -154,8 +211,8 @@ attn_prefix_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
       mbar_wait(s_full, 0);  // every Q.K^T MMA has retired: Q / K are dead, V^T may land on top of K
       for (int kb = 0; kb < nkb; ++kb) {
-        const int slot = kb % UA_VSLOTS;
-        if (kb >= UA_VSLOTS) mbar_wait(&v_empty[slot], ((kb / UA_VSLOTS) - 1) & 1);
+        const int slot = kb % nslots;
+        if (kb >= nslots) mbar_wait(&v_empty[slot], ((kb / nslots) - 1) & 1);
         mbar_arrive_expect_tx(&v_full[slot], UA_VBLK);
         tma_load_2d(sV + slot * UA_VBLK, &tmVT, &v_full[slot], kb * 64, b * UA_HD);
       }
@@ -185,8 +242,8 @@ attn_prefix_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       tc_fence_after();
       const uint32_t idesc_o = make_idesc_n(UA_HD);
       for (int kb = 0; kb < nkb; ++kb) {
-        const int slot = kb % UA_VSLOTS;
-        mbar_wait(&v_full[slot], (kb / UA_VSLOTS) & 1);
+        const int slot = kb % nslots;
+        mbar_wait(&v_full[slot], (kb / nslots) & 1);
         tc_fence_after();
         const uint64_t pd = make_desc_kmajor_sw128(smem_u32(sP + kb * UA_PBLK));
         const uint64_t vd = make_desc_kmajor_sw128(smem_u32(sV + slot * UA_VBLK));
@@ -198,58 +255,53 @@ attn_prefix_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ softmax + epilogue: one row per thread
+    // ------------------------------------------------------------------ softmax + epilogue
+    // Row = TMEM lane; the two warps of a lane quarter take the even / odd 16-column chunks (a fixed assignment, so the
+    // result does not depend on how far the key range is padded).
     pdl_wait();
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int tl = row >> 3, h = row & 7;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     int n_keys = p.klen_dev != nullptr ? p.klen_dev[b] : p.klen;
     n_keys = max(1, min(n_keys, tk_pad));
+    const float c2 = p.scale * 1.4426950408889634f;
     mbar_wait(s_full, 0);
     tc_fence_after();
-    float m = -INFINITY;
-    for (int c0 = 0; c0 < n_keys; c0 += 32) {
-      uint32_t r[32];
-      ld_cols(taddr + c0, c0 + 32 <= tk_pad, r);
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (c0 + i < n_keys) m = fmaxf(m, __uint_as_float(r[i]) * p.scale);
+    float m = -INFINITY, l = 0.f;
+    for (int ch = half; ch * 16 < n_keys; ch += 2) {
+      uint32_t rr[16];
+      tmem_ld_x16(taddr + ch * 16, rr);
+      tmem_wait_ld();
+      online_chunk(rr, min(16, n_keys - ch * 16), c2, m, l);
     }
-    float l = 0.f;
-    for (int c0 = 0; c0 < n_keys; c0 += 32) {
-      uint32_t r[32];
-      ld_cols(taddr + c0, c0 + 32 <= tk_pad, r);
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (c0 + i < n_keys) l += __expf(__uint_as_float(r[i]) * p.scale - m);
-    }
-    const float inv = 1.0f / l;
+    red2[half * 128 + row] = make_float2(m, l);
+    named_bar(1, UA_SOFT);
+    const float2 s0 = red2[row], s1 = red2[128 + row];
+    const float M = fmaxf(s0.x, s1.x);
+    const float Mc = M * c2;
+    const float Ls = s0.y * ex2_approx((s0.x - M) * c2) + s1.y * ex2_approx((s1.x - M) * c2);  // an empty half has (-inf, 0)
+    const float inv = 1.0f / Ls;
     // P[row][key] -> canonical K-major SWIZZLE_128B tile: 8-row groups of 1024 B, 16-byte chunk index XOR (row % 8)
     const uint32_t p_row = smem_u32(sP) + static_cast<uint32_t>(row >> 3) * 1024u + static_cast<uint32_t>(row & 7) * 128u;
-    for (int c0 = 0; c0 < tk_pad; c0 += 32) {
-      const bool wide = c0 + 32 <= tk_pad;
-      uint32_t r[32];
-      if (c0 < n_keys) {
-        ld_cols(taddr + c0, wide, r);
+    for (int ch = half; ch * 16 < tk_pad; ch += 2) {
+      const int nv = max(0, min(16, n_keys - ch * 16));
+      uint32_t pk[8];
+      if (nv > 0) {  // warp-uniform
+        uint32_t rr[16];
+        tmem_ld_x16(taddr + ch * 16, rr);
+        tmem_wait_ld();
+        prob_chunk(rr, nv, c2, Mc, inv, pk);
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = 0u;
+        for (int i = 0; i < 8; ++i) pk[i] = 0u;
       }
-      uint32_t pk[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float a = c0 + 2 * i < n_keys ? __expf(__uint_as_float(r[2 * i]) * p.scale - m) * inv : 0.f;
-        const float bb = c0 + 2 * i + 1 < n_keys ? __expf(__uint_as_float(r[2 * i + 1]) * p.scale - m) * inv : 0.f;
-        pk[i] = pack_bf16x2(a, bb);
-      }
+      const int c0 = ch * 16;
       const uint32_t blk = p_row + static_cast<uint32_t>(c0 >> 6) * UA_PBLK;
-      const int ch0 = (c0 & 63) >> 3;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j < 2 || wide)
-          sts_u4(blk + (static_cast<uint32_t>((ch0 + j) ^ (row & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-      }
+      const int chunk = (c0 & 63) >> 3;
+      sts_u4(blk + (static_cast<uint32_t>(chunk ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+      sts_u4(blk + (static_cast<uint32_t>((chunk + 1) ^ (row & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
     }
     fence_proxy_async();  // generic-proxy writes of P -> visible to the tensor core's async-proxy reads
     tc_fence_before();
@@ -258,10 +310,10 @@ attn_prefix_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     mbar_wait(o_full, 0);
     tc_fence_after();
     const int t = tile * UA_TOK + tl;
-    bf16* op = p.out + b * p.o_bs + static_cast<long>(t) * p.o_rs + h * UA_HD;
-    for (int c0 = 0; c0 < UA_HD; c0 += 32) {
+    bf16* op = p.out + b * p.o_bs + static_cast<long>(t) * p.o_rs + h * UA_HD + half * 128;
+    for (int c0 = 0; c0 < 128; c0 += 32) {
       uint32_t r[32];
-      tmem_ld_x32(taddr + c0, r);
+      tmem_ld_x32(taddr + half * 128 + c0, r);
       tmem_wait_ld();
       if (t < p.tq) {
 #pragma unroll
@@ -273,6 +325,390 @@ attn_prefix_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         }
       }
     }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Denoise-step attention on tcgen05 (PI0FlowMatching.denoise_step, modeling_pi0.py:717-752 -> eager_attention_forward,
+// paligemma_with_expert.py:376-434): one CTA per candidate, its heads x suffix-token query rows (8 x 5 = 40) attend the
+// rephrase's prefix KV cache (<= 336 keys, static during the loop: K tiles are prefetched by TMA BEFORE the
+// programmatic-dependency wait) plus the candidate's own suffix keys (pi0 suffix mask).
+//   * Q rows and the suffix keys are loaded from the fused qkv buffer, rotated (RoPE table, same arithmetic as
+//     rope_kernel) and written straight into K-major 128-byte-swizzled UMMA tiles; query row r sits in TMEM lane
+//     (r % 4) * 32 + r / 4 so that all four lane quarters - and therefore 16 softmax warps - share the rows;
+//   * S = Q K^T: tcgen05.mma N = 256 + remainder (prefix keys) and N = 16 (suffix keys) into one TMEM accumulator;
+//   * exact softmax (global max / sum over all keys, probabilities normalised THEN rounded to bf16) by 4 warps per
+//     lane quarter, 1/4 of the columns each, combined through shared memory in fixed order (deterministic);
+//   * O = P V for the prefix keys on tcgen05 with V^T tiles (transposed cache written by the prefix RoPE kernel); the
+//     <= 8 suffix keys are added in fp32 by the epilogue threads (5 x 256 MACs per row - not worth a tile).
+// Replaces the cluster split-KV mma.sync kernel (ops_attention_decode.cu: 20 us, bound by the mma.sync issue rate and
+// the DSMEM reduce-scatter; tools/decode_ts.py).
+constexpr int UD_THREADS = 576;   // warp 0 TMA, warp 1 MMA, warps 2..17 staging / softmax / epilogue
+constexpr int UD_SOFT = 512;
+constexpr int UD_KSBLK = 16 * 128;  // suffix-key tile of one hd-block: 16 rows x 64 bf16
+constexpr int UD_MISC = 10 * 1024;  // red2[4][128] (max, sum) | psuf[128][8] bf16 | v1[8][256] bf16
+constexpr int UD_OS_LD = 260;       // fp32 row stride of the output staging tile (bank spread, 16-byte aligned)
+__host__ __device__ inline int ud_misc_off(int nkb, int vslots, int rows_total) {
+  const int pv = nkb * UA_PBLK + vslots * UA_VBLK;
+  const int os = (rows_total * UD_OS_LD * 4 + 1023) / 1024 * 1024;
+  return pv > os ? pv : os;
+}
+
+struct UmmaDecodeParams {
+  const bf16* q;
+  long q_bs, q_rs;
+  const int* kv0_len_dev;
+  int kv0_len;
+  int q_per_kv_batch;
+  long k_rows_per_batch;
+  const bf16* k1;
+  const bf16* v1;
+  long kv1_bs, kv1_rs;
+  int kv1_len;
+  int suffix_mask;
+  bf16* out;
+  long o_bs, o_rs;
+  int heads, tq, tk_pad;
+  float scale;
+  int kv0_static;
+  const float2* rope;  // [kv batches][tq][128] (cos, sin) or nullptr
+  unsigned long long* ts;  // diagnostics (cvb_debug_set_timestamps) or nullptr
+};
+
+__device__ __forceinline__ unsigned long long ud_timer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define UD_TS(i)                                                                            \
+  do {                                                                                      \
+    if (p.ts != nullptr && threadIdx.x == 64) p.ts[blockIdx.x * 8 + (i)] = ud_timer();       \
+  } while (0)
+
+// rotate 8 (x1, x2) pairs exactly like rope_kernel / the cluster decode kernel (separate mul / add, no contraction)
+__device__ __forceinline__ void rope8_umma(uint4& v1, uint4& v2, const float2* cs) {
+  uint32_t u1[4] = {v1.x, v1.y, v1.z, v1.w}, u2[4] = {v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 a = unpack_bf16x2(u1[e]), b = unpack_bf16x2(u2[e]);
+    const float2 t0 = cs[2 * e], t1 = cs[2 * e + 1];
+    u1[e] = pack_bf16x2(__fsub_rn(__fmul_rn(a.x, t0.x), __fmul_rn(b.x, t0.y)),
+                        __fsub_rn(__fmul_rn(a.y, t1.x), __fmul_rn(b.y, t1.y)));
+    u2[e] = pack_bf16x2(__fadd_rn(__fmul_rn(b.x, t0.x), __fmul_rn(a.x, t0.y)),
+                        __fadd_rn(__fmul_rn(b.y, t1.x), __fmul_rn(a.y, t1.y)));
+  }
+  v1 = make_uint4(u1[0], u1[1], u1[2], u1[3]);
+  v2 = make_uint4(u2[0], u2[1], u2[2], u2[3]);
+}
+
+__global__ void __launch_bounds__(UD_THREADS, 1)
+attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmVT,
+                        const UmmaDecodeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int tk_pad = p.tk_pad;
+  const int KT = tk_pad + 16;  // S columns: prefix keys, then the 16-wide suffix-key tile
+  const uint32_t kblk = static_cast<uint32_t>(tk_pad) * 128u;
+  const int nkb = (tk_pad + 63) / 64;
+  const int kslots = 4u * UA_QBLK + 4u * UD_KSBLK + 4u * kblk <= static_cast<uint32_t>(UA_BODY_MAX) ? 4 : 3;
+  const int vslots = min(nkb, (UA_BODY_MAX - UD_MISC - nkb * UA_PBLK) / UA_VBLK);
+  const uint32_t qk_bytes = 4u * UA_QBLK + 4u * UD_KSBLK + static_cast<uint32_t>(kslots) * kblk;
+  const int rows_total = p.heads * p.tq;
+  const uint32_t misc_off = static_cast<uint32_t>(ud_misc_off(nkb, vslots, rows_total));
+  const uint32_t body = max(qk_bytes, misc_off + UD_MISC);
+  uint8_t* sQ = smem;
+  uint8_t* sKs = smem + 4 * UA_QBLK;
+  uint8_t* sK = sKs + 4 * UD_KSBLK;
+  uint8_t* sP = smem;
+  uint8_t* sV = smem + static_cast<uint32_t>(nkb) * UA_PBLK;
+  uint8_t* misc = smem + misc_off;
+  float2* red2 = reinterpret_cast<float2*>(misc);              // [4][128] (max, sum) per column group
+  bf16* psuf = reinterpret_cast<bf16*>(misc + 4096);           // [128][8]
+  bf16* sV1 = reinterpret_cast<bf16*>(misc + 6144);            // [8][256]
+  uint64_t* k_full = reinterpret_cast<uint64_t*>(smem + body);
+  uint64_t* q_ready = k_full + 4;
+  uint64_t* s_full = q_ready + 1;
+  uint64_t* p_ready = s_full + 1;
+  uint64_t* v_full = p_ready + 1;
+  uint64_t* v_empty = v_full + UA_VSLOTS;
+  uint64_t* o_full = v_empty + UA_VSLOTS;
+  uint64_t* k0_free = o_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k0_free + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  const int kvb = b / p.q_per_kv_batch;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmVT);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int c = 0; c < 4; ++c) mbar_init(&k_full[c], 1);
+      mbar_init(q_ready, UD_SOFT);
+      mbar_init(s_full, 1);
+      mbar_init(p_ready, UD_SOFT);
+      for (int s = 0; s < UA_VSLOTS; ++s) {
+        mbar_init(&v_full[s], 1);
+        mbar_init(&v_empty[s], 1);
+      }
+      mbar_init(o_full, 1);
+      mbar_init(k0_free, 1);
+      fence_barrier_init();
+      fence_proxy_async();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      if (!p.kv0_static) pdl_wait();
+      const int k_row0 = static_cast<int>(kvb * p.k_rows_per_batch);
+      const int half_rows = tk_pad / 2;
+      for (int c = 0; c < 4; ++c) {
+        uint8_t* kdst = sK + (c % kslots) * kblk;
+        if (c >= kslots) mbar_wait(k0_free, 0);
+        mbar_arrive_expect_tx(&k_full[c], kblk);
+        tma_load_2d_hint(kdst, &tmK, &k_full[c], c * 64, k_row0, kEvictLast);
+        tma_load_2d_hint(kdst + static_cast<uint32_t>(half_rows) * 128u, &tmK, &k_full[c], c * 64, k_row0 + half_rows, kEvictLast);
+      }
+      mbar_wait(s_full, 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int slot = kb % vslots;
+        if (kb >= vslots) mbar_wait(&v_empty[slot], ((kb / vslots) - 1) & 1);
+        mbar_arrive_expect_tx(&v_full[slot], UA_VBLK);
+        tma_load_2d_hint(sV + slot * UA_VBLK, &tmVT, &v_full[slot], kb * 64, kvb * UA_HD, kEvictLast);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const int n1 = min(tk_pad, 256), n2 = tk_pad - n1;
+      const uint32_t idesc1 = make_idesc_n(n1), idesc2 = make_idesc_n(n2), idesc3 = make_idesc_n(16);
+      mbar_wait(q_ready, 0);
+      tc_fence_after();
+      for (int c = 0; c < 4; ++c) {
+        mbar_wait(&k_full[c], 0);
+        tc_fence_after();
+        const uint64_t qd = make_desc_kmajor_sw128(smem_u32(sQ + c * UA_QBLK));
+        const uint32_t k_addr = smem_u32(sK + (c % kslots) * kblk);
+        const uint64_t kd = make_desc_kmajor_sw128(k_addr);
+        const uint64_t kd2 = make_desc_kmajor_sw128(k_addr + 256u * 128u);
+        const uint64_t ksd = make_desc_kmajor_sw128(smem_u32(sKs + c * UD_KSBLK));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t acc = (c | k) != 0 ? 1u : 0u;
+          umma_bf16(tmem_base, qd + 2 * k, kd + 2 * k, idesc1, acc);
+          if (n2 > 0) umma_bf16(tmem_base + 256, qd + 2 * k, kd2 + 2 * k, idesc2, acc);
+          umma_bf16(tmem_base + tk_pad, qd + 2 * k, ksd + 2 * k, idesc3, acc);
+        }
+        if (c == 0 && kslots < 4) umma_commit(k0_free);
+      }
+      umma_commit(s_full);
+      mbar_wait(p_ready, 0);
+      tc_fence_after();
+      const uint32_t idesc_o = make_idesc_n(UA_HD);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int slot = kb % vslots;
+        mbar_wait(&v_full[slot], (kb / vslots) & 1);
+        tc_fence_after();
+        const uint64_t pd = make_desc_kmajor_sw128(smem_u32(sP + kb * UA_PBLK));
+        const uint64_t vd = make_desc_kmajor_sw128(smem_u32(sV + slot * UA_VBLK));
+        const int ksteps = min(4, (tk_pad - kb * 64) / 16);
+        for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_base, pd + 2 * k, vd + 2 * k, idesc_o, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(&v_empty[slot]);
+      }
+      umma_commit(o_full);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ staging, softmax, epilogue (512 threads)
+    const int sid = threadIdx.x - 64;
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int g = (warp - 2) >> 2;   // column group 0..3
+    UD_TS(0);
+    pdl_wait();
+    UD_TS(1);
+    const int n0 = min(p.kv0_len_dev != nullptr ? p.kv0_len_dev[kvb] : p.kv0_len, tk_pad);
+    const float2* rope = p.rope != nullptr ? p.rope + static_cast<long>(kvb) * p.tq * 128 : nullptr;
+    // ---- Q rows and suffix keys: global -> registers -> RoPE -> swizzled UMMA tiles
+    const int n_items = (rows_total + p.kv1_len) * 16;
+    for (int item = sid; item < n_items; item += UD_SOFT) {
+      const bool isq = item < rows_total * 16;
+      const int r = isq ? item >> 4 : (item - rows_total * 16) >> 4;
+      const int c = item & 15;  // 8-wide chunk of the first half of the head
+      const int t = isq ? r / p.heads : r;
+      const bf16* src = isq ? p.q + b * p.q_bs + t * p.q_rs + (r % p.heads) * UA_HD + c * 8
+                            : p.k1 + b * p.kv1_bs + r * p.kv1_rs + c * 8;
+      uint4 x1 = *reinterpret_cast<const uint4*>(src);
+      uint4 x2 = *reinterpret_cast<const uint4*>(src + 128);
+      if (rope != nullptr) {
+        float4 cs[4];
+        const float4* tp = reinterpret_cast<const float4*>(rope + t * 128 + c * 8);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) cs[e] = tp[e];
+        rope8_umma(x1, x2, reinterpret_cast<const float2*>(cs));
+      }
+      const int row = isq ? (r & 3) * 32 + (r >> 2) : r;
+      const uint32_t tile = isq ? smem_u32(sQ) + static_cast<uint32_t>(c >> 3) * UA_QBLK
+                                : smem_u32(sKs) + static_cast<uint32_t>(c >> 3) * UD_KSBLK;
+      const uint32_t tile2 = tile + 2u * (isq ? UA_QBLK : UD_KSBLK);  // columns + 128 live two hd-blocks further
+      const uint32_t off = static_cast<uint32_t>(row >> 3) * 1024u + static_cast<uint32_t>(row & 7) * 128u +
+                           (static_cast<uint32_t>((c & 7) ^ (row & 7)) << 4);
+      sts_u4(tile + off, x1.x, x1.y, x1.z, x1.w);
+      sts_u4(tile2 + off, x2.x, x2.y, x2.z, x2.w);
+    }
+    uint4 v1reg = make_uint4(0, 0, 0, 0);
+    if (sid < p.kv1_len * 32) v1reg = *reinterpret_cast<const uint4*>(p.v1 + b * p.kv1_bs + (sid >> 5) * p.kv1_rs + (sid & 31) * 8);
+    fence_proxy_async();
+    mbar_arrive(q_ready);
+    UD_TS(2);
+
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    UD_TS(3);
+    if (sid < p.kv1_len * 32) *reinterpret_cast<uint4*>(sV1 + (sid >> 5) * UA_HD + (sid & 31) * 8) = v1reg;
+
+    // ---- softmax: row r of the candidate sits in lane L = (r % 4) * 32 + r / 4  ->  this thread owns r = lane * 4 + q.
+    // A warp can only read its own TMEM lane quarter and the 4 warps of a quarter share one scheduler, so the cost is
+    // (columns x passes x instructions per element) per scheduler whatever the number of live rows: the loops below are
+    // kept to ~7 instructions per element (raw max, one FFMA + ex2 per exponential, no per-element mask in full chunks).
+    const int L = q * 32 + lane;
+    const int r = lane * 4 + q;
+    const bool active = r < rows_total;
+    const int t = r / p.heads, h = r % p.heads;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const bool first_only = p.suffix_mask && t == 0;  // the state token sees only itself among the suffix keys
+    // Column group g takes the prefix chunks g, g + 4, g + 8, ... and group 3 ends with the suffix chunk: a fixed
+    // assignment, so the sums do not depend on how far the prefix range is padded.  Valid columns of a chunk are
+    // always a prefix of it.
+    const int npc = tk_pad / 16;  // prefix chunks
+    const int nv_suffix = first_only ? 1 : p.kv1_len;
+    const float c2 = p.scale * 1.4426950408889634f;
+    float m = -INFINITY, l = 0.f;
+    for (int ch = g; ch * 16 < n0; ch += 4) {
+      uint32_t rr[16];
+      tmem_ld_x16(taddr + ch * 16, rr);
+      tmem_wait_ld();
+      online_chunk(rr, min(16, n0 - ch * 16), c2, m, l);
+    }
+    if (g == 3) {
+      uint32_t rr[16];
+      tmem_ld_x16(taddr + tk_pad, rr);
+      tmem_wait_ld();
+      online_chunk(rr, nv_suffix, c2, m, l);
+    }
+    red2[g * 128 + L] = make_float2(m, l);
+    named_bar(1, UD_SOFT);
+    UD_TS(4);
+    float M = -INFINITY;
+#pragma unroll
+    for (int gg = 0; gg < 4; ++gg) M = fmaxf(M, red2[gg * 128 + L].x);
+    const float Mc = M * c2;
+    float Ls = 0.f;
+#pragma unroll
+    for (int gg = 0; gg < 4; ++gg) {
+      const float2 sg = red2[gg * 128 + L];
+      Ls += sg.y * ex2_approx((sg.x - M) * c2);  // a group without valid columns holds (-inf, 0)
+    }
+    const float inv = 1.0f / Ls;
+    const uint32_t p_row = smem_u32(sP) + static_cast<uint32_t>(L >> 3) * 1024u + static_cast<uint32_t>(L & 7) * 128u;
+    for (int ch = g; ch < npc; ch += 4) {
+      const int nv = max(0, min(16, n0 - ch * 16));
+      uint32_t pk[8];
+      if (nv > 0) {  // warp-uniform
+        uint32_t rr[16];
+        tmem_ld_x16(taddr + ch * 16, rr);
+        tmem_wait_ld();
+        prob_chunk(rr, active ? nv : 0, c2, Mc, inv, pk);  // rows past the candidate's are written as zeros
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = 0u;
+      }
+      const int c0 = ch * 16;
+      const uint32_t blk = p_row + static_cast<uint32_t>(c0 >> 6) * UA_PBLK;
+      const int chunk = (c0 & 63) >> 3;
+      sts_u4(blk + (static_cast<uint32_t>(chunk ^ (L & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+      sts_u4(blk + (static_cast<uint32_t>((chunk + 1) ^ (L & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
+    }
+    if (g == 3) {
+      uint32_t rr[16], pk[8];
+      tmem_ld_x16(taddr + tk_pad, rr);
+      tmem_wait_ld();
+      prob_chunk(rr, active ? nv_suffix : 0, c2, Mc, inv, pk);
+      *reinterpret_cast<uint4*>(psuf + L * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);  // suffix keys 0..7
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    mbar_arrive(p_ready);
+    UD_TS(5);
+
+    // ---- epilogue.  (a) TMEM -> fp32 rows in shared memory (P / V^T are dead once o_full fires); warp (q, g) moves
+    // O[rows of quarter q][64 g .. 64 g + 64)
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    UD_TS(6);
+    float* Os = reinterpret_cast<float*>(smem);
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      uint32_t rr[16];
+      tmem_ld_x16(taddr + g * 64 + cc * 16, rr);  // warp-collective (.sync.aligned): never under a divergent branch
+      tmem_wait_ld();
+      if (active) {
+        float* dst = Os + r * UD_OS_LD + g * 64 + cc * 16;
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          *reinterpret_cast<uint4*>(dst + 4 * v) = make_uint4(rr[4 * v], rr[4 * v + 1], rr[4 * v + 2], rr[4 * v + 3]);
+      }
+    }
+    named_bar(2, UD_SOFT);  // O rows, psuf and sV1 (written by other warps) are visible
+    // (b) all 512 threads: 8 output columns per item, + the suffix keys' P.V in fp32, bf16 store (512 B per warp)
+    for (int item = sid; item < rows_total * 32; item += UD_SOFT) {
+      const int ro = item >> 5, cg = item & 31;
+      const int Lr = (ro & 3) * 32 + (ro >> 2);
+      const float4 o0 = *reinterpret_cast<const float4*>(Os + ro * UD_OS_LD + cg * 8);
+      const float4 o1 = *reinterpret_cast<const float4*>(Os + ro * UD_OS_LD + cg * 8 + 4);
+      float o[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+      const uint4 pu = *reinterpret_cast<const uint4*>(psuf + Lr * 8);
+      const uint32_t pw[4] = {pu.x, pu.y, pu.z, pu.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < p.kv1_len) {
+          const float2 pp = unpack_bf16x2(pw[j >> 1]);
+          const float pj = (j & 1) ? pp.y : pp.x;
+          const uint4 vv = *reinterpret_cast<const uint4*>(sV1 + j * UA_HD + cg * 8);
+          const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack_bf16x2(vw[e]);
+            o[2 * e] = fmaf(pj, f.x, o[2 * e]);
+            o[2 * e + 1] = fmaf(pj, f.y, o[2 * e + 1]);
+          }
+        }
+      }
+      bf16* op = p.out + b * p.o_bs + static_cast<long>(ro / p.heads) * p.o_rs + (ro % p.heads) * UA_HD + cg * 8;
+      *reinterpret_cast<uint4*>(op) =
+          make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+    UD_TS(7);
+    (void)h;
   }
 
   tc_fence_before();
@@ -326,11 +762,11 @@ int attention_umma(cudaStream_t st, const UmmaAttnCall& c) {
   p.q_rows_per_batch = c.q_rows_per_batch, p.k_rows_per_batch = c.k_rows_per_batch;
   p.out = c.out, p.o_bs = c.o_batch_stride, p.o_rs = c.o_row_stride, p.scale = c.scale;
   const int nkb = (tk_pad + 63) / 64;
-  const int nslots = std::min(nkb, UA_VSLOTS);
+  const int nslots = std::min(std::min(nkb, UA_VSLOTS), (UA_BODY_MAX - nkb * UA_PBLK) / UA_VBLK);
   const int kslots = 4 * UA_QBLK + 4 * tk_pad * 128 <= UA_BODY_MAX ? 4 : 3;
   const int body = std::max(4 * UA_QBLK + kslots * tk_pad * 128, nkb * UA_PBLK + nslots * UA_VBLK);
-  CVB_REQUIRE(body <= UA_BODY_MAX, "tcgen05 prefix attention operands do not fit shared memory");
-  const int smem = 1024 + body + (4 + 1 + 1 + 2 * UA_VSLOTS + 2) * 8 + 16;
+  CVB_REQUIRE(body <= UA_BODY_MAX && nslots >= 1, "tcgen05 prefix attention operands do not fit shared memory");
+  const int smem = 1024 + body + (4 + 1 + 1 + 2 * UA_VSLOTS + 2 + 2) * 8 + 2 * 128 * 8 + 64;
   static int attr_smem = 0;
   if (smem > attr_smem) {
     CVB_CUDA(cudaFuncSetAttribute(attn_prefix_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -338,6 +774,54 @@ int attention_umma(cudaStream_t st, const UmmaAttnCall& c) {
   }
   dim3 grid((c.tq + UA_TOK - 1) / UA_TOK, c.batches);
   CVB_TRY(launch_pdl(attn_prefix_umma_kernel, grid, dim3(UA_THREADS), smem, st, 1, tmQ, tmK, tmVT, p));
+  CVB_LAUNCHED();
+  return 0;
+}
+
+bool attention_decode_umma_eligible(const AttnCall& c) {
+  if (c.k1 == nullptr || c.vt0 == nullptr || c.kv_heads != 1 || c.head_dim != UA_HD || c.force_two_pass) return false;
+  if (c.heads * c.tq > 128 || c.heads > 128 || c.kv1_len < 1 || c.kv1_len > 8) return false;
+  if (c.kv0_row_stride != UA_HD || c.kv0_batch_stride % UA_HD != 0 || c.vt0_ld % 8 != 0) return false;
+  const int kmax = c.kv0_len_dev != nullptr ? c.kv0_max : c.kv0_len;
+  const int tk_pad = (kmax + 15) / 16 * 16;
+  if (tk_pad < 16 || tk_pad > UA_MAX_KEYS - 16) return false;
+  const int nkb = (tk_pad + 63) / 64;
+  const int kslots = 4 * UA_QBLK + 4 * UD_KSBLK + 4 * tk_pad * 128 <= UA_BODY_MAX ? 4 : 3;
+  const int vslots = std::min(nkb, (UA_BODY_MAX - UD_MISC - nkb * UA_PBLK) / UA_VBLK);
+  return vslots >= 1 && 4 * UA_QBLK + 4 * UD_KSBLK + kslots * tk_pad * 128 <= UA_BODY_MAX &&
+         ud_misc_off(nkb, vslots, c.heads * c.tq) + UD_MISC <= UA_BODY_MAX;
+}
+
+int attention_decode_umma(cudaStream_t st, const AttnCall& c) {
+  CVB_REQUIRE(attention_decode_umma_eligible(c), "shape not eligible for the tcgen05 decode attention");
+  const int kmax = c.kv0_len_dev != nullptr ? c.kv0_max : c.kv0_len;
+  const int tk_pad = (kmax + 15) / 16 * 16;
+  const int kv_batches = (c.batches + c.q_per_kv_batch - 1) / c.q_per_kv_batch;
+  const long rows_per_batch = c.kv0_batch_stride / UA_HD;
+  CUtensorMap tmK, tmVT;
+  CVB_TRY(get_tmap_cached(c.k0, static_cast<uint64_t>(kv_batches) * rows_per_batch, UA_HD, UA_HD, tk_pad / 2, &tmK));
+  CVB_TRY(get_tmap_cached(c.vt0, static_cast<uint64_t>(kv_batches) * UA_HD, c.vt0_ld, c.vt0_ld, UA_HD, &tmVT));
+  UmmaDecodeParams p;
+  p.q = c.q, p.q_bs = c.q_batch_stride, p.q_rs = c.q_row_stride;
+  p.kv0_len_dev = c.kv0_len_dev, p.kv0_len = c.kv0_len, p.q_per_kv_batch = c.q_per_kv_batch;
+  p.k_rows_per_batch = rows_per_batch;
+  p.k1 = c.k1, p.v1 = c.v1, p.kv1_bs = c.kv1_batch_stride, p.kv1_rs = c.kv1_row_stride, p.kv1_len = c.kv1_len;
+  p.suffix_mask = c.suffix_mask;
+  p.out = c.out, p.o_bs = c.o_batch_stride, p.o_rs = c.o_row_stride;
+  p.heads = c.heads, p.tq = c.tq, p.tk_pad = tk_pad, p.scale = c.scale, p.kv0_static = c.kv0_static, p.rope = c.rope;
+  p.ts = g_skinny_ts;
+  const int nkb = (tk_pad + 63) / 64;
+  const int kslots = 4 * UA_QBLK + 4 * UD_KSBLK + 4 * tk_pad * 128 <= UA_BODY_MAX ? 4 : 3;
+  const int vslots = std::min(nkb, (UA_BODY_MAX - UD_MISC - nkb * UA_PBLK) / UA_VBLK);
+  const int body = std::max(4 * UA_QBLK + 4 * UD_KSBLK + kslots * tk_pad * 128,
+                            ud_misc_off(nkb, vslots, c.heads * c.tq) + UD_MISC);
+  const int smem = 1024 + body + (4 + 1 + 1 + 1 + 2 * UA_VSLOTS + 2) * 8 + 16;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    CVB_CUDA(cudaFuncSetAttribute(attn_decode_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  CVB_TRY(launch_pdl(attn_decode_umma_kernel, dim3(c.batches), dim3(UD_THREADS), smem, st, 1, tmK, tmVT, p));
   CVB_LAUNCHED();
   return 0;
 }

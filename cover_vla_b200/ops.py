@@ -71,25 +71,34 @@ def rmsnorm_reduce(partials, resid, w, eps=1e-6):
 
 
 def attention(q, k0, v0, *, heads, kv_heads, head_dim, kv0_len=None, kv0_len_dev=None, q_per_kv_batch=1,
-              k1=None, v1=None, suffix_mask=False, scale=None, force_two_pass=False, rope=None, algo=0):
+              k1=None, v1=None, suffix_mask=False, scale=None, force_two_pass=False, rope=None, algo=0, vt0=None):
     """q [B, Tq, heads*hd]; k0/v0 [Bkv, T0, kv_heads*hd]; optional k1/v1 [B, T1, kv_heads*hd] (bf16, CUDA)."""
     lib = _lib.load()
     B, Tq, _ = q.shape
     out = torch.empty(B, Tq, heads * head_dim, device=q.device, dtype=torch.bfloat16)
     scale = float(scale if scale is not None else head_dim ** -0.5)
     T0 = k0.shape[1]
-    lib.cvb_op_attention.argtypes = ([C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
-                                      C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
-                                      C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64] + [C.c_int] * 5 +
-                                     [C.c_float, C.c_int, C.c_void_p, C.c_void_p])
-    rc = lib.cvb_op_attention(
+    lib.cvb_op_attention_tc.argtypes = ([C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                         C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+                                         C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64] + [C.c_int] * 5 +
+                                        [C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p])
+    rc = lib.cvb_op_attention_tc(
         _lib.ptr(q), q.stride(0), q.stride(1), _lib.ptr(k0), _lib.ptr(v0), k0.stride(0), k0.stride(1),
         _lib.ptr(kv0_len_dev), int(kv0_len if kv0_len is not None else T0), T0, q_per_kv_batch,
         _lib.ptr(k1), _lib.ptr(v1), k1.stride(0) if k1 is not None else 0, k1.stride(1) if k1 is not None else 0,
         k1.shape[1] if k1 is not None else 0, int(suffix_mask), _lib.ptr(out), out.stride(0), out.stride(1),
-        B, heads, kv_heads, Tq, head_dim, scale, (int(algo) + 1 if algo else int(force_two_pass)), _lib.ptr(rope), _lib.stream_ptr())
+        B, heads, kv_heads, Tq, head_dim, scale, (int(algo) + 1 if algo else int(force_two_pass)), _lib.ptr(rope),
+        _lib.ptr(vt0), (vt0.stride(1) if vt0 is not None else 0), _lib.stream_ptr())
     _lib.check(rc)
     return out
+
+
+def transpose_values(v, pad_to=64):
+    """[B, T, hd] -> V^T [B, hd, round_up(T, pad_to)] (zero padded): the layout the tcgen05 attention kernels read."""
+    B, T, hd = v.shape
+    vt = torch.zeros(B, hd, (T + pad_to - 1) // pad_to * pad_to, device=v.device, dtype=v.dtype)
+    vt[:, :, :T] = v.transpose(1, 2)
+    return vt
 
 
 def attention_umma(q, k, v, *, lens=None, kmax=None, scale=None):

@@ -77,6 +77,17 @@ CVB_API int cvb_op_attention(const void* q, int64_t q_bs, int64_t q_rs, const vo
                              int heads, int kv_heads, int tq, int head_dim, float scale, int force_two_pass,
                              const float* rope_cos_sin, void* stream);
 
+/* cvb_op_attention plus an optional TRANSPOSED copy of the segment-0 values, vt0[(kv batch * head_dim + d) * vt0_ld + key]
+ * (finite past the valid length).  With it, multi-query head_dim-256 two-segment calls (the denoise step, heads * tq <=
+ * 128, <= 8 segment-1 keys) run on the tcgen05 / TMEM kernel; force_two_pass = 4 requires that kernel (error if the
+ * shape is not eligible). */
+CVB_API int cvb_op_attention_tc(const void* q, int64_t q_bs, int64_t q_rs, const void* k0, const void* v0,
+                                int64_t kv0_bs, int64_t kv0_rs, const int32_t* kv0_len_dev, int kv0_len, int kv0_max,
+                                int q_per_kv_batch, const void* k1, const void* v1, int64_t kv1_bs, int64_t kv1_rs,
+                                int kv1_len, int suffix_mask, void* out, int64_t o_bs, int64_t o_rs, int batches,
+                                int heads, int kv_heads, int tq, int head_dim, float scale, int force_two_pass,
+                                const float* rope_cos_sin, const void* vt0, int64_t vt0_ld, void* stream);
+
 /* tcgen05 / TMEM prefix attention (PaliGemma prefix pass, paligemma_with_expert.py:236-360, eager_attention_forward
  * :376-434): multi-query, heads = 8, head_dim = 256, <= 384 keys, every query token of a batch attends the first
  * klen_dev[b] (or klen) keys.  q: token (b * q_rows_per_batch + t) at q + row * q_ld, head h at column h * 256;

@@ -143,3 +143,54 @@ def test_prefix_attention_tcgen05_rejects_unsupported_shapes():
     k = torch.randn(1, 392, 256, device="cuda").to(torch.bfloat16)
     with pytest.raises(_lib.CvbError):
         ops.attention_umma(q, k, k)
+
+
+@pytest.mark.parametrize("R,K,S,P,heads,lens,use_rope", [
+    (3, 4, 5, 328, 8, [270, 328, 300], True), (8, 5, 5, 280, 8, [264, 270, 280, 265, 277, 256, 280, 269], True),
+    (1, 5, 5, 328, 8, [61], True), (2, 2, 8, 100, 4, [100, 7], False), (2, 3, 5, 40, 8, [1, 40], True),
+    (1, 1, 16, 352, 8, [352], False), (2, 2, 1, 64, 8, [33, 64], True)])
+def test_denoise_attention_tcgen05(R, K, S, P, heads, lens, use_rope):
+    """tcgen05/TMEM decode attention (algo 3): RoPE fused into the swizzled UMMA tile staging, exact softmax split over
+    16 warps, prefix P.V on the tensor core with the transposed V cache, suffix keys added in fp32."""
+    from cover_vla_b200 import ops
+    torch.manual_seed(13)
+    hd = 256
+    N = R * K
+    q = torch.randn(N, S, heads * hd, device="cuda").to(torch.bfloat16)
+    k0 = torch.randn(R, P, hd, device="cuda").to(torch.bfloat16)
+    v0 = torch.randn(R, P, hd, device="cuda").to(torch.bfloat16)
+    k1 = torch.randn(N, S if S <= 8 else 5, hd, device="cuda").to(torch.bfloat16)
+    v1 = torch.randn_like(k1)
+    S1 = k1.shape[1]
+    lens_t = torch.tensor(lens, device="cuda", dtype=torch.int32)
+    pos = lens_t[:, None] + torch.arange(S, device="cuda")[None, :]
+    half = hd // 2
+    ts = 10000.0 ** ((2.0 / hd) * torch.arange(half, dtype=torch.float32, device="cuda"))
+    rad = pos[..., None].float() / ts
+    tab = torch.stack([torch.cos(rad), torch.sin(rad)], dim=-1).contiguous() if use_rope else None
+    vt0 = ops.transpose_values(v0)
+    kw = dict(heads=heads, kv_heads=1, head_dim=hd, kv0_len_dev=lens_t, q_per_kv_batch=K, k1=k1, v1=v1,
+              suffix_mask=True, rope=tab, vt0=vt0, algo=3)
+    out = ops.attention(q, k0, v0, **kw)
+    out2 = ops.attention(q, k0, v0, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)  # fixed-order reductions: deterministic
+    if use_rope:
+        posn = pos.repeat_interleave(K, dim=0)
+        qr = _rope(q.view(N, S, heads, hd), posn, hd).view(N, S, heads * hd)
+        k1r = _rope(k1.view(N, S1, 1, hd), posn[:, :S1], hd).view(N, S1, hd)
+    else:
+        qr, k1r = q, k1
+    for n in range(N):
+        r = n // K
+        L = int(lens[r])
+        kk = torch.cat([k0[r, :L], k1r[n]])[None]
+        vv = torch.cat([v0[r, :L], v1[n]])[None]
+        mask = torch.ones(1, S, L + S1, dtype=torch.bool, device="cuda")
+        mask[0, 0, L + 1:] = False
+        ref = _ref(qr[n:n + 1], kk, vv, heads, 1, hd, mask)
+        err = (out[n:n + 1].float() - ref).abs().max().item()
+        assert err < 2e-2, (n, err)
+    if S * heads <= 64 and use_rope:  # the cluster mma.sync kernel it replaces (same ledger)
+        old = ops.attention(q, k0, v0, **{**kw, "algo": 2, "vt0": None})
+        assert (out.float() - old.float()).abs().max().item() < 2e-2

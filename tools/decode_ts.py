@@ -6,22 +6,23 @@ sys.path.insert(0, ".")
 from cover_vla_b200 import ops, _lib
 lib = _lib.load()
 lib.cvb_debug_set_timestamps.argtypes = [C.c_void_p]
-R, K, S, P, heads, hd = 8, 5, 5, 328, 8, 256
+R, K, S, P, heads, hd = 8, 5, 5, int(__import__('os').environ.get('P', 280)), 8, 256
 N = R * K
 q = torch.randn(N, S, heads * hd, device="cuda").to(torch.bfloat16)
 k0 = torch.randn(R, P, hd, device="cuda").to(torch.bfloat16)
 v0 = torch.randn(R, P, hd, device="cuda").to(torch.bfloat16)
 k1 = torch.randn(N, S, hd, device="cuda").to(torch.bfloat16)
 v1 = torch.randn(N, S, hd, device="cuda").to(torch.bfloat16)
-lens = torch.randint(264, 281, (R,), device="cuda", dtype=torch.int32)
+lens = torch.randint(264, min(P, 280) + 1, (R,), device="cuda", dtype=torch.int32)
 tab = torch.randn(R, S, hd // 2, 2, device="cuda")
 kw = dict(heads=heads, kv_heads=1, head_dim=hd, kv0_len_dev=lens, q_per_kv_batch=K, k1=k1, v1=v1, suffix_mask=True, rope=tab)
 for _ in range(3):
     ops.attention(q, k0, v0, **kw)
 torch.cuda.synchronize()
 import os
+kw["vt0"] = ops.transpose_values(v0)
 if os.environ.get("TS"):
-  kw["algo"] = 2
+  kw["algo"] = int(os.environ["TS"])
   ts = torch.zeros(4096 * 8, dtype=torch.int64, device="cuda")
   lib.cvb_debug_set_timestamps(C.c_void_p(ts.data_ptr()))
   for rep in range(2):
@@ -33,11 +34,15 @@ if os.environ.get("TS"):
     t0 = t[:, 0].min()
     rel = (t[:, :7] - t0).float() / 1e3
     print(f"{t.shape[0]} CTAs; us since first CTA start (min / median / max)")
-    for i, n in enumerate(["start", "staged", "qk+stats", "bar1", "pv+sent", "bar2", "final"]):
+    names = (["start", "staged", "qk+stats", "bar1", "pv+sent", "bar2", "final"] if kw["algo"] == 2 else
+             ["start", "dep_ok", "staged", "s_full", "sums", "p_ready", "o_full", "stored"])
+    rel = (t[:, :len(names)] - t0).float() / 1e3
+    for i, n in enumerate(names):
         c = rel[:, i]
         print(f"  {n:9s} {c.min():7.2f} {c.median():7.2f} {c.max():7.2f}")
   lib.cvb_debug_set_timestamps(C.c_void_p(0))
-for algo in (1, 2):
+kw["vt0"] = ops.transpose_values(v0)
+for algo in (1, 2, 3):
   kw["algo"] = algo
   e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
   g = torch.cuda.CUDAGraph()

@@ -53,6 +53,14 @@ int cvb_op_rmsnorm_reduce(const float* P, int S, int64_t split_stride, int64_t l
                              (cvb::bf16*)h_out, ldh, (cvb::bf16*)y, ldy, rows, width, eps);
 }
 
+int cvb_op_layernorm_reduce(const float* P, int S, int64_t split_stride, int64_t ldp, const void* bias, const void* resid,
+                            int64_t ldr, const void* w, const void* b, void* h_out, int64_t ldh, void* y, int64_t ldy,
+                            int rows, int width, float eps, void* stream) {
+  return cvb::layernorm_reduce((cudaStream_t)stream, P, S, split_stride, ldp, (const cvb::bf16*)bias,
+                               (const cvb::bf16*)resid, ldr, (const cvb::bf16*)w, (const cvb::bf16*)b, (cvb::bf16*)h_out,
+                               ldh, (cvb::bf16*)y, ldy, rows, width, eps);
+}
+
 int cvb_op_sgemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, int M, int N, int K, float* C,
                      int64_t ldc, const float* bias, const float* row_bias, const float* resid, int64_t ldr, int act,
                      void* stream) {

@@ -114,6 +114,8 @@ struct Pi0State {
   bf16* vt_p = nullptr;  // V^T of the current prefix layer: [max_rephrases][head_dim][vt_ld] (tcgen05 prefix attention)
   long vt_ld = 0;
   float* part_e = nullptr;  // split-K partials of the expert's o_proj / down_proj: [kMaxSplitK][N*S][ex_width] fp32
+  float* part_v = nullptr;  // split-K partials of the SigLIP tower's out_proj / fc2: [kMaxSplitK][n_img][vis_width] fp32
+  int splitk_vo = 0, splitk_v2 = 0;
   int splitk_o = 0, splitk_d = 0;  // K-splits of o_proj / down_proj in the denoise loop (0 = fused-epilogue GEMMs)
   int lang_hint = 0;  // caller's bound on valid language tokens per prompt (0 = max_lang_len), cvb_pi0_set_lang_len_hint
   GraphCache graphs;  // key = (lang rows << 40) | R << 16 | K

@@ -298,6 +298,17 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
   // Denoise-loop o_proj / down_proj as split-K partials reduced inside the following RMSNorm (ops_misc.cu
   // rmsnorm_reduce_kernel).  The rows of one denoise step must fit one UMMA N (<= 256); larger candidate counts keep
   // the fused-epilogue GEMMs.  CVB_SPLITK_O / CVB_SPLITK_D override the split counts (0 disables).
+  if (T <= 256) {  // SigLIP tower: out_proj / fc2 the same way (LayerNorm variant); CVB_SPLITK_VO / CVB_SPLITK_V2 override
+    auto pickv = [&](const char* env, int kdim, int dflt) {
+      const int kb = (kdim + 63) / 64;
+      int sp = std::min(dflt, std::max(1, kb / 2));
+      if (const char* e = getenv(env)) sp = std::max(0, std::min(atoi(e), std::min(kMaxSplitK, kb)));
+      return sp;
+    };
+    s.splitk_vo = pickv("CVB_SPLITK_VO", Wv, 6);
+    s.splitk_v2 = pickv("CVB_SPLITK_V2", c.vis_mlp, 8);
+    CVB_TRY(dalloc_t(h, &s.part_v, (size_t)kMaxSplitK * T * Wv));
+  }
   if (Me <= 256) {
     auto pick = [&](const char* env, int kdim) {
       const int kb = (kdim + 63) / 64, tiles = (We + 127) / 128;
@@ -329,9 +340,23 @@ static int run_vision(cvb_handle* h, cudaStream_t st) {
   CVB_TRY(im2col_patches(st, s.in_image, s.patches, 3, c.vis_image, c.vis_image, c.vis_patch, s.kpad));
   // hv = bf16(bf16(conv + bias) + pos_emb)
   CVB_TRY(gemm(st, s.patches, s.kpad, s.w_patch, s.kpad, T, Wv, s.kpad, EPI_RESID, s.hv, Wv, b_patch, pos, Wv));
+  // out_proj / fc2 leave split-K partials that the following LayerNorm kernel reduces (bias + residual + norm in one
+  // pass, ops_misc.cu layernorm_reduce_kernel); pending = partials of the previous fc2 not yet folded into hv
+  int pending = 0;
+  const bf16* pending_bias = nullptr;
+  auto gemm_part = [&](const bf16* A, long lda, const bf16* Wt, int Kd, int splits, int* used) {
+    GemmCall g;
+    g.A = A, g.lda = lda, g.W = Wt, g.ldw = Kd, g.M = T, g.N = Wv, g.K = Kd, g.C = s.part_v, g.ldc = Wv;
+    return gemm_splitk_partial(st, g, splits, used);
+  };
   for (int l = 0; l < c.vis_layers; ++l) {
     const VisLayer& L = s.vis[l];
-    CVB_TRY(layernorm_bf16(st, s.hv, Wv, L.ln1_w, L.ln1_b, s.xv, Wv, T, Wv, 1e-6f));
+    if (pending > 0)
+      CVB_TRY(layernorm_reduce(st, s.part_v, pending, (long)T * Wv, Wv, pending_bias, s.hv, Wv, L.ln1_w, L.ln1_b, s.hv, Wv,
+                               s.xv, Wv, T, Wv, 1e-6f));
+    else
+      CVB_TRY(layernorm_bf16(st, s.hv, Wv, L.ln1_w, L.ln1_b, s.xv, Wv, T, Wv, 1e-6f));
+    pending = 0;
     CVB_TRY(gemm(st, s.xv, Wv, L.wqkv, Wv, T, 3 * Wv, Wv, EPI_STORE, s.qkv_v, 3 * Wv, L.bqkv));
     AttnCall a;
     a.q = s.qkv_v, a.q_batch_stride = 0, a.q_row_stride = 3 * Wv;
@@ -341,12 +366,28 @@ static int run_vision(cvb_handle* h, cudaStream_t st) {
     a.batches = 1, a.heads = c.vis_heads, a.kv_heads = c.vis_heads, a.tq = T, a.head_dim = hd;
     a.scale = 1.0f / sqrtf(static_cast<float>(hd));
     CVB_TRY(attention(st, a));
-    CVB_TRY(gemm(st, s.attn_v, Wv, L.wo, Wv, T, Wv, Wv, EPI_RESID, s.hv, Wv, L.bo, s.hv, Wv));
-    CVB_TRY(layernorm_bf16(st, s.hv, Wv, L.ln2_w, L.ln2_b, s.xv, Wv, T, Wv, 1e-6f));
+    if (s.splitk_vo > 0) {
+      int used = 0;
+      CVB_TRY(gemm_part(s.attn_v, Wv, L.wo, Wv, s.splitk_vo, &used));
+      CVB_TRY(layernorm_reduce(st, s.part_v, used, (long)T * Wv, Wv, L.bo, s.hv, Wv, L.ln2_w, L.ln2_b, s.hv, Wv, s.xv, Wv,
+                               T, Wv, 1e-6f));
+    } else {
+      CVB_TRY(gemm(st, s.attn_v, Wv, L.wo, Wv, T, Wv, Wv, EPI_RESID, s.hv, Wv, L.bo, s.hv, Wv));
+      CVB_TRY(layernorm_bf16(st, s.hv, Wv, L.ln2_w, L.ln2_b, s.xv, Wv, T, Wv, 1e-6f));
+    }
     CVB_TRY(gemm(st, s.xv, Wv, L.w1, Wv, T, c.vis_mlp, Wv, EPI_GELU, s.mlp_v, c.vis_mlp, L.b1));
-    CVB_TRY(gemm(st, s.mlp_v, c.vis_mlp, L.w2, c.vis_mlp, T, Wv, c.vis_mlp, EPI_RESID, s.hv, Wv, L.b2, s.hv, Wv));
+    if (s.splitk_v2 > 0) {
+      CVB_TRY(gemm_part(s.mlp_v, c.vis_mlp, L.w2, c.vis_mlp, s.splitk_v2, &pending));
+      pending_bias = L.b2;
+    } else {
+      CVB_TRY(gemm(st, s.mlp_v, c.vis_mlp, L.w2, c.vis_mlp, T, Wv, c.vis_mlp, EPI_RESID, s.hv, Wv, L.b2, s.hv, Wv));
+    }
   }
-  CVB_TRY(layernorm_bf16(st, s.hv, Wv, post_w, post_b, s.xv, Wv, T, Wv, 1e-6f));
+  if (pending > 0)
+    CVB_TRY(layernorm_reduce(st, s.part_v, pending, (long)T * Wv, Wv, pending_bias, s.hv, Wv, post_w, post_b, s.hv, Wv, s.xv,
+                             Wv, T, Wv, 1e-6f));
+  else
+    CVB_TRY(layernorm_bf16(st, s.hv, Wv, post_w, post_b, s.xv, Wv, T, Wv, 1e-6f));
   CVB_TRY(gemm(st, s.xv, Wv, w_proj, Wv, T, D, Wv, EPI_STORE, s.proj_out, D, b_proj));
   return 0;
 }

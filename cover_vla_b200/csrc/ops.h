@@ -64,6 +64,10 @@ int rmsnorm(cudaStream_t st, const void* x, int x_is_f32, long ldx, const void* 
 int rmsnorm_reduce(cudaStream_t st, const float* P, int S, long split_stride, long ldp, const void* resid,
                    int resid_is_f32, long ldr, const void* w, int w_is_f32, bf16* h_out, long ldh, bf16* y, long ldy,
                    int rows, int width, float eps);
+// Same for a LayerNorm block (SigLIP tower): h = bf16(bf16(sum_s P[s] + bias) + resid), y = LayerNorm(h) (bf16 affine).
+int layernorm_reduce(cudaStream_t st, const float* P, int S, long split_stride, long ldp, const bf16* bias,
+                     const bf16* resid, long ldr, const bf16* w, const bf16* b, bf16* h_out, long ldh, bf16* y, long ldy,
+                     int rows, int width, float eps);
 // LayerNorm on bf16 rows (fp32 statistics), bf16 affine.
 int layernorm_bf16(cudaStream_t st, const bf16* x, long ldx, const bf16* w, const bf16* b, bf16* y,
                    long ldy, int rows, int width, float eps);

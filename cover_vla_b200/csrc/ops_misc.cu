@@ -258,6 +258,87 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const bf16* __restr
   }
 }
 
+// Tail of a split-K linear layer fused with the LayerNorm that follows it (SigLIP encoder block: out_proj + residual ->
+// layer_norm2, fc2 + residual -> next layer_norm1 / post_layernorm; reached through embed_image,
+// paligemma_with_expert.py:229-230).  h = bf16(bf16(sum_s P[s] + bias) + resid), y = LayerNorm(h) exactly as
+// layernorm_bf16_kernel computes it.
+__global__ void __launch_bounds__(256) layernorm_reduce_kernel(const float* __restrict__ P, int S, long split_stride,
+                                                               long ldp, const bf16* __restrict__ bias, const bf16* resid,
+                                                               long ldr, const bf16* __restrict__ w,
+                                                               const bf16* __restrict__ b, bf16* h_out, long ldh,
+                                                               bf16* __restrict__ y, long ldy, int width, float eps) {
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ float hrow[];
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const float* pr = P + row * ldp;
+  float s = 0.f;
+  for (int i = threadIdx.x * 4; i < width; i += blockDim.x * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int sp = 0;
+    for (; sp + 4 <= S; sp += 4) {
+      const float4 a0 = *reinterpret_cast<const float4*>(pr + (sp + 0) * split_stride + i);
+      const float4 a1 = *reinterpret_cast<const float4*>(pr + (sp + 1) * split_stride + i);
+      const float4 a2 = *reinterpret_cast<const float4*>(pr + (sp + 2) * split_stride + i);
+      const float4 a3 = *reinterpret_cast<const float4*>(pr + (sp + 3) * split_stride + i);
+      acc.x = (((acc.x + a0.x) + a1.x) + a2.x) + a3.x;
+      acc.y = (((acc.y + a0.y) + a1.y) + a2.y) + a3.y;
+      acc.z = (((acc.z + a0.z) + a1.z) + a2.z) + a3.z;
+      acc.w = (((acc.w + a0.w) + a1.w) + a2.w) + a3.w;
+    }
+    for (; sp < S; ++sp) {
+      const float4 a = *reinterpret_cast<const float4*>(pr + sp * split_stride + i);
+      acc.x += a.x, acc.y += a.y, acc.z += a.z, acc.w += a.w;
+    }
+    float bb[4] = {0.f, 0.f, 0.f, 0.f};
+    if (bias != nullptr) {
+      const uint2 v = *reinterpret_cast<const uint2*>(bias + i);
+      const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y);
+      bb[0] = f0.x, bb[1] = f0.y, bb[2] = f1.x, bb[3] = f1.y;
+    }
+    const uint2 rv = *reinterpret_cast<const uint2*>(resid + row * ldr + i);
+    const float2 r0 = unpack_bf16x2(rv.x), r1 = unpack_bf16x2(rv.y);
+    const float hv[4] = {bf16_round(bf16_round(acc.x + bb[0]) + r0.x), bf16_round(bf16_round(acc.y + bb[1]) + r0.y),
+                         bf16_round(bf16_round(acc.z + bb[2]) + r1.x), bf16_round(bf16_round(acc.w + bb[3]) + r1.y)};
+    *reinterpret_cast<uint2*>(h_out + row * ldh + i) = make_uint2(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]));
+    *reinterpret_cast<float4*>(hrow + i) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+    s += hv[0] + hv[1] + hv[2] + hv[3];
+  }
+  const float mean = block_sum(s, red) / static_cast<float>(width);
+  float vs = 0.f;
+  for (int i = threadIdx.x * 4; i < width; i += blockDim.x * 4) {
+    const float4 f = *reinterpret_cast<const float4*>(hrow + i);
+    vs += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean) + (f.z - mean) * (f.z - mean) +
+          (f.w - mean) * (f.w - mean);
+  }
+  const float var = block_sum(vs, red) / static_cast<float>(width);
+  const float rstd = 1.0f / sqrtf(var + eps);
+  bf16* yr = y + row * ldy;
+  for (int i = threadIdx.x * 4; i < width; i += blockDim.x * 4) {
+    const float4 f = *reinterpret_cast<const float4*>(hrow + i);
+    const uint2 wv = *reinterpret_cast<const uint2*>(w + i);
+    const uint2 bv = *reinterpret_cast<const uint2*>(b + i);
+    const float2 g0 = unpack_bf16x2(wv.x), g1 = unpack_bf16x2(wv.y), h0 = unpack_bf16x2(bv.x), h1 = unpack_bf16x2(bv.y);
+    *reinterpret_cast<uint2*>(yr + i) =
+        make_uint2(pack_bf16x2((f.x - mean) * rstd * g0.x + h0.x, (f.y - mean) * rstd * g0.y + h0.y),
+                   pack_bf16x2((f.z - mean) * rstd * g1.x + h1.x, (f.w - mean) * rstd * g1.y + h1.y));
+  }
+}
+
+int layernorm_reduce(cudaStream_t st, const float* P, int S, long split_stride, long ldp, const bf16* bias,
+                     const bf16* resid, long ldr, const bf16* w, const bf16* b, bf16* h_out, long ldh, bf16* y, long ldy,
+                     int rows, int width, float eps) {
+  CVB_REQUIRE(width % 4 == 0 && ldp % 4 == 0 && split_stride % 4 == 0 && ldr % 4 == 0 && ldh % 4 == 0 && ldy % 4 == 0,
+              "layernorm_reduce needs 4-element aligned rows");
+  CVB_REQUIRE(S >= 1 && resid != nullptr, "layernorm_reduce needs >= 1 partial and a residual");
+  const size_t smem = static_cast<size_t>(width) * sizeof(float);
+  CVB_TRY(launch_pdl(layernorm_reduce_kernel, dim3(rows), dim3(256), smem, st, 1, P, S, split_stride, ldp, bias, resid, ldr,
+                     w, b, h_out, ldh, y, ldy, width, eps));
+  CVB_LAUNCHED();
+  return 0;
+}
+
 int layernorm_bf16(cudaStream_t st, const bf16* x, long ldx, const bf16* w, const bf16* b, bf16* y,
                    long ldy, int rows, int width, float eps) {
   CVB_REQUIRE(width % 8 == 0, "layernorm width must be a multiple of 8");

@@ -70,6 +70,23 @@ def rmsnorm_reduce(partials, resid, w, eps=1e-6):
     return h, y
 
 
+def layernorm_reduce(partials, bias, resid, w, b, eps=1e-6):
+    """(h, y): h = bf16(bf16(sum_s partials[s] + bias) + resid), y = LayerNorm(h) * w + b (all bf16 but the partials)."""
+    lib = _lib.load()
+    S, M, N = partials.shape
+    assert partials.dtype == torch.float32 and partials.is_contiguous()
+    h = torch.empty(M, N, device=partials.device, dtype=torch.bfloat16)
+    y = torch.empty_like(h)
+    lib.cvb_op_layernorm_reduce.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                            C.c_int, C.c_int, C.c_float, C.c_void_p]
+    rc = lib.cvb_op_layernorm_reduce(_lib.ptr(partials), S, M * N, N, _lib.ptr(bias), _lib.ptr(resid), resid.stride(0),
+                                     _lib.ptr(w), _lib.ptr(b), _lib.ptr(h), N, _lib.ptr(y), N, M, N, float(eps),
+                                     _lib.stream_ptr())
+    _lib.check(rc)
+    return h, y
+
+
 def attention(q, k0, v0, *, heads, kv_heads, head_dim, kv0_len=None, kv0_len_dev=None, q_per_kv_batch=1,
               k1=None, v1=None, suffix_mask=False, scale=None, force_two_pass=False, rope=None, algo=0, vt0=None):
     """q [B, Tq, heads*hd]; k0/v0 [Bkv, T0, kv_heads*hd]; optional k1/v1 [B, T1, kv_heads*hd] (bf16, CUDA)."""

@@ -57,6 +57,12 @@ CVB_API int cvb_op_rmsnorm_reduce(const float* P, int S, int64_t split_stride, i
                                   int resid_is_f32, int64_t ldr, const void* w, int w_is_f32, void* h_out, int64_t ldh,
                                   void* y, int64_t ldy, int rows, int width, float eps, void* stream);
 
+/* LayerNorm variant (SigLIP encoder block, reached through embed_image, paligemma_with_expert.py:229-230):
+ *   h = bf16(bf16(sum_s P[s] + bias) + resid),  y = LayerNorm(h) * w + b   (bias may be NULL; bias / resid / w / b bf16). */
+CVB_API int cvb_op_layernorm_reduce(const float* P, int S, int64_t split_stride, int64_t ldp, const void* bias,
+                                    const void* resid, int64_t ldr, const void* w, const void* b, void* h_out,
+                                    int64_t ldh, void* y, int64_t ldy, int rows, int width, float eps, void* stream);
+
 /* fp32 linear for the parts of the path the reference keeps in float32 (modeling_pi0.py:598-609 suffix MLP,
  * efficient_ensemble_merged.py:194-247 verifier heads): C = act(A[M,K] . W[N,K]^T + bias + row_bias) + resid, true-fp32
  * FFMA accumulation (no TF32).  act: 0 none | 1 relu | 2 gelu(erf) | 3 silu.  Any pointer but A / W / C may be NULL. */

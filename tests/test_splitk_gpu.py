@@ -79,3 +79,47 @@ def test_pair_matches_fused_epilogue_gemm():
     assert (d <= 2.0 ** -6 * mag + 1e-6).all()
     assert (d > 0).float().mean().item() < 0.05
     assert ((y.float() - _gemma_rmsnorm(h, g).float()).abs() <= 2.0 ** -7 * y.float().abs() + 1e-6).all()
+
+
+@pytest.mark.parametrize("M,N,S,with_bias", [(256, 1152, 8, True), (256, 1152, 6, True), (16, 64, 1, False), (100, 288, 3, True)])
+def test_layernorm_reduce_matches_the_ledger(M, N, S, with_bias):
+    from cover_vla_b200 import ops
+    torch.manual_seed(M + N + S)
+    p = torch.randn(S, M, N, device="cuda", dtype=torch.float32)
+    bias = torch.randn(N, device="cuda").to(torch.bfloat16) if with_bias else None
+    resid = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+    w = (1.0 + 0.1 * torch.randn(N, device="cuda")).to(torch.bfloat16)
+    b = (0.1 * torch.randn(N, device="cuda")).to(torch.bfloat16)
+    h, y = ops.layernorm_reduce(p, bias, resid, w, b)
+    torch.cuda.synchronize()
+    acc = torch.zeros(M, N, device="cuda")
+    for s in range(S):
+        acc = acc + p[s]
+    if with_bias:
+        acc = acc + bias.float()
+    h_ref = (acc.to(torch.bfloat16).float() + resid.float()).to(torch.bfloat16)
+    assert torch.equal(h, h_ref)
+    y_ref = torch.nn.functional.layer_norm(h_ref.float(), (N,), w.float(), b.float(), 1e-6).to(torch.bfloat16)
+    diff = (y.float() - y_ref.float()).abs()
+    assert (diff <= 2.0 ** -7 * y_ref.float().abs() + 2e-3).all()
+    assert (diff > 0).float().mean().item() < 0.05
+
+
+def test_siglip_block_tail_matches_fused_epilogue_gemm():
+    """fc2 (K = 4304, ragged last k-block) through partials + LayerNorm-reduce vs the EPI_RESID GEMM."""
+    from cover_vla_b200 import ops
+    torch.manual_seed(5)
+    M, N, K = 256, 1152, 4304
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda").to(torch.bfloat16)
+    resid = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+    g = torch.ones(N, device="cuda", dtype=torch.bfloat16)
+    z = torch.zeros(N, device="cuda", dtype=torch.bfloat16)
+    h_fused = ops.gemm_bf16(a, w, bias=bias, epilogue=ops.EPI_RESID, resid=resid, force_bn=64)
+    h, _ = ops.layernorm_reduce(ops.gemm_splitk_partial(a, w, 8), bias, resid, g, z)
+    torch.cuda.synchronize()
+    d = (h.float() - h_fused.float()).abs()
+    mag = (h_fused.float() - resid.float()).abs() + h_fused.float().abs()
+    assert (d <= 2.0 ** -6 * mag + 1e-6).all()
+    assert (d > 0).float().mean().item() < 0.05

@@ -53,10 +53,11 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols
 }
 
 // 3-D view [rows][heads][hd] of a row-major bf16 matrix whose rows hold `heads` consecutive hd-wide heads (leading
-// dimension ld): box = [box_rows rows] x [all heads] x [64 columns], 128-byte swizzle.  One box lands in shared memory
+// dimension ld): box = [box_rows rows] x [box_heads heads, 0 = all] x [64 columns], 128-byte swizzle; columns past hd
+// are zero-filled (a head_dim that is not a multiple of 64 is padded for free).  One box lands in shared memory
 // as (row, head)-major 128-byte lines, i.e. the heads are folded into the UMMA M dimension (ops_attention_umma.cu).
 int make_tmap_3d_heads(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t heads, uint64_t hd, uint64_t ld,
-                       uint32_t box_rows) {
+                       uint32_t box_rows, uint32_t box_heads) {
   PFN_encodeTiled fn = get_encode_fn();
   CVB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled driver entry point unavailable");
   CVB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base must be 16-byte aligned");
@@ -64,7 +65,7 @@ int make_tmap_3d_heads(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_
   CVB_REQUIRE(heads <= 256 && box_rows <= 256, "box extents <= 256");
   cuuint64_t gdim[3] = {hd, heads, rows};
   cuuint64_t gstride[2] = {hd * 2, ld * 2};
-  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(heads), box_rows};
+  cuuint32_t box[3] = {64, box_heads == 0 ? static_cast<cuuint32_t>(heads) : box_heads, box_rows};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -415,6 +415,8 @@ bool attention_group_eligible(const AttnCall& c);
 int attention_group(cudaStream_t st, const AttnCall& c);
 bool attention_decode_umma_eligible(const AttnCall& c);
 int attention_decode_umma(cudaStream_t st, const AttnCall& c);
+bool attention_mha_umma_eligible(const AttnCall& c);
+int attention_mha_umma(cudaStream_t st, const AttnCall& c);
 
 int attention(cudaStream_t st, const AttnCall& c) {
   CVB_REQUIRE(c.head_dim % 8 == 0 && c.head_dim <= 256, "head_dim must be a multiple of 8, <= 256");
@@ -423,7 +425,8 @@ int attention(cudaStream_t st, const AttnCall& c) {
   // cluster kernel, keep the grouped one for shapes the cluster cannot take (> 8 key tiles, > 64 rows per KV group)
   // tcgen05 kernel first (measured 2-3x faster than the mma.sync cluster kernel at the denoise shape)
   if ((c.algo == 0 || c.algo == 3) && attention_decode_umma_eligible(c)) return attention_decode_umma(st, c);
-  CVB_REQUIRE(c.algo != 3, "shape not eligible for the tcgen05 decode attention");
+  if ((c.algo == 0 || c.algo == 3) && c.k1 == nullptr && attention_mha_umma_eligible(c)) return attention_mha_umma(st, c);
+  CVB_REQUIRE(c.algo != 3, "shape not eligible for a tcgen05 attention kernel");
   if (c.k1 != nullptr && c.algo != 1 && attention_decode_eligible(c)) return attention_decode(st, c, c.rope);
   if (c.k1 != nullptr && c.algo != 2 && attention_group_eligible(c)) return attention_group(st, c);
   CVB_REQUIRE(c.rope == nullptr, "fused RoPE needs the cluster decode attention (shape not eligible)");

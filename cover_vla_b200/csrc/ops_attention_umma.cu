@@ -27,7 +27,7 @@ namespace cvb {
 
 int get_tmap_cached(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, CUtensorMap* out);
 int make_tmap_3d_heads(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t heads, uint64_t hd, uint64_t ld,
-                       uint32_t box_rows);
+                       uint32_t box_rows, uint32_t box_heads);
 
 extern unsigned long long* g_skinny_ts;
 
@@ -719,18 +719,243 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Multi-head self-attention of the SigLIP tower on tcgen05 (SiglipAttention reached through embed_image,
+// paligemma_with_expert.py:229-230; 16 heads x head_dim 72, 256 tokens): one CTA = 128 query tokens of one head.
+//   * Q / K tiles by 3-D TMA straight out of the fused qkv buffer ([head_dim, heads, tokens] view: columns past
+//     head_dim are zero-filled, which pads 72 to the UMMA K granularity for free);
+//   * V^T (the K-major "B" operand of P.V) is built by the softmax warps from plain loads while Q.K^T runs;
+//   * S = Q K^T (N = keys <= 256), online softmax out of TMEM on 8 warps, P -> bf16 -> swizzled A tile,
+//     O = P V (N = head_dim rounded up to 16), O -> bf16 -> global.
+// Same rounding ledger as the mma.sync kernel it replaces (probabilities normalised, then rounded to bf16).
+constexpr int UM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 V^T staging / softmax / epilogue
+constexpr int UM_SOFT = 256;
+
+struct UmmaMhaParams {
+  const bf16* v;
+  long v_bs, v_rs;
+  const int* klen_dev;
+  int klen;
+  int tq, tk_pad, hd, hdp;
+  long q_rows_per_batch, k_rows_per_batch;
+  bf16* out;
+  long o_bs, o_rs;
+  float scale;
+};
+
+__global__ void __launch_bounds__(UM_THREADS, 1)
+attn_mha_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const UmmaMhaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int tk_pad = p.tk_pad, hd = p.hd, hdp = p.hdp;
+  const int nb = (hd + 63) / 64;        // hd-blocks of Q / K
+  const int nkb = (tk_pad + 63) / 64;   // key-blocks of P / V^T
+  const uint32_t kblk = static_cast<uint32_t>(tk_pad) * 128u;
+  const uint32_t vblk = static_cast<uint32_t>(hdp) * 128u;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + nb * UA_QBLK;
+  uint8_t* sP = sK + nb * kblk;
+  uint8_t* sV = sP + nkb * UA_PBLK;
+  uint64_t* qk_full = reinterpret_cast<uint64_t*>(sV + nkb * vblk);  // [2]
+  uint64_t* s_full = qk_full + 2;
+  uint64_t* p_ready = s_full + 1;
+  uint64_t* o_full = p_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  float2* red2 = reinterpret_cast<float2*>(o_full + 3);  // [2][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(&qk_full[0], 1);
+      mbar_init(&qk_full[1], 1);
+      mbar_init(s_full, 1);
+      mbar_init(p_ready, UM_SOFT);
+      mbar_init(o_full, 1);
+      fence_barrier_init();
+      fence_proxy_async();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      pdl_wait();
+      const int q_row0 = static_cast<int>(b * p.q_rows_per_batch) + tile * 128;
+      const int k_row0 = static_cast<int>(b * p.k_rows_per_batch);
+      const int half_rows = tk_pad / 2;
+      for (int c = 0; c < nb; ++c) {
+        mbar_arrive_expect_tx(&qk_full[c], UA_QBLK + kblk);
+        tma_load_3d(sQ + c * UA_QBLK, &tmQ, &qk_full[c], c * 64, head, q_row0);
+        tma_load_3d(sK + c * kblk, &tmK, &qk_full[c], c * 64, head, k_row0);
+        tma_load_3d(sK + c * kblk + static_cast<uint32_t>(half_rows) * 128u, &tmK, &qk_full[c], c * 64, head, k_row0 + half_rows);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_n(tk_pad);
+      for (int c = 0; c < nb; ++c) {
+        mbar_wait(&qk_full[c], 0);
+        tc_fence_after();
+        const uint64_t qd = make_desc_kmajor_sw128(smem_u32(sQ + c * UA_QBLK));
+        const uint64_t kd = make_desc_kmajor_sw128(smem_u32(sK + c * kblk));
+        const int ksteps = min(4, (hd - c * 64 + 15) / 16);
+        for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_base, qd + 2 * k, kd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
+      }
+      umma_commit(s_full);
+      mbar_wait(p_ready, 0);  // P and V^T are in shared memory, S has been consumed
+      tc_fence_after();
+      const uint32_t idesc_o = make_idesc_n(hdp);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const uint64_t pd = make_desc_kmajor_sw128(smem_u32(sP + kb * UA_PBLK));
+        const uint64_t vd = make_desc_kmajor_sw128(smem_u32(sV + kb * vblk));
+        const int ksteps = min(4, (tk_pad - kb * 64) / 16);
+        for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_base, pd + 2 * k, vd + 2 * k, idesc_o, (kb | k) != 0 ? 1u : 0u);
+      }
+      umma_commit(o_full);
+    }
+    __syncwarp();
+  } else {
+    const int sid = threadIdx.x - 64;
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    pdl_wait();
+    int n_keys = p.klen_dev != nullptr ? p.klen_dev[b] : p.klen;
+    n_keys = max(1, min(n_keys, tk_pad));
+    // ---- V^T[d][key] tiles (K-major, 128-byte swizzle) from V[key][d]: one key per thread, 16-byte loads, 2-byte stores
+    for (int key = sid; key < tk_pad; key += UM_SOFT) {
+      const bf16* vp = p.v + b * p.v_bs + static_cast<long>(key) * p.v_rs + head * hd;
+      const uint32_t col = smem_u32(sV) + static_cast<uint32_t>(key >> 6) * vblk + static_cast<uint32_t>(key & 7) * 2u;
+      const int chunk = (key & 63) >> 3;
+      for (int d0 = 0; d0 < hdp; d0 += 8) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (key < n_keys && d0 < hd) v = *reinterpret_cast<const uint4*>(vp + d0);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int d = d0 + e;  // row of the tile; d & 7 == e
+          const uint16_t val = static_cast<uint16_t>(e & 1 ? u[e >> 1] >> 16 : u[e >> 1] & 0xffffu);
+          const uint32_t addr = col + static_cast<uint32_t>(d >> 3) * 1024u + static_cast<uint32_t>(e) * 128u +
+                                (static_cast<uint32_t>(chunk ^ e) << 4);
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(val) : "memory");
+        }
+      }
+    }
+    const float c2 = p.scale * 1.4426950408889634f;
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    float m = -INFINITY, l = 0.f;
+    for (int ch = half; ch * 16 < n_keys; ch += 2) {
+      uint32_t rr[16];
+      tmem_ld_x16(taddr + ch * 16, rr);
+      tmem_wait_ld();
+      online_chunk(rr, min(16, n_keys - ch * 16), c2, m, l);
+    }
+    red2[half * 128 + row] = make_float2(m, l);
+    named_bar(1, UM_SOFT);
+    const float2 s0 = red2[row], s1 = red2[128 + row];
+    const float M = fmaxf(s0.x, s1.x);
+    const float Mc = M * c2;
+    const float inv = 1.0f / (s0.y * ex2_approx((s0.x - M) * c2) + s1.y * ex2_approx((s1.x - M) * c2));
+    const uint32_t p_row = smem_u32(sP) + static_cast<uint32_t>(row >> 3) * 1024u + static_cast<uint32_t>(row & 7) * 128u;
+    for (int ch = half; ch * 16 < tk_pad; ch += 2) {
+      const int nv = max(0, min(16, n_keys - ch * 16));
+      uint32_t pk[8];
+      if (nv > 0) {
+        uint32_t rr[16];
+        tmem_ld_x16(taddr + ch * 16, rr);
+        tmem_wait_ld();
+        prob_chunk(rr, nv, c2, Mc, inv, pk);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = 0u;
+      }
+      const int c0 = ch * 16;
+      const uint32_t blk = p_row + static_cast<uint32_t>(c0 >> 6) * UA_PBLK;
+      const int chunk = (c0 & 63) >> 3;
+      sts_u4(blk + (static_cast<uint32_t>(chunk ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+      sts_u4(blk + (static_cast<uint32_t>((chunk + 1) ^ (row & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    mbar_arrive(p_ready);
+
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int t = tile * 128 + row;
+    bf16* op = p.out + b * p.o_bs + static_cast<long>(t) * p.o_rs + head * hd;
+    for (int ch = half; ch * 16 < hdp; ch += 2) {
+      uint32_t rr[16];
+      tmem_ld_x16(taddr + ch * 16, rr);
+      tmem_wait_ld();
+      if (t < p.tq) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (ch * 16 + j * 8 < hd)  // hd is a multiple of 8
+            *reinterpret_cast<uint4*>(op + ch * 16 + j * 8) =
+                make_uint4(pack_bf16x2(__uint_as_float(rr[8 * j]), __uint_as_float(rr[8 * j + 1])),
+                           pack_bf16x2(__uint_as_float(rr[8 * j + 2]), __uint_as_float(rr[8 * j + 3])),
+                           pack_bf16x2(__uint_as_float(rr[8 * j + 4]), __uint_as_float(rr[8 * j + 5])),
+                           pack_bf16x2(__uint_as_float(rr[8 * j + 6]), __uint_as_float(rr[8 * j + 7])));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 struct Q3Key {
   const void* ptr;
-  uint64_t rows, ld;
-  bool operator==(const Q3Key& o) const { return ptr == o.ptr && rows == o.rows && ld == o.ld; }
+  uint64_t rows, ld, heads, hd;
+  uint32_t box_rows, box_heads;
+  bool operator==(const Q3Key& o) const {
+    return ptr == o.ptr && rows == o.rows && ld == o.ld && heads == o.heads && hd == o.hd && box_rows == o.box_rows &&
+           box_heads == o.box_heads;
+  }
 };
 struct Q3Hash {
   size_t operator()(const Q3Key& k) const {
-    return reinterpret_cast<size_t>(k.ptr) ^ (k.rows * 0x9E3779B97F4A7C15ull) ^ (k.ld * 0xC2B2AE3D27D4EB4Full);
+    return reinterpret_cast<size_t>(k.ptr) ^ (k.rows * 0x9E3779B97F4A7C15ull) ^ (k.ld * 0xC2B2AE3D27D4EB4Full) ^
+           (k.heads * 1315423911ull) ^ (k.hd << 20) ^ (static_cast<size_t>(k.box_rows) << 40) ^ k.box_heads;
   }
 };
 std::mutex g_q3_mu;
 std::unordered_map<Q3Key, CUtensorMap, Q3Hash> g_q3;
+
+int get_tmap3_cached(const void* ptr, uint64_t rows, uint64_t heads, uint64_t hd, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_heads, CUtensorMap* out) {
+  std::lock_guard<std::mutex> lk(g_q3_mu);
+  Q3Key key{ptr, rows, ld, heads, hd, box_rows, box_heads};
+  auto it = g_q3.find(key);
+  if (it == g_q3.end()) {
+    CUtensorMap tm;
+    CVB_TRY(make_tmap_3d_heads(&tm, ptr, rows, heads, hd, ld, box_rows, box_heads));
+    it = g_q3.emplace(key, tm).first;
+  }
+  *out = it->second;
+  return 0;
+}
 
 }  // namespace
 
@@ -744,17 +969,7 @@ int attention_umma(cudaStream_t st, const UmmaAttnCall& c) {
   CVB_REQUIRE(attention_umma_eligible(c), "shape not eligible for the tcgen05 prefix attention");
   const int tk_pad = (c.kmax + 15) / 16 * 16;
   CUtensorMap tmQ, tmK, tmVT;
-  {
-    std::lock_guard<std::mutex> lk(g_q3_mu);
-    Q3Key key{c.q, static_cast<uint64_t>(c.q_total_rows), static_cast<uint64_t>(c.q_ld)};
-    auto it = g_q3.find(key);
-    if (it == g_q3.end()) {
-      CUtensorMap tm;
-      CVB_TRY(make_tmap_3d_heads(&tm, c.q, c.q_total_rows, UA_HEADS, UA_HD, c.q_ld, UA_TOK));
-      it = g_q3.emplace(key, tm).first;
-    }
-    tmQ = it->second;
-  }
+  CVB_TRY(get_tmap3_cached(c.q, c.q_total_rows, UA_HEADS, UA_HD, c.q_ld, UA_TOK, 0, &tmQ));
   CVB_TRY(get_tmap_cached(c.k, c.k_total_rows, UA_HD, UA_HD, tk_pad / 2, &tmK));
   CVB_TRY(get_tmap_cached(c.vt, static_cast<uint64_t>(c.batches) * UA_HD, c.vt_ld, c.vt_ld, UA_HD, &tmVT));
   UmmaAttnParams p;
@@ -822,6 +1037,53 @@ int attention_decode_umma(cudaStream_t st, const AttnCall& c) {
     attr_smem = smem;
   }
   CVB_TRY(launch_pdl(attn_decode_umma_kernel, dim3(c.batches), dim3(UD_THREADS), smem, st, 1, tmK, tmVT, p));
+  CVB_LAUNCHED();
+  return 0;
+}
+
+// ---- multi-head (kv_heads == heads) single-segment self-attention, <= 256 keys, head_dim <= 128 (SigLIP tower)
+static int mha_smem_bytes(int tk_pad, int hd, int hdp) {
+  const int nb = (hd + 63) / 64, nkb = (tk_pad + 63) / 64;
+  return nb * UA_QBLK + nb * tk_pad * 128 + nkb * UA_PBLK + nkb * hdp * 128;
+}
+
+bool attention_mha_umma_eligible(const AttnCall& c) {
+  if (c.k1 != nullptr || c.rope != nullptr || c.force_two_pass || c.heads != c.kv_heads) return false;
+  if (c.head_dim % 8 != 0 || c.head_dim > 128 || c.head_dim < 16) return false;
+  const int kmax = c.kv0_len_dev != nullptr ? c.kv0_max : c.kv0_len;
+  if (kmax < 1 || kmax > 256) return false;
+  if (c.q_row_stride % 8 != 0 || c.kv0_row_stride % 8 != 0 || c.o_row_stride % 8 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(c.q) | reinterpret_cast<uintptr_t>(c.k0) | reinterpret_cast<uintptr_t>(c.v0) |
+       reinterpret_cast<uintptr_t>(c.out)) & 15) return false;
+  if (c.batches > 1 && (c.q_batch_stride % c.q_row_stride != 0 || c.kv0_batch_stride % c.kv0_row_stride != 0 ||
+                        c.q_per_kv_batch != 1)) return false;
+  const int tk_pad = (kmax + 15) / 16 * 16, hdp = (c.head_dim + 15) / 16 * 16;
+  return mha_smem_bytes(tk_pad, c.head_dim, hdp) <= UA_BODY_MAX;
+}
+
+int attention_mha_umma(cudaStream_t st, const AttnCall& c) {
+  CVB_REQUIRE(attention_mha_umma_eligible(c), "shape not eligible for the tcgen05 multi-head attention");
+  const int kmax = c.kv0_len_dev != nullptr ? c.kv0_max : c.kv0_len;
+  const int tk_pad = (kmax + 15) / 16 * 16, hd = c.head_dim, hdp = (hd + 15) / 16 * 16;
+  const long q_rpb = c.batches > 1 ? c.q_batch_stride / c.q_row_stride : 0;
+  const long k_rpb = c.batches > 1 ? c.kv0_batch_stride / c.kv0_row_stride : 0;
+  CUtensorMap tmQ, tmK;
+  CVB_TRY(get_tmap3_cached(c.q, static_cast<uint64_t>(q_rpb) * (c.batches - 1) + c.tq, c.heads, hd, c.q_row_stride, 128, 1, &tmQ));
+  CVB_TRY(get_tmap3_cached(c.k0, static_cast<uint64_t>(k_rpb) * (c.batches - 1) + kmax, c.heads, hd, c.kv0_row_stride,
+                           tk_pad / 2, 1, &tmK));
+  UmmaMhaParams p;
+  p.v = c.v0, p.v_bs = c.kv0_batch_stride, p.v_rs = c.kv0_row_stride;
+  p.klen_dev = c.kv0_len_dev, p.klen = c.kv0_len, p.tq = c.tq, p.tk_pad = tk_pad, p.hd = hd, p.hdp = hdp;
+  p.q_rows_per_batch = q_rpb, p.k_rows_per_batch = k_rpb;
+  p.out = c.out, p.o_bs = c.o_batch_stride, p.o_rs = c.o_row_stride, p.scale = c.scale;
+  const int smem = 1024 + mha_smem_bytes(tk_pad, hd, hdp) + 8 * 8 + 2 * 128 * 8 + 64;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    CVB_CUDA(cudaFuncSetAttribute(attn_mha_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  dim3 grid((c.tq + 127) / 128, c.heads, c.batches);
+  CVB_TRY(launch_pdl(attn_mha_umma_kernel, grid, dim3(UM_THREADS), smem, st, 1, tmQ, tmK, p));
   CVB_LAUNCHED();
   return 0;
 }

@@ -101,6 +101,24 @@ __device__ __forceinline__ void online_chunk(const uint32_t (&rr)[16], int nv, f
   l = l * ex2_approx((m - mn) * c2) + acc;  // first chunk: m = -inf -> factor 0
   m = mn;
 }
+// (1b) same, and the exponentials (relative to the NEW running max, 0 for invalid columns) replace rr
+__device__ __forceinline__ void online_chunk_keep(uint32_t (&rr)[16], int nv, float c2, float& m, float& l) {
+  float cm = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if (i < nv) cm = fmaxf(cm, __uint_as_float(rr[i]));
+  const float mn = fmaxf(m, cm);
+  const float mc = mn * c2;
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float e = i < nv ? ex2_approx(fmaf(__uint_as_float(rr[i]), c2, -mc)) : 0.f;
+    acc += e;
+    rr[i] = __float_as_uint(e);
+  }
+  l = l * ex2_approx((m - mn) * c2) + acc;
+  m = mn;
+}
 // (2) normalised probabilities, rounded to bf16 and packed in key order (invalid columns -> 0)
 __device__ __forceinline__ void prob_chunk(const uint32_t (&rr)[16], int nv, float c2, float Mc, float inv, uint32_t (&pk)[8]) {
   if (nv == 16) {
@@ -352,11 +370,12 @@ attn_prefix_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 // the DSMEM reduce-scatter; tools/decode_ts.py).
 constexpr int UD_THREADS = 576;   // warp 0 TMA, warp 1 MMA, warps 2..17 staging / softmax / epilogue
 constexpr int UD_SOFT = 512;
+constexpr int UD_VSLOTS = 8;         // V^T slots (mbarrier pairs); every key-block is resident when the tiles are halved
 constexpr int UD_KSBLK = 16 * 128;  // suffix-key tile of one hd-block: 16 rows x 64 bf16
 constexpr int UD_MISC = 10 * 1024;  // red2[4][128] (max, sum) | psuf[128][8] bf16 | v1[8][256] bf16
 constexpr int UD_OS_LD = 260;       // fp32 row stride of the output staging tile (bank spread, 16-byte aligned)
-__host__ __device__ inline int ud_misc_off(int nkb, int vslots, int rows_total) {
-  const int pv = nkb * UA_PBLK + vslots * UA_VBLK;
+__host__ __device__ inline int ud_misc_off(int nkb, int vslots, int rows_total, int hdw) {
+  const int pv = nkb * UA_PBLK + vslots * hdw * 128;
   const int os = (rows_total * UD_OS_LD * 4 + 1023) / 1024 * 1024;
   return pv > os ? pv : os;
 }
@@ -376,6 +395,7 @@ struct UmmaDecodeParams {
   bf16* out;
   long o_bs, o_rs;
   int heads, tq, tk_pad;
+  int hdw;  // output columns per CTA: 256, or 128 with gridDim.y = 2 (each CTA repeats Q.K^T / softmax, halves P.V)
   float scale;
   int kv0_static;
   const float2* rope;  // [kv batches][tq][128] (cos, sin) or nullptr
@@ -389,7 +409,7 @@ __device__ __forceinline__ unsigned long long ud_timer() {
 }
 #define UD_TS(i)                                                                            \
   do {                                                                                      \
-    if (p.ts != nullptr && threadIdx.x == 64) p.ts[blockIdx.x * 8 + (i)] = ud_timer();       \
+    if (p.ts != nullptr && threadIdx.x == 64) p.ts[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = ud_timer();       \
   } while (0)
 
 // rotate 8 (x1, x2) pairs exactly like rope_kernel / the cluster decode kernel (separate mul / add, no contraction)
@@ -408,6 +428,7 @@ __device__ __forceinline__ void rope8_umma(uint4& v1, uint4& v2, const float2* c
   v2 = make_uint4(u2[0], u2[1], u2[2], u2[3]);
 }
 
+template <int UD_IPT>  // output items (8 columns of one row) per thread: ceil(rows * 32 / 512)
 __global__ void __launch_bounds__(UD_THREADS, 1)
 attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmVT,
                         const UmmaDecodeParams p) {
@@ -418,10 +439,13 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   const uint32_t kblk = static_cast<uint32_t>(tk_pad) * 128u;
   const int nkb = (tk_pad + 63) / 64;
   const int kslots = 4u * UA_QBLK + 4u * UD_KSBLK + 4u * kblk <= static_cast<uint32_t>(UA_BODY_MAX) ? 4 : 3;
-  const int vslots = min(nkb, (UA_BODY_MAX - UD_MISC - nkb * UA_PBLK) / UA_VBLK);
+  const int hdw = p.hdw;                                   // output columns of this CTA (256, or 128 when two CTAs share a candidate)
+  const int hy = blockIdx.y;
+  const uint32_t vblk = static_cast<uint32_t>(hdw) * 128u;  // one key-block of V^T: hdw rows x 64 keys
+  const int vslots = min(min(nkb, UD_VSLOTS), (UA_BODY_MAX - UD_MISC - nkb * UA_PBLK) / static_cast<int>(vblk));
   const uint32_t qk_bytes = 4u * UA_QBLK + 4u * UD_KSBLK + static_cast<uint32_t>(kslots) * kblk;
   const int rows_total = p.heads * p.tq;
-  const uint32_t misc_off = static_cast<uint32_t>(ud_misc_off(nkb, vslots, rows_total));
+  const uint32_t misc_off = static_cast<uint32_t>(ud_misc_off(nkb, vslots, rows_total, hdw));
   const uint32_t body = max(qk_bytes, misc_off + UD_MISC);
   uint8_t* sQ = smem;
   uint8_t* sKs = smem + 4 * UA_QBLK;
@@ -437,8 +461,8 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   uint64_t* s_full = q_ready + 1;
   uint64_t* p_ready = s_full + 1;
   uint64_t* v_full = p_ready + 1;
-  uint64_t* v_empty = v_full + UA_VSLOTS;
-  uint64_t* o_full = v_empty + UA_VSLOTS;
+  uint64_t* v_empty = v_full + UD_VSLOTS;
+  uint64_t* o_full = v_empty + UD_VSLOTS;
   uint64_t* k0_free = o_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k0_free + 1);
 
@@ -456,7 +480,7 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
       mbar_init(q_ready, UD_SOFT);
       mbar_init(s_full, 1);
       mbar_init(p_ready, UD_SOFT);
-      for (int s = 0; s < UA_VSLOTS; ++s) {
+      for (int s = 0; s < UD_VSLOTS; ++s) {
         mbar_init(&v_full[s], 1);
         mbar_init(&v_empty[s], 1);
       }
@@ -492,8 +516,8 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
       for (int kb = 0; kb < nkb; ++kb) {
         const int slot = kb % vslots;
         if (kb >= vslots) mbar_wait(&v_empty[slot], ((kb / vslots) - 1) & 1);
-        mbar_arrive_expect_tx(&v_full[slot], UA_VBLK);
-        tma_load_2d_hint(sV + slot * UA_VBLK, &tmVT, &v_full[slot], kb * 64, kvb * UA_HD, kEvictLast);
+        mbar_arrive_expect_tx(&v_full[slot], vblk);
+        tma_load_2d_hint(sV + slot * vblk, &tmVT, &v_full[slot], kb * 64, kvb * UA_HD + hy * hdw, kEvictLast);
       }
     }
     __syncwarp();
@@ -524,13 +548,13 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
       umma_commit(s_full);
       mbar_wait(p_ready, 0);
       tc_fence_after();
-      const uint32_t idesc_o = make_idesc_n(UA_HD);
+      const uint32_t idesc_o = make_idesc_n(hdw);
       for (int kb = 0; kb < nkb; ++kb) {
         const int slot = kb % vslots;
         mbar_wait(&v_full[slot], (kb / vslots) & 1);
         tc_fence_after();
         const uint64_t pd = make_desc_kmajor_sw128(smem_u32(sP + kb * UA_PBLK));
-        const uint64_t vd = make_desc_kmajor_sw128(smem_u32(sV + slot * UA_VBLK));
+        const uint64_t vd = make_desc_kmajor_sw128(smem_u32(sV + slot * vblk));
         const int ksteps = min(4, (tk_pad - kb * 64) / 16);
         for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_base, pd + 2 * k, vd + 2 * k, idesc_o, (kb | k) != 0 ? 1u : 0u);
         umma_commit(&v_empty[slot]);
@@ -602,110 +626,153 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     const int npc = tk_pad / 16;  // prefix chunks
     const int nv_suffix = first_only ? 1 : p.kv1_len;
     const float c2 = p.scale * 1.4426950408889634f;
+    // Pass A (online max / sum): the exponentials are written back over S in TMEM together with the running max they
+    // refer to, so pass B needs one ex2 per CHUNK instead of one per element (the SFU handles 4 lanes per clock and
+    // scheduler: the exponentials are the longest chain of the kernel).
+    constexpr int UD_CPT = 6;  // prefix chunks per thread: ceil(352 / 16 / 4)
     float m = -INFINITY, l = 0.f;
-    for (int ch = g; ch * 16 < n0; ch += 4) {
-      uint32_t rr[16];
-      tmem_ld_x16(taddr + ch * 16, rr);
-      tmem_wait_ld();
-      online_chunk(rr, min(16, n0 - ch * 16), c2, m, l);
+    float mref[UD_CPT + 1];
+#pragma unroll
+    for (int k = 0; k < UD_CPT; ++k) {
+      const int ch = g + 4 * k;
+      mref[k] = -INFINITY;
+      if (ch * 16 < n0) {  // warp-uniform
+        uint32_t rr[16];
+        tmem_ld_x16(taddr + ch * 16, rr);
+        tmem_wait_ld();
+        online_chunk_keep(rr, min(16, n0 - ch * 16), c2, m, l);
+        tmem_st_x16(taddr + ch * 16, rr);
+        mref[k] = m;
+      }
     }
+    mref[UD_CPT] = -INFINITY;
     if (g == 3) {
       uint32_t rr[16];
       tmem_ld_x16(taddr + tk_pad, rr);
       tmem_wait_ld();
-      online_chunk(rr, nv_suffix, c2, m, l);
+      online_chunk_keep(rr, nv_suffix, c2, m, l);
+      tmem_st_x16(taddr + tk_pad, rr);
+      mref[UD_CPT] = m;
     }
+    tmem_wait_st();
     red2[g * 128 + L] = make_float2(m, l);
     named_bar(1, UD_SOFT);
     UD_TS(4);
     float M = -INFINITY;
 #pragma unroll
     for (int gg = 0; gg < 4; ++gg) M = fmaxf(M, red2[gg * 128 + L].x);
-    const float Mc = M * c2;
     float Ls = 0.f;
 #pragma unroll
     for (int gg = 0; gg < 4; ++gg) {
       const float2 sg = red2[gg * 128 + L];
       Ls += sg.y * ex2_approx((sg.x - M) * c2);  // a group without valid columns holds (-inf, 0)
     }
-    const float inv = 1.0f / Ls;
+    const float inv = active ? 1.0f / Ls : 0.f;  // rows past the candidate's are written as zeros
+    // Pass B: p = e * 2^((m_ref - M) c2) / L  ->  bf16  ->  swizzled A tile of the P.V GEMM
     const uint32_t p_row = smem_u32(sP) + static_cast<uint32_t>(L >> 3) * 1024u + static_cast<uint32_t>(L & 7) * 128u;
-    for (int ch = g; ch < npc; ch += 4) {
-      const int nv = max(0, min(16, n0 - ch * 16));
-      uint32_t pk[8];
-      if (nv > 0) {  // warp-uniform
-        uint32_t rr[16];
-        tmem_ld_x16(taddr + ch * 16, rr);
-        tmem_wait_ld();
-        prob_chunk(rr, active ? nv : 0, c2, Mc, inv, pk);  // rows past the candidate's are written as zeros
-      } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) pk[i] = 0u;
+    for (int k = 0; k < UD_CPT; ++k) {
+      const int ch = g + 4 * k;
+      if (ch < npc) {
+        uint32_t pk[8];
+        if (ch * 16 < n0) {
+          uint32_t rr[16];
+          tmem_ld_x16(taddr + ch * 16, rr);
+          tmem_wait_ld();
+          const float f = active ? ex2_approx((mref[k] - M) * c2) * inv : 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(__uint_as_float(rr[2 * i]) * f, __uint_as_float(rr[2 * i + 1]) * f);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[i] = 0u;
+        }
+        const int c0 = ch * 16;
+        const uint32_t blk = p_row + static_cast<uint32_t>(c0 >> 6) * UA_PBLK;
+        const int chunk = (c0 & 63) >> 3;
+        sts_u4(blk + (static_cast<uint32_t>(chunk ^ (L & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+        sts_u4(blk + (static_cast<uint32_t>((chunk + 1) ^ (L & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
       }
-      const int c0 = ch * 16;
-      const uint32_t blk = p_row + static_cast<uint32_t>(c0 >> 6) * UA_PBLK;
-      const int chunk = (c0 & 63) >> 3;
-      sts_u4(blk + (static_cast<uint32_t>(chunk ^ (L & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
-      sts_u4(blk + (static_cast<uint32_t>((chunk + 1) ^ (L & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
     }
     if (g == 3) {
-      uint32_t rr[16], pk[8];
+      uint32_t rr[16];
       tmem_ld_x16(taddr + tk_pad, rr);
       tmem_wait_ld();
-      prob_chunk(rr, active ? nv_suffix : 0, c2, Mc, inv, pk);
-      *reinterpret_cast<uint4*>(psuf + L * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);  // suffix keys 0..7
+      const float f = active ? ex2_approx((mref[UD_CPT] - M) * c2) * inv : 0.f;
+      *reinterpret_cast<uint4*>(psuf + L * 8) =  // suffix keys 0..7
+          make_uint4(pack_bf16x2(__uint_as_float(rr[0]) * f, __uint_as_float(rr[1]) * f),
+                     pack_bf16x2(__uint_as_float(rr[2]) * f, __uint_as_float(rr[3]) * f),
+                     pack_bf16x2(__uint_as_float(rr[4]) * f, __uint_as_float(rr[5]) * f),
+                     pack_bf16x2(__uint_as_float(rr[6]) * f, __uint_as_float(rr[7]) * f));
     }
     fence_proxy_async();
     tc_fence_before();
     mbar_arrive(p_ready);
     UD_TS(5);
 
-    // ---- epilogue.  (a) TMEM -> fp32 rows in shared memory (P / V^T are dead once o_full fires); warp (q, g) moves
+    // ---- epilogue.  While the P.V MMAs run: the suffix keys' contribution (<= 8 keys x 8 columns per item, fp32) for
+    // the output items this thread will store (item = 8 consecutive columns of one row; 512 B per warp).
+    named_bar(2, UD_SOFT);  // psuf / sV1 (written by other warps) are visible
+    const int cgs = hdw >> 3;  // 8-column groups per output row of this CTA
+    float sc[UD_IPT][8];
+#pragma unroll
+    for (int it = 0; it < UD_IPT; ++it) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sc[it][e] = 0.f;
+      const int item = sid + it * UD_SOFT;
+      if (item < rows_total * cgs) {
+        const int ro = item / cgs, cg = item % cgs;
+        const int Lr = (ro & 3) * 32 + (ro >> 2);
+        const uint4 pu = *reinterpret_cast<const uint4*>(psuf + Lr * 8);
+        const uint32_t pw[4] = {pu.x, pu.y, pu.z, pu.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < p.kv1_len) {
+            const float2 pp = unpack_bf16x2(pw[j >> 1]);
+            const float pj = (j & 1) ? pp.y : pp.x;
+            const uint4 vv = *reinterpret_cast<const uint4*>(sV1 + j * UA_HD + hy * hdw + cg * 8);
+            const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_bf16x2(vw[e]);
+              sc[it][2 * e] = fmaf(pj, f.x, sc[it][2 * e]);
+              sc[it][2 * e + 1] = fmaf(pj, f.y, sc[it][2 * e + 1]);
+            }
+          }
+        }
+      }
+    }
+    // (a) TMEM -> fp32 rows in shared memory (P / V^T are dead once o_full fires); warp (q, g) moves
     // O[rows of quarter q][64 g .. 64 g + 64)
     mbar_wait(o_full, 0);
     tc_fence_after();
     UD_TS(6);
     float* Os = reinterpret_cast<float*>(smem);
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
+    const int wcols = hdw >> 2;  // columns moved by one warp: 64 or 32
+    for (int cc = 0; cc < (wcols >> 4); ++cc) {
       uint32_t rr[16];
-      tmem_ld_x16(taddr + g * 64 + cc * 16, rr);  // warp-collective (.sync.aligned): never under a divergent branch
+      tmem_ld_x16(taddr + g * wcols + cc * 16, rr);  // warp-collective (.sync.aligned): never under a divergent branch
       tmem_wait_ld();
       if (active) {
-        float* dst = Os + r * UD_OS_LD + g * 64 + cc * 16;
+        float* dst = Os + r * UD_OS_LD + g * wcols + cc * 16;
 #pragma unroll
         for (int v = 0; v < 4; ++v)
           *reinterpret_cast<uint4*>(dst + 4 * v) = make_uint4(rr[4 * v], rr[4 * v + 1], rr[4 * v + 2], rr[4 * v + 3]);
       }
     }
-    named_bar(2, UD_SOFT);  // O rows, psuf and sV1 (written by other warps) are visible
-    // (b) all 512 threads: 8 output columns per item, + the suffix keys' P.V in fp32, bf16 store (512 B per warp)
-    for (int item = sid; item < rows_total * 32; item += UD_SOFT) {
-      const int ro = item >> 5, cg = item & 31;
-      const int Lr = (ro & 3) * 32 + (ro >> 2);
-      const float4 o0 = *reinterpret_cast<const float4*>(Os + ro * UD_OS_LD + cg * 8);
-      const float4 o1 = *reinterpret_cast<const float4*>(Os + ro * UD_OS_LD + cg * 8 + 4);
-      float o[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-      const uint4 pu = *reinterpret_cast<const uint4*>(psuf + Lr * 8);
-      const uint32_t pw[4] = {pu.x, pu.y, pu.z, pu.w};
+    named_bar(1, UD_SOFT);
+    // (b) prefix part + suffix part -> bf16 -> global
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j < p.kv1_len) {
-          const float2 pp = unpack_bf16x2(pw[j >> 1]);
-          const float pj = (j & 1) ? pp.y : pp.x;
-          const uint4 vv = *reinterpret_cast<const uint4*>(sV1 + j * UA_HD + cg * 8);
-          const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 f = unpack_bf16x2(vw[e]);
-            o[2 * e] = fmaf(pj, f.x, o[2 * e]);
-            o[2 * e + 1] = fmaf(pj, f.y, o[2 * e + 1]);
-          }
-        }
+    for (int it = 0; it < UD_IPT; ++it) {
+      const int item = sid + it * UD_SOFT;
+      if (item < rows_total * cgs) {
+        const int ro = item / cgs, cg = item % cgs;
+        const float4 o0 = *reinterpret_cast<const float4*>(Os + ro * UD_OS_LD + cg * 8);
+        const float4 o1 = *reinterpret_cast<const float4*>(Os + ro * UD_OS_LD + cg * 8 + 4);
+        bf16* op = p.out + b * p.o_bs + static_cast<long>(ro / p.heads) * p.o_rs + (ro % p.heads) * UA_HD + hy * hdw + cg * 8;
+        *reinterpret_cast<uint4*>(op) =
+            make_uint4(pack_bf16x2(o0.x + sc[it][0], o0.y + sc[it][1]), pack_bf16x2(o0.z + sc[it][2], o0.w + sc[it][3]),
+                       pack_bf16x2(o1.x + sc[it][4], o1.y + sc[it][5]), pack_bf16x2(o1.z + sc[it][6], o1.w + sc[it][7]));
       }
-      bf16* op = p.out + b * p.o_bs + static_cast<long>(ro / p.heads) * p.o_rs + (ro % p.heads) * UA_HD + cg * 8;
-      *reinterpret_cast<uint4*>(op) =
-          make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
     }
     UD_TS(7);
     (void)h;
@@ -1004,7 +1071,7 @@ bool attention_decode_umma_eligible(const AttnCall& c) {
   const int kslots = 4 * UA_QBLK + 4 * UD_KSBLK + 4 * tk_pad * 128 <= UA_BODY_MAX ? 4 : 3;
   const int vslots = std::min(nkb, (UA_BODY_MAX - UD_MISC - nkb * UA_PBLK) / UA_VBLK);
   return vslots >= 1 && 4 * UA_QBLK + 4 * UD_KSBLK + kslots * tk_pad * 128 <= UA_BODY_MAX &&
-         ud_misc_off(nkb, vslots, c.heads * c.tq) + UD_MISC <= UA_BODY_MAX;
+         ud_misc_off(nkb, vslots, c.heads * c.tq, UA_HD) + UD_MISC <= UA_BODY_MAX;
 }
 
 int attention_decode_umma(cudaStream_t st, const AttnCall& c) {
@@ -1015,8 +1082,13 @@ int attention_decode_umma(cudaStream_t st, const AttnCall& c) {
   const long rows_per_batch = c.kv0_batch_stride / UA_HD;
   CUtensorMap tmK, tmVT;
   CVB_TRY(get_tmap_cached(c.k0, static_cast<uint64_t>(kv_batches) * rows_per_batch, UA_HD, UA_HD, tk_pad / 2, &tmK));
-  CVB_TRY(get_tmap_cached(c.vt0, static_cast<uint64_t>(kv_batches) * UA_HD, c.vt0_ld, c.vt0_ld, UA_HD, &tmVT));
+  // Two CTAs per candidate (each one half of the output columns) while that still fits one wave: the V^T tiles halve,
+  // so all key-blocks are resident (no ring reuse on the critical path) and the P.V MMAs / epilogue take half the time
+  const int split = c.batches * 2 <= device_sm_count() ? 2 : 1;
+  const int hdw = UA_HD / split;
+  CVB_TRY(get_tmap_cached(c.vt0, static_cast<uint64_t>(kv_batches) * UA_HD, c.vt0_ld, c.vt0_ld, hdw, &tmVT));
   UmmaDecodeParams p;
+  p.hdw = hdw;
   p.q = c.q, p.q_bs = c.q_batch_stride, p.q_rs = c.q_row_stride;
   p.kv0_len_dev = c.kv0_len_dev, p.kv0_len = c.kv0_len, p.q_per_kv_batch = c.q_per_kv_batch;
   p.k_rows_per_batch = rows_per_batch;
@@ -1027,16 +1099,18 @@ int attention_decode_umma(cudaStream_t st, const AttnCall& c) {
   p.ts = g_skinny_ts;
   const int nkb = (tk_pad + 63) / 64;
   const int kslots = 4 * UA_QBLK + 4 * UD_KSBLK + 4 * tk_pad * 128 <= UA_BODY_MAX ? 4 : 3;
-  const int vslots = std::min(nkb, (UA_BODY_MAX - UD_MISC - nkb * UA_PBLK) / UA_VBLK);
+  const int vslots = std::min(std::min(nkb, UD_VSLOTS), (UA_BODY_MAX - UD_MISC - nkb * UA_PBLK) / (hdw * 128));
   const int body = std::max(4 * UA_QBLK + 4 * UD_KSBLK + kslots * tk_pad * 128,
-                            ud_misc_off(nkb, vslots, c.heads * c.tq) + UD_MISC);
-  const int smem = 1024 + body + (4 + 1 + 1 + 1 + 2 * UA_VSLOTS + 2) * 8 + 16;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    CVB_CUDA(cudaFuncSetAttribute(attn_decode_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
+                            ud_misc_off(nkb, vslots, c.heads * c.tq, hdw) + UD_MISC);
+  const int smem = 1024 + body + (4 + 1 + 1 + 1 + 2 * UD_VSLOTS + 2) * 8 + 16;
+  const bool small = c.heads * c.tq * (hdw / 8) <= 3 * UD_SOFT;  // the denoise step has 40 query rows
+  auto kern = small ? attn_decode_umma_kernel<3> : attn_decode_umma_kernel<8>;
+  static int attr_smem[2] = {0, 0};
+  if (smem > attr_smem[small]) {
+    CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem[small] = smem;
   }
-  CVB_TRY(launch_pdl(attn_decode_umma_kernel, dim3(c.batches), dim3(UD_THREADS), smem, st, 1, tmK, tmVT, p));
+  CVB_TRY(launch_pdl(kern, dim3(c.batches, split), dim3(UD_THREADS), smem, st, 1, tmK, tmVT, p));
   CVB_LAUNCHED();
   return 0;
 }

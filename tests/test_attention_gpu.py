@@ -148,7 +148,8 @@ def test_prefix_attention_tcgen05_rejects_unsupported_shapes():
 @pytest.mark.parametrize("R,K,S,P,heads,lens,use_rope", [
     (3, 4, 5, 328, 8, [270, 328, 300], True), (8, 5, 5, 280, 8, [264, 270, 280, 265, 277, 256, 280, 269], True),
     (1, 5, 5, 328, 8, [61], True), (2, 2, 8, 100, 4, [100, 7], False), (2, 3, 5, 40, 8, [1, 40], True),
-    (1, 1, 16, 352, 8, [352], False), (2, 2, 1, 64, 8, [33, 64], True)])
+    (1, 1, 16, 352, 8, [352], False), (2, 2, 1, 64, 8, [33, 64], True),
+    (8, 20, 5, 280, 8, [264, 270, 280, 265, 277, 256, 280, 269], True)])  # 160 candidates: one CTA per candidate
 def test_denoise_attention_tcgen05(R, K, S, P, heads, lens, use_rope):
     """tcgen05/TMEM decode attention (algo 3): RoPE fused into the swizzled UMMA tile staging, exact softmax split over
     16 warps, prefix P.V on the tensor core with the transposed V cache, suffix keys added in fp32."""

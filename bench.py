@@ -272,7 +272,7 @@ def run_gpu(args):
         gemm_flops = 2.0 * M_ * (2 * I_) * Kd
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
         peak = float(peaks["bf16_tflops"])
-        roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05<256,4,EPI_GEGLU> (prefix gate/up, M=%d N=%d K=%d)" % (M_, 2 * I_, Kd),
+        roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_2sm<EPI_GEGLU> (cta_group::2, 256x256 tiles; prefix gate/up, M=%d N=%d K=%d)" % (M_, 2 * I_, Kd),
                     "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                     "traffic": NCU_TRAFFIC_BYTES, "algorithmic_bytes": int((M_ * Kd + 2 * I_ * Kd + M_ * I_) * 2),
                     "peak_source": peak_src + ", burst figure (kernel timed alone)",

@@ -61,6 +61,104 @@ __device__ __forceinline__ float load_bias(const void* bias, int is_f32, int n) 
                 : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(bias)[n]);
 }
 
+// Fused epilogue of one accumulator row: this thread owns row m of the tile (TMEM lane), BN fp32 columns starting at
+// taddr; nt = N-tile index.  Shared by the 1-CTA and the 2-CTA (cta_group::2) kernels.
+template <int BN, int EPI>
+__device__ __forceinline__ void gemm_epilogue_rows(const GemmArgs& g, uint32_t taddr, int m, bool row_ok, int nt) {
+  if constexpr (EPI == EPI_GEGLU) {
+    static_assert(EPI != EPI_GEGLU || BN == 256, "GEGLU packing is 128 gate + 128 up rows");
+    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(g.C) + static_cast<long>(m) * g.ldc;
+#pragma unroll 1
+    for (int c = 0; c < BN / 2; c += 32) {
+      uint32_t rg[32], ru[32];
+      tmem_ld_x32(taddr + c, rg);
+      tmem_ld_x32(taddr + BN / 2 + c, ru);
+      tmem_wait_ld();
+      const int f0 = nt * (BN / 2) + c;
+      if (row_ok) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int f = f0 + v * 8;
+          if (f < g.n_out) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float r2[2];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int i = v * 8 + e * 2 + h;
+                const float gt = bf16_round(__uint_as_float(rg[i]));
+                const float up = bf16_round(__uint_as_float(ru[i]));
+                const float act = bf16_round(gelu_tanh_f(gt));
+                r2[h] = act * up;
+              }
+              o[e] = pack_bf16x2(r2[0], r2[1]);
+            }
+            *reinterpret_cast<uint4*>(crow + f) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld_x32(taddr + c, r);
+      tmem_wait_ld();
+      const int n0 = nt * BN + c;
+      if (row_ok) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int n = n0 + v * 8;
+          if (n < g.N) {
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              x[e] = __uint_as_float(r[v * 8 + e]) + load_bias(g.bias, g.bias_is_f32, n + e);
+            if constexpr (EPI == EPI_F32) {
+              float* crow = reinterpret_cast<float*>(g.C) + static_cast<long>(m) * g.ldc + n;
+              *reinterpret_cast<float4*>(crow) = make_float4(x[0], x[1], x[2], x[3]);
+              *reinterpret_cast<float4*>(crow + 4) = make_float4(x[4], x[5], x[6], x[7]);
+            } else {
+              if constexpr (EPI == EPI_GELU) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] = gelu_tanh_f(bf16_round(x[e]));
+              }
+              if constexpr (EPI == EPI_RESID) {
+                if (g.resid_is_f32) {
+                  const float* rp = reinterpret_cast<const float*>(g.resid) +
+                                    static_cast<long>(m) * g.ldr + n;
+                  const float4 r0 = *reinterpret_cast<const float4*>(rp);
+                  const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
+                  const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) x[e] = bf16_round(x[e]) + rr[e];
+                } else {
+                  const uint4 rv = *reinterpret_cast<const uint4*>(
+                      reinterpret_cast<const __nv_bfloat16*>(g.resid) +
+                      static_cast<long>(m) * g.ldr + n);
+                  const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f2 = unpack_bf16x2(rr[e]);
+                    x[2 * e] = bf16_round(x[2 * e]) + f2.x;
+                    x[2 * e + 1] = bf16_round(x[2 * e + 1]) + f2.y;
+                  }
+                }
+              }
+              __nv_bfloat16* crow =
+                  reinterpret_cast<__nv_bfloat16*>(g.C) + static_cast<long>(m) * g.ldc + n;
+              *reinterpret_cast<uint4*>(crow) =
+                  make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]),
+                             pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -204,98 +302,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int m = mt * GEMM_BM + row_in_tile;
       const bool row_ok = m < M;
 
-      if constexpr (EPI == EPI_GEGLU) {
-        static_assert(EPI != EPI_GEGLU || BN == 256, "GEGLU packing is 128 gate + 128 up rows");
-        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(g.C) + static_cast<long>(m) * g.ldc;
-#pragma unroll 1
-        for (int c = 0; c < BN / 2; c += 32) {
-          uint32_t rg[32], ru[32];
-          tmem_ld_x32(taddr + c, rg);
-          tmem_ld_x32(taddr + BN / 2 + c, ru);
-          tmem_wait_ld();
-          const int f0 = nt * (BN / 2) + c;
-          if (row_ok) {
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              const int f = f0 + v * 8;
-              if (f < g.n_out) {
-                uint32_t o[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float r2[2];
-#pragma unroll
-                  for (int h = 0; h < 2; ++h) {
-                    const int i = v * 8 + e * 2 + h;
-                    const float gt = bf16_round(__uint_as_float(rg[i]));
-                    const float up = bf16_round(__uint_as_float(ru[i]));
-                    const float act = bf16_round(gelu_tanh_f(gt));
-                    r2[h] = act * up;
-                  }
-                  o[e] = pack_bf16x2(r2[0], r2[1]);
-                }
-                *reinterpret_cast<uint4*>(crow + f) = make_uint4(o[0], o[1], o[2], o[3]);
-              }
-            }
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t r[32];
-          tmem_ld_x32(taddr + c, r);
-          tmem_wait_ld();
-          const int n0 = nt * BN + c;
-          if (row_ok) {
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              const int n = n0 + v * 8;
-              if (n < g.N) {
-                float x[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  x[e] = __uint_as_float(r[v * 8 + e]) + load_bias(g.bias, g.bias_is_f32, n + e);
-                if constexpr (EPI == EPI_F32) {
-                  float* crow = reinterpret_cast<float*>(g.C) + static_cast<long>(m) * g.ldc + n;
-                  *reinterpret_cast<float4*>(crow) = make_float4(x[0], x[1], x[2], x[3]);
-                  *reinterpret_cast<float4*>(crow + 4) = make_float4(x[4], x[5], x[6], x[7]);
-                } else {
-                  if constexpr (EPI == EPI_GELU) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) x[e] = gelu_tanh_f(bf16_round(x[e]));
-                  }
-                  if constexpr (EPI == EPI_RESID) {
-                    if (g.resid_is_f32) {
-                      const float* rp = reinterpret_cast<const float*>(g.resid) +
-                                        static_cast<long>(m) * g.ldr + n;
-                      const float4 r0 = *reinterpret_cast<const float4*>(rp);
-                      const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
-                      const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                      for (int e = 0; e < 8; ++e) x[e] = bf16_round(x[e]) + rr[e];
-                    } else {
-                      const uint4 rv = *reinterpret_cast<const uint4*>(
-                          reinterpret_cast<const __nv_bfloat16*>(g.resid) +
-                          static_cast<long>(m) * g.ldr + n);
-                      const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                      for (int e = 0; e < 4; ++e) {
-                        const float2 f2 = unpack_bf16x2(rr[e]);
-                        x[2 * e] = bf16_round(x[2 * e]) + f2.x;
-                        x[2 * e + 1] = bf16_round(x[2 * e + 1]) + f2.y;
-                      }
-                    }
-                  }
-                  __nv_bfloat16* crow =
-                      reinterpret_cast<__nv_bfloat16*>(g.C) + static_cast<long>(m) * g.ldc + n;
-                  *reinterpret_cast<uint4*>(crow) =
-                      make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]),
-                                 pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
-                }
-              }
-            }
-          }
-        }
-      }
+      gemm_epilogue_rows<BN, EPI>(g, taddr, m, row_ok, nt);
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
       acc ^= 1;

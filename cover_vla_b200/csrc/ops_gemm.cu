@@ -1,9 +1,11 @@
 // Host dispatch for the tcgen05 GEMM: tensor-map construction (cached), tile-shape heuristic, launch.
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
 #include "gemm_tcgen05.cuh"
+#include "gemm_tcgen05_2sm.cuh"
 #include "host_common.h"
 #include "ops.h"
 
@@ -89,6 +91,40 @@ int launch(cudaStream_t st, const GemmCall& c, int grid) {
   return 0;
 }
 
+// CTA-pair kernel (cta_group::2): grid = 2 x pairs, cluster (2,1,1)
+template <int EPI>
+int launch_2sm(cudaStream_t st, const GemmCall& c) {
+  CUtensorMap tmA, tmB;
+  CVB_TRY(get_tmap(c.A, c.M, c.K, c.lda, 128, &tmA));
+  CVB_TRY(get_tmap(c.W, c.N, c.K, c.ldw, 128, &tmB));
+  GemmArgs g;
+  g.C = c.C, g.ldc = c.ldc, g.bias = c.bias, g.bias_is_f32 = c.bias_is_f32;
+  g.resid = c.resid, g.resid_is_f32 = c.resid_is_f32, g.ldr = c.ldr;
+  g.M = c.M, g.N = c.N, g.K = c.K, g.n_out = c.n_out, g.m_dev = nullptr;
+  auto kern = gemm_bf16_tcgen05_2sm<EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM));
+    attr_set = true;
+  }
+  const int tiles = ((c.M + 255) / 256) * ((c.N + 255) / 256);
+  const int pairs = std::min(tiles, device_sm_count() / 2);
+  CVB_TRY(launch_pdl(kern, dim3(2 * pairs), dim3(GEMM_THREADS), GEMM2_SMEM, st, 2, tmA, tmB, g));
+  CVB_LAUNCHED();
+  return 0;
+}
+
+// The pair kernel pays off when the problem is tensor-bound: at least ~one wave of 256 x 256 tiles.  CVB_GEMM_2SM=0
+// disables it; force_bn = 512 forces it (tests).
+bool use_2sm(const GemmCall& c) {
+  static const int env = getenv("CVB_GEMM_2SM") != nullptr ? atoi(getenv("CVB_GEMM_2SM")) : 1;
+  if (c.m_dev != nullptr || c.K % 8 != 0 || c.N % 8 != 0) return false;
+  if (c.force_bn == 512) return true;
+  if (env == 0 || c.force_bn != 0) return false;
+  const long tiles = static_cast<long>((c.M + 255) / 256) * ((c.N + 255) / 256);
+  return c.M >= 1024 && tiles * 10 >= device_sm_count() / 2 * 9;
+}
+
 template <int EPI>
 int launch_bn(cudaStream_t st, const GemmCall& c, int bn, int grid) {
   switch (bn) {
@@ -113,6 +149,24 @@ int gemm_bf16(cudaStream_t st, const GemmCall& c) {
   CVB_REQUIRE(c.K % 8 == 0, "K must be a multiple of 8 (16-byte TMA rows)");
   CVB_REQUIRE(c.N % 8 == 0, "N must be a multiple of 8 (16-byte vector epilogue)");
   CVB_REQUIRE(c.ldc % 8 == 0 || c.epi == EPI_F32, "ldc must be a multiple of 8");
+  if (use_2sm(c)) {
+    if (c.epi == EPI_GEGLU) CVB_REQUIRE(c.N % 256 == 0, "EPI_GEGLU expects 256-row packed gate|up blocks");
+    switch (c.epi) {
+      case EPI_STORE:
+        return launch_2sm<EPI_STORE>(st, c);
+      case EPI_GELU:
+        return launch_2sm<EPI_GELU>(st, c);
+      case EPI_RESID:
+        CVB_REQUIRE(c.resid != nullptr, "EPI_RESID needs a residual pointer");
+        return launch_2sm<EPI_RESID>(st, c);
+      case EPI_GEGLU:
+        return launch_2sm<EPI_GEGLU>(st, c);
+      case EPI_F32:
+        return launch_2sm<EPI_F32>(st, c);
+      default:
+        break;
+    }
+  }
   const int sms = device_sm_count();
   const int m_tiles = (c.M + GEMM_BM - 1) / GEMM_BM;
   auto tiles = [&](int bn) { return m_tiles * ((c.N + bn - 1) / bn); };

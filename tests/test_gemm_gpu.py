@@ -179,3 +179,57 @@ def test_skinny_geglu64(M, I, K):
     ref = torch.nn.functional.gelu(g, approximate="tanh") * u
     assert y.shape == (M, I)
     assert _rel_err(y, ref) < 6e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CTA-pair kernel (tcgen05.mma.cta_group::2, 256 x 256 tiles): force_bn = 512
+# ---------------------------------------------------------------------------------------------------------------
+PAIR_SHAPES = [(2240, 2560, 2048), (2240, 2048, 2048), (2624, 2048, 1024), (256, 256, 64), (300, 512, 1024),
+               (128, 256, 128), (5, 64, 64), (130, 72, 200), (513, 264, 328), (4096, 1024, 512)]
+
+
+@pytest.mark.parametrize("M,N,K", PAIR_SHAPES)
+def test_pair_gemm_store(M, N, K):
+    from cover_vla_b200 import ops
+    torch.manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", dtype=torch.bfloat16)
+    y = ops.gemm_bf16(a, w, bias=bias, force_bn=512)
+    torch.cuda.synchronize()
+    ref = _ref(a, w, bias)
+    assert _rel_err(y, ref) < 4e-3, (M, N, K, _rel_err(y, ref))
+    assert (y.float() - ref).abs().max().item() < 0.06
+    # one fp32 accumulator over the whole K with the same rounding points: same bits as the 1-CTA kernel up to the
+    # accumulation order inside the tensor core
+    y1 = ops.gemm_bf16(a, w, bias=bias, force_bn=256)
+    assert (y.float() - y1.float()).abs().max().item() <= 2 ** -5
+    assert (y != y1).float().mean().item() < 0.02
+
+
+def test_pair_gemm_epilogues():
+    from cover_vla_b200 import ops
+    torch.manual_seed(0)
+    M, N, K = 1500, 512, 1024
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", dtype=torch.float32)
+    ref = _ref(a, w, bias)
+    y = ops.gemm_bf16(a, w, bias=bias, epilogue=ops.EPI_F32, force_bn=512)
+    assert _rel_err(y, ref) < 1e-5
+    bias16 = bias.to(torch.bfloat16)
+    ref16 = _ref(a, w, bias16).to(torch.bfloat16)
+    y = ops.gemm_bf16(a, w, bias=bias16, epilogue=ops.EPI_GELU, force_bn=512)
+    assert _rel_err(y, torch.nn.functional.gelu(ref16, approximate="tanh")) < 4e-3
+    r = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+    r2 = r.clone()
+    ops.gemm_bf16(a, w, bias=bias16, epilogue=ops.EPI_RESID, resid=r2, out=r2, force_bn=512)
+    assert _rel_err(r2, (ref16.float() + r.float()).to(torch.bfloat16)) < 4e-3
+    I = 2048
+    wg = (torch.randn(I, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    wu = (torch.randn(I, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    packed = torch.stack([wg.view(I // 128, 128, K), wu.view(I // 128, 128, K)], dim=1).reshape(2 * I, K).contiguous()
+    y = ops.gemm_bf16(a, packed, epilogue=ops.EPI_GEGLU, n_out=I, force_bn=512)
+    g = (a.float() @ wg.float().t()).to(torch.bfloat16)
+    u = (a.float() @ wu.float().t()).to(torch.bfloat16)
+    assert _rel_err(y, torch.nn.functional.gelu(g, approximate="tanh") * u) < 6e-3

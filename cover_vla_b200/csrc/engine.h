@@ -95,6 +95,8 @@ struct Pi0State {
   float2* rope_tab = nullptr;       // [max_rephrases][suffix_len][hd/2] (cos, sin) of the suffix positions
   float* time_vec = nullptr;        // [steps, We] = W_in[:, We:] . bf16(time_emb[s])
   float* time_emb_f32 = nullptr;    // [steps, We] (bf16-rounded values)
+  float* w_ain_comb = nullptr;      // [We, max_action_dim] = W_in[:, :We] . W_action_in  (two fp32 linears with nothing between)
+  float* b_ain_comb = nullptr;      // [We] = W_in[:, :We] . b_action_in + b_in
   std::vector<float> times;
   float dt = 0.f;
   // inputs (staged copies so the captured graph only touches internal memory)

@@ -255,6 +255,25 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
     g.A = s.time_emb_f32, g.lda = We, g.W = w_in + We, g.ldw = 2 * We, g.M = n, g.N = We, g.K = We;
     g.C = s.time_vec, g.ldc = We;
     CVB_TRY(sgemm_f32(st, g));
+    // action_in_proj and the action half of action_time_mlp_in are two fp32 linear maps with nothing in between
+    // (modeling_pi0.py:598-606): compose them once (fp32) - the per-step K = 1024 linear becomes a K = 32 one.
+    // CVB_NO_FOLD_AIN=1 keeps the two-step evaluation.
+    if (getenv("CVB_NO_FOLD_AIN") == nullptr) {
+      const float *w_ain, *b_ain, *b_in;
+      CVB_TRY(W(h, "action_in_proj.weight", CVB_F32, (int64_t)We * c.max_action_dim, &w_ain));
+      CVB_TRY(W(h, "action_in_proj.bias", CVB_F32, We, &b_ain));
+      CVB_TRY(W(h, "action_time_mlp_in.bias", CVB_F32, We, &b_in));
+      CVB_TRY(dalloc_t(h, &s.w_ain_comb, (size_t)We * c.max_action_dim));
+      CVB_TRY(dalloc_t(h, &s.b_ain_comb, We));
+      SgemmCall gc;
+      gc.A = w_in, gc.lda = 2 * We, gc.W = w_ain, gc.ldw = c.max_action_dim, gc.w_kn = 1;
+      gc.M = We, gc.N = c.max_action_dim, gc.K = We, gc.C = s.w_ain_comb, gc.ldc = c.max_action_dim;
+      CVB_TRY(sgemm_f32(st, gc));
+      SgemmCall gb;
+      gb.A = b_ain, gb.lda = We, gb.W = w_in, gb.ldw = 2 * We, gb.M = 1, gb.N = We, gb.K = We;
+      gb.C = s.b_ain_comb, gb.ldc = We, gb.bias = b_in;
+      CVB_TRY(sgemm_f32(st, gb));
+    }
   }
 
   // ---- workspace
@@ -486,13 +505,18 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
   if (fused_rope) CVB_TRY(rope_table(st, s.rope_timescale, s.plen, R, S, hd / 2, s.rope_tab));
   for (size_t step = 0; step < s.times.size(); ++step) {
     {  // embed_suffix (modeling_pi0.py:598-609), time half of mlp_in folded into time_vec[step]
-      SgemmCall g;
-      g.A = s.x_t, g.lda = c.max_action_dim, g.W = w_ain, g.ldw = c.max_action_dim;
-      g.M = Ma, g.N = We, g.K = c.max_action_dim, g.C = s.a1, g.ldc = We, g.bias = b_ain;
-      CVB_TRY(sgemm_f32(st, g));
       SgemmCall g2;
-      g2.A = s.a1, g2.lda = We, g2.W = w_in, g2.ldw = 2 * We, g2.M = Ma, g2.N = We, g2.K = We;
-      g2.C = s.a2, g2.ldc = We, g2.bias = b_in, g2.row_bias = s.time_vec + step * We, g2.act = SACT_SILU;
+      if (s.w_ain_comb != nullptr) {
+        g2.A = s.x_t, g2.lda = c.max_action_dim, g2.W = s.w_ain_comb, g2.ldw = c.max_action_dim;
+        g2.M = Ma, g2.N = We, g2.K = c.max_action_dim, g2.bias = s.b_ain_comb;
+      } else {
+        SgemmCall g;
+        g.A = s.x_t, g.lda = c.max_action_dim, g.W = w_ain, g.ldw = c.max_action_dim;
+        g.M = Ma, g.N = We, g.K = c.max_action_dim, g.C = s.a1, g.ldc = We, g.bias = b_ain;
+        CVB_TRY(sgemm_f32(st, g));
+        g2.A = s.a1, g2.lda = We, g2.W = w_in, g2.ldw = 2 * We, g2.M = Ma, g2.N = We, g2.K = We, g2.bias = b_in;
+      }
+      g2.C = s.a2, g2.ldc = We, g2.row_bias = s.time_vec + step * We, g2.act = SACT_SILU;
       CVB_TRY(sgemm_f32(st, g2));
       SgemmCall g3;
       g3.A = s.a2, g3.lda = We, g3.W = w_out, g3.ldw = We, g3.M = Ma, g3.N = We, g3.K = We;

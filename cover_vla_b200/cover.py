@@ -21,10 +21,10 @@ from . import _lib
 from .engine import Engine
 
 # INT-ACT/config/dataset/bridge_statistics.json "action" p01 / p99 (first 6 dims; the gripper is not scaled)
-BRIDGE_ACTION_P01 = (-0.02872725307941437, -0.04170349963009357, -0.026093858778476715,
-                     -0.08092105075716972, -0.09288699507713317, -0.20718276381492615)
-BRIDGE_ACTION_P99 = (0.028309678435325586, 0.040855254605412394, 0.040161586627364146,
-                     0.08192047759890528, 0.07792850524187081, 0.20382574498653397)
+BRIDGE_ACTION_P01 = (-0.028539552688598632, -0.041432044506073, -0.025977383628487588,
+                     -0.08020886614918708, -0.09213060349225997, -0.2054861941933632)
+BRIDGE_ACTION_P99 = (0.028122276067733765, 0.040630316659808145, 0.03994889184832546,
+                     0.08121915772557152, 0.07724379181861864, 0.20214049845933896)
 
 
 def format_trajectories(actions, past, history: int, n_future: int, p01=BRIDGE_ACTION_P01, p99=BRIDGE_ACTION_P99,
@@ -44,6 +44,26 @@ def format_trajectories(actions, past, history: int, n_future: int, p01=BRIDGE_A
         _lib.check(lib.cvb_format_trajectories(_lib.ptr(actions), N, chunk, stride, a, b, _lib.ptr(past), num_past,
                                                history, n_future, _lib.ptr(out), _lib.stream_ptr()))
     return out
+
+
+def execution_action(actions, best_idx, K: int, step: int = 0, p01=BRIDGE_ACTION_P01, p99=BRIDGE_ACTION_P99):
+    """Execution-format action of candidate best_idx (device i32 tensor) + gripper vote of its K-sample group.
+
+    actions f32 [N, chunk, stride>=7] (device) -> (f64 [7] = xyz, axis*angle, gripper +-1; i32 [2] = close / open votes).
+    Mirrors run_simpler_eval_with_openpi.py:368-391 (process_inputs(verifier_action=False) + the vote)."""
+    lib = _lib.load()
+    N, chunk, stride = actions.shape
+    out = torch.empty(7, dtype=torch.float64, device=actions.device)
+    votes = torch.empty(2, dtype=torch.int32, device=actions.device)
+    a = (C.c_double * 6)(*p01)
+    b = (C.c_double * 6)(*p99)
+    lib.cvb_execution_action.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]
+    with torch.cuda.device(actions.device):
+        _lib.check(lib.cvb_execution_action(_lib.ptr(actions), N, chunk, stride, a, b, _lib.ptr(best_idx), int(K), int(step),
+                                            _lib.ptr(out), _lib.ptr(votes), _lib.stream_ptr()))
+    return out, votes
 
 
 @dataclass
@@ -109,6 +129,21 @@ class CoverStep:
         winner = actions.index_select(0, idx.to(torch.int64).reshape(1))[0, :, :7]
         packed = torch.cat([idx.to(torch.float32).reshape(1), score.reshape(1), winner.reshape(-1)]).cpu()
         return int(packed[0]), float(packed[1]), packed[2:].reshape(-1, 7)
+
+    def decide_and_execute(self, x: CoverInputs, gate_threshold: float = 0.1):
+        """__call__ plus the action the reference actually executes (run_simpler_eval_with_openpi.py:368-391): the
+        winner's first step in execution format (xyz, axis-angle, gripper) with the gripper voted by its K-sample group,
+        computed on the device.  Returns (best_idx, best_score, winner actions [chunk, 7] f32, execute_action [7] f64)."""
+        actions, traj, scores, gmean, bidx, bscore = self.sample_and_score(x)
+        use0 = scores[0] >= gate_threshold
+        idx = torch.where(use0, torch.zeros_like(bidx[0]), bidx[0])
+        score = torch.where(use0, scores[0], bscore[0])
+        ex, _ = execution_action(actions, idx.to(torch.int32).reshape(1).contiguous(), self.K, 0, self.p01, self.p99)
+        winner = actions.index_select(0, idx.to(torch.int64).reshape(1))[0, :, :7]
+        packed = torch.cat([idx.to(torch.float64).reshape(1), score.to(torch.float64).reshape(1),
+                            winner.reshape(-1).to(torch.float64), ex]).cpu()
+        n = winner.numel()
+        return int(packed[0]), float(packed[1]), packed[2:2 + n].to(torch.float32).reshape(-1, 7), packed[2 + n:].numpy()
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -179,6 +179,17 @@ int cvb_format_trajectories(const float* actions, int n_cand, int chunk, int act
                                   history, n_future, traj);
 }
 
+int cvb_execution_action(const float* actions, int n_cand, int chunk, int action_stride, const double* p01_host,
+                         const double* p99_host, const int32_t* best_idx, int K, int step, double* exec_action,
+                         int32_t* votes, void* stream) {
+  CVB_REQUIRE(actions != nullptr && exec_action != nullptr && best_idx != nullptr && p01_host != nullptr &&
+                  p99_host != nullptr, "null argument");
+  cvb::FormatStats st;
+  for (int i = 0; i < 6; ++i) st.p01[i] = p01_host[i], st.p99[i] = p99_host[i];
+  return cvb::execution_action((cudaStream_t)stream, actions, n_cand, chunk, action_stride, st, best_idx, K, step,
+                               exec_action, votes);
+}
+
 int cvb_cover_step(cvb_handle* h, const float* image, const int64_t* lang_tokens, const int32_t* lang_len,
                    const float* state, const float* noise, int R, int K, const float* vf_image,
                    const int64_t* vf_text_tokens, const double* p01_host, const double* p99_host, const float* past,

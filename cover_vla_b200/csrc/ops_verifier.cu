@@ -512,4 +512,87 @@ int format_trajectories(cudaStream_t stream, const float* actions, int n_cand, i
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Execution-format action of the winner + gripper vote on the device.  Replaces, per
+// decision, process_inputs(verifier_action=False) for the winning group (eval_utils.py:172-221 ->
+// BridgeSimplerAdapter.postprocess, INT-ACT/src/experiments/env_adapters/simpler.py:123-166: denormalize_bound
+// base.py:20-31, euler2axangle src/utils/geometry.py:261-363 + :365-436 with axes 'sxyz', postprocess_gripper
+// :211-220) and the majority vote of run_simpler_eval_with_openpi.py:368-391.  All arithmetic in float64 with numpy's /
+// CPython's operation order (no fused multiply-add); (x + 1) / 2 in float32 as numpy's promotion does.
+__global__ void execution_action_kernel(const float* __restrict__ actions, int chunk, int adim_stride, FormatStats st,
+                                        const int* __restrict__ best_idx, int K, int step, double* __restrict__ out,
+                                        int* __restrict__ votes) {
+  pdl_wait();
+  pdl_launch();
+  if (threadIdx.x != 0) return;
+  const int idx = *best_idx;
+  const float* a = actions + (static_cast<long>(idx) * chunk + step) * adim_stride;
+  double raw[6];
+  for (int c = 0; c < 6; ++c) {
+    const float t = (a[c] - (-1.0f)) / 2.0f;
+    raw[c] = __dadd_rn(__dmul_rn(static_cast<double>(t), __dsub_rn(st.p99[c], st.p01[c])), st.p01[c]);
+  }
+  // euler2quat, static xyz: q = (w, x, y, z)
+  const double ai = raw[3] / 2.0, aj = raw[4] / 2.0, ak = raw[5] / 2.0;
+  const double ci = cos(ai), si = sin(ai), cj = cos(aj), sj = sin(aj), ck = cos(ak), sk = sin(ak);
+  const double cc = __dmul_rn(ci, ck), cs = __dmul_rn(ci, sk), sc = __dmul_rn(si, ck), ss = __dmul_rn(si, sk);
+  double q[4];
+  q[0] = __dadd_rn(__dmul_rn(cj, cc), __dmul_rn(sj, ss));
+  q[1] = __dsub_rn(__dmul_rn(cj, sc), __dmul_rn(sj, cs));
+  q[2] = __dadd_rn(__dmul_rn(cj, ss), __dmul_rn(sj, cc));
+  q[3] = __dsub_rn(__dmul_rn(cj, cs), __dmul_rn(sj, sc));
+  // quat2axangle
+  const double eps = 2.220446049250313e-16;
+  double ax[3] = {1.0, 0.0, 0.0}, theta = 0.0;
+  const double Nq = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(q[0], q[0]), __dmul_rn(q[1], q[1])), __dmul_rn(q[2], q[2])),
+                              __dmul_rn(q[3], q[3]));
+  if (!isfinite(Nq)) {
+    theta = nan("");
+  } else if (!(Nq < eps * eps)) {
+    if (Nq != 1.0) {
+      const double sn = sqrt(Nq);
+      for (int i = 0; i < 4; ++i) q[i] = q[i] / sn;
+    }
+    const double len2 = __dadd_rn(__dadd_rn(__dmul_rn(q[1], q[1]), __dmul_rn(q[2], q[2])), __dmul_rn(q[3], q[3]));
+    const double thr = eps * 3.0;
+    if (!(len2 < thr * thr)) {
+      theta = 2.0 * acos(fmax(fmin(q[0], 1.0), -1.0));
+      const double l = sqrt(len2);
+      for (int i = 0; i < 3; ++i) ax[i] = q[1 + i] / l;
+    }
+  }
+  // gripper of the winner and the vote of its K-sample group (>= 0 closed, < 0 open in the reference's wording)
+  const int g0 = (idx / K) * K;
+  int close_votes = 0, open_votes = 0;
+  for (int m = g0; m < g0 + K; ++m) {
+    const float gm = actions[(static_cast<long>(m) * chunk + step) * adim_stride + 6];
+    if (2.0 * (gm > 0.5f ? 1.0 : 0.0) - 1.0 >= 0.0)
+      ++close_votes;
+    else
+      ++open_votes;
+  }
+  double grip = 2.0 * (a[6] > 0.5f ? 1.0 : 0.0) - 1.0;
+  if (close_votes > open_votes)
+    grip = 1.0;
+  else if (open_votes > close_votes)
+    grip = -1.0;
+  else
+    grip = grip >= 0.0 ? 1.0 : -1.0;
+  out[0] = raw[0], out[1] = raw[1], out[2] = raw[2];
+  for (int i = 0; i < 3; ++i) out[3 + i] = __dmul_rn(ax[i], theta);
+  out[6] = grip;
+  if (votes != nullptr) votes[0] = close_votes, votes[1] = open_votes;
+}
+
+int execution_action(cudaStream_t stream, const float* actions, int n_cand, int chunk, int adim_stride, const FormatStats& st,
+                     const int* best_idx, int K, int step, double* out, int* votes) {
+  CVB_REQUIRE(step >= 0 && step < chunk, "step must be in [0, chunk)");
+  CVB_REQUIRE(K >= 1 && n_cand % K == 0, "the candidate count must be a multiple of K");
+  CVB_REQUIRE(adim_stride >= 7, "action stride must be >= 7");
+  CVB_TRY(launch_pdl(execution_action_kernel, dim3(1), dim3(32), 0, stream, 1, actions, chunk, adim_stride, st, best_idx, K,
+                     step, out, votes));
+  CVB_LAUNCHED();
+  return 0;
+}
+
 }  // namespace cvb

@@ -37,6 +37,8 @@ struct FormatStats {
 int format_trajectories(cudaStream_t stream, const float* actions, int n_cand, int chunk, int adim_stride,
                         const FormatStats& st, const float* past, int num_past, int history, int n_future,
                         float* traj);
+int execution_action(cudaStream_t stream, const float* actions, int n_cand, int chunk, int adim_stride, const FormatStats& st,
+                     const int* best_idx, int K, int step, double* out, int* votes);
 
 int embed_tokens_pos(cudaStream_t st, const bf16* table, const bf16* pos, const int64_t* tok, bf16* out,
                      int tokens, int width);

@@ -197,6 +197,17 @@ CVB_API int cvb_verifier_context(cvb_handle* h, const float* image, const int64_
 CVB_API int cvb_format_trajectories(const float* actions, int n_cand, int chunk, int action_stride,
                                     const double* p01_host, const double* p99_host, const float* past,
                                     int num_past, int history, int n_future, float* traj, void* stream);
+/* Execution-format action of the selected candidate + gripper vote of its K-sample group, on the device (replaces
+ * process_inputs(verifier_action=False) for the winning group, eval_utils.py:172-221 -> BridgeSimplerAdapter.postprocess
+ * INT-ACT/src/experiments/env_adapters/simpler.py:123-166 [denormalize_bound base.py:20-31, euler2axangle
+ * src/utils/geometry.py:261-436 'sxyz', postprocess_gripper :211-220], and the vote of
+ * run_simpler_eval_with_openpi.py:368-391).
+ *   actions f32 [n_cand, chunk, action_stride] (policy output); best_idx i32 [1] (device, e.g. from cvb_select);
+ *   step = which chunk step is executed (0 in the reference); exec_action f64 [7] = (xyz, axis * angle, gripper +-1);
+ *   votes i32 [2] = (close, open) or NULL.  float64 with numpy's operation order. */
+CVB_API int cvb_execution_action(const float* actions, int n_cand, int chunk, int action_stride,
+                                 const double* p01_host, const double* p99_host, const int32_t* best_idx, int K,
+                                 int step, double* exec_action, int32_t* votes, void* stream);
 /* One whole CoVer decision in one call / one CUDA graph: cvb_pi0_sample -> cvb_format_trajectories ->
  * cvb_verifier_score for N = R*K candidates (the body of run_simpler_eval_with_openpi.py:322-363 on the device, no host
  * round trip in between).  The verifier's image/text side is forked onto an internal stream after the prefix and runs

@@ -56,6 +56,13 @@ def test_cover_step_matches_oracle():
     assert torch.equal(win, actions[idx, :, :7].cpu())
     i3, s3, win3 = step(x, gate_threshold=-1e9)  # always confident -> candidate 0
     assert i3 == 0 and abs(s3 - float(ref_scores[0])) < 5e-3
+    # the action the reference executes (run_simpler_eval_with_openpi.py:368-391): execution format + gripper vote
+    from oracle import exec_action_oracle as X
+    i4, s4, win4, ex = step.decide_and_execute(x, gate_threshold=10.0)
+    assert i4 == idx and torch.equal(win4, win)
+    ex_ref, _ = X.execution_action(actions.cpu().numpy(), idx, K, BRIDGE_ACTION_P01, BRIDGE_ACTION_P99)
+    assert np.array_equal(ex[:3], ex_ref[:3]) and ex[6] == ex_ref[6]
+    assert np.allclose(ex[3:6], ex_ref[3:6], rtol=0, atol=1e-12)
     eng.close()
 
 

@@ -37,7 +37,7 @@ struct GemmaLayer {
   const bf16 *in_norm, *post_norm;
   bf16* wqkv;  // owned [(H+2)*hd, D]
   const bf16* wo;
-  bf16* wgu;  // owned packed [256*ceil(I/128), D]
+  bf16* wgu;  // owned packed gate|up blocks: [2*half*ceil(I/half), D], half = 128 (prefix) or 64 (expert)
   const bf16* wd;
 };
 
@@ -118,6 +118,7 @@ struct Pi0State {
   float* part_e = nullptr;  // split-K partials of the expert's o_proj / down_proj: [kMaxSplitK][N*S][ex_width] fp32
   float* part_v = nullptr;  // split-K partials of the SigLIP tower's out_proj / fc2: [kMaxSplitK][n_img][vis_width] fp32
   int splitk_vo = 0, splitk_v2 = 0;
+  int ex_gu_half = 64;  // gate/up packing of the expert: [half gate | half up] rows per block
   int splitk_o = 0, splitk_d = 0;  // K-splits of o_proj / down_proj in the denoise loop (0 = fused-epilogue GEMMs)
   int lang_hint = 0;  // caller's bound on valid language tokens per prompt (0 = max_lang_len), cvb_pi0_set_lang_len_hint
   GraphCache graphs;  // key = (lang rows << 40) | R << 16 | K

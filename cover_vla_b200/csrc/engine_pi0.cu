@@ -54,17 +54,18 @@ int concat_rows(cvb_handle* h, cudaStream_t st, std::vector<std::pair<const bf16
 }
 
 // gate/up -> [128 gate rows | 128 up rows] per 128-feature block (zero padded)
+// (half = 128: prefix, 256-wide GeGLU tiles; half = 64: expert, 128-wide tiles)
 int pack_gate_up(cvb_handle* h, cudaStream_t st, const bf16* wg, const bf16* wu, int I, int D,
-                 bf16** out) {
-  const int blocks = (I + 127) / 128;
-  CVB_TRY(dalloc_t(h, out, static_cast<size_t>(blocks) * 256 * D));
-  CVB_CUDA(cudaMemsetAsync(*out, 0, static_cast<size_t>(blocks) * 256 * D * sizeof(bf16), st));
+                 bf16** out, int half = 128) {
+  const int blocks = (I + half - 1) / half;
+  CVB_TRY(dalloc_t(h, out, static_cast<size_t>(blocks) * 2 * half * D));
+  CVB_CUDA(cudaMemsetAsync(*out, 0, static_cast<size_t>(blocks) * 2 * half * D * sizeof(bf16), st));
   for (int b = 0; b < blocks; ++b) {
-    const int rows = std::min(128, I - b * 128);
-    CVB_CUDA(cudaMemcpyAsync(*out + (static_cast<size_t>(b) * 256) * D, wg + static_cast<size_t>(b) * 128 * D,
+    const int rows = std::min(half, I - b * half);
+    CVB_CUDA(cudaMemcpyAsync(*out + (static_cast<size_t>(b) * 2 * half) * D, wg + static_cast<size_t>(b) * half * D,
                              static_cast<size_t>(rows) * D * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
-    CVB_CUDA(cudaMemcpyAsync(*out + (static_cast<size_t>(b) * 256 + 128) * D,
-                             wu + static_cast<size_t>(b) * 128 * D,
+    CVB_CUDA(cudaMemcpyAsync(*out + (static_cast<size_t>(b) * 2 * half + half) * D,
+                             wu + static_cast<size_t>(b) * half * D,
                              static_cast<size_t>(rows) * D * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
   }
   return 0;
@@ -72,8 +73,9 @@ int pack_gate_up(cvb_handle* h, cudaStream_t st, const bf16* wg, const bf16* wu,
 
 int gemm(cudaStream_t st, const bf16* A, long lda, const bf16* Wt, long ldw, int M, int N, int K,
          int epi, void* C, long ldc, const void* bias = nullptr, const void* resid = nullptr,
-         long ldr = 0, int resid_f32 = 0, int n_out = 0) {
+         long ldr = 0, int resid_f32 = 0, int n_out = 0, int force_bn = 0) {
   GemmCall c;
+  c.force_bn = force_bn;
   c.A = A, c.lda = lda, c.W = Wt, c.ldw = ldw, c.M = M, c.N = N, c.K = K, c.epi = epi;
   c.C = C, c.ldc = ldc, c.bias = bias, c.bias_is_f32 = 0, c.resid = resid, c.ldr = ldr;
   c.resid_is_f32 = resid_f32, c.n_out = n_out;
@@ -210,7 +212,9 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
       CVB_TRY(W(h, p + "self_attn.o_proj.weight", CVB_BF16, (int64_t)qd * Dt, &L.wo));
       CVB_TRY(W(h, p + "mlp.gate_proj.weight", CVB_BF16, (int64_t)I * Dt, &wg));
       CVB_TRY(W(h, p + "mlp.up_proj.weight", CVB_BF16, (int64_t)I * Dt, &wu));
-      CVB_TRY(pack_gate_up(h, st, wg, wu, I, Dt, &L.wgu));
+      // expert: [64 gate | 64 up] blocks for 128-wide GeGLU tiles (CVB_EXPERT_GU256=1 keeps the 256-wide packing)
+      s.ex_gu_half = getenv("CVB_EXPERT_GU256") != nullptr ? 128 : 64;
+      CVB_TRY(pack_gate_up(h, st, wg, wu, I, Dt, &L.wgu, t == 0 ? 128 : s.ex_gu_half));
       CVB_TRY(W(h, p + "mlp.down_proj.weight", CVB_BF16, (int64_t)I * Dt, &L.wd));
       CVB_TRY(W(h, p + "input_layernorm.weight", CVB_BF16, Dt, &L.in_norm));
       CVB_TRY(W(h, p + "post_attention_layernorm.weight", CVB_BF16, Dt, &L.post_norm));
@@ -492,7 +496,8 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
     CVB_TRY(fill_state_rows(st, s.state_emb, s.suffix, N, We, S));
   }
   const long layer_stride = (long)c.max_rephrases * P * hd;
-  const int packed = ((c.ex_mlp + 127) / 128) * 256;
+  const int gu_half = s.ex_gu_half;
+  const int packed = ((c.ex_mlp + gu_half - 1) / gu_half) * 2 * gu_half;
   // RoPE of the suffix is applied inside the cluster decode attention (from a table built once per sample) when the
   // shape is eligible; otherwise by the standalone kernel
   AttnCall probe;
@@ -566,7 +571,10 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
         CVB_TRY(gemm(st, s.attn_e, qd, L.wo, qd, M, We, qd, EPI_RESID, s.he, We, nullptr, resid, We, resid_f32));
         CVB_TRY(rmsnorm(st, s.he, 0, We, L.post_norm, 0, s.xe, We, M, We, 1e-6f, nullptr));
       }
-      CVB_TRY(gemm(st, s.xe, We, L.wgu, We, M, packed, We, EPI_GEGLU, s.act_e, c.ex_mlp, nullptr, nullptr, 0, 0, c.ex_mlp));
+      if (gu_half == 64)  // epilogue 5 + force_bn 128: general kernel, 128 x 128 GeGLU tiles
+        CVB_TRY(gemm(st, s.xe, We, L.wgu, We, M, packed, We, 5, s.act_e, c.ex_mlp, nullptr, nullptr, 0, 0, c.ex_mlp, 128));
+      else
+        CVB_TRY(gemm(st, s.xe, We, L.wgu, We, M, packed, We, EPI_GEGLU, s.act_e, c.ex_mlp, nullptr, nullptr, 0, 0, c.ex_mlp));
       if (s.splitk_d > 0)
         CVB_TRY(gemm_part(s.act_e, c.ex_mlp, L.wd, c.ex_mlp, s.splitk_d, &pending));
       else

@@ -66,7 +66,8 @@ __device__ __forceinline__ float load_bias(const void* bias, int is_f32, int n) 
 template <int BN, int EPI>
 __device__ __forceinline__ void gemm_epilogue_rows(const GemmArgs& g, uint32_t taddr, int m, bool row_ok, int nt) {
   if constexpr (EPI == EPI_GEGLU) {
-    static_assert(EPI != EPI_GEGLU || BN == 256, "GEGLU packing is 128 gate + 128 up rows");
+    // packing: [BN/2 gate rows | BN/2 up rows] per BN-row block (BN = 256: prefix; BN = 128: expert, many small tiles)
+    static_assert(EPI != EPI_GEGLU || BN == 256 || BN == 128, "GEGLU tiles hold BN/2 gate + BN/2 up rows");
     __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(g.C) + static_cast<long>(m) * g.ldc;
 #pragma unroll 1
     for (int c = 0; c < BN / 2; c += 32) {

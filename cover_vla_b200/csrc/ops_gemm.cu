@@ -143,6 +143,13 @@ int gemm_bf16(cudaStream_t st, const GemmCall& c) {
   CVB_REQUIRE(c.M > 0 && c.N > 0 && c.K > 0, "empty GEMM");
   // force_bn: 0 = auto, 64/128/256 = general kernel with that tile, -100 = skinny auto, -1..-16 = skinny with that split
   if (c.force_bn < 0 && c.epi != 6) return gemm_skinny(st, c, c.force_bn == -100 ? 0 : -c.force_bn);
+  // epilogue 5 = GeGLU on [64 gate | 64 up] packed rows: skinny kernel, or (force_bn = 128) the general kernel with
+  // 128 x 128 tiles - twice the CTAs of the 256-wide GeGLU tiles, a third fewer bytes per CTA (denoise gate/up)
+  if (c.epi == 5 && c.force_bn == 128) {
+    CVB_REQUIRE(c.N % 128 == 0 && c.K % 8 == 0, "GeGLU-64 expects 128-row packed [64 gate | 64 up] blocks");
+    const int tiles128 = ((c.M + GEMM_BM - 1) / GEMM_BM) * (c.N / 128);
+    return launch<128, 6, EPI_GEGLU>(st, c, std::min(tiles128, device_sm_count()));
+  }
   if (c.epi == 5) return gemm_skinny(st, c, 0);
   if (c.epi == 6) return gemm_splitk_partial(st, c, c.force_bn < 0 ? -c.force_bn : 0, nullptr);  // EPI_PARTIAL
   if (c.force_bn == 0 && skinny_eligible(c)) return gemm_skinny(st, c, 0);

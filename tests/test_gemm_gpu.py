@@ -233,3 +233,23 @@ def test_pair_gemm_epilogues():
     g = (a.float() @ wg.float().t()).to(torch.bfloat16)
     u = (a.float() @ wu.float().t()).to(torch.bfloat16)
     assert _rel_err(y, torch.nn.functional.gelu(g, approximate="tanh") * u) < 6e-3
+
+
+@pytest.mark.parametrize("M,I,K", [(200, 4096, 1024), (37, 320, 256), (1280, 1024, 1024)])
+def test_geglu64_on_128_wide_general_tiles(M, I, K):
+    """[64 gate | 64 up] packing on the general kernel with 128 x 128 tiles (the expert's gate/up in the denoise loop)."""
+    from cover_vla_b200 import ops
+    torch.manual_seed(4)
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    wg = (torch.randn(I, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    wu = (torch.randn(I, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    packed = torch.stack([wg.view(I // 64, 64, K), wu.view(I // 64, 64, K)], dim=1).reshape(2 * I, K).contiguous()
+    y = ops.gemm_bf16(a, packed, epilogue=ops.EPI_GEGLU64, n_out=I, force_bn=128)
+    g = (a.float() @ wg.float().t()).to(torch.bfloat16)
+    u = (a.float() @ wu.float().t()).to(torch.bfloat16)
+    ref = torch.nn.functional.gelu(g, approximate="tanh") * u
+    assert y.shape == (M, I)
+    assert _rel_err(y, ref) < 6e-3
+    if M <= 256:  # same rounding points as the skinny kernel
+        y2 = ops.gemm_bf16(a, packed, epilogue=ops.EPI_GEGLU64, n_out=I)
+        assert (y.float() - y2.float()).abs().max().item() <= 2 ** -5

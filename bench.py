@@ -319,10 +319,10 @@ def run_gpu(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel, from the committed
-# `ncu --set full` capture (profiles/r1d_gateup_gemm_ncu.txt: 143.7 MB read + 49.4 MB written per launch at M=2240,
+# `ncu --set full` capture (profiles/r1e_gateup_gemm_ncu.txt: 143.5 MB read + 51.8 MB written per launch at M=2240,
 # the bench shape of tools/gateup_one.py; algorithmic bytes at that M are 217 MB - part of the bf16 output is still
 # in L2 when the launch ends)
-NCU_TRAFFIC_BYTES = 193.1e6
+NCU_TRAFFIC_BYTES = 195.3e6
 
 
 def sstep_inputs(x, K, world, rank):

@@ -2,6 +2,8 @@
 // the pi0 suffix embedding MLP / action_out_proj (modeling_pi0.py:577-609,751) and the verifier heads
 // (bridge_verifier/ensemble_eval/efficient_ensemble_merged.py:194-247).  The score tolerance is 1e-3
 // relative, so these stay true-fp32 FFMA (no TF32): 64x64 tile, 16-deep k slices, 4x4 per thread.
+#include <cstdlib>
+
 #include "host_common.h"
 #include "ops.h"
 #include "ptx.cuh"
@@ -249,7 +251,10 @@ int sgemm_f32(cudaStream_t st, const SgemmCall& c) {
     // largest tile that still gives every SM about two CTAs
     const long t64 = static_cast<long>((c.M + 63) / 64) * ((c.N + 63) / 64);
     const long t32x64 = static_cast<long>((c.M + 31) / 32) * ((c.N + 63) / 64);
-    if (t64 >= 296) return launch_pipe<64, 64>(st, c);
+    // (the 64 x 64 tile does 10.7 FMAs per shared-memory load, the 32 x 64 one 8, the 32 x 32 one 5.3: take the big tile
+    // when every SM gets about two CTAs; measured: a lower bar (CVB_SGEMM_T64_MIN=148) changes nothing in the step)
+    static const long t64_min = getenv("CVB_SGEMM_T64_MIN") != nullptr ? atol(getenv("CVB_SGEMM_T64_MIN")) : 296;
+    if (t64 >= t64_min) return launch_pipe<64, 64>(st, c);
     if (t32x64 >= 296) return launch_pipe<32, 64>(st, c);
     return launch_pipe<32, 32>(st, c);
   }

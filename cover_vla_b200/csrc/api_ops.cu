@@ -115,4 +115,9 @@ int cvb_op_attention_umma(const void* q, int64_t q_ld, int64_t q_total_rows, int
   return cvb::attention_umma((cudaStream_t)stream, c);
 }
 
+int cvb_preprocess_policy_image(const uint8_t* img_u8_hwc, int H, int W, int out_h, int out_w, uint8_t* out_u8_hwc,
+                                float* out_f32_chw, void* stream) {
+  return cvb::preprocess_policy_image((cudaStream_t)stream, img_u8_hwc, H, W, out_h, out_w, out_u8_hwc, out_f32_chw);
+}
+
 }  // extern "C"

@@ -75,6 +75,11 @@ int layernorm_bf16(cudaStream_t st, const bf16* x, long ldx, const bf16* w, cons
 int layernorm_f32(cudaStream_t st, const float* x, const float* resid, const float* w,
                   const float* b, float* y, int rows, int width, float eps);
 
+// ---- observation pre-processing (ops_preprocess.cu) ----------------------------------------------------------
+// cv2.resize(frame_u8_hwc, (dw, dh), INTER_LANCZOS4) bit-exact (+ optional x/255 -> (x - 0.5)/0.5 float32 CHW output)
+int preprocess_policy_image(cudaStream_t st, const uint8_t* img_hwc, int H, int W, int dh, int dw, uint8_t* out_u8_hwc,
+                            float* out_f32_chw);
+
 // ---- attention (attention.cuh) -----------------------------------------------------------------
 struct AttnCall {
   // Q rows for batch b, head h, token t:  q + (b*q_batch_stride + t*q_row_stride + h*head_dim)

@@ -1,0 +1,158 @@
+// Policy-side observation pre-processing on the device: replaces, per decision,
+// BridgeSimplerAdapter.preprocess (INT-ACT/src/experiments/env_adapters/simpler.py:43-65): cv2.resize(frame, (224, 224),
+// interpolation=cv2.INTER_LANCZOS4) on the uint8 HWC simulator frame followed by process_images (src/utils/pipeline.py:
+// 34-69: x * (1/255), (x - 0.5) / 0.5 in float32).  One uint8 H2D copy per step instead of a host resize.
+//
+// The 8-bit INTER_LANCZOS4 path of cv::resize is integer arithmetic: per destination column / row 8 taps with int16
+// coefficients (cv::interpolateLanczos4 in float / double, quantised to 11 bits with cvRound), replicated borders, an
+// exact int32 horizontal pass, an exact int32 vertical pass, then (v + 2^21) >> 22 with saturation.  The coefficient
+// tables depend only on the sizes: they are computed on the host exactly as OpenCV does (same libm) and cached on the
+// device; the kernel evaluates the 8 x 8 taps of one output pixel per thread (all three channels).  Bit-exact against
+// cv2.resize (tests/test_preprocess.py).
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include "host_common.h"
+#include "ops.h"
+#include "ptx.cuh"
+
+namespace cvb {
+
+namespace {
+
+// cv::interpolateLanczos4 (imgproc: float x, double trigonometry, float accumulation)
+void lanczos4_coeffs(float x, float* coeffs) {
+  static const double s45 = 0.70710678118654752440084436210485;
+  static const double cs[][2] = {{1, 0}, {-s45, -s45}, {0, 1}, {s45, -s45}, {-1, 0}, {s45, s45}, {0, -1}, {-s45, s45}};
+  const double pi = 3.1415926535897932384626433832795;
+  float sum = 0;
+  const double y0 = -(x + 3) * pi * 0.25, s0 = std::sin(y0), c0 = std::cos(y0);
+  for (int i = 0; i < 8; i++) {
+    const float y0_ = (x + 3 - i);
+    if (std::fabs(y0_) >= 1e-6f) {
+      const double y = -y0_ * pi * 0.25;
+      coeffs[i] = static_cast<float>((cs[i][0] * s0 + cs[i][1] * c0) / (y * y));
+    } else {
+      coeffs[i] = 1e30f;
+    }
+    sum += coeffs[i];
+  }
+  sum = 1.f / sum;
+  for (int i = 0; i < 8; i++) coeffs[i] *= sum;
+}
+
+void lanczos4_tables(int src, int dst, std::vector<int>* ofs, std::vector<short>* coef) {
+  const double scale = 1.0 / (static_cast<double>(dst) / src);
+  ofs->resize(dst);
+  coef->resize(static_cast<size_t>(dst) * 8);
+  for (int d = 0; d < dst; ++d) {
+    float f = static_cast<float>((d + 0.5) * scale - 0.5);
+    const int s = static_cast<int>(std::floor(f));
+    f -= s;
+    (*ofs)[d] = s;
+    float c[8];
+    lanczos4_coeffs(f, c);
+    for (int k = 0; k < 8; ++k) {
+      const long r = std::lrintf(c[k] * 2048.0f);  // cvRound: nearest-even; saturate_cast<short>
+      (*coef)[static_cast<size_t>(d) * 8 + k] = static_cast<short>(r < -32768 ? -32768 : (r > 32767 ? 32767 : r));
+    }
+  }
+}
+
+struct Tables {
+  int* xofs = nullptr;
+  int* yofs = nullptr;
+  short* xcoef = nullptr;
+  short* ycoef = nullptr;
+};
+std::mutex g_mu;
+std::map<std::tuple<int, int, int, int, int>, Tables> g_tables;  // (device, H, W, dh, dw)
+
+__global__ void __launch_bounds__(128) lanczos4_policy_image_kernel(const uint8_t* __restrict__ img, int H, int W, int dh,
+                                                                    int dw, const int* __restrict__ xofs,
+                                                                    const short* __restrict__ xcoef,
+                                                                    const int* __restrict__ yofs,
+                                                                    const short* __restrict__ ycoef,
+                                                                    uint8_t* __restrict__ out_u8, float* __restrict__ out_f32) {
+  pdl_wait();
+  pdl_launch();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= dh * dw) return;
+  const int dy = idx / dw, dx = idx % dw;
+  int xi[8], xa[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    xi[k] = min(max(xofs[dx] + k - 3, 0), W - 1) * 3;
+    xa[k] = xcoef[dx * 8 + k];
+  }
+  unsigned acc[3] = {0u, 0u, 0u};  // int32 arithmetic with wrap-around, like the int accumulators of cv::resize
+#pragma unroll
+  for (int ky = 0; ky < 8; ++ky) {
+    const int sy = min(max(yofs[dy] + ky - 3, 0), H - 1);
+    const uint8_t* row = img + static_cast<long>(sy) * W * 3;
+    unsigned h[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) h[c] += static_cast<unsigned>(static_cast<int>(row[xi[k] + c]) * xa[k]);
+    }
+    const int b = ycoef[dy * 8 + ky];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] += static_cast<unsigned>(static_cast<int>(h[c]) * b);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int v = (static_cast<int>(acc[c]) + (1 << 21)) >> 22;  // FixedPtCast<int, uchar, 22>
+    const int u = min(max(v, 0), 255);
+    if (out_u8 != nullptr) out_u8[(static_cast<long>(dy) * dw + dx) * 3 + c] = static_cast<uint8_t>(u);
+    if (out_f32 != nullptr) {
+      // pipeline.py: image * (1 / 255.0) -> (image - 0.5) / 0.5, float32, no contraction
+      const float r = __fmul_rn(static_cast<float>(u), static_cast<float>(1 / 255.0));
+      out_f32[(static_cast<long>(c) * dh + dy) * dw + dx] = __fdiv_rn(__fsub_rn(r, 0.5f), 0.5f);
+    }
+  }
+}
+
+}  // namespace
+
+int preprocess_policy_image(cudaStream_t st, const uint8_t* img_hwc, int H, int W, int dh, int dw, uint8_t* out_u8_hwc,
+                            float* out_f32_chw) {
+  CVB_REQUIRE(img_hwc != nullptr && (out_u8_hwc != nullptr || out_f32_chw != nullptr), "null argument");
+  CVB_REQUIRE(H >= 1 && W >= 1 && dh >= 1 && dw >= 1 && H <= 16384 && W <= 16384, "image sizes out of range");
+  int dev = 0;
+  CVB_CUDA(cudaGetDevice(&dev));
+  Tables t;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_tuple(dev, H, W, dh, dw);
+    auto it = g_tables.find(key);
+    if (it == g_tables.end()) {
+      std::vector<int> xo, yo;
+      std::vector<short> xc, yc;
+      lanczos4_tables(W, dw, &xo, &xc);
+      lanczos4_tables(H, dh, &yo, &yc);
+      CVB_CUDA(cudaMalloc(&t.xofs, xo.size() * sizeof(int)));
+      CVB_CUDA(cudaMalloc(&t.yofs, yo.size() * sizeof(int)));
+      CVB_CUDA(cudaMalloc(&t.xcoef, xc.size() * sizeof(short)));
+      CVB_CUDA(cudaMalloc(&t.ycoef, yc.size() * sizeof(short)));
+      // synchronous copies from stack-lifetime host vectors (once per image geometry)
+      CVB_CUDA(cudaMemcpy(t.xofs, xo.data(), xo.size() * sizeof(int), cudaMemcpyHostToDevice));
+      CVB_CUDA(cudaMemcpy(t.yofs, yo.data(), yo.size() * sizeof(int), cudaMemcpyHostToDevice));
+      CVB_CUDA(cudaMemcpy(t.xcoef, xc.data(), xc.size() * sizeof(short), cudaMemcpyHostToDevice));
+      CVB_CUDA(cudaMemcpy(t.ycoef, yc.data(), yc.size() * sizeof(short), cudaMemcpyHostToDevice));
+      g_tables.emplace(key, t);
+    } else {
+      t = it->second;
+    }
+  }
+  const int n = dh * dw;
+  CVB_TRY(launch_pdl(lanczos4_policy_image_kernel, dim3((n + 127) / 128), dim3(128), 0, st, 1, img_hwc, H, W, dh, dw, t.xofs,
+                     t.xcoef, t.yofs, t.ycoef, out_u8_hwc, out_f32_chw));
+  CVB_LAUNCHED();
+  return 0;
+}
+
+}  // namespace cvb

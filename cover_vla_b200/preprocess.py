@@ -1,0 +1,28 @@
+"""Device-side observation pre-processing.
+
+`policy_image` replaces BridgeSimplerAdapter.preprocess (INT-ACT/src/experiments/env_adapters/simpler.py:43-65): the uint8
+simulator frame is copied to the device once and resized with cv2's INTER_LANCZOS4 arithmetic (bit-exact), then scaled to
+[-1, 1] exactly as src/utils/pipeline.py:34-69 does."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def policy_image(frame_u8_hwc: torch.Tensor, size: int = 224, return_u8: bool = False):
+    """frame uint8 [H, W, 3] (CUDA, contiguous) -> float32 [1, 3, size, size] in [-1, 1] (and the uint8 HWC resize)."""
+    assert frame_u8_hwc.dtype == torch.uint8 and frame_u8_hwc.is_cuda and frame_u8_hwc.is_contiguous()
+    H, W, ch = frame_u8_hwc.shape
+    assert ch == 3, "expected an RGB frame"
+    lib = _lib.load()
+    out = torch.empty(1, 3, size, size, dtype=torch.float32, device=frame_u8_hwc.device)
+    u8 = torch.empty(size, size, 3, dtype=torch.uint8, device=frame_u8_hwc.device) if return_u8 else None
+    lib.cvb_preprocess_policy_image.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                C.c_void_p]
+    with torch.cuda.device(frame_u8_hwc.device):
+        _lib.check(lib.cvb_preprocess_policy_image(_lib.ptr(frame_u8_hwc), H, W, size, size, _lib.ptr(u8), _lib.ptr(out),
+                                                   _lib.stream_ptr()))
+    return (out, u8) if return_u8 else out

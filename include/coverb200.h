@@ -208,6 +208,13 @@ CVB_API int cvb_format_trajectories(const float* actions, int n_cand, int chunk,
 CVB_API int cvb_execution_action(const float* actions, int n_cand, int chunk, int action_stride,
                                  const double* p01_host, const double* p99_host, const int32_t* best_idx, int K,
                                  int step, double* exec_action, int32_t* votes, void* stream);
+/* Policy-side observation pre-processing on the device (replaces BridgeSimplerAdapter.preprocess,
+ * INT-ACT/src/experiments/env_adapters/simpler.py:43-65: cv2.resize(frame, (out_w, out_h), interpolation=cv2.INTER_LANCZOS4)
+ * then process_images, src/utils/pipeline.py:34-69).  img_u8_hwc: device uint8 [H, W, 3]; out_u8_hwc: device uint8
+ * [out_h, out_w, 3] (bit-exact with cv2, may be NULL); out_f32_chw: device f32 [3, out_h, out_w] = (u8 / 255 - 0.5) / 0.5
+ * (may be NULL).  Coefficient tables are computed once per geometry (host, synchronous) and cached. */
+CVB_API int cvb_preprocess_policy_image(const uint8_t* img_u8_hwc, int H, int W, int out_h, int out_w,
+                                        uint8_t* out_u8_hwc, float* out_f32_chw, void* stream);
 /* One whole CoVer decision in one call / one CUDA graph: cvb_pi0_sample -> cvb_format_trajectories ->
  * cvb_verifier_score for N = R*K candidates (the body of run_simpler_eval_with_openpi.py:322-363 on the device, no host
  * round trip in between).  The verifier's image/text side is forked onto an internal stream after the prefix and runs

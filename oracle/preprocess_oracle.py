@@ -1,0 +1,82 @@
+"""TEST INFRASTRUCTURE ONLY (oracle): CPU restatement of the policy-side observation pre-processing.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline leg may import it.
+
+Follows (reference, /root/reference):
+  * BridgeSimplerAdapter.preprocess   INT-ACT/src/experiments/env_adapters/simpler.py:43-65: cv2.resize(obs, (224, 224),
+    interpolation=cv2.INTER_LANCZOS4) on the uint8 HWC frame, then process_images(rescale 1/255, mean 0.5, std 0.5)
+  * process_images / rescale / normalize   INT-ACT/src/utils/pipeline.py:34-69 (float32 torch arithmetic)
+Third-party arithmetic: OpenCV (opencv-python, unpinned in /root/reference/requirements.txt; 4.13.0 in this image).  The
+8-bit INTER_LANCZOS4 path of cv::resize is restated from its published algorithm (imgproc/src/resize.cpp: resizeGeneric_
+with HResizeLanczos4<uchar,int,short> / VResizeLanczos4<..., FixedPtCast<int,uchar,22>>; interpolateLanczos4; coefficients
+quantised to 11 bits with cvRound; replicated borders; no anti-aliasing) and PINNED bit for bit against cv2.resize itself:
+tests/test_preprocess.py runs cv2 live (it is part of the image, here and on the GPU box) and replays the committed
+tests/golden/preprocess_lanczos4.npz made by oracle/make_golden_preprocess.py.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+_S45 = 0.70710678118654752440084436210485
+_CS = [(1, 0), (-_S45, -_S45), (0, 1), (_S45, -_S45), (-1, 0), (_S45, _S45), (0, -1), (-_S45, _S45)]
+_PI = 3.1415926535897932384626433832795
+COEF_BITS = 11  # INTER_RESIZE_COEF_BITS
+
+
+def lanczos4_coeffs(x) -> np.ndarray:
+    """cv::interpolateLanczos4 (float / double mix as in OpenCV)."""
+    x = np.float32(x)
+    co = np.zeros(8, dtype=np.float32)
+    s = np.float32(0)
+    y0 = -(float(x) + 3) * _PI * 0.25
+    s0, c0 = math.sin(y0), math.cos(y0)
+    for i in range(8):
+        y0_ = np.float32(x + np.float32(3) - np.float32(i))
+        if abs(y0_) >= np.float32(1e-6):
+            y = -float(y0_) * _PI * 0.25
+            co[i] = np.float32((_CS[i][0] * s0 + _CS[i][1] * c0) / (y * y))
+        else:
+            co[i] = np.float32(1e30)
+        s = np.float32(s + co[i])
+    s = np.float32(np.float32(1) / s)
+    return (co * s).astype(np.float32)
+
+
+def lanczos4_tables(src: int, dst: int):
+    """Per destination index: first-tap source offset (sx, taps at sx - 3 .. sx + 4) and 8 int16 coefficients."""
+    scale = 1.0 / (dst / src)
+    ofs = np.zeros(dst, dtype=np.int32)
+    coef = np.zeros((dst, 8), dtype=np.int16)
+    for d in range(dst):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        s = int(math.floor(f))
+        f = np.float32(f - np.float32(s))
+        ofs[d] = s
+        c = lanczos4_coeffs(f)
+        coef[d] = np.clip(np.rint(c * np.float32(1 << COEF_BITS)), -32768, 32767).astype(np.int16)
+    return ofs, coef
+
+
+def resize_lanczos4_u8(img: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LANCZOS4) for uint8 HWC images, bit-exact."""
+    H, W, _ = img.shape
+    xo, xa = lanczos4_tables(W, dw)
+    yo, ya = lanczos4_tables(H, dh)
+    src = img.astype(np.int64)
+    tmp = np.zeros((H, dw, img.shape[2]), dtype=np.int64)
+    for k in range(8):
+        tmp += src[:, np.clip(xo + k - 3, 0, W - 1), :] * xa[None, :, k, None].astype(np.int64)
+    out = np.zeros((dh, dw, img.shape[2]), dtype=np.int64)
+    for k in range(8):
+        out += tmp[np.clip(yo + k - 3, 0, H - 1), :, :] * ya[:, k, None, None].astype(np.int64)
+    out = (out + (1 << (2 * COEF_BITS - 1))) >> (2 * COEF_BITS)
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def policy_image(img_u8_hwc: np.ndarray, size: int = 224):
+    """simpler.py:47-65 -> (uint8 [size, size, 3], float32 [1, 3, size, size] in [-1, 1])."""
+    small = resize_lanczos4_u8(img_u8_hwc, size, size)
+    x = small.transpose(2, 0, 1)[None].astype(np.float32) * np.float32(1 / 255.0)   # pipeline.py:34-39
+    x = (x - np.float32(0.5)) / np.float32(0.5)                                     # pipeline.py:42-55
+    return small, x.astype(np.float32)

@@ -80,6 +80,10 @@ int layernorm_f32(cudaStream_t st, const float* x, const float* resid, const flo
 int preprocess_policy_image(cudaStream_t st, const uint8_t* img_hwc, int H, int W, int dh, int dw, uint8_t* out_u8_hwc,
                             float* out_f32_chw);
 
+// PIL Image.resize((dw, dh), BICUBIC) bit-exact (+ optional ToTensor / Normalize(0.5, 0.5) float32 CHW output)
+int preprocess_verifier_image(cudaStream_t st, const uint8_t* img_hwc, int H, int W, int dh, int dw, uint8_t* out_u8_hwc,
+                              float* out_f32_chw);
+
 // ---- attention (attention.cuh) -----------------------------------------------------------------
 struct AttnCall {
   // Q rows for batch b, head h, token t:  q + (b*q_batch_stride + t*q_row_stride + h*head_dim)

@@ -155,4 +155,145 @@ int preprocess_policy_image(cudaStream_t st, const uint8_t* img_hwc, int H, int 
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Verifier-side image transform on the device: open_clip's SigLIP transform as the reference applies it
+// (bridge_verifier/ensemble_eval/efficient_ensemble_merged.py:249-254 -> self.preprocess = open_clip image transform:
+// PIL Image.resize((384, 384), BICUBIC), ToTensor (x / 255), Normalize(mean 0.5, std 0.5)).  Pillow's 8-bit resampler
+// (src/libImaging/Resample.c; Pillow is unpinned in the reference, 12.2.0 in this image) is integer arithmetic: per
+// output index a window [xmin, xmin + n) of normalised double-precision bicubic weights (a = -0.5, support 2 x the
+// down-scale factor) quantised to 22 bits, a horizontal pass to an 8-bit intermediate (rounded, clipped), then the
+// vertical pass.  Tables are built on the host as Pillow does; the kernel evaluates both passes for one output pixel
+// per thread.  Bit-exact against PIL (tests/test_preprocess.py).
+namespace {
+
+constexpr int kPilPrecision = 22;
+
+double pil_bicubic(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+
+// precompute_coeffs + normalize_coeffs_8bpc of Resample.c; returns ksize
+int pil_tables(int in_size, int out_size, std::vector<int>* bounds, std::vector<int>* kk) {
+  double scale, filterscale;
+  filterscale = scale = static_cast<double>(in_size) / out_size;
+  if (filterscale < 1.0) filterscale = 1.0;
+  const double support = 2.0 * filterscale;
+  const int ksize = static_cast<int>(std::ceil(support)) * 2 + 1;
+  bounds->assign(static_cast<size_t>(out_size) * 2, 0);
+  kk->assign(static_cast<size_t>(out_size) * ksize, 0);
+  std::vector<double> k(ksize);
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    double ww = 0.0;
+    const double ss = 1.0 / filterscale;
+    int xmin = static_cast<int>(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    for (int x = 0; x < ksize; ++x) k[x] = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      const double w = pil_bicubic((x + xmin - center + 0.5) * ss);
+      k[x] = w;
+      ww += w;
+    }
+    for (int x = 0; x < xmax; ++x)
+      if (ww != 0.0) k[x] /= ww;
+    for (int x = 0; x < ksize; ++x) {
+      const double v = k[x] * (1 << kPilPrecision);
+      (*kk)[static_cast<size_t>(xx) * ksize + x] = k[x] < 0 ? static_cast<int>(-0.5 + v) : static_cast<int>(0.5 + v);
+    }
+    (*bounds)[xx * 2] = xmin;
+    (*bounds)[xx * 2 + 1] = xmax;
+  }
+  return ksize;
+}
+
+struct PilTables {
+  int *xb = nullptr, *yb = nullptr, *xk = nullptr, *yk = nullptr;
+  int xks = 0, yks = 0;
+};
+std::map<std::tuple<int, int, int, int, int>, PilTables> g_pil_tables;
+
+__device__ __forceinline__ int pil_clip8(unsigned acc) {
+  const int v = static_cast<int>(acc) >> kPilPrecision;
+  return min(max(v, 0), 255);
+}
+
+__global__ void __launch_bounds__(128) pil_bicubic_image_kernel(const uint8_t* __restrict__ img, int H, int W, int dh, int dw,
+                                                                const int* __restrict__ xb, const int* __restrict__ xk,
+                                                                int xks, const int* __restrict__ yb,
+                                                                const int* __restrict__ yk, int yks,
+                                                                uint8_t* __restrict__ out_u8, float* __restrict__ out_f32) {
+  pdl_wait();
+  pdl_launch();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= dh * dw) return;
+  const int yy = idx / dw, xx = idx % dw;
+  const int xmin = xb[xx * 2], xn = xb[xx * 2 + 1];
+  const int ymin = yb[yy * 2], yn = yb[yy * 2 + 1];
+  const unsigned half = 1u << (kPilPrecision - 1);
+  unsigned acc[3] = {half, half, half};
+  for (int y = 0; y < yn; ++y) {
+    const uint8_t* row = img + (static_cast<long>(ymin + y) * W + xmin) * 3;
+    unsigned h[3] = {half, half, half};
+    for (int x = 0; x < xn; ++x) {
+      const int kx = xk[xx * xks + x];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) h[c] += static_cast<unsigned>(static_cast<int>(row[x * 3 + c]) * kx);
+    }
+    const int ky = yk[yy * yks + y];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] += static_cast<unsigned>(pil_clip8(h[c]) * ky);  // 8-bit intermediate image
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int u = pil_clip8(acc[c]);
+    if (out_u8 != nullptr) out_u8[(static_cast<long>(yy) * dw + xx) * 3 + c] = static_cast<uint8_t>(u);
+    if (out_f32 != nullptr)  // ToTensor: x / 255; Normalize: (x - 0.5) / 0.5 (float32)
+      out_f32[(static_cast<long>(c) * dh + yy) * dw + xx] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(u), 255.0f), 0.5f), 0.5f);
+  }
+}
+
+}  // namespace
+
+int preprocess_verifier_image(cudaStream_t st, const uint8_t* img_hwc, int H, int W, int dh, int dw, uint8_t* out_u8_hwc,
+                              float* out_f32_chw) {
+  CVB_REQUIRE(img_hwc != nullptr && (out_u8_hwc != nullptr || out_f32_chw != nullptr), "null argument");
+  CVB_REQUIRE(H >= 1 && W >= 1 && dh >= 1 && dw >= 1 && H <= 16384 && W <= 16384, "image sizes out of range");
+  int dev = 0;
+  CVB_CUDA(cudaGetDevice(&dev));
+  PilTables t;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_tuple(dev, H, W, dh, dw);
+    auto it = g_pil_tables.find(key);
+    if (it == g_pil_tables.end()) {
+      std::vector<int> xb, yb, xk, yk;
+      t.xks = pil_tables(W, dw, &xb, &xk);
+      t.yks = pil_tables(H, dh, &yb, &yk);
+      CVB_CUDA(cudaMalloc(&t.xb, xb.size() * sizeof(int)));
+      CVB_CUDA(cudaMalloc(&t.yb, yb.size() * sizeof(int)));
+      CVB_CUDA(cudaMalloc(&t.xk, xk.size() * sizeof(int)));
+      CVB_CUDA(cudaMalloc(&t.yk, yk.size() * sizeof(int)));
+      CVB_CUDA(cudaMemcpy(t.xb, xb.data(), xb.size() * sizeof(int), cudaMemcpyHostToDevice));
+      CVB_CUDA(cudaMemcpy(t.yb, yb.data(), yb.size() * sizeof(int), cudaMemcpyHostToDevice));
+      CVB_CUDA(cudaMemcpy(t.xk, xk.data(), xk.size() * sizeof(int), cudaMemcpyHostToDevice));
+      CVB_CUDA(cudaMemcpy(t.yk, yk.data(), yk.size() * sizeof(int), cudaMemcpyHostToDevice));
+      g_pil_tables.emplace(key, t);
+    } else {
+      t = it->second;
+    }
+  }
+  const int n = dh * dw;
+  CVB_TRY(launch_pdl(pil_bicubic_image_kernel, dim3((n + 127) / 128), dim3(128), 0, st, 1, img_hwc, H, W, dh, dw, t.xb, t.xk,
+                     t.xks, t.yb, t.yk, t.yks, out_u8_hwc, out_f32_chw));
+  CVB_LAUNCHED();
+  return 0;
+}
+
 }  // namespace cvb

@@ -26,3 +26,20 @@ def policy_image(frame_u8_hwc: torch.Tensor, size: int = 224, return_u8: bool = 
         _lib.check(lib.cvb_preprocess_policy_image(_lib.ptr(frame_u8_hwc), H, W, size, size, _lib.ptr(u8), _lib.ptr(out),
                                                    _lib.stream_ptr()))
     return (out, u8) if return_u8 else out
+
+
+def verifier_image(frame_u8_hwc: torch.Tensor, size: int = 384, return_u8: bool = False):
+    """open_clip's SigLIP image transform (PIL bicubic squash-resize -> [0, 1] -> (x - 0.5) / 0.5) on the device:
+    frame uint8 [H, W, 3] (CUDA, contiguous) -> float32 [1, 3, size, size]; the uint8 resize is bit-exact with Pillow."""
+    assert frame_u8_hwc.dtype == torch.uint8 and frame_u8_hwc.is_cuda and frame_u8_hwc.is_contiguous()
+    H, W, ch = frame_u8_hwc.shape
+    assert ch == 3, "expected an RGB frame"
+    lib = _lib.load()
+    out = torch.empty(1, 3, size, size, dtype=torch.float32, device=frame_u8_hwc.device)
+    u8 = torch.empty(size, size, 3, dtype=torch.uint8, device=frame_u8_hwc.device) if return_u8 else None
+    lib.cvb_preprocess_verifier_image.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p]
+    with torch.cuda.device(frame_u8_hwc.device):
+        _lib.check(lib.cvb_preprocess_verifier_image(_lib.ptr(frame_u8_hwc), H, W, size, size, _lib.ptr(u8), _lib.ptr(out),
+                                                     _lib.stream_ptr()))
+    return (out, u8) if return_u8 else out

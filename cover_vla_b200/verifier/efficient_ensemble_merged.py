@@ -94,6 +94,8 @@ class EfficientEnsembleMerged:
         self.engine = engine
         self.tokenizer = tokenizer
         self.preprocess = preprocess or default_preprocess(engine.cfg.vf_image)
+        # RGB uint8 frames (PIL images / arrays) take the device-side transform unless a custom preprocess was injected
+        self._device_preprocess = preprocess is None
         self.siglip_model = _SiglipShim(engine.cfg.vf_text_ctx)
         self._ctx_key = None
 
@@ -116,8 +118,15 @@ class EfficientEnsembleMerged:
             img = image.to(torch.float32)
             raw = img.cpu().numpy().tobytes() if not img.is_cuda else None
         else:
-            raw = np.asarray(image).tobytes()
-            img = self.preprocess(image)
+            arr = np.asarray(image)
+            raw = arr.tobytes()
+            if self._device_preprocess and arr.dtype == np.uint8 and arr.ndim == 3 and arr.shape[2] == 3:
+                # open_clip's transform on the device (bit-exact with PIL's bicubic resize): one uint8 H2D copy
+                from .. import preprocess as _pp
+                img = _pp.verifier_image(torch.from_numpy(np.ascontiguousarray(arr)).to(self.device),
+                                         self.engine.cfg.vf_image)[0]
+            else:
+                img = self.preprocess(image)
         tok = self._tokens(instruction)
         key = None
         if raw is not None:

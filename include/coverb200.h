@@ -215,6 +215,11 @@ CVB_API int cvb_execution_action(const float* actions, int n_cand, int chunk, in
  * (may be NULL).  Coefficient tables are computed once per geometry (host, synchronous) and cached. */
 CVB_API int cvb_preprocess_policy_image(const uint8_t* img_u8_hwc, int H, int W, int out_h, int out_w,
                                         uint8_t* out_u8_hwc, float* out_f32_chw, void* stream);
+/* Verifier-side image transform on the device (replaces the open_clip transform the reference applies at
+ * bridge_verifier/ensemble_eval/efficient_ensemble_merged.py:249-254: PIL resize((out_w, out_h), BICUBIC), ToTensor,
+ * Normalize(0.5, 0.5)).  Same conventions as cvb_preprocess_policy_image; out_u8_hwc is bit-exact with Pillow. */
+CVB_API int cvb_preprocess_verifier_image(const uint8_t* img_u8_hwc, int H, int W, int out_h, int out_w,
+                                          uint8_t* out_u8_hwc, float* out_f32_chw, void* stream);
 /* One whole CoVer decision in one call / one CUDA graph: cvb_pi0_sample -> cvb_format_trajectories ->
  * cvb_verifier_score for N = R*K candidates (the body of run_simpler_eval_with_openpi.py:322-363 on the device, no host
  * round trip in between).  The verifier's image/text side is forked onto an internal stream after the prefix and runs

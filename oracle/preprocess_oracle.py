@@ -80,3 +80,82 @@ def policy_image(img_u8_hwc: np.ndarray, size: int = 224):
     x = small.transpose(2, 0, 1)[None].astype(np.float32) * np.float32(1 / 255.0)   # pipeline.py:34-39
     x = (x - np.float32(0.5)) / np.float32(0.5)                                     # pipeline.py:42-55
     return small, x.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Verifier image: open_clip's SigLIP transform as applied at bridge_verifier/ensemble_eval/efficient_ensemble_merged.py:
+# 249-254 (self.preprocess): PIL Image.resize((384, 384), BICUBIC) -> ToTensor -> Normalize(0.5, 0.5).  Pillow's 8-bit
+# resampler (src/libImaging/Resample.c: precompute_coeffs, normalize_coeffs_8bpc, ImagingResampleHorizontal_8bpc /
+# Vertical_8bpc; Pillow unpinned in the reference, 12.2.0 here) restated and pinned bit for bit against PIL itself.
+_PIL_PREC = 22
+
+
+def _pil_bicubic(x: float) -> float:
+    a = -0.5
+    x = abs(x)
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def pil_tables(in_size: int, out_size: int):
+    scale = filterscale = in_size / out_size
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = 2.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), dtype=np.int64)
+    kk = np.zeros((out_size, ksize), dtype=np.int64)
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        ww = 0.0
+        ss = 1.0 / filterscale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        k = [0.0] * ksize
+        for x in range(xmax):
+            w = _pil_bicubic((x + xmin - center + 0.5) * ss)
+            k[x] = w
+            ww += w
+        for x in range(xmax):
+            if ww != 0.0:
+                k[x] /= ww
+        for x in range(ksize):
+            v = k[x] * (1 << _PIL_PREC)
+            kk[xx, x] = int(-0.5 + v) if k[x] < 0 else int(0.5 + v)
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk
+
+
+def resize_pil_bicubic_u8(img: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """np.asarray(Image.fromarray(img).resize((dw, dh), Image.BICUBIC)) for uint8 RGB images, bit-exact."""
+    H, W, ch = img.shape
+    bx, kx = pil_tables(W, dw)
+    by, ky = pil_tables(H, dh)
+    src = img.astype(np.int64)
+    half = 1 << (_PIL_PREC - 1)
+    tmp = np.zeros((H, dw, ch), dtype=np.int64)
+    for xx in range(dw):
+        xmin, n = bx[xx]
+        ss = np.full((H, ch), half, dtype=np.int64)
+        for x in range(n):
+            ss += src[:, xmin + x, :] * kx[xx, x]
+        tmp[:, xx, :] = np.clip(ss >> _PIL_PREC, 0, 255)
+    out = np.zeros((dh, dw, ch), dtype=np.int64)
+    for yy in range(dh):
+        ymin, n = by[yy]
+        ss = np.full((dw, ch), half, dtype=np.int64)
+        for y in range(n):
+            ss += tmp[ymin + y] * ky[yy, y]
+        out[yy] = np.clip(ss >> _PIL_PREC, 0, 255)
+    return out.astype(np.uint8)
+
+
+def verifier_image(img_u8_hwc: np.ndarray, size: int = 384):
+    """-> (uint8 [size, size, 3], float32 [1, 3, size, size]): resize, ToTensor (x / 255), Normalize(0.5, 0.5)."""
+    small = resize_pil_bicubic_u8(img_u8_hwc, size, size)
+    x = small.transpose(2, 0, 1)[None].astype(np.float32) / np.float32(255)
+    x = (x - np.float32(0.5)) / np.float32(0.5)
+    return small, x.astype(np.float32)

@@ -62,3 +62,60 @@ def test_cuda_policy_image_matches_live_cv2():
         ref = cv2.resize(img, (S, S), interpolation=cv2.INTER_LANCZOS4)
         _, u8 = preprocess.policy_image(torch.from_numpy(img).cuda(), S, return_u8=True)
         assert np.array_equal(u8.cpu().numpy(), ref), (H, W, S)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# verifier image: open_clip's SigLIP transform (PIL bicubic 384, ToTensor, Normalize) as applied at
+# bridge_verifier/ensemble_eval/efficient_ensemble_merged.py:249-254
+# ---------------------------------------------------------------------------------------------------------------
+def _vfull_frame():
+    return np.random.default_rng(4321).integers(0, 256, size=(256, 256, 3), dtype=np.uint8)
+
+
+def test_verifier_image_oracle_matches_pil_golden_bit_exact():
+    z = np.load(GOLD)
+    for i in range(int(z["vn"])):
+        u8, f32 = P.verifier_image(z[f"vimg{i}"], int(z[f"vsize{i}"]))
+        assert np.array_equal(u8, z[f"vu8_{i}"]) and np.array_equal(f32, z[f"vf32_{i}"])
+    u8, f32 = P.verifier_image(_vfull_frame(), 384)
+    assert hashlib.sha256(u8.tobytes()).hexdigest() == str(z["vfull_u8_sha256"])
+    assert hashlib.sha256(f32.tobytes()).hexdigest() == str(z["vfull_f32_sha256"])
+
+
+def test_verifier_image_oracle_matches_live_pil_and_the_host_mirror():
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(6)
+    for H, W, S in [(256, 256, 384), (480, 640, 384), (100, 77, 64), (384, 384, 384)]:
+        img = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+        ref = np.asarray(Image.fromarray(img).convert("RGB").resize((S, S), Image.BICUBIC))
+        assert np.array_equal(P.resize_pil_bicubic_u8(img, S, S), ref), (H, W, S)
+    # the host-side mirror of the reference transform (cover_vla_b200.verifier) produces the same float32 tensor
+    from cover_vla_b200.verifier import efficient_ensemble_merged as E
+    img = _vfull_frame()
+    host = E.default_preprocess(384)(Image.fromarray(img))
+    assert np.array_equal(host.numpy()[None], P.verifier_image(img, 384)[1])
+
+
+@pytest.mark.gpu
+def test_cuda_verifier_image_is_bit_exact():
+    from cover_vla_b200 import preprocess
+    z = np.load(GOLD)
+    for i in range(int(z["vn"])):
+        f32, u8 = preprocess.verifier_image(torch.from_numpy(z[f"vimg{i}"]).cuda(), int(z[f"vsize{i}"]), return_u8=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(u8.cpu().numpy(), z[f"vu8_{i}"]) and np.array_equal(f32.cpu().numpy(), z[f"vf32_{i}"])
+    f32, u8 = preprocess.verifier_image(torch.from_numpy(_vfull_frame()).cuda(), 384, return_u8=True)
+    assert hashlib.sha256(u8.cpu().numpy().tobytes()).hexdigest() == str(z["vfull_u8_sha256"])
+    assert hashlib.sha256(f32.cpu().numpy().tobytes()).hexdigest() == str(z["vfull_f32_sha256"])
+
+
+@pytest.mark.gpu
+def test_cuda_verifier_image_matches_live_pil():
+    Image = pytest.importorskip("PIL.Image")
+    from cover_vla_b200 import preprocess
+    rng = np.random.default_rng(10)
+    for H, W, S in [(256, 256, 384), (480, 640, 384), (1080, 1920, 384), (64, 48, 384)]:
+        img = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+        ref = np.asarray(Image.fromarray(img).convert("RGB").resize((S, S), Image.BICUBIC))
+        _, u8 = preprocess.verifier_image(torch.from_numpy(img).cuda(), S, return_u8=True)
+        assert np.array_equal(u8.cpu().numpy(), ref), (H, W, S)

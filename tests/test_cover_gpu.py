@@ -130,8 +130,21 @@ def test_policy_and_ensemble_surfaces():
     assert int(gi1) == 0 and abs(ms1 - float(ref_scores[0])) < 5e-3
     hist, sc = ens.predict(vin["image"][0], vin["tokens"][0], vin["histories"])
     assert len(sc) == N and abs(sc["0"] - float(ref_scores[0])) < 5e-3
+    # a uint8 frame through the DEFAULT transform takes the device-side open_clip transform (bit-exact with PIL), so the
+    # scores equal those of the host-side PIL route exactly
+    from PIL import Image
+    from cover_vla_b200.verifier.efficient_ensemble_merged import default_preprocess
+    frame = np.random.default_rng(0).integers(0, 256, size=(96, 128, 3)).astype(np.uint8)
+    ens2 = EfficientEnsembleMerged(ensemble_components=comps, trunk_state_dict=trunk, vf_config=vf_cfg, max_candidates=N)
+    s_dev = ens2.compute_max_similarity_scores_batch([Image.fromarray(frame)] * N, instr, vin["histories"],
+                                                     cfg_repeat_language_instructions=K)[0]
+    host_img = default_preprocess(v.image)(Image.fromarray(frame))
+    s_host = ens.compute_max_similarity_scores_batch([host_img] * N, instr, vin["histories"],
+                                                     cfg_repeat_language_instructions=K)[0]
+    assert s_dev == s_host
     policy.engine.close()
     ens.engine.close()
+    ens2.engine.close()
 
 
 @pytest.mark.parametrize("with_past", [True, False])

@@ -119,6 +119,7 @@ int launch_2sm(cudaStream_t st, const GemmCall& c) {
 bool use_2sm(const GemmCall& c) {
   static const int env = getenv("CVB_GEMM_2SM") != nullptr ? atoi(getenv("CVB_GEMM_2SM")) : 1;
   if (c.m_dev != nullptr || c.K % 8 != 0 || c.N % 8 != 0) return false;
+  if (c.ldc % 8 != 0 && c.epi != EPI_F32) return false;  // 16-byte vector stores of the shared epilogue
   if (c.force_bn == 512) return true;
   if (env == 0 || c.force_bn != 0) return false;
   const long tiles = static_cast<long>((c.M + 255) / 256) * ((c.N + 255) / 256);

@@ -123,7 +123,7 @@ class EfficientEnsembleMerged:
             if self._device_preprocess and arr.dtype == np.uint8 and arr.ndim == 3 and arr.shape[2] == 3:
                 # open_clip's transform on the device (bit-exact with PIL's bicubic resize): one uint8 H2D copy
                 from .. import preprocess as _pp
-                img = _pp.verifier_image(torch.from_numpy(np.ascontiguousarray(arr)).to(self.device),
+                img = _pp.verifier_image(torch.from_numpy(np.array(arr)).to(self.device),
                                          self.engine.cfg.vf_image)[0]
             else:
                 img = self.preprocess(image)

@@ -194,16 +194,33 @@ __global__ void __launch_bounds__(256) action_out_euler_kernel(const bf16* __res
                                                                float dt) {
   pdl_wait();
   pdl_launch();
+  // one CTA per (candidate, chunk step): the row is staged once in shared memory (fp32), then 8 threads per output
+  // stream its weight row with independent 16-byte loads (all in flight at once: the previous one-warp-per-output
+  // loop was a chain of exposed L2 round trips, 27 us per launch) and combine in a fixed shuffle order.
+  extern __shared__ float hs[];
   const int n = blockIdx.x / chunk, j = blockIdx.x % chunk;
   const bf16* h = hn + (static_cast<long>(n) * suffix_len + (suffix_len - chunk) + j) * ld;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int o = warp; o < adim; o += nw) {
-    const float* wr = w + static_cast<long>(o) * width;
+  for (int i = threadIdx.x; i < width; i += blockDim.x) hs[i] = __bfloat162float(h[i]);
+  __syncthreads();
+  const int s = threadIdx.x & 7;
+  for (int o0 = 0; o0 < adim; o0 += 32) {
+    const int o = o0 + (threadIdx.x >> 3);
     float acc = 0.f;
-    for (int i = lane; i < width; i += 32) acc = fmaf(__bfloat162float(h[i]), wr[i], acc);
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) {
+    if (o < adim) {
+      const float* wr = w + static_cast<long>(o) * width;
+#pragma unroll 8
+      for (int k = s * 4; k < width; k += 32) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wr + k);
+        acc = fmaf(hs[k], w4.x, acc);
+        acc = fmaf(hs[k + 1], w4.y, acc);
+        acc = fmaf(hs[k + 2], w4.z, acc);
+        acc = fmaf(hs[k + 3], w4.w, acc);
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (s == 0 && o < adim) {
       const float v = acc + bias[o];
       const long idx = (static_cast<long>(n) * chunk + j) * adim + o;
       if (v_out != nullptr) v_out[idx] = v;
@@ -215,8 +232,9 @@ __global__ void __launch_bounds__(256) action_out_euler_kernel(const bf16* __res
 int action_out_euler(cudaStream_t st, const bf16* hn, long ld, const float* w, const float* bias,
                      float* x_t, float* v_out, int n_cand, int width, int adim, int chunk,
                      int suffix_len, float dt) {
-  CVB_TRY(launch_pdl(action_out_euler_kernel, dim3(n_cand * chunk), dim3(256), 0, st, 1, hn, ld, w, bias, x_t, v_out, width, adim,
-                                                         chunk, suffix_len, dt));
+  CVB_REQUIRE(width % 4 == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0, "action_out_proj rows must be 16-byte addressable");
+  CVB_TRY(launch_pdl(action_out_euler_kernel, dim3(n_cand * chunk), dim3(256), static_cast<size_t>(width) * sizeof(float), st, 1,
+                     hn, ld, w, bias, x_t, v_out, width, adim, chunk, suffix_len, dt));
   CVB_LAUNCHED();
   return 0;
 }

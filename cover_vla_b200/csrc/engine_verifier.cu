@@ -448,7 +448,7 @@ static int run_heads_context(cvb_handle* h, cudaStream_t st) {
 static int run_context(cvb_handle* h, cudaStream_t st) {
   const cvb_config& c = h->cfg;
   VerifierState& s = *h->vf;
-  const int Wd = c.vf_width, E = c.vf_embed, L = c.vf_pool_layers, M = c.vf_members;
+  const int Wd = c.vf_width;
   const int Np = (c.vf_image / c.vf_patch) * (c.vf_image / c.vf_patch), Tt = c.vf_text_ctx;
   // image tower -> patch features (hook output), text tower -> per-token projected features
   CVB_TRY(im2col_patches(st, s.in_image, s.patches, 3, c.vf_image, c.vf_image, c.vf_patch, s.kpad));

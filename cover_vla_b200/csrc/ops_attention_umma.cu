@@ -136,21 +136,6 @@ __device__ __forceinline__ void prob_chunk(const uint32_t (&rr)[16], int nv, flo
   }
 }
 
-// r[0..31] <- 32 (or 16) consecutive fp32 columns of this thread's TMEM lane
-__device__ __forceinline__ void ld_cols(uint32_t taddr, bool wide, uint32_t (&r)[32]) {
-  if (wide) {
-    tmem_ld_x32(taddr, r);
-  } else {
-    uint32_t r16[16];
-    tmem_ld_x16(taddr, r16);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) r[i] = r16[i];
-#pragma unroll
-    for (int i = 16; i < 32; ++i) r[i] = 0u;
-  }
-  tmem_wait_ld();
-}
-
 __global__ void __launch_bounds__(UA_THREADS, 1)
 attn_prefix_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmVT, const UmmaAttnParams p) {
@@ -435,7 +420,7 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int tk_pad = p.tk_pad;
-  const int KT = tk_pad + 16;  // S columns: prefix keys, then the 16-wide suffix-key tile
+  // S columns: tk_pad prefix keys, then the 16-wide suffix-key tile
   const uint32_t kblk = static_cast<uint32_t>(tk_pad) * 128u;
   const int nkb = (tk_pad + 63) / 64;
   const int kslots = 4u * UA_QBLK + 4u * UD_KSBLK + 4u * kblk <= static_cast<uint32_t>(UA_BODY_MAX) ? 4 : 3;
@@ -617,7 +602,7 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     const int L = q * 32 + lane;
     const int r = lane * 4 + q;
     const bool active = r < rows_total;
-    const int t = r / p.heads, h = r % p.heads;
+    const int t = r / p.heads;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const bool first_only = p.suffix_mask && t == 0;  // the state token sees only itself among the suffix keys
     // Column group g takes the prefix chunks g, g + 4, g + 8, ... and group 3 ends with the suffix chunk: a fixed
@@ -775,7 +760,6 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
       }
     }
     UD_TS(7);
-    (void)h;
   }
 
   tc_fence_before();

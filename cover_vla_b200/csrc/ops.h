@@ -31,7 +31,22 @@ struct GemmCall {
 int gemm_bf16(cudaStream_t st, const GemmCall& c);
 // Split-K GEMM (M <= 256) that leaves S fp32 partial products in C = float[S][M][ldc] (epi / bias / resid unused);
 // splits <= 0 picks S so that n_tiles * S fills the SMs once.  The partials are consumed by rmsnorm_reduce().
-int gemm_splitk_partial(cudaStream_t st, const GemmCall& c, int splits, int* splits_out);
+// With `norm` the reduction + residual + Gemma RMSNorm of rmsnorm_reduce() run inside the same launch (after a
+// grid-wide arrive counter); `norm->sync` = two zero-initialised device words owned by the caller.
+struct SplitKNorm {
+  const void* resid = nullptr;
+  int resid_is_f32 = 0;
+  long ldr = 0;
+  const void* w = nullptr;
+  int w_is_f32 = 0;
+  bf16* h_out = nullptr;
+  long ldh = 0;
+  bf16* y = nullptr;
+  long ldy = 0;
+  float eps = 1e-6f;
+  unsigned* sync = nullptr;
+};
+int gemm_splitk_partial(cudaStream_t st, const GemmCall& c, int splits, int* splits_out, const SplitKNorm* norm = nullptr);
 
 // ---- fp32 SIMT GEMM (sgemm.cuh): C = act(A[M,K] * W[N,K]^T + bias) (+ resid) -------------------
 enum SgemmAct : int { SACT_NONE = 0, SACT_RELU = 1, SACT_GELU_ERF = 2, SACT_SILU = 3 };

@@ -150,7 +150,8 @@ def run_gpu(args):
         R_max = max(rephrase_shard(R, world, r)[1] - rephrase_shard(R, world, r)[0] for r in range(world))
     else:
         R_loc = R_max = R
-    eng = S.build_engine(d, w, v, vw, R_max, K, device=device)
+    eng = S.build_engine(d, w, v, vw, R_max, K, device=device,
+                         use_cuda_graph=0 if os.environ.get("CVB_BENCH_EAGER") else 1)  # CVB_BENCH_EAGER=1: diagnostic only
     del w, vw
     t_build = time.time() - t0
     # episode mode: every rank has its own observation; sharded mode: all ranks see the SAME observation

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "../../include/coverb200.h"
+#include "expert_mega.h"
 #include "host_common.h"
 #include "ops.h"
 
@@ -124,6 +125,7 @@ struct Pi0State {
   int splitk_o = 0, splitk_d = 0;  // K-splits of o_proj / down_proj in the denoise loop (0 = fused-epilogue GEMMs)
   int lang_hint = 0;  // caller's bound on valid language tokens per prompt (0 = max_lang_len), cvb_pi0_set_lang_len_hint
   GraphCache graphs;  // key = (lang rows << 40) | R << 16 | K
+  ExpertMega mega;    // persistent expert kernel (engine_expert_mega.cu)
 };
 
 struct VerifierState;  // engine_verifier.cu
@@ -179,6 +181,10 @@ int pi0_sample(cvb_handle* h, const float* image, const int64_t* tokens, const i
 int pi0_run_phase(cvb_handle* h, int phase, int R, int K, cudaStream_t st);
 int64_t pi0_debug_copy(cvb_handle* h, const std::string& name, void* dst, int64_t max_bytes,
                        cudaStream_t st);
+
+int expert_mega_prepare(cvb_handle* h, cudaStream_t st);
+int expert_mega_program(cvb_handle* h, int rows, cudaStream_t st, const MegaProgram** out);
+int expert_mega_launch(cvb_handle* h, cudaStream_t st, const MegaProgram& pg, int first, int count);
 
 void verifier_required_weights(const cvb_config& c, std::vector<WeightSpec>* out);
 int verifier_finalize(cvb_handle* h, cudaStream_t st);

@@ -354,6 +354,7 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
     s.fuse_norm = (fe != nullptr && fe[0] == '1') && s.splitk_o > 0 && s.splitk_d > 0 &&
                   tiles * std::max(s.splitk_o, s.splitk_d) <= device_sm_count() && We % 4 == 0 && We <= 2048;
   }
+  CVB_TRY(expert_mega_prepare(h, st));  // persistent expert kernel (engine_expert_mega.cu), when the shape allows it
   return 0;
 }
 
@@ -518,6 +519,12 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
   const bool fused_rope = attention_group_eligible(probe) || attention_decode_eligible(probe) ||
                           attention_decode_umma_eligible(probe);
   if (fused_rope) CVB_TRY(rope_table(st, s.rope_timescale, s.plen, R, S, hd / 2, s.rope_tab));
+  // Persistent expert kernel: one launch per layer covers o_proj -> norm -> gate/up -> down -> norm -> next qkv with
+  // device-wide barriers instead of kernel boundaries and a weight ring that prefetches across them; only the
+  // attention stays a separate launch.
+  const MegaProgram* pg = nullptr;
+  const bool mega = s.mega.mode != 0 && attention_decode_umma_eligible(probe) && M <= 256;
+  if (mega) CVB_TRY(expert_mega_program(h, M, st, &pg));
   for (size_t step = 0; step < s.times.size(); ++step) {
     {  // embed_suffix (modeling_pi0.py:598-609), time half of mlp_in folded into time_vec[step]
       SgemmCall g2;
@@ -537,6 +544,34 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
       g3.A = s.a2, g3.lda = We, g3.W = w_out, g3.ldw = We, g3.M = Ma, g3.N = We, g3.K = We;
       g3.C = s.suffix, g3.ldc = We, g3.bias = b_out, g3.out_group = c.chunk_size;
       CVB_TRY(sgemm_f32(st, g3));
+    }
+    if (mega) {
+      const int Mmax = c.max_rephrases * c.max_samples * S;
+      int first = 0;
+      for (int l = 0; l < c.layers; ++l) {
+        CVB_TRY(expert_mega_launch(h, st, *pg, first, pg->attn_after[l] - first));
+        first = pg->attn_after[l];
+        AttnCall a;
+        a.rope = s.rope_tab, a.kv0_static = 1;
+        a.q = s.qkv_e, a.q_batch_stride = (long)S * qkvw, a.q_row_stride = qkvw;
+        a.k0 = s.kcache + l * layer_stride, a.v0 = s.vcache + l * layer_stride;
+        a.kv0_batch_stride = (long)P * hd, a.kv0_row_stride = hd, a.kv0_len_dev = s.plen, a.kv0_max = h->n_img() + h->lang_rows();
+        a.q_per_kv_batch = K;
+        a.vt0 = s.vt_p + (size_t)l * c.max_rephrases * hd * s.vt_ld, a.vt0_ld = s.vt_ld;
+        a.k1 = s.qkv_e + qd, a.v1 = s.qkv_e + qd + hd, a.kv1_batch_stride = (long)S * qkvw;
+        a.kv1_row_stride = qkvw, a.kv1_len = S, a.suffix_mask = 1;
+        a.q_part = s.mega.part_qkv, a.k1_part = s.mega.part_qkv + qd, a.v1_part = s.mega.part_qkv + qd + hd;
+        a.part_splits = pg->host[pg->attn_after[l] - 1].splits, a.part_split_stride = (long)Mmax * qkvw;
+        a.out = s.attn_e, a.o_batch_stride = (long)S * qd, a.o_row_stride = qd;
+        a.batches = N, a.heads = c.heads, a.kv_heads = 1, a.tq = S, a.head_dim = hd;
+        a.scale = 1.0f / sqrtf(static_cast<float>(hd));
+        a.algo = 3;
+        CVB_TRY(attention(st, a));
+      }
+      CVB_TRY(expert_mega_launch(h, st, *pg, first, static_cast<int>(pg->host.size()) - first));
+      CVB_TRY(action_out_euler(st, s.xe, We, w_aout, b_aout, s.x_t, step == 0 ? s.v0 : nullptr, N, We,
+                               c.max_action_dim, c.chunk_size, S, s.dt));
+      continue;
     }
     // pending = split-K partials of the previous down_proj still to be folded into he by the next norm
     // (-1: the previous down_proj launch already did it - fused tail - and xe holds the normalised rows)

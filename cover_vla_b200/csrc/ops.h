@@ -134,6 +134,13 @@ struct AttnCall {
   // length): enables the tcgen05 decode kernel (ops_attention_umma.cu) for MQA / head_dim 256 shapes
   const bf16* vt0 = nullptr;
   long vt0_ld = 0;
+  // optional (tcgen05 decode kernel only): q / k1 / v1 given as fp32 split-K partials of the fused qkv projection,
+  // [part_splits][same element strides as q / k1 / v1]; summed in split order and rounded to bf16 while staging
+  const float* q_part = nullptr;
+  const float* k1_part = nullptr;
+  const float* v1_part = nullptr;
+  int part_splits = 0;
+  long part_split_stride = 0;
 };
 int attention(cudaStream_t st, const AttnCall& c);
 

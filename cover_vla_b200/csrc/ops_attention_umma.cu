@@ -385,7 +385,41 @@ struct UmmaDecodeParams {
   int kv0_static;
   const float2* rope;  // [kv batches][tq][128] (cos, sin) or nullptr
   unsigned long long* ts;  // diagnostics (cvb_debug_set_timestamps) or nullptr
+  // optional: the fused qkv projection as fp32 split-K partials [part_S][rows][same strides as q / k1 / v1] (written by
+  // the persistent expert kernel, expert_mega.cuh): summed in split order and rounded to bf16 while staging
+  const float* qf;
+  const float* k1f;
+  const float* v1f;
+  int part_S;
+  long part_ss;
 };
+
+// 8 consecutive bf16 of the qkv projection at element offset `off`: plain load, or sum of the fp32 partials -> bf16
+__device__ __forceinline__ uint4 ud_load8(const bf16* base, const float* part, long off, int S, long ss) {
+  if (part == nullptr) return *reinterpret_cast<const uint4*>(base + off);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  int s = 0;
+  for (; s + 4 <= S; s += 4) {  // eight loads in flight, summed in split order
+    float4 x[4], y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      x[j] = __ldcg(reinterpret_cast<const float4*>(part + (s + j) * ss + off));
+      y[j] = __ldcg(reinterpret_cast<const float4*>(part + (s + j) * ss + off + 4));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      a.x += x[j].x, a.y += x[j].y, a.z += x[j].z, a.w += x[j].w;
+      b.x += y[j].x, b.y += y[j].y, b.z += y[j].z, b.w += y[j].w;
+    }
+  }
+  for (; s < S; ++s) {
+    const float4 x = __ldcg(reinterpret_cast<const float4*>(part + s * ss + off));
+    const float4 y = __ldcg(reinterpret_cast<const float4*>(part + s * ss + off + 4));
+    a.x += x.x, a.y += x.y, a.z += x.z, a.w += x.w;
+    b.x += y.x, b.y += y.y, b.z += y.z, b.w += y.w;
+  }
+  return make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+}
 
 __device__ __forceinline__ unsigned long long ud_timer() {
   unsigned long long t;
@@ -564,10 +598,9 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
       const int r = isq ? item >> 4 : (item - rows_total * 16) >> 4;
       const int c = item & 15;  // 8-wide chunk of the first half of the head
       const int t = isq ? r / p.heads : r;
-      const bf16* src = isq ? p.q + b * p.q_bs + t * p.q_rs + (r % p.heads) * UA_HD + c * 8
-                            : p.k1 + b * p.kv1_bs + r * p.kv1_rs + c * 8;
-      uint4 x1 = *reinterpret_cast<const uint4*>(src);
-      uint4 x2 = *reinterpret_cast<const uint4*>(src + 128);
+      const long soff = isq ? b * p.q_bs + t * p.q_rs + (r % p.heads) * UA_HD + c * 8 : b * p.kv1_bs + r * p.kv1_rs + c * 8;
+      uint4 x1 = ud_load8(isq ? p.q : p.k1, isq ? p.qf : p.k1f, soff, p.part_S, p.part_ss);
+      uint4 x2 = ud_load8(isq ? p.q : p.k1, isq ? p.qf : p.k1f, soff + 128, p.part_S, p.part_ss);
       if (rope != nullptr) {
         float4 cs[4];
         const float4* tp = reinterpret_cast<const float4*>(rope + t * 128 + c * 8);
@@ -585,7 +618,7 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
       sts_u4(tile2 + off, x2.x, x2.y, x2.z, x2.w);
     }
     uint4 v1reg = make_uint4(0, 0, 0, 0);
-    if (sid < p.kv1_len * 32) v1reg = *reinterpret_cast<const uint4*>(p.v1 + b * p.kv1_bs + (sid >> 5) * p.kv1_rs + (sid & 31) * 8);
+    if (sid < p.kv1_len * 32) v1reg = ud_load8(p.v1, p.v1f, b * p.kv1_bs + (sid >> 5) * p.kv1_rs + (sid & 31) * 8, p.part_S, p.part_ss);
     fence_proxy_async();
     mbar_arrive(q_ready);
     UD_TS(2);
@@ -1045,7 +1078,7 @@ int attention_umma(cudaStream_t st, const UmmaAttnCall& c) {
 }
 
 bool attention_decode_umma_eligible(const AttnCall& c) {
-  if (c.k1 == nullptr || c.vt0 == nullptr || c.kv_heads != 1 || c.head_dim != UA_HD || c.force_two_pass) return false;
+  if ((c.k1 == nullptr && c.k1_part == nullptr) || c.vt0 == nullptr || c.kv_heads != 1 || c.head_dim != UA_HD || c.force_two_pass) return false;
   if (c.heads * c.tq > 128 || c.heads > 128 || c.kv1_len < 1 || c.kv1_len > 8) return false;
   if (c.kv0_row_stride != UA_HD || c.kv0_batch_stride % UA_HD != 0 || c.vt0_ld % 8 != 0) return false;
   const int kmax = c.kv0_len_dev != nullptr ? c.kv0_max : c.kv0_len;
@@ -1081,6 +1114,7 @@ int attention_decode_umma(cudaStream_t st, const AttnCall& c) {
   p.out = c.out, p.o_bs = c.o_batch_stride, p.o_rs = c.o_row_stride;
   p.heads = c.heads, p.tq = c.tq, p.tk_pad = tk_pad, p.scale = c.scale, p.kv0_static = c.kv0_static, p.rope = c.rope;
   p.ts = g_skinny_ts;
+  p.qf = c.q_part, p.k1f = c.k1_part, p.v1f = c.v1_part, p.part_S = c.part_splits, p.part_ss = c.part_split_stride;
   const int nkb = (tk_pad + 63) / 64;
   const int kslots = 4 * UA_QBLK + 4 * UD_KSBLK + 4 * tk_pad * 128 <= UA_BODY_MAX ? 4 : 3;
   const int vslots = std::min(std::min(nkb, UD_VSLOTS), (UA_BODY_MAX - UD_MISC - nkb * UA_PBLK) / (hdw * 128));

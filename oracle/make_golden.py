@@ -21,7 +21,15 @@ from oracle import ref_shim
 OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
 
 
-def pi0_golden(name: str, R: int, K: int, seed: int = 0):
+def pi0_truth(d, w, inp, K):
+    """fp32 'truth' (SURVEY.md F10): the oracle graph with every bf16 rounding point removed, on the de-duplicated
+    schedule (identical in exact arithmetic to the reference's batch layout; fp32 rounding differences ~1e-6)."""
+    with O.truth_mode():
+        return O.sample_actions_dedup(O.truth_weights(w), d, inp["image"], inp["tokens"], inp["masks"],
+                                      inp["state"], inp["noise"], K)
+
+
+def pi0_golden(name: str, R: int, K: int, seed: int = 0, truth: bool = False):
     d = getattr(O, name.upper())
     torch.manual_seed(0)
     t0 = time.time()
@@ -51,6 +59,11 @@ def pi0_golden(name: str, R: int, K: int, seed: int = 0):
                k0_slice=cache[0]["key_states"][::K, ::11, 0, ::7].clone(),
                vlast_slice=cache[L]["value_states"][::K, ::11, 0, ::7].clone(),
                lens=inp["lens"], torch_version=str(torch.__version__))
+    if truth:
+        t1 = time.time()
+        fix["actions_truth"] = pi0_truth(d, w, inp, K)
+        fix["err_ref_vs_truth"] = float((actions - fix["actions_truth"]).abs().max())
+        print(f"  fp32 truth: {time.time() - t1:.1f}s  max|reference_bf16 - truth| = {fix['err_ref_vs_truth']:.3e}")
     OUT.mkdir(parents=True, exist_ok=True)
     torch.save(fix, OUT / f"pi0_{name}_R{R}K{K}.pt")
     print(f"pi0 {name} R={R} K={K}: {time.time() - t0:.1f}s  |actions-noise|max="
@@ -65,7 +78,14 @@ if __name__ == "__main__":
     if "mid" in which:
         pi0_golden("mid", 2, 2)
     if "full" in which:
-        pi0_golden("full", 2, 2)
+        pi0_golden("full", 2, 2, truth=True)
+    if "full_r1k5" in which:  # BASELINE.json configs[1]
+        pi0_golden("full", 1, 5, truth=True)
+    if "full_r8k5" in which:  # BASELINE.json configs[2]
+        pi0_golden("full", 8, 5, truth=True)
+    if "mid_truth" in which:
+        pi0_golden("mid", 2, 2, truth=True)
+        pi0_golden("mid", 2, 3, truth=True)
     if "verifier" in which:
         from oracle import make_golden_verifier
         make_golden_verifier.main()

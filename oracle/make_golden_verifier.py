@@ -60,18 +60,24 @@ def make(name: str, R: int, K: int, seed: int):
     fact = fact / fact.norm(dim=-1, keepdim=True)
     scores = (fit @ fact.T)[0]
     fix = dict(name=name, R=R, K=K, seed=seed, max_score=ref["max_score"], global_idx=ref["global_idx"], scores=scores,
-               it_emb=ref["it"], act_emb_slice=ref["act"][:, ::3, ::17].clone(), torch_version=str(torch.__version__))
+               it_emb=ref["it"], act_emb_slice=ref["act"][:, ::3, ::17].clone(), torch_version=str(torch.__version__),
+               # trunk restatement outputs (strided slices): pins the CUDA trunk at sizes the GPU tests do not recompute
+               patch_slice=ref["patch"][0, ::7, ::13].clone(), text_slice=ref["text"][0, ::3, ::13].clone())
     OUT.mkdir(parents=True, exist_ok=True)
     torch.save(fix, OUT / f"verifier_{name.lower()}_R{R}K{K}.pt")
     print(f"verifier {name} R={R} K={K}: max_score {ref['max_score']:.6f} idx {ref['global_idx']}")
 
 
-def main():
+def main(full: bool = False):
     torch.set_num_threads(8)
+    if full:  # BASELINE.json configs[0] / configs[2]: full-size trunk + heads, 8 rephrases x 5 samples
+        make("VFULL", 8, 5, seed=2)
+        return
     make("VTINY", 4, 3, seed=1)
     make("VMID", 8, 5, seed=2)
     make("VMID", 1, 1, seed=3)
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    main(full="full" in sys.argv[1:])

@@ -37,6 +37,28 @@ from cover_vla_b200.synthetic import (EX, FULL, LM, MID, MM, PW, TINY, VT, PI0Di
 # ------------------------------------------------------------------------------------------------
 # building blocks
 # ------------------------------------------------------------------------------------------------
+# Activation dtype of the graph.  bfloat16 = the reference's ledger.  `truth_mode()` switches it
+# to float32: the SAME graph with every bf16 rounding point removed (weights keep their bf16 VALUES, upcast) - the
+# "fp32 truth" SURVEY.md F10 asks for, used only to arbitrate err(ours, truth) against err(reference_bf16, truth).
+ACT = torch.bfloat16
+
+
+class truth_mode:
+    def __enter__(self):
+        global ACT
+        self._old, ACT = ACT, torch.float32
+        return self
+
+    def __exit__(self, *exc):
+        global ACT
+        ACT = self._old
+
+
+def truth_weights(w):
+    """fp32 copies of the (bf16-valued) reference weights for truth_mode()."""
+    return {k: v.float() for k, v in w.items()}
+
+
 def gemma_rmsnorm(x, w, eps=1e-6):
     # transformers GemmaRMSNorm: _norm(x.float()) * (1 + w.float()), cast back to x.dtype
     xf = x.float()
@@ -114,7 +136,7 @@ def denoise_times(num_steps: int):
 # SigLIP tower + projector  (transformers SiglipVisionModel, PaliGemma get_image_features @4.48.3)
 # ------------------------------------------------------------------------------------------------
 def siglip_tower(w, d: PI0Dims, pixel_values):
-    x = pixel_values.to(torch.bfloat16)
+    x = pixel_values.to(ACT)
     pe = F.conv2d(x, w[VT + "embeddings.patch_embedding.weight"], w[VT + "embeddings.patch_embedding.bias"],
                   stride=d.vis_patch)
     h = pe.flatten(2).transpose(1, 2)
@@ -151,7 +173,7 @@ def embed_image(w, d: PI0Dims, pixel_values):
 
 def embed_prefix(w, d: PI0Dims, image, lang_tokens, lang_masks):
     # modeling_pi0.py:517-567 (one camera, img_mask all True)
-    img_emb = embed_image(w, d, image).to(torch.bfloat16)
+    img_emb = embed_image(w, d, image).to(ACT)
     img_emb = img_emb * torch.tensor(img_emb.shape[-1] ** 0.5, dtype=img_emb.dtype)
     B, n_img = img_emb.shape[:2]
     lang_emb = F.embedding(lang_tokens, w[LM + "embed_tokens.weight"])
@@ -172,7 +194,7 @@ def _tower_forward(w, d: PI0Dims, prefix: str, x, mask, pos, cache, fill, last_l
     for l in range(d.layers):
         p = prefix + f"layers.{l}."
         y = gemma_rmsnorm(x, w[p + "input_layernorm.weight"])
-        y = y.to(torch.bfloat16)
+        y = y.to(ACT)
         shp = (*y.shape[:-1], -1, d.head_dim)
         q = F.linear(y, w[p + "self_attn.q_proj.weight"]).view(shp)
         k = F.linear(y, w[p + "self_attn.k_proj.weight"]).view(shp)
@@ -186,7 +208,7 @@ def _tower_forward(w, d: PI0Dims, prefix: str, x, mask, pos, cache, fill, last_l
         else:
             k = torch.cat([cache[l]["key_states"], k], dim=1)
             v = torch.cat([cache[l]["value_states"], v], dim=1)
-        a = eager_attention(mask, q, k, v, d.heads, d.head_dim).to(torch.bfloat16)
+        a = eager_attention(mask, q, k, v, d.heads, d.head_dim).to(ACT)
         out = F.linear(a, w[p + "self_attn.o_proj.weight"])
         out += x  # in place: the result keeps out's dtype (bf16) even when x is fp32 (layer 0 of the suffix)
         res = out.clone()
@@ -199,8 +221,8 @@ def _tower_forward(w, d: PI0Dims, prefix: str, x, mask, pos, cache, fill, last_l
 
 def embed_suffix(w, d: PI0Dims, state, x_t, timestep):
     # modeling_pi0.py:569-629
-    state_emb = F.linear(state, w["state_proj.weight"], w["state_proj.bias"]).to(torch.bfloat16)
-    time_emb = sinusoidal_time_embedding(timestep, d.ex_width).type(dtype=torch.bfloat16)
+    state_emb = F.linear(state, w["state_proj.weight"], w["state_proj.bias"]).to(ACT)
+    time_emb = sinusoidal_time_embedding(timestep, d.ex_width).type(dtype=ACT)
     action_emb = F.linear(x_t, w["action_in_proj.weight"], w["action_in_proj.bias"])
     time_emb = time_emb[:, None, :].expand_as(action_emb)
     at = torch.cat([action_emb, time_emb], dim=2)

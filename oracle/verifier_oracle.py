@@ -39,6 +39,27 @@ from cover_vla_b200.synthetic import make_verifier_inputs as make_inputs  # noqa
 # ------------------------------------------------------------------------------------------------
 # trunk (restated third-party architecture; see module docstring)
 # ------------------------------------------------------------------------------------------------
+# Activation dtype of the trunk: bfloat16 = what the reference runs (efficient_ensemble_merged.py:66 casts the trunk).
+# truth_mode() + truth_weights() evaluate the SAME trunk in fp32 (weights keep their bf16 values): the arbiter for the
+# score gate, like pi0_oracle.truth_mode - the heads are fp32 on both sides already.
+ACT = torch.bfloat16
+
+
+class truth_mode:
+    def __enter__(self):
+        global ACT
+        self._old, ACT = ACT, torch.float32
+        return self
+
+    def __exit__(self, *exc):
+        global ACT
+        ACT = self._old
+
+
+def truth_weights(w):
+    return {k: (v.float() if torch.is_tensor(v) and v.dtype == torch.bfloat16 else v) for k, v in w.items()}
+
+
 def _mha_self(x, w_in, b_in, w_out, b_out, heads):
     B, T, Wd = x.shape
     hd = Wd // heads
@@ -53,7 +74,7 @@ def _mha_self(x, w_in, b_in, w_out, b_out, heads):
 def trunk_image_patches(w, d: VerifierDims, image):
     """image [B,3,H,W] -> output of visual.trunk.blocks[-1].attn (the hook at ddp.py:272-274), bf16."""
     v = TR + "visual.trunk."
-    x = image.to(torch.bfloat16)
+    x = image.to(ACT)
     x = F.conv2d(x, w[v + "patch_embed.proj.weight"], w[v + "patch_embed.proj.bias"], stride=d.patch)
     x = x.flatten(2).transpose(1, 2)
     x = x + w[v + "pos_embed"]

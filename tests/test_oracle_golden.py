@@ -41,6 +41,36 @@ def test_pi0_oracle_reproduces_reference_golden(name):
     assert L >= 0
 
 
+@pytest.mark.parametrize("fname", ["pi0_mid_R2K2.pt", "pi0_mid_R2K3.pt"])
+def test_fp32_truth_fixture_is_reproduced(fname):
+    """The fp32 'truth' (oracle truth_mode = the same graph without bf16 rounding points) stored next to
+    the reference's bf16 result: reproduced here, and the reference's own distance to it is what the fixture says.
+    The full-size fixtures (pi0_full_R*.pt) were made by the same code path (oracle/make_golden.py)."""
+    g = torch.load(GOLD / fname)
+    d = O.MID
+    R, K = g["R"], g["K"]
+    w = O.make_pi0_weights(d, seed=g["seed"])
+    inp = O.make_inputs(d, R, K, seed=g["seed"])
+    torch.set_num_threads(8)
+    with O.truth_mode():
+        truth = O.sample_actions_dedup(O.truth_weights(w), d, inp["image"], inp["tokens"], inp["masks"], inp["state"],
+                                       inp["noise"], K)
+    assert O.ACT == torch.bfloat16  # the context manager restored the ledger
+    assert (truth - g["actions_truth"]).abs().max().item() < 1e-4
+    assert abs((g["actions"] - g["actions_truth"]).abs().max().item() - g["err_ref_vs_truth"]) < 1e-6
+    # the reference's bf16 evaluation is itself ~1e-2 away from the exact result of its graph
+    assert 1e-3 < g["err_ref_vs_truth"] < 5e-2
+
+
+def test_full_size_fixtures_carry_reference_and_truth():
+    for R, K in [(2, 2), (1, 5), (8, 5)]:
+        g = torch.load(GOLD / f"pi0_full_R{R}K{K}.pt")
+        assert g["dims"] == O.FULL.as_dict() and g["actions"].shape == (R * K, 4, 32) == g["actions_truth"].shape
+        assert torch.isfinite(g["actions"]).all() and 5e-3 < g["err_ref_vs_truth"] < 5e-2
+    g = torch.load(GOLD / "verifier_vfull_R8K5.pt")
+    assert g["scores"].shape == (40,) and 0 <= g["global_idx"] < 40
+
+
 @pytest.mark.parametrize("fname", ["verifier_vtiny_R4K3.pt", "verifier_vmid_R8K5.pt", "verifier_vmid_R1K1.pt"])
 def test_verifier_oracle_reproduces_reference_golden(fname):
     """EfficientEnsembleMerged.compute_max_similarity_scores_batch (efficient_ensemble_merged.py:309-454): heads,

@@ -9,7 +9,7 @@ import torch
 
 from oracle import pi0_oracle as O
 from oracle import verifier_oracle as V
-from tests.helpers import build_full_engine, max_abs, rel_l2
+from tests.helpers import SCORE_TOL, build_full_engine, max_abs, rel_l2, score_gate, verifier_truth_scores
 
 pytestmark = pytest.mark.gpu
 
@@ -65,8 +65,7 @@ def test_end_to_end_scores(vname, R, K):
     ggap = (msrt[0] - msrt[1]).item() if R > 1 else 1.0
     print(f"{vname} end-to-end: max abs score err {err:.2e}, |score|max {ref.abs().max().item():.3f}, "
           f"top-2 gap in group {gap:.2e}, group gap {ggap:.2e}")
-    # bf16 trunk noise floor: scores are cosines in [-1, 1]
-    assert err < 5e-3
+    score_gate(scores, ref, verifier_truth_scores(V, vw, v, inp["image"], inp["tokens"], traj), f"{vname} end-to-end")
     if gap > 2 * err and ggap > 2 * err:
         assert int(bidx.item()) == idx
     eng.close()

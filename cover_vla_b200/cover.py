@@ -95,7 +95,7 @@ class CoverStep:
         self.fused = True
         self._side = torch.cuda.Stream(device=engine.device)
 
-    def sample_and_score(self, x: CoverInputs, select: bool = True):
+    def sample_and_score(self, x: CoverInputs):
         """Asynchronous; returns device tensors (actions, traj, scores, group_mean, best_idx, best_score)."""
         e = self.engine
         R = x.lang_tokens.shape[0]
@@ -111,12 +111,12 @@ class CoverStep:
                 e.verifier_context(x.vf_image, x.vf_tokens)
             traj = format_trajectories(actions, x.past, e.cfg.vf_history, self.n_future, self.p01, self.p99)
             cur.wait_stream(self._side)
-            scores, gmean, bidx, bscore = e.verifier_score(None, None, traj, R if select else 0, self.K,
+            scores, gmean, bidx, bscore = e.verifier_score(None, None, traj, R, self.K,
                                                            recompute_context=False)
         else:
             actions = e.pi0_sample(x.image, x.lang_tokens, x.lang_len, x.state, x.noise, K=self.K, lang_len_max=x.lang_len_max)
             traj = format_trajectories(actions, x.past, e.cfg.vf_history, self.n_future, self.p01, self.p99)
-            scores, gmean, bidx, bscore = e.verifier_score(x.vf_image, x.vf_tokens, traj, R if select else 0, self.K)
+            scores, gmean, bidx, bscore = e.verifier_score(x.vf_image, x.vf_tokens, traj, R, self.K)
         return actions, traj, scores, gmean, bidx, bscore
 
     def __call__(self, x: CoverInputs, gate_threshold: float = 0.1):
@@ -144,6 +144,52 @@ class CoverStep:
                             winner.reshape(-1).to(torch.float64), ex]).cpu()
         n = winner.numel()
         return int(packed[0]), float(packed[1]), packed[2:2 + n].to(torch.float32).reshape(-1, 7), packed[2 + n:].numpy()
+
+
+class BatchedCoverStep:
+    """B independent decisions per call (BASELINE.json configs[4]): the episode-batched driver
+    around run_simpler_eval_with_openpi.py:190-449 steps several environments per tick and hands their observations to
+    ONE cvb_cover_step_batch.  Every observation keeps its own image, state, rephrases, noise, verifier context and
+    action history; the weights are streamed once for all of them."""
+
+    def __init__(self, engine: Engine, samples_per_rephrase: int, n_future: int | None = None,
+                 p01=BRIDGE_ACTION_P01, p99=BRIDGE_ACTION_P99):
+        self.engine = engine
+        self.K = samples_per_rephrase
+        self.n_future = n_future or engine.cfg.chunk_size
+        self.p01, self.p99 = p01, p99
+
+    @staticmethod
+    def stack(xs: list[CoverInputs]) -> CoverInputs:
+        """Stack B single-observation inputs (same R, same history length) along a new leading dimension."""
+        past = None if xs[0].past is None else torch.stack([x.past for x in xs]).contiguous()
+        hints = [x.lang_len_max for x in xs]
+        return CoverInputs(image=torch.stack([x.image for x in xs]).contiguous(),
+                           lang_tokens=torch.stack([x.lang_tokens for x in xs]).contiguous(),
+                           lang_len=torch.stack([x.lang_len for x in xs]).contiguous(),
+                           state=torch.stack([x.state for x in xs]).contiguous(),
+                           noise=torch.stack([x.noise for x in xs]).contiguous(),
+                           vf_image=torch.stack([x.vf_image for x in xs]).contiguous(),
+                           vf_tokens=torch.stack([x.vf_tokens for x in xs]).contiguous(), past=past,
+                           lang_len_max=None if any(h is None for h in hints) else max(hints))
+
+    def sample_and_score(self, xb: CoverInputs):
+        """xb: stacked inputs (leading dimension B).  Asynchronous; device tensors (actions [B,N,chunk,A], traj, scores
+        [B,N], group_mean [B,R], best_idx [B], best_score [B])."""
+        return self.engine.cover_step_batch(xb.image, xb.lang_tokens, xb.lang_len, xb.state, xb.noise, self.K, xb.vf_image,
+                                            xb.vf_tokens, self.p01, self.p99, past=xb.past, n_future=self.n_future,
+                                            lang_len_max=xb.lang_len_max)
+
+    def __call__(self, xb: CoverInputs, gate_threshold: float = 0.1):
+        """B decisions incl. the one D2H read: (best_idx [B], best_score [B], winner actions [B, chunk, 7]) on the host."""
+        actions, traj, scores, gmean, bidx, bscore = self.sample_and_score(xb)
+        B = actions.shape[0]
+        use0 = scores[:, 0] >= gate_threshold  # the 1-candidate gate of run_simpler_eval_with_openpi.py:344-363
+        idx = torch.where(use0, torch.zeros_like(bidx), bidx).to(torch.int64)
+        score = torch.where(use0, scores[:, 0], bscore)
+        winner = actions[torch.arange(B, device=actions.device), idx][:, :, :7]
+        packed = torch.cat([idx.to(torch.float32).reshape(B, 1), score.reshape(B, 1), winner.reshape(B, -1)], dim=1).cpu()
+        return packed[:, 0].to(torch.int64), packed[:, 1], packed[:, 2:].reshape(B, -1, 7)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -198,17 +244,29 @@ class ShardedCoverStep:
     """CoverStep over torch.distributed (one process per GPU, NCCL): each rank samples and scores its own
     rephrase slice; a single small all-gather collects the scores for the global argmax."""
 
-    def __init__(self, engine: Engine, samples_per_rephrase: int, group=None, **kw):
+    def __init__(self, engine: Engine, samples_per_rephrase: int, group=None, peer_memory: bool = True, **kw):
+        """peer_memory=True (default on CUDA): the exchange is cvb_allgather_select - one kernel per rank storing its slice
+        into its peers' HBM over NVLink and selecting (cover_vla_b200/comm.py); False: two NCCL all-gathers + cvb_select."""
         import torch.distributed as dist
         self.step = CoverStep(engine, samples_per_rephrase, **kw)
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        self.peer = None
+        if peer_memory and self.world > 1:
+            from .comm import PeerGather
+            cfg = engine.cfg
+            n_max = cfg.max_rephrases * cfg.max_samples  # this rank's workspace bound is also its slice bound
+            self.peer = PeerGather(n_max * (1 + cfg.chunk_size * 7), device=engine.device, group=group)
 
     def __call__(self, x: CoverInputs):
         R, K = x.lang_tokens.shape[0], self.step.K
         mine = shard_inputs(x, K, self.world, self.rank)
         if mine.lang_tokens.shape[0] == 0:
             raise ValueError("more ranks than rephrases: shrink the process group for this decision")
-        actions, traj, scores, *_ = self.step.sample_and_score(mine, select=False)
-        return gather_and_select(scores, actions[:, :, :7].contiguous(), R, K, self.step.engine.select, self.group)
+        actions, traj, scores, *_ = self.step.sample_and_score(mine)
+        local_actions = actions[:, :, :7].contiguous()
+        if self.peer is not None:
+            s, a, gmean, idx, score = self.peer(scores, local_actions, R, K)
+            return s, a, gmean, idx, score
+        return gather_and_select(scores, local_actions, R, K, self.step.engine.select, self.group)

@@ -95,6 +95,11 @@ const char* cvb_required_weight_name(cvb_handle* h, int index) {
   return h->required[index].key.c_str();
 }
 
+int cvb_required_weight_dtype(cvb_handle* h, int index) {
+  if (h == nullptr || index < 0 || index >= (int)h->required.size()) return -1;
+  return h->required[index].dtype;
+}
+
 int cvb_finalize(cvb_handle* h, void* stream) {
   CVB_REQUIRE(h != nullptr, "null handle");
   CVB_REQUIRE(!h->finalized, "handle already finalized");
@@ -199,6 +204,28 @@ int cvb_cover_step(cvb_handle* h, const float* image, const int64_t* lang_tokens
   return cvb::cover_step(h, image, lang_tokens, lang_len, state, noise, R, K, vf_image, vf_text_tokens, p01_host,
                          p99_host, past, num_past, n_future, actions, traj, scores, group_mean, best_idx, best_score,
                          (cudaStream_t)stream);
+}
+
+int cvb_cover_step_batch(cvb_handle* h, int B, const float* images, const int64_t* lang_tokens, const int32_t* lang_len,
+                         const float* states, const float* noise, int R, int K, const float* vf_images,
+                         const int64_t* vf_text_tokens, const double* p01_host, const double* p99_host, const float* past,
+                         int num_past, int n_future, float* actions, float* traj, float* scores, float* group_mean,
+                         int32_t* best_idx, float* best_score, void* stream) {
+  CVB_REQUIRE(h != nullptr, "null handle");
+  return cvb::cover_step(h, images, lang_tokens, lang_len, states, noise, R, K, vf_images, vf_text_tokens, p01_host,
+                         p99_host, past, num_past, n_future, actions, traj, scores, group_mean, best_idx, best_score,
+                         (cudaStream_t)stream, B);
+}
+
+int cvb_pi0_sample_batch(cvb_handle* h, int B, const float* images, const int64_t* lang_tokens, const int32_t* lang_len,
+                         const float* states, const float* noise, int R, int K, float* actions, void* stream) {
+  CVB_REQUIRE(h != nullptr, "null handle");
+  return cvb::pi0_sample(h, images, lang_tokens, lang_len, states, noise, R, K, actions, (cudaStream_t)stream, B);
+}
+
+int cvb_pi0_run_phase_batch(cvb_handle* h, int phase, int B, int R, int K, void* stream) {
+  CVB_REQUIRE(h != nullptr, "null handle");
+  return cvb::pi0_run_phase(h, phase, R, K, (cudaStream_t)stream, B);
 }
 
 int cvb_select(const float* scores, int R, int K, float* group_mean, int32_t* best_idx, float* best_score,

@@ -110,6 +110,7 @@ struct Pi0State {
   // workspace
   bf16 *patches = nullptr, *hv = nullptr, *xv = nullptr, *qkv_v = nullptr, *attn_v = nullptr,
        *mlp_v = nullptr, *proj_out = nullptr;
+  bf16* pos_tiled = nullptr;  // SigLIP position embedding repeated per observation (max_observations > 1)
   bf16 *hp = nullptr, *xp = nullptr, *qkv_p = nullptr, *attn_p = nullptr, *act_p = nullptr;
   bf16 *kcache = nullptr, *vcache = nullptr;
   float *state_emb = nullptr, *a1 = nullptr, *a2 = nullptr, *suffix = nullptr, *v0 = nullptr;
@@ -153,6 +154,9 @@ struct cvb_handle {
   cvb::CoverState cover;
 
   int n_img() const { return (cfg.vis_image / cfg.vis_patch) * (cfg.vis_image / cfg.vis_patch); }
+  // observations per batched call (cvb_pi0_sample_batch / cvb_cover_step_batch) and the global rephrase capacity
+  int max_obs() const { return cfg.max_observations > 1 ? cfg.max_observations : 1; }
+  int rm_total() const { return cfg.max_rephrases * max_obs(); }
   int prefix_len() const { return n_img() + cfg.max_lang_len; }
   int suffix_len() const { return 1 + cfg.chunk_size; }
   // language rows actually processed per prompt: the caller's hint rounded up to 8 (bounds the number of graphs)
@@ -176,9 +180,11 @@ int get_weight(cvb_handle* h, const std::string& key, int dtype, int64_t numel, 
 
 void pi0_required_weights(const cvb_config& c, std::vector<WeightSpec>* out);
 int pi0_finalize(cvb_handle* h, cudaStream_t st);
+// B > 1: B observations per call; images [B,3,H,W], tokens [B*R,L], lang_len [B*R], state [B,max_state_dim], noise /
+// actions [B*R*K, chunk, max_action_dim] (observation-major, then rephrase-major)
 int pi0_sample(cvb_handle* h, const float* image, const int64_t* tokens, const int32_t* lang_len,
-               const float* state, const float* noise, int R, int K, float* actions, cudaStream_t st);
-int pi0_run_phase(cvb_handle* h, int phase, int R, int K, cudaStream_t st);
+               const float* state, const float* noise, int R, int K, float* actions, cudaStream_t st, int B = 1);
+int pi0_run_phase(cvb_handle* h, int phase, int R, int K, cudaStream_t st, int B = 1);
 int64_t pi0_debug_copy(cvb_handle* h, const std::string& name, void* dst, int64_t max_bytes,
                        cudaStream_t st);
 
@@ -195,20 +201,20 @@ int verifier_score(cvb_handle* h, const float* image, const int64_t* tokens, con
 int verifier_context(cvb_handle* h, const float* image, const int64_t* tokens, cudaStream_t st);
 // building blocks of the fused decision (engine_cover.cu)
 int pi0_stage_inputs(cvb_handle* h, const float* image, const int64_t* tokens, const int32_t* lang_len,
-                     const float* state, const float* noise, int R, int K, cudaStream_t st);
-int pi0_enqueue(cvb_handle* h, cudaStream_t st, int R, int K, int part);  // 0 = vision + prefix, 1 = denoise loop
+                     const float* state, const float* noise, int R, int K, cudaStream_t st, int B = 1);
+int pi0_enqueue(cvb_handle* h, cudaStream_t st, int R, int K, int part, int B = 1);  // 0 = vision + prefix, 1 = denoise loop
 float* pi0_actions_buffer(cvb_handle* h);
-int verifier_stage_context_inputs(cvb_handle* h, const float* image, const int64_t* tokens, cudaStream_t st);
-int verifier_enqueue_context(cvb_handle* h, cudaStream_t st);
-int verifier_enqueue_score(cvb_handle* h, cudaStream_t st, int N, int R, int K);
+int verifier_stage_context_inputs(cvb_handle* h, const float* image, const int64_t* tokens, cudaStream_t st, int B = 1);
+int verifier_enqueue_context(cvb_handle* h, cudaStream_t st, int obs = 0);
+int verifier_enqueue_score(cvb_handle* h, cudaStream_t st, int N, int R, int K, int B = 1);
 float* verifier_traj_buffer(cvb_handle* h);
 int verifier_copy_results(cvb_handle* h, int N, int R, float* scores, float* group_mean, int32_t* best_idx,
-                          float* best_score, cudaStream_t st);
+                          float* best_score, cudaStream_t st, int B = 1);
 int cover_step(cvb_handle* h, const float* image, const int64_t* lang_tokens, const int32_t* lang_len,
                const float* state, const float* noise, int R, int K, const float* vf_image, const int64_t* vf_tokens,
                const double* p01_host, const double* p99_host, const float* past, int num_past, int n_future,
                float* actions, float* traj, float* scores, float* group_mean, int32_t* best_idx, float* best_score,
-               cudaStream_t st);
+               cudaStream_t st, int B = 1);
 void cover_destroy(cvb_handle* h);
 int64_t verifier_debug_copy(cvb_handle* h, const std::string& name, void* dst, int64_t max_bytes, cudaStream_t st);
 int verifier_set_features(cvb_handle* h, const float* patch, const float* text, cudaStream_t st);

@@ -26,7 +26,7 @@ int cover_step(cvb_handle* h, const float* image, const int64_t* lang_tokens, co
                const float* state, const float* noise, int R, int K, const float* vf_image, const int64_t* vf_tokens,
                const double* p01_host, const double* p99_host, const float* past, int num_past, int n_future,
                float* actions, float* traj, float* scores, float* group_mean, int32_t* best_idx, float* best_score,
-               cudaStream_t st) {
+               cudaStream_t st, int B) {
   const cvb_config& c = h->cfg;
   CVB_REQUIRE(h->finalized && h->vf != nullptr && c.layers > 0, "cvb_cover_step needs a handle with pi0 AND the verifier");
   CVB_REQUIRE(p01_host != nullptr && p99_host != nullptr, "action statistics required");
@@ -35,12 +35,13 @@ int cover_step(cvb_handle* h, const float* image, const int64_t* lang_tokens, co
   CVB_REQUIRE(num_past >= 0 && num_past + n_future <= c.vf_history, "history too short for past + future actions");
   CVB_REQUIRE(c.vf_action_dim == 7 && c.max_action_dim >= 7, "the Bridge formatting needs 7-d actions");
   CoverState& cs = h->cover;
-  const int N = R * K;
+  const int N = R * K;  // candidates per observation; B observations per call (cvb_cover_step_batch)
+  CVB_REQUIRE(B >= 1 && B <= h->max_obs(), "number of observations out of range (max_observations)");
   if (cs.side == nullptr) {
     CVB_CUDA(cudaStreamCreateWithFlags(&cs.side, cudaStreamNonBlocking));
     CVB_CUDA(cudaEventCreateWithFlags(&cs.ev_fork, cudaEventDisableTiming));
     CVB_CUDA(cudaEventCreateWithFlags(&cs.ev_join, cudaEventDisableTiming));
-    CVB_TRY(dalloc_t(h, &cs.past, (size_t)c.vf_history * 7));
+    CVB_TRY(dalloc_t(h, &cs.past, (size_t)h->max_obs() * c.vf_history * 7));
   }
   double stats[12];
   for (int i = 0; i < 6; ++i) stats[i] = p01_host[i], stats[6 + i] = p99_host[i];
@@ -52,35 +53,41 @@ int cover_step(cvb_handle* h, const float* image, const int64_t* lang_tokens, co
   FormatStats fs;
   for (int i = 0; i < 6; ++i) fs.p01[i] = stats[i], fs.p99[i] = stats[6 + i];
 
-  CVB_TRY(pi0_stage_inputs(h, image, lang_tokens, lang_len, state, noise, R, K, st));
-  CVB_TRY(verifier_stage_context_inputs(h, vf_image, vf_tokens, st));
+  CVB_TRY(pi0_stage_inputs(h, image, lang_tokens, lang_len, state, noise, R, K, st, B));
+  CVB_TRY(verifier_stage_context_inputs(h, vf_image, vf_tokens, st, B));
   if (num_past > 0)
-    CVB_CUDA(cudaMemcpyAsync(cs.past, past, (size_t)num_past * 7 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CVB_CUDA(cudaMemcpyAsync(cs.past, past, (size_t)B * num_past * 7 * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
-  const long key = ((long)h->lang_rows() << 48) | ((long)num_past << 40) | ((long)n_future << 32) | ((long)R << 16) | K;
+  const long key = ((long)h->lang_rows() << 48) | ((long)num_past << 40) | ((long)n_future << 32) | ((long)B << 24) |
+                   ((long)R << 12) | K;
   CVB_TRY(cs.graphs.run(c.use_cuda_graph != 0, key, st, [&](cudaStream_t s0) {
-    CVB_TRY(pi0_enqueue(h, s0, R, K, 0));  // vision tower + prefix
+    // One observation: the verifier's image/text side forks AFTER the prefix (whose GEMMs fill every SM) and hides under
+    // the latency-bound denoise loop.  A batch of observations: the denoise GEMMs are no longer latency-bound (M = 5 N B
+    // rows), so the B contexts fork right away and interleave with the whole sampler.
+    if (B == 1) CVB_TRY(pi0_enqueue(h, s0, R, K, 0, B));  // vision tower + prefix
     CVB_CUDA(cudaEventRecord(cs.ev_fork, s0));
     CVB_CUDA(cudaStreamWaitEvent(cs.side, cs.ev_fork, 0));
-    const int rc_side = verifier_enqueue_context(h, cs.side);
+    int rc_side = 0;
+    for (int b = 0; b < B && rc_side == 0; ++b) rc_side = verifier_enqueue_context(h, cs.side, b);
     CVB_CUDA(cudaEventRecord(cs.ev_join, cs.side));  // always rejoin, even on error, so a capture can end cleanly
     int rc = rc_side;
-    if (rc == 0) rc = pi0_enqueue(h, s0, R, K, 1);  // denoise loop
+    if (rc == 0 && B > 1) rc = pi0_enqueue(h, s0, R, K, 0, B);
+    if (rc == 0) rc = pi0_enqueue(h, s0, R, K, 1, B);  // denoise loop
     if (rc == 0)
-      rc = format_trajectories(s0, pi0_actions_buffer(h), N, c.chunk_size, c.max_action_dim, fs, cs.past, num_past,
-                               c.vf_history, n_future, verifier_traj_buffer(h));
+      rc = format_trajectories(s0, pi0_actions_buffer(h), B * N, c.chunk_size, c.max_action_dim, fs, cs.past, num_past,
+                               c.vf_history, n_future, verifier_traj_buffer(h), B > 1 ? N : 0);
     CVB_CUDA(cudaStreamWaitEvent(s0, cs.ev_join, 0));
-    if (rc == 0) rc = verifier_enqueue_score(h, s0, N, R, K);
+    if (rc == 0) rc = verifier_enqueue_score(h, s0, N, R, K, B);
     return rc;
   }));
 
   if (actions != nullptr)
-    CVB_CUDA(cudaMemcpyAsync(actions, pi0_actions_buffer(h), (size_t)N * c.chunk_size * c.max_action_dim * sizeof(float),
+    CVB_CUDA(cudaMemcpyAsync(actions, pi0_actions_buffer(h), (size_t)B * N * c.chunk_size * c.max_action_dim * sizeof(float),
                              cudaMemcpyDeviceToDevice, st));
   if (traj != nullptr)
-    CVB_CUDA(cudaMemcpyAsync(traj, verifier_traj_buffer(h), (size_t)N * c.vf_history * 7 * sizeof(float),
+    CVB_CUDA(cudaMemcpyAsync(traj, verifier_traj_buffer(h), (size_t)B * N * c.vf_history * 7 * sizeof(float),
                              cudaMemcpyDeviceToDevice, st));
-  return verifier_copy_results(h, N, R, scores, group_mean, best_idx, best_score, st);
+  return verifier_copy_results(h, N, R, scores, group_mean, best_idx, best_score, st, B);
 }
 
 }  // namespace cvb

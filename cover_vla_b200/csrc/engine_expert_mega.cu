@@ -40,7 +40,7 @@ int expert_mega_prepare(cvb_handle* h, cudaStream_t st) {
   ExpertMega& m = s.mega;
   m.mode = 0;
   const int We = c.ex_width, hd = c.head_dim, qd = c.heads * hd, qkvw = qd + 2 * hd, I = c.ex_mlp;
-  const int Mmax = c.max_rephrases * c.max_samples * h->suffix_len();
+  const int Mmax = h->rm_total() * c.max_samples * h->suffix_len();
   // 0 (default) = separate kernels, 1 = persistent chain kernel.  Measured on B200 (profiles/r2_mega_timeline.txt): the
   // chain kernel is correct and deterministic but not faster - the loop is bound by L2 -> SM traffic of activations and
   // split-K partials (~170 MB per layer at ~7 TB/s), not by launches; see DESIGN.md section 3.6.
@@ -104,7 +104,7 @@ int expert_mega_program(cvb_handle* h, int rows, cudaStream_t st, const MegaProg
   CVB_REQUIRE(cap == cudaStreamCaptureStatusNone, "the expert program must be built before graph capture (warm-up call)");
   const int We = c.ex_width, hd = c.head_dim, qd = c.heads * hd, qkvw = qd + 2 * hd, I = c.ex_mlp, L = c.layers;
   const int rows_pad = (rows + 15) / 16 * 16;
-  const int Mmax = c.max_rephrases * c.max_samples * h->suffix_len();
+  const int Mmax = h->rm_total() * c.max_samples * h->suffix_len();
   const float* w_norm = nullptr;
   {
     const void* p = nullptr;

@@ -157,7 +157,10 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
   const int T = h->n_img(), P = h->prefix_len(), S = h->suffix_len();
   const int Wv = c.vis_width, D = c.lm_width, We = c.ex_width;
   const int qd = c.heads * c.head_dim, qkvw = qd + 2 * c.head_dim;
-  const int Rm = c.max_rephrases, Nm = c.max_rephrases * c.max_samples;
+  // Bm observations per call (cvb_*_batch): every "rephrase" index below is global,
+  // r = observation * R + rephrase; the image / state of rephrase r are those of observation r / R
+  const int Bm = h->max_obs();
+  const int Rm = h->rm_total(), Nm = Rm * c.max_samples;
 
   // ---- patch embedding weight, K padded to a multiple of 8 (TMA rows are 16-byte multiples)
   const int kreal = 3 * c.vis_patch * c.vis_patch;
@@ -281,21 +284,29 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
   }
 
   // ---- workspace
-  CVB_TRY(dalloc_t(h, &s.in_image, (size_t)3 * c.vis_image * c.vis_image));
+  CVB_TRY(dalloc_t(h, &s.in_image, (size_t)Bm * 3 * c.vis_image * c.vis_image));
   CVB_TRY(dalloc_t(h, &s.in_tokens, (size_t)Rm * c.max_lang_len));
   CVB_TRY(dalloc_t(h, &s.in_lang_len, Rm));
   CVB_TRY(dalloc_t(h, &s.plen, Rm));
   CVB_TRY(dalloc_t(h, &s.rope_tab, (size_t)Rm * S * (c.head_dim / 2)));
-  CVB_TRY(dalloc_t(h, &s.in_state, c.max_state_dim));
+  CVB_TRY(dalloc_t(h, &s.in_state, (size_t)Bm * c.max_state_dim));
   CVB_TRY(dalloc_t(h, &s.x_t, (size_t)Nm * c.chunk_size * c.max_action_dim));
   CVB_TRY(dalloc_t(h, &s.v0, (size_t)Nm * c.chunk_size * c.max_action_dim));
-  CVB_TRY(dalloc_t(h, &s.patches, (size_t)T * s.kpad));
-  CVB_TRY(dalloc_t(h, &s.hv, (size_t)T * Wv));
-  CVB_TRY(dalloc_t(h, &s.xv, (size_t)T * Wv));
-  CVB_TRY(dalloc_t(h, &s.qkv_v, (size_t)T * 3 * Wv));
-  CVB_TRY(dalloc_t(h, &s.attn_v, (size_t)T * Wv));
-  CVB_TRY(dalloc_t(h, &s.mlp_v, (size_t)T * c.vis_mlp));
-  CVB_TRY(dalloc_t(h, &s.proj_out, (size_t)T * D));
+  const size_t Tb = (size_t)Bm * T;
+  CVB_TRY(dalloc_t(h, &s.patches, Tb * s.kpad));
+  CVB_TRY(dalloc_t(h, &s.hv, Tb * Wv));
+  CVB_TRY(dalloc_t(h, &s.xv, Tb * Wv));
+  CVB_TRY(dalloc_t(h, &s.qkv_v, Tb * 3 * Wv));
+  CVB_TRY(dalloc_t(h, &s.attn_v, Tb * Wv));
+  CVB_TRY(dalloc_t(h, &s.mlp_v, Tb * c.vis_mlp));
+  CVB_TRY(dalloc_t(h, &s.proj_out, Tb * D));
+  if (Bm > 1) {  // position embedding tiled per observation (the residual operand of the patch-embedding GEMM)
+    const bf16* pos = nullptr;
+    CVB_TRY(W(h, VT + "embeddings.position_embedding.weight", CVB_BF16, (int64_t)T * Wv, &pos));
+    CVB_TRY(dalloc_t(h, &s.pos_tiled, Tb * Wv));
+    for (int b = 0; b < Bm; ++b)
+      CVB_CUDA(cudaMemcpyAsync(s.pos_tiled + (size_t)b * T * Wv, pos, (size_t)T * Wv * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+  }
   const size_t Mp = (size_t)Rm * P;
   CVB_TRY(dalloc_t(h, &s.hp, Mp * D));
   CVB_TRY(dalloc_t(h, &s.xp, Mp * D));
@@ -309,7 +320,7 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
   CVB_TRY(dalloc_t(h, &s.vt_p, (size_t)c.layers * Rm * c.head_dim * s.vt_ld));
   CVB_CUDA(cudaMemsetAsync(s.vt_p, 0, (size_t)c.layers * Rm * c.head_dim * s.vt_ld * sizeof(bf16), st));  // padding keys stay finite
   const size_t Me = (size_t)Nm * S, Ma = (size_t)Nm * c.chunk_size;
-  CVB_TRY(dalloc_t(h, &s.state_emb, We));
+  CVB_TRY(dalloc_t(h, &s.state_emb, (size_t)Bm * We));
   CVB_TRY(dalloc_t(h, &s.a1, Ma * We));
   CVB_TRY(dalloc_t(h, &s.a2, Ma * We));
   CVB_TRY(dalloc_t(h, &s.suffix, Me * We));
@@ -332,7 +343,8 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
     s.splitk_v2 = pickv("CVB_SPLITK_V2", c.vis_mlp, 8);
     CVB_TRY(dalloc_t(h, &s.part_v, (size_t)kMaxSplitK * T * Wv));
   }
-  if (Me <= 256) {
+  {  // used whenever a call's suffix rows fit one UMMA N (<= 256); larger batches take the fused-epilogue GEMMs
+    const size_t Me_sk = std::min<size_t>(Me, 256);
     auto pick = [&](const char* env, int kdim) {
       const int kb = (kdim + 63) / 64, tiles = (We + 127) / 128;
       // measured (tools/splitk_bench.py): 8 splits beat 4 / 12 / 16 at both shapes (more splits = more partial traffic)
@@ -342,7 +354,7 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
     };
     s.splitk_o = pick("CVB_SPLITK_O", qd);
     s.splitk_d = pick("CVB_SPLITK_D", c.ex_mlp);
-    CVB_TRY(dalloc_t(h, &s.part_e, (size_t)kMaxSplitK * Me * We));
+    CVB_TRY(dalloc_t(h, &s.part_e, (size_t)kMaxSplitK * Me_sk * We));
     // Fused tail (grid-wide arrive counter inside the split-K launch).  MEASURED SLOWER than the separate norm kernel
     // (step 23.3 vs 22.1 ms: the barrier waits for the slowest of 64 CTAs and 64 CTAs then reduce 200 rows, while the
     // separate kernel spreads them over 200 CTAs and overlaps its launch with the GEMM's tail), so it is OFF unless
@@ -359,19 +371,23 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
 }
 
 // --------------------------------------------------------------------------------------------------
-static int run_vision(cvb_handle* h, cudaStream_t st) {
+static int run_vision(cvb_handle* h, cudaStream_t st, int B) {
   const cvb_config& c = h->cfg;
   Pi0State& s = h->pi0;
-  const int T = h->n_img(), Wv = c.vis_width, hd = Wv / c.vis_heads, D = c.lm_width;
+  const int T1 = h->n_img(), T = B * T1, Wv = c.vis_width, hd = Wv / c.vis_heads, D = c.lm_width;
   const bf16 *b_patch, *pos, *post_w, *post_b, *w_proj, *b_proj;
   CVB_TRY(W(h, VT + "embeddings.patch_embedding.bias", CVB_BF16, Wv, &b_patch));
-  CVB_TRY(W(h, VT + "embeddings.position_embedding.weight", CVB_BF16, (int64_t)T * Wv, &pos));
+  CVB_TRY(W(h, VT + "embeddings.position_embedding.weight", CVB_BF16, (int64_t)T1 * Wv, &pos));
+  if (B > 1) pos = s.pos_tiled;
+  // split-K + LayerNorm-reduce path: single-observation (latency) handles only.  A handle built for batches takes the
+  // fused-epilogue GEMMs for every B, so a row's result never depends on how many observations share the call.
+  const bool sk = h->max_obs() == 1;
   CVB_TRY(W(h, VT + "post_layernorm.weight", CVB_BF16, Wv, &post_w));
   CVB_TRY(W(h, VT + "post_layernorm.bias", CVB_BF16, Wv, &post_b));
   CVB_TRY(W(h, MM + "weight", CVB_BF16, (int64_t)D * Wv, &w_proj));
   CVB_TRY(W(h, MM + "bias", CVB_BF16, D, &b_proj));
 
-  CVB_TRY(im2col_patches(st, s.in_image, s.patches, 3, c.vis_image, c.vis_image, c.vis_patch, s.kpad));
+  CVB_TRY(im2col_patches(st, s.in_image, s.patches, 3, c.vis_image, c.vis_image, c.vis_patch, s.kpad, B));
   // hv = bf16(bf16(conv + bias) + pos_emb)
   CVB_TRY(gemm(st, s.patches, s.kpad, s.w_patch, s.kpad, T, Wv, s.kpad, EPI_RESID, s.hv, Wv, b_patch, pos, Wv));
   // out_proj / fc2 leave split-K partials that the following LayerNorm kernel reduces (bias + residual + norm in one
@@ -393,14 +409,14 @@ static int run_vision(cvb_handle* h, cudaStream_t st) {
     pending = 0;
     CVB_TRY(gemm(st, s.xv, Wv, L.wqkv, Wv, T, 3 * Wv, Wv, EPI_STORE, s.qkv_v, 3 * Wv, L.bqkv));
     AttnCall a;
-    a.q = s.qkv_v, a.q_batch_stride = 0, a.q_row_stride = 3 * Wv;
-    a.k0 = s.qkv_v + Wv, a.v0 = s.qkv_v + 2 * Wv, a.kv0_batch_stride = 0, a.kv0_row_stride = 3 * Wv;
-    a.kv0_len = T, a.q_per_kv_batch = 1;
-    a.out = s.attn_v, a.o_batch_stride = 0, a.o_row_stride = Wv;
-    a.batches = 1, a.heads = c.vis_heads, a.kv_heads = c.vis_heads, a.tq = T, a.head_dim = hd;
+    a.q = s.qkv_v, a.q_batch_stride = (long)T1 * 3 * Wv, a.q_row_stride = 3 * Wv;
+    a.k0 = s.qkv_v + Wv, a.v0 = s.qkv_v + 2 * Wv, a.kv0_batch_stride = (long)T1 * 3 * Wv, a.kv0_row_stride = 3 * Wv;
+    a.kv0_len = T1, a.q_per_kv_batch = 1;
+    a.out = s.attn_v, a.o_batch_stride = (long)T1 * Wv, a.o_row_stride = Wv;
+    a.batches = B, a.heads = c.vis_heads, a.kv_heads = c.vis_heads, a.tq = T1, a.head_dim = hd;
     a.scale = 1.0f / sqrtf(static_cast<float>(hd));
     CVB_TRY(attention(st, a));
-    if (s.splitk_vo > 0) {
+    if (sk && s.splitk_vo > 0) {
       int used = 0;
       CVB_TRY(gemm_part(s.attn_v, Wv, L.wo, Wv, s.splitk_vo, &used));
       CVB_TRY(layernorm_reduce(st, s.part_v, used, (long)T * Wv, Wv, L.bo, s.hv, Wv, L.ln2_w, L.ln2_b, s.hv, Wv, s.xv, Wv,
@@ -410,7 +426,7 @@ static int run_vision(cvb_handle* h, cudaStream_t st) {
       CVB_TRY(layernorm_bf16(st, s.hv, Wv, L.ln2_w, L.ln2_b, s.xv, Wv, T, Wv, 1e-6f));
     }
     CVB_TRY(gemm(st, s.xv, Wv, L.w1, Wv, T, c.vis_mlp, Wv, EPI_GELU, s.mlp_v, c.vis_mlp, L.b1));
-    if (s.splitk_v2 > 0) {
+    if (sk && s.splitk_v2 > 0) {
       CVB_TRY(gemm_part(s.mlp_v, c.vis_mlp, L.w2, c.vis_mlp, s.splitk_v2, &pending));
       pending_bias = L.b2;
     } else {
@@ -426,19 +442,20 @@ static int run_vision(cvb_handle* h, cudaStream_t st) {
   return 0;
 }
 
-static int run_prefix(cvb_handle* h, cudaStream_t st, int R) {
+static int run_prefix(cvb_handle* h, cudaStream_t st, int B, int Rpo) {
   const cvb_config& c = h->cfg;
   Pi0State& s = h->pi0;
   // Right-padded language tokens are masked as keys and their own rows are never read (dropping them
   // is bit-exact on the reference), so only Pe = image tokens + lang_rows() rows per prompt are processed; the KV
   // cache keeps the full-P layout the denoise attention indexes.
   const int T = h->n_img(), P = h->prefix_len(), Le = h->lang_rows(), Pe = T + Le, D = c.lm_width, hd = c.head_dim;
+  const int R = B * Rpo;  // global rephrase count; rephrase r belongs to observation r / Rpo
   const int qd = c.heads * hd, qkvw = qd + 2 * hd, M = R * Pe;
   const bf16* embed;
   CVB_TRY(W(h, LM + "embed_tokens.weight", CVB_BF16, (int64_t)c.vocab * D, &embed));
-  CVB_TRY(build_prefix(st, s.proj_out, embed, s.in_tokens, s.hp, R, T, Le, c.max_lang_len, D));
+  CVB_TRY(build_prefix(st, s.proj_out, embed, s.in_tokens, s.hp, R, T, Le, c.max_lang_len, D, Rpo));
   CVB_TRY(prefix_lengths(st, s.in_lang_len, s.plen, R, T, Le));
-  const long layer_stride = (long)c.max_rephrases * P * hd;
+  const long layer_stride = (long)h->rm_total() * P * hd;
   for (int l = 0; l < c.layers; ++l) {
     const GemmaLayer& L = s.lm[l];
     bf16* kc = s.kcache + l * layer_stride;
@@ -448,8 +465,8 @@ static int run_prefix(cvb_handle* h, cudaStream_t st, int R) {
     // tcgen05 attention (8 heads folded into UMMA rows, V^T written by the RoPE kernel) when the shape allows it
     UmmaAttnCall u;
     u.q = s.qkv_p, u.q_ld = qkvw, u.q_total_rows = M, u.q_rows_per_batch = Pe;
-    u.k = kc, u.k_total_rows = (long)c.max_rephrases * P, u.k_rows_per_batch = P;
-    bf16* vt = s.vt_p + (size_t)l * c.max_rephrases * hd * s.vt_ld;
+    u.k = kc, u.k_total_rows = (long)h->rm_total() * P, u.k_rows_per_batch = P;
+    bf16* vt = s.vt_p + (size_t)l * h->rm_total() * hd * s.vt_ld;
     u.vt = vt, u.vt_ld = s.vt_ld, u.klen_dev = s.plen, u.kmax = Pe;
     u.out = s.attn_p, u.o_batch_stride = (long)Pe * qd, u.o_row_stride = qd;
     u.batches = R, u.tq = Pe, u.heads = c.heads, u.head_dim = hd, u.scale = 1.0f / sqrtf(static_cast<float>(hd));
@@ -480,11 +497,13 @@ static int run_prefix(cvb_handle* h, cudaStream_t st, int R) {
   return 0;
 }
 
-static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
+static int run_denoise(cvb_handle* h, cudaStream_t st, int B, int Rpo, int K) {
   const cvb_config& c = h->cfg;
   Pi0State& s = h->pi0;
   const int P = h->prefix_len(), S = h->suffix_len(), We = c.ex_width, hd = c.head_dim;
+  const int R = B * Rpo;
   const int qd = c.heads * hd, qkvw = qd + 2 * hd, N = R * K, M = N * S, Ma = N * c.chunk_size;
+  const bool sk = M <= 256 && h->max_obs() == 1;  // split-K + RMSNorm-reduce path (latency handles, one UMMA N of rows)
   const float *w_state, *b_state, *w_ain, *b_ain, *w_in, *b_in, *w_out, *b_out, *w_aout, *b_aout, *w_norm;
   CVB_TRY(W(h, "state_proj.weight", CVB_F32, (int64_t)We * c.max_state_dim, &w_state));
   CVB_TRY(W(h, "state_proj.bias", CVB_F32, We, &b_state));
@@ -502,11 +521,11 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
   {
     SgemmCall g;
     g.A = s.in_state, g.lda = c.max_state_dim, g.W = w_state, g.ldw = c.max_state_dim;
-    g.M = 1, g.N = We, g.K = c.max_state_dim, g.C = s.state_emb, g.ldc = We, g.bias = b_state;
+    g.M = B, g.N = We, g.K = c.max_state_dim, g.C = s.state_emb, g.ldc = We, g.bias = b_state;
     CVB_TRY(sgemm_f32(st, g));
-    CVB_TRY(fill_state_rows(st, s.state_emb, s.suffix, N, We, S));
+    CVB_TRY(fill_state_rows(st, s.state_emb, s.suffix, N, We, S, Rpo * K));
   }
-  const long layer_stride = (long)c.max_rephrases * P * hd;
+  const long layer_stride = (long)h->rm_total() * P * hd;
   const int gu_half = s.ex_gu_half;
   const int packed = ((c.ex_mlp + gu_half - 1) / gu_half) * 2 * gu_half;
   // RoPE of the suffix is applied inside the cluster decode attention (from a table built once per sample) when the
@@ -523,7 +542,7 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
   // device-wide barriers instead of kernel boundaries and a weight ring that prefetches across them; only the
   // attention stays a separate launch.
   const MegaProgram* pg = nullptr;
-  const bool mega = s.mega.mode != 0 && attention_decode_umma_eligible(probe) && M <= 256;
+  const bool mega = s.mega.mode != 0 && attention_decode_umma_eligible(probe) && M <= 256 && B == 1;
   if (mega) CVB_TRY(expert_mega_program(h, M, st, &pg));
   for (size_t step = 0; step < s.times.size(); ++step) {
     {  // embed_suffix (modeling_pi0.py:598-609), time half of mlp_in folded into time_vec[step]
@@ -546,7 +565,7 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
       CVB_TRY(sgemm_f32(st, g3));
     }
     if (mega) {
-      const int Mmax = c.max_rephrases * c.max_samples * S;
+      const int Mmax = h->rm_total() * c.max_samples * S;
       int first = 0;
       for (int l = 0; l < c.layers; ++l) {
         CVB_TRY(expert_mega_launch(h, st, *pg, first, pg->attn_after[l] - first));
@@ -557,7 +576,7 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
         a.k0 = s.kcache + l * layer_stride, a.v0 = s.vcache + l * layer_stride;
         a.kv0_batch_stride = (long)P * hd, a.kv0_row_stride = hd, a.kv0_len_dev = s.plen, a.kv0_max = h->n_img() + h->lang_rows();
         a.q_per_kv_batch = K;
-        a.vt0 = s.vt_p + (size_t)l * c.max_rephrases * hd * s.vt_ld, a.vt0_ld = s.vt_ld;
+        a.vt0 = s.vt_p + (size_t)l * h->rm_total() * hd * s.vt_ld, a.vt0_ld = s.vt_ld;
         a.k1 = s.qkv_e + qd, a.v1 = s.qkv_e + qd + hd, a.kv1_batch_stride = (long)S * qkvw;
         a.kv1_row_stride = qkvw, a.kv1_len = S, a.suffix_mask = 1;
         a.q_part = s.mega.part_qkv, a.k1_part = s.mega.part_qkv + qd, a.v1_part = s.mega.part_qkv + qd + hd;
@@ -601,14 +620,14 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
       a.k0 = s.kcache + l * layer_stride, a.v0 = s.vcache + l * layer_stride;
       a.kv0_batch_stride = (long)P * hd, a.kv0_row_stride = hd, a.kv0_len_dev = s.plen, a.kv0_max = h->n_img() + h->lang_rows();
       a.q_per_kv_batch = K;
-      if (getenv("CVB_NO_UMMA_ATTN") == nullptr) a.vt0 = s.vt_p + (size_t)l * c.max_rephrases * hd * s.vt_ld, a.vt0_ld = s.vt_ld;
+      if (getenv("CVB_NO_UMMA_ATTN") == nullptr) a.vt0 = s.vt_p + (size_t)l * h->rm_total() * hd * s.vt_ld, a.vt0_ld = s.vt_ld;
       a.k1 = s.qkv_e + qd, a.v1 = s.qkv_e + qd + hd, a.kv1_batch_stride = (long)S * qkvw;
       a.kv1_row_stride = qkvw, a.kv1_len = S, a.suffix_mask = 1;
       a.out = s.attn_e, a.o_batch_stride = (long)S * qd, a.o_row_stride = qd;
       a.batches = N, a.heads = c.heads, a.kv_heads = 1, a.tq = S, a.head_dim = hd;
       a.scale = 1.0f / sqrtf(static_cast<float>(hd));
       CVB_TRY(attention(st, a));
-      if (s.splitk_o > 0) {
+      if (sk && s.splitk_o > 0) {
         int used = 0;
         if (s.fuse_norm) {  // o_proj + residual + post_attention_layernorm in one launch
           SplitKNorm nm;
@@ -628,7 +647,7 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
         CVB_TRY(gemm(st, s.xe, We, L.wgu, We, M, packed, We, 5, s.act_e, c.ex_mlp, nullptr, nullptr, 0, 0, c.ex_mlp, 128));
       else
         CVB_TRY(gemm(st, s.xe, We, L.wgu, We, M, packed, We, EPI_GEGLU, s.act_e, c.ex_mlp, nullptr, nullptr, 0, 0, c.ex_mlp));
-      if (s.splitk_d > 0) {
+      if (sk && s.splitk_d > 0) {
         if (s.fuse_norm) {  // down_proj + residual + the NEXT norm (next layer's input_layernorm, or the final norm)
           SplitKNorm nm;
           nm.resid = s.he, nm.resid_is_f32 = 0, nm.ldr = We;
@@ -658,67 +677,69 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int R, int K) {
   return 0;
 }
 
-static int run_all(cvb_handle* h, cudaStream_t st, int R, int K) {
-  CVB_TRY(run_vision(h, st));
-  CVB_TRY(run_prefix(h, st, R));
-  CVB_TRY(run_denoise(h, st, R, K));
+static int run_all(cvb_handle* h, cudaStream_t st, int B, int R, int K) {
+  CVB_TRY(run_vision(h, st, B));
+  CVB_TRY(run_prefix(h, st, B, R));
+  CVB_TRY(run_denoise(h, st, B, R, K));
   return 0;
 }
 
 int pi0_stage_inputs(cvb_handle* h, const float* image, const int64_t* tokens, const int32_t* lang_len,
-                     const float* state, const float* noise, int R, int K, cudaStream_t st) {
+                     const float* state, const float* noise, int R, int K, cudaStream_t st, int B) {
   const cvb_config& c = h->cfg;
   Pi0State& s = h->pi0;
   CVB_REQUIRE(h->finalized, "cvb_finalize() has not been called");
   CVB_REQUIRE(c.layers > 0, "this handle was created without the pi0 model (layers == 0)");
+  CVB_REQUIRE(B >= 1 && B <= h->max_obs(), "number of observations out of range (max_observations)");
   CVB_REQUIRE(R >= 1 && R <= c.max_rephrases, "R out of range (max_rephrases)");
   CVB_REQUIRE(K >= 1 && K <= c.max_samples, "K out of range (max_samples)");
   CVB_REQUIRE(image != nullptr && tokens != nullptr && lang_len != nullptr && state != nullptr && noise != nullptr,
               "null input");
-  const size_t act_bytes = (size_t)R * K * c.chunk_size * c.max_action_dim * sizeof(float);
-  CVB_CUDA(cudaMemcpyAsync(s.in_image, image, (size_t)3 * c.vis_image * c.vis_image * sizeof(float),
+  const size_t act_bytes = (size_t)B * R * K * c.chunk_size * c.max_action_dim * sizeof(float);
+  CVB_CUDA(cudaMemcpyAsync(s.in_image, image, (size_t)B * 3 * c.vis_image * c.vis_image * sizeof(float),
                            cudaMemcpyDeviceToDevice, st));
-  CVB_CUDA(cudaMemcpyAsync(s.in_tokens, tokens, (size_t)R * c.max_lang_len * sizeof(int64_t),
+  CVB_CUDA(cudaMemcpyAsync(s.in_tokens, tokens, (size_t)B * R * c.max_lang_len * sizeof(int64_t),
                            cudaMemcpyDeviceToDevice, st));
-  CVB_CUDA(cudaMemcpyAsync(s.in_lang_len, lang_len, R * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-  CVB_CUDA(cudaMemcpyAsync(s.in_state, state, c.max_state_dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CVB_CUDA(cudaMemcpyAsync(s.in_lang_len, lang_len, (size_t)B * R * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  CVB_CUDA(cudaMemcpyAsync(s.in_state, state, (size_t)B * c.max_state_dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
   CVB_CUDA(cudaMemcpyAsync(s.x_t, noise, act_bytes, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
-int pi0_enqueue(cvb_handle* h, cudaStream_t st, int R, int K, int part) {
+int pi0_enqueue(cvb_handle* h, cudaStream_t st, int R, int K, int part, int B) {
   if (part == 0) {
-    CVB_TRY(run_vision(h, st));
-    return run_prefix(h, st, R);
+    CVB_TRY(run_vision(h, st, B));
+    return run_prefix(h, st, B, R);
   }
-  return run_denoise(h, st, R, K);
+  return run_denoise(h, st, B, R, K);
 }
 
 float* pi0_actions_buffer(cvb_handle* h) { return h->pi0.x_t; }
 
 int pi0_sample(cvb_handle* h, const float* image, const int64_t* tokens, const int32_t* lang_len,
-               const float* state, const float* noise, int R, int K, float* actions, cudaStream_t st) {
+               const float* state, const float* noise, int R, int K, float* actions, cudaStream_t st, int B) {
   const cvb_config& c = h->cfg;
   Pi0State& s = h->pi0;
-  CVB_TRY(pi0_stage_inputs(h, image, tokens, lang_len, state, noise, R, K, st));
-  const size_t act_bytes = (size_t)R * K * c.chunk_size * c.max_action_dim * sizeof(float);
-  const long key = ((long)h->lang_rows() << 40) | ((long)R << 16) | (long)K;
-  CVB_TRY(s.graphs.run(c.use_cuda_graph != 0, key, st, [&](cudaStream_t cs) { return run_all(h, cs, R, K); }));
+  CVB_TRY(pi0_stage_inputs(h, image, tokens, lang_len, state, noise, R, K, st, B));
+  const size_t act_bytes = (size_t)B * R * K * c.chunk_size * c.max_action_dim * sizeof(float);
+  const long key = ((long)h->lang_rows() << 40) | ((long)B << 28) | ((long)R << 16) | (long)K;
+  CVB_TRY(s.graphs.run(c.use_cuda_graph != 0, key, st, [&](cudaStream_t cs) { return run_all(h, cs, B, R, K); }));
   CVB_CUDA(cudaMemcpyAsync(actions, s.x_t, act_bytes, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
 // profiling hook: run one phase eagerly on the staged inputs of the last cvb_pi0_sample call
-int pi0_run_phase(cvb_handle* h, int phase, int R, int K, cudaStream_t st) {
+int pi0_run_phase(cvb_handle* h, int phase, int R, int K, cudaStream_t st, int B) {
   CVB_REQUIRE(h->finalized, "cvb_finalize() has not been called");
   CVB_REQUIRE(R >= 1 && R <= h->cfg.max_rephrases && K >= 1 && K <= h->cfg.max_samples, "R/K out of range");
+  CVB_REQUIRE(B >= 1 && B <= h->max_obs(), "number of observations out of range");
   switch (phase) {
     case 0:
-      return run_vision(h, st);
+      return run_vision(h, st, B);
     case 1:
-      return run_prefix(h, st, R);
+      return run_prefix(h, st, B, R);
     case 2:
-      return run_denoise(h, st, R, K);
+      return run_denoise(h, st, B, R, K);
     default:
       set_last_error("phase must be 0 (vision), 1 (prefix) or 2 (denoise)");
       return -1;
@@ -732,9 +753,9 @@ int64_t pi0_debug_copy(cvb_handle* h, const std::string& name, void* dst, int64_
   const int T = h->n_img(), P = h->prefix_len();
   const void* src = nullptr;
   int64_t bytes = 0;
-  const int64_t layer_bytes = (int64_t)c.max_rephrases * P * c.head_dim * sizeof(bf16);
+  const int64_t layer_bytes = (int64_t)h->rm_total() * P * c.head_dim * sizeof(bf16);
   if (name == "image_emb") {
-    src = s.proj_out, bytes = (int64_t)T * c.lm_width * sizeof(bf16);
+    src = s.proj_out, bytes = (int64_t)h->max_obs() * T * c.lm_width * sizeof(bf16);
   } else if (name == "vision_hidden") {
     src = s.xv, bytes = (int64_t)T * c.vis_width * sizeof(bf16);
   } else if (name == "prefix_k0") {
@@ -746,11 +767,11 @@ int64_t pi0_debug_copy(cvb_handle* h, const std::string& name, void* dst, int64_
   } else if (name == "prefix_vlast") {
     src = s.vcache + (int64_t)(c.layers - 1) * (layer_bytes / sizeof(bf16)), bytes = layer_bytes;
   } else if (name == "v0") {
-    src = s.v0, bytes = (int64_t)c.max_rephrases * c.max_samples * c.chunk_size * c.max_action_dim * sizeof(float);
+    src = s.v0, bytes = (int64_t)h->rm_total() * c.max_samples * c.chunk_size * c.max_action_dim * sizeof(float);
   } else if (name == "time_emb") {
     src = s.time_emb_f32, bytes = (int64_t)s.times.size() * c.ex_width * sizeof(float);
   } else if (name == "suffix") {
-    src = s.suffix, bytes = (int64_t)c.max_rephrases * c.max_samples * h->suffix_len() * c.ex_width * sizeof(float);
+    src = s.suffix, bytes = (int64_t)h->rm_total() * c.max_samples * h->suffix_len() * c.ex_width * sizeof(float);
   } else {
     set_last_error("unknown debug buffer: " + name);
     return -1;

@@ -48,6 +48,7 @@ struct VerifierState {
   // head workspace
   float *Pn = nullptr, *Tn = nullptr, *sim = nullptr, *pe = nullptr, *taf = nullptr, *kv_v = nullptr,
         *kv_t = nullptr, *vtok = nullptr, *ttok = nullptr, *it = nullptr;
+  float* it_obs = nullptr;  // [max_observations][members][embed]: what the score kernel reads (slot 0 for single calls)
   float *tx = nullptr, *tqkv = nullptr, *tatt = nullptr, *ty = nullptr, *tff = nullptr, *act = nullptr;
   float* scores = nullptr;
   float* gmean = nullptr;
@@ -191,7 +192,8 @@ int verifier_finalize(cvb_handle* h, cudaStream_t st) {
   VerifierState& s = *h->vf;
   const int Wd = c.vf_width, E = c.vf_embed, L = c.vf_pool_layers, M = c.vf_members;
   const int Np = (c.vf_image / c.vf_patch) * (c.vf_image / c.vf_patch), Tt = c.vf_text_ctx;
-  const int Nm = c.max_rephrases * c.max_samples, S = c.vf_history;
+  const int Bm = h->max_obs();  // observations per batched call
+  const int Nm = h->rm_total() * c.max_samples, S = c.vf_history;
   CVB_REQUIRE(Wd % 8 == 0 && c.vf_mlp % 8 == 0 && (Wd / c.vf_heads) % 8 == 0, "verifier trunk widths must be multiples of 8");
   CVB_REQUIRE(L <= kMaxPoolLayers, "too many pooling layers");
   CVB_REQUIRE(E % c.vf_pool_heads == 0, "embed must divide by pool heads");
@@ -253,8 +255,8 @@ int verifier_finalize(cvb_handle* h, cudaStream_t st) {
 
   // ---- workspace (trunk)
   const int Tmax = std::max(Np, Tt);
-  CVB_TRY(dalloc_t(h, &s.in_image, (size_t)3 * c.vf_image * c.vf_image));
-  CVB_TRY(dalloc_t(h, &s.in_tokens, Tt));
+  CVB_TRY(dalloc_t(h, &s.in_image, (size_t)Bm * 3 * c.vf_image * c.vf_image));
+  CVB_TRY(dalloc_t(h, &s.in_tokens, (size_t)Bm * Tt));
   CVB_TRY(dalloc_t(h, &s.in_traj, (size_t)Nm * S * c.vf_action_dim));
   CVB_TRY(dalloc_t(h, &s.patches, (size_t)Np * s.kpad));
   CVB_TRY(dalloc_t(h, &s.hv, (size_t)Tmax * Wd));
@@ -276,6 +278,7 @@ int verifier_finalize(cvb_handle* h, cudaStream_t st) {
   CVB_TRY(dalloc_t(h, &s.vtok, (size_t)M * E));
   CVB_TRY(dalloc_t(h, &s.ttok, (size_t)M * E));
   CVB_TRY(dalloc_t(h, &s.it, (size_t)M * E));
+  CVB_TRY(dalloc_t(h, &s.it_obs, (size_t)Bm * M * E));  // image-text embeddings of every observation's context
   const size_t rows = (size_t)Nm * S;
   CVB_TRY(dalloc_t(h, &s.tx, rows * E * M));
   CVB_TRY(dalloc_t(h, &s.tqkv, rows * 3 * E * M));
@@ -292,8 +295,8 @@ int verifier_finalize(cvb_handle* h, cudaStream_t st) {
   CVB_TRY(dalloc_t(h, &s.act, (size_t)M * Nm * E));
   CVB_TRY(dalloc_t(h, &s.scores, Nm));
   CVB_TRY(dalloc_t(h, &s.gmean, Nm));
-  CVB_TRY(dalloc_t(h, &s.bidx, 1));
-  CVB_TRY(dalloc_t(h, &s.bscore, 1));
+  CVB_TRY(dalloc_t(h, &s.bidx, Bm));
+  CVB_TRY(dalloc_t(h, &s.bscore, Bm));
 
   // ---- heads: pack K/V projections of all pooling blocks (they only depend on the kv input)
   s.mem.resize(M);
@@ -425,7 +428,7 @@ static int run_blocks(cudaStream_t st, VerifierState& s, const std::vector<Trunk
 }
 
 // image-text heads of every member (N-independent: SURVEY.md F4) from the normalised features Pn / Tn
-static int run_heads_context(cvb_handle* h, cudaStream_t st) {
+static int run_heads_context(cvb_handle* h, cudaStream_t st, int obs = 0) {
   const cvb_config& c = h->cfg;
   VerifierState& s = *h->vf;
   const int Wd = c.vf_width, E = c.vf_embed, L = c.vf_pool_layers, M = c.vf_members;
@@ -442,25 +445,28 @@ static int run_heads_context(cvb_handle* h, cudaStream_t st) {
   }
   CVB_TRY(pool_chains(st, s.chains, 2 * M, E, c.vf_pool_heads, Tt));
   CVB_TRY(it_finalize(st, s.itf, M, E));
+  CVB_CUDA(cudaMemcpyAsync(s.it_obs + (size_t)obs * M * E, s.it, (size_t)M * E * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
-static int run_context(cvb_handle* h, cudaStream_t st) {
+static int run_context(cvb_handle* h, cudaStream_t st, int obs = 0) {
   const cvb_config& c = h->cfg;
   VerifierState& s = *h->vf;
   const int Wd = c.vf_width;
   const int Np = (c.vf_image / c.vf_patch) * (c.vf_image / c.vf_patch), Tt = c.vf_text_ctx;
+  const float* in_image = s.in_image + (size_t)obs * 3 * c.vf_image * c.vf_image;
+  const int64_t* in_tokens = s.in_tokens + (size_t)obs * Tt;
   // image tower -> patch features (hook output), text tower -> per-token projected features
-  CVB_TRY(im2col_patches(st, s.in_image, s.patches, 3, c.vf_image, c.vf_image, c.vf_patch, s.kpad));
+  CVB_TRY(im2col_patches(st, in_image, s.patches, 3, c.vf_image, c.vf_image, c.vf_patch, s.kpad));
   CVB_TRY(gemm(st, s.patches, s.kpad, s.w_patch, s.kpad, Np, Wd, s.kpad, EPI_RESID, s.hv, Wd, s.patch_b, s.pos_embed, Wd));
   CVB_TRY(run_blocks(st, s, s.vis, s.hv, Np, Wd, c.vf_heads, c.vf_mlp, true, s.pfeat));
-  CVB_TRY(embed_tokens_pos(st, s.tok_emb, s.txt_pos, s.in_tokens, s.ht, Tt, Wd));
+  CVB_TRY(embed_tokens_pos(st, s.tok_emb, s.txt_pos, in_tokens, s.ht, Tt, Wd));
   CVB_TRY(run_blocks(st, s, s.txt, s.ht, Tt, Wd, c.vf_heads, c.vf_mlp, false, nullptr));
   CVB_TRY(layernorm_bf16(st, s.ht, Wd, s.lnf_w, s.lnf_b, s.xv, Wd, Tt, Wd, 1e-6f));
   CVB_TRY(gemm(st, s.xv, Wd, s.wproj, Wd, Tt, Wd, Wd, EPI_STORE, s.tfeat, Wd, s.bproj));
   CVB_TRY(l2norm_rows_bf16_to_f32(st, s.pfeat, Wd, s.Pn, Np, Wd));
   CVB_TRY(l2norm_rows_bf16_to_f32(st, s.tfeat, Wd, s.Tn, Tt, Wd));
-  CVB_TRY(run_heads_context(h, st));
+  CVB_TRY(run_heads_context(h, st, obs));
   return 0;
 }
 
@@ -469,7 +475,7 @@ static int run_member_trajectories(cvb_handle* h, cudaStream_t st, int N, int m)
   VerifierState& s = *h->vf;
   const int E = c.vf_embed, S = c.vf_history, A = c.vf_action_dim, FF = c.vf_traj_ff;
   const int rows = N * S;
-  const size_t cap = (size_t)c.max_rephrases * c.max_samples * S;  // rows of workspace per member
+  const size_t cap = (size_t)h->rm_total() * c.max_samples * S;  // rows of workspace per member
   float* tx = s.tx + (size_t)m * cap * E;
   float* tqkv = s.tqkv + (size_t)m * cap * 3 * E;
   float* tatt = s.tatt + (size_t)m * cap * E;
@@ -526,7 +532,7 @@ int verifier_score(cvb_handle* h, const float* image, const int64_t* tokens, con
   const long key = ((long)N << 32) | ((long)R << 16) | (long)K;
   CVB_TRY(s.traj_graph.run(c.use_cuda_graph != 0, key, st, [&](cudaStream_t cs) {
     CVB_TRY(run_trajectories(h, cs, N));
-    return fuse_score_select(cs, s.it, s.act, c.vf_members, N, c.vf_embed, s.scores, R, K, s.gmean, s.bidx, s.bscore,
+    return fuse_score_select(cs, s.it_obs, s.act, c.vf_members, N, c.vf_embed, s.scores, R, K, s.gmean, s.bidx, s.bscore,
                              R > 0 ? 1 : 0);
   }));
   CVB_CUDA(cudaMemcpyAsync(scores, s.scores, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -539,45 +545,52 @@ int verifier_score(cvb_handle* h, const float* image, const int64_t* tokens, con
   return 0;
 }
 
-int verifier_stage_context_inputs(cvb_handle* h, const float* image, const int64_t* tokens, cudaStream_t st) {
+int verifier_stage_context_inputs(cvb_handle* h, const float* image, const int64_t* tokens, cudaStream_t st, int B) {
   const cvb_config& c = h->cfg;
   CVB_REQUIRE(h->finalized && h->vf != nullptr, "verifier not configured (vf_members == 0?) or not finalized");
   CVB_REQUIRE(image != nullptr && tokens != nullptr, "image / tokens required");
+  CVB_REQUIRE(B >= 1 && B <= h->max_obs(), "number of observations out of range (max_observations)");
   VerifierState& s = *h->vf;
-  CVB_CUDA(cudaMemcpyAsync(s.in_image, image, (size_t)3 * c.vf_image * c.vf_image * sizeof(float),
+  CVB_CUDA(cudaMemcpyAsync(s.in_image, image, (size_t)B * 3 * c.vf_image * c.vf_image * sizeof(float),
                            cudaMemcpyDeviceToDevice, st));
-  CVB_CUDA(cudaMemcpyAsync(s.in_tokens, tokens, c.vf_text_ctx * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  CVB_CUDA(cudaMemcpyAsync(s.in_tokens, tokens, (size_t)B * c.vf_text_ctx * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
-int verifier_enqueue_context(cvb_handle* h, cudaStream_t st) {
-  CVB_TRY(run_context(h, st));
+// image/text side of observation `obs` (its inputs were staged by verifier_stage_context_inputs)
+int verifier_enqueue_context(cvb_handle* h, cudaStream_t st, int obs) {
+  CVB_TRY(run_context(h, st, obs));
   h->vf->context_valid = true;
   return 0;
 }
 
-int verifier_enqueue_score(cvb_handle* h, cudaStream_t st, int N, int R, int K) {
+// N candidates per observation, B observations: one pass of the trajectory encoders over all B * N histories, then one
+// fused score / select CTA group per observation against ITS context
+int verifier_enqueue_score(cvb_handle* h, cudaStream_t st, int N, int R, int K, int B) {
   const cvb_config& c = h->cfg;
   VerifierState& s = *h->vf;
   CVB_REQUIRE(N >= 1 && N <= c.max_rephrases * c.max_samples, "N out of range");
   CVB_REQUIRE(R == 0 || R * K == N, "R*K must equal N");
-  CVB_TRY(run_trajectories(h, st, N));
-  return fuse_score_select(st, s.it, s.act, c.vf_members, N, c.vf_embed, s.scores, R, K, s.gmean, s.bidx, s.bscore,
-                           R > 0 ? 1 : 0);
+  CVB_REQUIRE(B >= 1 && B <= h->max_obs(), "number of observations out of range");
+  CVB_TRY(run_trajectories(h, st, B * N));
+  return fuse_score_select(st, s.it_obs, s.act, c.vf_members, N, c.vf_embed, s.scores, R, K, s.gmean, s.bidx, s.bscore,
+                           R > 0 ? 1 : 0, B);
 }
 
 float* verifier_traj_buffer(cvb_handle* h) { return h->vf->in_traj; }
 
 int verifier_copy_results(cvb_handle* h, int N, int R, float* scores, float* group_mean, int32_t* best_idx,
-                          float* best_score, cudaStream_t st) {
+                          float* best_score, cudaStream_t st, int B) {
   VerifierState& s = *h->vf;
-  if (scores != nullptr) CVB_CUDA(cudaMemcpyAsync(scores, s.scores, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (scores != nullptr)
+    CVB_CUDA(cudaMemcpyAsync(scores, s.scores, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (R > 0) {
     if (group_mean != nullptr)
-      CVB_CUDA(cudaMemcpyAsync(group_mean, s.gmean, R * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (best_idx != nullptr) CVB_CUDA(cudaMemcpyAsync(best_idx, s.bidx, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+      CVB_CUDA(cudaMemcpyAsync(group_mean, s.gmean, (size_t)B * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (best_idx != nullptr)
+      CVB_CUDA(cudaMemcpyAsync(best_idx, s.bidx, B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     if (best_score != nullptr)
-      CVB_CUDA(cudaMemcpyAsync(best_score, s.bscore, sizeof(float), cudaMemcpyDeviceToDevice, st));
+      CVB_CUDA(cudaMemcpyAsync(best_score, s.bscore, B * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   return 0;
 }
@@ -607,9 +620,9 @@ int64_t verifier_debug_copy(cvb_handle* h, const std::string& name, void* dst, i
   } else if (name == "vf_text_features") {
     src = s.Tn, bytes = (int64_t)c.vf_text_ctx * c.vf_width * 4;
   } else if (name == "vf_it_emb") {
-    src = s.it, bytes = (int64_t)c.vf_members * c.vf_embed * 4;
+    src = s.it_obs, bytes = (int64_t)c.vf_members * c.vf_embed * 4;
   } else if (name == "vf_act_emb") {
-    src = s.act, bytes = (int64_t)c.vf_members * c.max_rephrases * c.max_samples * c.vf_embed * 4;
+    src = s.act, bytes = (int64_t)c.vf_members * h->rm_total() * c.max_samples * c.vf_embed * 4;
   } else {
     return -1;
   }

@@ -90,6 +90,20 @@ bool pdl_enabled() {
   return v == 1;
 }
 
+int ensure_dyn_smem_impl(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, int> set_bytes;  // (device, kernel) -> attribute value in force
+  int dev = 0;
+  CVB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  int& cur = set_bytes[{dev, func}];
+  if (bytes > cur) {
+    CVB_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    cur = bytes;
+  }
+  return 0;
+}
+
 int device_sm_count() {
   static int sms = 0;
   if (sms == 0) {

@@ -48,6 +48,14 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols
 
 int device_sm_count();
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: raise it (once per device and kernel, and again
+// whenever a larger size is needed) on the CURRENT device.  Handles on several GPUs of one process each get it.
+int ensure_dyn_smem_impl(const void* func, int bytes);
+template <typename F>
+int ensure_dyn_smem(F* func, int bytes) {
+  return ensure_dyn_smem_impl(reinterpret_cast<const void*>(func), bytes);
+}
+
 // number of kernel launches enqueued by this library (bench.py reports it as gpu_launches)
 void count_launch();
 long launch_count();

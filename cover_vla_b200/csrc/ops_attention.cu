@@ -383,11 +383,7 @@ template <int HDP>
 int launch_attn_smem(cudaStream_t st, const AttnParams& p, dim3 grid, int max_tiles) {
   const int smem = (BQ + 2 * BKV) * (HDP + 8) * 2 + max_tiles * 32 * ATT_THREADS * 4;
   auto kern = attn_smem_kernel<HDP>;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
+  CVB_TRY(ensure_dyn_smem(kern, smem));
   CVB_TRY(launch_pdl(kern, dim3(grid), dim3(ATT_THREADS), smem, st, 1, p));
   CVB_LAUNCHED();
   return 0;
@@ -397,11 +393,7 @@ template <int HDP>
 int launch_attn(cudaStream_t st, const AttnParams& p, dim3 grid) {
   constexpr int SMEM = (BQ + 2 * BKV) * (HDP + 8) * 2;
   auto kern = attn_kernel<HDP>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
-  }
+  CVB_TRY(ensure_dyn_smem(kern, SMEM));
   CVB_TRY(launch_pdl(kern, dim3(grid), dim3(ATT_THREADS), SMEM, st, 1, p));
   CVB_LAUNCHED();
   return 0;

@@ -343,11 +343,7 @@ template <int HD>
 int launch_decode(cudaStream_t st, const DecodeParams& p, dim3 grid) {
   const int smem = 3 * BQ * (HD + 8) * 2 + p.C * BQ * 8;
   auto kern = attn_decode_kernel<HD>;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
+  CVB_TRY(ensure_dyn_smem(kern, smem));
   CVB_TRY(launch_pdl(kern, grid, dim3(ATT_THREADS), smem, st, p.C, p));
   CVB_LAUNCHED();
   return 0;

@@ -280,11 +280,7 @@ template <int HD>
 int launch_group(cudaStream_t st, const GroupParams& p, dim3 grid) {
   const int smem = (GR + NS * BKV) * (HD + 8) * 2 + GR * p.s_ld * 4 + 2 * GR * 4;
   auto kern = attn_group_kernel<HD>;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
+  CVB_TRY(ensure_dyn_smem(kern, smem));
   CVB_TRY(launch_pdl(kern, grid, dim3(ATT_THREADS), smem, st, 1, p));
   CVB_LAUNCHED();
   return 0;

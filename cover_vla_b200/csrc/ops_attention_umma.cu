@@ -1066,11 +1066,7 @@ int attention_umma(cudaStream_t st, const UmmaAttnCall& c) {
   const int body = std::max(4 * UA_QBLK + kslots * tk_pad * 128, nkb * UA_PBLK + nslots * UA_VBLK);
   CVB_REQUIRE(body <= UA_BODY_MAX && nslots >= 1, "tcgen05 prefix attention operands do not fit shared memory");
   const int smem = 1024 + body + (4 + 1 + 1 + 2 * UA_VSLOTS + 2 + 2) * 8 + 2 * 128 * 8 + 64;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    CVB_CUDA(cudaFuncSetAttribute(attn_prefix_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
+  CVB_TRY(ensure_dyn_smem(attn_prefix_umma_kernel, smem));
   dim3 grid((c.tq + UA_TOK - 1) / UA_TOK, c.batches);
   CVB_TRY(launch_pdl(attn_prefix_umma_kernel, grid, dim3(UA_THREADS), smem, st, 1, tmQ, tmK, tmVT, p));
   CVB_LAUNCHED();
@@ -1123,11 +1119,7 @@ int attention_decode_umma(cudaStream_t st, const AttnCall& c) {
   const int smem = 1024 + body + (4 + 1 + 1 + 1 + 2 * UD_VSLOTS + 2) * 8 + 16;
   const bool small = c.heads * c.tq * (hdw / 8) <= 3 * UD_SOFT;  // the denoise step has 40 query rows
   auto kern = small ? attn_decode_umma_kernel<3> : attn_decode_umma_kernel<8>;
-  static int attr_smem[2] = {0, 0};
-  if (smem > attr_smem[small]) {
-    CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem[small] = smem;
-  }
+  CVB_TRY(ensure_dyn_smem(kern, smem));
   CVB_TRY(launch_pdl(kern, dim3(c.batches, split), dim3(UD_THREADS), smem, st, 1, tmK, tmVT, p));
   CVB_LAUNCHED();
   return 0;
@@ -1169,11 +1161,7 @@ int attention_mha_umma(cudaStream_t st, const AttnCall& c) {
   p.q_rows_per_batch = q_rpb, p.k_rows_per_batch = k_rpb;
   p.out = c.out, p.o_bs = c.o_batch_stride, p.o_rs = c.o_row_stride, p.scale = c.scale;
   const int smem = 1024 + mha_smem_bytes(tk_pad, hd, hdp) + 8 * 8 + 2 * 128 * 8 + 64;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    CVB_CUDA(cudaFuncSetAttribute(attn_mha_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
+  CVB_TRY(ensure_dyn_smem(attn_mha_umma_kernel, smem));
   dim3 grid((c.tq + 127) / 128, c.heads, c.batches);
   CVB_TRY(launch_pdl(attn_mha_umma_kernel, grid, dim3(UM_THREADS), smem, st, 1, tmQ, tmK, p));
   CVB_LAUNCHED();

@@ -81,11 +81,7 @@ int launch(cudaStream_t st, const GemmCall& c, int grid) {
   g.n_out = c.n_out;
   g.m_dev = c.m_dev;
   auto kern = gemm_bf16_tcgen05<BN, STAGES, EPI>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
-  }
+  CVB_TRY(ensure_dyn_smem(kern, S::TOTAL));
   CVB_TRY(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), S::TOTAL, st, 1, tmA, tmB, g));
   CVB_LAUNCHED();
   return 0;
@@ -102,11 +98,7 @@ int launch_2sm(cudaStream_t st, const GemmCall& c) {
   g.resid = c.resid, g.resid_is_f32 = c.resid_is_f32, g.ldr = c.ldr;
   g.M = c.M, g.N = c.N, g.K = c.K, g.n_out = c.n_out, g.m_dev = nullptr;
   auto kern = gemm_bf16_tcgen05_2sm<EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM));
-    attr_set = true;
-  }
+  CVB_TRY(ensure_dyn_smem(kern, GEMM2_SMEM));
   const int tiles = ((c.M + 255) / 256) * ((c.N + 255) / 256);
   const int pairs = std::min(tiles, device_sm_count() / 2);
   CVB_TRY(launch_pdl(kern, dim3(2 * pairs), dim3(GEMM_THREADS), GEMM2_SMEM, st, 2, tmA, tmB, g));

@@ -27,16 +27,8 @@ int launch_skinny(cudaStream_t st, const GemmCall& c, const SkinnyArgs& g, int n
   const uint32_t body = (std::max<uint32_t>(g.stages * stage_bytes, g.Mp * 512u) + 1023u) & ~1023u;
   const int smem = 1024 + body + recv_bytes + (2 * g.stages + 2) * 8 + 16;
   auto kern = gemm_skinny_tcgen05<EPI>;
-  static int attr_smem = 0;
-  static bool nonportable = false;
-  if (smem > attr_smem) {
-    CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
-  if (g.S > 8 && !nonportable) {
-    CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    nonportable = true;
-  }
+  CVB_TRY(ensure_dyn_smem(kern, smem));
+  if (g.S > 8) CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));  // per device: set on every such launch
   CVB_TRY(launch_pdl(kern, dim3(n_tiles * g.S), dim3(SK_THREADS), smem, st, g.S, tmW, tmA, g));
   CVB_LAUNCHED();
   return 0;
@@ -152,11 +144,7 @@ int gemm_splitk_partial(cudaStream_t st, const GemmCall& c, int splits, int* spl
   CVB_TRY(get_tmap_cached(c.W, c.N, c.K, c.ldw, 128, &tmW));
   CVB_TRY(get_tmap_cached(c.A, c.M, c.K, c.lda, g.Mp, &tmA));
   const int smem = 1024 + g.stages * stage_bytes + (2 * g.stages + 1) * 8 + 16;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    CVB_CUDA(cudaFuncSetAttribute(gemm_splitk_partial_tcgen05<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
+  CVB_TRY(ensure_dyn_smem(gemm_splitk_partial_tcgen05<0>, smem));
   CVB_TRY(launch_pdl(gemm_splitk_partial_tcgen05<0>, dim3(n_tiles * S), dim3(SK_THREADS), smem, st, 1, tmW, tmA, g));
   CVB_LAUNCHED();
   if (splits_out != nullptr) *splits_out = S;

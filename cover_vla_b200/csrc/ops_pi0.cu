@@ -16,6 +16,8 @@ __global__ void im2col_kernel(const float* __restrict__ img, bf16* __restrict__ 
   const int gw = W / P;
   const int py = t / gw, px = t % gw;
   const int kreal = C * P * P;
+  img += static_cast<long>(blockIdx.y) * C * H * W;  // image of this observation
+  out += static_cast<long>(blockIdx.y) * gridDim.x * kpad;
   for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
     float v = 0.f;
     if (k < kreal) {
@@ -28,9 +30,9 @@ __global__ void im2col_kernel(const float* __restrict__ img, bf16* __restrict__ 
 }
 
 int im2col_patches(cudaStream_t st, const float* img, bf16* out, int C, int H, int W, int P,
-                   int kpad) {
+                   int kpad, int images) {
   const int tokens = (H / P) * (W / P);
-  CVB_TRY(launch_pdl(im2col_kernel, dim3(tokens), dim3(128), 0, st, 1, img, out, C, H, W, P, kpad));
+  CVB_TRY(launch_pdl(im2col_kernel, dim3(tokens, images), dim3(128), 0, st, 1, img, out, C, H, W, P, kpad));
   CVB_LAUNCHED();
   return 0;
 }
@@ -40,14 +42,16 @@ int im2col_patches(cudaStream_t st, const float* img, bf16* out, int C, int H, i
 //                             : bf16(embed[tok[r, t-n_img], :] * sqrt(D))               + HF get_image_features, :549-553)
 __global__ void build_prefix_kernel(const bf16* __restrict__ proj, const bf16* __restrict__ embed,
                                     const int64_t* __restrict__ tok, bf16* __restrict__ prefix,
-                                    int n_img, int n_lang, int tok_stride, int D, float sqrt_d, float sqrt_d_bf16) {
+                                    int n_img, int n_lang, int tok_stride, int D, float sqrt_d, float sqrt_d_bf16,
+                                    int rpo) {
   pdl_wait();
   pdl_launch();
   const int t = blockIdx.x, r = blockIdx.y;
   const int P = n_img + n_lang;
   bf16* dst = prefix + (static_cast<long>(r) * P + t) * D;
   if (t < n_img) {
-    const bf16* src = proj + static_cast<long>(t) * D;
+    // image rows of the observation this rephrase belongs to (rpo rephrases per observation; 0 = one observation)
+    const bf16* src = proj + (static_cast<long>(rpo > 0 ? r / rpo : 0) * n_img + t) * D;
     for (int i = threadIdx.x * 8; i < D; i += blockDim.x * 8) {
       const uint4 v = *reinterpret_cast<const uint4*>(src + i);
       const uint32_t u[4] = {v.x, v.y, v.z, v.w};
@@ -77,12 +81,13 @@ __global__ void build_prefix_kernel(const bf16* __restrict__ proj, const bf16* _
 }
 
 int build_prefix(cudaStream_t st, const bf16* proj, const bf16* embed, const int64_t* tok,
-                 bf16* prefix, int R, int n_img, int n_lang, int tok_stride, int D) {
+                 bf16* prefix, int R, int n_img, int n_lang, int tok_stride, int D, int rephrases_per_obs) {
   CVB_REQUIRE(D % 8 == 0, "lm width must be a multiple of 8");
   const float s = static_cast<float>(sqrt(static_cast<double>(D)));  // (float)(D ** 0.5)
   const float sb = __bfloat162float(__float2bfloat16_rn(s));
   dim3 grid(n_img + n_lang, R);
-  CVB_TRY(launch_pdl(build_prefix_kernel, dim3(grid), dim3(128), 0, st, 1, proj, embed, tok, prefix, n_img, n_lang, tok_stride, D, s, sb));
+  CVB_TRY(launch_pdl(build_prefix_kernel, dim3(grid), dim3(128), 0, st, 1, proj, embed, tok, prefix, n_img, n_lang, tok_stride, D, s, sb,
+                     rephrases_per_obs));
   CVB_LAUNCHED();
   return 0;
 }
@@ -242,16 +247,18 @@ int action_out_euler(cudaStream_t st, const bf16* hn, long ld, const float* w, c
 // ------------------------------------------------------------------------------------------------
 // suffix[n, 0, :] = float(bf16(state_emb))  (the state row never changes across denoise steps)
 __global__ void fill_state_rows_kernel(const float* __restrict__ state_emb, float* __restrict__ suffix,
-                                       int width, int suffix_len) {
+                                       int width, int suffix_len, int cpo) {
   pdl_wait();
   pdl_launch();
   float* dst = suffix + static_cast<long>(blockIdx.x) * suffix_len * width;
+  if (cpo > 0) state_emb += static_cast<long>(blockIdx.x / cpo) * width;  // state of this candidate's observation
   for (int i = threadIdx.x; i < width; i += blockDim.x) dst[i] = bf16_round(state_emb[i]);
 }
 
 int fill_state_rows(cudaStream_t st, const float* state_emb, float* suffix, int n_cand, int width,
-                    int suffix_len) {
-  CVB_TRY(launch_pdl(fill_state_rows_kernel, dim3(n_cand), dim3(256), 0, st, 1, state_emb, suffix, width, suffix_len));
+                    int suffix_len, int cands_per_obs) {
+  CVB_TRY(launch_pdl(fill_state_rows_kernel, dim3(n_cand), dim3(256), 0, st, 1, state_emb, suffix, width, suffix_len,
+                     cands_per_obs));
   CVB_LAUNCHED();
   return 0;
 }

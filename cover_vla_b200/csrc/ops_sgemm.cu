@@ -229,11 +229,7 @@ template <int PTM, int PTN>
 int launch_pipe(cudaStream_t st, const SgemmCall& c) {
   constexpr int smem = PSTAGES * (PTM + PTN) * PLD * static_cast<int>(sizeof(float));
   auto kern = sgemm_pipe_kernel<PTM, PTN>;
-  static bool attr = false;
-  if (!attr && smem > 48 * 1024) {
-    CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
+  if (smem > 48 * 1024) CVB_TRY(ensure_dyn_smem(kern, smem));
   dim3 grid((c.N + PTN - 1) / PTN, (c.M + PTM - 1) / PTM);
   CVB_TRY(launch_pdl(kern, grid, dim3(128), smem, st, 1, c.A, c.lda, c.W, c.ldw, c.M, c.N, c.K, c.C, c.ldc, c.bias,
                      c.row_bias, c.resid, c.ldr, c.act, c.out_group, c.w_dynamic));

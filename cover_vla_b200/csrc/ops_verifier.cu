@@ -323,11 +323,7 @@ int traj_attention(cudaStream_t st, const float* qkv, const float* traj, float* 
   CVB_REQUIRE(S <= 32, "history length must be <= 32");
   CVB_REQUIRE((3 * E) % 4 == 0, "embed must be a multiple of 4");
   const size_t smem = (static_cast<size_t>(S) * 3 * E + static_cast<size_t>(H) * S * S) * sizeof(float);
-  static size_t attr = 0;
-  if (smem > attr) {
-    CVB_CUDA(cudaFuncSetAttribute(traj_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  if (smem > 48 * 1024) CVB_TRY(ensure_dyn_smem(traj_attention_kernel, (int)smem));
   CVB_TRY(launch_pdl(traj_attention_kernel, dim3(n_cand), dim3(256), smem, st, 1, qkv, traj, out, S, E, H, adim, pad_value));
   CVB_LAUNCHED();
   return 0;
@@ -391,17 +387,20 @@ __device__ void select_block(const float* __restrict__ scores, int R, int K, flo
   }
 }
 
-__global__ void __launch_bounds__(1024) fuse_score_select_kernel(const float* __restrict__ it, const float* __restrict__ act,
-                                                                 int M, int N, int E, float* __restrict__ scores, int R,
-                                                                 int K, float* __restrict__ group_mean,
-                                                                 int* __restrict__ best_idx, float* __restrict__ best_score,
-                                                                 int do_select) {
+// grid = (candidate blocks, observations): 8 warps per CTA, one candidate per warp, every load of a candidate in
+// flight at once (the round-1 kernel ran ONE CTA whose warps walked the members in dependent L2 round trips: 52 us).
+__global__ void __launch_bounds__(256) fuse_score_kernel(const float* __restrict__ it, long it_obs_stride,
+                                                         const float* __restrict__ act, long act_member_stride, int M, int N,
+                                                         int E, float* __restrict__ scores) {
   pdl_wait();
   pdl_launch();
   extern __shared__ float sm[];
   __shared__ float red[32];
-  float* fit = sm;          // [E]
-  float* sh_mean = sm + E;  // [R]
+  const int obs = blockIdx.y;
+  it += obs * it_obs_stride;
+  act += static_cast<long>(obs) * N * E;
+  scores += static_cast<long>(obs) * N;
+  float* fit = sm;  // [E]
   float ss = 0.f;
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
     float s = 0.f;
@@ -414,52 +413,64 @@ __global__ void __launch_bounds__(1024) fuse_score_select_kernel(const float* __
   __syncthreads();
   for (int e = threadIdx.x; e < E; e += blockDim.x) fit[e] = fit[e] / nrm;
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int n = warp; n < N; n += nw) {
-    float an = 0.f;
-    for (int e = lane; e < E; e += 32) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= N) return;
+  // fused action embedding of candidate n: mean over the members, then normalise (efficient_ensemble_merged.py:404-411)
+  constexpr int kMaxPer = 32;  // E <= 1024
+  float v[kMaxPer];
+  float an = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxPer; ++j) {
+    const int e = lane + 32 * j;
+    v[j] = 0.f;
+    if (e < E) {
       float s = 0.f;
-      for (int m = 0; m < M; ++m) s += act[(static_cast<long>(m) * N + n) * E + e];
-      s = s / static_cast<float>(M);
-      an += s * s;
+      for (int m = 0; m < M; ++m) s += act[m * act_member_stride + static_cast<long>(n) * E + e];
+      v[j] = s / static_cast<float>(M);
+      an += v[j] * v[j];
     }
-    an = sqrtf(wsum(an));
-    float dot = 0.f;
-    for (int e = lane; e < E; e += 32) {
-      float s = 0.f;
-      for (int m = 0; m < M; ++m) s += act[(static_cast<long>(m) * N + n) * E + e];
-      s = s / static_cast<float>(M);
-      dot = fmaf(fit[e], s / an, dot);
-    }
-    dot = wsum(dot);
-    if (lane == 0) scores[n] = dot;
   }
-  __syncthreads();
-  if (do_select) {
-    __threadfence_block();
-    select_block(scores, R, K, group_mean, best_idx, best_score, sh_mean);
+  an = sqrtf(wsum(an));
+  float dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxPer; ++j) {
+    const int e = lane + 32 * j;
+    if (e < E) dot = fmaf(fit[e], v[j] / an, dot);
   }
+  dot = wsum(dot);
+  if (lane == 0) scores[n] = dot;
 }
+
+int select_best(cudaStream_t st, const float* scores, int R, int K, float* group_mean, int* best_idx,
+                float* best_score, int n_obs);
 int fuse_score_select(cudaStream_t st, const float* it, const float* act, int M, int N, int E, float* scores, int R,
-                      int K, float* group_mean, int* best_idx, float* best_score, int do_select) {
+                      int K, float* group_mean, int* best_idx, float* best_score, int do_select, int n_obs,
+                      long act_member_stride) {
   CVB_REQUIRE(!do_select || R * K == N, "R*K must equal the number of candidates");
-  CVB_TRY(launch_pdl(fuse_score_select_kernel, dim3(1), dim3(1024), (E + R + 1) * sizeof(float), st, 1, it, act, M, N, E, scores, R, K, group_mean,
-                                                                         best_idx, best_score, do_select));
+  CVB_REQUIRE(E <= 1024, "embedding width above 1024");
+  if (act_member_stride == 0) act_member_stride = static_cast<long>(n_obs) * N * E;
+  CVB_TRY(launch_pdl(fuse_score_kernel, dim3((N + 7) / 8, n_obs), dim3(256), E * sizeof(float), st, 1, it,
+                     static_cast<long>(M) * E, act, act_member_stride, M, N, E, scores));
   CVB_LAUNCHED();
+  if (do_select) CVB_TRY(select_best(st, scores, R, K, group_mean, best_idx, best_score, n_obs));
   return 0;
 }
 
+// one CTA per observation
 __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ scores, int R, int K,
                                                      float* __restrict__ group_mean, int* __restrict__ best_idx,
                                                      float* __restrict__ best_score) {
   pdl_wait();
   pdl_launch();
   extern __shared__ float sm[];
-  select_block(scores, R, K, group_mean, best_idx, best_score, sm);
+  const int obs = blockIdx.x;
+  select_block(scores + static_cast<long>(obs) * R * K, R, K, group_mean != nullptr ? group_mean + obs * R : nullptr,
+               best_idx + obs, best_score + obs, sm);
 }
 int select_best(cudaStream_t st, const float* scores, int R, int K, float* group_mean, int* best_idx,
-                float* best_score) {
-  CVB_TRY(launch_pdl(select_kernel, dim3(1), dim3(256), (R + 1) * sizeof(float), st, 1, scores, R, K, group_mean, best_idx, best_score));
+                float* best_score, int n_obs) {
+  CVB_TRY(launch_pdl(select_kernel, dim3(n_obs), dim3(256), (R + 1) * sizeof(float), st, 1, scores, R, K, group_mean, best_idx, best_score));
   CVB_LAUNCHED();
   return 0;
 }
@@ -473,10 +484,11 @@ int select_best(cudaStream_t st, const float* scores, int R, int K, float* group
 // numpy's promotion: (x + 1) / 2 in float32, then * (p99 - p01) + p01 in float64, rounded to float32.
 __global__ void format_traj_kernel(const float* __restrict__ actions, int chunk, int adim_stride,
                                    FormatStats st, const float* __restrict__ past, int num_past, int history,
-                                   int n_future, float* __restrict__ traj) {
+                                   int n_future, float* __restrict__ traj, int cands_per_obs) {
   pdl_wait();
   pdl_launch();
   const int n = blockIdx.x;
+  if (cands_per_obs > 0) past += static_cast<long>(n / cands_per_obs) * num_past * 7;  // this observation's history
   const int A = 7;
   const int used = num_past + n_future;
   const int lead = history - used;  // rows of -5 padding (>= 0, checked on the host)
@@ -502,12 +514,12 @@ __global__ void format_traj_kernel(const float* __restrict__ actions, int chunk,
 }
 int format_trajectories(cudaStream_t stream, const float* actions, int n_cand, int chunk, int adim_stride,
                         const FormatStats& st, const float* past, int num_past, int history, int n_future,
-                        float* traj) {
+                        float* traj, int cands_per_obs) {
   CVB_REQUIRE(n_future >= 1 && n_future <= chunk, "n_future must be in [1, chunk]");
   CVB_REQUIRE(num_past >= 0 && num_past + n_future <= history, "history too short for past + future actions");
   CVB_REQUIRE(adim_stride >= 7, "action stride must be >= 7");
   CVB_TRY(launch_pdl(format_traj_kernel, dim3(n_cand), dim3(96), 0, stream, 1, actions, chunk, adim_stride, st, past, num_past, history, n_future,
-                                                traj));
+                                                traj, cands_per_obs));
   CVB_LAUNCHED();
   return 0;
 }

@@ -36,7 +36,7 @@ struct FormatStats {
 };
 int format_trajectories(cudaStream_t stream, const float* actions, int n_cand, int chunk, int adim_stride,
                         const FormatStats& st, const float* past, int num_past, int history, int n_future,
-                        float* traj);
+                        float* traj, int cands_per_obs = 0);  // cands_per_obs > 0: past is [n_obs][num_past][7]
 int execution_action(cudaStream_t stream, const float* actions, int n_cand, int chunk, int adim_stride, const FormatStats& st,
                      const int* best_idx, int K, int step, double* out, int* votes);
 
@@ -51,9 +51,12 @@ int traj_attention(cudaStream_t st, const float* qkv, const float* traj, float* 
                    int adim, float pad_value);
 int masked_mean_l2norm(cudaStream_t st, const float* x, const float* traj, float* out, int n_cand, int S, int E,
                        int adim, float pad_value);
+// n_obs observations: it [n_obs][M][E], act [M][n_obs * N][E] (member stride act_member_stride, 0 = contiguous),
+// scores [n_obs * N], group_mean [n_obs * R], best_idx / best_score [n_obs]
 int fuse_score_select(cudaStream_t st, const float* it, const float* act, int M, int N, int E, float* scores, int R,
-                      int K, float* group_mean, int* best_idx, float* best_score, int do_select);
+                      int K, float* group_mean, int* best_idx, float* best_score, int do_select, int n_obs = 1,
+                      long act_member_stride = 0);
 int select_best(cudaStream_t st, const float* scores, int R, int K, float* group_mean, int* best_idx,
-                float* best_score);
+                float* best_score, int n_obs = 1);
 
 }  // namespace cvb

@@ -20,6 +20,7 @@ _CFG_FIELDS = [
     "vf_members", "vf_embed", "vf_pool_heads", "vf_pool_layers", "vf_traj_layers", "vf_traj_ff",
     "vf_history", "vf_action_dim",
     "use_cuda_graph",
+    "max_observations",
 ]
 
 
@@ -70,6 +71,7 @@ class EngineConfig:
     vf_history: int = 10
     vf_action_dim: int = 7
     use_cuda_graph: int = 1
+    max_observations: int = 1
 
     def to_c(self) -> CvbConfig:
         c = CvbConfig()
@@ -102,6 +104,9 @@ class Engine:
             _lib.check(self.lib.cvb_create(C.byref(ccfg), C.byref(self._h)))
         self._keep = {}  # tensors whose memory the handle borrows
         self.finalized = False
+        # bumped by every call that rewrites the verifier's image/text context, so a host-side cache of "the context is
+        # still (image, instruction) X" (EfficientEnsembleMerged) notices another caller's write
+        self.ctx_generation = 0
 
     def _declare(self):
         L = self.lib
@@ -112,6 +117,7 @@ class Engine:
         L.cvb_required_weight_count.argtypes = [C.c_void_p]
         L.cvb_required_weight_name.argtypes = [C.c_void_p, C.c_int]
         L.cvb_required_weight_name.restype = C.c_char_p
+        L.cvb_required_weight_dtype.argtypes = [C.c_void_p, C.c_int]
         L.cvb_finalize.argtypes = [C.c_void_p, C.c_void_p]
         L.cvb_pi0_sample.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.cvb_pi0_set_lang_len_hint.argtypes = [C.c_void_p, C.c_int]
@@ -124,6 +130,10 @@ class Engine:
         L.cvb_cover_step.argtypes = ([C.c_void_p] * 6 + [C.c_int, C.c_int] + [C.c_void_p] * 2 +
                                      [C.POINTER(C.c_double)] * 2 + [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7)
         L.cvb_select.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.cvb_pi0_sample_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.cvb_pi0_run_phase_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.cvb_cover_step_batch.argtypes = ([C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_int] + [C.c_void_p] * 2 +
+                                           [C.POINTER(C.c_double)] * 2 + [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7)
 
     # ------------------------------------------------------------------ weights
     def required_weights(self) -> list[str]:
@@ -140,11 +150,33 @@ class Engine:
         _lib.check(self.lib.cvb_bind_weight(self._h, key.encode(), _lib.ptr(t), _DTYPES[t.dtype], t.dim(), shape))
         self._keep[key] = t
 
+    def required_dtypes(self) -> dict:
+        """canonical weight name -> torch dtype the engine expects (bf16 / fp32)."""
+        inv = {v: k for k, v in _DTYPES.items()}
+        n = self.lib.cvb_required_weight_count(self._h)
+        return {self.lib.cvb_required_weight_name(self._h, i).decode(): inv[self.lib.cvb_required_weight_dtype(self._h, i)]
+                for i in range(n)}
+
     def load_state_dict(self, sd: dict, strict_unused: bool = False):
-        """Bind every tensor of a reference state dict (names unchanged)."""
+        """Bind a reference state dict (names unchanged).  Like the reference's load_state_dict -
+        which copies into parameters already cast by to_bfloat16_like_physical_intelligence
+        (paligemma_with_expert.py:216-227) - the STORED dtype does not matter: every tensor is cast to the dtype the
+        engine expects.  Tensors the sampling path never reads (lm_head, the tied embedding copy, normalisation
+        buffers, ...) are skipped instead of being copied to the GPU; strict_unused=True raises on them."""
+        from .synthetic import canonical_key
+        want = self.required_dtypes()
+        unused = []
         for k, v in sd.items():
-            if isinstance(v, torch.Tensor):
-                self.bind(k, v)
+            if not isinstance(v, torch.Tensor):
+                continue
+            ck = canonical_key(k)
+            if ck not in want:
+                unused.append(k)
+                continue
+            self.bind(k, v.to(device=self.device, dtype=want[ck]))
+        if strict_unused and unused:
+            raise _lib.CvbError(f"state dict has tensors the engine does not use: {unused[:5]} ...")
+        return unused
 
     def finalize(self, release_repacked: bool = True):
         with torch.cuda.device(self.device):
@@ -190,9 +222,71 @@ class Engine:
                                                _lib.stream_ptr()))
         return out
 
-    def pi0_run_phase(self, phase: int, R: int, K: int):
+    def pi0_run_phase(self, phase: int, R: int, K: int, B: int = 1):
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.cvb_pi0_run_phase(self._h, phase, R, K, _lib.stream_ptr()))
+            _lib.check(self.lib.cvb_pi0_run_phase_batch(self._h, phase, B, R, K, _lib.stream_ptr()))
+
+    def pi0_sample_batch(self, images, lang_tokens, lang_len, states, noise, K: int, out=None,
+                         lang_len_max: int | None = None):
+        """B observations in one pass (cvb_pi0_sample_batch): images f32 [B,3,H,W]; lang_tokens i64 [B,R,L]; lang_len
+        i32 [B,R]; states f32 [B,max_state_dim]; noise f32 [B,R*K,chunk,max_action_dim] -> actions (same shape)."""
+        cfg = self.cfg
+        B, R = lang_tokens.shape[0], lang_tokens.shape[1]
+        assert B <= cfg.max_observations, "engine was built with a smaller max_observations"
+        assert images.dtype == torch.float32 and tuple(images.shape) == (B, 3, cfg.vis_image, cfg.vis_image)
+        assert lang_tokens.dtype == torch.int64 and lang_tokens.shape[2] == cfg.max_lang_len
+        assert lang_len.dtype == torch.int32 and tuple(lang_len.shape) == (B, R)
+        assert states.dtype == torch.float32 and tuple(states.shape) == (B, cfg.max_state_dim)
+        assert noise.dtype == torch.float32 and tuple(noise.shape) == (B, R * K, cfg.chunk_size, cfg.max_action_dim)
+        for t in (images, lang_tokens, lang_len, states, noise):
+            assert t.is_cuda and t.is_contiguous()
+        if out is None:
+            out = torch.empty_like(noise)
+        self.set_lang_len_hint(lang_len_max)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cvb_pi0_sample_batch(self._h, B, _lib.ptr(images), _lib.ptr(lang_tokens), _lib.ptr(lang_len),
+                                                     _lib.ptr(states), _lib.ptr(noise), R, K, _lib.ptr(out),
+                                                     _lib.stream_ptr()))
+        return out
+
+    def cover_step_batch(self, images, lang_tokens, lang_len, states, noise, K: int, vf_images, vf_tokens, p01, p99,
+                         past=None, n_future: int | None = None, lang_len_max: int | None = None):
+        """B whole decisions in one graph (cvb_cover_step_batch).  Shapes as pi0_sample_batch plus vf_images f32
+        [B,3,S,S], vf_tokens i64 [B,ctx], past f32 [B,num_past,7] or None.  Returns device tensors (actions
+        [B,N,chunk,A], traj [B,N,H,7], scores [B,N], group_mean [B,R], best_idx i32 [B], best_score [B])."""
+        cfg = self.cfg
+        B, R = lang_tokens.shape[0], lang_tokens.shape[1]
+        N = R * K
+        assert B <= cfg.max_observations, "engine was built with a smaller max_observations"
+        assert tuple(noise.shape) == (B, N, cfg.chunk_size, cfg.max_action_dim) and noise.dtype == torch.float32
+        assert tuple(images.shape) == (B, 3, cfg.vis_image, cfg.vis_image) and tuple(states.shape) == (B, cfg.max_state_dim)
+        assert tuple(vf_images.shape) == (B, 3, cfg.vf_image, cfg.vf_image) and tuple(vf_tokens.shape) == (B, cfg.vf_text_ctx)
+        assert tuple(lang_len.shape) == (B, R) and lang_tokens.shape[2] == cfg.max_lang_len
+        for t in (images, lang_tokens, lang_len, states, noise, vf_images, vf_tokens):
+            assert t.is_cuda and t.is_contiguous()
+        assert lang_tokens.dtype == torch.int64 and lang_len.dtype == torch.int32 and vf_tokens.dtype == torch.int64
+        num_past = 0 if past is None else int(past.shape[1])
+        if past is not None:
+            assert past.dtype == torch.float32 and past.is_cuda and past.is_contiguous() and tuple(past.shape) == (B, num_past, 7)
+        n_future = n_future or cfg.chunk_size
+        dev = self.device
+        actions = torch.empty_like(noise)
+        traj = torch.empty(B, N, cfg.vf_history, 7, dtype=torch.float32, device=dev)
+        scores = torch.empty(B, N, dtype=torch.float32, device=dev)
+        gmean = torch.empty(B, R, dtype=torch.float32, device=dev)
+        bidx = torch.zeros(B, dtype=torch.int32, device=dev)
+        bscore = torch.zeros(B, dtype=torch.float32, device=dev)
+        a = (C.c_double * 6)(*p01)
+        b = (C.c_double * 6)(*p99)
+        self.set_lang_len_hint(lang_len_max)
+        self.ctx_generation += 1
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.cvb_cover_step_batch(self._h, B, _lib.ptr(images), _lib.ptr(lang_tokens), _lib.ptr(lang_len),
+                                                     _lib.ptr(states), _lib.ptr(noise), R, K, _lib.ptr(vf_images),
+                                                     _lib.ptr(vf_tokens), a, b, _lib.ptr(past), num_past, n_future,
+                                                     _lib.ptr(actions), _lib.ptr(traj), _lib.ptr(scores), _lib.ptr(gmean),
+                                                     _lib.ptr(bidx), _lib.ptr(bscore), _lib.stream_ptr()))
+        return actions, traj, scores, gmean, bidx, bscore
 
     # ------------------------------------------------------------------ verifier
     def verifier_score(self, image, text_tokens, traj, R: int, K: int, recompute_context: bool = True):
@@ -210,6 +304,8 @@ class Engine:
         gmean = torch.empty(max(R, 1), dtype=torch.float32, device=self.device)
         bidx = torch.zeros(1, dtype=torch.int32, device=self.device)
         bscore = torch.zeros(1, dtype=torch.float32, device=self.device)
+        if recompute_context:
+            self.ctx_generation += 1
         with torch.cuda.device(self.device):
             _lib.check(self.lib.cvb_verifier_score(self._h, _lib.ptr(image), _lib.ptr(text_tokens), _lib.ptr(traj),
                                                    N, R, K, _lib.ptr(scores), _lib.ptr(gmean), _lib.ptr(bidx),
@@ -217,7 +313,7 @@ class Engine:
         return scores, gmean, bidx, bscore
 
     def cover_step(self, image, lang_tokens, lang_len, state, noise, K: int, vf_image, vf_tokens, p01, p99, past=None,
-                   n_future: int | None = None, lang_len_max: int | None = None, select: bool = True):
+                   n_future: int | None = None, lang_len_max: int | None = None):
         """One whole decision (cvb_cover_step): sample -> format -> score -> select in one graph.  Returns device
         tensors (actions [N,chunk,A], traj [N,H,7], scores [N], group_mean [R], best_idx i32 [1], best_score [1])."""
         cfg = self.cfg
@@ -240,9 +336,10 @@ class Engine:
         a = (C.c_double * 6)(*p01)
         b = (C.c_double * 6)(*p99)
         self.set_lang_len_hint(lang_len_max)
+        self.ctx_generation += 1
         with torch.cuda.device(self.device):
             _lib.check(self.lib.cvb_cover_step(self._h, _lib.ptr(image), _lib.ptr(lang_tokens), _lib.ptr(lang_len),
-                                               _lib.ptr(state), _lib.ptr(noise), R if select else R, K, _lib.ptr(vf_image),
+                                               _lib.ptr(state), _lib.ptr(noise), R, K, _lib.ptr(vf_image),
                                                _lib.ptr(vf_tokens), a, b, _lib.ptr(past), num_past, n_future,
                                                _lib.ptr(actions), _lib.ptr(traj), _lib.ptr(scores), _lib.ptr(gmean),
                                                _lib.ptr(bidx), _lib.ptr(bscore), _lib.stream_ptr()))
@@ -254,11 +351,13 @@ class Engine:
         cfg = self.cfg
         assert image.dtype == torch.float32 and image.numel() == 3 * cfg.vf_image ** 2 and image.is_contiguous()
         assert text_tokens.dtype == torch.int64 and text_tokens.numel() == cfg.vf_text_ctx
+        self.ctx_generation += 1
         with torch.cuda.device(self.device):
             _lib.check(self.lib.cvb_verifier_context(self._h, _lib.ptr(image), _lib.ptr(text_tokens), _lib.stream_ptr()))
 
     def verifier_set_features(self, patch, text):
         assert patch.dtype == torch.float32 and text.dtype == torch.float32 and patch.is_cuda and text.is_cuda
+        self.ctx_generation += 1
         with torch.cuda.device(self.device):
             _lib.check(self.lib.cvb_verifier_set_features(self._h, _lib.ptr(patch.contiguous()),
                                                           _lib.ptr(text.contiguous()), _lib.stream_ptr()))

@@ -19,7 +19,7 @@ import torch.nn.functional as F
 from torch import Tensor
 
 from ..engine import Engine, EngineConfig
-from .configuration_pi0 import PI0Config
+from .configuration_pi0 import PI0Config, PolicyFeature
 
 OBS_ROBOT = "observation.state"
 ACTION = "action"
@@ -136,8 +136,17 @@ class PI0FlowMatching:
             hint = self.lang_len_hint
         R, K = self._layout(images, lang_tokens)
         if R > self.engine.cfg.max_rephrases or K > self.engine.cfg.max_samples:
-            raise ValueError(f"batch layout R={R}, K={K} exceeds the engine workspace "
-                             f"(max_rephrases={self.engine.cfg.max_rephrases}, max_samples={self.engine.cfg.max_samples})")
+            # e.g. two adjacent rephrases tokenise identically (duplicates, truncation) so the rows do not group into the
+            # configured R x K, or the batch is larger than the workspace: the reference handles any batch, so fall back
+            # to row-by-row prompts (K = 1) in chunks of max_rephrases - same arithmetic, no de-duplication
+            out = torch.empty_like(noise)
+            step = self.engine.cfg.max_rephrases
+            for a in range(0, bsize, step):
+                b = min(bsize, a + step)
+                out[a:b] = self.engine.pi0_sample(img[0].contiguous(), lang_tokens[a:b].contiguous(),
+                                                  lang_len[a:b].contiguous(), state[0].contiguous(),
+                                                  noise[a:b].contiguous(), K=1, lang_len_max=hint)
+            return out
         return self.engine.pi0_sample(img[0].contiguous(), lang_tokens[::K].contiguous(), lang_len[::K].contiguous(),
                                       state[0].contiguous(), noise.contiguous(), K=K, lang_len_max=hint)
 
@@ -219,8 +228,37 @@ class PI0Policy:
         if config is None:
             raw = json.loads((path / "config.json").read_text())
             known = {f for f in PI0Config.__dataclass_fields__}
-            config = PI0Config(**{k: v for k, v in raw.items() if k in known and k not in ("input_features", "output_features", "normalization_mapping")})
+            args = {k: v for k, v in raw.items() if k in known and k not in ("input_features", "output_features",
+                                                                             "normalization_mapping")}
+            # features and the normalisation mapping as the reference's PreTrainedConfig stores them
+            # (configs/policies.py:130-176): {"name": {"type": "VISUAL", "shape": [3, 224, 224]}}, {"VISUAL": "IDENTITY"}
+            for fk in ("input_features", "output_features"):
+                if isinstance(raw.get(fk), dict):
+                    args[fk] = {name: PolicyFeature(str(ft["type"]).split(".")[-1], tuple(ft["shape"]))
+                                for name, ft in raw[fk].items()}
+            if isinstance(raw.get("normalization_mapping"), dict):
+                args["normalization_mapping"] = {str(k).split(".")[-1]: str(v).split(".")[-1]
+                                                 for k, v in raw["normalization_mapping"].items()}
+            if isinstance(args.get("resize_imgs_with_padding"), list):
+                args["resize_imgs_with_padding"] = tuple(args["resize_imgs_with_padding"])
+            config = PI0Config(**args)
         sd = load_file(str(path / "model.safetensors"))
+        # dataset statistics travel as buffers of the (un)normalisation modules (normalize.py:40-43):
+        # normalize_inputs.buffer_<feature with . -> _>.<mean|std|min|max>
+        if "dataset_stats" not in kw:
+            stats = {}
+            for k, v in sd.items():
+                if k.startswith(("normalize_inputs.buffer_", "unnormalize_outputs.buffer_")):
+                    feat, stat = k.split("buffer_", 1)[1].rsplit(".", 1)
+                    stats.setdefault(feat, {})[stat] = v
+            if stats:
+                names = list(config.input_features) + list(config.output_features)
+                kw["dataset_stats"] = {n: stats[n.replace(".", "_")] for n in names if n.replace(".", "_") in stats}
+        need = {t for t, m in config.normalization_mapping.items() if str(getattr(m, "name", m)) != "IDENTITY"}
+        used = {ft.type for ft in list(config.input_features.values()) + list(config.output_features.values())}
+        if need & used and not kw.get("dataset_stats"):
+            raise ValueError(f"checkpoint config normalises {sorted(need & used)} features but carries no dataset statistics: "
+                             "pass dataset_stats= (the reference would fail on its infinite placeholder buffers)")
         if language_tokenizer is None:
             try:
                 from transformers import AutoTokenizer
@@ -272,6 +310,7 @@ class PI0Policy:
     def prepare_language(self, batch):
         device = batch[OBS_ROBOT].device
         if "lang_tokens" in batch:  # pre-tokenised (tests / hosts without the PaliGemma tokenizer)
+            self.model.lang_len_hint = None  # a bound left by an earlier tokenised call must not truncate these prompts
             return batch["lang_tokens"].to(device), batch["lang_masks"].to(device=device, dtype=torch.bool)
         if self.language_tokenizer is None:
             raise RuntimeError("no language tokenizer available offline: pass `lang_tokens` / `lang_masks` in the batch")

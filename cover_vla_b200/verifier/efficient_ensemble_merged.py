@@ -11,7 +11,7 @@ pair is not re-encoded on the second call of a decision (the 1-candidate gate, t
 """
 from __future__ import annotations
 
-import zlib
+import hashlib
 
 import numpy as np
 import torch
@@ -74,8 +74,22 @@ class EfficientEnsembleMerged:
                                 max_samples=1, **cfgd)
             engine = Engine(ecfg, device=self.device)
             if trunk_state_dict is None:
-                raise RuntimeError("the SigLIP2 trunk weights must be passed as trunk_state_dict "
-                                   "(open_clip / hub access is not available here)")
+                # exactly what the reference does (efficient_ensemble_merged.py:57-69): the shared trunk, its image
+                # transform and its tokenizer come from open_clip, not from the checkpoint
+                try:
+                    import open_clip
+                except ImportError as e:
+                    raise RuntimeError("the SigLIP2 trunk is loaded with open_clip.create_model_from_pretrained("
+                                       f"{self.backbone!r}) like the reference does, but open_clip is not installed: "
+                                       "install open_clip_torch + timm, or pass trunk_state_dict= (and tokenizer= / "
+                                       "preprocess=)") from e
+                siglip_model, oc_preprocess = open_clip.create_model_from_pretrained(self.backbone)
+                trunk_state_dict = siglip_model.state_dict()
+                if preprocess is None:
+                    preprocess = oc_preprocess
+                if tokenizer is None:
+                    tokenizer = open_clip.get_tokenizer(self.backbone)
+                del siglip_model
             for k, v in trunk_state_dict.items():
                 k = k if k.startswith("verifier.trunk.") else "verifier.trunk." + k
                 if k in engine_required(engine):
@@ -130,11 +144,14 @@ class EfficientEnsembleMerged:
         tok = self._tokens(instruction)
         key = None
         if raw is not None:
-            key = (zlib.crc32(raw), len(raw), tuple(tok.tolist()))
-        recompute = key is None or key != self._ctx_key
+            key = (hashlib.blake2b(raw, digest_size=16).digest(), len(raw), tuple(tok.tolist()))
+        # reuse only if the pair is unchanged AND nobody else (CoverStep, verifier_context, ...) rewrote the engine's
+        # context since this wrapper last did (Engine.ctx_generation)
+        recompute = key is None or key != self._ctx_key or self.engine.ctx_generation != getattr(self, "_ctx_gen", -1)
         self._ctx_key = key
         if not recompute:
             return None, None, False
+        self._ctx_gen = self.engine.ctx_generation + 1  # the verifier_score(recompute_context=True) that follows bumps it
         return img.to(self.device).contiguous(), tok.to(self.device).contiguous(), True
 
     def _pad(self, all_action_histories) -> torch.Tensor:

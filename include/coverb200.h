@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define CVB_ABI_VERSION 1
+#define CVB_ABI_VERSION 2
 #if defined(__GNUC__)
 #define CVB_API __attribute__((visibility("default")))
 #else
@@ -126,6 +126,9 @@ typedef struct cvb_config {
   int32_t vf_members, vf_embed, vf_pool_heads, vf_pool_layers, vf_traj_layers, vf_traj_ff;
   int32_t vf_history, vf_action_dim;
   int32_t use_cuda_graph; /* capture the per-(R,K) launch sequence once and replay it */
+  /* observations per batched call (cvb_pi0_sample_batch / cvb_cover_step_batch); 0 or 1 = single-observation handle.
+   * Workspace (KV caches, activations) is sized for max_observations * max_rephrases prompts. */
+  int32_t max_observations;
 } cvb_config;
 
 typedef struct cvb_handle cvb_handle;
@@ -145,6 +148,9 @@ CVB_API int cvb_bind_weight(cvb_handle* h, const char* key, const void* dev_ptr,
 /* Number of weights the configuration requires; names retrievable one by one (for loaders / tests). */
 CVB_API int cvb_required_weight_count(cvb_handle* h);
 CVB_API const char* cvb_required_weight_name(cvb_handle* h, int index);
+/* dtype (CVB_F32 / CVB_BF16) the engine expects for required weight `index` - what the reference's
+ * to_bfloat16_like_physical_intelligence (paligemma_with_expert.py:216-227) leaves it in; loaders cast to it. */
+CVB_API int cvb_required_weight_dtype(cvb_handle* h, int index);
 /* Validate that every required weight is bound, repack, allocate the workspace. */
 CVB_API int cvb_finalize(cvb_handle* h, void* stream);
 
@@ -160,6 +166,18 @@ CVB_API int cvb_pi0_sample(cvb_handle* h, const float* image, const int64_t* lan
                            const int32_t* lang_len, const float* state, const float* noise, int R,
                            int K, float* actions, void* stream);
 
+/* B independent observations in ONE pass (the episode-batched driver around
+ * run_simpler_eval_with_openpi.py:190-449; BASELINE.json configs[4]).  Same arithmetic per observation as B calls of
+ * cvb_pi0_sample - each observation's rephrases attend only its own image, each candidate only its own rephrase's
+ * KV cache - but every weight is streamed once for all B * R * K candidates, so the denoise GEMMs run on
+ * 5 * B * R * K rows instead of 5 * R * K.  Layouts are observation-major:
+ *   images f32 [B, 3, vis_image, vis_image]; lang_tokens i64 [B*R, max_lang_len]; lang_len i32 [B*R];
+ *   states f32 [B, max_state_dim]; noise / actions f32 [B*R*K, chunk_size, max_action_dim].
+ * Requires B <= cfg.max_observations. */
+CVB_API int cvb_pi0_sample_batch(cvb_handle* h, int B, const float* images, const int64_t* lang_tokens,
+                                 const int32_t* lang_len, const float* states, const float* noise, int R, int K,
+                                 float* actions, void* stream);
+
 /* Optional bound on the number of VALID language tokens per prompt for the following cvb_pi0_sample calls (0 = none:
  * max_lang_len rows are processed).  Right-padded tokens are masked as keys and never read (exact),
  * so a host that knows its tokenizer output (it produced it) lets the prefix skip them; longer prompts are truncated
@@ -169,6 +187,8 @@ CVB_API int cvb_pi0_set_lang_len_hint(cvb_handle* h, int max_valid_tokens);
 /* Profiling hook: re-run one phase (0 vision tower, 1 prefix, 2 denoise loop) eagerly on the inputs staged by
  * the last cvb_pi0_sample call, so a host can time the phases separately with CUDA events. */
 CVB_API int cvb_pi0_run_phase(cvb_handle* h, int phase, int R, int K, void* stream);
+/* same for the inputs staged by the last cvb_pi0_sample_batch / cvb_cover_step_batch call with B observations */
+CVB_API int cvb_pi0_run_phase_batch(cvb_handle* h, int phase, int B, int R, int K, void* stream);
 
 /* Score N = R*K candidate action histories against ONE (image, instruction) pair and select
  * (replaces EfficientEnsembleMerged.compute_max_similarity_scores_batch, efficient_ensemble_merged.py:309-454;
@@ -232,12 +252,45 @@ CVB_API int cvb_cover_step(cvb_handle* h, const float* image, const int64_t* lan
                            const float* past, int num_past, int n_future, float* actions, float* traj, float* scores,
                            float* group_mean, int32_t* best_idx, float* best_score, void* stream);
 
+/* cvb_cover_step for B independent observations in one graph (configs[4]): sampler batched as in cvb_pi0_sample_batch,
+ * one verifier context per observation (vf_images f32 [B, 3, vf_image, vf_image], vf_text_tokens i64 [B, vf_text_ctx])
+ * on the forked stream, the trajectory encoders over all B * N histories at once, one score / select group per
+ * observation.  past f32 [B, num_past, 7]; outputs actions [B*N, chunk, max_action_dim], traj [B*N, vf_history, 7],
+ * scores [B*N], group_mean [B*R], best_idx i32 [B] (index INSIDE the observation's N candidates), best_score [B]. */
+CVB_API int cvb_cover_step_batch(cvb_handle* h, int B, const float* images, const int64_t* lang_tokens,
+                                 const int32_t* lang_len, const float* states, const float* noise, int R, int K,
+                                 const float* vf_images, const int64_t* vf_text_tokens, const double* p01_host,
+                                 const double* p99_host, const float* past, int num_past, int n_future, float* actions,
+                                 float* traj, float* scores, float* group_mean, int32_t* best_idx, float* best_score,
+                                 void* stream);
+
 /* Test hook: inject normalised trunk features (patch f32 [Np, W], text f32 [ctx, W]) and recompute the
  * image-text heads, so the fp32 heads can be checked in isolation from the bf16 trunk. */
 CVB_API int cvb_verifier_set_features(cvb_handle* h, const float* patch, const float* text, void* stream);
 /* group-mean -> argmax group -> argmax inside the group over a (gathered) score vector (:417-447). */
 CVB_API int cvb_select(const float* scores, int R, int K, float* group_mean, int32_t* best_idx, float* best_score,
                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: fused score all-gather + selection over NVLink peer memory (BASELINE.json
+ * configs[3]: one observation, rephrases sharded over the ranks, one process per GPU).  Each rank owns a mailbox in its
+ * HBM; cvb_allgather_select is ONE kernel per rank that stores its slice into every peer's mailbox (peer-mapped
+ * st.global over NVLink), publishes an epoch flag, waits for the other ranks' flags and runs the selection - no NCCL
+ * call, no host round trip.  Setup (once): cvb_comm_create on every rank, exchange the cvb_comm_handle_bytes()-byte
+ * handles of cvb_comm_local_handle through any host channel (torch.distributed in cover_vla_b200/comm.py), then
+ * cvb_comm_open_peers with all `world` handles in rank order.
+ *   Shards are contiguous rephrase ranges: rank r owns R/world (+1 for r < R % world) rephrases, K candidates each.
+ *   local_scores f32 [n_loc]; local_actions f32 [n_loc, act_floats] or NULL; scores f32 [R*K]; actions f32
+ *   [R*K, act_floats] or NULL; group_mean f32 [R] or NULL; best_idx i32 [1]; best_score f32 [1] - identical on all ranks. */
+typedef struct cvb_comm cvb_comm;
+CVB_API int cvb_comm_create(int rank, int world, int max_slot_floats, cvb_comm** out);
+CVB_API int cvb_comm_handle_bytes(void);
+CVB_API int cvb_comm_local_handle(cvb_comm* comm, void* handle_out_host);
+CVB_API int cvb_comm_open_peers(cvb_comm* comm, const void* all_handles_host);
+CVB_API void cvb_comm_destroy(cvb_comm* comm);
+CVB_API int cvb_allgather_select(cvb_comm* comm, const float* local_scores, const float* local_actions, int act_floats,
+                                 int R, int K, float* scores, float* actions, float* group_mean, int32_t* best_idx,
+                                 float* best_score, void* stream);
 
 /* Test/diagnostic tap: copy an internal buffer ("image_emb", "prefix_k0", "prefix_vlast", "v0",
  * "time_emb", ...) to dst (device).  Returns the number of bytes copied or a negative error. */

@@ -15,7 +15,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, R, K, q):
+def _worker(rank, world, port, R, K, peer, q):
     import torch.distributed as dist
     from cover_vla_b200 import synthetic as S
     from cover_vla_b200.cover import CoverInputs, CoverStep, ShardedCoverStep
@@ -33,8 +33,11 @@ def _worker(rank, world, port, R, K, q):
                         lang_len=inp["lens"].to(torch.int32).to(dev), state=inp["state"][0].to(dev).contiguous(),
                         noise=inp["noise"].to(dev), vf_image=vin["image"][0].to(dev).contiguous(),
                         vf_tokens=vin["tokens"][0].to(dev), past=None, lang_len_max=int(inp["lens"].max()))
-        scores, actions, gmean, idx, score = ShardedCoverStep(eng, K)(x)
-        torch.cuda.synchronize()
+        sstep = ShardedCoverStep(eng, K, peer_memory=peer)
+        assert (sstep.peer is not None) == peer
+        for _ in range(4):  # several decisions: the mailbox epochs / parities advance, results must not
+            scores, actions, gmean, idx, score = sstep(x)
+            torch.cuda.synchronize()
         out = dict(rank=rank, scores=scores.cpu(), actions=actions.cpu(), idx=int(idx.item()), score=float(score.item()))
         if rank == 0:  # single-GPU answer for the whole candidate set
             a1, t1, s1, g1, i1, b1 = CoverStep(eng, K).sample_and_score(x)
@@ -47,14 +50,15 @@ def _worker(rank, world, port, R, K, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("R,K", [(4, 3), (3, 2)])
-def test_sharded_decision_equals_single_gpu(R, K):
+@pytest.mark.parametrize("R,K,peer", [(4, 3, True), (3, 2, True), (4, 3, False)])
+def test_sharded_decision_equals_single_gpu(R, K, peer):
+    """peer=True: cvb_allgather_select (peer-memory stores over NVLink + in-kernel selection); False: NCCL all-gathers."""
     import torch.multiprocessing as mp
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, R, K, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, R, K, peer, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda o: o["rank"])

@@ -87,11 +87,29 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------
-def algorithmic_flops(R: int, K: int) -> dict:
-    """De-duplicated algorithmic FLOPs per decision."""
+def algorithmic_flops(R: int, K: int, prefix_rows: int = 328) -> dict:
+    """De-duplicated algorithmic FLOPs per decision, counted on the rows the engine PROCESSES:
+    the prefix runs on `prefix_rows` = 256 image tokens + the valid language rows (right-padding is skipped, SURVEY.md
+    F11), not on all 328.  Linear layers scale with the rows, the attention (4 Tq Tk d per layer) with their square."""
     N = R * K
-    return {"vision": 220.2e9, "prefix": 1315.9e9 * R, "denoise": 33.6e9 * N, "verifier_trunk": 420.6e9,
+    att = lambda t: 4.0 * t * t * 2048 * 18
+    prefix = (1315.9e9 - att(328)) * prefix_rows / 328.0 + att(prefix_rows)
+    return {"vision": 220.2e9, "prefix": prefix * R, "denoise": 33.6e9 * N, "verifier_trunk": 420.6e9,
             "verifier_heads": 3.7e9 + 20.2e9 * N / 40}
+
+
+EXPERT_WEIGHT_BYTES = 311.4e6 * 2  # bf16 action-expert weights streamed once per denoise step (SURVEY.md section 8d)
+
+
+def ncu_traffic(name: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from THIS round's `ncu --set full` capture as
+    summarised in profiles/r2_ncu_traffic.json (written by tools/ncu_traffic.py from the .ncu-rep); None if absent."""
+    p = ROOT / "profiles" / "r2_ncu_traffic.json"
+    if not p.exists():
+        return None, None
+    d = json.loads(p.read_text())
+    e = d.get(name)
+    return (e.get("dram_bytes_per_launch"), "profiles/r2_ncu_traffic.json:" + name) if e else (None, None)
 
 
 def make_device_inputs(S, d, v, R, K, seed, device):
@@ -152,7 +170,6 @@ def run_gpu(args):
         R_loc = R_max = R
     eng = S.build_engine(d, w, v, vw, R_max, K, device=device,
                          use_cuda_graph=0 if os.environ.get("CVB_BENCH_EAGER") else 1)  # CVB_BENCH_EAGER=1: diagnostic only
-    del w, vw
     t_build = time.time() - t0
     # episode mode: every rank has its own observation; sharded mode: all ranks see the SAME observation
     host, x, lmax = make_device_inputs(S, d, v, R, K, seed=100 + (0 if sharded else rank), device=device)
@@ -229,6 +246,86 @@ def run_gpu(args):
     h2d = sum(t.numel() * t.element_size() for t in host.values())
     d2h = (2 + d.chunk_size * 7) * 4
 
+    # ---- throughput mode (BASELINE.json configs[4], per-GPU share): B independent configs[2] decisions per step through
+    # ONE cvb_cover_step_batch on a batch-capable handle - every weight is streamed once for all B * N candidates
+    batched = None
+    if not sharded and args.batch_obs > 1:
+        from cover_vla_b200.cover import BatchedCoverStep
+        Bo = args.batch_obs
+        engB = S.build_engine(d, w, v, vw, R, K, device=device, max_observations=Bo)
+        xsB = [make_device_inputs(S, d, v, R, K, seed=1000 + rank * Bo + b, device=device)[1] for b in range(Bo)]
+        xb = BatchedCoverStep.stack(xsB)
+        bstep = BatchedCoverStep(engB, K)
+        for _ in range(3):
+            bstep.sample_and_score(xb)
+        nb = max(3, args.steps // 4)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(nb):
+            outB = bstep.sample_and_score(xb)
+        e1.record()
+        barrier()
+        msB = e0.elapsed_time(e1) / nb
+        if world > 1:
+            t = torch.tensor([msB], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            msB = float(t.item())
+        batched = {"workload": "BASELINE.json configs[4] per-GPU share: %d independent configs[2] decisions per step in one "
+                               "cvb_cover_step_batch (sampler batched, one verifier context per observation)" % Bo,
+                   "observations_per_gpu_per_step": Bo, "steps": nb, "ms_per_step": round(msB, 3),
+                   "ms_per_decision": round(msB / Bo, 3), "value": round(world * Bo * N / (msB * 1e-3), 2), "unit": UNIT,
+                   "vs_single_decision_mode": round((world * Bo * N / (msB * 1e-3)) / value, 3)}
+        engB.close()
+        del engB, xsB, xb, outB
+        torch.cuda.empty_cache()
+
+    # ---- BASELINE.json configs[3] under the same clock (N > 1 only): ONE observation, 16 rephrases x 16 samples, sharded
+    # by rephrase over the ranks; the exchange is cvb_allgather_select (peer-memory stores over NVLink + in-kernel
+    # selection).  Every rank also runs the WHOLE decision alone and checks the sharded result against it.
+    sharded_info = None
+    if not sharded and world > 1 and world <= 16 and not args.no_sharded:
+        Rs, Ks = 16, 16
+        engS = S.build_engine(d, w, v, vw, Rs, Ks, device=device)
+        _, xS, _ = make_device_inputs(S, d, v, Rs, Ks, seed=777, device=device)  # the SAME observation on every rank
+        a1, t1, s1, g1, i1, b1 = [t.clone() for t in CoverStep(engS, Ks).sample_and_score(xS)]
+        res = {}
+        for name, peer in (("peer_memory", True), ("nccl", False)):
+            ss = ShardedCoverStep(engS, Ks, peer_memory=peer)
+            for _ in range(3):
+                so = ss(xS)
+            barrier()
+            ns = max(3, args.steps // 2)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(ns):
+                so = ss(xS)
+            e1.record()
+            barrier()
+            msS = e0.elapsed_time(e1) / ns
+            scores_s, actions_s, gmean_s, idx_s, score_s = so
+            ok_idx = int(idx_s.item()) == int(i1.item())
+            bit = bool(torch.equal(scores_s, s1)) and bool(torch.equal(actions_s, a1[:, :, :7]))
+            diff = float((scores_s - s1).abs().max().item())
+            t = torch.tensor([msS, -float(ok_idx), -float(bit), diff], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max time / worst agreement over the ranks
+            res[name] = {"ms_per_decision": round(float(t[0]), 3), "value": round(Rs * Ks / (float(t[0]) * 1e-3), 2),
+                         "index_equals_single_gpu_on_every_rank": bool(t[1] == -1.0),
+                         "scores_bit_identical_to_single_gpu": bool(t[2] == -1.0),
+                         "scores_max_abs_diff_vs_single_gpu": float(t[3])}
+            if ss.peer is not None:
+                ss.peer.close()
+        assert res["peer_memory"]["index_equals_single_gpu_on_every_rank"], "sharded decision disagrees with the 1-GPU decision"
+        sharded_info = {"workload": "BASELINE.json configs[3]: ONE observation, 16 rephrases x 16 samples = 256 candidates sharded "
+                                    "by rephrase over %d ranks, fused peer-memory all-gather + select" % world,
+                        "unit": UNIT, "candidates": Rs * Ks, **res["peer_memory"], "nccl_allgather_variant": res["nccl"],
+                        "note": "bit-identical when the per-rank row count takes the same kernel path as the 1-GPU pass "
+                                "(> 256 suffix rows: fused-epilogue GEMMs; <= 256: split-K), else equal within bf16 noise"}
+        engS.close()
+        del engS
+        torch.cuda.empty_cache()
+    del w, vw
+
     line = None
     if rank == 0:
         peaks, peak_src = _peaks()
@@ -248,12 +345,12 @@ def run_gpu(args):
         phases = {nm: ev_ms(lambda p=p: eng.pi0_run_phase(p, R_loc, K)) for p, nm in enumerate(["vision", "prefix", "denoise"])}
         phases["verifier_context"] = ev_ms(lambda: eng.verifier_context(x.vf_image, x.vf_tokens))
         phases["verifier_trajectories_select"] = ev_ms(lambda: eng.verifier_score(None, None, traj0, R_loc, K, recompute_context=False))
-        fl = algorithmic_flops(R, K)
+        lang_rows = min(d.max_lang_len, (lmax + 7) // 8 * 8)
+        fl = algorithmic_flops(R, K, d.n_img_tokens + lang_rows)
         total_flops = sum(fl.values())
 
         # dominant kernel: the prefix gate/up GeGLU GEMM (tcgen05), M = R*(256 + language rows), N = 2*16384 packed,
         # K = 2048.  Timed alone, cycling through 6 different weight matrices (6 x 134 MB >> 126 MB L2).
-        lang_rows = min(d.max_lang_len, (lmax + 7) // 8 * 8)
         M_, Kd, I_ = R_loc * (d.n_img_tokens + lang_rows), d.lm_width, d.lm_mlp
         a_ = torch.randn(M_, Kd, device=device, dtype=torch.bfloat16)
         ws = [(torch.randn(2 * I_, Kd, device=device) * 0.02).to(torch.bfloat16) for _ in range(6)]
@@ -275,11 +372,22 @@ def run_gpu(args):
         peak = float(peaks["bf16_tflops"])
         roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_2sm<EPI_GEGLU> (cta_group::2, 256x256 tiles; prefix gate/up, M=%d N=%d K=%d)" % (M_, 2 * I_, Kd),
                     "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-                    "traffic": NCU_TRAFFIC_BYTES, "algorithmic_bytes": int((M_ * Kd + 2 * I_ * Kd + M_ * I_) * 2),
+                    "traffic": ncu_traffic("prefix_gateup_gemm")[0], "traffic_source": ncu_traffic("prefix_gateup_gemm")[1],
+                    "algorithmic_bytes": int((M_ * Kd + 2 * I_ * Kd + M_ * I_) * 2),
                     "peak_source": peak_src + ", burst figure (kernel timed alone)",
                     "launch_ms": round(gemm_ms, 4), "launches_per_step": d.layers - 1,
-                    "step_frac_of_sustained_peak": round(total_flops / (ms_per_step * 1e-3) / 1e12 / float(peaks["bf16_tflops_sustained"]), 4)}
+                    "step_frac_of_sustained_peak": round(total_flops / (ms_per_step * 1e-3) / 1e12 / float(peaks["bf16_tflops_sustained"]) /
+                                                         (world if sharded else 1), 4)}
         del a_, ws, o_
+        # second roofline: the denoise loop is an HBM weight stream (the expert's 0.62 GB once per Euler step, M = 5 N rows)
+        n_steps = d.num_steps
+        den_gbs = EXPERT_WEIGHT_BYTES * n_steps / (phases["denoise"] * 1e-3) / 1e9
+        roofline_denoise = {"bound": "hbm", "kernel": "denoise loop (%d Euler steps x %d expert layers; split-K tcgen05 GEMMs + "
+                            "tcgen05 decode attention + RMSNorm-reduce)" % (n_steps, d.layers),
+                            "achieved": round(den_gbs, 1), "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
+                            "frac": round(den_gbs / float(peaks["hbm_gbs"]), 4), "traffic": None,
+                            "algorithmic_bytes": int(EXPERT_WEIGHT_BYTES * n_steps), "phase_ms": round(phases["denoise"], 3),
+                            "peak_source": peak_src + ", STREAM-style copy"}
 
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -309,6 +417,9 @@ def run_gpu(args):
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "roofline": roofline,
+            "roofline_denoise": roofline_denoise,
+            "batched": batched,
+            "sharded": sharded_info,
             "cpu_baseline": cpu,
             "build_s": round(t_build, 1),
         }
@@ -317,13 +428,6 @@ def run_gpu(args):
         dist.barrier()
         dist.destroy_process_group()
     return line
-
-
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel, from the committed
-# `ncu --set full` capture (profiles/r1e_gateup_gemm_ncu.txt: 143.5 MB read + 51.8 MB written per launch at M=2240,
-# the bench shape of tools/gateup_one.py; algorithmic bytes at that M are 217 MB - part of the bf16 output is still
-# in L2 when the launch ends)
-NCU_TRAFFIC_BYTES = 195.3e6
 
 
 def sstep_inputs(x, K, world, rank):
@@ -374,7 +478,7 @@ def cpu_decision(R: int, K: int, seed: int):
     return time.perf_counter() - t0, idx
 
 
-CPU_SAMPLE_R, CPU_SAMPLE_K = 4, 5  # bounded sample: 20 of the 40 candidates, reference batch layout (B = 20)
+CPU_SAMPLE_R, CPU_SAMPLE_K = 8, 5  # one whole configs[2] decision: 40 candidates in the reference's batch layout (B = 40)
 
 
 def cpu_baseline_sample():
@@ -383,9 +487,9 @@ def cpu_baseline_sample():
     cpu_decision(1, 1, seed=1)  # warm-up (thread pools, allocator)
     t, _ = cpu_decision(R, K, seed=2)
     return {"value": round(R * K / t, 4), "unit": UNIT, "cores": st["cores"], "kind": "port",
-            "sample": "full-size models, one decision over %d of the 40 candidates (R=%d, K=%d) in the reference's batch "
-                      "layout incl. verifier; oracle port (bit-exact vs the reference files in the authoring container); "
-                      "%.1f s of CPU work" % (R * K, R, K, t)}
+            "sample": "full-size models, ONE configs[2] decision: all %d candidates (R=%d, K=%d) in the reference's batch "
+                      "layout (no de-duplication) incl. verifier; oracle port (bit-exact vs the reference files in the "
+                      "authoring container); %.1f s of CPU work" % (R * K, R, K, t)}
 
 
 def run_reference(args):
@@ -395,11 +499,11 @@ def run_reference(args):
         return
     st = _cpu_setup()
     R, K = CPU_SAMPLE_R, CPU_SAMPLE_K
-    # bounded sample: each step = one decision over R*K = 20 candidates (B = 20 in the reference's batch layout)
+    # each step = one whole configs[2] decision: R*K = 40 candidates (B = 40 in the reference's batch layout), ~13 s
     for i in range(max(1, min(args.warmup, 1))):
         cpu_decision(R, K, seed=10 + i)
     times = []
-    budget = 240.0
+    budget = 900.0  # the driver allows 1800 s for this arm
     t_start = time.perf_counter()
     for i in range(args.steps):
         t, _ = cpu_decision(R, K, seed=20 + i)
@@ -408,14 +512,16 @@ def run_reference(args):
             break
     ms = 1e3 * sum(times) / len(times)
     value = R * K / (ms / 1e3)
-    sample = ("each step = one full-size CoVer decision over %d of the 40 candidates (R=%d, K=%d, reference batch layout, "
+    sample = ("each step = one full-size configs[2] decision over all %d candidates (R=%d, K=%d, reference batch layout, "
               "no de-duplication, incl. verifier trunk + heads + selection) on %d host threads; %d of %d steps run inside "
               "the %.0f s budget" % (R * K, R, K, st["cores"], len(times), args.steps, budget))
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world,
             "steps": len(times), "warmup": args.warmup, "ms_per_step": round(ms, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "BASELINE.json configs[2] (bounded sample): full CoVer step on the host CPU",
-                       "rephrases": R, "samples_per_rephrase": K},
+            "config": {"workload": "BASELINE.json configs[2]: full CoVer step, pi0 %d rephrases x %d samples (%d candidates) "
+                                   "+ 3-member verifier argmax, simpler_widowx shapes, full-size random-init models, on the "
+                                   "host CPU" % (R, K, R * K),
+                       "rephrases": R, "samples_per_rephrase": K, "candidates_per_step": R * K},
             "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": st["cores"], "kind": "port", "sample": sample},
             "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -431,6 +537,9 @@ def main():
     ap.add_argument("--rephrases", type=int, default=R_DEFAULT)
     ap.add_argument("--samples", type=int, default=K_DEFAULT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch-obs", type=int, default=8, help="observations per step of the throughput-mode sub-measurement "
+                                                             "(configs[4] per-GPU share); 0 / 1 disables it")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the configs[3] sub-measurement under torchrun")
     ap.add_argument("--mode", default="episode", choices=["episode", "sharded"],
                     help="episode: every rank decides its own observation (weak scaling, BASELINE configs[2]/[4]); "
                          "sharded: ONE observation, rephrases sharded over the ranks + NCCL score all-gather "

@@ -409,6 +409,8 @@ bool attention_decode_umma_eligible(const AttnCall& c);
 int attention_decode_umma(cudaStream_t st, const AttnCall& c);
 bool attention_mha_umma_eligible(const AttnCall& c);
 int attention_mha_umma(cudaStream_t st, const AttnCall& c);
+bool attention_mha_long_umma_eligible(const AttnCall& c);
+int attention_mha_long_umma(cudaStream_t st, const AttnCall& c);
 
 int attention(cudaStream_t st, const AttnCall& c) {
   CVB_REQUIRE(c.head_dim % 8 == 0 && c.head_dim <= 256, "head_dim must be a multiple of 8, <= 256");
@@ -418,6 +420,7 @@ int attention(cudaStream_t st, const AttnCall& c) {
   // tcgen05 kernel first (measured 2-3x faster than the mma.sync cluster kernel at the denoise shape)
   if ((c.algo == 0 || c.algo == 3) && attention_decode_umma_eligible(c)) return attention_decode_umma(st, c);
   if ((c.algo == 0 || c.algo == 3) && c.k1 == nullptr && attention_mha_umma_eligible(c)) return attention_mha_umma(st, c);
+  if ((c.algo == 0 || c.algo == 3) && c.k1 == nullptr && attention_mha_long_umma_eligible(c)) return attention_mha_long_umma(st, c);
   CVB_REQUIRE(c.algo != 3 && c.q_part == nullptr, "shape not eligible for a tcgen05 attention kernel");
   if (c.k1 != nullptr && c.algo != 1 && attention_decode_eligible(c)) return attention_decode(st, c, c.rope);
   if (c.k1 != nullptr && c.algo != 2 && attention_group_eligible(c)) return attention_group(st, c);

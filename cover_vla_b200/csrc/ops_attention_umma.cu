@@ -1009,6 +1009,252 @@ attn_mha_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Multi-head self-attention for LONGER sequences on tcgen05: the verifier's SigLIP2 ViT-L/16-384 trunk (576 tokens, 16
+// heads x head_dim 64; timm Attention reached through VLA_SigLIP2_Bridge.extract_features,
+// finetune_trajectory_bridge_ddp.py:297-355).  A 128 x 576 fp32 logit tile does not fit TMEM (512 columns), and the
+// ledger normalises the probabilities BEFORE rounding them to bf16, so the kernel is exact two-pass over key chunks of
+// 192:
+//   pass 1:  S_c = Q K_c^T (double-buffered in TMEM) -> running (max, sum) per row;
+//   pass 2:  S_c again (4 UMMAs per chunk at head_dim 64 - cheaper than keeping 576 columns), P_c = 2^((S_c - M) c2) / L
+//            -> bf16 -> swizzled A tile, O += P_c V_c with O (head_dim columns) resident in TMEM.
+// K for all keys stays in shared memory (one TMA pass), V^T is built by the softmax warps while pass 1 runs.
+// Replaces attn_smem_kernel<64> (mma.sync, 54 us per launch at this shape) on the verifier trunk.
+constexpr int UL_CH = 192;  // keys per chunk
+
+struct UmmaLongParams {
+  const bf16* v;
+  long v_bs, v_rs;
+  const int* klen_dev;
+  int klen;
+  int tq, tk_pad, hd, hdp, nc;  // nc = chunks
+  long q_rows_per_batch, k_rows_per_batch;
+  bf16* out;
+  long o_bs, o_rs;
+  float scale;
+};
+
+__host__ __device__ inline int ul_smem_bytes(int tk_pad, int hd, int hdp) {
+  const int nb = (hd + 63) / 64, nc = (tk_pad + UL_CH - 1) / UL_CH, nkb = tk_pad / 64;
+  return nb * UA_QBLK + nb * nc * UL_CH * 128 + 3 * UA_PBLK + nkb * hdp * 128;
+}
+
+__global__ void __launch_bounds__(UM_THREADS, 1)
+attn_mha_long_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                          const UmmaLongParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int tk_pad = p.tk_pad, hd = p.hd, hdp = p.hdp, nc = p.nc;
+  const int nb = (hd + 63) / 64;   // hd-blocks of Q / K
+  const int nkb = tk_pad / 64;     // key-blocks of V^T
+  const uint32_t kblk = static_cast<uint32_t>(nc) * UL_CH * 128u;  // one hd-block of K: all chunks
+  const uint32_t vblk = static_cast<uint32_t>(hdp) * 128u;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + nb * UA_QBLK;
+  uint8_t* sP = sK + nb * kblk;
+  uint8_t* sV = sP + 3 * UA_PBLK;
+  uint64_t* qk_full = reinterpret_cast<uint64_t*>(sV + nkb * vblk);  // [2]
+  uint64_t* s_full = qk_full + 2;   // [2]
+  uint64_t* s_free = s_full + 2;    // [2]
+  uint64_t* p_ready = s_free + 2;
+  uint64_t* p_free = p_ready + 1;
+  uint64_t* o_full = p_free + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  float2* red2 = reinterpret_cast<float2*>(o_full + 3);  // [2][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  constexpr uint32_t O_COL = 2 * UL_CH;  // O accumulator behind the two S buffers
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&qk_full[i], 1);
+        mbar_init(&s_full[i], 1);
+        mbar_init(&s_free[i], UM_SOFT);
+      }
+      mbar_init(p_ready, UM_SOFT);
+      mbar_init(p_free, 1);
+      mbar_init(o_full, 1);
+      fence_barrier_init();
+      fence_proxy_async();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      pdl_wait();
+      const int q_row0 = static_cast<int>(b * p.q_rows_per_batch) + tile * 128;
+      const int k_row0 = static_cast<int>(b * p.k_rows_per_batch);
+      for (int c = 0; c < nb; ++c) {
+        mbar_arrive_expect_tx(&qk_full[c], UA_QBLK + kblk);
+        tma_load_3d(sQ + c * UA_QBLK, &tmQ, &qk_full[c], c * 64, head, q_row0);
+        for (int ch = 0; ch < nc; ++ch)  // box = UL_CH rows; rows past the tensor are zero-filled
+          tma_load_3d(sK + c * kblk + static_cast<uint32_t>(ch) * UL_CH * 128u, &tmK, &qk_full[c], c * 64, head, k_row0 + ch * UL_CH);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int c = 0; c < nb; ++c) {
+        mbar_wait(&qk_full[c], 0);
+        tc_fence_after();
+      }
+      const uint32_t idesc_o = make_idesc_n(hdp);
+      for (int j = 0; j < 2 * nc; ++j) {  // production j: chunk j % nc, pass j / nc, S buffer j & 1
+        const int ch = j % nc, buf = j & 1, use = j >> 1;
+        const int n_ch = min(UL_CH, tk_pad - ch * UL_CH);
+        mbar_wait(&s_free[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t idesc_s = make_idesc_n(n_ch);
+        for (int c = 0; c < nb; ++c) {
+          const uint64_t qd = make_desc_kmajor_sw128(smem_u32(sQ + c * UA_QBLK));
+          const uint64_t kd = make_desc_kmajor_sw128(smem_u32(sK + c * kblk + static_cast<uint32_t>(ch) * UL_CH * 128u));
+          const int ksteps = min(4, (hd - c * 64 + 15) / 16);
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(tmem_base + buf * UL_CH, qd + 2 * k, kd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[buf]);
+        if (j >= nc) {  // pass 2: O += P_ch V_ch once the softmax warps have written P_ch
+          mbar_wait(p_ready, ch & 1);
+          tc_fence_after();
+          const int kbs = n_ch / 64;
+          for (int kb = 0; kb < kbs; ++kb) {
+            const uint64_t pd = make_desc_kmajor_sw128(smem_u32(sP + kb * UA_PBLK));
+            const uint64_t vd = make_desc_kmajor_sw128(smem_u32(sV + (ch * 3 + kb) * vblk));
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + O_COL, pd + 2 * k, vd + 2 * k, idesc_o, (ch | kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(p_free);
+          if (ch == nc - 1) umma_commit(o_full);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int sid = threadIdx.x - 64;
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    pdl_wait();
+    int n_keys = p.klen_dev != nullptr ? p.klen_dev[b] : p.klen;
+    n_keys = max(1, min(n_keys, tk_pad));
+    // ---- V^T[d][key] tiles (K-major, 128-byte swizzle) from V[key][d]: one key per thread
+    for (int key = sid; key < tk_pad; key += UM_SOFT) {
+      const bf16* vp = p.v + b * p.v_bs + static_cast<long>(key) * p.v_rs + head * hd;
+      const uint32_t col = smem_u32(sV) + static_cast<uint32_t>(key >> 6) * vblk + static_cast<uint32_t>(key & 7) * 2u;
+      const int chunk = (key & 63) >> 3;
+      for (int d0 = 0; d0 < hdp; d0 += 8) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (key < n_keys && d0 < hd) v = *reinterpret_cast<const uint4*>(vp + d0);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int d = d0 + e;
+          const uint16_t val = static_cast<uint16_t>(e & 1 ? u[e >> 1] >> 16 : u[e >> 1] & 0xffffu);
+          const uint32_t addr = col + static_cast<uint32_t>(d >> 3) * 1024u + static_cast<uint32_t>(e) * 128u +
+                                (static_cast<uint32_t>(chunk ^ e) << 4);
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(val) : "memory");
+        }
+      }
+    }
+    const float c2 = p.scale * 1.4426950408889634f;
+    // ---- pass 1: exact row statistics over all keys
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < nc; ++j) {
+      const int buf = j & 1, use = j >> 1;
+      const int nv_c = max(0, min(UL_CH, n_keys - j * UL_CH));
+      mbar_wait(&s_full[buf], use & 1);
+      tc_fence_after();
+      for (int ch = half; ch * 16 < nv_c; ch += 2) {
+        uint32_t rr[16];
+        tmem_ld_x16(taddr + buf * UL_CH + ch * 16, rr);
+        tmem_wait_ld();
+        online_chunk(rr, min(16, nv_c - ch * 16), c2, m, l);
+      }
+      tc_fence_before();
+      mbar_arrive(&s_free[buf]);
+    }
+    red2[half * 128 + row] = make_float2(m, l);
+    named_bar(1, UM_SOFT);
+    const float2 s0 = red2[row], s1 = red2[128 + row];
+    const float M = fmaxf(s0.x, s1.x);
+    const float Mc = M * c2;
+    const float inv = 1.0f / (s0.y * ex2_approx((s0.x - M) * c2) + s1.y * ex2_approx((s1.x - M) * c2));
+    const uint32_t p_row = smem_u32(sP) + static_cast<uint32_t>(row >> 3) * 1024u + static_cast<uint32_t>(row & 7) * 128u;
+    // ---- pass 2: probabilities of chunk c -> bf16 -> the A tile of O += P_c V_c
+    for (int c = 0; c < nc; ++c) {
+      const int j = nc + c, buf = j & 1, use = j >> 1;
+      const int n_ch = min(UL_CH, tk_pad - c * UL_CH);
+      const int nv_c = max(0, min(UL_CH, n_keys - c * UL_CH));
+      mbar_wait(&s_full[buf], use & 1);
+      tc_fence_after();
+      if (c > 0) mbar_wait(p_free, (c - 1) & 1);  // the P.V MMAs of the previous chunk have read sP
+      for (int ch = half; ch * 16 < n_ch; ch += 2) {
+        const int nv = max(0, min(16, nv_c - ch * 16));
+        uint32_t pk[8];
+        if (nv > 0) {
+          uint32_t rr[16];
+          tmem_ld_x16(taddr + buf * UL_CH + ch * 16, rr);
+          tmem_wait_ld();
+          prob_chunk(rr, nv, c2, Mc, inv, pk);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[i] = 0u;
+        }
+        const int c0 = ch * 16;
+        const uint32_t blk = p_row + static_cast<uint32_t>(c0 >> 6) * UA_PBLK;
+        const int chunk = (c0 & 63) >> 3;
+        sts_u4(blk + (static_cast<uint32_t>(chunk ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+        sts_u4(blk + (static_cast<uint32_t>((chunk + 1) ^ (row & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&s_free[buf]);
+      mbar_arrive(p_ready);
+    }
+    // ---- epilogue
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int t = tile * 128 + row;
+    bf16* op = p.out + b * p.o_bs + static_cast<long>(t) * p.o_rs + head * hd;
+    for (int ch = half; ch * 16 < hdp; ch += 2) {
+      uint32_t rr[16];
+      tmem_ld_x16(taddr + O_COL + ch * 16, rr);
+      tmem_wait_ld();
+      if (t < p.tq) {
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          if (ch * 16 + jj * 8 < hd)
+            *reinterpret_cast<uint4*>(op + ch * 16 + jj * 8) =
+                make_uint4(pack_bf16x2(__uint_as_float(rr[8 * jj]), __uint_as_float(rr[8 * jj + 1])),
+                           pack_bf16x2(__uint_as_float(rr[8 * jj + 2]), __uint_as_float(rr[8 * jj + 3])),
+                           pack_bf16x2(__uint_as_float(rr[8 * jj + 4]), __uint_as_float(rr[8 * jj + 5])),
+                           pack_bf16x2(__uint_as_float(rr[8 * jj + 6]), __uint_as_float(rr[8 * jj + 7])));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 struct Q3Key {
   const void* ptr;
   uint64_t rows, ld, heads, hd;
@@ -1164,6 +1410,45 @@ int attention_mha_umma(cudaStream_t st, const AttnCall& c) {
   CVB_TRY(ensure_dyn_smem(attn_mha_umma_kernel, smem));
   dim3 grid((c.tq + 127) / 128, c.heads, c.batches);
   CVB_TRY(launch_pdl(attn_mha_umma_kernel, grid, dim3(UM_THREADS), smem, st, 1, tmQ, tmK, p));
+  CVB_LAUNCHED();
+  return 0;
+}
+
+// ---- longer multi-head self-attention (257 .. 768 keys, head_dim <= 128 as far as shared memory allows): verifier ViT-L
+bool attention_mha_long_umma_eligible(const AttnCall& c) {
+  if (c.k1 != nullptr || c.rope != nullptr || c.force_two_pass || c.heads != c.kv_heads) return false;
+  if (c.head_dim % 8 != 0 || c.head_dim > 128 || c.head_dim < 16) return false;
+  const int kmax = c.kv0_len_dev != nullptr ? c.kv0_max : c.kv0_len;
+  if (kmax <= 256 || kmax > 768) return false;
+  if (c.q_row_stride % 8 != 0 || c.kv0_row_stride % 8 != 0 || c.o_row_stride % 8 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(c.q) | reinterpret_cast<uintptr_t>(c.k0) | reinterpret_cast<uintptr_t>(c.v0) |
+       reinterpret_cast<uintptr_t>(c.out)) & 15) return false;
+  if (c.batches > 1 && (c.q_batch_stride % c.q_row_stride != 0 || c.kv0_batch_stride % c.kv0_row_stride != 0 ||
+                        c.q_per_kv_batch != 1)) return false;
+  const int tk_pad = (kmax + 63) / 64 * 64, hdp = (c.head_dim + 15) / 16 * 16;
+  return 2 * UL_CH + hdp <= 512 && ul_smem_bytes(tk_pad, c.head_dim, hdp) <= UA_BODY_MAX;
+}
+
+int attention_mha_long_umma(cudaStream_t st, const AttnCall& c) {
+  CVB_REQUIRE(attention_mha_long_umma_eligible(c), "shape not eligible for the long tcgen05 multi-head attention");
+  const int kmax = c.kv0_len_dev != nullptr ? c.kv0_max : c.kv0_len;
+  const int tk_pad = (kmax + 63) / 64 * 64, hd = c.head_dim, hdp = (hd + 15) / 16 * 16;
+  const long q_rpb = c.batches > 1 ? c.q_batch_stride / c.q_row_stride : 0;
+  const long k_rpb = c.batches > 1 ? c.kv0_batch_stride / c.kv0_row_stride : 0;
+  CUtensorMap tmQ, tmK;
+  CVB_TRY(get_tmap3_cached(c.q, static_cast<uint64_t>(q_rpb) * (c.batches - 1) + c.tq, c.heads, hd, c.q_row_stride, 128, 1, &tmQ));
+  CVB_TRY(get_tmap3_cached(c.k0, static_cast<uint64_t>(k_rpb) * (c.batches - 1) + kmax, c.heads, hd, c.kv0_row_stride, UL_CH, 1,
+                           &tmK));
+  UmmaLongParams p;
+  p.v = c.v0, p.v_bs = c.kv0_batch_stride, p.v_rs = c.kv0_row_stride;
+  p.klen_dev = c.kv0_len_dev, p.klen = c.kv0_len, p.tq = c.tq, p.tk_pad = tk_pad, p.hd = hd, p.hdp = hdp;
+  p.nc = (tk_pad + UL_CH - 1) / UL_CH;
+  p.q_rows_per_batch = q_rpb, p.k_rows_per_batch = k_rpb;
+  p.out = c.out, p.o_bs = c.o_batch_stride, p.o_rs = c.o_row_stride, p.scale = c.scale;
+  const int smem = 1024 + ul_smem_bytes(tk_pad, hd, hdp) + 12 * 8 + 2 * 128 * 8 + 64;
+  CVB_TRY(ensure_dyn_smem(attn_mha_long_umma_kernel, smem));
+  dim3 grid((c.tq + 127) / 128, c.heads, c.batches);
+  CVB_TRY(launch_pdl(attn_mha_long_umma_kernel, grid, dim3(UM_THREADS), smem, st, 1, tmQ, tmK, p));
   CVB_LAUNCHED();
   return 0;
 }

@@ -195,3 +195,27 @@ def test_denoise_attention_tcgen05(R, K, S, P, heads, lens, use_rope):
     if S * heads <= 64 and use_rope:  # the cluster mma.sync kernel it replaces (same ledger)
         old = ops.attention(q, k0, v0, **{**kw, "algo": 2, "vt0": None})
         assert (out.float() - old.float()).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("B,T,heads,hd,full", [(1, 576, 16, 64, True), (2, 576, 16, 64, False), (1, 300, 4, 64, False),
+                                               (1, 512, 2, 64, False), (3, 257, 2, 32, False), (1, 768, 3, 32, True)])
+def test_long_multihead_attention_tcgen05(B, T, heads, hd, full):
+    """attn_mha_long_umma_kernel (verifier ViT-L/16-384: 576 tokens x 16 heads x 64): exact two-pass softmax over key
+    chunks of 192 with S double-buffered and O resident in TMEM; q / k / v are strided views of a fused qkv buffer as in
+    the trunk; algo=3 fails unless a tcgen05 kernel takes the shape."""
+    from cover_vla_b200 import ops
+    torch.manual_seed(T * 7 + heads)
+    W = heads * hd
+    qkv = torch.randn(B, T, 3 * W, device="cuda").to(torch.bfloat16)
+    q, k, v = qkv[:, :, :W], qkv[:, :, W:2 * W], qkv[:, :, 2 * W:]
+    lens = (torch.full((B,), T, device="cuda", dtype=torch.int32) if full else
+            torch.randint(T // 2, T + 1, (B,), device="cuda", dtype=torch.int32))
+    out = ops.attention(q, k, v, heads=heads, kv_heads=heads, head_dim=hd, kv0_len_dev=lens, algo=3)
+    mask = (torch.arange(T, device="cuda")[None, :] < lens[:, None])[:, None, :].expand(B, T, T)
+    ref = _ref(q.contiguous(), k.contiguous(), v.contiguous(), heads, heads, hd, mask)
+    err = (out.float() - ref).abs().max().item()
+    rel = ((out.float() - ref).norm() / ref.norm()).item()
+    assert err < 2e-2 and rel < 5e-3, (err, rel)
+    # same ledger as the mma.sync kernel it replaces
+    old = ops.attention(q, k, v, heads=heads, kv_heads=heads, head_dim=hd, kv0_len_dev=lens, force_two_pass=True)
+    assert ((out.float() - old.float()).norm() / ref.norm()).item() < 5e-3

@@ -13,7 +13,7 @@ vin = S.make_verifier_inputs(v, 1, seed=3)
 x = CoverInputs(image=inp["image"][0].cuda().contiguous(), lang_tokens=inp["tokens"].cuda(),
                 lang_len=inp["lens"].to(torch.int32).cuda(), state=inp["state"][0].cuda().contiguous(),
                 noise=inp["noise"].cuda(), vf_image=vin["image"][0].cuda().contiguous(),
-                vf_tokens=vin["tokens"][0].cuda(), past=None)
+                vf_tokens=vin["tokens"][0].cuda(), past=None, lang_len_max=int(inp["lens"].max()))
 step = CoverStep(eng, K)
 for _ in range(2):
     step.sample_and_score(x)

@@ -120,6 +120,11 @@ int cvb_preprocess_policy_image(const uint8_t* img_u8_hwc, int H, int W, int out
   return cvb::preprocess_policy_image((cudaStream_t)stream, img_u8_hwc, H, W, out_h, out_w, out_u8_hwc, out_f32_chw);
 }
 
+int cvb_resize_bilinear_antialias_u8(const uint8_t* img_u8_hwc, int H, int W, int out_h, int out_w, float* scratch_f32,
+                                     uint8_t* out_u8_hwc, void* stream) {
+  return cvb::resize_bilinear_antialias_u8((cudaStream_t)stream, img_u8_hwc, H, W, out_h, out_w, scratch_f32, out_u8_hwc);
+}
+
 int cvb_preprocess_verifier_image(const uint8_t* img_u8_hwc, int H, int W, int out_h, int out_w, uint8_t* out_u8_hwc,
                                   float* out_f32_chw, void* stream) {
   return cvb::preprocess_verifier_image((cudaStream_t)stream, img_u8_hwc, H, W, out_h, out_w, out_u8_hwc, out_f32_chw);

@@ -99,6 +99,11 @@ int preprocess_policy_image(cudaStream_t st, const uint8_t* img_hwc, int H, int 
 int preprocess_verifier_image(cudaStream_t st, const uint8_t* img_hwc, int H, int W, int dh, int dw, uint8_t* out_u8_hwc,
                               float* out_f32_chw);
 
+// tf.image.resize(frame_u8, (dh, dw), BILINEAR, antialias=True) -> uint8 (truncating cast): process_raw_image_to_jpg,
+// eval_utils.py:228-286.  scratch_f32: dh * W * 3 floats (the row pass's intermediate).
+int resize_bilinear_antialias_u8(cudaStream_t st, const uint8_t* img_hwc, int H, int W, int dh, int dw, float* scratch_f32,
+                                 uint8_t* out_u8_hwc);
+
 // ---- attention (attention.cuh) -----------------------------------------------------------------
 struct AttnCall {
   // Q rows for batch b, head h, token t:  q + (b*q_batch_stride + t*q_row_stride + h*head_dim)

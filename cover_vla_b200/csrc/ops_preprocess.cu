@@ -9,7 +9,9 @@
 // tables depend only on the sizes: they are computed on the host exactly as OpenCV does (same libm) and cached on the
 // device; the kernel evaluates the 8 x 8 taps of one output pixel per thread (all three channels).  Bit-exact against
 // cv2.resize (tests/test_preprocess.py).
+#include <algorithm>
 #include <cmath>
+#include <limits>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -292,6 +294,144 @@ int preprocess_verifier_image(cudaStream_t st, const uint8_t* img_hwc, int H, in
   const int n = dh * dw;
   CVB_TRY(launch_pdl(pil_bicubic_image_kernel, dim3((n + 127) / 128), dim3(128), 0, st, 1, img_hwc, H, W, dh, dw, t.xb, t.xk,
                      t.xks, t.yb, t.yk, t.yks, out_u8_hwc, out_f32_chw));
+  CVB_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Verifier-side frame reduction on the device: process_raw_image_to_jpg (CoVer_VLA/inference/experiments/robot/simpler/
+// eval_utils.py:228-286) = tf.image.resize(frame_u8, (256, 256), BILINEAR, antialias=True) -> tf.cast(uint8).
+// TensorFlow is a third-party dependency absent from /root/reference and from this image ("tensorflow" unpinned in
+// CoVer_VLA/inference/pyproject.toml), so its published algorithm is restated (tensorflow/core/kernels/image/
+// scale_and_translate_op.cc: ComputeSpansCore with the triangle kernel, then GatherRows, then GatherColumns):
+//   scale = float(out) / float(in); inv_scale = 1 / scale; kernel_scale = max(inv_scale, 1)      (antialias)
+//   sample = (x + 0.5) * inv_scale;  span = [ceil(sample - kernel_scale - 0.5), floor(sample + kernel_scale - 0.5)]
+//   clamped to the image; w(src) = max(0, 1 - |src + 0.5 - sample| / kernel_scale), normalised by their float32 sum;
+//   rows first into a float32 intermediate [out_h, W, 3], then columns; sequential float32 multiply-adds in source
+//   order WITHOUT contraction; the cast to uint8 truncates.
+// Parity: bit-exact against oracle/preprocess_oracle.tf_resize_bilinear_antialias_u8 (the same restatement in numpy
+// float32); UNPINNED against TensorFlow itself (no TensorFlow here) - see DESIGN.md section 4.
+namespace {
+
+struct TfTables {
+  int* starts = nullptr;   // [out]
+  float* weights = nullptr;  // [out][span]
+  int span = 0;
+};
+std::map<std::tuple<int, int, int>, TfTables> g_tf_tables;  // (device, in, out)
+
+void tf_spans(int in_size, int out_size, std::vector<int>* starts, std::vector<float>* weights, int* span_out) {
+  const float scale = static_cast<float>(out_size) / static_cast<float>(in_size);
+  const float inv_scale = 1.0f / scale;
+  const float kernel_scale = std::max(inv_scale, 1.0f);
+  const float radius = 1.0f;  // triangle kernel
+  const int span = std::min(2 * static_cast<int>(std::ceil(radius * kernel_scale)) + 1, in_size);
+  starts->assign(out_size, 0);
+  weights->assign(static_cast<size_t>(out_size) * span, 0.0f);
+  for (int x = 0; x < out_size; ++x) {
+    const float col_f = x + 0.5f;
+    const float sample_f = col_f * inv_scale;
+    if (sample_f < 0 || sample_f > in_size) continue;
+    long span_start = static_cast<long>(std::ceil(sample_f - radius * kernel_scale - 0.5f));
+    long span_end = static_cast<long>(std::floor(sample_f + radius * kernel_scale - 0.5f));
+    span_start = std::min<long>(std::max<long>(span_start, 0), in_size - 1);
+    span_end = std::min<long>(std::max<long>(span_end, 0), in_size - 1) + 1;
+    const int n = static_cast<int>(span_end - span_start);
+    float total = 0.0f;
+    std::vector<float> tmp(n);
+    for (int i = 0; i < n; ++i) {
+      const float kernel_pos = static_cast<float>(span_start + i) + 0.5f - sample_f;
+      const float v = std::fabs(kernel_pos / kernel_scale);
+      const float wgt = std::max(0.0f, 1.0f - v);
+      total += wgt;
+      tmp[i] = wgt;
+    }
+    (*starts)[x] = static_cast<int>(span_start);
+    if (std::fabs(total) >= 1000.0f * std::numeric_limits<float>::min()) {
+      const float one_over = 1.0f / total;
+      for (int i = 0; i < n && i < span; ++i) (*weights)[static_cast<size_t>(x) * span + i] = tmp[i] * one_over;
+    }
+  }
+  *span_out = span;
+}
+
+// rows: inter[y][x][c] = sum_i float(img[ys + i][x][c]) * wy[y][i]   (sequential, no contraction)
+__global__ void __launch_bounds__(256) tf_gather_rows_kernel(const uint8_t* __restrict__ img, int H, int W, int dh,
+                                                             const int* __restrict__ ystart, const float* __restrict__ wy,
+                                                             int span, float* __restrict__ inter) {
+  pdl_wait();
+  pdl_launch();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over dh * W * 3
+  if (i >= dh * W * 3) return;
+  const int y = i / (W * 3), rem = i % (W * 3);
+  const int ys = ystart[y];
+  float acc = 0.0f;
+  for (int k = 0; k < span; ++k) {
+    const int sy = ys + k;
+    if (sy >= H) break;
+    const float w = wy[y * span + k];
+    acc = __fadd_rn(acc, __fmul_rn(static_cast<float>(img[static_cast<long>(sy) * W * 3 + rem]), w));
+  }
+  inter[i] = acc;
+}
+// columns: out[y][x][c] = uint8(trunc(sum_i inter[y][xs + i][c] * wx[x][i]))
+__global__ void __launch_bounds__(256) tf_gather_cols_kernel(const float* __restrict__ inter, int W, int dh, int dw,
+                                                             const int* __restrict__ xstart, const float* __restrict__ wx,
+                                                             int span, uint8_t* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over dh * dw * 3
+  if (i >= dh * dw * 3) return;
+  const int c = i % 3, x = (i / 3) % dw, y = i / (3 * dw);
+  const int xs = xstart[x];
+  float acc = 0.0f;
+  for (int k = 0; k < span; ++k) {
+    const int sx = xs + k;
+    if (sx >= W) break;
+    acc = __fadd_rn(acc, __fmul_rn(inter[(static_cast<long>(y) * W + sx) * 3 + c], wx[x * span + k]));
+  }
+  // tf.cast(float32 -> uint8): truncation toward zero (values are in [0, 255] up to rounding)
+  out[i] = static_cast<uint8_t>(static_cast<int>(fminf(fmaxf(acc, 0.0f), 255.0f)));
+}
+
+int tf_get_tables(int dev, int in_size, int out_size, TfTables* t) {
+  auto key = std::make_tuple(dev, in_size, out_size);
+  auto it = g_tf_tables.find(key);
+  if (it != g_tf_tables.end()) {
+    *t = it->second;
+    return 0;
+  }
+  std::vector<int> st;
+  std::vector<float> w;
+  tf_spans(in_size, out_size, &st, &w, &t->span);
+  CVB_CUDA(cudaMalloc(&t->starts, st.size() * sizeof(int)));
+  CVB_CUDA(cudaMalloc(&t->weights, w.size() * sizeof(float)));
+  CVB_CUDA(cudaMemcpy(t->starts, st.data(), st.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CVB_CUDA(cudaMemcpy(t->weights, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+  g_tf_tables.emplace(key, *t);
+  return 0;
+}
+
+}  // namespace
+
+int resize_bilinear_antialias_u8(cudaStream_t st, const uint8_t* img_hwc, int H, int W, int dh, int dw, float* scratch_f32,
+                                 uint8_t* out_u8_hwc) {
+  CVB_REQUIRE(img_hwc != nullptr && out_u8_hwc != nullptr && scratch_f32 != nullptr, "null argument");
+  CVB_REQUIRE(H >= 1 && W >= 1 && dh >= 1 && dw >= 1 && H <= 16384 && W <= 16384, "image sizes out of range");
+  int dev = 0;
+  CVB_CUDA(cudaGetDevice(&dev));
+  TfTables ty, tx;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    CVB_TRY(tf_get_tables(dev, H, dh, &ty));
+    CVB_TRY(tf_get_tables(dev, W, dw, &tx));
+  }
+  const int n1 = dh * W * 3, n2 = dh * dw * 3;
+  CVB_TRY(launch_pdl(tf_gather_rows_kernel, dim3((n1 + 255) / 256), dim3(256), 0, st, 1, img_hwc, H, W, dh, ty.starts,
+                     ty.weights, ty.span, scratch_f32));
+  CVB_LAUNCHED();
+  CVB_TRY(launch_pdl(tf_gather_cols_kernel, dim3((n2 + 255) / 256), dim3(256), 0, st, 1, scratch_f32, W, dh, dw, tx.starts,
+                     tx.weights, tx.span, out_u8_hwc));
   CVB_LAUNCHED();
   return 0;
 }

@@ -240,6 +240,13 @@ CVB_API int cvb_preprocess_policy_image(const uint8_t* img_u8_hwc, int H, int W,
  * Normalize(0.5, 0.5)).  Same conventions as cvb_preprocess_policy_image; out_u8_hwc is bit-exact with Pillow. */
 CVB_API int cvb_preprocess_verifier_image(const uint8_t* img_u8_hwc, int H, int W, int out_h, int out_w,
                                           uint8_t* out_u8_hwc, float* out_f32_chw, void* stream);
+/* The first verifier-side frame step on the device (replaces process_raw_image_to_jpg, CoVer_VLA/inference/experiments/
+ * robot/simpler/eval_utils.py:228-286: tf.image.resize(frame, (256, 256), BILINEAR, antialias=True) then tf.cast(uint8)).
+ * img_u8_hwc: device uint8 [H, W, 3]; scratch_f32: device float [out_h * W * 3]; out_u8_hwc: device uint8 [out_h, out_w, 3].
+ * TensorFlow's scale_and_translate algorithm restated (triangle kernel, antialias); bit-exact against the numpy
+ * restatement in oracle/, unpinned against TensorFlow itself (absent offline). */
+CVB_API int cvb_resize_bilinear_antialias_u8(const uint8_t* img_u8_hwc, int H, int W, int out_h, int out_w,
+                                             float* scratch_f32, uint8_t* out_u8_hwc, void* stream);
 /* One whole CoVer decision in one call / one CUDA graph: cvb_pi0_sample -> cvb_format_trajectories ->
  * cvb_verifier_score for N = R*K candidates (the body of run_simpler_eval_with_openpi.py:322-363 on the device, no host
  * round trip in between).  The verifier's image/text side is forked onto an internal stream after the prefix and runs

@@ -159,3 +159,71 @@ def verifier_image(img_u8_hwc: np.ndarray, size: int = 384):
     x = small.transpose(2, 0, 1)[None].astype(np.float32) / np.float32(255)
     x = (x - np.float32(0.5)) / np.float32(0.5)
     return small, x.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# process_raw_image_to_jpg (CoVer_VLA/inference/experiments/robot/simpler/eval_utils.py:228-286):
+#   tf.image.resize(image_u8, (256, 256), method=BILINEAR, preserve_aspect_ratio=False, antialias=True) -> tf.cast(uint8)
+# Third-party arithmetic: TensorFlow ("tensorflow" is an unpinned dependency of CoVer_VLA/inference/pyproject.toml; NOT
+# installed here and not vendored).  Restated from its published algorithm - tensorflow/python/ops/image_ops_impl.py
+# (resize_images_v2 with antialias -> scale_and_translate, scale = float32(new) / float32(old), translation 0) and
+# tensorflow/core/kernels/image/scale_and_translate_op.cc (ComputeSpansCore with the triangle kernel of radius 1,
+# kernel_scale = max(1 / scale, 1); GatherRows then GatherColumns, float32, sequential multiply-adds).  PARITY UNPINNED
+# against TensorFlow itself: there is no TensorFlow to run and the reference holds no fixture for this step; the CUDA
+# kernel is bit-exact against THIS restatement (tests/test_preprocess.py), and the structural properties any correct
+# triangle-filter resize has (constant images stay constant, weights sum to one, identity at equal sizes) are tested.
+def tf_spans(in_size: int, out_size: int):
+    f32 = np.float32
+    scale = f32(out_size) / f32(in_size)
+    inv_scale = f32(1.0) / scale
+    kernel_scale = max(inv_scale, f32(1.0))
+    radius = f32(1.0)
+    span = min(2 * int(math.ceil(float(radius * kernel_scale))) + 1, in_size)
+    starts = np.zeros(out_size, dtype=np.int64)
+    weights = np.zeros((out_size, span), dtype=np.float32)
+    for x in range(out_size):
+        col_f = f32(x) + f32(0.5)
+        sample_f = f32(col_f * inv_scale)
+        if sample_f < 0 or sample_f > in_size:
+            continue
+        s0 = int(math.ceil(float(f32(f32(sample_f - f32(radius * kernel_scale)) - f32(0.5)))))
+        s1 = int(math.floor(float(f32(f32(sample_f + f32(radius * kernel_scale)) - f32(0.5)))))
+        s0 = min(max(s0, 0), in_size - 1)
+        s1 = min(max(s1, 0), in_size - 1) + 1
+        tmp = np.zeros(s1 - s0, dtype=np.float32)
+        total = f32(0.0)
+        for i in range(s1 - s0):
+            kernel_pos = f32(f32(f32(s0 + i) + f32(0.5)) - sample_f)
+            v = abs(f32(kernel_pos / kernel_scale))
+            w = max(f32(0.0), f32(f32(1.0) - v))
+            total = f32(total + w)
+            tmp[i] = w
+        starts[x] = s0
+        if abs(total) >= 1000.0 * np.finfo(np.float32).tiny:
+            one_over = f32(f32(1.0) / total)
+            n = min(len(tmp), span)
+            weights[x, :n] = (tmp[:n] * one_over).astype(np.float32)
+    return starts, weights, span
+
+
+def tf_resize_bilinear_antialias_u8(img: np.ndarray, dh: int, dw: int) -> np.ndarray:
+    """uint8 [H, W, C] -> uint8 [dh, dw, C]; float32 sequential accumulation in source order, truncating cast."""
+    H, W, C = img.shape
+    ys, wy, sy = tf_spans(H, dh)
+    xs, wx, sx = tf_spans(W, dw)
+    src = img.astype(np.float32)
+    inter = np.zeros((dh, W, C), dtype=np.float32)
+    for k in range(sy):  # rows first (GatherRows)
+        idx = ys + k
+        ok = idx < H
+        rows = src[np.minimum(idx, H - 1)]  # [dh, W, C]
+        term = (rows * wy[:, k][:, None, None]).astype(np.float32)
+        inter = np.where(ok[:, None, None], (inter + term).astype(np.float32), inter)
+    out = np.zeros((dh, dw, C), dtype=np.float32)
+    for k in range(sx):  # then columns (GatherColumns)
+        idx = xs + k
+        ok = idx < W
+        cols = inter[:, np.minimum(idx, W - 1)]  # [dh, dw, C]
+        term = (cols * wx[:, k][None, :, None]).astype(np.float32)
+        out = np.where(ok[None, :, None], (out + term).astype(np.float32), out)
+    return np.clip(out, 0.0, 255.0).astype(np.int32).astype(np.uint8)  # tf.cast truncates toward zero

@@ -119,3 +119,46 @@ def test_cuda_verifier_image_matches_live_pil():
         ref = np.asarray(Image.fromarray(img).convert("RGB").resize((S, S), Image.BICUBIC))
         _, u8 = preprocess.verifier_image(torch.from_numpy(img).cuda(), S, return_u8=True)
         assert np.array_equal(u8.cpu().numpy(), ref), (H, W, S)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# verifier frame: process_raw_image_to_jpg (eval_utils.py:228-286) = tf.image.resize(BILINEAR, antialias=True) -> uint8.
+# TensorFlow is absent (parity unpinned upstream): the restatement's structural properties, then CUDA == restatement.
+# ---------------------------------------------------------------------------------------------------------------
+def test_tf_antialias_resize_restatement_properties():
+    rng = np.random.default_rng(8)
+    for n_in, n_out in [(480, 256), (640, 256), (256, 256), (100, 256), (1080, 256)]:
+        starts, w, span = P.tf_spans(n_in, n_out)
+        assert w.dtype == np.float32 and (w >= 0).all()
+        assert np.abs(w.sum(1) - 1).max() < 1e-6                      # normalised triangle weights
+        assert (starts >= 0).all() and (starts + (w > 0).sum(1) <= n_in).all()
+        centre = (np.arange(n_out) + 0.5) * n_in / n_out               # the filter is centred on the sample position
+        mean_src = (w * (starts[:, None] + np.arange(span)[None, :] + 0.5)).sum(1)
+        inside = (centre > span) & (centre < n_in - span)
+        assert np.abs(mean_src - centre)[inside].max() < 0.1               # (a sampled triangle is only nearly symmetric)
+    img = rng.integers(0, 256, size=(64, 48, 3), dtype=np.uint8)
+    assert np.array_equal(P.tf_resize_bilinear_antialias_u8(img, 64, 48), img)   # identity at equal sizes
+    flat = np.full((480, 640, 3), 200, np.uint8)
+    out = P.tf_resize_bilinear_antialias_u8(flat, 256, 256)
+    assert set(np.unique(out)) <= {199, 200}                            # float32 weight sums of 1 - 1 ulp truncate down
+    # down-scaling averages: a 2x2 checkerboard of 0 / 255 at 2:1 lands mid-grey, not on an aliased extreme
+    cb = (np.indices((512, 512)).sum(0) % 2 * 255).astype(np.uint8)[:, :, None].repeat(3, 2)
+    out = P.tf_resize_bilinear_antialias_u8(cb, 256, 256)
+    assert 120 <= out.min() and out.max() <= 135
+
+
+@pytest.mark.gpu
+def test_cuda_tf_antialias_resize_is_bit_exact_vs_restatement():
+    from cover_vla_b200 import preprocess
+    rng = np.random.default_rng(12)
+    for H, W, S in [(480, 640, 256), (512, 640, 256), (256, 256, 256), (100, 130, 256), (1080, 1920, 256), (37, 53, 64)]:
+        img = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+        ref = P.tf_resize_bilinear_antialias_u8(img, S, S)
+        out = preprocess.verifier_frame(torch.from_numpy(img).cuda(), S)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), ref), (H, W, S)
+    # the whole verifier-side image path from one uint8 frame: 256^2 antialias -> PIL-bicubic 384^2 -> normalise
+    img = rng.integers(0, 256, size=(480, 640, 3), dtype=np.uint8)
+    f32 = preprocess.verifier_image_from_raw(torch.from_numpy(img).cuda(), 384)
+    ref = P.verifier_image(P.tf_resize_bilinear_antialias_u8(img, 256, 256), 384)[1]
+    assert np.array_equal(f32.cpu().numpy(), ref)

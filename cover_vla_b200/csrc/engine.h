@@ -115,6 +115,7 @@ struct Pi0State {
   bf16 *kcache = nullptr, *vcache = nullptr;
   float *state_emb = nullptr, *a1 = nullptr, *a2 = nullptr, *suffix = nullptr, *v0 = nullptr;
   bf16 *he = nullptr, *xe = nullptr, *qkv_e = nullptr, *attn_e = nullptr, *act_e = nullptr;
+  bf16 *state_k = nullptr, *state_v = nullptr;  // [layers][candidates][head_dim]: the suffix state token's rotated K / V (F7 hoist)
   bf16* vt_p = nullptr;  // V^T of the current prefix layer: [max_rephrases][head_dim][vt_ld] (tcgen05 prefix attention)
   long vt_ld = 0;
   float* part_e = nullptr;  // split-K partials of the expert's o_proj / down_proj: [kMaxSplitK][N*S][ex_width] fp32

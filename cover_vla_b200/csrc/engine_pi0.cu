@@ -321,6 +321,9 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
   CVB_CUDA(cudaMemsetAsync(s.vt_p, 0, (size_t)c.layers * Rm * c.head_dim * s.vt_ld * sizeof(bf16), st));  // padding keys stay finite
   const size_t Me = (size_t)Nm * S, Ma = (size_t)Nm * c.chunk_size;
   CVB_TRY(dalloc_t(h, &s.state_emb, (size_t)Bm * We));
+  // F7 hoist: rotated key / value of the state token of every candidate and expert layer, written by denoise step 0
+  CVB_TRY(dalloc_t(h, &s.state_k, (size_t)c.layers * Nm * c.head_dim));
+  CVB_TRY(dalloc_t(h, &s.state_v, (size_t)c.layers * Nm * c.head_dim));
   CVB_TRY(dalloc_t(h, &s.a1, Ma * We));
   CVB_TRY(dalloc_t(h, &s.a2, Ma * We));
   CVB_TRY(dalloc_t(h, &s.suffix, Me * We));
@@ -544,7 +547,18 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int B, int Rpo, int K) {
   const MegaProgram* pg = nullptr;
   const bool mega = s.mega.mode != 0 && attention_decode_umma_eligible(probe) && M <= 256 && B == 1;
   if (mega) CVB_TRY(expert_mega_program(h, M, st, &pg));
+  // F7 hoist: the suffix's state token attends the prefix and itself only and its input never changes, so
+  // its K / V of every layer are identical in all denoise steps.  Step 0 runs all S rows per candidate and keeps them
+  // (the tcgen05 attention kernel writes the rotated key / the value while staging); steps 1.. run the chunk_size action
+  // rows only (M = 4 N instead of 5 N: -20 % GEMM rows, activation and partial traffic) and read the state key / value
+  // from the cache.  Bit-identical to recomputing it (tests/test_pi0_gpu.py::test_state_token_hoist_is_exact).
+  const bool hoist = !mega && getenv("CVB_NO_HOIST") == nullptr && attention_decode_umma_eligible(probe) && S == c.chunk_size + 1 &&
+                     s.times.size() > 1;
+  const long Nm_all = (long)h->rm_total() * c.max_samples;
   for (size_t step = 0; step < s.times.size(); ++step) {
+    const bool hoisted = hoist && step > 0;  // this step runs without the state rows
+    const int Sc = hoisted ? S - 1 : S;      // suffix rows per candidate in this step
+    const int M = N * Sc;
     {  // embed_suffix (modeling_pi0.py:598-609), time half of mlp_in folded into time_vec[step]
       SgemmCall g2;
       if (s.w_ain_comb != nullptr) {
@@ -561,7 +575,7 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int B, int Rpo, int K) {
       CVB_TRY(sgemm_f32(st, g2));
       SgemmCall g3;
       g3.A = s.a2, g3.lda = We, g3.W = w_out, g3.ldw = We, g3.M = Ma, g3.N = We, g3.K = We;
-      g3.C = s.suffix, g3.ldc = We, g3.bias = b_out, g3.out_group = c.chunk_size;
+      g3.C = s.suffix, g3.ldc = We, g3.bias = b_out, g3.out_group = hoisted ? 0 : c.chunk_size;
       CVB_TRY(sgemm_f32(st, g3));
     }
     if (mega) {
@@ -616,16 +630,26 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int B, int Rpo, int K) {
       AttnCall a;
       a.rope = fused_rope ? s.rope_tab : nullptr;
       a.kv0_static = 1;
-      a.q = s.qkv_e, a.q_batch_stride = (long)S * qkvw, a.q_row_stride = qkvw;
+      a.q = s.qkv_e, a.q_batch_stride = (long)Sc * qkvw, a.q_row_stride = qkvw;
       a.k0 = s.kcache + l * layer_stride, a.v0 = s.vcache + l * layer_stride;
       a.kv0_batch_stride = (long)P * hd, a.kv0_row_stride = hd, a.kv0_len_dev = s.plen, a.kv0_max = h->n_img() + h->lang_rows();
       a.q_per_kv_batch = K;
       if (getenv("CVB_NO_UMMA_ATTN") == nullptr) a.vt0 = s.vt_p + (size_t)l * h->rm_total() * hd * s.vt_ld, a.vt0_ld = s.vt_ld;
-      a.k1 = s.qkv_e + qd, a.v1 = s.qkv_e + qd + hd, a.kv1_batch_stride = (long)S * qkvw;
+      a.k1 = s.qkv_e + qd, a.v1 = s.qkv_e + qd + hd, a.kv1_batch_stride = (long)Sc * qkvw;
       a.kv1_row_stride = qkvw, a.kv1_len = S, a.suffix_mask = 1;
-      a.out = s.attn_e, a.o_batch_stride = (long)S * qd, a.o_row_stride = qd;
-      a.batches = N, a.heads = c.heads, a.kv_heads = 1, a.tq = S, a.head_dim = hd;
+      a.out = s.attn_e, a.o_batch_stride = (long)Sc * qd, a.o_row_stride = qd;
+      a.batches = N, a.heads = c.heads, a.kv_heads = 1, a.tq = Sc, a.head_dim = hd;
       a.scale = 1.0f / sqrtf(static_cast<float>(hd));
+      if (hoist) {
+        bf16* ck = s.state_k + (size_t)l * Nm_all * hd;
+        bf16* cv = s.state_v + (size_t)l * Nm_all * hd;
+        a.rope_rows = S;
+        if (hoisted) {  // suffix keys = [cached state key, the chunk_size action keys of this step]; no state query row
+          a.kv1_cached_k = ck, a.kv1_cached_v = cv, a.kv1_cached = 1, a.suffix_mask = 0, a.rope_off = 1;
+        } else {
+          a.kv1_cache_out_k = ck, a.kv1_cache_out_v = cv;
+        }
+      }
       CVB_TRY(attention(st, a));
       if (sk && s.splitk_o > 0) {
         int used = 0;
@@ -672,7 +696,7 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int B, int Rpo, int K) {
     else if (pending == 0)
       CVB_TRY(rmsnorm(st, s.he, 0, We, w_norm, 1, s.xe, We, M, We, 1e-6f, nullptr));
     CVB_TRY(action_out_euler(st, s.xe, We, w_aout, b_aout, s.x_t, step == 0 ? s.v0 : nullptr, N, We,
-                             c.max_action_dim, c.chunk_size, S, s.dt));
+                             c.max_action_dim, c.chunk_size, Sc, s.dt));
   }
   return 0;
 }

@@ -141,6 +141,16 @@ struct AttnCall {
   long vt0_ld = 0;
   // optional (tcgen05 decode kernel only): q / k1 / v1 given as fp32 split-K partials of the fused qkv projection,
   // [part_splits][same element strides as q / k1 / v1]; summed in split order and rounded to bf16 while staging
+  // optional (tcgen05 decode kernel only), SURVEY.md F7: the first kv1_cached of the kv1_len suffix keys / values come from
+  // a cache ([batches][kv1_cached][head_dim] bf16, keys already rotated) - k1 / v1 then hold kv1_len - kv1_cached rows;
+  // kv1_cache_out_*: the rotated key / value of suffix key 0 are written there (the step that fills the cache);
+  // rope_rows / rope_off: rows of the rope table per kv batch (0 = tq) and the table row of query token 0 / new key 0
+  const bf16* kv1_cached_k = nullptr;
+  const bf16* kv1_cached_v = nullptr;
+  int kv1_cached = 0;
+  bf16* kv1_cache_out_k = nullptr;
+  bf16* kv1_cache_out_v = nullptr;
+  int rope_rows = 0, rope_off = 0;
   const float* q_part = nullptr;
   const float* k1_part = nullptr;
   const float* v1_part = nullptr;

@@ -421,7 +421,8 @@ int attention(cudaStream_t st, const AttnCall& c) {
   if ((c.algo == 0 || c.algo == 3) && attention_decode_umma_eligible(c)) return attention_decode_umma(st, c);
   if ((c.algo == 0 || c.algo == 3) && c.k1 == nullptr && attention_mha_umma_eligible(c)) return attention_mha_umma(st, c);
   if ((c.algo == 0 || c.algo == 3) && c.k1 == nullptr && attention_mha_long_umma_eligible(c)) return attention_mha_long_umma(st, c);
-  CVB_REQUIRE(c.algo != 3 && c.q_part == nullptr, "shape not eligible for a tcgen05 attention kernel");
+  CVB_REQUIRE(c.algo != 3 && c.q_part == nullptr && c.kv1_cached_k == nullptr && c.kv1_cache_out_k == nullptr,
+              "shape not eligible for a tcgen05 attention kernel");
   if (c.k1 != nullptr && c.algo != 1 && attention_decode_eligible(c)) return attention_decode(st, c, c.rope);
   if (c.k1 != nullptr && c.algo != 2 && attention_group_eligible(c)) return attention_group(st, c);
   CVB_REQUIRE(c.rope == nullptr, "fused RoPE needs the cluster decode attention (shape not eligible)");

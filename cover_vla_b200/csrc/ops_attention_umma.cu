@@ -392,6 +392,15 @@ struct UmmaDecodeParams {
   const float* v1f;
   int part_S;
   long part_ss;
+  // F7 hoist: the first `kc` suffix keys / values (the state token) are not recomputed every denoise step -
+  // they come from kc_k / kc_v ([batches][kc][256] bf16, K already rotated); k1 / v1 then hold only kv1_len - kc rows.
+  // kout_k / kout_v (step 0): the rotated key / the value of suffix key 0 are also written there.
+  const bf16* kc_k;
+  const bf16* kc_v;
+  int kc;
+  bf16* kout_k;
+  bf16* kout_v;
+  int rope_rows, rope_off;  // rows of the rope table per kv batch, and the table row of query token 0 / new key 0
 };
 
 // 8 consecutive bf16 of the qkv projection at element offset `off`: plain load, or sum of the fp32 partials -> bf16
@@ -590,23 +599,36 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     pdl_wait();
     UD_TS(1);
     const int n0 = min(p.kv0_len_dev != nullptr ? p.kv0_len_dev[kvb] : p.kv0_len, tk_pad);
-    const float2* rope = p.rope != nullptr ? p.rope + static_cast<long>(kvb) * p.tq * 128 : nullptr;
+    const float2* rope = p.rope != nullptr ? p.rope + (static_cast<long>(kvb) * p.rope_rows + p.rope_off) * 128 : nullptr;
     // ---- Q rows and suffix keys: global -> registers -> RoPE -> swizzled UMMA tiles
     const int n_items = (rows_total + p.kv1_len) * 16;
     for (int item = sid; item < n_items; item += UD_SOFT) {
       const bool isq = item < rows_total * 16;
       const int r = isq ? item >> 4 : (item - rows_total * 16) >> 4;
       const int c = item & 15;  // 8-wide chunk of the first half of the head
-      const int t = isq ? r / p.heads : r;
-      const long soff = isq ? b * p.q_bs + t * p.q_rs + (r % p.heads) * UA_HD + c * 8 : b * p.kv1_bs + r * p.kv1_rs + c * 8;
-      uint4 x1 = ud_load8(isq ? p.q : p.k1, isq ? p.qf : p.k1f, soff, p.part_S, p.part_ss);
-      uint4 x2 = ud_load8(isq ? p.q : p.k1, isq ? p.qf : p.k1f, soff + 128, p.part_S, p.part_ss);
-      if (rope != nullptr) {
+      const bool cached = !isq && r < p.kc;  // a hoisted suffix key: already rotated, read from the cache
+      const int t = isq ? r / p.heads : r - p.kc;
+      const long soff = isq ? b * p.q_bs + t * p.q_rs + (r % p.heads) * UA_HD + c * 8 : b * p.kv1_bs + t * p.kv1_rs + c * 8;
+      uint4 x1, x2;
+      if (cached) {
+        const bf16* kp = p.kc_k + (static_cast<long>(b) * p.kc + r) * UA_HD + c * 8;
+        x1 = *reinterpret_cast<const uint4*>(kp);
+        x2 = *reinterpret_cast<const uint4*>(kp + 128);
+      } else {
+        x1 = ud_load8(isq ? p.q : p.k1, isq ? p.qf : p.k1f, soff, p.part_S, p.part_ss);
+        x2 = ud_load8(isq ? p.q : p.k1, isq ? p.qf : p.k1f, soff + 128, p.part_S, p.part_ss);
+      }
+      if (rope != nullptr && !cached) {
         float4 cs[4];
         const float4* tp = reinterpret_cast<const float4*>(rope + t * 128 + c * 8);
 #pragma unroll
         for (int e = 0; e < 4; ++e) cs[e] = tp[e];
         rope8_umma(x1, x2, reinterpret_cast<const float2*>(cs));
+      }
+      if (p.kout_k != nullptr && !isq && r == 0 && hy == 0) {  // step 0: keep the state token's rotated key
+        bf16* kp = p.kout_k + static_cast<long>(b) * UA_HD + c * 8;
+        *reinterpret_cast<uint4*>(kp) = x1;
+        *reinterpret_cast<uint4*>(kp + 128) = x2;
       }
       const int row = isq ? (r & 3) * 32 + (r >> 2) : r;
       const uint32_t tile = isq ? smem_u32(sQ) + static_cast<uint32_t>(c >> 3) * UA_QBLK
@@ -618,7 +640,15 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
       sts_u4(tile2 + off, x2.x, x2.y, x2.z, x2.w);
     }
     uint4 v1reg = make_uint4(0, 0, 0, 0);
-    if (sid < p.kv1_len * 32) v1reg = ud_load8(p.v1, p.v1f, b * p.kv1_bs + (sid >> 5) * p.kv1_rs + (sid & 31) * 8, p.part_S, p.part_ss);
+    if (sid < p.kv1_len * 32) {
+      const int j = sid >> 5;
+      if (j < p.kc)
+        v1reg = *reinterpret_cast<const uint4*>(p.kc_v + (static_cast<long>(b) * p.kc + j) * UA_HD + (sid & 31) * 8);
+      else
+        v1reg = ud_load8(p.v1, p.v1f, b * p.kv1_bs + (j - p.kc) * p.kv1_rs + (sid & 31) * 8, p.part_S, p.part_ss);
+      if (p.kout_v != nullptr && j == 0 && hy == 0)
+        *reinterpret_cast<uint4*>(p.kout_v + static_cast<long>(b) * UA_HD + (sid & 31) * 8) = v1reg;
+    }
     fence_proxy_async();
     mbar_arrive(q_ready);
     UD_TS(2);
@@ -1357,6 +1387,11 @@ int attention_decode_umma(cudaStream_t st, const AttnCall& c) {
   p.heads = c.heads, p.tq = c.tq, p.tk_pad = tk_pad, p.scale = c.scale, p.kv0_static = c.kv0_static, p.rope = c.rope;
   p.ts = g_skinny_ts;
   p.qf = c.q_part, p.k1f = c.k1_part, p.v1f = c.v1_part, p.part_S = c.part_splits, p.part_ss = c.part_split_stride;
+  p.kc_k = c.kv1_cached_k, p.kc_v = c.kv1_cached_v, p.kc = c.kv1_cached_k != nullptr ? c.kv1_cached : 0;
+  p.kout_k = c.kv1_cache_out_k, p.kout_v = c.kv1_cache_out_v;
+  p.rope_rows = c.rope_rows > 0 ? c.rope_rows : c.tq, p.rope_off = c.rope_off;
+  CVB_REQUIRE(p.kc >= 0 && p.kc < c.kv1_len, "cached suffix keys must leave at least one new key");
+  CVB_REQUIRE(p.kc == 0 || !c.suffix_mask, "the suffix mask applies to the state-token query, which a hoisted call does not have");
   const int nkb = (tk_pad + 63) / 64;
   const int kslots = 4 * UA_QBLK + 4 * UD_KSBLK + 4 * tk_pad * 128 <= UA_BODY_MAX ? 4 : 3;
   const int vslots = std::min(std::min(nkb, UD_VSLOTS), (UA_BODY_MAX - UD_MISC - nkb * UA_PBLK) / (hdw * 128));

@@ -142,3 +142,27 @@ def test_persistent_expert_kernel_matches_oracle_and_separate_kernels(R, K, monk
         action_gate(runs[0], ref, truth, f"MID R={R} K={K} mega={flag}")
         eng.close()
     assert max_abs(outs["0"], outs["1"]) < 2e-2
+
+
+@pytest.mark.parametrize("R,K", [(2, 3), (8, 5), (1, 1)])
+def test_state_token_hoist_is_exact(R, K, monkeypatch):
+    """the suffix's state token never sees x_t or the time, so its per-layer K / V are computed in denoise
+    step 0 only and steps 1.. run the action rows alone (M = 4 N).  Must not change one bit."""
+    d = O.MID
+    w = O.make_pi0_weights(d, seed=7)
+    inp = O.make_inputs(d, R, K, seed=7)
+    args = (inp["image"][0].cuda().contiguous(), inp["tokens"].cuda(), inp["lens"].to(torch.int32).cuda(),
+            inp["state"][0].cuda().contiguous(), inp["noise"].cuda())
+    outs = {}
+    for flag in ("1", None):
+        if flag is None:
+            monkeypatch.delenv("CVB_NO_HOIST", raising=False)
+        else:
+            monkeypatch.setenv("CVB_NO_HOIST", flag)
+        eng = build_pi0_engine(d, w, R, K)
+        runs = [eng.pi0_sample(*args, K=K).cpu() for _ in range(3)]
+        torch.cuda.synchronize()
+        assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+        outs[flag] = runs[0]
+        eng.close()
+    assert torch.equal(outs["1"], outs[None])

@@ -86,7 +86,7 @@ int cvb_op_attention_tc(const void* q, int64_t q_bs, int64_t q_rs, const void* k
   c.out = (cvb::bf16*)out, c.o_batch_stride = o_bs, c.o_row_stride = o_rs;
   c.batches = batches, c.heads = heads, c.kv_heads = kv_heads, c.tq = tq, c.head_dim = head_dim, c.scale = scale;
   c.force_two_pass = force_two_pass == 1;
-  c.algo = force_two_pass == 2 ? 1 : force_two_pass == 3 ? 2 : force_two_pass == 4 ? 3 : 0;
+  c.algo = force_two_pass == 4 ? 3 : 0;
   c.rope = reinterpret_cast<const float2*>(rope_cos_sin);
   c.vt0 = (const cvb::bf16*)vt0, c.vt0_ld = vt0_ld;
   return cvb::attention((cudaStream_t)stream, c);

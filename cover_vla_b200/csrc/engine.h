@@ -121,8 +121,6 @@ struct Pi0State {
   float* part_e = nullptr;  // split-K partials of the expert's o_proj / down_proj: [kMaxSplitK][N*S][ex_width] fp32
   float* part_v = nullptr;  // split-K partials of the SigLIP tower's out_proj / fc2: [kMaxSplitK][n_img][vis_width] fp32
   int splitk_vo = 0, splitk_v2 = 0;
-  unsigned* splitk_sync = nullptr;  // [2] arrive / depart counters of the fused split-K + RMSNorm launches
-  int fuse_norm = 0;                // 1: o_proj / down_proj reduce + residual + RMSNorm inside the split-K GEMM launch
   int ex_gu_half = 64;  // gate/up packing of the expert: [half gate | half up] rows per block
   int splitk_o = 0, splitk_d = 0;  // K-splits of o_proj / down_proj in the denoise loop (0 = fused-epilogue GEMMs)
   int lang_hint = 0;  // caller's bound on valid language tokens per prompt (0 = max_lang_len), cvb_pi0_set_lang_len_hint

@@ -15,8 +15,6 @@
 
 namespace cvb {
 
-bool attention_decode_eligible(const AttnCall& c);
-bool attention_group_eligible(const AttnCall& c);
 bool attention_decode_umma_eligible(const AttnCall& c);
 
 namespace {
@@ -358,16 +356,6 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
     s.splitk_o = pick("CVB_SPLITK_O", qd);
     s.splitk_d = pick("CVB_SPLITK_D", c.ex_mlp);
     CVB_TRY(dalloc_t(h, &s.part_e, (size_t)kMaxSplitK * Me_sk * We));
-    // Fused tail (grid-wide arrive counter inside the split-K launch).  MEASURED SLOWER than the separate norm kernel
-    // (step 23.3 vs 22.1 ms: the barrier waits for the slowest of 64 CTAs and 64 CTAs then reduce 200 rows, while the
-    // separate kernel spreads them over 200 CTAs and overlaps its launch with the GEMM's tail), so it is OFF unless
-    // CVB_FUSE_NORM=1; kept as a tested, documented negative result.
-    CVB_TRY(dalloc_t(h, &s.splitk_sync, 2));
-    CVB_CUDA(cudaMemsetAsync(s.splitk_sync, 0, 2 * sizeof(unsigned), st));
-    const char* fe = getenv("CVB_FUSE_NORM");
-    const int tiles = (We + 127) / 128;
-    s.fuse_norm = (fe != nullptr && fe[0] == '1') && s.splitk_o > 0 && s.splitk_d > 0 &&
-                  tiles * std::max(s.splitk_o, s.splitk_d) <= device_sm_count() && We % 4 == 0 && We <= 2048;
   }
   CVB_TRY(expert_mega_prepare(h, st));  // persistent expert kernel (engine_expert_mega.cu), when the shape allows it
   return 0;
@@ -538,8 +526,7 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int B, int Rpo, int K) {
   probe.heads = c.heads, probe.kv_heads = 1, probe.tq = S, probe.head_dim = hd;
   probe.q_per_kv_batch = K, probe.batches = N;
   probe.kv0_row_stride = hd, probe.kv0_batch_stride = (long)P * hd, probe.vt0 = getenv("CVB_NO_UMMA_ATTN") == nullptr ? s.vt_p : nullptr, probe.vt0_ld = s.vt_ld;
-  const bool fused_rope = attention_group_eligible(probe) || attention_decode_eligible(probe) ||
-                          attention_decode_umma_eligible(probe);
+  const bool fused_rope = attention_decode_umma_eligible(probe);
   if (fused_rope) CVB_TRY(rope_table(st, s.rope_timescale, s.plen, R, S, hd / 2, s.rope_tab));
   // Persistent expert kernel: one launch per layer covers o_proj -> norm -> gate/up -> down -> norm -> next qkv with
   // device-wide barriers instead of kernel boundaries and a weight ring that prefetches across them; only the
@@ -607,12 +594,11 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int B, int Rpo, int K) {
       continue;
     }
     // pending = split-K partials of the previous down_proj still to be folded into he by the next norm
-    // (-1: the previous down_proj launch already did it - fused tail - and xe holds the normalised rows)
     int pending = 0;
-    auto gemm_part = [&](const bf16* A, long lda, const bf16* Wt, int Kd, int splits, int* used, const SplitKNorm* nm) {
+    auto gemm_part = [&](const bf16* A, long lda, const bf16* Wt, int Kd, int splits, int* used) {
       GemmCall g;
       g.A = A, g.lda = lda, g.W = Wt, g.ldw = Kd, g.M = M, g.N = We, g.K = Kd, g.C = s.part_e, g.ldc = We;
-      return gemm_splitk_partial(st, g, splits, used, nm);
+      return gemm_splitk_partial(st, g, splits, used);
     };
     for (int l = 0; l < c.layers; ++l) {
       const GemmaLayer& L = s.ex[l];
@@ -621,7 +607,7 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int B, int Rpo, int K) {
       if (pending > 0)  // he = he + down_proj(l-1), xe = input_layernorm(he)
         CVB_TRY(rmsnorm_reduce(st, s.part_e, pending, (long)M * We, We, s.he, 0, We, L.in_norm, 0, s.he, We, s.xe, We, M,
                                We, 1e-6f));
-      else if (pending == 0)
+      else
         CVB_TRY(rmsnorm(st, resid, resid_f32, We, L.in_norm, 0, s.xe, We, M, We, 1e-6f, nullptr));
       pending = 0;
       CVB_TRY(gemm(st, s.xe, We, L.wqkv, We, M, qkvw, We, EPI_STORE, s.qkv_e, qkvw));
@@ -653,16 +639,9 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int B, int Rpo, int K) {
       CVB_TRY(attention(st, a));
       if (sk && s.splitk_o > 0) {
         int used = 0;
-        if (s.fuse_norm) {  // o_proj + residual + post_attention_layernorm in one launch
-          SplitKNorm nm;
-          nm.resid = resid, nm.resid_is_f32 = resid_f32, nm.ldr = We, nm.w = L.post_norm, nm.w_is_f32 = 0;
-          nm.h_out = s.he, nm.ldh = We, nm.y = s.xe, nm.ldy = We, nm.sync = s.splitk_sync;
-          CVB_TRY(gemm_part(s.attn_e, qd, L.wo, qd, s.splitk_o, &used, &nm));
-        } else {
-          CVB_TRY(gemm_part(s.attn_e, qd, L.wo, qd, s.splitk_o, &used, nullptr));
-          CVB_TRY(rmsnorm_reduce(st, s.part_e, used, (long)M * We, We, resid, resid_f32, We, L.post_norm, 0, s.he, We,
-                                 s.xe, We, M, We, 1e-6f));
-        }
+        CVB_TRY(gemm_part(s.attn_e, qd, L.wo, qd, s.splitk_o, &used));
+        CVB_TRY(rmsnorm_reduce(st, s.part_e, used, (long)M * We, We, resid, resid_f32, We, L.post_norm, 0, s.he, We,
+                               s.xe, We, M, We, 1e-6f));
       } else {
         CVB_TRY(gemm(st, s.attn_e, qd, L.wo, qd, M, We, qd, EPI_RESID, s.he, We, nullptr, resid, We, resid_f32));
         CVB_TRY(rmsnorm(st, s.he, 0, We, L.post_norm, 0, s.xe, We, M, We, 1e-6f, nullptr));
@@ -672,20 +651,7 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int B, int Rpo, int K) {
       else
         CVB_TRY(gemm(st, s.xe, We, L.wgu, We, M, packed, We, EPI_GEGLU, s.act_e, c.ex_mlp, nullptr, nullptr, 0, 0, c.ex_mlp));
       if (sk && s.splitk_d > 0) {
-        if (s.fuse_norm) {  // down_proj + residual + the NEXT norm (next layer's input_layernorm, or the final norm)
-          SplitKNorm nm;
-          nm.resid = s.he, nm.resid_is_f32 = 0, nm.ldr = We;
-          if (l + 1 < c.layers)
-            nm.w = s.ex[l + 1].in_norm, nm.w_is_f32 = 0;
-          else
-            nm.w = w_norm, nm.w_is_f32 = 1;
-          nm.h_out = s.he, nm.ldh = We, nm.y = s.xe, nm.ldy = We, nm.sync = s.splitk_sync;
-          int used = 0;
-          CVB_TRY(gemm_part(s.act_e, c.ex_mlp, L.wd, c.ex_mlp, s.splitk_d, &used, &nm));
-          pending = -1;
-        } else {
-          CVB_TRY(gemm_part(s.act_e, c.ex_mlp, L.wd, c.ex_mlp, s.splitk_d, &pending, nullptr));
-        }
+        CVB_TRY(gemm_part(s.act_e, c.ex_mlp, L.wd, c.ex_mlp, s.splitk_d, &pending));
       } else {
         CVB_TRY(gemm(st, s.act_e, c.ex_mlp, L.wd, c.ex_mlp, M, We, c.ex_mlp, EPI_RESID, s.he, We, nullptr, s.he, We));
       }
@@ -693,7 +659,7 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int B, int Rpo, int K) {
     if (pending > 0)
       CVB_TRY(rmsnorm_reduce(st, s.part_e, pending, (long)M * We, We, s.he, 0, We, w_norm, 1, s.he, We, s.xe, We, M, We,
                              1e-6f));
-    else if (pending == 0)
+    else
       CVB_TRY(rmsnorm(st, s.he, 0, We, w_norm, 1, s.xe, We, M, We, 1e-6f, nullptr));
     CVB_TRY(action_out_euler(st, s.xe, We, w_aout, b_aout, s.x_t, step == 0 ? s.v0 : nullptr, N, We,
                              c.max_action_dim, c.chunk_size, Sc, s.dt));

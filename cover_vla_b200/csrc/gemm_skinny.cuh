@@ -394,21 +394,6 @@ struct SplitKArgs {
   int S;       // K-splits (grid = n_tiles * S)
   int stages;  // smem ring depth
   int tmem_cols;
-  // Optional fused tail (fuse_norm = 1): once EVERY CTA of the grid has stored its partial tile (device-wide arrive
-  // counter - the grid is at most one CTA per SM, so all CTAs are co-resident), each CTA reduces a share of the rows:
-  // h = bf16(bf16(sum_s P[s]) + resid), y = GemmaRMSNorm(h) - the work of rmsnorm_reduce_kernel without its launch.
-  int fuse_norm;
-  const void* resid;
-  int resid_is_f32;
-  long ldr;
-  const void* nw;
-  int nw_is_f32;
-  __nv_bfloat16* h_out;
-  long ldh;
-  __nv_bfloat16* y;
-  long ldy;
-  float eps;
-  unsigned* sync;  // [2] arrive / depart counters, zero-initialised, reset by the last CTA to leave
 };
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
@@ -426,7 +411,9 @@ gemm_splitk_partial_tcgen05(const __grid_constant__ CUtensorMap tmW, const __gri
                                              ~static_cast<uintptr_t>(1023));
   const uint32_t a_bytes = static_cast<uint32_t>(g.Mp) * 128u;
   const uint32_t stage_bytes = SK_W_BYTES + a_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + static_cast<uint32_t>(g.stages) * stage_bytes);
+  // the ring is reused as the transposed fp32 output tile [Mp][128]: the barriers sit behind the larger of the two
+  const uint32_t body = max(static_cast<uint32_t>(g.stages) * stage_bytes, static_cast<uint32_t>(g.Mp) * 512u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + body);
   uint64_t* empty_bar = full_bar + g.stages;
   uint64_t* tfull_bar = empty_bar + g.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
@@ -517,12 +504,14 @@ gemm_splitk_partial_tcgen05(const __grid_constant__ CUtensorMap tmW, const __gri
     pdl_wait();  // P may still be read by the kernel that consumed the previous partials
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
-    // TMEM lane = feature, column = activation row: lane L of the warp's quarter stores P[split][m][tile*128 + L]
+    // TMEM lane = feature, column = activation row.  The TMA ring is dead (every load consumed, every MMA retired), so
+    // the tile is transposed through it: each warp parks its 32 features x 32 rows as stage[row][feature] (conflict-free:
+    // a warp writes 32 consecutive floats), then the 8 epilogue warps store whole rows - one 512-byte float4 store per
+    // row instead of four scattered 128-byte ones (SM -> L2 writes were the slow part of this kernel).
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int n = tile * 128 + q * 32 + lane;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    float* pp = g.P + static_cast<long>(split) * g.split_stride + n;
+    float* stage = reinterpret_cast<float*>(smem);
     for (int c0 = half * 32; c0 < g.Mp; c0 += 64) {
       uint32_t r[32];
       const bool wide = c0 + 32 <= g.Mp;  // Mp is a multiple of 16: the last chunk may be 16 columns
@@ -535,13 +524,17 @@ gemm_splitk_partial_tcgen05(const __grid_constant__ CUtensorMap tmW, const __gri
         for (int i = 0; i < 16; ++i) r[i] = r16[i];
       }
       tmem_wait_ld();
-      if (n < g.N) {
+      float* sp = stage + static_cast<long>(c0) * 128 + q * 32 + lane;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int m = c0 + i;
-          if ((i < 16 || wide) && m < g.M) pp[static_cast<long>(m) * g.ldp] = __uint_as_float(r[i]);
-        }
-      }
+      for (int i = 0; i < 32; ++i)
+        if (i < 16 || wide) sp[i * 128] = __uint_as_float(r[i]);
+    }
+    named_bar_sync(1, SK_THREADS - 64);
+    const int n0 = tile * 128 + lane * 4;
+    float* pp = g.P + static_cast<long>(split) * g.split_stride + n0;
+    if (n0 < g.N) {  // N is a multiple of 4 (checked on the host)
+      for (int m = warp - 2; m < g.M; m += 8)
+        *reinterpret_cast<float4*>(pp + static_cast<long>(m) * g.ldp) = *reinterpret_cast<const float4*>(stage + m * 128 + lane * 4);
     }
   }
 
@@ -550,87 +543,6 @@ gemm_splitk_partial_tcgen05(const __grid_constant__ CUtensorMap tmW, const __gri
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, g.tmem_cols);
-  }
-
-  if (g.fuse_norm) {
-    // ---- grid-wide arrive: every partial tile is in global memory (L2) before any row is reduced
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      atomicAdd(&g.sync[0], 1u);
-      while (ld_acquire_gpu(&g.sync[0]) < gridDim.x) {
-      }
-    }
-    __syncthreads();
-    // ---- 4 rows at a time, 64 threads (2 warps) per row; the dead TMA ring holds the rows as fp32
-    float* hbuf = reinterpret_cast<float*>(smem);
-    __shared__ float red2[8];
-    const int pr = warp >> 1;                  // row slot 0..3 (warps 8, 9 idle)
-    const int t = (warp & 1) * 32 + lane;      // 0..63 inside the row
-    for (int row0 = blockIdx.x * 4; row0 < g.M; row0 += gridDim.x * 4) {
-      const int row = row0 + pr;
-      const bool on = warp < 8 && row < g.M;
-      float* hrow = hbuf + pr * g.N;
-      float ss = 0.f;
-      if (on) {
-        const float* prow = g.P + static_cast<long>(row) * g.ldp;
-        for (int i = t * 4; i < g.N; i += 256) {
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int sp = 0; sp < g.S; ++sp) {  // split order, L1 bypassed (written by other SMs)
-            const float4 a = __ldcg(reinterpret_cast<const float4*>(prow + sp * g.split_stride + i));
-            acc.x += a.x, acc.y += a.y, acc.z += a.z, acc.w += a.w;
-          }
-          float rr[4];
-          if (g.resid_is_f32) {
-            const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.resid) + row * g.ldr + i);
-            rr[0] = v.x, rr[1] = v.y, rr[2] = v.z, rr[3] = v.w;
-          } else {
-            const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g.resid) + row * g.ldr + i);
-            const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y);
-            rr[0] = f0.x, rr[1] = f0.y, rr[2] = f1.x, rr[3] = f1.y;
-          }
-          const float hv[4] = {bf16_round(bf16_round(acc.x) + rr[0]), bf16_round(bf16_round(acc.y) + rr[1]),
-                               bf16_round(bf16_round(acc.z) + rr[2]), bf16_round(bf16_round(acc.w) + rr[3])};
-          *reinterpret_cast<uint2*>(g.h_out + row * g.ldh + i) = make_uint2(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]));
-          *reinterpret_cast<float4*>(hrow + i) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-          ss += hv[0] * hv[0] + hv[1] * hv[1] + hv[2] * hv[2] + hv[3] * hv[3];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        if (lane == 0) red2[warp] = ss;
-      }
-      __syncthreads();
-      if (on) {
-        const float tot = red2[pr * 2] + red2[pr * 2 + 1];
-        const float r = 1.0f / sqrtf(tot / static_cast<float>(g.N) + g.eps);
-        __nv_bfloat16* yr = g.y + row * g.ldy;
-        for (int i = t * 4; i < g.N; i += 256) {  // each thread re-reads its own hrow entries
-          const float4 hv = *reinterpret_cast<const float4*>(hrow + i);
-          float wv[4];
-          if (g.nw_is_f32) {
-            const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.nw) + i);
-            wv[0] = v.x, wv[1] = v.y, wv[2] = v.z, wv[3] = v.w;
-          } else {
-            const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g.nw) + i);
-            const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y);
-            wv[0] = f0.x, wv[1] = f0.y, wv[2] = f1.x, wv[3] = f1.y;
-          }
-          *reinterpret_cast<uint2*>(yr + i) =
-              make_uint2(pack_bf16x2((hv.x * r) * (1.0f + wv[0]), (hv.y * r) * (1.0f + wv[1])),
-                         pack_bf16x2((hv.z * r) * (1.0f + wv[2]), (hv.w * r) * (1.0f + wv[3])));
-        }
-      }
-      __syncthreads();  // red2 / hbuf are reused by the next group of rows
-    }
-    // ---- depart: the last CTA past the barrier re-arms the counters for the next launch
-    if (threadIdx.x == 0) {
-      const unsigned d = atomicAdd(&g.sync[1], 1u);
-      if (d == gridDim.x - 1) {
-        g.sync[0] = 0u;
-        g.sync[1] = 0u;
-        __threadfence();
-      }
-    }
   }
 }
 

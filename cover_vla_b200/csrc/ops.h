@@ -30,23 +30,9 @@ struct GemmCall {
 };
 int gemm_bf16(cudaStream_t st, const GemmCall& c);
 // Split-K GEMM (M <= 256) that leaves S fp32 partial products in C = float[S][M][ldc] (epi / bias / resid unused);
-// splits <= 0 picks S so that n_tiles * S fills the SMs once.  The partials are consumed by rmsnorm_reduce().
-// With `norm` the reduction + residual + Gemma RMSNorm of rmsnorm_reduce() run inside the same launch (after a
-// grid-wide arrive counter); `norm->sync` = two zero-initialised device words owned by the caller.
-struct SplitKNorm {
-  const void* resid = nullptr;
-  int resid_is_f32 = 0;
-  long ldr = 0;
-  const void* w = nullptr;
-  int w_is_f32 = 0;
-  bf16* h_out = nullptr;
-  long ldh = 0;
-  bf16* y = nullptr;
-  long ldy = 0;
-  float eps = 1e-6f;
-  unsigned* sync = nullptr;
-};
-int gemm_splitk_partial(cudaStream_t st, const GemmCall& c, int splits, int* splits_out, const SplitKNorm* norm = nullptr);
+// splits <= 0 picks S so that n_tiles * S fills the SMs once.  The partials are consumed by rmsnorm_reduce() /
+// layernorm_reduce(), which sum them in split order (deterministic) inside the norm that follows the linear layer anyway.
+int gemm_splitk_partial(cudaStream_t st, const GemmCall& c, int splits, int* splits_out);
 
 // ---- fp32 SIMT GEMM (sgemm.cuh): C = act(A[M,K] * W[N,K]^T + bias) (+ resid) -------------------
 enum SgemmAct : int { SACT_NONE = 0, SACT_RELU = 1, SACT_GELU_ERF = 2, SACT_SILU = 3 };
@@ -134,7 +120,7 @@ struct AttnCall {
   // segment 0 (and kv0_len_dev) is NOT written by the kernel launched just before this one: its tiles may be
   // prefetched before the programmatic-dependency wait (the prefix KV cache during the denoise loop)
   int kv0_static = 0;
-  int algo = 0;  // two-segment calls: 0 auto, 1 rephrase-grouped kernel only, 2 cluster decode kernel only, 3 tcgen05 only
+  int algo = 0;  // 0 auto, 3 tcgen05 kernels only (error if the shape is not eligible)
   // optional TRANSPOSED copy of segment-0 values, vt0[(kv batch * head_dim + d) * vt0_ld + key] (finite past the valid
   // length): enables the tcgen05 decode kernel (ops_attention_umma.cu) for MQA / head_dim 256 shapes
   const bf16* vt0 = nullptr;

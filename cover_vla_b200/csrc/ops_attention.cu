@@ -401,10 +401,6 @@ int launch_attn(cudaStream_t st, const AttnParams& p, dim3 grid) {
 
 }  // namespace
 
-bool attention_decode_eligible(const AttnCall& c);
-int attention_decode(cudaStream_t st, const AttnCall& c, const float2* rope);
-bool attention_group_eligible(const AttnCall& c);
-int attention_group(cudaStream_t st, const AttnCall& c);
 bool attention_decode_umma_eligible(const AttnCall& c);
 int attention_decode_umma(cudaStream_t st, const AttnCall& c);
 bool attention_mha_umma_eligible(const AttnCall& c);
@@ -415,16 +411,13 @@ int attention_mha_long_umma(cudaStream_t st, const AttnCall& c);
 int attention(cudaStream_t st, const AttnCall& c) {
   CVB_REQUIRE(c.head_dim % 8 == 0 && c.head_dim <= 256, "head_dim must be a multiple of 8, <= 256");
   CVB_REQUIRE(c.heads % c.kv_heads == 0, "heads must be a multiple of kv_heads");
-  // measured at the denoise shape (tools/decode_ts.py): cluster split-KV 21 us, rephrase-grouped 32 us -> prefer the
-  // cluster kernel, keep the grouped one for shapes the cluster cannot take (> 8 key tiles, > 64 rows per KV group)
-  // tcgen05 kernel first (measured 2-3x faster than the mma.sync cluster kernel at the denoise shape)
+  // tcgen05 kernels for every shape of the full-size models (denoise step, SigLIP tower, verifier trunk); the exact
+  // mma.sync kernels below serve the remaining shapes (other head dims, > 768 keys) - one fallback, no algorithm menu
   if ((c.algo == 0 || c.algo == 3) && attention_decode_umma_eligible(c)) return attention_decode_umma(st, c);
   if ((c.algo == 0 || c.algo == 3) && c.k1 == nullptr && attention_mha_umma_eligible(c)) return attention_mha_umma(st, c);
   if ((c.algo == 0 || c.algo == 3) && c.k1 == nullptr && attention_mha_long_umma_eligible(c)) return attention_mha_long_umma(st, c);
   CVB_REQUIRE(c.algo != 3 && c.q_part == nullptr && c.kv1_cached_k == nullptr && c.kv1_cache_out_k == nullptr,
               "shape not eligible for a tcgen05 attention kernel");
-  if (c.k1 != nullptr && c.algo != 1 && attention_decode_eligible(c)) return attention_decode(st, c, c.rope);
-  if (c.k1 != nullptr && c.algo != 2 && attention_group_eligible(c)) return attention_group(st, c);
   CVB_REQUIRE(c.rope == nullptr, "fused RoPE needs the cluster decode attention (shape not eligible)");
   CVB_REQUIRE(c.heads % c.kv_heads == 0, "heads must be a multiple of kv_heads");
   CVB_REQUIRE(c.batches > 0 && c.tq > 0, "empty attention");

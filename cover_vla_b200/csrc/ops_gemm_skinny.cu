@@ -108,7 +108,7 @@ int gemm_skinny(cudaStream_t st, const GemmCall& c, int force_split) {
 
 // Split-K GEMM with fp32 partials in global memory (no cluster): C = fp32 [S][M][ldc], consumed by rmsnorm_reduce().
 // Returns the number of splits actually used through *splits_out (<= requested; every split owns >= 1 k-block).
-int gemm_splitk_partial(cudaStream_t st, const GemmCall& c, int splits, int* splits_out, const SplitKNorm* norm) {
+int gemm_splitk_partial(cudaStream_t st, const GemmCall& c, int splits, int* splits_out) {
   CVB_REQUIRE(c.M > 0 && c.M <= 256, "split-K partial GEMM handles 1..256 activation rows");
   CVB_REQUIRE(c.K % 8 == 0, "K must be a multiple of 8 (16-byte TMA rows)");
   CVB_REQUIRE(c.m_dev == nullptr && c.bias == nullptr && c.resid == nullptr,
@@ -129,21 +129,13 @@ int gemm_splitk_partial(cudaStream_t st, const GemmCall& c, int splits, int* spl
   const int kbs = (kb_total + S - 1) / S;
   g.stages = std::max(1, std::min(std::min(kbs, 5), (kSmemBudget - 1024) / stage_bytes));
   g.tmem_cols = g.Mp <= 32 ? 32 : g.Mp <= 64 ? 64 : g.Mp <= 128 ? 128 : 256;
-  g.fuse_norm = 0, g.resid = nullptr, g.resid_is_f32 = 0, g.ldr = 0, g.nw = nullptr, g.nw_is_f32 = 0;
-  g.h_out = nullptr, g.ldh = 0, g.y = nullptr, g.ldy = 0, g.eps = 0.f, g.sync = nullptr;
-  if (norm != nullptr) {
-    // the in-kernel grid barrier needs every CTA resident at once: at most one CTA per SM; rows staged in the dead ring
-    CVB_REQUIRE(n_tiles * S <= device_sm_count(), "fused norm: the split-K grid must fit one wave");
-    CVB_REQUIRE(c.N % 4 == 0 && 4L * c.N * 4 <= static_cast<long>(g.stages) * stage_bytes, "fused norm: row staging does not fit");
-    CVB_REQUIRE(norm->sync != nullptr && norm->resid != nullptr && norm->w != nullptr, "fused norm: null argument");
-    g.fuse_norm = 1, g.resid = norm->resid, g.resid_is_f32 = norm->resid_is_f32, g.ldr = norm->ldr;
-    g.nw = norm->w, g.nw_is_f32 = norm->w_is_f32, g.h_out = norm->h_out, g.ldh = norm->ldh, g.y = norm->y, g.ldy = norm->ldy;
-    g.eps = norm->eps, g.sync = norm->sync;
-  }
   CUtensorMap tmW, tmA;
   CVB_TRY(get_tmap_cached(c.W, c.N, c.K, c.ldw, 128, &tmW));
   CVB_TRY(get_tmap_cached(c.A, c.M, c.K, c.lda, g.Mp, &tmA));
-  const int smem = 1024 + g.stages * stage_bytes + (2 * g.stages + 1) * 8 + 16;
+  CVB_REQUIRE(c.N % 4 == 0 && c.ldc % 4 == 0, "split-K partial GEMM needs 4-element aligned output rows");
+  // the ring doubles as the transposed output tile (Mp rows x 128 features, fp32) once the MMAs have retired
+  const int ring = std::max(g.stages * stage_bytes, g.Mp * 512);
+  const int smem = 1024 + ring + (2 * g.stages + 1) * 8 + 16;
   CVB_TRY(ensure_dyn_smem(gemm_splitk_partial_tcgen05<0>, smem));
   CVB_TRY(launch_pdl(gemm_splitk_partial_tcgen05<0>, dim3(n_tiles * S), dim3(SK_THREADS), smem, st, 1, tmW, tmA, g));
   CVB_LAUNCHED();

@@ -16,7 +16,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float block_sum(float v, float* red) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   v = warp_sum(v);
-  __syncthreads();
+  __syncthreads();  // `red` may still be read by a previous reduction of the same kernel
   if (lane == 0) red[warp] = v;
   __syncthreads();
   const int nw = (blockDim.x + 31) >> 5;
@@ -124,48 +124,85 @@ __global__ void __launch_bounds__(256) rmsnorm_reduce_kernel(const float* __rest
                                                              long ldp, const void* resid, long ldr,
                                                              const void* __restrict__ w, bf16* h_out, long ldh,
                                                              bf16* __restrict__ y, long ldy, int width, float eps) {
-  pdl_wait();
-  pdl_launch();
+  // loads that do not depend on the preceding kernel (norm weight) are issued before the dependency wait
   extern __shared__ float hrow[];  // the new residual row (bf16 values held as fp32)
   __shared__ float red[32];
   const int row = blockIdx.x;
+  const bool one = width <= static_cast<int>(blockDim.x) * 4;  // one float4 per thread: everything stays in registers
+  const int i0 = threadIdx.x * 4;
+  float wreg[4] = {0.f, 0.f, 0.f, 0.f};
+  if (one && i0 < width) {
+    if constexpr (W_F32) {
+      const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(w) + i0);
+      wreg[0] = v.x, wreg[1] = v.y, wreg[2] = v.z, wreg[3] = v.w;
+    } else {
+      const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(w) + i0);
+      const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y);
+      wreg[0] = f0.x, wreg[1] = f0.y, wreg[2] = f1.x, wreg[3] = f1.y;
+    }
+  }
+  pdl_wait();
+  pdl_launch();
   const float* pr = P + row * ldp;
   float ss = 0.f;
-  for (int i = threadIdx.x * 4; i < width; i += blockDim.x * 4) {
+  float hreg[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = i0; i < width; i += blockDim.x * 4) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float rr[4];
+    // residual first, then ALL partials of this element group in flight at once (up to 8 per round), summed in split
+    // order - the order (and therefore every bit) is the same as a one-at-a-time loop
+    float4 rv4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint2 rv2 = make_uint2(0u, 0u);
+    if constexpr (R_F32)
+      rv4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(resid) + row * ldr + i);
+    else
+      rv2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(resid) + row * ldr + i);
     int s = 0;
-    for (; s + 4 <= S; s += 4) {  // four independent loads in flight, summed in split order
-      const float4 a0 = *reinterpret_cast<const float4*>(pr + (s + 0) * split_stride + i);
-      const float4 a1 = *reinterpret_cast<const float4*>(pr + (s + 1) * split_stride + i);
-      const float4 a2 = *reinterpret_cast<const float4*>(pr + (s + 2) * split_stride + i);
-      const float4 a3 = *reinterpret_cast<const float4*>(pr + (s + 3) * split_stride + i);
-      acc.x = (((acc.x + a0.x) + a1.x) + a2.x) + a3.x;
-      acc.y = (((acc.y + a0.y) + a1.y) + a2.y) + a3.y;
-      acc.z = (((acc.z + a0.z) + a1.z) + a2.z) + a3.z;
-      acc.w = (((acc.w + a0.w) + a1.w) + a2.w) + a3.w;
+    for (; s + 8 <= S; s += 8) {
+      float4 a[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = *reinterpret_cast<const float4*>(pr + (s + j) * split_stride + i);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc.x += a[j].x, acc.y += a[j].y, acc.z += a[j].z, acc.w += a[j].w;
+    }
+    if (s + 4 <= S) {
+      float4 a[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[j] = *reinterpret_cast<const float4*>(pr + (s + j) * split_stride + i);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc.x += a[j].x, acc.y += a[j].y, acc.z += a[j].z, acc.w += a[j].w;
+      s += 4;
     }
     for (; s < S; ++s) {
       const float4 a = *reinterpret_cast<const float4*>(pr + s * split_stride + i);
       acc.x += a.x, acc.y += a.y, acc.z += a.z, acc.w += a.w;
     }
-    float rr[4];
     if constexpr (R_F32) {
-      const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(resid) + row * ldr + i);
-      rr[0] = v.x, rr[1] = v.y, rr[2] = v.z, rr[3] = v.w;
+      rr[0] = rv4.x, rr[1] = rv4.y, rr[2] = rv4.z, rr[3] = rv4.w;
     } else {
-      const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(resid) + row * ldr + i);
-      const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y);
+      const float2 f0 = unpack_bf16x2(rv2.x), f1 = unpack_bf16x2(rv2.y);
       rr[0] = f0.x, rr[1] = f0.y, rr[2] = f1.x, rr[3] = f1.y;
     }
     const float hv[4] = {bf16_round(bf16_round(acc.x) + rr[0]), bf16_round(bf16_round(acc.y) + rr[1]),
                          bf16_round(bf16_round(acc.z) + rr[2]), bf16_round(bf16_round(acc.w) + rr[3])};
     *reinterpret_cast<uint2*>(h_out + row * ldh + i) = make_uint2(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]));
-    *reinterpret_cast<float4*>(hrow + i) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+    if (one) {
+      hreg[0] = hv[0], hreg[1] = hv[1], hreg[2] = hv[2], hreg[3] = hv[3];
+    } else {
+      *reinterpret_cast<float4*>(hrow + i) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+    }
     ss += hv[0] * hv[0] + hv[1] * hv[1] + hv[2] * hv[2] + hv[3] * hv[3];
   }
   ss = block_sum(ss, red);
   const float r = 1.0f / sqrtf(ss / static_cast<float>(width) + eps);
   bf16* yr = y + row * ldy;
+  if (one) {
+    if (i0 < width)
+      *reinterpret_cast<uint2*>(yr + i0) =
+          make_uint2(pack_bf16x2((hreg[0] * r) * (1.0f + wreg[0]), (hreg[1] * r) * (1.0f + wreg[1])),
+                     pack_bf16x2((hreg[2] * r) * (1.0f + wreg[2]), (hreg[3] * r) * (1.0f + wreg[3])));
+    return;
+  }
   for (int i = threadIdx.x * 4; i < width; i += blockDim.x * 4) {  // each thread re-reads its own hrow entries
     const float4 hv = *reinterpret_cast<const float4*>(hrow + i);
     float wv[4];

@@ -74,7 +74,8 @@ CVB_API int cvb_op_sgemm_f32(const float* A, int64_t lda, const float* W, int64_
  * paligemma_with_expert.py:376-434): q [batches, tq, heads*head_dim] (strides q_bs / q_rs in elements), keys in two
  * segments - segment 0 shared per kv batch (kv batch = batch / q_per_kv_batch; length from kv0_len_dev[kv batch] or
  * kv0_len), segment 1 per batch (e.g. the suffix tokens' own keys) with the pi0 suffix mask when suffix_mask = 1.
- * force_two_pass: 0 auto, 1 two-pass fallback, 2 rephrase-grouped kernel only, 3 cluster split-KV kernel only.
+ * force_two_pass: 0 auto (tcgen05 kernel when the shape allows it, else the exact mma.sync kernel), 1 the two-pass variant
+ * of the mma.sync kernel, 4 tcgen05 only (error if the shape is not eligible).
  * rope_cos_sin (optional, f32 [kv batches, tq, head_dim/2, 2]): RoPE applied to q and the segment-1 keys while staging. */
 CVB_API int cvb_op_attention(const void* q, int64_t q_bs, int64_t q_rs, const void* k0, const void* v0, int64_t kv0_bs,
                              int64_t kv0_rs, const int32_t* kv0_len_dev, int kv0_len, int kv0_max,

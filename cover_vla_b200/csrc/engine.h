@@ -113,6 +113,7 @@ struct Pi0State {
   bf16* pos_tiled = nullptr;  // SigLIP position embedding repeated per observation (max_observations > 1)
   bf16 *hp = nullptr, *xp = nullptr, *qkv_p = nullptr, *attn_p = nullptr, *act_p = nullptr;
   bf16 *kcache = nullptr, *vcache = nullptr;
+  bf16 *w_out3 = nullptr, *a2s = nullptr;  // action_time_mlp_out as [hi | lo | hi] bf16, its input as [hi | hi | lo]
   float *state_emb = nullptr, *a1 = nullptr, *a2 = nullptr, *suffix = nullptr, *v0 = nullptr;
   bf16 *he = nullptr, *xe = nullptr, *qkv_e = nullptr, *attn_e = nullptr, *act_e = nullptr;
   bf16 *state_k = nullptr, *state_v = nullptr;  // [layers][candidates][head_dim]: the suffix state token's rotated K / V (F7 hoist)

@@ -324,6 +324,16 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
   CVB_TRY(dalloc_t(h, &s.state_v, (size_t)c.layers * Nm * c.head_dim));
   CVB_TRY(dalloc_t(h, &s.a1, Ma * We));
   CVB_TRY(dalloc_t(h, &s.a2, Ma * We));
+  // action_time_mlp_out (fp32 in the reference, modeling_pi0.py:607-609) on the tensor cores with fp32 accuracy: 3-term
+  // bf16 split (ops_misc.cu split3_rows), [hi | lo | hi] weights once, [hi | hi | lo] activations per step; the fp32
+  // SIMT GEMM it replaces took 36 us of every Euler step.  CVB_SUFFIX_SIMT=1 keeps the SIMT kernel.
+  if (getenv("CVB_SUFFIX_SIMT") == nullptr && We % 8 == 0) {
+    const float* w_out_f32 = nullptr;
+    CVB_TRY(W(h, "action_time_mlp_out.weight", CVB_F32, (int64_t)We * We, &w_out_f32));
+    CVB_TRY(dalloc_t(h, &s.w_out3, (size_t)We * 3 * We));
+    CVB_TRY(split3_rows(st, w_out_f32, We, s.w_out3, We, We, 1));
+    CVB_TRY(dalloc_t(h, &s.a2s, std::min<size_t>(Ma, 256) * 3 * We));
+  }
   CVB_TRY(dalloc_t(h, &s.suffix, Me * We));
   CVB_TRY(dalloc_t(h, &s.he, Me * We));
   CVB_TRY(dalloc_t(h, &s.xe, Me * We));
@@ -560,10 +570,22 @@ static int run_denoise(cvb_handle* h, cudaStream_t st, int B, int Rpo, int K) {
       }
       g2.C = s.a2, g2.ldc = We, g2.row_bias = s.time_vec + step * We, g2.act = SACT_SILU;
       CVB_TRY(sgemm_f32(st, g2));
+      // (latency handles only: on a batch-capable handle a row's arithmetic must not depend on the number of observations)
+      if (s.w_out3 != nullptr && Ma <= 256 && h->max_obs() == 1) {  // 3-term bf16 split-K GEMM + fp32 reduce (+ bias, row layout)
+        CVB_TRY(split3_rows(st, s.a2, We, s.a2s, Ma, We, 0));
+        GemmCall gt;
+        gt.A = s.a2s, gt.lda = 3 * We, gt.W = s.w_out3, gt.ldw = 3 * We, gt.M = Ma, gt.N = We, gt.K = 3 * We;
+        gt.C = s.part_e, gt.ldc = We;
+        int used = 0;
+        CVB_TRY(gemm_splitk_partial(st, gt, kMaxSplitK, &used));
+        CVB_TRY(partial_reduce_f32(st, s.part_e, used, (long)Ma * We, We, b_out, s.suffix, We, Ma, We,
+                                   hoisted ? 0 : c.chunk_size));
+      } else {
       SgemmCall g3;
       g3.A = s.a2, g3.lda = We, g3.W = w_out, g3.ldw = We, g3.M = Ma, g3.N = We, g3.K = We;
       g3.C = s.suffix, g3.ldc = We, g3.bias = b_out, g3.out_group = hoisted ? 0 : c.chunk_size;
       CVB_TRY(sgemm_f32(st, g3));
+      }
     }
     if (mega) {
       const int Mmax = h->rm_total() * c.max_samples * S;

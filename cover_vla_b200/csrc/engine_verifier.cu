@@ -7,6 +7,7 @@
 // is computed once per call (not N times), the last vision block stops after attn.proj, the text
 // tower applies ln_final + text_projection to every token.
 #include <cmath>
+#include <cstdlib>
 
 #include "engine.h"
 #include "gemm_tcgen05.cuh"
@@ -20,6 +21,8 @@ struct TrunkBlock {
 };
 struct TrajLayer {
   const float *w_in, *b_in, *wo, *bo, *w1, *b1, *w2, *b2, *n1w, *n1b, *n2w, *n2b;
+  // [hi | lo | hi] bf16 copies of the four weight matrices: the B operands of the 3-term bf16 tensor-core GEMMs
+  bf16 *w_in3 = nullptr, *wo3 = nullptr, *w13 = nullptr, *w23 = nullptr;
 };
 struct MemberW {
   const float *temp, *pos_emb, *w_ss, *b_ss;
@@ -49,6 +52,8 @@ struct VerifierState {
   float *Pn = nullptr, *Tn = nullptr, *sim = nullptr, *pe = nullptr, *taf = nullptr, *kv_v = nullptr,
         *kv_t = nullptr, *vtok = nullptr, *ttok = nullptr, *it = nullptr;
   float* it_obs = nullptr;  // [max_observations][members][embed]: what the score kernel reads (slot 0 for single calls)
+  bf16 *txs = nullptr, *tatts = nullptr, *tffs = nullptr;  // [hi | hi | lo] copies of tx / tatt / relu(tff) per member
+  bool traj_tc = false;                                     // trajectory-encoder GEMMs on the tensor cores (3-term bf16 split)
   float *tx = nullptr, *tqkv = nullptr, *tatt = nullptr, *ty = nullptr, *tff = nullptr, *act = nullptr;
   float* scores = nullptr;
   float* gmean = nullptr;
@@ -280,6 +285,13 @@ int verifier_finalize(cvb_handle* h, cudaStream_t st) {
   CVB_TRY(dalloc_t(h, &s.it, (size_t)M * E));
   CVB_TRY(dalloc_t(h, &s.it_obs, (size_t)Bm * M * E));  // image-text embeddings of every observation's context
   const size_t rows = (size_t)Nm * S;
+  // CVB_TRAJ_SIMT=1 keeps the fp32 SIMT GEMMs (A/B testing); the tensor-core path needs 8-element aligned widths
+  s.traj_tc = getenv("CVB_TRAJ_SIMT") == nullptr && E % 8 == 0 && c.vf_traj_ff % 8 == 0;
+  if (s.traj_tc) {
+    CVB_TRY(dalloc_t(h, &s.txs, rows * 3 * E * M));
+    CVB_TRY(dalloc_t(h, &s.tatts, rows * 3 * E * M));
+    CVB_TRY(dalloc_t(h, &s.tffs, rows * 3 * c.vf_traj_ff * M));
+  }
   CVB_TRY(dalloc_t(h, &s.tx, rows * E * M));
   CVB_TRY(dalloc_t(h, &s.tqkv, rows * 3 * E * M));
   CVB_TRY(dalloc_t(h, &s.tatt, rows * E * M));
@@ -374,6 +386,17 @@ int verifier_finalize(cvb_handle* h, cudaStream_t st) {
       CVB_TRY(W(h, q + "norm1.bias", CVB_F32, E, &T.n1b));
       CVB_TRY(W(h, q + "norm2.weight", CVB_F32, E, &T.n2w));
       CVB_TRY(W(h, q + "norm2.bias", CVB_F32, E, &T.n2b));
+      if (s.traj_tc) {
+        const int FF = c.vf_traj_ff;
+        CVB_TRY(dalloc_t(h, &T.w_in3, (size_t)3 * E * 3 * E));
+        CVB_TRY(dalloc_t(h, &T.wo3, (size_t)E * 3 * E));
+        CVB_TRY(dalloc_t(h, &T.w13, (size_t)FF * 3 * E));
+        CVB_TRY(dalloc_t(h, &T.w23, (size_t)E * 3 * FF));
+        CVB_TRY(split3_rows(st, T.w_in, E, T.w_in3, 3 * E, E, 1));
+        CVB_TRY(split3_rows(st, T.wo, E, T.wo3, E, E, 1));
+        CVB_TRY(split3_rows(st, T.w1, E, T.w13, FF, E, 1));
+        CVB_TRY(split3_rows(st, T.w2, FF, T.w23, E, FF, 1));
+      }
     }
   }
   CVB_TRY(dalloc_t(h, &s.chains, chains.size()));
@@ -483,6 +506,32 @@ static int run_member_trajectories(cvb_handle* h, cudaStream_t st, int N, int m)
   float* tff = s.tff + (size_t)m * cap * FF;
   const MemberW& Mw = s.mem[m];
   CVB_TRY(sg(st, s.in_traj, A, Mw.w_ss, A, rows, E, A, tx, E, Mw.b_ss));
+  if (s.traj_tc) {
+    // every linear layer as ONE tcgen05 GEMM over the 3K axis of the [hi | hi | lo] x [hi | lo | hi] operands (fp32
+    // accumulate, fp32 bias, fp32 store): same post-norm layer, same fp32 attention / LayerNorm kernels in between
+    bf16* txs = s.txs + (size_t)m * cap * 3 * E;
+    bf16* tatts = s.tatts + (size_t)m * cap * 3 * E;
+    bf16* tffs = s.tffs + (size_t)m * cap * 3 * FF;
+    auto tc = [&](const bf16* Ap, const bf16* Wp, int Nn, int Kk, float* Cp, const float* bias) {
+      GemmCall g;
+      g.A = Ap, g.lda = 3 * Kk, g.W = Wp, g.ldw = 3 * Kk, g.M = rows, g.N = Nn, g.K = 3 * Kk, g.epi = EPI_F32;
+      g.C = Cp, g.ldc = Nn, g.bias = bias, g.bias_is_f32 = 1;
+      return gemm_bf16(st, g);
+    };
+    CVB_TRY(split3_rows(st, tx, E, txs, rows, E, 0));
+    for (const TrajLayer& T : Mw.traj) {
+      CVB_TRY(tc(txs, T.w_in3, 3 * E, E, tqkv, T.b_in));
+      CVB_TRY(traj_attention(st, tqkv, s.in_traj, tatt, N, S, E, c.vf_pool_heads, A, -5.0f));
+      CVB_TRY(split3_rows(st, tatt, E, tatts, rows, E, 0));
+      CVB_TRY(tc(tatts, T.wo3, E, E, ty, T.bo));
+      CVB_TRY(layernorm_f32(st, ty, tx, T.n1w, T.n1b, tx, rows, E, 1e-5f, txs));
+      CVB_TRY(tc(txs, T.w13, FF, E, tff, T.b1));
+      CVB_TRY(split3_rows(st, tff, FF, tffs, rows, FF, 0, /*relu=*/1));
+      CVB_TRY(tc(tffs, T.w23, E, FF, ty, T.b2));
+      CVB_TRY(layernorm_f32(st, ty, tx, T.n2w, T.n2b, tx, rows, E, 1e-5f, txs));
+    }
+    return masked_mean_l2norm(st, tx, s.in_traj, s.act + (size_t)m * N * E, N, S, E, A, -5.0f);
+  }
   for (const TrajLayer& T : Mw.traj) {
     CVB_TRY(sg(st, tx, E, T.w_in, E, rows, 3 * E, E, tqkv, 3 * E, T.b_in));
     CVB_TRY(traj_attention(st, tqkv, s.in_traj, tatt, N, S, E, c.vf_pool_heads, A, -5.0f));

@@ -73,8 +73,16 @@ int layernorm_reduce(cudaStream_t st, const float* P, int S, long split_stride, 
 int layernorm_bf16(cudaStream_t st, const bf16* x, long ldx, const bf16* w, const bf16* b, bf16* y,
                    long ldy, int rows, int width, float eps);
 // LayerNorm on fp32 rows, fp32 affine (verifier heads); optional residual added BEFORE the norm.
+// y_split (optional): the result also as the [hi | hi | lo] bf16 A operand of the 3-term bf16 GEMM (split3_rows)
 int layernorm_f32(cudaStream_t st, const float* x, const float* resid, const float* w,
-                  const float* b, float* y, int rows, int width, float eps);
+                  const float* b, float* y, int rows, int width, float eps, bf16* y_split = nullptr);
+// fp32-accurate GEMM on the bf16 tensor cores: out[rows, 3K] bf16 = [hi | hi | lo] (mode 0, activations) or [hi | lo | hi]
+// (mode 1, weights) of x[rows, K] fp32, hi = bf16(x), lo = bf16(x - hi); act 1 applies ReLU first.  A GEMM over the 3K
+// axis then evaluates a_hi w_hi + a_hi w_lo + a_lo w_hi with fp32 accumulation (error ~2^-16 relative per product).
+int split3_rows(cudaStream_t st, const float* x, long ldx, bf16* out, long rows, int K, int mode, int act = 0);
+// out[map(m)][n] = sum_s P[s][m][n] + bias[n] (fp32; split order); out_group as in SgemmCall
+int partial_reduce_f32(cudaStream_t st, const float* P, int S, long split_stride, long ldp, const float* bias, float* out,
+                       long ldo, int rows, int N, int out_group);
 
 // ---- observation pre-processing (ops_preprocess.cu) ----------------------------------------------------------
 // cv2.resize(frame_u8_hwc, (dw, dh), INTER_LANCZOS4) bit-exact (+ optional x/255 -> (x - 0.5)/0.5 float32 CHW output)

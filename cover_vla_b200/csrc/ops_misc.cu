@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(128) layernorm_f32_kernel(const float* __restr
                                                             const float* __restrict__ w,
                                                             const float* __restrict__ b,
                                                             float* __restrict__ y, int width,
-                                                            float eps) {
+                                                            float eps, bf16* __restrict__ y_split) {
   pdl_wait();
   pdl_launch();
   __shared__ float red[32];
@@ -412,13 +412,107 @@ __global__ void __launch_bounds__(128) layernorm_f32_kernel(const float* __restr
   }
   const float var = block_sum(vs, red) / static_cast<float>(width);
   const float rstd = 1.0f / sqrtf(var + eps);
-  for (int i = threadIdx.x; i < width; i += blockDim.x)
-    y[off + i] = (rowbuf[i] - mean) * rstd * w[i] + b[i];
+  bf16* ys = y_split != nullptr ? y_split + static_cast<long>(blockIdx.x) * 3 * width : nullptr;
+  for (int i = threadIdx.x; i < width; i += blockDim.x) {
+    const float v = (rowbuf[i] - mean) * rstd * w[i] + b[i];
+    y[off + i] = v;
+    if (ys != nullptr) {  // [hi | hi | lo]: the A operand of the 3-term bf16 GEMM (split3_rows)
+      const bf16 hi = __float2bfloat16_rn(v);
+      const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      ys[i] = hi, ys[width + i] = hi, ys[2 * width + i] = lo;
+    }
+  }
 }
 
 int layernorm_f32(cudaStream_t st, const float* x, const float* resid, const float* w,
-                  const float* b, float* y, int rows, int width, float eps) {
-  CVB_TRY(launch_pdl(layernorm_f32_kernel, dim3(rows), dim3(128), width * sizeof(float), st, 1, x, resid, w, b, y, width, eps));
+                  const float* b, float* y, int rows, int width, float eps, bf16* y_split) {
+  CVB_TRY(launch_pdl(layernorm_f32_kernel, dim3(rows), dim3(128), width * sizeof(float), st, 1, x, resid, w, b, y, width, eps,
+                     y_split));
+  CVB_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32-accurate GEMMs on the bf16 tensor cores (round 2): x = hi + lo + O(2^-17 |x|) with hi = bf16(x), lo = bf16(x - hi),
+// so  a . w = a_hi w_hi + a_hi w_lo + a_lo w_hi + O(2^-16 |a||w|)  - three bf16 products accumulated in fp32 by ONE
+// tcgen05 GEMM over a K axis of length 3K:  A' = [a_hi | a_hi | a_lo],  W' = [w_hi | w_lo | w_hi].  The dropped terms
+// are below the fp32 rounding of a K = 512 .. 1024 dot product accumulated in another order, two orders of magnitude
+// under the score tolerance.  Replaces the fp32 SIMT GEMMs of the verifier's trajectory encoder
+// (efficient_ensemble_merged.py:229-245) and of action_time_mlp_out (modeling_pi0.py:607-609): 20-48 us each.
+// mode 0: activation layout [hi | hi | lo]; mode 1: weight layout [hi | lo | hi]; act 1: ReLU applied first.
+__global__ void __launch_bounds__(256) split3_rows_kernel(const float* __restrict__ x, long ldx, bf16* __restrict__ out,
+                                                          int K, int mode, int act, long total) {
+  pdl_wait();
+  pdl_launch();
+  const long i = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= total) return;
+  const long r = i / K;
+  const int k = static_cast<int>(i % K);  // K % 4 == 0: the four elements share a row
+  const float4 v4 = *reinterpret_cast<const float4*>(x + r * ldx + k);
+  float v[4] = {v4.x, v4.y, v4.z, v4.w};
+  uint32_t hi2[2], lo2[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    float a = v[2 * e], b = v[2 * e + 1];
+    if (act == 1) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
+    const float ah = bf16_round(a), bh = bf16_round(b);
+    hi2[e] = pack_bf16x2(ah, bh);
+    lo2[e] = pack_bf16x2(a - ah, b - bh);
+  }
+  bf16* o = out + r * 3 * K + k;
+  const uint2 H = make_uint2(hi2[0], hi2[1]), L = make_uint2(lo2[0], lo2[1]);
+  *reinterpret_cast<uint2*>(o) = H;
+  *reinterpret_cast<uint2*>(o + K) = mode == 0 ? H : L;
+  *reinterpret_cast<uint2*>(o + 2 * K) = mode == 0 ? L : H;
+}
+
+int split3_rows(cudaStream_t st, const float* x, long ldx, bf16* out, long rows, int K, int mode, int act) {
+  CVB_REQUIRE(K % 4 == 0 && ldx % 4 == 0, "split3_rows needs 4-element aligned rows");
+  const long total = rows * K;
+  CVB_TRY(launch_pdl(split3_rows_kernel, dim3(static_cast<unsigned>((total / 4 + 255) / 256)), dim3(256), 0, st, 1, x, ldx, out, K,
+                     mode, act, total));
+  CVB_LAUNCHED();
+  return 0;
+}
+
+// out[map(m)][n] = sum_s P[s][m][n] (split order) + bias[n]; map = the suffix layout of sgemm's out_group (0 = identity)
+__global__ void __launch_bounds__(256) partial_reduce_f32_kernel(const float* __restrict__ P, int S, long split_stride, long ldp,
+                                                                 const float* __restrict__ bias, float* __restrict__ out,
+                                                                 long ldo, int N, int out_group, long total) {
+  pdl_wait();
+  pdl_launch();
+  const long i = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= total) return;
+  const long m = i / N;
+  const int n = static_cast<int>(i % N);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* p = P + m * ldp + n;
+  int s = 0;
+  for (; s + 8 <= S; s += 8) {
+    float4 a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = *reinterpret_cast<const float4*>(p + (s + j) * split_stride);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc.x += a[j].x, acc.y += a[j].y, acc.z += a[j].z, acc.w += a[j].w;
+  }
+  for (; s < S; ++s) {
+    const float4 a = *reinterpret_cast<const float4*>(p + s * split_stride);
+    acc.x += a.x, acc.y += a.y, acc.z += a.z, acc.w += a.w;
+  }
+  if (bias != nullptr) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + n);
+    acc.x += b.x, acc.y += b.y, acc.z += b.z, acc.w += b.w;
+  }
+  const long mo = out_group > 0 ? (m / out_group) * (out_group + 1) + 1 + m % out_group : m;
+  *reinterpret_cast<float4*>(out + mo * ldo + n) = acc;
+}
+
+int partial_reduce_f32(cudaStream_t st, const float* P, int S, long split_stride, long ldp, const float* bias, float* out,
+                       long ldo, int rows, int N, int out_group) {
+  CVB_REQUIRE(N % 4 == 0 && ldp % 4 == 0 && ldo % 4 == 0 && split_stride % 4 == 0, "partial_reduce_f32 needs 4-element aligned rows");
+  const long total = static_cast<long>(rows) * N;
+  CVB_TRY(launch_pdl(partial_reduce_f32_kernel, dim3(static_cast<unsigned>((total / 4 + 255) / 256)), dim3(256), 0, st, 1, P, S,
+                     split_stride, ldp, bias, out, ldo, N, out_group, total));
   CVB_LAUNCHED();
   return 0;
 }

@@ -71,6 +71,12 @@ int cvb_op_sgemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, i
   return cvb::sgemm_f32((cudaStream_t)stream, c);
 }
 
+int cvb_op_split3_f32(const float* x, int64_t ldx, void* out_bf16, int64_t rows, int K, int weight_layout, int relu,
+                      void* stream) {
+  return cvb::split3_rows((cudaStream_t)stream, x, ldx, reinterpret_cast<cvb::bf16*>(out_bf16), rows, K, weight_layout ? 1 : 0,
+                          relu ? 1 : 0);
+}
+
 int cvb_op_attention_tc(const void* q, int64_t q_bs, int64_t q_rs, const void* k0, const void* v0, int64_t kv0_bs,
                         int64_t kv0_rs, const int32_t* kv0_len_dev, int kv0_len, int kv0_max, int q_per_kv_batch,
                         const void* k1, const void* v1, int64_t kv1_bs, int64_t kv1_rs, int kv1_len, int suffix_mask,

@@ -38,6 +38,19 @@ def gemm_bf16(a, w, *, epilogue=EPI_STORE, bias=None, resid=None, out=None, n_ou
     return out
 
 
+def split3_f32(x, weight_layout=False, relu=False):
+    """fp32 [rows, K] -> bf16 [rows, 3K]: [hi | hi | lo] (activations) or [hi | lo | hi] (weights), hi = bf16(x), lo = bf16(x - hi).
+    gemm_bf16(split3(a), split3(w, weight_layout=True), epilogue=EPI_F32) is an fp32-accurate a @ w^T on the tensor cores."""
+    lib = _lib.load()
+    assert x.dtype == torch.float32 and x.is_cuda and x.stride(-1) == 1 and x.dim() == 2
+    rows, K = x.shape
+    out = torch.empty(rows, 3 * K, device=x.device, dtype=torch.bfloat16)
+    lib.cvb_op_split3_f32.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    _lib.check(lib.cvb_op_split3_f32(_lib.ptr(x), x.stride(0), _lib.ptr(out), rows, K, int(weight_layout), int(relu),
+                                     _lib.stream_ptr()))
+    return out
+
+
 def gemm_splitk_partial(a, w, splits):
     """fp32 partial products [S, M, N] of a[M, K] @ w[N, K]^T, K split into S balanced runs of 64-wide blocks."""
     M, K = a.shape

@@ -70,6 +70,15 @@ CVB_API int cvb_op_sgemm_f32(const float* A, int64_t lda, const float* W, int64_
                              int64_t ldc, const float* bias, const float* row_bias, const float* resid, int64_t ldr,
                              int act, void* stream);
 
+/* fp32-accurate linear layers on the bf16 tensor cores: out bf16 [rows, 3K] = [hi | hi | lo] of x fp32 [rows, K]
+ * (activation layout; weight_layout = 1: [hi | lo | hi]), hi = bf16(x), lo = bf16(x - hi); relu = 1 applies ReLU first.
+ * cvb_op_gemm_bf16 (epilogue 4, fp32 bias) over the 3K axis of an activation-layout A and a weight-layout W then evaluates
+ * a_hi w_hi + a_hi w_lo + a_lo w_hi with fp32 accumulation: relative error ~1e-5 of |a||w| per product, far below the
+ * 1e-3 score tolerance.  Used for the verifier's trajectory encoder (efficient_ensemble_merged.py:229-245) and
+ * action_time_mlp_out (modeling_pi0.py:607-609), which the reference keeps in float32. */
+CVB_API int cvb_op_split3_f32(const float* x, int64_t ldx, void* out_bf16, int64_t rows, int K, int weight_layout, int relu,
+                              void* stream);
+
 /* Exact-softmax attention with the reference's rounding ledger (eager_attention_forward,
  * paligemma_with_expert.py:376-434): q [batches, tq, heads*head_dim] (strides q_bs / q_rs in elements), keys in two
  * segments - segment 0 shared per kv batch (kv batch = batch / q_per_kv_batch; length from kv0_len_dev[kv batch] or

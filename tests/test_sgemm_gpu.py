@@ -43,3 +43,29 @@ def test_sgemm_strided_and_plain():
     torch.cuda.synchronize()
     z = a.double() @ w.double().t()
     assert (y.double() - z).abs().max().item() < 5e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(400, 1536, 512), (400, 512, 1024), (160, 1024, 1024), (40, 512, 512)])
+def test_three_term_bf16_split_gemm_is_fp32_accurate(M, N, K):
+    """The tensor-core replacement of the fp32 SIMT GEMMs (verifier trajectory encoder, action_time_mlp_out): a_hi w_hi +
+    a_hi w_lo + a_lo w_hi accumulated in fp32 by one bf16 tcgen05 GEMM over the 3K axis.  Error budget: measured against a
+    float64 product it must stay within 4x the fp32 SIMT kernel's own error and below 3e-5 of the row/column norms -
+    two orders of magnitude under the 1e-3 score tolerance."""
+    from cover_vla_b200 import ops
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") / K ** 0.5
+    bias = torch.randn(N, device="cuda")
+    a3, w3 = ops.split3_f32(a), ops.split3_f32(w, weight_layout=True)
+    assert a3.shape == (M, 3 * K) and torch.equal(a3[:, :K], a.to(torch.bfloat16)) and torch.equal(a3[:, :K], a3[:, K:2 * K])
+    assert torch.equal(w3[:, :K], w3[:, 2 * K:]) and torch.equal(w3[:, K:2 * K], (w - w3[:, :K].float()).to(torch.bfloat16))
+    out = ops.gemm_bf16(a3, w3, epilogue=ops.EPI_F32, bias=bias)
+    ref = (a.double() @ w.double().T + bias.double())
+    scale = (a.double().norm(dim=1)[:, None] * w.double().norm(dim=1)[None, :])
+    err_tc = ((out.double() - ref).abs() / scale).max().item()
+    simt = ops.sgemm_f32(a, w, bias=bias)
+    err_simt = ((simt.double() - ref).abs() / scale).max().item()
+    print(f"{M}x{N}x{K}: 3-term bf16 split {err_tc:.2e} vs fp32 SIMT {err_simt:.2e} (relative to |a||w|)")
+    assert err_tc < 3e-5 and err_tc < max(4 * err_simt, 2e-6)
+    relu = ops.split3_f32(a, relu=True)
+    assert torch.equal(relu[:, :K], a.clamp_min(0).to(torch.bfloat16))

@@ -116,14 +116,54 @@ int add_f32(cudaStream_t st, const float* a, const float* b, float* y, long n) {
 // AttentionPooling with one learned query (model.py:76-112): the whole 4-block chain for one pooling
 // in ONE CTA (K/V projections of all blocks are precomputed by one GEMM since they do not depend on q).
 namespace {
+// ---- thread-block cluster plumbing: a pooling chain is a SERIAL chain of 16 matrix-vector products (1 MB of fp32 weights
+// each).  One CTA per chain (round 1: 6 CTAs on a 148-SM part, 1.0 ms) streams them at ~16 GB/s; a cluster of kPoolCluster
+// CTAs per chain splits every product by output rows and broadcasts its slice of the result into every CTA's shared
+// memory (st.shared::cluster), one cluster barrier per product.
+constexpr int kPoolCluster = 8;
+__device__ __forceinline__ uint32_t cl_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cl_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cl_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// out[o] = v in the shared memory of EVERY CTA of the cluster (same offset in each)
+__device__ __forceinline__ void cl_store_all(float* out_local, int o, float v, uint32_t ncta) {
+  const uint32_t a = smem_u32(out_local + o);
+  for (uint32_t p = 0; p < ncta; ++p) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(p));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(r), "f"(v) : "memory");
+  }
+}
+
+// out = W in + bias.  ncta == 1: the whole product in this CTA (then __syncthreads).  ncta > 1: this CTA computes rows
+// [rank * n_out / ncta, (rank + 1) * n_out / ncta), stores them into every CTA of the cluster and the cluster syncs.
+// The arithmetic of one output row is the same in both modes (bit-identical results).
 __device__ void matvec(float* __restrict__ out, const float* __restrict__ W, const float* __restrict__ in,
-                       const float* __restrict__ bias, int n_out, int n_in) {
+                       const float* __restrict__ bias, int n_out, int n_in, uint32_t rank = 0, uint32_t ncta = 1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int o_begin = static_cast<int>(static_cast<long>(rank) * n_out / ncta);
+  const int o_end = static_cast<int>(static_cast<long>(rank + 1) * n_out / ncta);
+  auto put = [&](int o, float v) {
+    if (ncta > 1)
+      cl_store_all(out, o, v, ncta);
+    else
+      out[o] = v;
+  };
   if ((n_in & 127) == 0) {
     // two output rows per warp iteration, float4 loads: 8+ independent 16-byte loads in flight per lane
-    for (int o = warp * 2; o < n_out; o += nw * 2) {
+    for (int o = o_begin + warp * 2; o < o_end; o += nw * 2) {
       const float4* w0 = reinterpret_cast<const float4*>(W + static_cast<long>(o) * n_in);
-      const float4* w1 = reinterpret_cast<const float4*>(W + static_cast<long>(min(o + 1, n_out - 1)) * n_in);
+      const float4* w1 = reinterpret_cast<const float4*>(W + static_cast<long>(min(o + 1, o_end - 1)) * n_in);
       const float4* x4 = reinterpret_cast<const float4*>(in);
       float a0 = 0.f, a1 = 0.f;
 #pragma unroll 4
@@ -135,20 +175,23 @@ __device__ void matvec(float* __restrict__ out, const float* __restrict__ W, con
       a0 = wsum(a0);
       a1 = wsum(a1);
       if (lane == 0) {
-        out[o] = a0 + (bias != nullptr ? bias[o] : 0.f);
-        if (o + 1 < n_out) out[o + 1] = a1 + (bias != nullptr ? bias[o + 1] : 0.f);
+        put(o, a0 + (bias != nullptr ? bias[o] : 0.f));
+        if (o + 1 < o_end) put(o + 1, a1 + (bias != nullptr ? bias[o + 1] : 0.f));
       }
     }
   } else {
-    for (int o = warp; o < n_out; o += nw) {
+    for (int o = o_begin + warp; o < o_end; o += nw) {
       const float* wr = W + static_cast<long>(o) * n_in;
       float acc = 0.f;
       for (int i = lane; i < n_in; i += 32) acc = fmaf(wr[i], in[i], acc);
       acc = wsum(acc);
-      if (lane == 0) out[o] = acc + (bias != nullptr ? bias[o] : 0.f);
+      if (lane == 0) put(o, acc + (bias != nullptr ? bias[o] : 0.f));
     }
   }
-  __syncthreads();
+  if (ncta > 1)
+    cl_sync();  // every CTA's slice has landed everywhere (release / acquire at cluster scope); also a CTA barrier
+  else
+    __syncthreads();
 }
 __device__ void layernorm_vec(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ w,
                               const float* __restrict__ b, int n, float* red) {
@@ -169,19 +212,25 @@ __global__ void __launch_bounds__(512) pool_chain_kernel(const PoolChain* __rest
   pdl_launch();
   extern __shared__ float sm[];
   __shared__ float red[32];
-  const PoolChain& c = chains[blockIdx.x];
+  const uint32_t ncta = cl_size(), rank = cl_rank();  // cluster of kPoolCluster CTAs per chain (or 1)
+  const PoolChain& c = chains[blockIdx.x / ncta];
   const int E = c.embed, H = c.heads, hd = E / H, T = c.tokens;
   float* q = sm;             // [E]
   float* a = q + E;          // [E]
   float* b = a + E;          // [E]
-  float* prob = b + E;       // [H * T]
+  float* t = b + E;          // [E] attention output projection (its own buffer: see the hazard note below)
+  float* prob = t + E;       // [H * T]
   for (int i = threadIdx.x; i < E; i += blockDim.x) q[i] = c.query[i];
   __syncthreads();
+  // Cluster mode hazard rule: a product's destination is written REMOTELY by fast peers, so it must not be a buffer a
+  // slow peer may still be reading.  a <- Wq q, a <- fc1 q, b <- fc2 a are safe (their destination was last read before
+  // an earlier cluster barrier); the attention reads `a` right before the o-projection, hence t <- Wo b.
+  if (ncta > 1) cl_sync();
   const float qscale = sqrtf(1.0f / static_cast<float>(hd));
   for (int l = 0; l < c.layers; ++l) {
     const PoolBlockW& w = c.blk[l];
     layernorm_vec(q, q, w.qln_w, w.qln_b, E, red);         // q = q_layer_norm(q)
-    matvec(a, w.wq, q, w.b_in, E, E);                       // a = Wq q + bq
+    matvec(a, w.wq, q, w.b_in, E, E, rank, ncta);           // a = Wq q + bq
     for (int i = threadIdx.x; i < E; i += blockDim.x) a[i] *= qscale;
     __syncthreads();
     const float* Kp = c.kv + static_cast<long>(l) * 2 * E;  // K_l at cols [l*2E, l*2E+E), V_l after it
@@ -212,25 +261,28 @@ __global__ void __launch_bounds__(512) pool_chain_kernel(const PoolChain* __rest
       }
     }
     __syncthreads();
-    matvec(a, w.wo, b, w.bo, E, E);                         // attn_out
-    for (int i = threadIdx.x; i < E; i += blockDim.x) q[i] = q[i] + a[i];
+    matvec(t, w.wo, b, w.bo, E, E, rank, ncta);             // attn_out
+    for (int i = threadIdx.x; i < E; i += blockDim.x) q[i] = q[i] + t[i];
     __syncthreads();
     layernorm_vec(q, q, w.ln_w, w.ln_b, E, red);            // q = layer_norm(q + attn)
-    matvec(a, w.fc1_w, q, w.fc1_b, E, E);
+    matvec(a, w.fc1_w, q, w.fc1_b, E, E, rank, ncta);
     for (int i = threadIdx.x; i < E; i += blockDim.x)
       a[i] = 0.5f * a[i] * (1.0f + erff(a[i] * 0.70710678118654752440f));
     __syncthreads();
-    matvec(b, w.fc2_w, a, w.fc2_b, E, E);
+    matvec(b, w.fc2_w, a, w.fc2_b, E, E, rank, ncta);
     for (int i = threadIdx.x; i < E; i += blockDim.x) q[i] = q[i] + b[i];
     __syncthreads();
   }
   layernorm_vec(a, q, c.fin_w, c.fin_b, E, red);
-  for (int i = threadIdx.x; i < E; i += blockDim.x) c.out[i] = a[i];
+  if (rank == 0)
+    for (int i = threadIdx.x; i < E; i += blockDim.x) c.out[i] = a[i];
+  if (ncta > 1) cl_sync();  // no CTA may exit while a peer could still address its shared memory
 }
 
 int pool_chains(cudaStream_t st, const PoolChain* chains_dev, int n_chains, int embed, int heads, int tokens) {
-  const size_t smem = (3 * embed + heads * tokens) * sizeof(float);
-  CVB_TRY(launch_pdl(pool_chain_kernel, dim3(n_chains), dim3(512), smem, st, 1, chains_dev));
+  const size_t smem = (4 * embed + heads * tokens) * sizeof(float);
+  const int cl = embed % (2 * kPoolCluster) == 0 ? kPoolCluster : 1;  // every CTA owns an even number of output rows
+  CVB_TRY(launch_pdl(pool_chain_kernel, dim3(n_chains * cl), dim3(512), smem, st, cl, chains_dev));
   CVB_LAUNCHED();
   return 0;
 }
@@ -241,7 +293,8 @@ __global__ void __launch_bounds__(256) it_finalize_kernel(const ItFinal* __restr
   pdl_launch();
   extern __shared__ float sm[];
   __shared__ float red[32];
-  const ItFinal& f = items[blockIdx.x];
+  const uint32_t ncta = cl_size(), rank = cl_rank();
+  const ItFinal& f = items[blockIdx.x / ncta];
   float* in = sm;       // [2E]
   float* out = sm + 2 * E;
   for (int i = threadIdx.x; i < E; i += blockDim.x) {
@@ -249,14 +302,18 @@ __global__ void __launch_bounds__(256) it_finalize_kernel(const ItFinal* __restr
     in[E + i] = f.vision_tok[i];
   }
   __syncthreads();
-  matvec(out, f.w, in, f.b, E, 2 * E);
+  if (ncta > 1) cl_sync();  // every CTA of the cluster is running before any remote store
+  matvec(out, f.w, in, f.b, E, 2 * E, rank, ncta);
   float ss = 0.f;
   for (int i = threadIdx.x; i < E; i += blockDim.x) ss += out[i] * out[i];
   const float nrm = sqrtf(bsum(ss, red));
-  for (int i = threadIdx.x; i < E; i += blockDim.x) f.out[i] = out[i] / nrm;
+  if (rank == 0)
+    for (int i = threadIdx.x; i < E; i += blockDim.x) f.out[i] = out[i] / nrm;
+  if (ncta > 1) cl_sync();
 }
 int it_finalize(cudaStream_t st, const ItFinal* items_dev, int members, int embed) {
-  CVB_TRY(launch_pdl(it_finalize_kernel, dim3(members), dim3(256), 3 * embed * sizeof(float), st, 1, items_dev, embed));
+  const int cl = embed % (2 * kPoolCluster) == 0 ? kPoolCluster : 1;
+  CVB_TRY(launch_pdl(it_finalize_kernel, dim3(members * cl), dim3(256), 3 * embed * sizeof(float), st, cl, items_dev, embed));
   CVB_LAUNCHED();
   return 0;
 }

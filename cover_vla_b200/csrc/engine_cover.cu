@@ -68,7 +68,7 @@ int cover_step(cvb_handle* h, const float* image, const int64_t* lang_tokens, co
     CVB_CUDA(cudaEventRecord(cs.ev_fork, s0));
     CVB_CUDA(cudaStreamWaitEvent(cs.side, cs.ev_fork, 0));
     int rc_side = 0;
-    for (int b = 0; b < B && rc_side == 0; ++b) rc_side = verifier_enqueue_context(h, cs.side, b);
+    rc_side = verifier_enqueue_context(h, cs.side, 0, B);  // every observation's towers and heads in one pass
     CVB_CUDA(cudaEventRecord(cs.ev_join, cs.side));  // always rejoin, even on error, so a capture can end cleanly
     int rc = rc_side;
     if (rc == 0 && B > 1) rc = pi0_enqueue(h, s0, R, K, 0, B);

@@ -35,6 +35,7 @@ struct VerifierState {
   std::vector<TrunkBlock> vis, txt;
   const bf16 *patch_b, *pos_embed, *tok_emb, *txt_pos, *lnf_w, *lnf_b, *wproj, *bproj;
   bf16* w_patch = nullptr;
+  bf16* pos_tiled = nullptr;  // pos_embed repeated max_observations times (residual operand of the batched patch GEMM)
   int kpad = 0;
   std::vector<MemberW> mem;
   float* wkv_t = nullptr;  // owned [M*L*2E, W] text pooling K/V projections of all members
@@ -50,7 +51,7 @@ struct VerifierState {
        *pfeat = nullptr, *ht = nullptr, *tfeat = nullptr;
   // head workspace
   float *Pn = nullptr, *Tn = nullptr, *sim = nullptr, *pe = nullptr, *taf = nullptr, *kv_v = nullptr,
-        *kv_t = nullptr, *vtok = nullptr, *ttok = nullptr, *it = nullptr;
+        *kv_t = nullptr, *vtok = nullptr, *ttok = nullptr;
   float* it_obs = nullptr;  // [max_observations][members][embed]: what the score kernel reads (slot 0 for single calls)
   bf16 *txs = nullptr, *tatts = nullptr, *tffs = nullptr;  // [hi | hi | lo] copies of tx / tatt / relu(tff) per member
   bool traj_tc = false;                                     // trajectory-encoder GEMMs on the tensor cores (3-term bf16 split)
@@ -263,26 +264,33 @@ int verifier_finalize(cvb_handle* h, cudaStream_t st) {
   CVB_TRY(dalloc_t(h, &s.in_image, (size_t)Bm * 3 * c.vf_image * c.vf_image));
   CVB_TRY(dalloc_t(h, &s.in_tokens, (size_t)Bm * Tt));
   CVB_TRY(dalloc_t(h, &s.in_traj, (size_t)Nm * S * c.vf_action_dim));
-  CVB_TRY(dalloc_t(h, &s.patches, (size_t)Np * s.kpad));
-  CVB_TRY(dalloc_t(h, &s.hv, (size_t)Tmax * Wd));
-  CVB_TRY(dalloc_t(h, &s.xv, (size_t)Tmax * Wd));
-  CVB_TRY(dalloc_t(h, &s.qkv, (size_t)Tmax * 3 * Wd));
-  CVB_TRY(dalloc_t(h, &s.att, (size_t)Tmax * Wd));
-  CVB_TRY(dalloc_t(h, &s.mlp, (size_t)Tmax * c.vf_mlp));
-  CVB_TRY(dalloc_t(h, &s.pfeat, (size_t)Np * Wd));
-  CVB_TRY(dalloc_t(h, &s.ht, (size_t)Tt * Wd));
-  CVB_TRY(dalloc_t(h, &s.tfeat, (size_t)Tt * Wd));
+  // the trunk runs all observations of a batched call at once (rows = observations x tokens); the heads keep one slot
+  // per observation so that the pooling chains of every observation run in ONE launch
+  CVB_TRY(dalloc_t(h, &s.patches, (size_t)Bm * Np * s.kpad));
+  CVB_TRY(dalloc_t(h, &s.hv, (size_t)Bm * Tmax * Wd));
+  CVB_TRY(dalloc_t(h, &s.xv, (size_t)Bm * Tmax * Wd));
+  CVB_TRY(dalloc_t(h, &s.qkv, (size_t)Bm * Tmax * 3 * Wd));
+  CVB_TRY(dalloc_t(h, &s.att, (size_t)Bm * Tmax * Wd));
+  CVB_TRY(dalloc_t(h, &s.mlp, (size_t)Bm * Tmax * c.vf_mlp));
+  CVB_TRY(dalloc_t(h, &s.pfeat, (size_t)Bm * Np * Wd));
+  CVB_TRY(dalloc_t(h, &s.ht, (size_t)Bm * Tt * Wd));
+  CVB_TRY(dalloc_t(h, &s.tfeat, (size_t)Bm * Tt * Wd));
+  if (Bm > 1) {
+    CVB_TRY(dalloc_t(h, &s.pos_tiled, (size_t)Bm * Np * Wd));
+    for (int b = 0; b < Bm; ++b)
+      CVB_CUDA(cudaMemcpyAsync(s.pos_tiled + (size_t)b * Np * Wd, s.pos_embed, (size_t)Np * Wd * sizeof(bf16),
+                               cudaMemcpyDeviceToDevice, st));
+  }
   // ---- workspace (heads)
-  CVB_TRY(dalloc_t(h, &s.Pn, (size_t)Np * Wd));
-  CVB_TRY(dalloc_t(h, &s.Tn, (size_t)Tt * Wd));
-  CVB_TRY(dalloc_t(h, &s.sim, (size_t)Tt * Np));
-  CVB_TRY(dalloc_t(h, &s.pe, (size_t)Np * Wd));
-  CVB_TRY(dalloc_t(h, &s.taf, (size_t)M * Tt * Wd));
-  CVB_TRY(dalloc_t(h, &s.kv_v, (size_t)M * Tt * L * 2 * E));
-  CVB_TRY(dalloc_t(h, &s.kv_t, (size_t)Tt * M * L * 2 * E));
-  CVB_TRY(dalloc_t(h, &s.vtok, (size_t)M * E));
-  CVB_TRY(dalloc_t(h, &s.ttok, (size_t)M * E));
-  CVB_TRY(dalloc_t(h, &s.it, (size_t)M * E));
+  CVB_TRY(dalloc_t(h, &s.Pn, (size_t)Bm * Np * Wd));
+  CVB_TRY(dalloc_t(h, &s.Tn, (size_t)Bm * Tt * Wd));
+  CVB_TRY(dalloc_t(h, &s.sim, (size_t)Bm * Tt * Np));
+  CVB_TRY(dalloc_t(h, &s.pe, (size_t)Bm * Np * Wd));
+  CVB_TRY(dalloc_t(h, &s.taf, (size_t)M * Bm * Tt * Wd));          // [member][observation][token][W]
+  CVB_TRY(dalloc_t(h, &s.kv_v, (size_t)M * Bm * Tt * L * 2 * E));  // [member][observation][token][L*2E]
+  CVB_TRY(dalloc_t(h, &s.kv_t, (size_t)Bm * Tt * M * L * 2 * E));  // [observation][token][member][L*2E]
+  CVB_TRY(dalloc_t(h, &s.vtok, (size_t)Bm * M * E));
+  CVB_TRY(dalloc_t(h, &s.ttok, (size_t)Bm * M * E));
   CVB_TRY(dalloc_t(h, &s.it_obs, (size_t)Bm * M * E));  // image-text embeddings of every observation's context
   const size_t rows = (size_t)Nm * S;
   // CVB_TRAJ_SIMT=1 keeps the fp32 SIMT GEMMs (A/B testing); the tensor-core path needs 8-element aligned widths
@@ -314,8 +322,8 @@ int verifier_finalize(cvb_handle* h, cudaStream_t st) {
   s.mem.resize(M);
   CVB_TRY(dalloc_t(h, &s.wkv_t, (size_t)M * L * 2 * E * Wd));
   CVB_TRY(dalloc_t(h, &s.bkv_t, (size_t)M * L * 2 * E));
-  std::vector<PoolChain> chains(2 * M);
-  std::vector<ItFinal> itf(M);
+  std::vector<PoolChain> chains((size_t)Bm * 2 * M);  // [observation][member][vision, text]; slot 0 filled first
+  std::vector<ItFinal> itf((size_t)Bm * M);
   for (int m = 0; m < M; ++m) {
     const std::string b = "verifier." + std::to_string(m) + ".";
     MemberW& Mw = s.mem[m];
@@ -336,7 +344,7 @@ int verifier_finalize(cvb_handle* h, cudaStream_t st) {
       float* wdst = pi == 0 ? Mw.wkv_v : s.wkv_t + (size_t)m * L * 2 * E * Wd;
       float* bdst = pi == 0 ? Mw.bkv_v : s.bkv_t + (size_t)m * L * 2 * E;
       if (pi == 0) {
-        ch.kv = s.kv_v + (size_t)m * Tt * L * 2 * E, ch.kv_ld = L * 2 * E, ch.out = s.vtok + (size_t)m * E;
+        ch.kv = s.kv_v + (size_t)m * Bm * Tt * L * 2 * E, ch.kv_ld = L * 2 * E, ch.out = s.vtok + (size_t)m * E;
       } else {
         ch.kv = s.kv_t + (size_t)m * L * 2 * E, ch.kv_ld = M * L * 2 * E, ch.out = s.ttok + (size_t)m * E;
       }
@@ -367,7 +375,7 @@ int verifier_finalize(cvb_handle* h, cudaStream_t st) {
       }
     }
     ItFinal& f = itf[m];
-    f.text_tok = s.ttok + (size_t)m * E, f.vision_tok = s.vtok + (size_t)m * E, f.out = s.it + (size_t)m * E;
+    f.text_tok = s.ttok + (size_t)m * E, f.vision_tok = s.vtok + (size_t)m * E, f.out = s.it_obs + (size_t)m * E;
     CVB_TRY(W(h, b + "input_projection.weight", CVB_F32, (int64_t)E * 2 * E, &f.w));
     CVB_TRY(W(h, b + "input_projection.bias", CVB_F32, E, &f.b));
     Mw.traj.resize(c.vf_traj_layers);
@@ -399,6 +407,19 @@ int verifier_finalize(cvb_handle* h, cudaStream_t st) {
       }
     }
   }
+  for (int o = 1; o < Bm; ++o) {  // the other observation slots: same weights, their own K/V, token and output rows
+    for (int m = 0; m < M; ++m) {
+      PoolChain& cv = chains[((size_t)o * M + m) * 2];
+      PoolChain& ct = chains[((size_t)o * M + m) * 2 + 1];
+      cv = chains[m * 2], ct = chains[m * 2 + 1];
+      cv.kv = s.kv_v + ((size_t)m * Bm + o) * Tt * L * 2 * E, cv.out = s.vtok + ((size_t)o * M + m) * E;
+      ct.kv = s.kv_t + (size_t)o * Tt * M * L * 2 * E + (size_t)m * L * 2 * E, ct.out = s.ttok + ((size_t)o * M + m) * E;
+      ItFinal& f = itf[(size_t)o * M + m];
+      f = itf[m];
+      f.text_tok = s.ttok + ((size_t)o * M + m) * E, f.vision_tok = s.vtok + ((size_t)o * M + m) * E;
+      f.out = s.it_obs + ((size_t)o * M + m) * E;
+    }
+  }
   CVB_TRY(dalloc_t(h, &s.chains, chains.size()));
   CVB_TRY(dalloc_t(h, &s.itf, itf.size()));
   CVB_CUDA(cudaMemcpyAsync(s.chains, chains.data(), chains.size() * sizeof(PoolChain), cudaMemcpyHostToDevice, st));
@@ -423,9 +444,9 @@ void verifier_destroy(cvb_handle* h) {
 
 // pre-norm transformer block stack on bf16 rows; `stop_after_attn_proj` implements the hook on
 // visual.trunk.blocks[-1].attn (the last block's attention output BEFORE the residual).
-static int run_blocks(cudaStream_t st, VerifierState& s, const std::vector<TrunkBlock>& blocks, bf16* hbuf, int T,
-                      int Wd, int heads, int mlp, bool last_is_attn_only, bf16* attn_only_out) {
-  const int hd = Wd / heads;
+static int run_blocks(cudaStream_t st, VerifierState& s, const std::vector<TrunkBlock>& blocks, bf16* hbuf, int Tseq,
+                      int Wd, int heads, int mlp, bool last_is_attn_only, bf16* attn_only_out, int nb = 1) {
+  const int hd = Wd / heads, T = nb * Tseq;  // T rows through the linear layers, nb attention batches of Tseq tokens
   for (size_t l = 0; l < blocks.size(); ++l) {
     const TrunkBlock& B = blocks[l];
     const bool last = last_is_attn_only && l + 1 == blocks.size();
@@ -433,9 +454,10 @@ static int run_blocks(cudaStream_t st, VerifierState& s, const std::vector<Trunk
     CVB_TRY(gemm(st, s.xv, Wd, B.wqkv, Wd, T, 3 * Wd, Wd, EPI_STORE, s.qkv, 3 * Wd, B.bqkv));
     AttnCall a;
     a.q = s.qkv, a.q_row_stride = 3 * Wd;
-    a.k0 = s.qkv + Wd, a.v0 = s.qkv + 2 * Wd, a.kv0_row_stride = 3 * Wd, a.kv0_len = T;
+    a.k0 = s.qkv + Wd, a.v0 = s.qkv + 2 * Wd, a.kv0_row_stride = 3 * Wd, a.kv0_len = Tseq;
     a.out = s.att, a.o_row_stride = Wd;
-    a.batches = 1, a.heads = heads, a.kv_heads = heads, a.tq = T, a.head_dim = hd;
+    a.q_batch_stride = (long)Tseq * 3 * Wd, a.kv0_batch_stride = (long)Tseq * 3 * Wd, a.o_batch_stride = (long)Tseq * Wd;
+    a.batches = nb, a.heads = heads, a.kv_heads = heads, a.tq = Tseq, a.head_dim = hd;
     a.scale = 1.0f / sqrtf(static_cast<float>(hd));
     CVB_TRY(attention(st, a));
     if (last) {
@@ -450,46 +472,57 @@ static int run_blocks(cudaStream_t st, VerifierState& s, const std::vector<Trunk
   return 0;
 }
 
-// image-text heads of every member (N-independent: SURVEY.md F4) from the normalised features Pn / Tn
-static int run_heads_context(cvb_handle* h, cudaStream_t st, int obs = 0) {
+// image-text heads of every member (N-independent: SURVEY.md F4) from the normalised features Pn / Tn of observations
+// [obs0, obs0 + nb) (rows of Pn / Tn are RELATIVE to obs0; every other buffer is indexed by the absolute slot)
+static int run_heads_context(cvb_handle* h, cudaStream_t st, int obs0 = 0, int nb = 1) {
   const cvb_config& c = h->cfg;
   VerifierState& s = *h->vf;
-  const int Wd = c.vf_width, E = c.vf_embed, L = c.vf_pool_layers, M = c.vf_members;
+  const int Wd = c.vf_width, E = c.vf_embed, L = c.vf_pool_layers, M = c.vf_members, Bm = h->max_obs();
   const int Np = (c.vf_image / c.vf_patch) * (c.vf_image / c.vf_patch), Tt = c.vf_text_ctx;
-  CVB_TRY(sg(st, s.Tn, Wd, s.wkv_t, Wd, Tt, M * L * 2 * E, Wd, s.kv_t, M * L * 2 * E, s.bkv_t));
+  const int L2E = L * 2 * E;
+  // text pooling K/V of every member and observation: one GEMM over nb * Tt rows
+  CVB_TRY(sg(st, s.Tn, Wd, s.wkv_t, Wd, nb * Tt, M * L2E, Wd, s.kv_t + (size_t)obs0 * Tt * M * L2E, M * L2E, s.bkv_t));
   for (int m = 0; m < M; ++m) {
     const MemberW& Mw = s.mem[m];
-    float* taf = s.taf + (size_t)m * Tt * Wd;
-    CVB_TRY(sg(st, s.Tn, Wd, s.Pn, Wd, Tt, Np, Wd, s.sim, Np, nullptr, 0, nullptr, 0, 0, /*w_dynamic=*/1));
-    CVB_TRY(softmax_rows_temp(st, s.sim, Tt, Np, Mw.temp));
-    CVB_TRY(add_f32(st, s.Pn, Mw.pos_emb, s.pe, (long)Np * Wd));
-    CVB_TRY(sg(st, s.sim, Np, s.pe, Wd, Tt, Wd, Np, taf, Wd, nullptr, 0, nullptr, 0, /*w_kn=*/1));
-    CVB_TRY(sg(st, taf, Wd, Mw.wkv_v, Wd, Tt, L * 2 * E, Wd, s.kv_v + (size_t)m * Tt * L * 2 * E, L * 2 * E, Mw.bkv_v));
+    float* taf = s.taf + ((size_t)m * Bm + obs0) * Tt * Wd;
+    for (int o = 0; o < nb; ++o) {
+      const float* Pn = s.Pn + (size_t)o * Np * Wd;
+      const float* Tn = s.Tn + (size_t)o * Tt * Wd;
+      float* sim = s.sim + (size_t)o * Tt * Np;
+      float* pe = s.pe + (size_t)o * Np * Wd;
+      CVB_TRY(sg(st, Tn, Wd, Pn, Wd, Tt, Np, Wd, sim, Np, nullptr, 0, nullptr, 0, 0, /*w_dynamic=*/1));
+      CVB_TRY(softmax_rows_temp(st, sim, Tt, Np, Mw.temp));
+      CVB_TRY(add_f32(st, Pn, Mw.pos_emb, pe, (long)Np * Wd));
+      CVB_TRY(sg(st, sim, Np, pe, Wd, Tt, Wd, Np, taf + (size_t)o * Tt * Wd, Wd, nullptr, 0, nullptr, 0, /*w_kn=*/1));
+    }
+    // vision pooling K/V of this member for every observation: one GEMM over nb * Tt rows
+    CVB_TRY(sg(st, taf, Wd, Mw.wkv_v, Wd, nb * Tt, L2E, Wd, s.kv_v + ((size_t)m * Bm + obs0) * Tt * L2E, L2E, Mw.bkv_v));
   }
-  CVB_TRY(pool_chains(st, s.chains, 2 * M, E, c.vf_pool_heads, Tt));
-  CVB_TRY(it_finalize(st, s.itf, M, E));
-  CVB_CUDA(cudaMemcpyAsync(s.it_obs + (size_t)obs * M * E, s.it, (size_t)M * E * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CVB_TRY(pool_chains(st, s.chains + (size_t)obs0 * 2 * M, nb * 2 * M, E, c.vf_pool_heads, Tt));
+  CVB_TRY(it_finalize(st, s.itf + (size_t)obs0 * M, nb * M, E));  // writes it_obs[obs0 .. obs0 + nb)
   return 0;
 }
 
-static int run_context(cvb_handle* h, cudaStream_t st, int obs = 0) {
+// image / text towers + heads of observations [obs0, obs0 + nb) (inputs staged by verifier_stage_context_inputs)
+static int run_context(cvb_handle* h, cudaStream_t st, int obs0 = 0, int nb = 1) {
   const cvb_config& c = h->cfg;
   VerifierState& s = *h->vf;
   const int Wd = c.vf_width;
   const int Np = (c.vf_image / c.vf_patch) * (c.vf_image / c.vf_patch), Tt = c.vf_text_ctx;
-  const float* in_image = s.in_image + (size_t)obs * 3 * c.vf_image * c.vf_image;
-  const int64_t* in_tokens = s.in_tokens + (size_t)obs * Tt;
+  const float* in_image = s.in_image + (size_t)obs0 * 3 * c.vf_image * c.vf_image;
+  const int64_t* in_tokens = s.in_tokens + (size_t)obs0 * Tt;
   // image tower -> patch features (hook output), text tower -> per-token projected features
-  CVB_TRY(im2col_patches(st, in_image, s.patches, 3, c.vf_image, c.vf_image, c.vf_patch, s.kpad));
-  CVB_TRY(gemm(st, s.patches, s.kpad, s.w_patch, s.kpad, Np, Wd, s.kpad, EPI_RESID, s.hv, Wd, s.patch_b, s.pos_embed, Wd));
-  CVB_TRY(run_blocks(st, s, s.vis, s.hv, Np, Wd, c.vf_heads, c.vf_mlp, true, s.pfeat));
-  CVB_TRY(embed_tokens_pos(st, s.tok_emb, s.txt_pos, in_tokens, s.ht, Tt, Wd));
-  CVB_TRY(run_blocks(st, s, s.txt, s.ht, Tt, Wd, c.vf_heads, c.vf_mlp, false, nullptr));
-  CVB_TRY(layernorm_bf16(st, s.ht, Wd, s.lnf_w, s.lnf_b, s.xv, Wd, Tt, Wd, 1e-6f));
-  CVB_TRY(gemm(st, s.xv, Wd, s.wproj, Wd, Tt, Wd, Wd, EPI_STORE, s.tfeat, Wd, s.bproj));
-  CVB_TRY(l2norm_rows_bf16_to_f32(st, s.pfeat, Wd, s.Pn, Np, Wd));
-  CVB_TRY(l2norm_rows_bf16_to_f32(st, s.tfeat, Wd, s.Tn, Tt, Wd));
-  CVB_TRY(run_heads_context(h, st, obs));
+  CVB_TRY(im2col_patches(st, in_image, s.patches, 3, c.vf_image, c.vf_image, c.vf_patch, s.kpad, nb));
+  CVB_TRY(gemm(st, s.patches, s.kpad, s.w_patch, s.kpad, nb * Np, Wd, s.kpad, EPI_RESID, s.hv, Wd, s.patch_b,
+               nb > 1 ? s.pos_tiled : s.pos_embed, Wd));
+  CVB_TRY(run_blocks(st, s, s.vis, s.hv, Np, Wd, c.vf_heads, c.vf_mlp, true, s.pfeat, nb));
+  CVB_TRY(embed_tokens_pos(st, s.tok_emb, s.txt_pos, in_tokens, s.ht, nb * Tt, Wd, Tt));
+  CVB_TRY(run_blocks(st, s, s.txt, s.ht, Tt, Wd, c.vf_heads, c.vf_mlp, false, nullptr, nb));
+  CVB_TRY(layernorm_bf16(st, s.ht, Wd, s.lnf_w, s.lnf_b, s.xv, Wd, nb * Tt, Wd, 1e-6f));
+  CVB_TRY(gemm(st, s.xv, Wd, s.wproj, Wd, nb * Tt, Wd, Wd, EPI_STORE, s.tfeat, Wd, s.bproj));
+  CVB_TRY(l2norm_rows_bf16_to_f32(st, s.pfeat, Wd, s.Pn, nb * Np, Wd));
+  CVB_TRY(l2norm_rows_bf16_to_f32(st, s.tfeat, Wd, s.Tn, nb * Tt, Wd));
+  CVB_TRY(run_heads_context(h, st, obs0, nb));
   return 0;
 }
 
@@ -607,8 +640,9 @@ int verifier_stage_context_inputs(cvb_handle* h, const float* image, const int64
 }
 
 // image/text side of observation `obs` (its inputs were staged by verifier_stage_context_inputs)
-int verifier_enqueue_context(cvb_handle* h, cudaStream_t st, int obs) {
-  CVB_TRY(run_context(h, st, obs));
+int verifier_enqueue_context(cvb_handle* h, cudaStream_t st, int obs, int nb) {
+  CVB_REQUIRE(obs >= 0 && nb >= 1 && obs + nb <= h->max_obs(), "observation slots out of range (max_observations)");
+  CVB_TRY(run_context(h, st, obs, nb));
   h->vf->context_valid = true;
   return 0;
 }
@@ -689,7 +723,7 @@ int verifier_set_features(cvb_handle* h, const float* patch, const float* text, 
   const int Np = (c.vf_image / c.vf_patch) * (c.vf_image / c.vf_patch), Tt = c.vf_text_ctx;
   CVB_CUDA(cudaMemcpyAsync(s.Pn, patch, (size_t)Np * Wd * 4, cudaMemcpyDeviceToDevice, st));
   CVB_CUDA(cudaMemcpyAsync(s.Tn, text, (size_t)Tt * Wd * 4, cudaMemcpyDeviceToDevice, st));
-  CVB_TRY(run_heads_context(h, st));
+  CVB_TRY(run_heads_context(h, st, 0, 1));
   s.context_valid = true;
   return 0;
 }

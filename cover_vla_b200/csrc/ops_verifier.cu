@@ -41,19 +41,20 @@ __device__ __forceinline__ float bmax(float v, float* red) {
 
 // ---------------------------------------------------------------------------------------------
 __global__ void embed_tokens_pos_kernel(const bf16* __restrict__ table, const bf16* __restrict__ pos,
-                                        const int64_t* __restrict__ tok, bf16* __restrict__ out, int width) {
+                                        const int64_t* __restrict__ tok, bf16* __restrict__ out, int width, int ctx) {
   pdl_wait();
   pdl_launch();
   const int t = blockIdx.x;
   const bf16* src = table + tok[t] * width;
-  const bf16* pp = pos + static_cast<long>(t) * width;
+  const bf16* pp = pos + static_cast<long>(t % ctx) * width;  // several texts of ctx tokens back to back
   for (int i = threadIdx.x; i < width; i += blockDim.x)
     out[static_cast<long>(t) * width + i] =
         __float2bfloat16_rn(__bfloat162float(src[i]) + __bfloat162float(pp[i]));
 }
 int embed_tokens_pos(cudaStream_t st, const bf16* table, const bf16* pos, const int64_t* tok, bf16* out,
-                     int tokens, int width) {
-  CVB_TRY(launch_pdl(embed_tokens_pos_kernel, dim3(tokens), dim3(256), 0, st, 1, table, pos, tok, out, width));
+                     int tokens, int width, int ctx) {
+  CVB_TRY(launch_pdl(embed_tokens_pos_kernel, dim3(tokens), dim3(256), 0, st, 1, table, pos, tok, out, width,
+                     ctx > 0 ? ctx : tokens));
   CVB_LAUNCHED();
   return 0;
 }

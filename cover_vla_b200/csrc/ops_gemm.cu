@@ -175,15 +175,17 @@ int gemm_bf16(cudaStream_t st, const GemmCall& c) {
     CVB_REQUIRE(c.N % 256 == 0, "EPI_GEGLU expects 256-row packed gate|up blocks");
     bn = 256;
   } else if (bn == 0) {
-    // a 256-wide tile does twice the math per shared-memory byte of a 128-wide one: prefer it as soon as it fills
-    // ~90% of one wave (e.g. the prefix o_proj / down_proj: 18 x 8 = 144 tiles on 148 SMs); CVB_GEMM_BN256_PCT overrides
-    static const int pct = getenv("CVB_GEMM_BN256_PCT") != nullptr ? atoi(getenv("CVB_GEMM_BN256_PCT")) : 90;
-    if (tiles(256) * 100 >= sms * pct)
-      bn = 256;
-    else if (tiles(128) >= sms)
-      bn = 128;
-    else
-      bn = 64;
+    // Measured cost model (tools/gemm_shapes_bench.py): the persistent kernel walks ceil(tiles / SMs) rounds of tiles, and a
+    // k-block of a 128 x BN tile costs in proportion to the bytes it pulls from L2 (A 16 KB + W BN/64 x 8 KB: 3 : 4 : 6
+    // for BN = 64 : 128 : 256) - these shapes are bound by L2 -> SM bandwidth, not by the tensor pipe.  Ties go to the
+    // wider tile (fewer bytes in total).  E.g. M = 1280, N = 1024: 160 narrow tiles = 2 rounds vs 80 tiles of 128 = 1 round
+    // at 4/3 the cost (36 -> 24 us at K = 4096).
+    long best = 0;
+    for (int cand : {256, 128, 64}) {
+      const long rounds = (tiles(cand) + sms - 1) / sms;
+      const long cost = rounds * (cand == 256 ? 6 : cand == 128 ? 4 : 3);
+      if (bn == 0 || cost < best) bn = cand, best = cost;
+    }
   }
   CVB_REQUIRE(bn == 64 || bn == 128 || bn == 256, "BN must be 64, 128 or 256");
   int grid = tiles(bn);

@@ -26,6 +26,9 @@ struct TrajLayer {
 };
 struct MemberW {
   const float *temp, *pos_emb, *w_ss, *b_ss;
+  // vf_traj_layers == 0 (use_transformer = False checkpoints): nn.Sequential(Linear, LayerNorm, ReLU, Dropout, Linear)
+  const float *mlp_w0 = nullptr, *mlp_b0 = nullptr, *mlp_lnw = nullptr, *mlp_lnb = nullptr, *mlp_w1 = nullptr,
+              *mlp_b1 = nullptr;
   float* wkv_v;  // owned [L*2E, W] (vision pooling K/V projections of all blocks)
   float* bkv_v;  // owned [L*2E]
   std::vector<TrajLayer> traj;
@@ -172,6 +175,18 @@ void verifier_required_weights(const cvb_config& c, std::vector<WeightSpec>* out
     }
     add(b + "input_projection.weight", CVB_F32, {E, 2 * E});
     add(b + "input_projection.bias", CVB_F32, {E});
+    if (c.vf_traj_layers == 0) {
+      // MLP action encoder over the flattened history (finetune_trajectory_bridge_ddp.py:254-262, merged checkpoints with
+      // use_transformer = False: efficient_ensemble_merged.py:161-171); hidden width = vf_traj_ff
+      const std::string q = b + "complex_action_encoder.";
+      add(q + "0.weight", CVB_F32, {c.vf_traj_ff, c.vf_history * c.vf_action_dim});
+      add(q + "0.bias", CVB_F32, {c.vf_traj_ff});
+      add(q + "1.weight", CVB_F32, {c.vf_traj_ff});
+      add(q + "1.bias", CVB_F32, {c.vf_traj_ff});
+      add(q + "4.weight", CVB_F32, {E, c.vf_traj_ff});
+      add(q + "4.bias", CVB_F32, {E});
+      continue;
+    }
     add(b + "single_step_action_encoder.weight", CVB_F32, {E, c.vf_action_dim});
     add(b + "single_step_action_encoder.bias", CVB_F32, {E});
     for (int i = 0; i < c.vf_traj_layers; ++i) {
@@ -294,7 +309,7 @@ int verifier_finalize(cvb_handle* h, cudaStream_t st) {
   CVB_TRY(dalloc_t(h, &s.it_obs, (size_t)Bm * M * E));  // image-text embeddings of every observation's context
   const size_t rows = (size_t)Nm * S;
   // CVB_TRAJ_SIMT=1 keeps the fp32 SIMT GEMMs (A/B testing); the tensor-core path needs 8-element aligned widths
-  s.traj_tc = getenv("CVB_TRAJ_SIMT") == nullptr && E % 8 == 0 && c.vf_traj_ff % 8 == 0;
+  s.traj_tc = getenv("CVB_TRAJ_SIMT") == nullptr && E % 8 == 0 && c.vf_traj_ff % 8 == 0 && c.vf_traj_layers > 0;
   if (s.traj_tc) {
     CVB_TRY(dalloc_t(h, &s.txs, rows * 3 * E * M));
     CVB_TRY(dalloc_t(h, &s.tatts, rows * 3 * E * M));
@@ -329,8 +344,19 @@ int verifier_finalize(cvb_handle* h, cudaStream_t st) {
     MemberW& Mw = s.mem[m];
     CVB_TRY(W(h, b + "text_aware_visual_extraction.temperature", CVB_F32, 1, &Mw.temp));
     CVB_TRY(W(h, b + "text_aware_visual_extraction.pos_emb", CVB_F32, (int64_t)Np * Wd, &Mw.pos_emb));
-    CVB_TRY(W(h, b + "single_step_action_encoder.weight", CVB_F32, (int64_t)E * c.vf_action_dim, &Mw.w_ss));
-    CVB_TRY(W(h, b + "single_step_action_encoder.bias", CVB_F32, E, &Mw.b_ss));
+    if (c.vf_traj_layers == 0) {
+      const std::string q = b + "complex_action_encoder.";
+      const int FFh = c.vf_traj_ff;
+      CVB_TRY(W(h, q + "0.weight", CVB_F32, (int64_t)FFh * c.vf_history * c.vf_action_dim, &Mw.mlp_w0));
+      CVB_TRY(W(h, q + "0.bias", CVB_F32, FFh, &Mw.mlp_b0));
+      CVB_TRY(W(h, q + "1.weight", CVB_F32, FFh, &Mw.mlp_lnw));
+      CVB_TRY(W(h, q + "1.bias", CVB_F32, FFh, &Mw.mlp_lnb));
+      CVB_TRY(W(h, q + "4.weight", CVB_F32, (int64_t)E * FFh, &Mw.mlp_w1));
+      CVB_TRY(W(h, q + "4.bias", CVB_F32, E, &Mw.mlp_b1));
+    } else {
+      CVB_TRY(W(h, b + "single_step_action_encoder.weight", CVB_F32, (int64_t)E * c.vf_action_dim, &Mw.w_ss));
+      CVB_TRY(W(h, b + "single_step_action_encoder.bias", CVB_F32, E, &Mw.b_ss));
+    }
     CVB_TRY(dalloc_t(h, &Mw.wkv_v, (size_t)L * 2 * E * Wd));
     CVB_TRY(dalloc_t(h, &Mw.bkv_v, (size_t)L * 2 * E));
     for (int pi = 0; pi < 2; ++pi) {
@@ -538,6 +564,14 @@ static int run_member_trajectories(cvb_handle* h, cudaStream_t st, int N, int m)
   float* ty = s.ty + (size_t)m * cap * E;
   float* tff = s.tff + (size_t)m * cap * FF;
   const MemberW& Mw = s.mem[m];
+  if (c.vf_traj_layers == 0) {
+    // MLP action encoder: flat history [N, S*A] -> Linear -> LayerNorm -> ReLU -> Linear -> unit norm
+    // (efficient_ensemble_merged.py:241-245; Dropout is the identity in eval mode)
+    CVB_TRY(sg(st, s.in_traj, (long)S * A, Mw.mlp_w0, (long)S * A, N, FF, S * A, tff, FF, Mw.mlp_b0));
+    CVB_TRY(layernorm_f32(st, tff, nullptr, Mw.mlp_lnw, Mw.mlp_lnb, tff, N, FF, 1e-5f, nullptr, /*relu=*/1));
+    CVB_TRY(sg(st, tff, FF, Mw.mlp_w1, FF, N, E, FF, ty, E, Mw.mlp_b1));
+    return l2norm_rows_f32(st, ty, s.act + (size_t)m * N * E, N, E);
+  }
   CVB_TRY(sg(st, s.in_traj, A, Mw.w_ss, A, rows, E, A, tx, E, Mw.b_ss));
   if (s.traj_tc) {
     // every linear layer as ONE tcgen05 GEMM over the 3K axis of the [hi | hi | lo] x [hi | lo | hi] operands (fp32

@@ -75,7 +75,8 @@ int layernorm_bf16(cudaStream_t st, const bf16* x, long ldx, const bf16* w, cons
 // LayerNorm on fp32 rows, fp32 affine (verifier heads); optional residual added BEFORE the norm.
 // y_split (optional): the result also as the [hi | hi | lo] bf16 A operand of the 3-term bf16 GEMM (split3_rows)
 int layernorm_f32(cudaStream_t st, const float* x, const float* resid, const float* w,
-                  const float* b, float* y, int rows, int width, float eps, bf16* y_split = nullptr);
+                  const float* b, float* y, int rows, int width, float eps, bf16* y_split = nullptr,
+                  int relu = 0);  // relu: max(LayerNorm(x), 0)
 // fp32-accurate GEMM on the bf16 tensor cores: out[rows, 3K] bf16 = [hi | hi | lo] (mode 0, activations) or [hi | lo | hi]
 // (mode 1, weights) of x[rows, K] fp32, hi = bf16(x), lo = bf16(x - hi); act 1 applies ReLU first.  A GEMM over the 3K
 // axis then evaluates a_hi w_hi + a_hi w_lo + a_lo w_hi with fp32 accumulation (error ~2^-16 relative per product).

@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(128) layernorm_f32_kernel(const float* __restr
                                                             const float* __restrict__ w,
                                                             const float* __restrict__ b,
                                                             float* __restrict__ y, int width,
-                                                            float eps, bf16* __restrict__ y_split) {
+                                                            float eps, bf16* __restrict__ y_split, int relu) {
   pdl_wait();
   pdl_launch();
   __shared__ float red[32];
@@ -414,7 +414,8 @@ __global__ void __launch_bounds__(128) layernorm_f32_kernel(const float* __restr
   const float rstd = 1.0f / sqrtf(var + eps);
   bf16* ys = y_split != nullptr ? y_split + static_cast<long>(blockIdx.x) * 3 * width : nullptr;
   for (int i = threadIdx.x; i < width; i += blockDim.x) {
-    const float v = (rowbuf[i] - mean) * rstd * w[i] + b[i];
+    float v = (rowbuf[i] - mean) * rstd * w[i] + b[i];
+    if (relu) v = fmaxf(v, 0.f);  // nn.Sequential(Linear, LayerNorm, ReLU, ...) of the MLP action encoder
     y[off + i] = v;
     if (ys != nullptr) {  // [hi | hi | lo]: the A operand of the 3-term bf16 GEMM (split3_rows)
       const bf16 hi = __float2bfloat16_rn(v);
@@ -425,9 +426,9 @@ __global__ void __launch_bounds__(128) layernorm_f32_kernel(const float* __restr
 }
 
 int layernorm_f32(cudaStream_t st, const float* x, const float* resid, const float* w,
-                  const float* b, float* y, int rows, int width, float eps, bf16* y_split) {
+                  const float* b, float* y, int rows, int width, float eps, bf16* y_split, int relu) {
   CVB_TRY(launch_pdl(layernorm_f32_kernel, dim3(rows), dim3(128), width * sizeof(float), st, 1, x, resid, w, b, y, width, eps,
-                     y_split));
+                     y_split, relu));
   CVB_LAUNCHED();
   return 0;
 }

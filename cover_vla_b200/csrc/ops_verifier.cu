@@ -74,6 +74,22 @@ __global__ void l2norm_bf16_kernel(const bf16* __restrict__ x, long ldx, float* 
   for (int i = threadIdx.x; i < width; i += blockDim.x)
     y[static_cast<long>(blockIdx.x) * width + i] = __bfloat162float(xr[i]) / nrm;
 }
+// y[r,:] = x[r,:] / ||x[r,:]||_2 on fp32 rows (MLP action encoder output, finetune_trajectory_bridge_ddp.py:413)
+__global__ void l2norm_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int width) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ float red[32];
+  const float* xr = x + static_cast<long>(blockIdx.x) * width;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < width; i += blockDim.x) ss += xr[i] * xr[i];
+  const float nrm = sqrtf(bsum(ss, red));
+  for (int i = threadIdx.x; i < width; i += blockDim.x) y[static_cast<long>(blockIdx.x) * width + i] = xr[i] / nrm;
+}
+int l2norm_rows_f32(cudaStream_t st, const float* x, float* y, int rows, int width) {
+  CVB_TRY(launch_pdl(l2norm_f32_kernel, dim3(rows), dim3(256), 0, st, 1, x, y, width));
+  CVB_LAUNCHED();
+  return 0;
+}
 int l2norm_rows_bf16_to_f32(cudaStream_t st, const bf16* x, long ldx, float* y, int rows, int width) {
   CVB_TRY(launch_pdl(l2norm_bf16_kernel, dim3(rows), dim3(256), 0, st, 1, x, ldx, y, width));
   CVB_LAUNCHED();

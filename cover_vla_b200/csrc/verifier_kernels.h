@@ -43,6 +43,7 @@ int execution_action(cudaStream_t stream, const float* actions, int n_cand, int 
 int embed_tokens_pos(cudaStream_t st, const bf16* table, const bf16* pos, const int64_t* tok, bf16* out,
                      int tokens, int width, int ctx = 0);  // ctx > 0: position = token index mod ctx
 int l2norm_rows_bf16_to_f32(cudaStream_t st, const bf16* x, long ldx, float* y, int rows, int width);
+int l2norm_rows_f32(cudaStream_t st, const float* x, float* y, int rows, int width);
 int softmax_rows_temp(cudaStream_t st, float* x, int rows, int cols, const float* temp_dev);
 int add_f32(cudaStream_t st, const float* a, const float* b, float* y, long n);
 int pool_chains(cudaStream_t st, const PoolChain* chains_dev, int n_chains, int embed, int heads, int tokens);

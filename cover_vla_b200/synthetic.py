@@ -223,6 +223,10 @@ VTINY = VerifierDims(image=64, patch=16, width=128, layers=2, heads=2, mlp=256, 
 VMID = VerifierDims(image=192, patch=16, width=256, layers=3, heads=4, mlp=1024, text_layers=3, text_ctx=64,
                     vocab=2000, members=3, embed=512, pool_heads=8, pool_layers=4, traj_layers=4, traj_ff=1024)
 
+# use_transformer = False checkpoints: traj_layers = 0, traj_ff = hidden width of the MLP action encoder
+VTINY_MLP = VerifierDims(**{**asdict(VTINY), "traj_layers": 0, "traj_ff": 48})
+VMID_MLP = VerifierDims(**{**asdict(VMID), "traj_layers": 0, "traj_ff": 512})
+
 TR = "verifier.trunk."
 
 
@@ -299,6 +303,15 @@ def head_specs(d: VerifierDims):
                     out.append((q + nm + ".bias", (E,), 0.1, 0.0, f32))
         out.append((b + "input_projection.weight", (E, 2 * E), 1.0 / math.sqrt(2 * E), 0.0, f32))
         out.append((b + "input_projection.bias", (E,), 0.05, 0.0, f32))
+        if d.traj_layers == 0:  # use_transformer = False: the MLP complex_action_encoder (hidden width = traj_ff)
+            q, Hm, Kin = b + "complex_action_encoder.", d.traj_ff, d.history * d.action_dim
+            out.append((q + "0.weight", (Hm, Kin), 1.0 / math.sqrt(Kin), 0.0, f32))
+            out.append((q + "0.bias", (Hm,), 0.05, 0.0, f32))
+            out.append((q + "1.weight", (Hm,), 0.1, 1.0, f32))
+            out.append((q + "1.bias", (Hm,), 0.1, 0.0, f32))
+            out.append((q + "4.weight", (E, Hm), 1.0 / math.sqrt(Hm), 0.0, f32))
+            out.append((q + "4.bias", (E,), 0.05, 0.0, f32))
+            continue
         out.append((b + "single_step_action_encoder.weight", (E, d.action_dim), 1.0 / math.sqrt(d.action_dim), 0.0, f32))
         out.append((b + "single_step_action_encoder.bias", (E,), 0.05, 0.0, f32))
         for i in range(d.traj_layers):

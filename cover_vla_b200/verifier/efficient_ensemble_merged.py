@@ -63,10 +63,13 @@ class EfficientEnsembleMerged:
         self.use_transformer = meta.get("use_transformer", True)
         self.history_length = meta.get("history_length", 10)
         self.action_dim = meta.get("action_dim", 7)
-        if not self.use_transformer:
-            raise NotImplementedError("use_transformer=False (MLP action encoder) checkpoints are not supported")
         if engine is None:
             cfgd = dict(_VF_DEFAULT)
+            if not self.use_transformer:
+                # MLP action encoder (:161-171): the engine takes vf_traj_layers = 0 and the hidden width (512 in the
+                # reference; read from the checkpoint) in vf_traj_ff
+                w0 = ensemble_components[0]["complex_action_encoder"]["0.weight"]
+                cfgd["vf_traj_layers"], cfgd["vf_traj_ff"] = 0, int(w0.shape[0])
             cfgd.update(vf_config or {})
             cfgd["vf_history"], cfgd["vf_action_dim"] = self.history_length, self.action_dim
             self.num_models = len(ensemble_components)
@@ -97,7 +100,7 @@ class EfficientEnsembleMerged:
             for m, comp in enumerate(ensemble_components):
                 for cname, sd in comp.items():
                     if not isinstance(sd, dict):
-                        continue  # action_padding_value (python float, -5.0)
+                        continue  # action_padding_value (python float, -5.0); None for the unused action encoder
                     for k, v in sd.items():
                         key = f"verifier.{m}.{cname}.{k}"
                         if key in engine_required(engine):

@@ -133,6 +133,9 @@ typedef struct cvb_config {
   /* verifier trunk (SigLIP2 ViT-L/16-384 + text tower) and heads; vf_members == 0 disables it */
   int32_t vf_image, vf_patch, vf_width, vf_layers, vf_heads, vf_mlp;
   int32_t vf_text_layers, vf_text_ctx, vf_vocab;
+  /* vf_traj_layers >= 1: transformer action encoder (use_transformer = True, efficient_ensemble_merged.py:135-160) with
+   * feed-forward width vf_traj_ff.  vf_traj_layers == 0: the MLP `complex_action_encoder` of use_transformer = False
+   * checkpoints (efficient_ensemble_merged.py:161-171) with hidden width vf_traj_ff (512 in the reference). */
   int32_t vf_members, vf_embed, vf_pool_heads, vf_pool_layers, vf_traj_layers, vf_traj_ff;
   int32_t vf_history, vf_action_dim;
   int32_t use_cuda_graph; /* capture the per-(R,K) launch sequence once and replay it */

@@ -76,6 +76,9 @@ def main(full: bool = False):
     make("VTINY", 4, 3, seed=1)
     make("VMID", 8, 5, seed=2)
     make("VMID", 1, 1, seed=3)
+    # use_transformer = False checkpoints (MLP action encoder, efficient_ensemble_merged.py:161-171, 241-245)
+    make("VTINY_MLP", 4, 3, seed=1)
+    make("VMID_MLP", 8, 5, seed=2)
 
 
 if __name__ == "__main__":

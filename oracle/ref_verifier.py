@@ -17,7 +17,7 @@ def build_reference_ensemble(d: V.VerifierDims, w: dict, feature_fn):
     VM, EM = ref_shim.verifier_modules()
     ens = EM.EfficientEnsembleMerged.__new__(EM.EfficientEnsembleMerged)
     ens.device = "cpu"
-    ens.use_transformer = True
+    ens.use_transformer = d.traj_layers > 0
     ens.history_length = d.history
     ens.action_dim = d.action_dim
     ens.num_models = d.members
@@ -40,6 +40,16 @@ def build_reference_ensemble(d: V.VerifierDims, w: dict, feature_fn):
         tp.load_state_dict(sub(b + "text_pooling."))
         ip = torch.nn.Linear(2 * E, E)
         ip.load_state_dict(sub(b + "input_projection."))
+        if d.traj_layers == 0:
+            # the use_transformer = False components of efficient_ensemble_merged.py:161-183 (hidden width from the dims)
+            ce = torch.nn.Sequential(torch.nn.Linear(d.history * d.action_dim, d.traj_ff), torch.nn.LayerNorm(d.traj_ff),
+                                     torch.nn.ReLU(), torch.nn.Dropout(0.1), torch.nn.Linear(d.traj_ff, E))
+            ce.load_state_dict(sub(b + "complex_action_encoder."))
+            comps = {"text_aware_visual_extraction": text_aware.eval(), "vision_poolings": vp.eval(),
+                     "text_pooling": tp.eval(), "input_projection": ip.eval(), "single_step_action_encoder": None,
+                     "trajectory_encoder": None, "complex_action_encoder": ce.eval(), "action_padding_value": -5.0}
+            ens.trainable_models.append(comps)
+            continue
         ss = torch.nn.Linear(d.action_dim, E)
         ss.load_state_dict(sub(b + "single_step_action_encoder."))
         layer = torch.nn.TransformerEncoderLayer(d_model=E, nhead=d.pool_heads, dim_feedforward=d.traj_ff, batch_first=False, dropout=0.1)

@@ -31,7 +31,7 @@ import numpy as np  # noqa: F401
 import torch
 import torch.nn.functional as F
 
-from cover_vla_b200.synthetic import (TR, VFULL, VMID, VTINY, VerifierDims, head_specs, make_verifier_weights,  # noqa: F401
+from cover_vla_b200.synthetic import (TR, VFULL, VMID, VMID_MLP, VTINY, VTINY_MLP, VerifierDims, head_specs, make_verifier_weights,  # noqa: F401
                                       pad_histories, sincos_position_embedding, trunk_specs)
 from cover_vla_b200.synthetic import make_verifier_inputs as make_inputs  # noqa: F401
 
@@ -182,6 +182,14 @@ def trajectory_embedding(w, m: int, d: VerifierDims, traj, pad_value=-5.0):
     E, H = d.embed, d.pool_heads
     hd = E // H
     a = traj.float()
+    if d.traj_layers == 0:
+        # use_transformer = False (efficient_ensemble_merged.py:161-171, 241-245): nn.Sequential(Linear, LayerNorm, ReLU,
+        # Dropout, Linear) over the flattened history; Dropout is the identity in eval mode
+        q = b + "complex_action_encoder."
+        hid = F.linear(a.reshape(a.shape[0], -1), w[q + "0.weight"], w[q + "0.bias"])
+        hid = F.relu(F.layer_norm(hid, (hid.shape[-1],), w[q + "1.weight"], w[q + "1.bias"]))
+        t = F.linear(hid, w[q + "4.weight"], w[q + "4.bias"])
+        return t / t.norm(dim=-1, keepdim=True)
     pad = a[:, :, 0] == pad_value  # [N, S]
     x = F.linear(a, w[b + "single_step_action_encoder.weight"], w[b + "single_step_action_encoder.bias"])
     N, S, _ = x.shape

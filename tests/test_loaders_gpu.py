@@ -143,9 +143,12 @@ def _fake_open_clip(v, vw, calls):
     return mod
 
 
-def test_ensemble_from_merged_checkpoint_path(tmp_path, monkeypatch):
+@pytest.mark.parametrize("vname", ["VTINY", "VMID_MLP"])
+def test_ensemble_from_merged_checkpoint_path(tmp_path, monkeypatch, vname):
+    """merged .pt -> EfficientEnsembleMerged(path): transformer (use_transformer = True, :135-160) and MLP action encoder
+    (use_transformer = False, :161-171) checkpoints."""
     from cover_vla_b200.verifier import EfficientEnsembleMerged
-    v = V.VTINY
+    v = getattr(V, vname)
     vw = V.make_verifier_weights(v, 0)
     comps = []
     for m in range(v.members):
@@ -156,14 +159,17 @@ def test_ensemble_from_merged_checkpoint_path(tmp_path, monkeypatch):
                 comp, name = k[len(pre):].split(".", 1)
                 c.setdefault(comp, {})[name] = t
         c["action_padding_value"] = -5.0
+        for unused in ("single_step_action_encoder", "trajectory_encoder", "complex_action_encoder"):
+            c.setdefault(unused, None)  # the reference stores None for the encoder the checkpoint does not use
         comps.append(c)
     ckpt = tmp_path / "ensemble.pt"
-    torch.save({"ensemble_components": comps, "backbone": "hf-hub:timm/ViT-L-16-SigLIP2-384", "use_transformer": True,
+    torch.save({"ensemble_components": comps, "backbone": "hf-hub:timm/ViT-L-16-SigLIP2-384", "use_transformer": v.traj_layers > 0,
                 "history_length": v.history, "action_dim": v.action_dim, "num_models": v.members}, ckpt)
     vf_cfg = dict(vf_image=v.image, vf_patch=v.patch, vf_width=v.width, vf_layers=v.layers, vf_heads=v.heads,
                   vf_mlp=v.mlp, vf_text_layers=v.text_layers, vf_text_ctx=v.text_ctx, vf_vocab=v.vocab,
-                  vf_embed=v.embed, vf_pool_heads=v.pool_heads, vf_pool_layers=v.pool_layers,
-                  vf_traj_layers=v.traj_layers, vf_traj_ff=v.traj_ff)
+                  vf_embed=v.embed, vf_pool_heads=v.pool_heads, vf_pool_layers=v.pool_layers)
+    if v.traj_layers > 0:  # MLP checkpoints: the mirror reads the encoder type and hidden width from the checkpoint
+        vf_cfg.update(vf_traj_layers=v.traj_layers, vf_traj_ff=v.traj_ff)
     # without open_clip the constructor says exactly what is missing
     monkeypatch.setitem(sys.modules, "open_clip", None)
     with pytest.raises(RuntimeError, match="open_clip"):

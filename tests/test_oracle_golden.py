@@ -71,7 +71,8 @@ def test_full_size_fixtures_carry_reference_and_truth():
     assert g["scores"].shape == (40,) and 0 <= g["global_idx"] < 40
 
 
-@pytest.mark.parametrize("fname", ["verifier_vtiny_R4K3.pt", "verifier_vmid_R8K5.pt", "verifier_vmid_R1K1.pt"])
+@pytest.mark.parametrize("fname", ["verifier_vtiny_R4K3.pt", "verifier_vmid_R8K5.pt", "verifier_vmid_R1K1.pt",
+                                   "verifier_vtiny_mlp_R4K3.pt", "verifier_vmid_mlp_R8K5.pt"])
 def test_verifier_oracle_reproduces_reference_golden(fname):
     """EfficientEnsembleMerged.compute_max_similarity_scores_batch (efficient_ensemble_merged.py:309-454): heads,
     fusion, scores and the group-mean / argmax rule, fp32."""

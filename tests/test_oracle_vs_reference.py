@@ -71,7 +71,8 @@ def test_time_embedding_and_schedule_vs_reference():
         assert torch.equal(O.sinusoidal_time_embedding(tv, 64), ref)
 
 
-@pytest.mark.parametrize("name,R,K,seed", [("VTINY", 4, 3, 1), ("VTINY", 1, 1, 6), ("VMID", 3, 2, 7)])
+@pytest.mark.parametrize("name,R,K,seed", [("VTINY", 4, 3, 1), ("VTINY", 1, 1, 6), ("VMID", 3, 2, 7),
+                                           ("VTINY_MLP", 4, 3, 1), ("VMID_MLP", 3, 2, 7)])
 def test_verifier_scores_vs_reference_object(name, R, K, seed):
     """compute_max_similarity_scores_batch of the real EfficientEnsembleMerged (trunk injected, see
     oracle/make_golden_verifier.py) vs the oracle restatement."""

@@ -22,7 +22,7 @@ def _engine(vname, R, K):
     return v, vw, build_full_engine(d, w, v, vw, R, K)
 
 
-@pytest.mark.parametrize("vname,R,K", [("VTINY", 4, 3), ("VMID", 8, 5), ("VMID", 1, 1)])
+@pytest.mark.parametrize("vname,R,K", [("VTINY", 4, 3), ("VMID", 8, 5), ("VMID", 1, 1), ("VTINY_MLP", 4, 3), ("VMID_MLP", 8, 5)])
 def test_heads_match_oracle_given_identical_features(vname, R, K):
     v, vw, eng = _engine(vname, R, K)
     inp = V.make_inputs(v, R * K, seed=1)
@@ -43,7 +43,7 @@ def test_heads_match_oracle_given_identical_features(vname, R, K):
     eng.close()
 
 
-@pytest.mark.parametrize("vname,R,K", [("VTINY", 4, 3), ("VMID", 8, 5)])
+@pytest.mark.parametrize("vname,R,K", [("VTINY", 4, 3), ("VMID", 8, 5), ("VMID_MLP", 8, 5)])
 def test_end_to_end_scores(vname, R, K):
     v, vw, eng = _engine(vname, R, K)
     inp = V.make_inputs(v, R * K, seed=2)

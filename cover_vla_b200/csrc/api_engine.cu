@@ -143,6 +143,13 @@ int cvb_pi0_set_lang_len_hint(cvb_handle* h, int max_valid_tokens) {
   return 0;
 }
 
+int cvb_pi0_set_active_cameras(cvb_handle* h, int cameras) {
+  CVB_REQUIRE(h != nullptr, "null handle");
+  CVB_REQUIRE(cameras >= 0 && cameras <= h->cams_max(), "cameras must be 0 (all) .. num_cameras");
+  h->active_cams = cameras;
+  return 0;
+}
+
 int cvb_pi0_run_phase(cvb_handle* h, int phase, int R, int K, void* stream) {
   CVB_REQUIRE(h != nullptr, "null handle");
   return cvb::pi0_run_phase(h, phase, R, K, (cudaStream_t)stream);

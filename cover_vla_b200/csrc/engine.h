@@ -153,11 +153,19 @@ struct cvb_handle {
   cvb::VerifierState* vf = nullptr;
   cvb::CoverState cover;
 
-  int n_img() const { return (cfg.vis_image / cfg.vis_patch) * (cfg.vis_image / cfg.vis_patch); }
+  // cameras per observation (modeling_pi0.py:344-387, 529-547): the handle is sized for cfg.num_cameras image streams, a
+  // call uses the first `active_cams` of them (cvb_pi0_set_active_cameras; empty / masked cameras are dropped by the host -
+  // their tokens are masked as keys and never read, so dropping them is exact, like right-padded language tokens)
+  int active_cams = 0;  // 0 = all of cfg.num_cameras
+  int cams_max() const { return cfg.num_cameras > 1 ? cfg.num_cameras : 1; }
+  int cams() const { return active_cams > 0 ? active_cams : cams_max(); }
+  int n_img1() const { return (cfg.vis_image / cfg.vis_patch) * (cfg.vis_image / cfg.vis_patch); }  // tokens per image
+  int n_img() const { return cams() * n_img1(); }          // image tokens of a prompt in THIS call
+  int n_img_max() const { return cams_max() * n_img1(); }  // workspace / cache sizing
   // observations per batched call (cvb_pi0_sample_batch / cvb_cover_step_batch) and the global rephrase capacity
   int max_obs() const { return cfg.max_observations > 1 ? cfg.max_observations : 1; }
   int rm_total() const { return cfg.max_rephrases * max_obs(); }
-  int prefix_len() const { return n_img() + cfg.max_lang_len; }
+  int prefix_len() const { return n_img_max() + cfg.max_lang_len; }  // KV-cache rows per prompt (a stride, not a length)
   int suffix_len() const { return 1 + cfg.chunk_size; }
   // language rows actually processed per prompt: the caller's hint rounded up to 8 (bounds the number of graphs)
   int lang_rows() const {

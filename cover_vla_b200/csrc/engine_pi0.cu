@@ -152,8 +152,9 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
               "vision head_dim must be a multiple of 8");
   CVB_REQUIRE(c.head_dim % 16 == 0 && c.head_dim <= 256, "head_dim must be a multiple of 16, <= 256");
   CVB_REQUIRE(c.vis_image % c.vis_patch == 0, "image size must be a multiple of the patch size");
-  const int T = h->n_img(), P = h->prefix_len(), S = h->suffix_len();
+  const int T = h->n_img_max(), T1 = h->n_img1(), P = h->prefix_len(), S = h->suffix_len();
   const int Wv = c.vis_width, D = c.lm_width, We = c.ex_width;
+  CVB_REQUIRE(c.num_cameras >= 0 && c.num_cameras <= 8, "num_cameras must be 0..8");
   const int qd = c.heads * c.head_dim, qkvw = qd + 2 * c.head_dim;
   // Bm observations per call (cvb_*_batch): every "rephrase" index below is global,
   // r = observation * R + rephrase; the image / state of rephrase r are those of observation r / R
@@ -282,7 +283,7 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
   }
 
   // ---- workspace
-  CVB_TRY(dalloc_t(h, &s.in_image, (size_t)Bm * 3 * c.vis_image * c.vis_image));
+  CVB_TRY(dalloc_t(h, &s.in_image, (size_t)Bm * h->cams_max() * 3 * c.vis_image * c.vis_image));
   CVB_TRY(dalloc_t(h, &s.in_tokens, (size_t)Rm * c.max_lang_len));
   CVB_TRY(dalloc_t(h, &s.in_lang_len, Rm));
   CVB_TRY(dalloc_t(h, &s.plen, Rm));
@@ -298,12 +299,12 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
   CVB_TRY(dalloc_t(h, &s.attn_v, Tb * Wv));
   CVB_TRY(dalloc_t(h, &s.mlp_v, Tb * c.vis_mlp));
   CVB_TRY(dalloc_t(h, &s.proj_out, Tb * D));
-  if (Bm > 1) {  // position embedding tiled per observation (the residual operand of the patch-embedding GEMM)
+  if (Bm * h->cams_max() > 1) {  // position embedding tiled per image (the residual operand of the patch-embedding GEMM)
     const bf16* pos = nullptr;
-    CVB_TRY(W(h, VT + "embeddings.position_embedding.weight", CVB_BF16, (int64_t)T * Wv, &pos));
+    CVB_TRY(W(h, VT + "embeddings.position_embedding.weight", CVB_BF16, (int64_t)T1 * Wv, &pos));
     CVB_TRY(dalloc_t(h, &s.pos_tiled, Tb * Wv));
-    for (int b = 0; b < Bm; ++b)
-      CVB_CUDA(cudaMemcpyAsync(s.pos_tiled + (size_t)b * T * Wv, pos, (size_t)T * Wv * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+    for (int b = 0; b < Bm * h->cams_max(); ++b)
+      CVB_CUDA(cudaMemcpyAsync(s.pos_tiled + (size_t)b * T1 * Wv, pos, (size_t)T1 * Wv * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
   }
   const size_t Mp = (size_t)Rm * P;
   CVB_TRY(dalloc_t(h, &s.hp, Mp * D));
@@ -372,17 +373,20 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
 }
 
 // --------------------------------------------------------------------------------------------------
-static int run_vision(cvb_handle* h, cudaStream_t st, int B) {
+static int run_vision(cvb_handle* h, cudaStream_t st, int n_obs) {
   const cvb_config& c = h->cfg;
   Pi0State& s = h->pi0;
-  const int T1 = h->n_img(), T = B * T1, Wv = c.vis_width, hd = Wv / c.vis_heads, D = c.lm_width;
+  // every camera of every observation is one image of the tower's batch: rows [observation][camera][token], which is
+  // also the order of the image tokens in a prompt (modeling_pi0.py:529-547)
+  const int B = n_obs * h->cams();
+  const int T1 = h->n_img1(), T = B * T1, Wv = c.vis_width, hd = Wv / c.vis_heads, D = c.lm_width;
   const bf16 *b_patch, *pos, *post_w, *post_b, *w_proj, *b_proj;
   CVB_TRY(W(h, VT + "embeddings.patch_embedding.bias", CVB_BF16, Wv, &b_patch));
   CVB_TRY(W(h, VT + "embeddings.position_embedding.weight", CVB_BF16, (int64_t)T1 * Wv, &pos));
   if (B > 1) pos = s.pos_tiled;
   // split-K + LayerNorm-reduce path: single-observation (latency) handles only.  A handle built for batches takes the
   // fused-epilogue GEMMs for every B, so a row's result never depends on how many observations share the call.
-  const bool sk = h->max_obs() == 1;
+  const bool sk = h->max_obs() == 1 && T <= 256;  // (the split-K kernel holds all rows in one UMMA N)
   CVB_TRY(W(h, VT + "post_layernorm.weight", CVB_BF16, Wv, &post_w));
   CVB_TRY(W(h, VT + "post_layernorm.bias", CVB_BF16, Wv, &post_b));
   CVB_TRY(W(h, MM + "weight", CVB_BF16, (int64_t)D * Wv, &w_proj));
@@ -708,7 +712,7 @@ int pi0_stage_inputs(cvb_handle* h, const float* image, const int64_t* tokens, c
   CVB_REQUIRE(image != nullptr && tokens != nullptr && lang_len != nullptr && state != nullptr && noise != nullptr,
               "null input");
   const size_t act_bytes = (size_t)B * R * K * c.chunk_size * c.max_action_dim * sizeof(float);
-  CVB_CUDA(cudaMemcpyAsync(s.in_image, image, (size_t)B * 3 * c.vis_image * c.vis_image * sizeof(float),
+  CVB_CUDA(cudaMemcpyAsync(s.in_image, image, (size_t)B * h->cams() * 3 * c.vis_image * c.vis_image * sizeof(float),
                            cudaMemcpyDeviceToDevice, st));
   CVB_CUDA(cudaMemcpyAsync(s.in_tokens, tokens, (size_t)B * R * c.max_lang_len * sizeof(int64_t),
                            cudaMemcpyDeviceToDevice, st));
@@ -734,7 +738,7 @@ int pi0_sample(cvb_handle* h, const float* image, const int64_t* tokens, const i
   Pi0State& s = h->pi0;
   CVB_TRY(pi0_stage_inputs(h, image, tokens, lang_len, state, noise, R, K, st, B));
   const size_t act_bytes = (size_t)B * R * K * c.chunk_size * c.max_action_dim * sizeof(float);
-  const long key = ((long)h->lang_rows() << 40) | ((long)B << 28) | ((long)R << 16) | (long)K;
+  const long key = ((long)h->cams() << 56) | ((long)h->lang_rows() << 40) | ((long)B << 28) | ((long)R << 16) | (long)K;
   CVB_TRY(s.graphs.run(c.use_cuda_graph != 0, key, st, [&](cudaStream_t cs) { return run_all(h, cs, B, R, K); }));
   CVB_CUDA(cudaMemcpyAsync(actions, s.x_t, act_bytes, cudaMemcpyDeviceToDevice, st));
   return 0;
@@ -767,7 +771,7 @@ int64_t pi0_debug_copy(cvb_handle* h, const std::string& name, void* dst, int64_
   int64_t bytes = 0;
   const int64_t layer_bytes = (int64_t)h->rm_total() * P * c.head_dim * sizeof(bf16);
   if (name == "image_emb") {
-    src = s.proj_out, bytes = (int64_t)h->max_obs() * T * c.lm_width * sizeof(bf16);
+    src = s.proj_out, bytes = (int64_t)h->max_obs() * h->n_img_max() * c.lm_width * sizeof(bf16);
   } else if (name == "vision_hidden") {
     src = s.xv, bytes = (int64_t)T * c.vis_width * sizeof(bf16);
   } else if (name == "prefix_k0") {

@@ -21,6 +21,7 @@ _CFG_FIELDS = [
     "vf_history", "vf_action_dim",
     "use_cuda_graph",
     "max_observations",
+    "num_cameras",
 ]
 
 
@@ -72,6 +73,7 @@ class EngineConfig:
     vf_action_dim: int = 7
     use_cuda_graph: int = 1
     max_observations: int = 1
+    num_cameras: int = 1
 
     def to_c(self) -> CvbConfig:
         c = CvbConfig()
@@ -121,6 +123,7 @@ class Engine:
         L.cvb_finalize.argtypes = [C.c_void_p, C.c_void_p]
         L.cvb_pi0_sample.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.cvb_pi0_set_lang_len_hint.argtypes = [C.c_void_p, C.c_int]
+        L.cvb_pi0_set_active_cameras.argtypes = [C.c_void_p, C.c_int]
         L.cvb_pi0_run_phase.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.cvb_debug_copy.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.cvb_debug_copy.restype = C.c_int64
@@ -201,12 +204,26 @@ class Engine:
             _lib.check(self.lib.cvb_pi0_set_lang_len_hint(self._h, n))
             self._lang_hint = n
 
+    def set_active_cameras(self, cameras: int | None):
+        """Cameras per observation in the following calls (None / 0 = cfg.num_cameras); masked cameras are dropped by the
+        caller, which is exact (include/coverb200.h)."""
+        n = int(cameras or 0)
+        if n == max(1, self.cfg.num_cameras):
+            n = 0
+        if n != getattr(self, "_active_cams", 0):
+            _lib.check(self.lib.cvb_pi0_set_active_cameras(self._h, n))
+            self._active_cams = n
+
+    def _image_numel(self):
+        cams = getattr(self, "_active_cams", 0) or max(1, self.cfg.num_cameras)
+        return cams * 3 * self.cfg.vis_image ** 2
+
     def pi0_sample(self, image, lang_tokens, lang_len, state, noise, K: int, out=None, lang_len_max: int | None = None):
-        """image f32 [3,H,W]; lang_tokens i64 [R,L]; lang_len i32 [R]; state f32 [max_state_dim];
-        noise f32 [R*K, chunk, max_action_dim] -> actions f32 (same shape).  Asynchronous."""
+        """image f32 [3,H,W] ([C,3,H,W] with C cameras); lang_tokens i64 [R,L]; lang_len i32 [R]; state f32
+        [max_state_dim]; noise f32 [R*K, chunk, max_action_dim] -> actions f32 (same shape).  Asynchronous."""
         cfg = self.cfg
         R = lang_tokens.shape[0]
-        assert image.dtype == torch.float32 and image.numel() == 3 * cfg.vis_image ** 2
+        assert image.dtype == torch.float32 and image.numel() == self._image_numel()
         assert lang_tokens.dtype == torch.int64 and lang_tokens.shape[1] == cfg.max_lang_len
         assert lang_len.dtype == torch.int32 and lang_len.numel() == R
         assert state.dtype == torch.float32 and state.numel() == cfg.max_state_dim
@@ -233,7 +250,7 @@ class Engine:
         cfg = self.cfg
         B, R = lang_tokens.shape[0], lang_tokens.shape[1]
         assert B <= cfg.max_observations, "engine was built with a smaller max_observations"
-        assert images.dtype == torch.float32 and tuple(images.shape) == (B, 3, cfg.vis_image, cfg.vis_image)
+        assert images.dtype == torch.float32 and images.shape[0] == B and images.numel() == B * self._image_numel()
         assert lang_tokens.dtype == torch.int64 and lang_tokens.shape[2] == cfg.max_lang_len
         assert lang_len.dtype == torch.int32 and tuple(lang_len.shape) == (B, R)
         assert states.dtype == torch.float32 and tuple(states.shape) == (B, cfg.max_state_dim)
@@ -259,7 +276,7 @@ class Engine:
         N = R * K
         assert B <= cfg.max_observations, "engine was built with a smaller max_observations"
         assert tuple(noise.shape) == (B, N, cfg.chunk_size, cfg.max_action_dim) and noise.dtype == torch.float32
-        assert tuple(images.shape) == (B, 3, cfg.vis_image, cfg.vis_image) and tuple(states.shape) == (B, cfg.max_state_dim)
+        assert images.shape[0] == B and images.numel() == B * self._image_numel() and tuple(states.shape) == (B, cfg.max_state_dim)
         assert tuple(vf_images.shape) == (B, 3, cfg.vf_image, cfg.vf_image) and tuple(vf_tokens.shape) == (B, cfg.vf_text_ctx)
         assert tuple(lang_len.shape) == (B, R) and lang_tokens.shape[2] == cfg.max_lang_len
         for t in (images, lang_tokens, lang_len, states, noise, vf_images, vf_tokens):

@@ -54,6 +54,10 @@ def pad_vector(vector, new_dim):
 
 
 def engine_config_from_policy_config(c: PI0Config, **extra) -> EngineConfig:
+    try:  # one image stream per camera key of the policy config (the Bridge checkpoints have one)
+        extra.setdefault("num_cameras", max(1, len(c.image_features)))
+    except Exception:  # noqa: BLE001 - configs without feature declarations
+        extra.setdefault("num_cameras", 1)
     return EngineConfig(vis_layers=c.vis_layers, vis_width=c.vis_width, vis_heads=c.vis_heads, vis_mlp=c.vis_mlp,
                         vis_patch=c.vis_patch, vis_image=c.vis_image, layers=c.layers, lm_width=c.lm_width,
                         lm_mlp=c.lm_mlp, heads=c.heads, head_dim=c.head_dim, ex_width=c.proj_width, ex_mlp=c.ex_mlp,
@@ -102,18 +106,31 @@ class PI0FlowMatching:
         observations are split into per-observation calls.
         """
         cfg = self.config
-        if len(images) != 1:
-            raise NotImplementedError("one camera per observation (the Bridge checkpoints use a single image key)")
-        img = images[0]
         bsize = state.shape[0]
+        # Cameras (modeling_pi0.py:344-387, 529-547): a camera whose mask is False for the whole batch is an "empty camera"
+        # (-1 image): its tokens are masked as keys, do not advance the position ids and are never read, so it is dropped
+        # (exact).  The present cameras are stacked [batch, C, 3, H, W] in the order the reference concatenates them.
+        if img_masks is not None and len(img_masks) == len(images) and not self.assume_cover_layout:
+            keep = []
+            for cam, m in enumerate(img_masks):
+                n_on = int(m.sum())
+                if n_on not in (0, m.numel()):
+                    raise NotImplementedError("a camera must be present (or absent) for the whole batch")
+                if n_on:
+                    keep.append(cam)
+            if not keep:
+                raise ValueError("every camera is masked out")
+            images = [images[cam] for cam in keep]
+        if len(images) > max(1, self.engine.cfg.num_cameras):
+            raise ValueError(f"{len(images)} cameras, but the engine was built for {self.engine.cfg.num_cameras} "
+                             "(EngineConfig.num_cameras / len(config.image_features))")
+        self.engine.set_active_cameras(len(images))
+        img = images[0] if len(images) == 1 else torch.stack(list(images), dim=1)
         device = state.device
         if device.type != "cuda":
             raise RuntimeError("coverb200 has no CPU path: move the observation to a CUDA device")
         if noise is None:
             noise = self.sample_noise((bsize, cfg.chunk_size, cfg.max_action_dim), device, noise_std)
-        if img_masks is not None and not self.assume_cover_layout:
-            if not bool(torch.stack([m.all() for m in img_masks]).all()):
-                raise NotImplementedError("masked-out cameras are not supported")
         img = img.to(torch.float32)
         state = state.to(torch.float32)
         lang_tokens = lang_tokens.to(torch.int64)
@@ -302,6 +319,9 @@ class PI0Policy:
             mask = torch.ones(img.shape[0], dtype=torch.bool, device=img.device)
             images.append(img)
             img_masks.append(mask)
+        # Missing keys: the reference appends up to config.empty_cameras images of -1 with an all-False mask (:377-385).
+        # Those tokens are masked as keys, do not advance the position ids and are never read, so they are not created
+        # here at all (exact; sample_actions also drops cameras whose mask is all False).
         return images, img_masks
 
     def prepare_state(self, batch):

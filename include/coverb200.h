@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define CVB_ABI_VERSION 2
+#define CVB_ABI_VERSION 3
 #if defined(__GNUC__)
 #define CVB_API __attribute__((visibility("default")))
 #else
@@ -142,6 +142,10 @@ typedef struct cvb_config {
   /* observations per batched call (cvb_pi0_sample_batch / cvb_cover_step_batch); 0 or 1 = single-observation handle.
    * Workspace (KV caches, activations) is sized for max_observations * max_rephrases prompts. */
   int32_t max_observations;
+  /* cameras (image streams) per observation the handle is sized for, modeling_pi0.py:344-387; 0 or 1 = one camera.
+   * With C cameras every `image` argument below is f32 [C, 3, vis_image, vis_image] per observation and a prompt holds
+   * C * (vis_image / vis_patch)^2 image tokens in camera order (modeling_pi0.py:529-547). */
+  int32_t num_cameras;
 } cvb_config;
 
 typedef struct cvb_handle cvb_handle;
@@ -196,6 +200,12 @@ CVB_API int cvb_pi0_sample_batch(cvb_handle* h, int B, const float* images, cons
  * so a host that knows its tokenizer output (it produced it) lets the prefix skip them; longer prompts are truncated
  * to the hint, as the reference truncates at tokenizer_max_length (modeling_pi0.py:389-409). */
 CVB_API int cvb_pi0_set_lang_len_hint(cvb_handle* h, int max_valid_tokens);
+
+/* Number of cameras the following calls pass per observation (1 .. num_cameras; 0 = num_cameras).  The reference fills
+ * missing cameras with -1 images whose mask is False (prepare_images, modeling_pi0.py:377-385): their tokens are masked
+ * as keys, do not advance the position ids (cumsum of the pad mask, :684) and are never read - the host simply drops
+ * them and passes the present cameras, which is exact. */
+CVB_API int cvb_pi0_set_active_cameras(cvb_handle* h, int cameras);
 
 /* Profiling hook: re-run one phase (0 vision tower, 1 prefix, 2 denoise loop) eagerly on the inputs staged by
  * the last cvb_pi0_sample call, so a host can time the phases separately with CUDA events. */

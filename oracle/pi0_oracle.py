@@ -171,15 +171,22 @@ def embed_image(w, d: PI0Dims, pixel_values):
     return feats / (d.lm_width ** 0.5)
 
 
-def embed_prefix(w, d: PI0Dims, image, lang_tokens, lang_masks):
-    # modeling_pi0.py:517-567 (one camera, img_mask all True)
-    img_emb = embed_image(w, d, image).to(ACT)
-    img_emb = img_emb * torch.tensor(img_emb.shape[-1] ** 0.5, dtype=img_emb.dtype)
-    B, n_img = img_emb.shape[:2]
+def embed_prefix(w, d: PI0Dims, image, lang_tokens, lang_masks, img_masks=None):
+    # modeling_pi0.py:517-567.  `image`: one camera tensor [B,3,H,W] or a list of them (camera order = prompt order);
+    # `img_masks`: per camera bool [B] (None = all present); masked cameras keep their tokens but are padding (:541-544)
+    images = list(image) if isinstance(image, (list, tuple)) else [image]
+    embs, pads = [], []
+    for cam, im in enumerate(images):
+        img_emb = embed_image(w, d, im).to(ACT)
+        img_emb = img_emb * torch.tensor(img_emb.shape[-1] ** 0.5, dtype=img_emb.dtype)
+        B, n_img = img_emb.shape[:2]
+        m = torch.ones(B, dtype=torch.bool) if img_masks is None else img_masks[cam]
+        embs.append(img_emb)
+        pads.append(m[:, None].expand(B, n_img))
     lang_emb = F.embedding(lang_tokens, w[LM + "embed_tokens.weight"])
     lang_emb = lang_emb * math.sqrt(lang_emb.shape[-1])
-    embs = torch.cat([img_emb, lang_emb], dim=1)
-    pad = torch.cat([torch.ones(B, n_img, dtype=torch.bool), lang_masks], dim=1)
+    embs = torch.cat(embs + [lang_emb], dim=1)
+    pad = torch.cat(pads + [lang_masks], dim=1)
     att = torch.zeros(B, pad.shape[1], dtype=torch.bool)
     return embs, pad, att
 
@@ -252,8 +259,8 @@ def denoise_step(w, d: PI0Dims, state, prefix_pad, cache, x_t, timestep):
     return F.linear(out, w["action_out_proj.weight"], w["action_out_proj.bias"])
 
 
-def prefix_cache(w, d: PI0Dims, image, lang_tokens, lang_masks, last_layer_kv_only=False):
-    embs, pad, att = embed_prefix(w, d, image, lang_tokens, lang_masks)
+def prefix_cache(w, d: PI0Dims, image, lang_tokens, lang_masks, last_layer_kv_only=False, img_masks=None):
+    embs, pad, att = embed_prefix(w, d, image, lang_tokens, lang_masks, img_masks)
     mask = make_att_2d_masks(pad, att)
     pos = torch.cumsum(pad, dim=1) - 1
     _, cache = _tower_forward(w, d, LM, embs, mask, pos, None, fill=True, last_layer_kv_only=last_layer_kv_only)
@@ -261,9 +268,10 @@ def prefix_cache(w, d: PI0Dims, image, lang_tokens, lang_masks, last_layer_kv_on
 
 
 @torch.no_grad()
-def sample_actions(w, d: PI0Dims, image, lang_tokens, lang_masks, state, noise, trace=None):
-    """Exactly the reference batch layout: every argument has leading dim B (= N candidates)."""
-    cache, pad = prefix_cache(w, d, image, lang_tokens, lang_masks)
+def sample_actions(w, d: PI0Dims, image, lang_tokens, lang_masks, state, noise, trace=None, img_masks=None):
+    """Exactly the reference batch layout: every argument has leading dim B (= N candidates); `image` may be a list of
+    camera tensors with `img_masks` (see embed_prefix)."""
+    cache, pad = prefix_cache(w, d, image, lang_tokens, lang_masks, img_masks=img_masks)
     if trace is not None:
         trace["k0"] = cache[0]["key_states"].clone()
         trace["v_last"] = cache[d.layers - 1]["value_states"].clone()
@@ -287,7 +295,10 @@ def sample_actions_dedup(w, d: PI0Dims, image1, lang_tokens_r, lang_masks_r, sta
     """Same arithmetic, de-duplicated the way the CUDA path schedules it: vision
     tower once, prefix once per rephrase (padded tokens kept), K samples share their rephrase's cache."""
     R = lang_tokens_r.shape[0]
-    img = image1.expand(R, -1, -1, -1)
+    if isinstance(image1, (list, tuple)):  # several cameras
+        img = [im.expand(R, -1, -1, -1) for im in image1]
+    else:
+        img = image1.expand(R, -1, -1, -1)
     cache, pad = prefix_cache(w, d, img, lang_tokens_r, lang_masks_r, last_layer_kv_only=True)
     rep = torch.arange(R).repeat_interleave(K)
     cache = {l: {k: v[rep] for k, v in c.items()} for l, c in cache.items()}

@@ -66,6 +66,56 @@ def test_cover_step_matches_oracle():
     eng.close()
 
 
+def test_policy_with_two_cameras_and_a_missing_one():
+    """PI0Policy.select_action with two image keys (prepare_images, modeling_pi0.py:344-387): both present -> two image
+    streams; one key missing from the batch -> the reference would add a masked -1 image (a no-op), the mirror runs the
+    present camera alone."""
+    from cover_vla_b200.pi0 import PI0Config, PI0Policy, PolicyFeature
+    d = O.TINY
+    R, K = 2, 2
+    N = R * K
+    w = O.make_pi0_weights(d, 0)
+    feat = PolicyFeature("VISUAL", (3, d.vis_image, d.vis_image))
+    cfg = PI0Config(chunk_size=d.chunk_size, n_action_steps=d.chunk_size, tokenizer_max_length=d.max_lang_len,
+                    proj_width=d.ex_width, num_steps=d.num_steps, vis_layers=d.vis_layers, vis_width=d.vis_width,
+                    vis_heads=d.vis_heads, vis_mlp=d.vis_mlp, vis_patch=d.vis_patch, vis_image=d.vis_image,
+                    layers=d.layers, lm_width=d.lm_width, lm_mlp=d.lm_mlp, heads=d.heads, head_dim=d.head_dim,
+                    ex_mlp=d.ex_mlp, vocab=d.vocab, max_rephrases=R, max_samples=K, empty_cameras=1,
+                    resize_imgs_with_padding=(d.vis_image, d.vis_image),
+                    input_features={"observation.images.top": feat, "observation.images.wrist": feat,
+                                    "observation.state": PolicyFeature("STATE", (7,))})
+    policy = PI0Policy(cfg, state_dict={"model." + k: t for k, t in w.items()})
+    assert policy.model.engine.cfg.num_cameras == 2
+    inp = O.make_inputs(d, R, K, seed=9)
+    b = O.expand_to_batch(inp, K)
+    cam2 = (torch.rand(1, 3, d.vis_image, d.vis_image, generator=torch.Generator().manual_seed(78)) * 2 - 1).repeat(N, 1, 1, 1)
+    obs = {"observation.images.top": b["image"].cuda(), "observation.images.wrist": cam2.cuda(),
+           "observation.state": b["state"][:, :7].cuda(), "lang_tokens": b["tokens"].cuda(),
+           "lang_masks": b["masks"].cuda(), "task": ["x"] * N}
+    q = policy.select_action(obs, noise=b["noise"].cuda())
+    got = torch.stack(list(q), dim=1).cpu()
+    q.clear()
+    ref = O.sample_actions(w, d, [b["image"], cam2], b["tokens"], b["masks"], b["state"], b["noise"])
+    with O.truth_mode():
+        truth = O.sample_actions_dedup(O.truth_weights(w), d, [inp["image"], cam2[:1]], inp["tokens"], inp["masks"],
+                                       inp["state"], inp["noise"], K)
+    action_gate(got, ref[:, :, :7], truth[:, :, :7], "select_action, 2 cameras")
+    obs.pop("observation.images.wrist")  # missing key = empty camera
+    q = policy.select_action(obs, noise=b["noise"].cuda())
+    got1 = torch.stack(list(q), dim=1).cpu()
+    # = the engine with one active camera on the same handle, bit for bit (the numerical parity of that call against the
+    # oracle is tests/test_pi0_gpu.py::test_two_cameras_match_oracle_and_masked_camera_is_dropped; that the reference's
+    # masked -1 image is a no-op is tests/test_oracle_vs_reference.py::test_pi0_two_cameras_and_masked_camera_vs_reference)
+    eng = policy.model.engine
+    assert getattr(eng, "_active_cams", 0) == 1
+    direct = eng.pi0_sample(inp["image"][0].cuda().contiguous(), inp["tokens"].cuda(), inp["lens"].to(torch.int32).cuda(),
+                            torch.nn.functional.pad(inp["state"][0, :7], (0, d.max_state_dim - 7)).cuda().contiguous(),
+                            inp["noise"].cuda(), K=K).cpu()
+    assert torch.equal(got1, direct[:, :, :7])
+    one = O.sample_actions(w, d, b["image"], b["tokens"], b["masks"], b["state"], b["noise"])
+    assert max_abs(got1, one[:, :, :7]) < 3e-2 < max_abs(got1, ref[:, :, :7])  # it is the 1-camera result, not the 2-camera one
+
+
 def test_policy_and_ensemble_surfaces():
     """The two reference-facing objects, used the way run_simpler_eval_with_openpi.py uses them."""
     from cover_vla_b200.pi0 import PI0Config, PI0Policy, PolicyFeature

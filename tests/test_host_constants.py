@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert len(names) >= 10
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/coverb200.h but not exported"
-    assert lib.cvb_abi_version() == 2
+    assert lib.cvb_abi_version() == 3
 
 
 def test_denoise_schedule_matches_reference_loop(lib):

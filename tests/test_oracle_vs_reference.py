@@ -37,6 +37,34 @@ def test_pi0_sample_actions_bit_exact_vs_reference(R, K, seed):
     assert torch.equal(out, ref)
 
 
+def test_pi0_two_cameras_and_masked_camera_vs_reference():
+    """prepare_images / embed_prefix with several image streams (modeling_pi0.py:344-387, 529-547): the oracle with a list
+    of cameras is bit-exact against the reference, and a masked ("empty") camera is a no-op - the reference with the -1
+    image and an all-False mask equals the reference without that camera (what the CUDA path relies on to drop it)."""
+    from oracle import pi0_oracle as O
+    d = O.TINY
+    R, K, seed = 2, 2, 3
+    model, w = _ref_model(d, seed)
+    inp = O.make_inputs(d, R, K, seed=seed)
+    b = O.expand_to_batch(inp, K)
+    N = R * K
+    cam2 = torch.rand(1, 3, d.vis_image, d.vis_image, generator=torch.Generator().manual_seed(77)) * 2 - 1
+    cam2 = cam2.repeat(N, 1, 1, 1)
+    on, off = torch.ones(N, dtype=torch.bool), torch.zeros(N, dtype=torch.bool)
+    with torch.no_grad():
+        ref2 = model.sample_actions([b["image"], cam2], [on, on], b["tokens"], b["masks"], b["state"], noise=b["noise"].clone())
+        ref1 = model.sample_actions([b["image"]], [on], b["tokens"], b["masks"], b["state"], noise=b["noise"].clone())
+        refm = model.sample_actions([b["image"], torch.ones_like(cam2) * -1], [on, off], b["tokens"], b["masks"], b["state"],
+                                    noise=b["noise"].clone())
+    out2 = O.sample_actions(w, d, [b["image"], cam2], b["tokens"], b["masks"], b["state"], b["noise"], img_masks=[on, on])
+    assert torch.equal(out2, ref2)
+    outm = O.sample_actions(w, d, [b["image"], torch.ones_like(cam2) * -1], b["tokens"], b["masks"], b["state"], b["noise"],
+                            img_masks=[on, off])
+    assert torch.equal(outm, refm)
+    assert (ref2 - ref1).abs().max().item() > 1e-2      # the second camera matters ...
+    assert (refm - ref1).abs().max().item() <= 1e-2     # ... a masked one does not (bf16 GEMM blocking noise only)
+
+
 def test_pi0_dedup_is_exact_on_the_reference_itself():
     """one prefix per unique rephrase shared by its K samples, padded language tokens dropped -
     the de-duplicated schedule the CUDA path runs equals the reference's B = N batch (bit-exact on CPU)."""

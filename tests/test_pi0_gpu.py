@@ -144,3 +144,36 @@ def test_state_token_hoist_is_exact(R, K, monkeypatch):
         outs[flag] = runs[0]
         eng.close()
     assert torch.equal(outs["1"], outs[None])
+
+
+@pytest.mark.parametrize("name,R,K", [("TINY", 2, 2), ("MID", 2, 2)])
+def test_two_cameras_match_oracle_and_masked_camera_is_dropped(name, R, K):
+    """Several image streams per observation (prepare_images / embed_prefix, modeling_pi0.py:344-387, 529-547): a handle
+    built for 2 cameras against the oracle (itself bit-exact against the reference with 2 cameras,
+    tests/test_oracle_vs_reference.py); with one active camera the same handle matches the 1-camera oracle (an "empty"
+    camera is dropped by the host - shown to be a no-op on the reference itself in the same CPU test)."""
+    d = getattr(O, name)
+    w = O.make_pi0_weights(d, seed=2)
+    inp = O.make_inputs(d, R, K, seed=5)
+    cam2 = torch.rand(1, 3, d.vis_image, d.vis_image, generator=torch.Generator().manual_seed(77)) * 2 - 1
+    b = O.expand_to_batch(inp, K)
+    N = R * K
+    ref = O.sample_actions(w, d, [b["image"], cam2.repeat(N, 1, 1, 1)], b["tokens"], b["masks"], b["state"], b["noise"])
+    with O.truth_mode():
+        truth = O.sample_actions_dedup(O.truth_weights(w), d, [inp["image"], cam2], inp["tokens"], inp["masks"],
+                                       inp["state"], inp["noise"], K)
+    eng = build_pi0_engine(d, w, R, K, num_cameras=2)
+    imgs = torch.cat([inp["image"], cam2]).cuda().contiguous()  # [2, 3, H, W]
+    rest = (inp["tokens"].cuda(), inp["lens"].to(torch.int32).cuda(), inp["state"][0].cuda().contiguous(), inp["noise"].cuda())
+    outs = [eng.pi0_sample(imgs, *rest, K=K).cpu() for _ in range(3)]   # eager, capture, replay
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    action_gate(outs[0], ref, truth, f"{name} 2 cameras R={R} K={K}")
+    one = O.sample_actions(w, d, b["image"], b["tokens"], b["masks"], b["state"], b["noise"])
+    assert max_abs(ref, one) > 1e-2  # the second camera is really used
+    eng.set_active_cameras(1)
+    a1 = eng.pi0_sample(inp["image"][0].cuda().contiguous(), *rest, K=K).cpu()
+    # (not bit-identical to a 1-camera handle: the KV-cache stride differs, so other kernels may be picked)
+    action_gate(a1, one, pi0_truth(O, w, d, inp, K), f"{name} 1 of 2 cameras active R={R} K={K}")
+    eng.set_active_cameras(2)
+    assert torch.equal(eng.pi0_sample(imgs, *rest, K=K).cpu(), outs[0])
+    eng.close()

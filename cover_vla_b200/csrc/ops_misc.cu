@@ -1,6 +1,7 @@
 // Fused elementwise / normalisation kernels of the pi0 path.  All of them are HBM- or latency-bound:
 // 16-byte vectorised, coalesced accesses; one CTA per row (or per small group of rows); the rounding
 // points follow SURVEY.md Appendix A.
+#include <algorithm>
 #include "host_common.h"
 #include "ops.h"
 #include "ptx.cuh"
@@ -299,60 +300,102 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const bf16* __restr
 // layer_norm2, fc2 + residual -> next layer_norm1 / post_layernorm; reached through embed_image,
 // paligemma_with_expert.py:229-230).  h = bf16(bf16(sum_s P[s] + bias) + resid), y = LayerNorm(h) exactly as
 // layernorm_bf16_kernel computes it.
-__global__ void __launch_bounds__(256) layernorm_reduce_kernel(const float* __restrict__ P, int S, long split_stride,
+__global__ void __launch_bounds__(320) layernorm_reduce_kernel(const float* __restrict__ P, int S, long split_stride,
                                                                long ldp, const bf16* __restrict__ bias, const bf16* resid,
                                                                long ldr, const bf16* __restrict__ w,
                                                                const bf16* __restrict__ b, bf16* h_out, long ldh,
                                                                bf16* __restrict__ y, long ldy, int width, float eps) {
-  pdl_wait();
-  pdl_launch();
+  // One float4 of the row per thread when the row fits (width <= 4 * blockDim: the SigLIP tower's 1152 = 288 threads):
+  // everything stays in registers.  Loads that do not depend on the preceding kernel (norm weight / bias, linear bias)
+  // are issued before the dependency wait; then the residual and ALL partials of the element group are in flight at
+  // once (up to 8 per round) and summed in split order - the same bits as a one-at-a-time loop.
   extern __shared__ float hrow[];
   __shared__ float red[32];
   const int row = blockIdx.x;
+  const bool one = width <= static_cast<int>(blockDim.x) * 4;
+  const int i0 = threadIdx.x * 4;
+  float wreg[4] = {0.f, 0.f, 0.f, 0.f}, breg[4] = {0.f, 0.f, 0.f, 0.f}, lbias[4] = {0.f, 0.f, 0.f, 0.f};
+  if (one && i0 < width) {
+    const uint2 wv = *reinterpret_cast<const uint2*>(w + i0);
+    const uint2 bv = *reinterpret_cast<const uint2*>(b + i0);
+    const float2 g0 = unpack_bf16x2(wv.x), g1 = unpack_bf16x2(wv.y), h0 = unpack_bf16x2(bv.x), h1 = unpack_bf16x2(bv.y);
+    wreg[0] = g0.x, wreg[1] = g0.y, wreg[2] = g1.x, wreg[3] = g1.y;
+    breg[0] = h0.x, breg[1] = h0.y, breg[2] = h1.x, breg[3] = h1.y;
+    if (bias != nullptr) {
+      const uint2 v = *reinterpret_cast<const uint2*>(bias + i0);
+      const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y);
+      lbias[0] = f0.x, lbias[1] = f0.y, lbias[2] = f1.x, lbias[3] = f1.y;
+    }
+  }
+  pdl_wait();
+  pdl_launch();
   const float* pr = P + row * ldp;
   float s = 0.f;
-  for (int i = threadIdx.x * 4; i < width; i += blockDim.x * 4) {
+  float hreg[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = i0; i < width; i += blockDim.x * 4) {
+    const uint2 rv = *reinterpret_cast<const uint2*>(resid + row * ldr + i);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int sp = 0;
-    for (; sp + 4 <= S; sp += 4) {
-      const float4 a0 = *reinterpret_cast<const float4*>(pr + (sp + 0) * split_stride + i);
-      const float4 a1 = *reinterpret_cast<const float4*>(pr + (sp + 1) * split_stride + i);
-      const float4 a2 = *reinterpret_cast<const float4*>(pr + (sp + 2) * split_stride + i);
-      const float4 a3 = *reinterpret_cast<const float4*>(pr + (sp + 3) * split_stride + i);
-      acc.x = (((acc.x + a0.x) + a1.x) + a2.x) + a3.x;
-      acc.y = (((acc.y + a0.y) + a1.y) + a2.y) + a3.y;
-      acc.z = (((acc.z + a0.z) + a1.z) + a2.z) + a3.z;
-      acc.w = (((acc.w + a0.w) + a1.w) + a2.w) + a3.w;
+    for (; sp + 8 <= S; sp += 8) {
+      float4 a[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] = *reinterpret_cast<const float4*>(pr + (sp + q) * split_stride + i);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc.x += a[q].x, acc.y += a[q].y, acc.z += a[q].z, acc.w += a[q].w;
+    }
+    if (sp + 4 <= S) {
+      float4 a[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[q] = *reinterpret_cast<const float4*>(pr + (sp + q) * split_stride + i);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc.x += a[q].x, acc.y += a[q].y, acc.z += a[q].z, acc.w += a[q].w;
+      sp += 4;
     }
     for (; sp < S; ++sp) {
       const float4 a = *reinterpret_cast<const float4*>(pr + sp * split_stride + i);
       acc.x += a.x, acc.y += a.y, acc.z += a.z, acc.w += a.w;
     }
-    float bb[4] = {0.f, 0.f, 0.f, 0.f};
-    if (bias != nullptr) {
+    float bb[4] = {lbias[0], lbias[1], lbias[2], lbias[3]};
+    if (!one && bias != nullptr) {
       const uint2 v = *reinterpret_cast<const uint2*>(bias + i);
       const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y);
       bb[0] = f0.x, bb[1] = f0.y, bb[2] = f1.x, bb[3] = f1.y;
     }
-    const uint2 rv = *reinterpret_cast<const uint2*>(resid + row * ldr + i);
     const float2 r0 = unpack_bf16x2(rv.x), r1 = unpack_bf16x2(rv.y);
     const float hv[4] = {bf16_round(bf16_round(acc.x + bb[0]) + r0.x), bf16_round(bf16_round(acc.y + bb[1]) + r0.y),
                          bf16_round(bf16_round(acc.z + bb[2]) + r1.x), bf16_round(bf16_round(acc.w + bb[3]) + r1.y)};
     *reinterpret_cast<uint2*>(h_out + row * ldh + i) = make_uint2(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]));
-    *reinterpret_cast<float4*>(hrow + i) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+    if (one) {
+      hreg[0] = hv[0], hreg[1] = hv[1], hreg[2] = hv[2], hreg[3] = hv[3];
+    } else {
+      *reinterpret_cast<float4*>(hrow + i) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+    }
     s += hv[0] + hv[1] + hv[2] + hv[3];
   }
   const float mean = block_sum(s, red) / static_cast<float>(width);
   float vs = 0.f;
-  for (int i = threadIdx.x * 4; i < width; i += blockDim.x * 4) {
-    const float4 f = *reinterpret_cast<const float4*>(hrow + i);
-    vs += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean) + (f.z - mean) * (f.z - mean) +
-          (f.w - mean) * (f.w - mean);
+  if (one) {
+    if (i0 < width)
+      vs = (hreg[0] - mean) * (hreg[0] - mean) + (hreg[1] - mean) * (hreg[1] - mean) + (hreg[2] - mean) * (hreg[2] - mean) +
+           (hreg[3] - mean) * (hreg[3] - mean);
+  } else {
+    for (int i = i0; i < width; i += blockDim.x * 4) {
+      const float4 f = *reinterpret_cast<const float4*>(hrow + i);
+      vs += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean) + (f.z - mean) * (f.z - mean) +
+            (f.w - mean) * (f.w - mean);
+    }
   }
   const float var = block_sum(vs, red) / static_cast<float>(width);
   const float rstd = 1.0f / sqrtf(var + eps);
   bf16* yr = y + row * ldy;
-  for (int i = threadIdx.x * 4; i < width; i += blockDim.x * 4) {
+  if (one) {
+    if (i0 < width)
+      *reinterpret_cast<uint2*>(yr + i0) =
+          make_uint2(pack_bf16x2((hreg[0] - mean) * rstd * wreg[0] + breg[0], (hreg[1] - mean) * rstd * wreg[1] + breg[1]),
+                     pack_bf16x2((hreg[2] - mean) * rstd * wreg[2] + breg[2], (hreg[3] - mean) * rstd * wreg[3] + breg[3]));
+    return;
+  }
+  for (int i = i0; i < width; i += blockDim.x * 4) {
     const float4 f = *reinterpret_cast<const float4*>(hrow + i);
     const uint2 wv = *reinterpret_cast<const uint2*>(w + i);
     const uint2 bv = *reinterpret_cast<const uint2*>(b + i);
@@ -370,7 +413,9 @@ int layernorm_reduce(cudaStream_t st, const float* P, int S, long split_stride, 
               "layernorm_reduce needs 4-element aligned rows");
   CVB_REQUIRE(S >= 1 && resid != nullptr, "layernorm_reduce needs >= 1 partial and a residual");
   const size_t smem = static_cast<size_t>(width) * sizeof(float);
-  CVB_TRY(launch_pdl(layernorm_reduce_kernel, dim3(rows), dim3(256), smem, st, 1, P, S, split_stride, ldp, bias, resid, ldr,
+  // one float4 per thread up to 1280 columns (whole warps), 256 threads striding over wider rows
+  const int threads = width <= 1280 ? std::max(32, (width / 4 + 31) / 32 * 32) : 256;
+  CVB_TRY(launch_pdl(layernorm_reduce_kernel, dim3(rows), dim3(threads), smem, st, 1, P, S, split_stride, ldp, bias, resid, ldr,
                      w, b, h_out, ldh, y, ldy, width, eps));
   CVB_LAUNCHED();
   return 0;

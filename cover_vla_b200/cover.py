@@ -93,6 +93,10 @@ class CoverStep:
         # default: the whole decision is one C-ABI call / one CUDA graph (cvb_cover_step) with the verifier context forked
         # after the prefix; False = three calls (cvb_pi0_sample, cvb_format_trajectories, cvb_verifier_score)
         self.fused = True
+        # per-task prompt cache: set True while the verifier instruction (x.vf_tokens) is the one of
+        # the previous decision - the verifier's text tower is then skipped (cvb_verifier_hold_text); the caller owns this
+        # promise, nothing is compared on the device.  Default False: every decision encodes the text, like the reference.
+        self.hold_text = False
         self._side = torch.cuda.Stream(device=engine.device)
 
     def sample_and_score(self, x: CoverInputs):
@@ -101,14 +105,15 @@ class CoverStep:
         R = x.lang_tokens.shape[0]
         if self.fused:
             return e.cover_step(x.image, x.lang_tokens, x.lang_len, x.state, x.noise, self.K, x.vf_image, x.vf_tokens,
-                                self.p01, self.p99, past=x.past, n_future=self.n_future, lang_len_max=x.lang_len_max)
+                                self.p01, self.p99, past=x.past, n_future=self.n_future, lang_len_max=x.lang_len_max,
+                                hold_text=self.hold_text)
         if self.overlap_context:
             cur = torch.cuda.current_stream(e.device)
             self._side.wait_stream(cur)
             # critical path first: one graph launch for the whole sampler, then the side work
             actions = e.pi0_sample(x.image, x.lang_tokens, x.lang_len, x.state, x.noise, K=self.K, lang_len_max=x.lang_len_max)
             with torch.cuda.stream(self._side):
-                e.verifier_context(x.vf_image, x.vf_tokens)
+                e.verifier_context(x.vf_image, x.vf_tokens, hold_text=self.hold_text)
             traj = format_trajectories(actions, x.past, e.cfg.vf_history, self.n_future, self.p01, self.p99)
             cur.wait_stream(self._side)
             scores, gmean, bidx, bscore = e.verifier_score(None, None, traj, R, self.K,
@@ -116,7 +121,7 @@ class CoverStep:
         else:
             actions = e.pi0_sample(x.image, x.lang_tokens, x.lang_len, x.state, x.noise, K=self.K, lang_len_max=x.lang_len_max)
             traj = format_trajectories(actions, x.past, e.cfg.vf_history, self.n_future, self.p01, self.p99)
-            scores, gmean, bidx, bscore = e.verifier_score(x.vf_image, x.vf_tokens, traj, R, self.K)
+            scores, gmean, bidx, bscore = e.verifier_score(x.vf_image, x.vf_tokens, traj, R, self.K, hold_text=self.hold_text)
         return actions, traj, scores, gmean, bidx, bscore
 
     def __call__(self, x: CoverInputs, gate_threshold: float = 0.1):
@@ -158,6 +163,7 @@ class BatchedCoverStep:
         self.K = samples_per_rephrase
         self.n_future = n_future or engine.cfg.chunk_size
         self.p01, self.p99 = p01, p99
+        self.hold_text = False  # per-task prompt cache, as CoverStep.hold_text (all B instructions unchanged)
 
     @staticmethod
     def stack(xs: list[CoverInputs]) -> CoverInputs:
@@ -178,7 +184,7 @@ class BatchedCoverStep:
         [B,N], group_mean [B,R], best_idx [B], best_score [B])."""
         return self.engine.cover_step_batch(xb.image, xb.lang_tokens, xb.lang_len, xb.state, xb.noise, self.K, xb.vf_image,
                                             xb.vf_tokens, self.p01, self.p99, past=xb.past, n_future=self.n_future,
-                                            lang_len_max=xb.lang_len_max)
+                                            lang_len_max=xb.lang_len_max, hold_text=self.hold_text)
 
     def __call__(self, xb: CoverInputs, gate_threshold: float = 0.1):
         """B decisions incl. the one D2H read: (best_idx [B], best_score [B], winner actions [B, chunk, 7]) on the host."""

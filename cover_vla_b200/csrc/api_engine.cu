@@ -143,6 +143,11 @@ int cvb_pi0_set_lang_len_hint(cvb_handle* h, int max_valid_tokens) {
   return 0;
 }
 
+int cvb_verifier_hold_text(cvb_handle* h, int hold) {
+  CVB_REQUIRE(h != nullptr, "null handle");
+  return cvb::verifier_hold_text(h, hold);
+}
+
 int cvb_pi0_set_active_cameras(cvb_handle* h, int cameras) {
   CVB_REQUIRE(h != nullptr, "null handle");
   CVB_REQUIRE(cameras >= 0 && cameras <= h->cams_max(), "cameras must be 0 (all) .. num_cameras");

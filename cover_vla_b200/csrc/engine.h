@@ -213,6 +213,8 @@ int pi0_stage_inputs(cvb_handle* h, const float* image, const int64_t* tokens, c
 int pi0_enqueue(cvb_handle* h, cudaStream_t st, int R, int K, int part, int B = 1);  // 0 = vision + prefix, 1 = denoise loop
 float* pi0_actions_buffer(cvb_handle* h);
 int verifier_stage_context_inputs(cvb_handle* h, const float* image, const int64_t* tokens, cudaStream_t st, int B = 1);
+bool verifier_text_cached(cvb_handle* h, int nb);
+int verifier_hold_text(cvb_handle* h, int hold);
 int verifier_enqueue_context(cvb_handle* h, cudaStream_t st, int obs = 0, int nb = 1);  // slots [obs, obs + nb)
 int verifier_enqueue_score(cvb_handle* h, cudaStream_t st, int N, int R, int K, int B = 1);
 float* verifier_traj_buffer(cvb_handle* h);

@@ -58,7 +58,7 @@ int cover_step(cvb_handle* h, const float* image, const int64_t* lang_tokens, co
   if (num_past > 0)
     CVB_CUDA(cudaMemcpyAsync(cs.past, past, (size_t)B * num_past * 7 * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
-  const long key = ((long)h->cams() << 56) | ((long)h->lang_rows() << 48) | ((long)num_past << 40) | ((long)n_future << 32) | ((long)B << 24) |
+  const long key = ((long)(verifier_text_cached(h, B) ? 1 : 0) << 60) | ((long)h->cams() << 56) | ((long)h->lang_rows() << 48) | ((long)num_past << 40) | ((long)n_future << 32) | ((long)B << 24) |
                    ((long)R << 12) | K;
   CVB_TRY(cs.graphs.run(c.use_cuda_graph != 0, key, st, [&](cudaStream_t s0) {
     // One observation: the verifier's image/text side forks AFTER the prefix (whose GEMMs fill every SM) and hides under

@@ -64,6 +64,10 @@ struct VerifierState {
   int* bidx = nullptr;
   float* bscore = nullptr;
   bool context_valid = false;
+  // per-task prompt cache (cvb_verifier_hold_text): while text_hold is set and the text features of
+  // `text_nb` observations are resident (Tn), a context call skips the text tower
+  bool text_hold = false;
+  int text_nb = 0;
   GraphCache ctx_graph, traj_graph;
   // the ensemble members' trajectory encoders are independent until the fused score: one branch (stream) per member
   std::vector<cudaStream_t> mstream;
@@ -542,12 +546,15 @@ static int run_context(cvb_handle* h, cudaStream_t st, int obs0 = 0, int nb = 1)
   CVB_TRY(gemm(st, s.patches, s.kpad, s.w_patch, s.kpad, nb * Np, Wd, s.kpad, EPI_RESID, s.hv, Wd, s.patch_b,
                nb > 1 ? s.pos_tiled : s.pos_embed, Wd));
   CVB_TRY(run_blocks(st, s, s.vis, s.hv, Np, Wd, c.vf_heads, c.vf_mlp, true, s.pfeat, nb));
-  CVB_TRY(embed_tokens_pos(st, s.tok_emb, s.txt_pos, in_tokens, s.ht, nb * Tt, Wd, Tt));
-  CVB_TRY(run_blocks(st, s, s.txt, s.ht, Tt, Wd, c.vf_heads, c.vf_mlp, false, nullptr, nb));
-  CVB_TRY(layernorm_bf16(st, s.ht, Wd, s.lnf_w, s.lnf_b, s.xv, Wd, nb * Tt, Wd, 1e-6f));
-  CVB_TRY(gemm(st, s.xv, Wd, s.wproj, Wd, nb * Tt, Wd, Wd, EPI_STORE, s.tfeat, Wd, s.bproj));
   CVB_TRY(l2norm_rows_bf16_to_f32(st, s.pfeat, Wd, s.Pn, nb * Np, Wd));
-  CVB_TRY(l2norm_rows_bf16_to_f32(st, s.tfeat, Wd, s.Tn, nb * Tt, Wd));
+  if (!(s.text_hold && s.text_nb == nb)) {  // (held: the caller vouches that the instructions did not change - Tn is resident)
+    CVB_TRY(embed_tokens_pos(st, s.tok_emb, s.txt_pos, in_tokens, s.ht, nb * Tt, Wd, Tt));
+    CVB_TRY(run_blocks(st, s, s.txt, s.ht, Tt, Wd, c.vf_heads, c.vf_mlp, false, nullptr, nb));
+    CVB_TRY(layernorm_bf16(st, s.ht, Wd, s.lnf_w, s.lnf_b, s.xv, Wd, nb * Tt, Wd, 1e-6f));
+    CVB_TRY(gemm(st, s.xv, Wd, s.wproj, Wd, nb * Tt, Wd, Wd, EPI_STORE, s.tfeat, Wd, s.bproj));
+    CVB_TRY(l2norm_rows_bf16_to_f32(st, s.tfeat, Wd, s.Tn, nb * Tt, Wd));
+    s.text_nb = nb;
+  }
   CVB_TRY(run_heads_context(h, st, obs0, nb));
   return 0;
 }
@@ -640,7 +647,8 @@ int verifier_score(cvb_handle* h, const float* image, const int64_t* tokens, con
     CVB_CUDA(cudaMemcpyAsync(s.in_image, image, (size_t)3 * c.vf_image * c.vf_image * sizeof(float),
                              cudaMemcpyDeviceToDevice, st));
     CVB_CUDA(cudaMemcpyAsync(s.in_tokens, tokens, c.vf_text_ctx * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
-    CVB_TRY(s.ctx_graph.run(c.use_cuda_graph != 0, 0, st, [&](cudaStream_t cs) { return run_context(h, cs); }));
+    CVB_TRY(s.ctx_graph.run(c.use_cuda_graph != 0, verifier_text_cached(h, 1) ? 1 : 0, st,
+                            [&](cudaStream_t cs) { return run_context(h, cs); }));
     s.context_valid = true;
   }
   CVB_CUDA(cudaMemcpyAsync(s.in_traj, traj, (size_t)N * c.vf_history * c.vf_action_dim * sizeof(float),
@@ -696,6 +704,14 @@ int verifier_enqueue_score(cvb_handle* h, cudaStream_t st, int N, int R, int K, 
 
 float* verifier_traj_buffer(cvb_handle* h) { return h->vf->in_traj; }
 
+// true when a context call for nb observations will skip the text tower (part of the callers' graph keys)
+bool verifier_text_cached(cvb_handle* h, int nb) { return h->vf != nullptr && h->vf->text_hold && h->vf->text_nb == nb; }
+int verifier_hold_text(cvb_handle* h, int hold) {
+  CVB_REQUIRE(h->vf != nullptr, "verifier not configured");
+  h->vf->text_hold = hold != 0;
+  return 0;
+}
+
 int verifier_copy_results(cvb_handle* h, int N, int R, float* scores, float* group_mean, int32_t* best_idx,
                           float* best_score, cudaStream_t st, int B) {
   VerifierState& s = *h->vf;
@@ -720,7 +736,8 @@ int verifier_context(cvb_handle* h, const float* image, const int64_t* tokens, c
   CVB_CUDA(cudaMemcpyAsync(s.in_image, image, (size_t)3 * c.vf_image * c.vf_image * sizeof(float),
                            cudaMemcpyDeviceToDevice, st));
   CVB_CUDA(cudaMemcpyAsync(s.in_tokens, tokens, c.vf_text_ctx * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
-  CVB_TRY(s.ctx_graph.run(c.use_cuda_graph != 0, 0, st, [&](cudaStream_t cs) { return run_context(h, cs); }));
+  CVB_TRY(s.ctx_graph.run(c.use_cuda_graph != 0, verifier_text_cached(h, 1) ? 1 : 0, st,
+                            [&](cudaStream_t cs) { return run_context(h, cs); }));
   s.context_valid = true;
   return 0;
 }

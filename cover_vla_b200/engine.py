@@ -124,6 +124,7 @@ class Engine:
         L.cvb_pi0_sample.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.cvb_pi0_set_lang_len_hint.argtypes = [C.c_void_p, C.c_int]
         L.cvb_pi0_set_active_cameras.argtypes = [C.c_void_p, C.c_int]
+        L.cvb_verifier_hold_text.argtypes = [C.c_void_p, C.c_int]
         L.cvb_pi0_run_phase.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.cvb_debug_copy.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.cvb_debug_copy.restype = C.c_int64
@@ -204,6 +205,13 @@ class Engine:
             _lib.check(self.lib.cvb_pi0_set_lang_len_hint(self._h, n))
             self._lang_hint = n
 
+    def verifier_hold_text(self, hold: bool):
+        """Per-task prompt cache: while held, context computations reuse the resident text-tower features (the caller
+        vouches that the instruction tokens did not change; include/coverb200.h cvb_verifier_hold_text)."""
+        if bool(hold) != getattr(self, "_hold_text", False):
+            _lib.check(self.lib.cvb_verifier_hold_text(self._h, 1 if hold else 0))
+            self._hold_text = bool(hold)
+
     def set_active_cameras(self, cameras: int | None):
         """Cameras per observation in the following calls (None / 0 = cfg.num_cameras); masked cameras are dropped by the
         caller, which is exact (include/coverb200.h)."""
@@ -267,11 +275,12 @@ class Engine:
         return out
 
     def cover_step_batch(self, images, lang_tokens, lang_len, states, noise, K: int, vf_images, vf_tokens, p01, p99,
-                         past=None, n_future: int | None = None, lang_len_max: int | None = None):
+                         past=None, n_future: int | None = None, lang_len_max: int | None = None, hold_text: bool = False):
         """B whole decisions in one graph (cvb_cover_step_batch).  Shapes as pi0_sample_batch plus vf_images f32
         [B,3,S,S], vf_tokens i64 [B,ctx], past f32 [B,num_past,7] or None.  Returns device tensors (actions
         [B,N,chunk,A], traj [B,N,H,7], scores [B,N], group_mean [B,R], best_idx i32 [B], best_score [B])."""
         cfg = self.cfg
+        self.verifier_hold_text(hold_text)  # per-task prompt cache: explicit per call, never inherited from another caller
         B, R = lang_tokens.shape[0], lang_tokens.shape[1]
         N = R * K
         assert B <= cfg.max_observations, "engine was built with a smaller max_observations"
@@ -306,11 +315,13 @@ class Engine:
         return actions, traj, scores, gmean, bidx, bscore
 
     # ------------------------------------------------------------------ verifier
-    def verifier_score(self, image, text_tokens, traj, R: int, K: int, recompute_context: bool = True):
+    def verifier_score(self, image, text_tokens, traj, R: int, K: int, recompute_context: bool = True,
+                       hold_text: bool = False):
         """image f32 [3,S,S] (or None to reuse the context); text_tokens i64 [ctx]; traj f32 [N,H,A] left-padded
         with -5.  Returns device tensors (scores [N], group_mean [R], best_idx i32 [1], best_score [1]).
         R == 0: scores only."""
         cfg = self.cfg
+        self.verifier_hold_text(hold_text)  # per-task prompt cache: explicit per call, never inherited from another caller
         N = traj.shape[0]
         assert traj.dtype == torch.float32 and tuple(traj.shape[1:]) == (cfg.vf_history, cfg.vf_action_dim)
         assert traj.is_cuda and traj.is_contiguous()
@@ -330,10 +341,11 @@ class Engine:
         return scores, gmean, bidx, bscore
 
     def cover_step(self, image, lang_tokens, lang_len, state, noise, K: int, vf_image, vf_tokens, p01, p99, past=None,
-                   n_future: int | None = None, lang_len_max: int | None = None):
+                   n_future: int | None = None, lang_len_max: int | None = None, hold_text: bool = False):
         """One whole decision (cvb_cover_step): sample -> format -> score -> select in one graph.  Returns device
         tensors (actions [N,chunk,A], traj [N,H,7], scores [N], group_mean [R], best_idx i32 [1], best_score [1])."""
         cfg = self.cfg
+        self.verifier_hold_text(hold_text)  # per-task prompt cache: explicit per call, never inherited from another caller
         R = lang_tokens.shape[0]
         N = R * K
         assert tuple(noise.shape) == (N, cfg.chunk_size, cfg.max_action_dim) and noise.dtype == torch.float32
@@ -362,10 +374,11 @@ class Engine:
                                                _lib.ptr(bidx), _lib.ptr(bscore), _lib.stream_ptr()))
         return actions, traj, scores, gmean, bidx, bscore
 
-    def verifier_context(self, image, text_tokens):
+    def verifier_context(self, image, text_tokens, hold_text: bool = False):
         """Image/text side only (trunk + image-text heads) on the current stream; pair with
         verifier_score(None, None, traj, ..., recompute_context=False)."""
         cfg = self.cfg
+        self.verifier_hold_text(hold_text)  # per-task prompt cache: explicit per call, never inherited from another caller
         assert image.dtype == torch.float32 and image.numel() == 3 * cfg.vf_image ** 2 and image.is_contiguous()
         assert text_tokens.dtype == torch.int64 and text_tokens.numel() == cfg.vf_text_ctx
         self.ctx_generation += 1

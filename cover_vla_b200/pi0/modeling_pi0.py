@@ -211,6 +211,7 @@ class PI0Policy:
         self.normalize_inputs = _Normalize(config.input_features, config.normalization_mapping, dataset_stats, False)
         self.unnormalize_outputs = _Normalize(config.output_features, config.normalization_mapping, dataset_stats, True)
         self.language_tokenizer = language_tokenizer
+        self._prompt_cache: dict = {}
         if engine is None:
             if state_dict is None:
                 raise ValueError("PI0Policy needs the reference state dict (or a finalized Engine)")
@@ -335,8 +336,19 @@ class PI0Policy:
         if self.language_tokenizer is None:
             raise RuntimeError("no language tokenizer available offline: pass `lang_tokens` / `lang_masks` in the batch")
         tasks = [t if t.endswith("\n") else f"{t}\n" for t in batch["task"]]
-        tok = self.language_tokenizer.__call__(tasks, padding="max_length", padding_side="right",
-                                               max_length=self.config.tokenizer_max_length, return_tensors="pt",
-                                               truncation=True)
-        self.model.lang_len_hint = int(tok["attention_mask"].sum(dim=1).max())  # host tensor: no device sync
-        return tok["input_ids"].to(device=device), tok["attention_mask"].to(device=device, dtype=torch.bool)
+        # per-task prompt cache: the prompts of an episode are static between the instruction
+        # swaps of run_simpler_eval_with_openpi.py:409, so the tokenizer run, the H2D copy and the length bound of the
+        # last few prompt sets are kept (device tensors; same values the tokenizer would return again)
+        key = (tuple(tasks), str(device), id(self.language_tokenizer))
+        hit = self._prompt_cache.get(key)
+        if hit is None:
+            tok = self.language_tokenizer.__call__(tasks, padding="max_length", padding_side="right",
+                                                   max_length=self.config.tokenizer_max_length, return_tensors="pt",
+                                                   truncation=True)
+            hit = (tok["input_ids"].to(device=device), tok["attention_mask"].to(device=device, dtype=torch.bool),
+                   int(tok["attention_mask"].sum(dim=1).max()))  # host tensor: no device sync
+            if len(self._prompt_cache) >= 8:
+                self._prompt_cache.pop(next(iter(self._prompt_cache)))
+            self._prompt_cache[key] = hit
+        self.model.lang_len_hint = hit[2]
+        return hit[0], hit[1]

@@ -154,6 +154,13 @@ class EfficientEnsembleMerged:
         self._ctx_key = key
         if not recompute:
             return None, None, False
+        # per-task prompt cache: the image changes every tick, the instruction only at the swaps of
+        # run_simpler_eval_with_openpi.py:409 - while the tokens are the ones this wrapper encoded last and nobody else
+        # rewrote the engine's context, the text tower is skipped (cvb_verifier_hold_text)
+        tkey = tuple(tok.tolist())
+        self._hold_text = (tkey == getattr(self, "_text_key", None) and
+                           self.engine.ctx_generation == getattr(self, "_ctx_gen", -1))
+        self._text_key = tkey
         self._ctx_gen = self.engine.ctx_generation + 1  # the verifier_score(recompute_context=True) that follows bumps it
         return img.to(self.device).contiguous(), tok.to(self.device).contiguous(), True
 
@@ -180,7 +187,8 @@ class EfficientEnsembleMerged:
         img, tok, recompute = self._set_context(images[0], instructions[0])
         traj = self._pad(all_action_histories).to(self.device, non_blocking=True)
         scores, gmean, bidx, bscore = self.engine.verifier_score(img, tok, traj, num_groups, group_size,
-                                                                 recompute_context=recompute)
+                                                                 recompute_context=recompute,
+                                                                 hold_text=recompute and self._hold_text)
         out = torch.stack([bscore[0], bidx[0].to(torch.float32)]).cpu()  # the one D2H sync (:439 does .item())
         max_score, gidx = float(out[0]), int(out[1])
         all_same = len(set(instructions)) == 1 if isinstance(instructions[0], str) else False
@@ -195,7 +203,8 @@ class EfficientEnsembleMerged:
         # :295-307 - diagonal of [N,512]@[512,N] with N identical image-text rows == the score vector
         img, tok, recompute = self._set_context(image, instruction)
         traj = self._pad(possible_action_histories).to(self.device)
-        scores, *_ = self.engine.verifier_score(img, tok, traj, 0, 1, recompute_context=recompute)
+        scores, *_ = self.engine.verifier_score(img, tok, traj, 0, 1, recompute_context=recompute,
+                                                hold_text=recompute and self._hold_text)
         scores = scores.cpu().numpy()
         idx = int(scores.argmax())
         return possible_action_histories[idx], {str(i): float(scores[i]) for i in range(len(scores))}
@@ -204,7 +213,7 @@ class EfficientEnsembleMerged:
         """(patch_features [1,Np,W], text_features [1,ctx,W]) fp32, L2-normalised (:188-192)."""
         cfg = self.engine.cfg
         dummy = torch.full((1, cfg.vf_history, cfg.vf_action_dim), 0.0, device=self.device)
-        self._ctx_key = None
+        self._ctx_key = self._text_key = None
         self.engine.verifier_score(img_tensor.reshape(3, cfg.vf_image, cfg.vf_image).to(self.device, torch.float32).contiguous(),
                                    text_tokens.reshape(-1).to(self.device, torch.int64).contiguous(), dummy, 0, 1)
         Np = (cfg.vf_image // cfg.vf_patch) ** 2

@@ -229,6 +229,13 @@ CVB_API int cvb_verifier_score(cvb_handle* h, const float* image, const int64_t*
  * on the sampled actions, so a host can enqueue it on a second stream while cvb_pi0_sample runs, then call
  * cvb_verifier_score(..., recompute_context = 0) after joining the streams. */
 CVB_API int cvb_verifier_context(cvb_handle* h, const float* image, const int64_t* text_tokens, void* stream);
+/* Per-task prompt cache: the instruction of an episode is static between the swaps of
+ * run_simpler_eval_with_openpi.py:409, and the text tower's output depends on nothing else.  hold = 1: the caller vouches
+ * that the text tokens of the following context computations (cvb_verifier_context / _score / cvb_cover_step[_batch]) equal
+ * those of the previous one - the resident text features are reused and the text tower (24 of the context's 48 transformer
+ * blocks) is skipped; a call with a different observation count than the resident features still computes it.  hold = 0
+ * (default): every context call runs the text tower, like the reference. */
+CVB_API int cvb_verifier_hold_text(cvb_handle* h, int hold);
 
 /* Sampler -> verifier action formatting on the device (replaces process_inputs(verifier_action=True),
  * eval_utils.py:172-221, BridgeSimplerAdapter.postprocess_verifier, INT-ACT/src/experiments/env_adapters/

@@ -66,6 +66,45 @@ def test_cover_step_matches_oracle():
     eng.close()
 
 
+def test_prompt_cache_hold_text_is_exact():
+    """cvb_verifier_hold_text (per-task prompt cache): with the instruction unchanged the decision
+    with the text tower skipped equals the full one bit for bit - fused step, eager and graph replay, single and batched;
+    releasing the hold re-encodes a new instruction."""
+    from cover_vla_b200.cover import BatchedCoverStep, CoverInputs, CoverStep
+    d, v = O.TINY, V.VTINY
+    R, K, B = 2, 2, 2
+    eng = build_full_engine(d, O.make_pi0_weights(d, 0), v, V.make_verifier_weights(v, 0), R, K, max_observations=B)
+    xs = []
+    for b in range(B):
+        inp = O.make_inputs(d, R, K, seed=20 + b)
+        vin = V.make_inputs(v, 1, seed=20 + b)
+        xs.append(CoverInputs(image=inp["image"][0].cuda().contiguous(), lang_tokens=inp["tokens"].cuda(),
+                              lang_len=inp["lens"].to(torch.int32).cuda(), state=inp["state"][0].cuda().contiguous(),
+                              noise=inp["noise"].cuda(), vf_image=vin["image"][0].cuda().contiguous(),
+                              vf_tokens=vin["tokens"][0].cuda(), past=None))
+    step = CoverStep(eng, K)
+    base = [t.clone() for t in step.sample_and_score(xs[0])]
+    step.hold_text = True
+    for _ in range(3):  # eager, capture, replay of the held variant
+        held = step.sample_and_score(xs[0])
+        assert all(torch.equal(a, b) for a, b in zip(held, base))
+    # a new image with the same instruction: still exact against the un-held computation
+    x2 = CoverInputs(**{**xs[0].__dict__, "vf_image": xs[1].vf_image})
+    held2 = [t.clone() for t in step.sample_and_score(x2)]
+    step.hold_text = False
+    full2 = step.sample_and_score(x2)
+    assert all(torch.equal(a, b) for a, b in zip(held2, full2))
+    assert not torch.equal(full2[2], base[2])
+    # batched: B observations
+    bstep = BatchedCoverStep(eng, K)
+    xb = BatchedCoverStep.stack(xs)
+    bbase = [t.clone() for t in bstep.sample_and_score(xb)]
+    bstep.hold_text = True
+    for _ in range(3):
+        assert all(torch.equal(a, b) for a, b in zip(bstep.sample_and_score(xb), bbase))
+    eng.close()
+
+
 def test_policy_with_two_cameras_and_a_missing_one():
     """PI0Policy.select_action with two image keys (prepare_images, modeling_pi0.py:344-387): both present -> two image
     streams; one key missing from the batch -> the reference would add a masked -1 image (a no-op), the mirror runs the

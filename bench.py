@@ -53,7 +53,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -64,6 +64,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self):
+        """Start of the timed region: only rows read after this call are reported (the sampler is started before the
+        warm-up so that nvidia-smi's start-up time does not eat a short timed region)."""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -72,8 +77,12 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        first = getattr(self, "first", 0)
+        rows, window = self.rows[first:], "timed region"
+        if not rows and self.rows:  # timed region shorter than one sampling period: the last warm-up samples (same load)
+            rows, window = self.rows[-3:], "warm-up steps right before the timed region (it was shorter than one sampling period)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -83,7 +92,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -188,6 +197,8 @@ def run_gpu(args):
 
     # ---- warm-up: the first call of a shape runs every kernel eagerly (this is where the launches of one decision are
     # counted), the second is captured into the CUDA graph, later ones replay it
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     l0 = lib.cvb_launch_count()
     out = one_step()
     torch.cuda.synchronize()
@@ -198,9 +209,8 @@ def run_gpu(args):
     traj0 = out[1] if sstep is None else step.sample_and_score(sstep_inputs(x, K, world, rank))[1]
 
     # ---- timed region: `steps` decisions, device-resident inputs, CUDA events, max over ranks
-    clocks = ClockSampler(local_rank)
     barrier()
-    clocks.start()
+    clocks.mark()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record()
     for i in range(args.steps):

@@ -90,6 +90,8 @@ int gemm(cudaStream_t st, const bf16* A, long lda, const bf16* Wt, long ldw, int
   GemmCall c;
   c.A = A, c.lda = lda, c.W = Wt, c.ldw = ldw, c.M = M, c.N = N, c.K = K, c.epi = epi;
   c.C = C, c.ldc = ldc, c.bias = bias, c.resid = resid, c.ldr = ldr;
+  static const int cap = getenv("CVB_CTX_MAX_CTAS") != nullptr ? atoi(getenv("CVB_CTX_MAX_CTAS")) : 0;
+  c.max_ctas = cap;
   return gemm_bf16(st, c);
 }
 int sg(cudaStream_t st, const float* A, long lda, const float* Wt, long ldw, int M, int N, int K, float* C, long ldc,

@@ -90,8 +90,13 @@ int gemm(cudaStream_t st, const bf16* A, long lda, const bf16* Wt, long ldw, int
   GemmCall c;
   c.A = A, c.lda = lda, c.W = Wt, c.ldw = ldw, c.M = M, c.N = N, c.K = K, c.epi = epi;
   c.C = C, c.ldc = ldc, c.bias = bias, c.resid = resid, c.ldr = ldr;
-  static const int cap = getenv("CVB_CTX_MAX_CTAS") != nullptr ? atoi(getenv("CVB_CTX_MAX_CTAS")) : 0;
-  c.max_ctas = cap;
+  // One image's trunk (M = 576) runs beside the denoise loop, which is bound by L2 -> SM bytes: what the
+  // step pays for this side work is the L2 traffic and the SMs it takes, not its own latency.  128-wide tiles (half the
+  // activation re-reads and half the CTAs of the 64-wide tiles the stand-alone cost model picks for o_proj / fc2) make the
+  // context 0.2 ms slower alone (4.06 -> 4.25 ms) and the decision 0.2-0.4 ms faster (tools/overlap_timeline.py: the
+  // context costs the critical path 2.0 ms of its 4 ms).  CVB_CTX_BN = 0 restores the automatic choice, 64 / 256 force.
+  static const int ctx_bn = getenv("CVB_CTX_BN") != nullptr ? atoi(getenv("CVB_CTX_BN")) : 128;
+  if (M > 256 && M < 1024 && ctx_bn > 0) c.force_bn = ctx_bn;
   return gemm_bf16(st, c);
 }
 int sg(cudaStream_t st, const float* A, long lda, const float* Wt, long ldw, int M, int N, int K, float* C, long ldc,

@@ -27,7 +27,6 @@ struct GemmCall {
   int n_out = 0;               // EPI_GEGLU: intermediate size
   const int* m_dev = nullptr;  // optional device-side row count
   int force_bn = 0;            // 0 = heuristic, else 64 / 128 / 256
-  int max_ctas = 0;            // > 0: cap the persistent grid (work that shares the GPU with a latency-critical stream)
 };
 int gemm_bf16(cudaStream_t st, const GemmCall& c);
 // Split-K GEMM (M <= 256) that leaves S fp32 partial products in C = float[S][M][ldc] (epi / bias / resid unused);

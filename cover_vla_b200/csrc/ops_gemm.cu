@@ -100,8 +100,7 @@ int launch_2sm(cudaStream_t st, const GemmCall& c) {
   auto kern = gemm_bf16_tcgen05_2sm<EPI>;
   CVB_TRY(ensure_dyn_smem(kern, GEMM2_SMEM));
   const int tiles = ((c.M + 255) / 256) * ((c.N + 255) / 256);
-  int pairs = std::min(tiles, device_sm_count() / 2);
-  if (c.max_ctas > 0) pairs = std::max(1, std::min(pairs, c.max_ctas / 2));
+  const int pairs = std::min(tiles, device_sm_count() / 2);
   CVB_TRY(launch_pdl(kern, dim3(2 * pairs), dim3(GEMM_THREADS), GEMM2_SMEM, st, 2, tmA, tmB, g));
   CVB_LAUNCHED();
   return 0;
@@ -183,8 +182,7 @@ int gemm_bf16(cudaStream_t st, const GemmCall& c) {
     // at 4/3 the cost (36 -> 24 us at K = 4096).
     long best = 0;
     for (int cand : {256, 128, 64}) {
-      const int ctas = c.max_ctas > 0 && c.max_ctas < sms ? c.max_ctas : sms;
-      const long rounds = (tiles(cand) + ctas - 1) / ctas;
+      const long rounds = (tiles(cand) + sms - 1) / sms;
       const long cost = rounds * (cand == 256 ? 6 : cand == 128 ? 4 : 3);
       if (bn == 0 || cost < best) bn = cand, best = cost;
     }
@@ -192,7 +190,6 @@ int gemm_bf16(cudaStream_t st, const GemmCall& c) {
   CVB_REQUIRE(bn == 64 || bn == 128 || bn == 256, "BN must be 64, 128 or 256");
   int grid = tiles(bn);
   if (grid > sms) grid = sms;
-  if (c.max_ctas > 0 && grid > c.max_ctas) grid = c.max_ctas;
   switch (c.epi) {
     case EPI_STORE:
       return launch_bn<EPI_STORE>(st, c, bn, grid);

@@ -53,6 +53,11 @@ int cvb_op_rmsnorm_reduce(const float* P, int S, int64_t split_stride, int64_t l
                              (cvb::bf16*)h_out, ldh, (cvb::bf16*)y, ldy, rows, width, eps);
 }
 
+int cvb_op_rmsnorm(const void* x, int x_is_f32, int64_t ldx, const void* w, int w_is_f32, void* y, int64_t ldy, int rows,
+                   int width, float eps, void* stream) {
+  return cvb::rmsnorm((cudaStream_t)stream, x, x_is_f32, ldx, w, w_is_f32, (cvb::bf16*)y, ldy, rows, width, eps, nullptr);
+}
+
 int cvb_op_layernorm_reduce(const float* P, int S, int64_t split_stride, int64_t ldp, const void* bias, const void* resid,
                             int64_t ldr, const void* w, const void* b, void* h_out, int64_t ldh, void* y, int64_t ldy,
                             int rows, int width, float eps, void* stream) {

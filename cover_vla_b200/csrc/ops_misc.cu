@@ -99,9 +99,75 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const void* __restrict__ x
   }
 }
 
+// One WARP per row (bf16 x, bf16 w, width = NV * 256 <= 2048): the whole row sits in registers (NV 16-byte loads in flight
+// per lane), the norm weight is loaded before the dependency wait, the reduction is five shuffles - no block barrier, one
+// pass over x.  The prefix runs this 35 x on 2240 rows x 2048: 7.0 -> 3.5 us per launch against the CTA-per-row kernel.
+template <int NV>
+__global__ void __launch_bounds__(256) rmsnorm_warp_kernel(const bf16* __restrict__ x, long ldx, const bf16* __restrict__ w,
+                                                           bf16* __restrict__ y, long ldy, int rows, float eps,
+                                                           const int* __restrict__ rows_dev) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  uint4 wv[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) wv[v] = *reinterpret_cast<const uint4*>(w + (v * 32 + lane) * 8);
+  pdl_wait();
+  pdl_launch();
+  if (row >= rows || (rows_dev != nullptr && row >= *rows_dev)) return;
+  const bf16* xr = x + row * ldx;
+  uint4 xv[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) xv[v] = *reinterpret_cast<const uint4*>(xr + (v * 32 + lane) * 8);
+  float ss = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const uint32_t u[4] = {xv[v].x, xv[v].y, xv[v].z, xv[v].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack_bf16x2(u[e]);
+      ss += f.x * f.x + f.y * f.y;
+    }
+  }
+  ss = warp_sum(ss);
+  const float r = 1.0f / sqrtf(ss / static_cast<float>(NV * 256) + eps);
+  bf16* yr = y + row * ldy;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const uint32_t u[4] = {xv[v].x, xv[v].y, xv[v].z, xv[v].w}, g[4] = {wv[v].x, wv[v].y, wv[v].z, wv[v].w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack_bf16x2(u[e]), q = unpack_bf16x2(g[e]);
+      o[e] = pack_bf16x2((f.x * r) * (1.0f + q.x), (f.y * r) * (1.0f + q.y));
+    }
+    *reinterpret_cast<uint4*>(yr + (v * 32 + lane) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 int rmsnorm(cudaStream_t st, const void* x, int x_is_f32, long ldx, const void* w, int w_is_f32,
             bf16* y, long ldy, int rows, int width, float eps, const int* rows_dev) {
   CVB_REQUIRE(width % 8 == 0, "rmsnorm width must be a multiple of 8");
+  if (!x_is_f32 && !w_is_f32 && width % 256 == 0 && width <= 2048 && rows >= 512 && ldx % 8 == 0 && ldy % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    const bf16* xb = reinterpret_cast<const bf16*>(x);
+    const bf16* wb = reinterpret_cast<const bf16*>(w);
+    const dim3 grid((rows + 7) / 8), block(256);
+#define CVB_RW(NV) \
+  CVB_TRY(launch_pdl(rmsnorm_warp_kernel<NV>, grid, block, 0, st, 1, xb, ldx, wb, y, ldy, rows, eps, rows_dev))
+    switch (width / 256) {
+      case 1: CVB_RW(1); break;
+      case 2: CVB_RW(2); break;
+      case 3: CVB_RW(3); break;
+      case 4: CVB_RW(4); break;
+      case 5: CVB_RW(5); break;
+      case 6: CVB_RW(6); break;
+      case 7: CVB_RW(7); break;
+      default: CVB_RW(8); break;
+    }
+#undef CVB_RW
+    CVB_LAUNCHED();
+    return 0;
+  }
   const int threads = width >= 2048 ? 256 : (width >= 512 ? 128 : 64);
   if (x_is_f32 && w_is_f32)
     CVB_TRY(launch_pdl(rmsnorm_kernel<true, true>, dim3(rows), dim3(threads), 0, st, 1, x, ldx, w, y, ldy, rows, width, eps, rows_dev));

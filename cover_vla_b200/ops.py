@@ -65,6 +65,19 @@ def gemm_splitk_partial(a, w, splits):
     return out
 
 
+def rmsnorm(x, w, eps=1e-6):
+    """y = bf16(x * rsqrt(mean(x^2) + eps) * (1 + w)): GemmaRMSNorm; x bf16 or fp32 [rows, width], w bf16 or fp32."""
+    lib = _lib.load()
+    M, N = x.shape
+    assert x.stride(1) == 1 and w.is_contiguous()
+    y = torch.empty(M, N, device=x.device, dtype=torch.bfloat16)
+    lib.cvb_op_rmsnorm.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int,
+                                   C.c_int, C.c_float, C.c_void_p]
+    _lib.check(lib.cvb_op_rmsnorm(_lib.ptr(x), int(x.dtype == torch.float32), x.stride(0), _lib.ptr(w),
+                                  int(w.dtype == torch.float32), _lib.ptr(y), N, M, N, float(eps), _lib.stream_ptr()))
+    return y
+
+
 def rmsnorm_reduce(partials, resid, w, eps=1e-6):
     """(h, y): h = bf16(bf16(sum_s partials[s]) + resid), y = GemmaRMSNorm(h) with weight w (bf16 or fp32)."""
     lib = _lib.load()

@@ -57,6 +57,11 @@ CVB_API int cvb_op_rmsnorm_reduce(const float* P, int S, int64_t split_stride, i
                                   int resid_is_f32, int64_t ldr, const void* w, int w_is_f32, void* h_out, int64_t ldh,
                                   void* y, int64_t ldy, int rows, int width, float eps, void* stream);
 
+/* Gemma RMSNorm alone (transformers GemmaRMSNorm, used at paligemma_with_expert.py:268,335,355):
+ *   y = bf16(x * rsqrt(mean(x^2) + eps) * (1 + w)), statistics in fp32; x bf16 or fp32 [rows, ldx]; w bf16 or fp32 [width]. */
+CVB_API int cvb_op_rmsnorm(const void* x, int x_is_f32, int64_t ldx, const void* w, int w_is_f32, void* y, int64_t ldy,
+                           int rows, int width, float eps, void* stream);
+
 /* LayerNorm variant (SigLIP encoder block, reached through embed_image, paligemma_with_expert.py:229-230):
  *   h = bf16(bf16(sum_s P[s] + bias) + resid),  y = LayerNorm(h) * w + b   (bias may be NULL; bias / resid / w / b bf16). */
 CVB_API int cvb_op_layernorm_reduce(const float* P, int S, int64_t split_stride, int64_t ldp, const void* bias,

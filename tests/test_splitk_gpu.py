@@ -123,3 +123,29 @@ def test_siglip_block_tail_matches_fused_epilogue_gemm():
     mag = (h_fused.float() - resid.float()).abs() + h_fused.float().abs()
     assert (d <= 2.0 ** -6 * mag + 1e-6).all()
     assert (d > 0).float().mean().item() < 0.05
+
+
+@pytest.mark.parametrize("M,N,xdt,wdt", [(2240, 2048, torch.bfloat16, torch.bfloat16), (17920, 2048, torch.bfloat16, torch.bfloat16),
+                                         (600, 1024, torch.bfloat16, torch.bfloat16), (513, 256, torch.bfloat16, torch.bfloat16),
+                                         (200, 1024, torch.bfloat16, torch.bfloat16), (300, 2048, torch.float32, torch.float32),
+                                         (1000, 1792, torch.bfloat16, torch.bfloat16), (700, 640, torch.bfloat16, torch.float32)])
+def test_rmsnorm_row_kernels(M, N, xdt, wdt):
+    """GemmaRMSNorm alone: the warp-per-row kernel (bf16, width a multiple of 256 up to 2048, >= 512 rows) and the
+    CTA-per-row kernel give the ledger value bf16((x * r) * (1 + w)) with r from an fp32 sum of squares."""
+    from cover_vla_b200 import ops
+    torch.manual_seed(M + N)
+    x = (torch.randn(M, N, device="cuda") * 3).to(xdt)
+    w = (torch.randn(N, device="cuda") * 0.2).to(wdt)
+    y = ops.rmsnorm(x, w)
+    torch.cuda.synchronize()
+    xf = x.float()
+    r = torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)
+    ref = ((xf * r) * (1.0 + w.float())).to(torch.bfloat16)
+    # r differs from torch's in the last bit (summation order): at most one bf16 ulp on a few elements
+    diff = (y.float() - ref.float()).abs()
+    assert (diff <= 2.0 ** -7 * ref.float().abs() + 1e-6).all()
+    assert (y != ref).float().mean().item() < 0.02
+    # strided input rows (a column slice of a wider buffer)
+    big = torch.zeros(M, N + 64, device="cuda", dtype=xdt)
+    big[:, :N] = x
+    assert torch.equal(ops.rmsnorm(big[:, :N], w), y)

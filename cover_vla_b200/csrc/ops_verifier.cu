@@ -222,6 +222,65 @@ __device__ void layernorm_vec(float* __restrict__ out, const float* __restrict__
   for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = (in[i] - mean) * rstd * w[i] + b[i];
   __syncthreads();
 }
+// Single-query attention of ONE head over T tokens (model.py:22-56 with a 1-token query): 8 threads per token form the
+// dot product from 32-byte slices of the K row (coalesced 256-byte rows), one warp does the softmax, then thread (d, group of
+// tokens) accumulates P V with V rows read contiguously over d; the groups are combined in a fixed order.  The head's hd
+// outputs go to out_b[h * hd ..] of every CTA of the cluster (ncta > 1) - the caller synchronises.
+__device__ void attend_head(float* __restrict__ out_b, float* __restrict__ prob, float* __restrict__ part,
+                            const float* __restrict__ qv, const float* __restrict__ Kp, const float* __restrict__ Vp,
+                            long kv_ld, int h, int hd, int T, uint32_t ncta) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  float* ph = prob + h * T;
+  const float* qh = qv + h * hd;
+  for (int j0 = 0; j0 < T; j0 += nt / 8) {
+    const int j = j0 + tid / 8, sl = tid & 7;
+    float s = 0.f;
+    if (j < T) {
+      const float* kr = Kp + static_cast<long>(j) * kv_ld + h * hd;
+      for (int d = sl * 4; d < hd; d += 32) {  // hd is a multiple of 4 (host check): float4 slices, 8 lanes = 128 bytes
+        const float4 k4 = *reinterpret_cast<const float4*>(kr + d);
+        s = fmaf(qh[d], k4.x, fmaf(qh[d + 1], k4.y, fmaf(qh[d + 2], k4.z, fmaf(qh[d + 3], k4.w, s))));
+      }
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (j < T && sl == 0) ph[j] = s;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float mx = -INFINITY;
+    for (int j = tid; j < T; j += 32) mx = fmaxf(mx, ph[j]);
+    mx = wmax(mx);
+    float sum = 0.f;
+    for (int j = tid; j < T; j += 32) {
+      const float e = expf(ph[j] - mx);
+      ph[j] = e;
+      sum += e;
+    }
+    sum = wsum(sum);
+    __syncwarp();
+    for (int j = tid; j < T; j += 32) ph[j] = ph[j] / sum;
+  }
+  __syncthreads();
+  const int groups = nt / hd;  // token groups (host check: blockDim is a multiple of hd)
+  const int d = tid % hd, g = tid / hd;
+  if (g < groups) {
+    float o = 0.f;
+    for (int j = g; j < T; j += groups) o = fmaf(ph[j], Vp[static_cast<long>(j) * kv_ld + h * hd + d], o);
+    part[g * hd + d] = o;
+  }
+  __syncthreads();
+  if (tid < hd) {
+    float o = 0.f;
+    for (int g2 = 0; g2 < groups; ++g2) o += part[g2 * hd + tid];
+    if (ncta > 1)
+      cl_store_all(out_b, h * hd + tid, o, ncta);
+    else
+      out_b[h * hd + tid] = o;
+  }
+  __syncthreads();
+}
 }  // namespace
 
 __global__ void __launch_bounds__(512) pool_chain_kernel(const PoolChain* __restrict__ chains) {
@@ -237,6 +296,7 @@ __global__ void __launch_bounds__(512) pool_chain_kernel(const PoolChain* __rest
   float* b = a + E;          // [E]
   float* t = b + E;          // [E] attention output projection (its own buffer: see the hazard note below)
   float* prob = t + E;       // [H * T]
+  float* part = prob + H * T;  // [blockDim / hd][hd] partial P V sums of the head this CTA attends
   for (int i = threadIdx.x; i < E; i += blockDim.x) q[i] = c.query[i];
   __syncthreads();
   // Cluster mode hazard rule: a product's destination is written REMOTELY by fast peers, so it must not be a buffer a
@@ -252,32 +312,13 @@ __global__ void __launch_bounds__(512) pool_chain_kernel(const PoolChain* __rest
     __syncthreads();
     const float* Kp = c.kv + static_cast<long>(l) * 2 * E;  // K_l at cols [l*2E, l*2E+E), V_l after it
     const float* Vp = Kp + E;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int h = warp; h < H; h += nw) {
-      float mx = -INFINITY;
-      for (int j = lane; j < T; j += 32) {
-        const float* kr = Kp + static_cast<long>(j) * c.kv_ld + h * hd;
-        float s = 0.f;
-        for (int d = 0; d < hd; ++d) s = fmaf(a[h * hd + d], kr[d], s);
-        prob[h * T + j] = s;
-        mx = fmaxf(mx, s);
-      }
-      mx = wmax(mx);
-      float sum = 0.f;
-      for (int j = lane; j < T; j += 32) {
-        const float e = expf(prob[h * T + j] - mx);
-        prob[h * T + j] = e;
-        sum += e;
-      }
-      sum = wsum(sum);
-      __syncwarp();
-      for (int d = lane; d < hd; d += 32) {
-        float o = 0.f;
-        for (int j = 0; j < T; ++j) o = fmaf(prob[h * T + j] / sum, Vp[static_cast<long>(j) * c.kv_ld + h * hd + d], o);
-        b[h * hd + d] = o;
-      }
-    }
-    __syncthreads();
+    // one head per CTA of the cluster (heads rank, rank + ncta, ...), the head's slice of b broadcast to every CTA
+    for (int h = static_cast<int>(rank); h < H; h += static_cast<int>(ncta))
+      attend_head(b, prob, part, a, Kp, Vp, c.kv_ld, h, hd, T, ncta);
+    if (ncta > 1)
+      cl_sync();
+    else
+      __syncthreads();
     matvec(t, w.wo, b, w.bo, E, E, rank, ncta);             // attn_out
     for (int i = threadIdx.x; i < E; i += blockDim.x) q[i] = q[i] + t[i];
     __syncthreads();
@@ -297,7 +338,9 @@ __global__ void __launch_bounds__(512) pool_chain_kernel(const PoolChain* __rest
 }
 
 int pool_chains(cudaStream_t st, const PoolChain* chains_dev, int n_chains, int embed, int heads, int tokens) {
-  const size_t smem = (4 * embed + heads * tokens) * sizeof(float);
+  const int hd = embed / heads;
+  CVB_REQUIRE(hd % 4 == 0 && 512 % hd == 0 && hd <= 512, "pooling head_dim must divide 512 and be a multiple of 4");
+  const size_t smem = (4 * embed + heads * tokens + 512) * sizeof(float);
   const int cl = embed % (2 * kPoolCluster) == 0 ? kPoolCluster : 1;  // every CTA owns an even number of output rows
   CVB_TRY(launch_pdl(pool_chain_kernel, dim3(n_chains * cl), dim3(512), smem, st, cl, chains_dev));
   CVB_LAUNCHED();

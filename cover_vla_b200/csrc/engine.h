@@ -214,6 +214,7 @@ int pi0_enqueue(cvb_handle* h, cudaStream_t st, int R, int K, int part, int B = 
 float* pi0_actions_buffer(cvb_handle* h);
 int verifier_stage_context_inputs(cvb_handle* h, const float* image, const int64_t* tokens, cudaStream_t st, int B = 1);
 bool verifier_text_cached(cvb_handle* h, int nb);
+void verifier_note_context(cvb_handle* h, int nb);
 int verifier_hold_text(cvb_handle* h, int hold);
 int verifier_enqueue_context(cvb_handle* h, cudaStream_t st, int obs = 0, int nb = 1);  // slots [obs, obs + nb)
 int verifier_enqueue_score(cvb_handle* h, cudaStream_t st, int N, int R, int K, int B = 1);

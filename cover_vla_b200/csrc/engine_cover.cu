@@ -80,6 +80,7 @@ int cover_step(cvb_handle* h, const float* image, const int64_t* lang_tokens, co
     if (rc == 0) rc = verifier_enqueue_score(h, s0, N, R, K, B);
     return rc;
   }));
+  verifier_note_context(h, B);
 
   if (actions != nullptr)
     CVB_CUDA(cudaMemcpyAsync(actions, pi0_actions_buffer(h), (size_t)B * N * c.chunk_size * c.max_action_dim * sizeof(float),

@@ -560,7 +560,6 @@ static int run_context(cvb_handle* h, cudaStream_t st, int obs0 = 0, int nb = 1)
     CVB_TRY(layernorm_bf16(st, s.ht, Wd, s.lnf_w, s.lnf_b, s.xv, Wd, nb * Tt, Wd, 1e-6f));
     CVB_TRY(gemm(st, s.xv, Wd, s.wproj, Wd, nb * Tt, Wd, Wd, EPI_STORE, s.tfeat, Wd, s.bproj));
     CVB_TRY(l2norm_rows_bf16_to_f32(st, s.tfeat, Wd, s.Tn, nb * Tt, Wd));
-    s.text_nb = nb;
   }
   CVB_TRY(run_heads_context(h, st, obs0, nb));
   return 0;
@@ -656,7 +655,7 @@ int verifier_score(cvb_handle* h, const float* image, const int64_t* tokens, con
     CVB_CUDA(cudaMemcpyAsync(s.in_tokens, tokens, c.vf_text_ctx * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     CVB_TRY(s.ctx_graph.run(c.use_cuda_graph != 0, verifier_text_cached(h, 1) ? 1 : 0, st,
                             [&](cudaStream_t cs) { return run_context(h, cs); }));
-    s.context_valid = true;
+    verifier_note_context(h, 1);
   }
   CVB_CUDA(cudaMemcpyAsync(s.in_traj, traj, (size_t)N * c.vf_history * c.vf_action_dim * sizeof(float),
                            cudaMemcpyDeviceToDevice, st));
@@ -713,6 +712,12 @@ float* verifier_traj_buffer(cvb_handle* h) { return h->vf->in_traj; }
 
 // true when a context call for nb observations will skip the text tower (part of the callers' graph keys)
 bool verifier_text_cached(cvb_handle* h, int nb) { return h->vf != nullptr && h->vf->text_hold && h->vf->text_nb == nb; }
+// Host-side bookkeeping of every context computation (called OUTSIDE the graph lambdas: a replayed graph does not run the
+// host code of run_context): the resident text features now belong to `nb` observations.
+void verifier_note_context(cvb_handle* h, int nb) {
+  h->vf->context_valid = true;
+  h->vf->text_nb = nb;
+}
 int verifier_hold_text(cvb_handle* h, int hold) {
   CVB_REQUIRE(h->vf != nullptr, "verifier not configured");
   h->vf->text_hold = hold != 0;
@@ -744,8 +749,8 @@ int verifier_context(cvb_handle* h, const float* image, const int64_t* tokens, c
                            cudaMemcpyDeviceToDevice, st));
   CVB_CUDA(cudaMemcpyAsync(s.in_tokens, tokens, c.vf_text_ctx * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   CVB_TRY(s.ctx_graph.run(c.use_cuda_graph != 0, verifier_text_cached(h, 1) ? 1 : 0, st,
-                            [&](cudaStream_t cs) { return run_context(h, cs); }));
-  s.context_valid = true;
+                          [&](cudaStream_t cs) { return run_context(h, cs); }));
+  verifier_note_context(h, 1);
   return 0;
 }
 

@@ -102,6 +102,11 @@ def test_prompt_cache_hold_text_is_exact():
     bstep.hold_text = True
     for _ in range(3):
         assert all(torch.equal(a, b) for a, b in zip(bstep.sample_and_score(xb), bbase))
+    # a single-observation call in between (graph replay) overwrites part of the resident text features: the engine
+    # tracks the observation count of the last context on the host path and re-encodes for the batch although held
+    step.hold_text = False
+    step.sample_and_score(xs[1])
+    assert all(torch.equal(a, b) for a, b in zip(bstep.sample_and_score(xb), bbase))
     eng.close()
 
 

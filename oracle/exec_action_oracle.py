@@ -90,3 +90,31 @@ def execution_action(actions: np.ndarray, best_idx: int, K: int, p01, p99, step:
         execute_action[-1] = 1.0 if execute_action[-1] >= 0 else -1.0
     execute_action[-1] = float(np.sign(execute_action[-1]))
     return execute_action, (close_votes, open_votes)
+
+
+def verifier_trajectories(actions: np.ndarray, past, history: int, p01, p99, n_future: int | None = None) -> np.ndarray:
+    """Verifier-format trajectories of all N candidates: f32 [N, history, 7].
+
+    Follows process_inputs(verifier_action=True) (eval_utils.py:172-221): every future step of every candidate goes through
+    BridgeSimplerAdapter.postprocess_verifier (simpler.py:96-121: denormalize_bound on the 6 pose dims in float64 - no
+    clipping, base.py:20-31 - and the gripper binarised to 0 / 1 at 0.5, simpler.py:222-226), the caller's last <= 6
+    executed actions are put in front of each candidate's futures, and EfficientEnsembleMerged left-pads with -5 to
+    `history` steps before the float32 cast (efficient_ensemble_merged.py:378-390).  `past` = None or [num_past, 7].
+    Pinned by tests/golden/format_traj.npz (oracle/make_golden_format.py ran the reference's own lines)."""
+    a = np.asarray(actions, dtype=np.float32)[:, :, :7]
+    if n_future is not None:
+        a = a[:, :n_future]
+    p01 = np.asarray(p01, dtype=np.float64)[:6]
+    p99 = np.asarray(p99, dtype=np.float64)[:6]
+    fut = np.zeros(a.shape, dtype=np.float64)
+    fut[:, :, :6] = (a[:, :, :6] - (-1)) / (1 - (-1)) * (p99 - p01) + p01       # base.py:29-30
+    fut[:, :, 6] = np.where(a[:, :, 6] < 0.5, 0, 1)                             # simpler.py:225
+    out = []
+    for n in range(a.shape[0]):
+        rows = fut[n]
+        if past is not None and len(past) > 0:
+            rows = np.concatenate([np.asarray(past, dtype=np.float64).reshape(-1, 7), rows], axis=0)   # eval_utils.py:213-216
+        if len(rows) < history:
+            rows = np.vstack([np.ones((history - len(rows), 7)) * -5, rows])    # efficient_ensemble_merged.py:384-386
+        out.append(rows)
+    return np.array(out).astype(np.float32)

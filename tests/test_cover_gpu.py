@@ -11,17 +11,11 @@ pytestmark = pytest.mark.gpu
 
 
 def _oracle_traj(actions, past, history, p01, p99):
-    """numpy restatement of eval_utils.process_inputs(verifier_action=True) + postprocess_verifier + padding."""
-    a = actions[:, :, :7].cpu().numpy().astype(np.float32)
-    fut = np.zeros(a.shape, dtype=np.float64)
-    t = (a[:, :, :6] - (-1)) / 2
-    fut[:, :, :6] = t * (np.array(p99) - np.array(p01)) + np.array(p01)
-    fut[:, :, 6] = np.where(a[:, :, 6] < 0.5, 0, 1)
-    hist = []
-    for n in range(a.shape[0]):
-        rows = fut[n] if past is None else np.concatenate([past.cpu().numpy().astype(np.float64), fut[n]], axis=0)
-        hist.append(rows)
-    return V.pad_histories(hist, history)
+    """process_inputs(verifier_action=True) + postprocess_verifier + padding: the oracle restatement, pinned by
+    tests/golden/format_traj.npz (tests/test_format_traj.py)."""
+    from oracle import exec_action_oracle as X
+    return torch.from_numpy(X.verifier_trajectories(actions.cpu().numpy(), None if past is None else past.cpu().numpy(),
+                                                    history, p01, p99))
 
 
 def test_cover_step_matches_oracle():

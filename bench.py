@@ -140,6 +140,67 @@ def make_device_inputs(S, d, v, R, K, seed, device):
     return host, dev, lmax
 
 
+def episode_driver_leg(engB, xsB, R, K, Bo, n_ticks, world, device):
+    """BASELINE.json configs[4] through the production surface: Bo environments stepped by EpisodeBatchDriver, timed per
+    DECISION tick with the host clock (the D2H read of the results synchronises).  Frames are synthetic 480 x 640 uint8
+    (the simulator's camera size) from a small host pool; states are random; the environments never finish."""
+    import numpy as np
+    import torch
+    from cover_vla_b200.episodes import EpisodeBatchDriver, TaskPrompts
+
+    class Env:
+        def __init__(self, seed):
+            rng = np.random.default_rng(seed)
+            self.pool = [rng.integers(0, 256, size=(480, 640, 3), dtype=np.uint8) for _ in range(4)]
+            self.states = rng.normal(size=(16, 7)).astype(np.float32)
+            self.k = 0
+
+        def reset(self, seed):
+            self.k = 0
+            return 0
+
+        def step(self, action):
+            self.k += 1
+            return self.k, False
+
+        def frame(self, obs):
+            return self.pool[obs % 4]
+
+        def state(self, obs):
+            return self.states[obs % 16]
+
+    tasks = [TaskPrompts([f"instruction {i}" for i in range(R)], x.lang_tokens, x.lang_len,
+                         x.vf_tokens[None, :].repeat(R, 1).contiguous(), x.lang_len_max) for x in xsB]
+    drv = EpisodeBatchDriver(engB, [Env(7 + b) for b in range(Bo)], tasks, [(b, 0, b) for b in range(Bo)], R, K,
+                             max_steps=10 ** 9)
+    n = drv.n_action_steps
+    for _ in range(6 * n):  # the history grows 0 -> 4 -> 6 rows: three shapes to run eagerly, capture and replay
+        drv.tick()
+    torch.cuda.synchronize()
+    t_dec = []
+    for _ in range(n_ticks * n):
+        deciding = drv.slots[0].t % n == 0
+        t1 = time.perf_counter()
+        drv.tick()
+        if deciding:
+            t_dec.append((time.perf_counter() - t1) * 1e3)
+    ms = statistics.median(t_dec)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"what": "EpisodeBatchDriver.tick() at a decision tick, host clock, p50: %d host frames (480x640x3 uint8) -> H2D -> "
+                    "Lanczos4 224 / bilinear-antialias 256 + bicubic 384 on the device -> cvb_cover_step_batch -> gate, "
+                    "execution-format actions + gripper vote, history rows -> one D2H read; per-task prompt cache active "
+                    "(the verifier text tower is skipped on ticks where no environment switched instruction)" % Bo,
+            "decision_ticks": len(t_dec), "ms_per_decision_tick": round(ms, 3), "ms_per_decision": round(ms / Bo, 3),
+            "value": round(world * Bo * R * K / (ms * 1e-3), 2), "unit": UNIT,
+            "h2d_bytes_per_decision": 480 * 640 * 3 + 32 * 4 + 6 * 7 * 4,  # frame, state, history tail (noise is drawn on the device)
+            "d2h_bytes_per_decision": (2 + 2 * 7 * n) * 8,
+            "batched_calls": drv.batched_calls, "decisions": drv.decisions}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -286,6 +347,14 @@ def run_gpu(args):
                    "observations_per_gpu_per_step": Bo, "steps": nb, "ms_per_step": round(msB, 3),
                    "ms_per_decision": round(msB / Bo, 3), "value": round(world * Bo * N / (msB * 1e-3), 2), "unit": UNIT,
                    "vs_single_decision_mode": round((world * Bo * N / (msB * 1e-3)) / value, 3)}
+        # ... and the same handle driven by the episode-batched driver (cover_vla_b200/episodes.py) from HOST simulator frames:
+        # per decision tick Bo uint8 480 x 640 frames go H2D, both image chains, the batched decision, the gate, the
+        # execution-format actions + gripper vote and the history rows run on the device, one D2H read returns them.
+        # A sub-measurement: a failure here must not lose the headline.
+        try:
+            batched["episode_driver"] = episode_driver_leg(engB, xsB, R, K, Bo, nb, world, device)
+        except Exception as e:  # noqa: BLE001
+            batched["episode_driver"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         engB.close()
         del engB, xsB, xb, outB
         torch.cuda.empty_cache()

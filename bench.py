@@ -184,12 +184,7 @@ def episode_driver_leg(engB, xsB, R, K, Bo, n_ticks, world, device):
         drv.tick()
         if deciding:
             t_dec.append((time.perf_counter() - t1) * 1e3)
-    ms = statistics.median(t_dec)
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = statistics.median(t_dec)  # this rank's; the caller takes the max over ranks (no collective in here)
     return {"what": "EpisodeBatchDriver.tick() at a decision tick, host clock, p50: %d host frames (480x640x3 uint8) -> H2D -> "
                     "Lanczos4 224 / bilinear-antialias 256 + bicubic 384 on the device -> cvb_cover_step_batch -> gate, "
                     "execution-format actions + gripper vote, history rows -> one D2H read; per-task prompt cache active "
@@ -352,9 +347,21 @@ def run_gpu(args):
         # execution-format actions + gripper vote and the history rows run on the device, one D2H read returns them.
         # A sub-measurement: a failure here must not lose the headline.
         try:
-            batched["episode_driver"] = episode_driver_leg(engB, xsB, R, K, Bo, nb, world, device)
+            leg = episode_driver_leg(engB, xsB, R, K, Bo, nb, world, device)
         except Exception as e:  # noqa: BLE001
-            batched["episode_driver"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            leg = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if world > 1:  # max over ranks OUTSIDE the guarded region: every rank reaches this collective whatever happened above
+            t = torch.tensor([leg.get("ms_per_decision_tick", -1.0), 1.0 if "error" in leg else 0.0], device=device,
+                             dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if "error" not in leg:
+                if float(t[1].item()) > 0:
+                    leg = {"error": "the leg failed on another rank"}
+                else:
+                    ms_all = float(t[0].item())
+                    leg.update(ms_per_decision_tick=round(ms_all, 3), ms_per_decision=round(ms_all / Bo, 3),
+                               value=round(world * Bo * N / (ms_all * 1e-3), 2))
+        batched["episode_driver"] = leg
         engB.close()
         del engB, xsB, xb, outB
         torch.cuda.empty_cache()
@@ -488,6 +495,7 @@ def run_gpu(args):
                        "max_valid_language_tokens": lmax,
                        "cuda_graph": bool(eng.cfg.use_cuda_graph)},
             "p50_ms": round(statistics.median(per_step), 3),
+            "p95_ms": round(sorted(per_step)[min(len(per_step) - 1, int(0.95 * len(per_step)))], 3),
             "phases_ms": {k: round(val, 3) for k, val in phases.items()},
             "algorithmic_tflop_per_step": round(total_flops / 1e12, 3),
             "clocks": clk,

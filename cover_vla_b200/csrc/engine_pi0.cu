@@ -69,11 +69,16 @@ int pack_gate_up(cvb_handle* h, cudaStream_t st, const bf16* wg, const bf16* wu,
   return 0;
 }
 
+// set by run_vision / run_prefix / run_denoise: a handle built for several observations must give a row the same bits
+// whatever the number of observations in the call, so its GEMMs never take the row-count dependent skinny kernel
+thread_local bool tl_batch_handle = false;
+
 int gemm(cudaStream_t st, const bf16* A, long lda, const bf16* Wt, long ldw, int M, int N, int K,
          int epi, void* C, long ldc, const void* bias = nullptr, const void* resid = nullptr,
          long ldr = 0, int resid_f32 = 0, int n_out = 0, int force_bn = 0) {
   GemmCall c;
   c.force_bn = force_bn;
+  c.no_skinny = tl_batch_handle ? 1 : 0;
   c.A = A, c.lda = lda, c.W = Wt, c.ldw = ldw, c.M = M, c.N = N, c.K = K, c.epi = epi;
   c.C = C, c.ldc = ldc, c.bias = bias, c.bias_is_f32 = 0, c.resid = resid, c.ldr = ldr;
   c.resid_is_f32 = resid_f32, c.n_out = n_out;
@@ -376,6 +381,7 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
 static int run_vision(cvb_handle* h, cudaStream_t st, int n_obs) {
   const cvb_config& c = h->cfg;
   Pi0State& s = h->pi0;
+  tl_batch_handle = h->max_obs() > 1;
   // every camera of every observation is one image of the tower's batch: rows [observation][camera][token], which is
   // also the order of the image tokens in a prompt (modeling_pi0.py:529-547)
   const int B = n_obs * h->cams();
@@ -450,6 +456,7 @@ static int run_vision(cvb_handle* h, cudaStream_t st, int n_obs) {
 static int run_prefix(cvb_handle* h, cudaStream_t st, int B, int Rpo) {
   const cvb_config& c = h->cfg;
   Pi0State& s = h->pi0;
+  tl_batch_handle = h->max_obs() > 1;
   // Right-padded language tokens are masked as keys and their own rows are never read (dropping them
   // is bit-exact on the reference), so only Pe = image tokens + lang_rows() rows per prompt are processed; the KV
   // cache keeps the full-P layout the denoise attention indexes.
@@ -505,6 +512,7 @@ static int run_prefix(cvb_handle* h, cudaStream_t st, int B, int Rpo) {
 static int run_denoise(cvb_handle* h, cudaStream_t st, int B, int Rpo, int K) {
   const cvb_config& c = h->cfg;
   Pi0State& s = h->pi0;
+  tl_batch_handle = h->max_obs() > 1;
   const int P = h->prefix_len(), S = h->suffix_len(), We = c.ex_width, hd = c.head_dim;
   const int R = B * Rpo;
   const int qd = c.heads * hd, qkvw = qd + 2 * hd, N = R * K, M = N * S, Ma = N * c.chunk_size;

@@ -85,9 +85,14 @@ int W(cvb_handle* h, const std::string& key, int dtype, int64_t numel, const T**
   *out = reinterpret_cast<const T*>(p);
   return 0;
 }
+// set by run_context / run_member_trajectories: on a handle built for several observations a row's bits must not depend
+// on how many observations share the call, so its GEMMs never take the row-count dependent skinny kernel
+thread_local bool tl_batch_handle = false;
+
 int gemm(cudaStream_t st, const bf16* A, long lda, const bf16* Wt, long ldw, int M, int N, int K, int epi, void* C,
          long ldc, const void* bias = nullptr, const void* resid = nullptr, long ldr = 0) {
   GemmCall c;
+  c.no_skinny = tl_batch_handle ? 1 : 0;
   c.A = A, c.lda = lda, c.W = Wt, c.ldw = ldw, c.M = M, c.N = N, c.K = K, c.epi = epi;
   c.C = C, c.ldc = ldc, c.bias = bias, c.resid = resid, c.ldr = ldr;
   // One image's trunk (M = 576) runs beside the denoise loop, which is bound by L2 -> SM bytes: what the
@@ -544,6 +549,7 @@ static int run_heads_context(cvb_handle* h, cudaStream_t st, int obs0 = 0, int n
 static int run_context(cvb_handle* h, cudaStream_t st, int obs0 = 0, int nb = 1) {
   const cvb_config& c = h->cfg;
   VerifierState& s = *h->vf;
+  tl_batch_handle = h->max_obs() > 1;
   const int Wd = c.vf_width;
   const int Np = (c.vf_image / c.vf_patch) * (c.vf_image / c.vf_patch), Tt = c.vf_text_ctx;
   const float* in_image = s.in_image + (size_t)obs0 * 3 * c.vf_image * c.vf_image;
@@ -596,6 +602,7 @@ static int run_member_trajectories(cvb_handle* h, cudaStream_t st, int N, int m)
       GemmCall g;
       g.A = Ap, g.lda = 3 * Kk, g.W = Wp, g.ldw = 3 * Kk, g.M = rows, g.N = Nn, g.K = 3 * Kk, g.epi = EPI_F32;
       g.C = Cp, g.ldc = Nn, g.bias = bias, g.bias_is_f32 = 1;
+      g.no_skinny = h->max_obs() > 1 ? 1 : 0;
       return gemm_bf16(st, g);
     };
     CVB_TRY(split3_rows(st, tx, E, txs, rows, E, 0));

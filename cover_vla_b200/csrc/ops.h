@@ -27,6 +27,8 @@ struct GemmCall {
   int n_out = 0;               // EPI_GEGLU: intermediate size
   const int* m_dev = nullptr;  // optional device-side row count
   int force_bn = 0;            // 0 = heuristic, else 64 / 128 / 256
+  int no_skinny = 0;           // batch-capable handles: never the swap-AB split-K kernel (its fp32 summation order differs
+                               // from the general kernel's, and the choice would depend on how many rows share the launch)
 };
 int gemm_bf16(cudaStream_t st, const GemmCall& c);
 // Split-K GEMM (M <= 256) that leaves S fp32 partial products in C = float[S][M][ldc] (epi / bias / resid unused);

@@ -145,7 +145,7 @@ int gemm_bf16(cudaStream_t st, const GemmCall& c) {
   }
   if (c.epi == 5) return gemm_skinny(st, c, 0);
   if (c.epi == 6) return gemm_splitk_partial(st, c, c.force_bn < 0 ? -c.force_bn : 0, nullptr);  // EPI_PARTIAL
-  if (c.force_bn == 0 && skinny_eligible(c)) return gemm_skinny(st, c, 0);
+  if (c.force_bn == 0 && !c.no_skinny && skinny_eligible(c)) return gemm_skinny(st, c, 0);
   CVB_REQUIRE(c.K % 8 == 0, "K must be a multiple of 8 (16-byte TMA rows)");
   CVB_REQUIRE(c.N % 8 == 0, "N must be a multiple of 8 (16-byte vector epilogue)");
   CVB_REQUIRE(c.ldc % 8 == 0 || c.epi == EPI_F32, "ldc must be a multiple of 8");

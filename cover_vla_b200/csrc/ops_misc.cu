@@ -147,11 +147,14 @@ __global__ void __launch_bounds__(256) rmsnorm_warp_kernel(const bf16* __restric
 int rmsnorm(cudaStream_t st, const void* x, int x_is_f32, long ldx, const void* w, int w_is_f32,
             bf16* y, long ldy, int rows, int width, float eps, const int* rows_dev) {
   CVB_REQUIRE(width % 8 == 0, "rmsnorm width must be a multiple of 8");
-  if (!x_is_f32 && !w_is_f32 && width % 256 == 0 && width <= 2048 && rows >= 512 && ldx % 8 == 0 && ldy % 8 == 0 &&
+  // (the choice must not depend on `rows`: the two kernels sum a row's squares in different orders, and a prompt's prefix
+  // has to come out the same whether it is computed alone - one rephrase per rank of a sharded decision - or beside others)
+  if (!x_is_f32 && !w_is_f32 && width % 256 == 0 && width <= 2048 && ldx % 8 == 0 && ldy % 8 == 0 &&
       ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
     const bf16* xb = reinterpret_cast<const bf16*>(x);
     const bf16* wb = reinterpret_cast<const bf16*>(w);
-    const dim3 grid((rows + 7) / 8), block(256);
+    const int wpc = rows >= 512 ? 8 : 2;  // rows (warps) per CTA: few rows are spread over more SMs
+    const dim3 grid((rows + wpc - 1) / wpc), block(32 * wpc);
 #define CVB_RW(NV) \
   CVB_TRY(launch_pdl(rmsnorm_warp_kernel<NV>, grid, block, 0, st, 1, xb, ldx, wb, y, ldy, rows, eps, rows_dev))
     switch (width / 256) {

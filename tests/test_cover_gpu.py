@@ -265,3 +265,29 @@ def test_fused_cover_step_equals_three_calls(with_past):
         for a, b in zip(out, ref):
             assert torch.equal(a, b)
     eng.close()
+
+
+@pytest.mark.parametrize("R,K", [(3, 2), (4, 3)])
+def test_rephrase_shards_equal_the_whole_decision(R, K):
+    """The sharding invariant of SURVEY.md section 8e on ONE GPU: what a rank computes for its rephrase slice - also a
+    slice of ONE rephrase - is bit-identical to those candidates' rows in the whole decision, for every world size.  (No
+    kernel choice may depend on how many prompts share a launch: round 2 briefly picked the RMSNorm kernel by row count,
+    which only the 2-GPU test tests/test_sharded_nccl_gpu.py - skipped on a 1-GPU box - could see.)"""
+    from cover_vla_b200.cover import CoverInputs, CoverStep, shard_inputs
+    d, v = O.MID, V.VMID
+    w, vw = O.make_pi0_weights(d, 0), V.make_verifier_weights(v, 0)
+    eng = build_full_engine(d, w, v, vw, R, K)
+    inp = O.make_inputs(d, R, K, seed=21)
+    vin = V.make_inputs(v, 1, seed=21)
+    x = CoverInputs(image=inp["image"][0].cuda().contiguous(), lang_tokens=inp["tokens"].cuda(),
+                    lang_len=inp["lens"].to(torch.int32).cuda(), state=inp["state"][0].cuda().contiguous(),
+                    noise=inp["noise"].cuda(), vf_image=vin["image"][0].cuda().contiguous(),
+                    vf_tokens=vin["tokens"][0].cuda(), past=None, lang_len_max=int(inp["lens"].max()))
+    step = CoverStep(eng, K)
+    whole = [t.clone() for t in step.sample_and_score(x)]
+    for world in range(2, R + 1):
+        parts = [[t.clone() for t in step.sample_and_score(shard_inputs(x, K, world, r))] for r in range(world)]
+        for i, name in enumerate(["actions", "trajectories", "scores"]):
+            got = torch.cat([p[i] for p in parts])
+            assert torch.equal(got, whole[i]), (world, name, max_abs(got, whole[i]))
+    eng.close()

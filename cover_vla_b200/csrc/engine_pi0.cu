@@ -219,8 +219,13 @@ int pi0_finalize(cvb_handle* h, cudaStream_t st) {
       CVB_TRY(W(h, p + "self_attn.o_proj.weight", CVB_BF16, (int64_t)qd * Dt, &L.wo));
       CVB_TRY(W(h, p + "mlp.gate_proj.weight", CVB_BF16, (int64_t)I * Dt, &wg));
       CVB_TRY(W(h, p + "mlp.up_proj.weight", CVB_BF16, (int64_t)I * Dt, &wu));
-      // expert: [64 gate | 64 up] blocks for 128-wide GeGLU tiles (CVB_EXPERT_GU256=1 keeps the 256-wide packing)
-      s.ex_gu_half = getenv("CVB_EXPERT_GU256") != nullptr ? 128 : 64;
+      // expert: [64 gate | 64 up] blocks for 128-wide GeGLU tiles on latency handles (M = 160-200 rows: 128 CTAs instead of
+      // 64).  A handle built for >= 4 observations keeps the 256-wide packing: at M >= 640 rows the 128-wide tiles make 5
+      // rounds of 640 tiles re-reading the activations 64 x, the CTA-pair kernel 3 rounds of 160 (batched denoise 31.5 ->
+      // 28.0 ms at 8 observations, 24.4 -> 21.0 ms at 4; tools/batch_time.py).  A handle-level choice: a row's bits do not
+      // depend on how many observations share a call.  CVB_EXPERT_GU256=1 / =0 force either.
+      const char* gu_env = getenv("CVB_EXPERT_GU256");
+      s.ex_gu_half = (gu_env != nullptr ? atoi(gu_env) != 0 : h->max_obs() >= 4) ? 128 : 64;
       CVB_TRY(pack_gate_up(h, st, wg, wu, I, Dt, &L.wgu, t == 0 ? 128 : s.ex_gu_half));
       CVB_TRY(W(h, p + "mlp.down_proj.weight", CVB_BF16, (int64_t)I * Dt, &L.wd));
       CVB_TRY(W(h, p + "input_layernorm.weight", CVB_BF16, Dt, &L.in_norm));

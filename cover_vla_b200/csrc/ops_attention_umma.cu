@@ -102,17 +102,19 @@ __device__ __forceinline__ void online_chunk(const uint32_t (&rr)[16], int nv, f
   m = mn;
 }
 // (1b) same, and the exponentials (relative to the NEW running max, 0 for invalid columns) replace rr
-__device__ __forceinline__ void online_chunk_keep(uint32_t (&rr)[16], int nv, float c2, float& m, float& l) {
+// (valid columns: [lo, lo + nv).  The sum walks the columns in order and the invalid ones add exact zeros, so a row's
+// result does not depend on `lo` - a candidate's suffix keys may sit anywhere in the 16-wide suffix tile)
+__device__ __forceinline__ void online_chunk_keep(uint32_t (&rr)[16], int nv, float c2, float& m, float& l, int lo = 0) {
   float cm = -INFINITY;
 #pragma unroll
   for (int i = 0; i < 16; ++i)
-    if (i < nv) cm = fmaxf(cm, __uint_as_float(rr[i]));
+    if (i >= lo && i < lo + nv) cm = fmaxf(cm, __uint_as_float(rr[i]));
   const float mn = fmaxf(m, cm);
   const float mc = mn * c2;
   float acc = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const float e = i < nv ? ex2_approx(fmaf(__uint_as_float(rr[i]), c2, -mc)) : 0.f;
+    const float e = (i >= lo && i < lo + nv) ? ex2_approx(fmaf(__uint_as_float(rr[i]), c2, -mc)) : 0.f;
     acc += e;
     rr[i] = __float_as_uint(e);
   }
@@ -357,7 +359,7 @@ constexpr int UD_THREADS = 576;   // warp 0 TMA, warp 1 MMA, warps 2..17 staging
 constexpr int UD_SOFT = 512;
 constexpr int UD_VSLOTS = 8;         // V^T slots (mbarrier pairs); every key-block is resident when the tiles are halved
 constexpr int UD_KSBLK = 16 * 128;  // suffix-key tile of one hd-block: 16 rows x 64 bf16
-constexpr int UD_MISC = 10 * 1024;  // red2[4][128] (max, sum) | psuf[128][8] bf16 | v1[8][256] bf16
+constexpr int UD_MISC = 14 * 1024;  // red2[4][128] (max, sum) | psuf[128][8] bf16 | v1[15][256] bf16 (<= 3 candidates x 5 keys)
 constexpr int UD_OS_LD = 260;       // fp32 row stride of the output staging tile (bank spread, 16-byte aligned)
 __host__ __device__ inline int ud_misc_off(int nkb, int vslots, int rows_total, int hdw) {
   const int pv = nkb * UA_PBLK + vslots * hdw * 128;
@@ -401,6 +403,11 @@ struct UmmaDecodeParams {
   bf16* kout_k;
   bf16* kout_v;
   int rope_rows, rope_off;  // rows of the rope table per kv batch, and the table row of query token 0 / new key 0
+  // Candidate grouping (more candidates than SMs, i.e. several observations per call): one CTA takes `group` consecutive
+  // candidates of the SAME kv batch (rephrase) - their query rows share the 128 UMMA rows and ONE copy of the prefix K /
+  // V^T, their suffix keys share the 16-wide suffix tile behind a block-diagonal mask.  group <= 1: one candidate per CTA.
+  int group;
+  int rows_max;  // group * heads * tq: sizes the shared-memory layout (the last group of a kv batch may be smaller)
 };
 
 // 8 consecutive bf16 of the qkv projection at element offset `off`: plain load, or sum of the fp32 partials -> bf16
@@ -472,8 +479,21 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   const uint32_t vblk = static_cast<uint32_t>(hdw) * 128u;  // one key-block of V^T: hdw rows x 64 keys
   const int vslots = min(min(nkb, UD_VSLOTS), (UA_BODY_MAX - UD_MISC - nkb * UA_PBLK) / static_cast<int>(vblk));
   const uint32_t qk_bytes = 4u * UA_QBLK + 4u * UD_KSBLK + static_cast<uint32_t>(kslots) * kblk;
-  const int rows_total = p.heads * p.tq;
-  const uint32_t misc_off = static_cast<uint32_t>(ud_misc_off(nkb, vslots, rows_total, hdw));
+  // which candidates: b .. b + G - 1 (all of kv batch kvb)
+  int b, kvb, G = 1;
+  if (p.group > 1) {
+    const int ngr = (p.q_per_kv_batch + p.group - 1) / p.group;
+    kvb = blockIdx.x / ngr;
+    const int c0 = (blockIdx.x - kvb * ngr) * p.group;
+    G = min(p.group, p.q_per_kv_batch - c0);
+    b = kvb * p.q_per_kv_batch + c0;
+  } else {
+    b = blockIdx.x;
+    kvb = b / p.q_per_kv_batch;
+  }
+  const int rows_cand = p.heads * p.tq;
+  const int rows_total = G * rows_cand;
+  const uint32_t misc_off = static_cast<uint32_t>(ud_misc_off(nkb, vslots, p.rows_max, hdw));
   const uint32_t body = max(qk_bytes, misc_off + UD_MISC);
   uint8_t* sQ = smem;
   uint8_t* sKs = smem + 4 * UA_QBLK;
@@ -495,8 +515,6 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k0_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x;
-  const int kvb = b / p.q_per_kv_batch;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmK);
@@ -601,17 +619,25 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     const int n0 = min(p.kv0_len_dev != nullptr ? p.kv0_len_dev[kvb] : p.kv0_len, tk_pad);
     const float2* rope = p.rope != nullptr ? p.rope + (static_cast<long>(kvb) * p.rope_rows + p.rope_off) * 128 : nullptr;
     // ---- Q rows and suffix keys: global -> registers -> RoPE -> swizzled UMMA tiles
-    const int n_items = (rows_total + p.kv1_len) * 16;
+    const int nkeys = G * p.kv1_len;  // suffix keys of the CTA's candidates: candidate gi owns tile rows [gi kv1_len, ..)
+    const int n_items = (rows_total + nkeys) * 16;
     for (int item = sid; item < n_items; item += UD_SOFT) {
       const bool isq = item < rows_total * 16;
-      const int r = isq ? item >> 4 : (item - rows_total * 16) >> 4;
+      const int r = isq ? item >> 4 : (item - rows_total * 16) >> 4;  // query row / suffix-key row of the CTA
       const int c = item & 15;  // 8-wide chunk of the first half of the head
-      const bool cached = !isq && r < p.kc;  // a hoisted suffix key: already rotated, read from the cache
-      const int t = isq ? r / p.heads : r - p.kc;
-      const long soff = isq ? b * p.q_bs + t * p.q_rs + (r % p.heads) * UA_HD + c * 8 : b * p.kv1_bs + t * p.kv1_rs + c * 8;
+      int gi, t, rk = 0;        // candidate within the group, token within the candidate, key within the candidate
+      if (isq) {
+        const int tt = r / p.heads;
+        gi = tt / p.tq, t = tt - gi * p.tq;
+      } else {
+        gi = r / p.kv1_len, rk = r - gi * p.kv1_len, t = rk - p.kc;
+      }
+      const bool cached = !isq && rk < p.kc;  // a hoisted suffix key: already rotated, read from the cache
+      const long bb = b + gi;
+      const long soff = isq ? bb * p.q_bs + t * p.q_rs + (r % p.heads) * UA_HD + c * 8 : bb * p.kv1_bs + t * p.kv1_rs + c * 8;
       uint4 x1, x2;
       if (cached) {
-        const bf16* kp = p.kc_k + (static_cast<long>(b) * p.kc + r) * UA_HD + c * 8;
+        const bf16* kp = p.kc_k + (bb * p.kc + rk) * UA_HD + c * 8;
         x1 = *reinterpret_cast<const uint4*>(kp);
         x2 = *reinterpret_cast<const uint4*>(kp + 128);
       } else {
@@ -625,8 +651,8 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
         for (int e = 0; e < 4; ++e) cs[e] = tp[e];
         rope8_umma(x1, x2, reinterpret_cast<const float2*>(cs));
       }
-      if (p.kout_k != nullptr && !isq && r == 0 && hy == 0) {  // step 0: keep the state token's rotated key
-        bf16* kp = p.kout_k + static_cast<long>(b) * UA_HD + c * 8;
+      if (p.kout_k != nullptr && !isq && rk == 0 && hy == 0) {  // step 0: keep the state token's rotated key
+        bf16* kp = p.kout_k + bb * UA_HD + c * 8;
         *reinterpret_cast<uint4*>(kp) = x1;
         *reinterpret_cast<uint4*>(kp + 128) = x2;
       }
@@ -640,14 +666,15 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
       sts_u4(tile2 + off, x2.x, x2.y, x2.z, x2.w);
     }
     uint4 v1reg = make_uint4(0, 0, 0, 0);
-    if (sid < p.kv1_len * 32) {
-      const int j = sid >> 5;
+    if (sid < nkeys * 32) {
+      const int gi = (sid >> 5) / p.kv1_len, j = (sid >> 5) - gi * p.kv1_len;
+      const long bb = b + gi;
       if (j < p.kc)
-        v1reg = *reinterpret_cast<const uint4*>(p.kc_v + (static_cast<long>(b) * p.kc + j) * UA_HD + (sid & 31) * 8);
+        v1reg = *reinterpret_cast<const uint4*>(p.kc_v + (bb * p.kc + j) * UA_HD + (sid & 31) * 8);
       else
-        v1reg = ud_load8(p.v1, p.v1f, b * p.kv1_bs + (j - p.kc) * p.kv1_rs + (sid & 31) * 8, p.part_S, p.part_ss);
+        v1reg = ud_load8(p.v1, p.v1f, bb * p.kv1_bs + (j - p.kc) * p.kv1_rs + (sid & 31) * 8, p.part_S, p.part_ss);
       if (p.kout_v != nullptr && j == 0 && hy == 0)
-        *reinterpret_cast<uint4*>(p.kout_v + static_cast<long>(b) * UA_HD + (sid & 31) * 8) = v1reg;
+        *reinterpret_cast<uint4*>(p.kout_v + bb * UA_HD + (sid & 31) * 8) = v1reg;
     }
     fence_proxy_async();
     mbar_arrive(q_ready);
@@ -656,7 +683,7 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     mbar_wait(s_full, 0);
     tc_fence_after();
     UD_TS(3);
-    if (sid < p.kv1_len * 32) *reinterpret_cast<uint4*>(sV1 + (sid >> 5) * UA_HD + (sid & 31) * 8) = v1reg;
+    if (sid < nkeys * 32) *reinterpret_cast<uint4*>(sV1 + (sid >> 5) * UA_HD + (sid & 31) * 8) = v1reg;
 
     // ---- softmax: row r of the candidate sits in lane L = (r % 4) * 32 + r / 4  ->  this thread owns r = lane * 4 + q.
     // A warp can only read its own TMEM lane quarter and the 4 warps of a quarter share one scheduler, so the cost is
@@ -665,7 +692,9 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     const int L = q * 32 + lane;
     const int r = lane * 4 + q;
     const bool active = r < rows_total;
-    const int t = r / p.heads;
+    const int gi = active ? (r / p.heads) / p.tq : 0;  // this row's candidate within the group ...
+    const int t = r / p.heads - gi * p.tq;             // ... its token ...
+    const int lo = gi * p.kv1_len;                     // ... and where that candidate's keys start in the suffix tile
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const bool first_only = p.suffix_mask && t == 0;  // the state token sees only itself among the suffix keys
     // Column group g takes the prefix chunks g, g + 4, g + 8, ... and group 3 ends with the suffix chunk: a fixed
@@ -698,7 +727,7 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
       uint32_t rr[16];
       tmem_ld_x16(taddr + tk_pad, rr);
       tmem_wait_ld();
-      online_chunk_keep(rr, nv_suffix, c2, m, l);
+      online_chunk_keep(rr, nv_suffix, c2, m, l, lo);
       tmem_st_x16(taddr + tk_pad, rr);
       mref[UD_CPT] = m;
     }
@@ -746,11 +775,19 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
       tmem_ld_x16(taddr + tk_pad, rr);
       tmem_wait_ld();
       const float f = active ? ex2_approx((mref[UD_CPT] - M) * c2) * inv : 0.f;
-      *reinterpret_cast<uint4*>(psuf + L * 8) =  // suffix keys 0..7
-          make_uint4(pack_bf16x2(__uint_as_float(rr[0]) * f, __uint_as_float(rr[1]) * f),
-                     pack_bf16x2(__uint_as_float(rr[2]) * f, __uint_as_float(rr[3]) * f),
-                     pack_bf16x2(__uint_as_float(rr[4]) * f, __uint_as_float(rr[5]) * f),
-                     pack_bf16x2(__uint_as_float(rr[6]) * f, __uint_as_float(rr[7]) * f));
+      if (p.group <= 1) {
+        *reinterpret_cast<uint4*>(psuf + L * 8) =  // suffix keys 0..7
+            make_uint4(pack_bf16x2(__uint_as_float(rr[0]) * f, __uint_as_float(rr[1]) * f),
+                       pack_bf16x2(__uint_as_float(rr[2]) * f, __uint_as_float(rr[3]) * f),
+                       pack_bf16x2(__uint_as_float(rr[4]) * f, __uint_as_float(rr[5]) * f),
+                       pack_bf16x2(__uint_as_float(rr[6]) * f, __uint_as_float(rr[7]) * f));
+      } else {  // the row's OWN candidate's keys, shifted to 0.. (same values, same rounding as the packed stores)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int j = i - lo;
+          if (j >= 0 && j < 8) psuf[L * 8 + j] = __float2bfloat16_rn(__uint_as_float(rr[i]) * f);
+        }
+      }
     }
     fence_proxy_async();
     tc_fence_before();
@@ -770,6 +807,7 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
       if (item < rows_total * cgs) {
         const int ro = item / cgs, cg = item % cgs;
         const int Lr = (ro & 3) * 32 + (ro >> 2);
+        const int vlo = ((ro / p.heads) / p.tq) * p.kv1_len;  // first suffix-tile row of this row's candidate
         const uint4 pu = *reinterpret_cast<const uint4*>(psuf + Lr * 8);
         const uint32_t pw[4] = {pu.x, pu.y, pu.z, pu.w};
 #pragma unroll
@@ -777,7 +815,7 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
           if (j < p.kv1_len) {
             const float2 pp = unpack_bf16x2(pw[j >> 1]);
             const float pj = (j & 1) ? pp.y : pp.x;
-            const uint4 vv = *reinterpret_cast<const uint4*>(sV1 + j * UA_HD + hy * hdw + cg * 8);
+            const uint4 vv = *reinterpret_cast<const uint4*>(sV1 + (vlo + j) * UA_HD + hy * hdw + cg * 8);
             const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -816,7 +854,9 @@ attn_decode_umma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
         const int ro = item / cgs, cg = item % cgs;
         const float4 o0 = *reinterpret_cast<const float4*>(Os + ro * UD_OS_LD + cg * 8);
         const float4 o1 = *reinterpret_cast<const float4*>(Os + ro * UD_OS_LD + cg * 8 + 4);
-        bf16* op = p.out + b * p.o_bs + static_cast<long>(ro / p.heads) * p.o_rs + (ro % p.heads) * UA_HD + hy * hdw + cg * 8;
+        const int og = (ro / p.heads) / p.tq;  // candidate within the group
+        bf16* op = p.out + static_cast<long>(b + og) * p.o_bs + static_cast<long>(ro / p.heads - og * p.tq) * p.o_rs +
+                   (ro % p.heads) * UA_HD + hy * hdw + cg * 8;
         *reinterpret_cast<uint4*>(op) =
             make_uint4(pack_bf16x2(o0.x + sc[it][0], o0.y + sc[it][1]), pack_bf16x2(o0.z + sc[it][2], o0.w + sc[it][3]),
                        pack_bf16x2(o1.x + sc[it][4], o1.y + sc[it][5]), pack_bf16x2(o1.z + sc[it][6], o1.w + sc[it][7]));
@@ -1395,13 +1435,32 @@ int attention_decode_umma(cudaStream_t st, const AttnCall& c) {
   const int nkb = (tk_pad + 63) / 64;
   const int kslots = 4 * UA_QBLK + 4 * UD_KSBLK + 4 * tk_pad * 128 <= UA_BODY_MAX ? 4 : 3;
   const int vslots = std::min(std::min(nkb, UD_VSLOTS), (UA_BODY_MAX - UD_MISC - nkb * UA_PBLK) / (hdw * 128));
+  // More candidates than SMs (several observations per call): the candidates of one rephrase share a CTA - up to 128 query
+  // rows and 15 suffix keys - so the prefix K / V^T of a rephrase is staged once per group instead of once per candidate
+  // and the launch fits one wave (8 observations x 40 candidates: 320 CTAs = 3 rounds -> 128 CTAs).  A row's arithmetic is
+  // the same either way (bit-identical: tests/test_attention_gpu.py), so the choice may depend on the launch size.
+  int group = 1, ngr = 1;
+  const int rows_cand = c.heads * c.tq;
+  static const int group_env = getenv("CVB_DECODE_GROUP") != nullptr ? atoi(getenv("CVB_DECODE_GROUP")) : -1;
+  if (split == 1 && c.q_per_kv_batch > 1 && c.batches % c.q_per_kv_batch == 0 &&
+      (group_env > 1 || (group_env < 0 && c.batches > device_sm_count()))) {
+    int gmax = std::min(std::min(128 / rows_cand, 15 / c.kv1_len), c.q_per_kv_batch);
+    if (group_env > 1) gmax = std::min(gmax, group_env);
+    if (gmax > 1) {
+      ngr = (c.q_per_kv_batch + gmax - 1) / gmax;
+      group = (c.q_per_kv_batch + ngr - 1) / ngr;  // balanced: 5 candidates -> 3 + 2
+      if (ud_misc_off(nkb, vslots, group * rows_cand, hdw) + UD_MISC > UA_BODY_MAX) group = 1, ngr = 1;
+    }
+  }
+  p.group = group, p.rows_max = group * rows_cand;
   const int body = std::max(4 * UA_QBLK + 4 * UD_KSBLK + kslots * tk_pad * 128,
-                            ud_misc_off(nkb, vslots, c.heads * c.tq, hdw) + UD_MISC);
+                            ud_misc_off(nkb, vslots, p.rows_max, hdw) + UD_MISC);
   const int smem = 1024 + body + (4 + 1 + 1 + 1 + 2 * UD_VSLOTS + 2) * 8 + 16;
-  const bool small = c.heads * c.tq * (hdw / 8) <= 3 * UD_SOFT;  // the denoise step has 40 query rows
+  const bool small = p.rows_max * (hdw / 8) <= 3 * UD_SOFT;  // the denoise step has 40 query rows
   auto kern = small ? attn_decode_umma_kernel<3> : attn_decode_umma_kernel<8>;
   CVB_TRY(ensure_dyn_smem(kern, smem));
-  CVB_TRY(launch_pdl(kern, dim3(c.batches, split), dim3(UD_THREADS), smem, st, 1, tmK, tmVT, p));
+  const int ctas = group > 1 ? kv_batches * ngr : c.batches;
+  CVB_TRY(launch_pdl(kern, dim3(ctas, split), dim3(UD_THREADS), smem, st, 1, tmK, tmVT, p));
   CVB_LAUNCHED();
   return 0;
 }

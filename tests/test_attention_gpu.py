@@ -178,6 +178,52 @@ def test_long_multihead_attention_tcgen05(B, T, heads, hd, full):
     assert ((out.float() - old.float()).norm() / ref.norm()).item() < 5e-3
 
 
+@pytest.mark.parametrize("R,K,S", [(32, 5, 5), (32, 5, 4), (40, 4, 5), (75, 2, 5), (30, 7, 4)])
+def test_denoise_attention_grouped_candidates_are_bit_identical(R, K, S):
+    """More candidates than SMs (several observations per call): the candidates of a rephrase share a CTA - its query
+    rows, one copy of the prefix K / V^T and the 16-wide suffix tile behind a block-diagonal mask (5 candidates -> 3 + 2).
+    A row's arithmetic must not change: the launch over all candidates equals, bit for bit, the same candidates launched
+    in slices small enough (<= 148 / 2) to take one candidate per CTA pair."""
+    from cover_vla_b200 import ops
+    torch.manual_seed(R * 31 + K)
+    hd, heads, P = 256, 8, 280
+    N = R * K
+    assert N > 148
+    q = torch.randn(N, S, heads * hd, device="cuda").to(torch.bfloat16)
+    k0 = torch.randn(R, P, hd, device="cuda").to(torch.bfloat16)
+    v0 = torch.randn(R, P, hd, device="cuda").to(torch.bfloat16)
+    k1 = torch.randn(N, S, hd, device="cuda").to(torch.bfloat16)
+    v1 = torch.randn_like(k1)
+    lens_t = torch.randint(200, P + 1, (R,), device="cuda", dtype=torch.int32)
+    pos = lens_t[:, None] + torch.arange(S, device="cuda")[None, :]
+    ts = 10000.0 ** ((2.0 / hd) * torch.arange(hd // 2, dtype=torch.float32, device="cuda"))
+    rad = pos[..., None].float() / ts
+    tab = torch.stack([torch.cos(rad), torch.sin(rad)], dim=-1).contiguous()
+    vt0 = ops.transpose_values(v0)
+    kw = dict(heads=heads, kv_heads=1, head_dim=hd, q_per_kv_batch=K, suffix_mask=True, algo=3)
+    out = ops.attention(q, k0, v0, kv0_len_dev=lens_t, k1=k1, v1=v1, rope=tab, vt0=vt0, **kw)
+    step = max(1, 70 // K)  # rephrases per slice: at most 70 candidates -> one candidate per CTA pair
+    for r0 in range(0, R, step):
+        r1 = min(R, r0 + step)
+        part = ops.attention(q[r0 * K:r1 * K].contiguous(), k0[r0:r1].contiguous(), v0[r0:r1].contiguous(),
+                             kv0_len_dev=lens_t[r0:r1].contiguous(), k1=k1[r0 * K:r1 * K].contiguous(),
+                             v1=v1[r0 * K:r1 * K].contiguous(), rope=tab[r0:r1].contiguous(), vt0=vt0[r0:r1].contiguous(), **kw)
+        assert torch.equal(part, out[r0 * K:r1 * K]), (r0, (part.float() - out[r0 * K:r1 * K].float()).abs().max().item())
+    # and it is right: a few candidates against the fp32 restatement of the eager ledger
+    posn = pos.repeat_interleave(K, dim=0)
+    qr = _rope(q.view(N, S, heads, hd), posn, hd).view(N, S, heads * hd)
+    k1r = _rope(k1.view(N, S, 1, hd), posn, hd).view(N, S, hd)
+    for n in (0, 1, K - 1, K, N // 2, N - 1):
+        r = n // K
+        L = int(lens_t[r])
+        kk = torch.cat([k0[r, :L], k1r[n]])[None]
+        vv = torch.cat([v0[r, :L], v1[n]])[None]
+        mask = torch.ones(1, S, L + S, dtype=torch.bool, device="cuda")
+        mask[0, 0, L + 1:] = False
+        ref = _ref(qr[n:n + 1], kk, vv, heads, 1, hd, mask)
+        assert (out[n:n + 1].float() - ref).abs().max().item() < 2e-2, n
+
+
 def test_denoise_attention_with_cached_state_key():
     """SURVEY.md F7 at operator level: step 0 (5 query rows / 5 suffix keys per candidate) writes the state token's rotated
     key and its value; a hoisted call (4 action query rows, suffix keys = [cached state key, 4 new keys]) must return

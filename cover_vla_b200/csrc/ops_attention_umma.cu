@@ -1442,7 +1442,7 @@ int attention_decode_umma(cudaStream_t st, const AttnCall& c) {
   int group = 1, ngr = 1;
   const int rows_cand = c.heads * c.tq;
   static const int group_env = getenv("CVB_DECODE_GROUP") != nullptr ? atoi(getenv("CVB_DECODE_GROUP")) : -1;
-  if (split == 1 && c.q_per_kv_batch > 1 && c.batches % c.q_per_kv_batch == 0 &&
+  if ((split == 1 || group_env > 1) && c.q_per_kv_batch > 1 && c.batches % c.q_per_kv_batch == 0 &&
       (group_env > 1 || (group_env < 0 && c.batches > device_sm_count()))) {
     int gmax = std::min(std::min(128 / rows_cand, 15 / c.kv1_len), c.q_per_kv_batch);
     if (group_env > 1) gmax = std::min(gmax, group_env);

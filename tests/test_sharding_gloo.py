@@ -45,7 +45,9 @@ def _worker(rank, world, port, R, K, q):
         local_scores = mine.noise.flatten(1).sum(1).tanh()
         local_actions = mine.noise[:, :, :7].contiguous()
         scores, actions, gmean, idx, score = gather_and_select(local_scores, local_actions, R, K, _select_cpu)
-        q.put((rank, scores, actions, int(idx), float(score)))
+        # numpy, not tensors: a tensor travels through the queue as a shared-memory handle that dies with this process -
+        # if the worker exits before the parent has read it the parent's q.get() raises EOFError (seen under load)
+        q.put((rank, scores.numpy().copy(), actions.numpy().copy(), int(idx), float(score)))
     finally:
         dist.destroy_process_group()
 
@@ -66,8 +68,8 @@ def test_sharded_gather_and_select_is_rank_invariant(world, R, K):
     full_scores = x.noise.flatten(1).sum(1).tanh()
     best, idx, gi, means = V.select(full_scores, K)
     for rank, scores, actions, ridx, rscore in res:
-        assert torch.equal(scores, full_scores)
-        assert torch.equal(actions, x.noise[:, :, :7])
+        assert torch.equal(torch.from_numpy(scores), full_scores)
+        assert torch.equal(torch.from_numpy(actions), x.noise[:, :, :7])
         assert ridx == idx and rscore == best
 
 

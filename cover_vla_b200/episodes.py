@@ -299,3 +299,24 @@ class EpisodeBatchDriver:
             self.tick()
             ticks += 1
         return self.finished
+
+
+# ----------------------------------------------------------------------------------------------------
+# episode-parallel over ranks (BASELINE.json configs[4]: 64 observations over 8 GPUs)
+# ----------------------------------------------------------------------------------------------------
+def shard_work(work: Iterable[tuple[int, int, int]], world_size: int, rank: int) -> list[tuple[int, int, int]]:
+    """Round-robin share of the (task, trial, seed) list for one rank: episodes are independent, so there is no data-path
+    collective - every rank drives its own environments with its own EpisodeBatchDriver."""
+    return [w for i, w in enumerate(work) if i % world_size == rank]
+
+
+def gather_records(records: list[EpisodeRecord], group=None) -> list[EpisodeRecord]:
+    """The one collective of the episode-parallel mode: every rank's finished episodes, gathered once at the end (host
+    objects over the process group's backend) and ordered by (task, trial, seed) so the result does not depend on the
+    number of ranks."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return sorted(records, key=lambda r: (r.task, r.trial, r.seed))
+    parts: list = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, records, group=group)
+    return sorted((r for part in parts for r in part), key=lambda r: (r.task, r.trial, r.seed))

@@ -168,3 +168,54 @@ def test_constructor_rejects_what_the_engine_cannot_hold():
         EpisodeBatchDriver(_engine(2), [ToyEnv()], tasks, [], 5, 3)          # the task has only 4 instructions
     with pytest.raises(ValueError):
         EpisodeBatchDriver(_engine(2), [ToyEnv()], tasks, [], 4, 3, num_steps_wait=2)
+
+
+def _rank_worker(rank, world, port, work, R, K, n, max_steps, q):
+    import os
+    import torch.distributed as dist
+    from cover_vla_b200.episodes import gather_records, shard_work
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        tasks = [_prompts(R), _prompts(R + 2)]
+        FakeDeviceDriver.groups = []
+        mine = shard_work(work, world, rank)
+        drv = FakeDeviceDriver(_engine(2), [ToyEnv(), ToyEnv()], tasks, mine, R, K, n_action_steps=n, max_steps=max_steps)
+        drv.run()
+        allrecs = gather_records(drv.finished)
+        q.put((rank, len(mine), [(r.task, r.trial, r.seed, r.success, r.episode_length, r.selected_indices,
+                                  [a.tolist() for a in r.execute_actions]) for r in allrecs]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_episode_parallel_ranks_gather_the_same_records(world):
+    """configs[4] across ranks: every rank drives its round-robin share of the episodes; the gathered, ordered records are
+    identical on every rank and equal each episode stepped alone (no data-path collective, one gather at the end)."""
+    import socket
+    import torch.multiprocessing as mp
+    R, K, n, max_steps = 4, 3, 4, 25
+    work = [(task, trial, 1000 + trial) for task in range(2) for trial in range(4)]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rank_worker, args=(r, world, port, work, R, K, n, max_steps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(world)])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sum(r[1] for r in res) == len(work)
+    tasks = [_prompts(R), _prompts(R + 2)]
+    first = res[0][2]
+    assert [(t, tr, sd) for t, tr, sd, *_ in first] == sorted(work)
+    for rank, _, recs in res:
+        assert recs == first
+    for task, trial, seed, success, length, idx, acts in first:
+        ref = reference_episode(task, trial, seed, tasks[task], R, K, n, max_steps, 0)
+        assert (success, length, idx) == (ref.success, ref.length, ref.idx)
+        assert acts == [a.tolist() for a in ref.acts]

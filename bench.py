@@ -155,7 +155,7 @@ def episode_driver_leg(engB, xsB, R, K, Bo, n_ticks, world, device):
             self.states = rng.normal(size=(16, 7)).astype(np.float32)
             self.k = 0
 
-        def reset(self, seed):
+        def reset(self, task, seed):
             self.k = 0
             return 0
 

@@ -19,7 +19,8 @@ policy and for the verifier and stay on the device; the prompt set of a decision
 (:299-302) - is an index gather, and the instruction swap of :409 moves one index.
 
 The simulator itself, its proprioception adapter and the rephrase generation are out of scope: an
-environment is any object with the four methods of `EpisodeEnv`.
+environment is any object with the four methods of `EpisodeEnv`; a slot's environment object is re-used for whatever
+(task, trial, seed) comes next, so `reset` receives the task.
 """
 from __future__ import annotations
 
@@ -40,7 +41,7 @@ MAX_PAST = 6  # run_simpler_eval_with_openpi.py:333 / eval_utils.py:209: the ver
 class EpisodeEnv(Protocol):
     """What the driver needs from a simulator wrapper (get_simpler_env + the adapter's proprioception, which stay host code)."""
 
-    def reset(self, seed: int): ...                      # -> obs                          (:231)
+    def reset(self, task: int, seed: int): ...           # -> obs; the environment of `task` (:194, :231)
     def step(self, action: np.ndarray): ...              # f64 [7] -> (obs, done: bool)     (:436)
     def frame(self, obs) -> np.ndarray: ...              # uint8 [H, W, 3]                  (:268)
     def state(self, obs) -> np.ndarray: ...              # float [<= max_state_dim]         (preprocess_adapter.preprocess, :284)
@@ -159,7 +160,7 @@ class EpisodeBatchDriver:
         s.task, s.current, s.t = task, 0, 0            # every trial starts from the original instruction (:220-223)
         s.history, s.queue_exec, s.queue_hist = [], [], []
         s.record = EpisodeRecord(task=task, trial=trial, seed=seed)
-        s.obs = s.env.reset(seed)
+        s.obs = s.env.reset(task, seed)
         s.active = True
 
     def _finish(self, s: _Slot, success: bool) -> None:

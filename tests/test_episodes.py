@@ -20,8 +20,8 @@ H, W = 12, 16
 class ToyEnv:
     """Deterministic stand-in for the simulator: what it shows depends on the seed and on every action it was given."""
 
-    def reset(self, seed):
-        self.seed, self.k, self.acc = seed, 0, hashlib.sha256(str(seed).encode()).digest()
+    def reset(self, task, seed):
+        self.seed, self.k, self.acc = seed, 0, hashlib.sha256(str((task, seed)).encode()).digest()
         return self._obs()
 
     def _obs(self):
@@ -78,7 +78,7 @@ class FakeDeviceDriver(EpisodeBatchDriver):
 def reference_episode(task, trial, seed, prompts, R, K, n, max_steps, wait):
     """run_simpler_eval_with_openpi.py:231-441 for ONE environment, in the reference's order of operations."""
     env = ToyEnv()
-    obs = env.reset(seed)                                                    # :231
+    obs = env.reset(task, seed)                                              # :194, :231
     t, action_history, task_description = 0, [], 0                           # :234-236, :220-223 (instruction ids)
     rec = types.SimpleNamespace(scores=[], instr=[], acts=[], ts=[], idx=[])
     done = False

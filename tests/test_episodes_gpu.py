@@ -21,8 +21,8 @@ FH, FW = 48, 64
 class ToyEnv:
     """Deterministic simulator stand-in: frames and states depend on the seed and on every executed action."""
 
-    def reset(self, seed):
-        self.k, self.acc = 0, hashlib.sha256(str(seed).encode()).digest()
+    def reset(self, task, seed):
+        self.k, self.acc = 0, hashlib.sha256(str((task, seed)).encode()).digest()
         return {"acc": self.acc}
 
     def step(self, action):
@@ -67,7 +67,7 @@ def _episode_alone(eng, tp, task, trial, seed, R, K, n, max_steps, gate):
     cfg = eng.cfg
     step = BatchedCoverStep(eng, K, n_future=n)
     env = ToyEnv()
-    obs = env.reset(seed)
+    obs = env.reset(task, seed)
     rec = EpisodeRecord(task=task, trial=trial, seed=seed)
     t, history, cur, done = 0, [], 0, False
     while t < max_steps:

@@ -198,3 +198,21 @@ def test_normalisation_matches_the_reference_modules_live(mode):
     if mode != "IDENTITY":  # without statistics the mirror refuses (the reference asserts on its infinite placeholder buffers)
         with pytest.raises(ValueError):
             _Normalize({OBS_ROBOT: PolicyFeature("STATE", (7,))}, our_map, None, False)(x)
+
+
+@pytest.mark.skipif(not REF.exists(), reason="the reference tree is only present in the authoring container")
+def test_image_and_state_glue_matches_the_reference_functions_live():
+    """resize_with_pad / pad_vector (modeling_pi0.py:131-165) incl. the mirror's shortcut for frames that already have the
+    target size (the reference interpolates them at scale 1, which returns the same bits)."""
+    from oracle import ref_shim
+    ref_shim.install()
+    import lerobot.common.policies.pi0.modeling_pi0 as R
+    from cover_vla_b200.pi0 import modeling_pi0 as M
+    g = torch.Generator().manual_seed(9)
+    for shape in [(2, 3, 224, 224), (1, 3, 480, 640), (2, 3, 100, 300), (1, 3, 256, 200)]:
+        img = torch.rand(*shape, generator=g) * 2 - 1
+        for pad in (0, -1):
+            assert torch.equal(M.resize_with_pad(img, 224, 224, pad_value=pad), R.resize_with_pad(img, 224, 224, pad_value=pad))
+    for shape in [(5, 7), (5, 32), (2, 4, 7)]:
+        v = torch.randn(*shape, generator=g)
+        assert torch.equal(M.pad_vector(v, 32), R.pad_vector(v, 32))

@@ -162,3 +162,23 @@ def test_cuda_tf_antialias_resize_is_bit_exact_vs_restatement():
     f32 = preprocess.verifier_image_from_raw(torch.from_numpy(img).cuda(), 384)
     ref = P.verifier_image(P.tf_resize_bilinear_antialias_u8(img, 256, 256), 384)[1]
     assert np.array_equal(f32.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("H,W", [(480, 640), (512, 512), (300, 400), (256, 256), (720, 1280)])
+def test_tf_resize_restatement_agrees_with_an_independent_implementation(H, W):
+    """tf.image.resize(..., BILINEAR, antialias=True) is restated from TensorFlow's scale_and_translate (TensorFlow is not
+    installed: parity unpinned against TF itself).  torch's F.interpolate(mode="bilinear", antialias=True) is an independent
+    implementation of the same triangle-filter resize with half-pixel centres: after the reference's truncating uint8 cast
+    the two may differ by one count where fp32 summation order moves a value across an integer, never by more."""
+    import torch.nn.functional as F
+    from oracle import preprocess_oracle as P
+    rng = np.random.default_rng(H + W)
+    yy, xx = np.mgrid[0:H, 0:W]
+    smooth = np.stack([(np.sin(xx / 37.0) + np.cos(yy / 23.0)) * 60 + 128, xx * 255.0 / W, yy * 255.0 / H], -1)
+    for img in (rng.integers(0, 256, (H, W, 3), dtype=np.uint8), smooth.clip(0, 255).astype(np.uint8)):
+        ours = P.tf_resize_bilinear_antialias_u8(img, 256, 256)
+        t = torch.from_numpy(img).permute(2, 0, 1)[None].float()
+        ref = F.interpolate(t, size=(256, 256), mode="bilinear", antialias=True, align_corners=False)
+        ref_u8 = ref[0].permute(1, 2, 0).numpy().astype(np.uint8)  # tf.cast(float -> uint8) truncates
+        diff = np.abs(ours.astype(np.int32) - ref_u8.astype(np.int32))
+        assert diff.max() <= 1 and (diff == 0).mean() > 0.97, (diff.max(), (diff == 0).mean())

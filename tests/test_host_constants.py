@@ -52,3 +52,39 @@ def test_time_embedding_bit_exact(lib):
             # allow a 1-ulp double-precision libm difference to flip at most a couple of bf16 roundings
             assert mism <= 2, (dim, t, mism)
             assert (got.float() - ref.float()).abs().max().item() <= 2 ** -7
+
+
+def test_product_path_never_touches_the_oracle_or_the_reference_tree():
+    """The oracle is test infrastructure: nothing under cover_vla_b200/ may import it or read /root/reference, bench.py may
+    only reach it from its CPU legs (cpu_baseline / --impl reference), and the product must fail loudly - not fall back -
+    when the CUDA library is missing."""
+    import ast
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    for f in sorted((root / "cover_vla_b200").rglob("*.py")):
+        src = f.read_text()
+        assert "/root/reference" not in src, f
+        for node in ast.walk(ast.parse(src)):
+            mods = []
+            if isinstance(node, ast.Import):
+                mods = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                mods = [node.module or ""]
+            assert not any(m == "oracle" or m.startswith("oracle.") for m in mods), (f, mods)
+    # bench.py: every oracle import sits inside a CPU-leg function
+    tree = ast.parse((root / "bench.py").read_text())
+    for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+        uses = any((isinstance(n, ast.ImportFrom) and (n.module or "").split(".")[0] == "oracle") or
+                   (isinstance(n, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in n.names)) for n in ast.walk(fn))
+        if uses:
+            assert fn.name in ("_cpu_setup", "cpu_decision", "cpu_baseline_sample", "run_reference"), fn.name
+    assert not any(isinstance(n, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(n) for n in tree.body)
+    # no silent fallback: a missing library is an error
+    from cover_vla_b200 import _lib
+    saved_path, saved_handle = _lib.LIB_PATH, _lib._lib
+    try:
+        _lib.LIB_PATH, _lib._lib = root / "cover_vla_b200" / "does_not_exist.so", None
+        with pytest.raises(_lib.CvbError):
+            _lib.load()
+    finally:
+        _lib.LIB_PATH, _lib._lib = saved_path, saved_handle

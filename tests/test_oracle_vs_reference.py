@@ -113,3 +113,45 @@ def test_verifier_scores_vs_reference_object(name, R, K, seed):
     best, idx, scores, means = V.compute_max_similarity_scores(w, d, inp["image"], inp["tokens"], inp["histories"], K)
     assert idx == ref["global_idx"]
     assert abs(best - ref["max_score"]) < 2e-6
+
+
+@pytest.mark.parametrize("name,R,K", [("VTINY", 4, 3), ("VTINY_MLP", 3, 2)])
+def test_reference_slow_path_consumes_pair_zero_only(name, R, K):
+    """with DISTINCT (image, instruction) pairs the reference encodes every pair
+    (efficient_ensemble_merged.py:348-376), tiles them over the N trajectories (the repeat of :213-214), and still reads
+    row 0 of the similarity matrix (:422-425) - the result is the one of pair 0 alone, and the instruction it returns is
+    instructions[min(g* . K, len - 1)] (:444).  That is what cvb_verifier_score computes (one context: pair 0) and what the
+    EfficientEnsembleMerged mirror returns; shown here on the reference's own code."""
+    from oracle import ref_verifier
+    from oracle import verifier_oracle as V
+    d = getattr(V, name)
+    w = V.make_verifier_weights(d, seed=0)
+    N = R * K
+    inp = V.make_inputs(d, N, seed=11)
+    g = torch.Generator().manual_seed(5)
+    images = [inp["image"][0]] + [torch.rand(3, d.image, d.image, generator=g) * 2 - 1 for _ in range(N - 1)]
+    tokens = [inp["tokens"][0]] + [torch.randint(1, d.vocab - 1, (d.text_ctx,), generator=g) for _ in range(N - 1)]
+    calls = []
+
+    def feature_fn(img_tensor, text_tokens):  # the trunk restatement, evaluated on the pair the reference hands over
+        calls.append((img_tensor.clone(), text_tokens.clone()))
+        return V.extract_features(w, d, img_tensor, text_tokens)
+
+    ens = ref_verifier.build_reference_ensemble(d, w, feature_fn)
+    ens.preprocess = lambda im: im
+    with torch.no_grad():
+        ms, mi, mh, gi = ens.compute_max_similarity_scores_batch(images, tokens, inp["histories"],
+                                                                 cfg_repeat_language_instructions=K)
+    assert len(calls) == N  # every pair WAS encoded ...
+    assert not torch.equal(calls[1][1], calls[0][1])
+    # ... and only pair 0 decided
+    best, idx, scores, means = V.compute_max_similarity_scores(w, d, inp["image"], inp["tokens"], inp["histories"], K)
+    assert int(gi) == idx
+    assert abs(float(ms) - best) < 2e-6
+    assert mi is tokens[min((idx // K) * K, N - 1)]
+    assert mh is inp["histories"][idx]
+    # a different pair 0 gives a different decision value: the check above is not vacuous
+    with torch.no_grad():
+        ms2, *_ = ens.compute_max_similarity_scores_batch(images[1:] + images[:1], tokens[1:] + tokens[:1], inp["histories"],
+                                                          cfg_repeat_language_instructions=K)
+    assert abs(float(ms2) - best) > 1e-6

@@ -155,3 +155,61 @@ def test_reference_slow_path_consumes_pair_zero_only(name, R, K):
         ms2, *_ = ens.compute_max_similarity_scores_batch(images[1:] + images[:1], tokens[1:] + tokens[:1], inp["histories"],
                                                           cfg_repeat_language_instructions=K)
     assert abs(float(ms2) - best) > 1e-6
+
+
+def test_state_token_kv_is_step_and_sample_invariant_on_the_reference():
+    """SURVEY.md F7 on the reference's own code: the suffix's state token attends the prefix and itself only (suffix
+    att mask [1, 1, 0, ...], modeling_pi0.py:590, 619) and its embedding is state_proj(state) alone (:577-580), so its
+    K / V rows in every expert layer are identical in all Euler steps and across the K samples of a rephrase - the hoist
+    the CUDA path applies (state-token K / V once per rephrase, 4 action rows per candidate in steps 1..9) is exact."""
+    from oracle import pi0_oracle as O
+    d = O.TINY
+    R, K = 2, 3
+    model, w = _ref_model(d, 3)
+    inp = O.make_inputs(d, R, K, seed=3)
+    b = O.expand_to_batch(inp, K)
+    expert = model.paligemma_with_expert.gemma_expert.model
+    seen = {}
+    hooks = []
+    for li, layer in enumerate(expert.layers):
+        for nm in ("k_proj", "v_proj"):
+            def hook(mod, args, out, key=(li, nm)):
+                if out.shape[1] == 1 + d.chunk_size:  # the suffix pass (state token + action tokens), not the prefix pass
+                    seen.setdefault(key, []).append(out[:, 0].detach().clone())
+            hooks.append(getattr(layer.self_attn, nm).register_forward_hook(hook))
+    with torch.no_grad():
+        model.sample_actions([b["image"]], [torch.ones(R * K, dtype=torch.bool)], b["tokens"], b["masks"], b["state"],
+                             noise=b["noise"].clone())
+    for h in hooks:
+        h.remove()
+    assert len(seen) == 2 * d.layers
+    for key, rows in seen.items():
+        assert len(rows) == d.num_steps, key
+        for step_rows in rows[1:]:
+            assert torch.equal(step_rows, rows[0]), key          # identical in every Euler step
+        r0 = rows[0].reshape(R, K, -1)
+        assert torch.equal(r0, r0[:, :1].expand_as(r0)), key     # identical across the K samples of a rephrase
+    k_last = seen[(d.layers - 1, "k_proj")][0].reshape(R, K, -1)
+    assert not torch.equal(k_last[0], k_last[1])                 # ... and it does depend on the rephrase
+
+
+@pytest.mark.parametrize("name", ["VTINY", "VMID_MLP"])
+def test_gate_call_equals_score_zero_of_the_full_call_on_the_reference(name):
+    """SURVEY.md F6 on the reference's own code: the 1-candidate gate call of run_simpler_eval_with_openpi.py:344-352 (same
+    image, same instruction, candidate 0 alone) returns the score the N-candidate call of :355-363 gives candidate 0 - one
+    pass yields both answers, which is how CoverStep / EpisodeBatchDriver apply the 0.1 gate without a second launch."""
+    from oracle import make_golden_verifier as G
+    from oracle import verifier_oracle as V
+    d = getattr(V, name)
+    w = V.make_verifier_weights(d, seed=0)
+    R, K = 4, 3
+    inp = V.make_inputs(d, R * K, seed=9)
+    full = G.run_reference(d, w, inp, K)
+    fit = full["it"].mean(0, keepdim=True)
+    fit = fit / fit.norm(dim=-1, keepdim=True)
+    fact = full["act"].mean(0)
+    fact = fact / fact.norm(dim=-1, keepdim=True)
+    score0_of_full_call = float((fit @ fact.T)[0, 0])
+    gate = G.run_reference(d, w, dict(inp, histories=inp["histories"][:1]), 1)
+    assert gate["global_idx"] == 0
+    assert abs(gate["max_score"] - score0_of_full_call) < 1e-6

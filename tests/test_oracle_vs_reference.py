@@ -213,3 +213,36 @@ def test_gate_call_equals_score_zero_of_the_full_call_on_the_reference(name):
     gate = G.run_reference(d, w, dict(inp, histories=inp["histories"][:1]), 1)
     assert gate["global_idx"] == 0
     assert abs(gate["max_score"] - score0_of_full_call) < 1e-6
+
+
+def test_last_prefix_layer_tail_is_dead_code_on_the_reference():
+    """DESIGN.md section 1 (de-duplication): the prefix pass keeps only the KV cache (modeling_pi0.py:688-695 discards the
+    output embeddings), so the LAST PaliGemma layer's o_proj, post-attention norm, MLP and the final norm never reach the
+    sampled actions - the engine stops that layer after K / V.  Shown on the reference: scrambling those weights leaves
+    sample_actions bit-identical, scrambling the same layer's k_proj does not."""
+    from oracle import pi0_oracle as O
+    d = O.TINY
+    R, K = 2, 2
+    model, w = _ref_model(d, 4)
+    inp = O.make_inputs(d, R, K, seed=4)
+    b = O.expand_to_batch(inp, K)
+
+    def run():
+        with torch.no_grad():
+            return model.sample_actions([b["image"]], [torch.ones(R * K, dtype=torch.bool)], b["tokens"], b["masks"],
+                                        b["state"], noise=b["noise"].clone())
+
+    ref = run()
+    lm = model.paligemma_with_expert.paligemma.language_model.model
+    last = lm.layers[d.layers - 1]
+    g = torch.Generator().manual_seed(1)
+    dead = [last.self_attn.o_proj.weight, last.post_attention_layernorm.weight, last.mlp.gate_proj.weight,
+            last.mlp.up_proj.weight, last.mlp.down_proj.weight, lm.norm.weight]
+    with torch.no_grad():
+        for p in dead:
+            p.copy_(torch.randn(p.shape, generator=g).to(p.dtype))
+    assert torch.equal(run(), ref)
+    with torch.no_grad():
+        p = last.self_attn.k_proj.weight
+        p.copy_(torch.randn(p.shape, generator=g).to(p.dtype) * 0.05)
+    assert not torch.equal(run(), ref)

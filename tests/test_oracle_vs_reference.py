@@ -246,3 +246,37 @@ def test_last_prefix_layer_tail_is_dead_code_on_the_reference():
         p = last.self_attn.k_proj.weight
         p.copy_(torch.randn(p.shape, generator=g).to(p.dtype) * 0.05)
     assert not torch.equal(run(), ref)
+
+
+@pytest.mark.parametrize("name,T", [("VTINY", 10), ("VTINY", 6), ("VMID_MLP", 10)])
+def test_predict_and_fuse_embeddings_vs_reference_object(name, T):
+    """SURVEY.md section 8 a16 on the reference's own code: EfficientEnsembleMerged.fuse_embeddings / predict
+    (efficient_ensemble_merged.py:249-307) for one (image, instruction) and N equal-length histories.  The reference does
+    NOT pad here (np.array of the histories, :266-267); the mirror (and cvb_verifier_score) always left-pads to 10 rows
+    of -5, which the trajectory transformer masks as keys and excludes from the mean - shown equivalent at T = 6."""
+    import numpy as np
+    from oracle import ref_verifier
+    from oracle import verifier_oracle as V
+    d = getattr(V, name)
+    w = V.make_verifier_weights(d, seed=0)
+    N = 7
+    inp = V.make_inputs(d, N, seed=13)
+    g = torch.Generator().manual_seed(17)
+    hist = []
+    for _ in range(N):
+        a = torch.rand(T, d.action_dim, generator=g) * 2 - 1
+        a[:, :6] *= 0.05
+        a[:, 6] = (a[:, 6] > 0).float()
+        hist.append(a.numpy())
+    patch, text = V.extract_features(w, d, inp["image"], inp["tokens"])
+    ens = ref_verifier.build_reference_ensemble(d, w, lambda img, tok: (patch, text))
+    ens.preprocess = lambda im: inp["image"][0]
+    with torch.no_grad():
+        fit, fact = ens.fuse_embeddings(inp["image"][0], inp["tokens"][0], hist)
+        best_hist, score_dict = ens.predict(inp["image"][0], inp["tokens"][0], hist)
+    assert fit.shape == (N, d.embed) and torch.equal(fit, fit[:1].expand_as(fit))  # N identical image-text rows
+    scores = V.scores_from_features(w, d, patch, text, V.pad_histories(hist, d.history))
+    ref_scores = torch.tensor([score_dict[str(i)] for i in range(N)])
+    assert (scores - ref_scores).abs().max().item() < 2e-6
+    assert best_hist is hist[int(scores.argmax())]
+    assert np.array_equal(best_hist, hist[int(ref_scores.argmax())])

@@ -1,0 +1,86 @@
+"""The reference's own `VLA_SigLIP2_Bridge.extract_features` (bridge_verifier/ensemble_eval/finetune_trajectory_bridge_ddp.py
+:297-355) EXECUTED UNMODIFIED on an open_clip-shaped model whose towers are Hugging Face transformers' SigLIP (an independent
+implementation of the published architecture; open_clip / timm are absent offline) carrying the oracle's trunk weights.
+
+What this pins (CPU, authoring container): everything the reference does AROUND the third-party trunk - the bf16 cast of the
+image, the two hook points (`visual.trunk.blocks[-1].attn` output, `text.transformer` output, :271-278), `ln_final` +
+`text_projection` applied to every token in bf16, the class-token rule (:340-349), the fp32 cast and the per-token L2
+normalisation - against `oracle.verifier_oracle.extract_features`, which the CUDA trunk is gated against.  Together with
+tests/test_trunk_vs_hf_siglip.py (same towers vs the restated trunk) the only unpinned piece left is whether timm / open_clip
+deviate from the published SigLIP."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from oracle import ref_shim
+from oracle import verifier_oracle as V
+from tests.test_trunk_vs_hf_siglip import _hf_models, _load
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="/root/reference is not present")
+
+
+class _Tap(torch.nn.Module):
+    """Runs `inner` and passes the tensor the open_clip module would return through `tap` (an Identity): a forward hook on
+    `tap` sees exactly what the reference's hook sees on the open_clip / timm module (a tensor, not HF's tuple / dataclass)."""
+
+    def __init__(self, inner, pick):
+        super().__init__()
+        self.inner, self.tap, self.pick = inner, torch.nn.Identity(), pick
+
+    def forward(self, *a, **kw):
+        out = self.inner(*a, **kw)
+        self.tap(self.pick(out))
+        return out
+
+
+def _open_clip_shaped(vis, txt, with_class_token=False):
+    last = vis.vision_model.encoder.layers[-1]
+    last.self_attn = _Tap(last.self_attn, lambda out: out[0] if isinstance(out, tuple) else out)
+    txt.text_model.encoder = _Tap(txt.text_model.encoder, lambda out: out.last_hidden_state)
+    attn_tap = last.self_attn.tap
+    if with_class_token:  # a trunk WITH a class token (577 tokens): the reference drops the first one, :340-342
+        class Prepend(torch.nn.Module):
+            def forward(self, x):
+                return torch.cat([torch.full_like(x[:, :1], 7.0), x], dim=1)
+        attn_tap = Prepend()
+        last.self_attn.tap = attn_tap
+    model = SimpleNamespace(
+        visual=SimpleNamespace(trunk=SimpleNamespace(blocks=[SimpleNamespace(attn=attn_tap)])),
+        text=SimpleNamespace(transformer=txt.text_model.encoder.tap, ln_final=txt.text_model.final_layer_norm,
+                             text_projection=txt.text_model.head),
+        encode_text=lambda text, normalize=False: txt(input_ids=text).pooler_output,
+        encode_image=lambda images, normalize=False: vis(pixel_values=images).pooler_output)
+    return model
+
+
+@pytest.mark.parametrize("name,cls_token", [("VTINY", False), ("VMID", False), ("VTINY", True)])
+def test_reference_extract_features_unmodified_vs_oracle(name, cls_token):
+    _, EM = ref_shim.verifier_modules()
+    d = getattr(V, name)
+    w = V.make_verifier_weights(d, seed=4)
+    inp = V.make_inputs(d, 1, seed=4)
+    vis, txt = _load(d, w, *_hf_models(d), torch.bfloat16)  # the reference keeps the frozen encoder in bf16 (:66)
+    model = _open_clip_shaped(vis, txt, cls_token)
+    # the hook registration of VLA_SigLIP2_Bridge.__init__ (:265-278), on the same attribute paths
+    me = SimpleNamespace(model=model, activation={}, num_img_patches=d.n_patches)
+
+    def get_activation(nm):
+        def hook(module, inputs, output):
+            me.activation[nm] = output
+        return hook
+
+    hooks = [model.visual.trunk.blocks[-1].attn.register_forward_hook(get_activation("image_patches")),
+             model.text.transformer.register_forward_hook(get_activation("text_features"))]
+    with torch.no_grad():
+        patch_ref, text_ref = EM.VLA_SigLIP2_Bridge.extract_features(me, inp["image"], inp["tokens"])  # the reference's lines
+    for h in hooks:
+        h.remove()
+    patch, text = V.extract_features(w, d, inp["image"], inp["tokens"])
+    assert patch_ref.dtype == text_ref.dtype == torch.float32
+    assert patch_ref.shape == patch.shape == (1, d.n_patches, d.width) and text_ref.shape == text.shape == (1, d.text_ctx, d.width)
+    for ours, ref, what in ((patch, patch_ref, "patch features"), (text, text_ref, "text features")):
+        rel = ((ours - ref).norm() / ref.norm()).item()
+        print(f"{name} {what}: rel-L2 oracle vs the reference's extract_features over HF SigLIP (bf16 trunk) {rel:.2e}")
+        assert rel < 2e-2, (what, rel)  # bf16 trunk: measured 0 on this torch build, the gate leaves room for another build
+        assert torch.allclose(ref.norm(dim=-1), torch.ones(ref.shape[:2]), atol=1e-5)  # unit rows, as the heads expect

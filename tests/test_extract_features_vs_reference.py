@@ -84,3 +84,31 @@ def test_reference_extract_features_unmodified_vs_oracle(name, cls_token):
         print(f"{name} {what}: rel-L2 oracle vs the reference's extract_features over HF SigLIP (bf16 trunk) {rel:.2e}")
         assert rel < 2e-2, (what, rel)  # bf16 trunk: measured 0 on this torch build, the gate leaves room for another build
         assert torch.allclose(ref.norm(dim=-1), torch.ones(ref.shape[:2]), atol=1e-5)  # unit rows, as the heads expect
+
+
+def test_whole_reference_decision_without_any_oracle_piece():
+    """End to end with NO oracle code on the reference side: HF SigLIP towers -> the reference's extract_features -> the
+    reference's EfficientEnsembleMerged.compute_max_similarity_scores_batch (heads, fusion, selection) - against the
+    oracle's compute_max_similarity_scores on the same weights and inputs.  (The committed verifier goldens were made with the
+    oracle's trunk injected into the reference object; this shows that choice changes nothing.)"""
+    from oracle import ref_verifier
+    _, EM = ref_shim.verifier_modules()
+    d = V.VMID
+    R, K = 3, 2
+    w = V.make_verifier_weights(d, seed=0)
+    inp = V.make_inputs(d, R * K, seed=21)
+    vis, txt = _load(d, w, *_hf_models(d), torch.bfloat16)
+    model = _open_clip_shaped(vis, txt)
+    me = SimpleNamespace(model=model, activation={}, num_img_patches=d.n_patches)
+    model.visual.trunk.blocks[-1].attn.register_forward_hook(lambda m, i, o: me.activation.__setitem__("image_patches", o))
+    model.text.transformer.register_forward_hook(lambda m, i, o: me.activation.__setitem__("text_features", o))
+    ens = ref_verifier.build_reference_ensemble(
+        d, w, lambda img, tok: EM.VLA_SigLIP2_Bridge.extract_features(me, img, tok))
+    ens.preprocess = lambda im: inp["image"][0]
+    N = R * K
+    with torch.no_grad():
+        ms, mi, mh, gi = ens.compute_max_similarity_scores_batch([inp["image"][0]] * N, [inp["tokens"][0]] * N,
+                                                                 inp["histories"], cfg_repeat_language_instructions=K)
+    best, idx, scores, means = V.compute_max_similarity_scores(w, d, inp["image"], inp["tokens"], inp["histories"], K)
+    assert int(gi) == idx
+    assert abs(float(ms) - best) < 2e-6

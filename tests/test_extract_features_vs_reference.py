@@ -112,3 +112,90 @@ def test_whole_reference_decision_without_any_oracle_piece():
     best, idx, scores, means = V.compute_max_similarity_scores(w, d, inp["image"], inp["tokens"], inp["histories"], K)
     assert int(gi) == idx
     assert abs(float(ms) - best) < 2e-6
+
+
+class _OpenClipShapedSigLIP(torch.nn.Module):
+    """What open_clip.create_model_from_pretrained('hf-hub:timm/ViT-L-16-SigLIP2-384') returns, as far as the reference
+    touches it (efficient_ensemble_merged.py:57-89, finetune_trajectory_bridge_ddp.py:183-214, 265-278, 297-355): an
+    nn.Module with .visual.trunk.{num_features, patch_embed.proj.kernel_size, blocks[-1].attn}, .visual.image_size,
+    .text.{output_dim, transformer, ln_final, text_projection}, encode_image / encode_text - over HF SigLIP towers."""
+
+    def __init__(self, vis, txt, d):
+        super().__init__()
+        self.vis_hf, self.txt_hf = vis, txt
+        last = vis.vision_model.encoder.layers[-1]
+        last.self_attn = _Tap(last.self_attn, lambda out: out[0] if isinstance(out, tuple) else out)
+        txt.text_model.encoder = _Tap(txt.text_model.encoder, lambda out: out.last_hidden_state)
+        self.visual = SimpleNamespace(
+            image_size=(d.image, d.image),
+            trunk=SimpleNamespace(num_features=d.width, blocks=[SimpleNamespace(attn=last.self_attn.tap)],
+                                  patch_embed=SimpleNamespace(proj=SimpleNamespace(kernel_size=(d.patch, d.patch)))))
+        self.text = SimpleNamespace(output_dim=d.width, transformer=txt.text_model.encoder.tap,
+                                    ln_final=txt.text_model.final_layer_norm, text_projection=txt.text_model.head)
+
+    def encode_text(self, text, normalize=False):
+        return self.txt_hf(input_ids=text).pooler_output
+
+    def encode_image(self, images, normalize=False):
+        return self.vis_hf(pixel_values=images).pooler_output
+
+
+def _merged_checkpoint(v, vw):
+    """The merged .pt layout of the reference (one dict of state dicts per member, :94-184) from the synthetic weights -
+    the same construction tests/test_loaders_gpu.py feeds the EfficientEnsembleMerged MIRROR."""
+    comps = []
+    for m in range(v.members):
+        c = {}
+        pre = f"verifier.{m}."
+        for k, t in vw.items():
+            if k.startswith(pre):
+                comp, nm = k[len(pre):].split(".", 1)
+                c.setdefault(comp, {})[nm] = t
+        c["action_padding_value"] = -5.0
+        for unused in ("single_step_action_encoder", "trajectory_encoder", "complex_action_encoder"):
+            c.setdefault(unused, None)
+        comps.append(c)
+    return {"ensemble_components": comps, "backbone": "hf-hub:timm/ViT-L-16-SigLIP2-384", "use_transformer": v.traj_layers > 0,
+            "history_length": v.history, "action_dim": v.action_dim, "num_models": v.members}
+
+
+@pytest.mark.parametrize("name,weights_only", [("VMID", False), ("VMID", True), ("VMID_MLP", False)])
+def test_reference_constructor_and_decision_unmodified(tmp_path, monkeypatch, name, weights_only):
+    """The reference's EfficientEnsembleMerged(merged_checkpoint_path, device) - its REAL __init__ (:26-186: torch.load of
+    the merged file, strict load_state_dict of every component, VLA_SigLIP2_Bridge with its hooks) and its REAL
+    compute_max_similarity_scores_batch / extract_shared_features - on a merged checkpoint in the layout the mirror's loader
+    test uses; only open_clip.create_model_from_pretrained / get_tokenizer (absent offline) are replaced, by HF SigLIP
+    towers with the oracle's trunk weights.  VMID has the head sizes the reference hard-codes (512 / 8 heads / 4 layers /
+    feed-forward 1024 / hidden 512), so nothing else is touched.  Result against the oracle's decision."""
+    _, EM = ref_shim.verifier_modules()
+    d = getattr(V, name)
+    w = V.make_verifier_weights(d, seed=0)
+    ck = _merged_checkpoint(d, w)
+    if weights_only:  # :40-48 - a checkpoint without metadata takes the CoVer-BridgeV2 defaults
+        ck = {"ensemble_components": ck["ensemble_components"]}
+    path = tmp_path / "merged.pt"
+    torch.save(ck, path)
+    created = []
+
+    def create_model_from_pretrained(backbone):
+        created.append(backbone)
+        vis, txt = _load(d, w, *_hf_models(d), torch.float32)  # the reference casts the encoder to bf16 itself (:66)
+        return _OpenClipShapedSigLIP(vis, txt, d), (lambda im: im)
+
+    monkeypatch.setattr(EM, "create_model_from_pretrained", create_model_from_pretrained)
+    monkeypatch.setattr(EM, "get_tokenizer", lambda backbone: (lambda texts, context_length=64: None))
+    ens = EM.EfficientEnsembleMerged(str(path), device="cpu")
+    assert created == ["hf-hub:timm/ViT-L-16-SigLIP2-384"]
+    assert (ens.num_models, ens.history_length, ens.action_dim, ens.use_transformer) == (d.members, 10, 7, d.traj_layers > 0)
+    assert all(p.dtype == torch.bfloat16 for p in ens.siglip_model.parameters())
+    R, K = 3, 2
+    N = R * K
+    inp = V.make_inputs(d, N, seed=23)
+    ms, mi, mh, gi = ens.compute_max_similarity_scores_batch([inp["image"][0]] * N, [inp["tokens"][0]] * N, inp["histories"],
+                                                             cfg_repeat_language_instructions=K)
+    best, idx, scores, means = V.compute_max_similarity_scores(w, d, inp["image"], inp["tokens"], inp["histories"], K)
+    assert int(gi) == idx
+    assert abs(float(ms) - best) < 2e-6
+    patch_ref, text_ref = ens.extract_shared_features(inp["image"], inp["tokens"])
+    patch, text = V.extract_features(w, d, inp["image"], inp["tokens"])
+    assert ((patch - patch_ref).norm() / patch_ref.norm()).item() < 2e-2 and ((text - text_ref).norm() / text_ref.norm()).item() < 2e-2

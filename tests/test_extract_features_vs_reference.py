@@ -123,6 +123,7 @@ class _OpenClipShapedSigLIP(torch.nn.Module):
     def __init__(self, vis, txt, d):
         super().__init__()
         self.vis_hf, self.txt_hf = vis, txt
+        self.context_length = d.text_ctx  # read by the string-instruction branches (:256-257, :342)
         last = vis.vision_model.encoder.layers[-1]
         last.self_attn = _Tap(last.self_attn, lambda out: out[0] if isinstance(out, tuple) else out)
         txt.text_model.encoder = _Tap(txt.text_model.encoder, lambda out: out.last_hidden_state)
@@ -199,3 +200,35 @@ def test_reference_constructor_and_decision_unmodified(tmp_path, monkeypatch, na
     patch_ref, text_ref = ens.extract_shared_features(inp["image"], inp["tokens"])
     patch, text = V.extract_features(w, d, inp["image"], inp["tokens"])
     assert ((patch - patch_ref).norm() / patch_ref.norm()).item() < 2e-2 and ((text - text_ref).norm() / text_ref.norm()).item() < 2e-2
+
+
+@pytest.mark.skipif(bool(__import__("os").environ.get("CVB_FAST_TESTS")), reason="full-size ViT-L on the CPU (about a minute); CVB_FAST_TESTS=1 skips it")
+def test_full_size_golden_is_reproduced_by_the_unmodified_reference_constructor(tmp_path, monkeypatch):
+    """BASELINE.json configs[0] at FULL size: tests/golden/verifier_vfull_R8K5.pt (made with the oracle's trunk injected into the
+    reference object) against the reference's real constructor + string-instruction fast path (:330-347) over HF SigLIP
+    ViT-L/16-384 towers carrying the same weights - the fixture the CUDA path is gated against at the configuration of record
+    does not depend on the oracle's trunk restatement."""
+    from pathlib import Path
+    _, EM = ref_shim.verifier_modules()
+    fx = torch.load(Path(__file__).resolve().parent / "golden" / "verifier_vfull_R8K5.pt")
+    d = V.VFULL
+    R, K = fx["R"], fx["K"]
+    N = R * K
+    w = V.make_verifier_weights(d, seed=0)
+    inp = V.make_inputs(d, N, seed=fx["seed"])
+    path = tmp_path / "merged.pt"
+    torch.save(_merged_checkpoint(d, w), path)
+
+    def create_model_from_pretrained(backbone):
+        vis, txt = _load(d, w, *_hf_models(d), torch.float32)
+        return _OpenClipShapedSigLIP(vis, txt, d), (lambda im: im)
+
+    monkeypatch.setattr(EM, "create_model_from_pretrained", create_model_from_pretrained)
+    monkeypatch.setattr(EM, "get_tokenizer", lambda backbone: (lambda texts, context_length=64: inp["tokens"][:1].clone()))
+    ens = EM.EfficientEnsembleMerged(str(path), device="cpu")
+    instr = "put the carrot on the plate"
+    ms, mi, mh, gi = ens.compute_max_similarity_scores_batch([inp["image"][0]] * N, [instr] * N, inp["histories"],
+                                                             cfg_repeat_language_instructions=K)
+    print(f"VFULL R{R}K{K}: reference constructor path max_score {float(ms):.9f} idx {int(gi)}; golden {fx['max_score']:.9f} idx {fx['global_idx']}")
+    assert mi == instr and int(gi) == fx["global_idx"]
+    assert abs(float(ms) - fx["max_score"]) <= 1e-3 * float(fx["scores"].abs().max())

@@ -182,3 +182,38 @@ def test_tf_resize_restatement_agrees_with_an_independent_implementation(H, W):
         ref_u8 = ref[0].permute(1, 2, 0).numpy().astype(np.uint8)  # tf.cast(float -> uint8) truncates
         diff = np.abs(ours.astype(np.int32) - ref_u8.astype(np.int32))
         assert diff.max() <= 1 and (diff == 0).mean() > 0.97, (diff.max(), (diff == 0).mean())
+
+
+@pytest.mark.skipif(not __import__("pathlib").Path("/root/reference/INT-ACT/src/utils/pipeline.py").exists(),
+                    reason="/root/reference is not present")
+def test_policy_image_oracle_matches_the_reference_preprocess_executed_unmodified():
+    """The reference's own BridgeSimplerAdapter.preprocess (INT-ACT/src/experiments/env_adapters/simpler.py:43-93) with the real
+    rescale / normalize / process_images of INT-ACT/src/utils/pipeline.py:34-69 and normalize_bound (base.py:8-18), AST-extracted
+    and executed as they are (the modules' import chains need absent packages): its 'observation.images.top' tensor equals the
+    oracle's policy_image bit for bit - cv2's Lanczos4 AND torch's float32 rescale / normalise arithmetic."""
+    import ast
+    import json
+    import types
+    cv2 = pytest.importorskip("cv2")
+    from oracle.make_golden_exec import REF, _method_source
+    src = (REF / "INT-ACT/src/utils/pipeline.py").read_text()
+    ns = {"torch": torch, "np": np, "cv2": cv2,
+          "IMAGENET_STANDARD_MEAN": torch.tensor([0.5, 0.5, 0.5]), "IMAGENET_STANDARD_STD": torch.tensor([0.5, 0.5, 0.5])}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("rescale", "normalize", "process_images"):
+            exec(ast.get_source_segment(src, node), ns)
+    exec(_method_source(REF / "INT-ACT/src/experiments/env_adapters/simpler.py", "SimplerAdapter", "preprocess"), ns)
+    exec(_method_source(REF / "INT-ACT/src/experiments/env_adapters/base.py", "BaseEnvAdapter", "normalize_bound"), ns)
+    stats = json.loads((REF / "INT-ACT/config/dataset/bridge_statistics.json").read_text())
+    me = types.SimpleNamespace(image_size=(224, 224), state_normalization_type="bound", dataset_statistics=stats,
+                               dtype=torch.float32, preprocess_proprio=lambda s: np.asarray(s, dtype=np.float64))
+    me.normalize_bound = types.MethodType(ns["normalize_bound"], me)
+    rng = np.random.default_rng(12)
+    for H, W in [(480, 640), (224, 224), (97, 301)]:
+        frame = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+        out = ns["preprocess"](me, {"observation.images.top": frame, "observation.state": rng.normal(size=7), "task": "x"})
+        img = out["observation.images.top"]
+        assert img.dtype == torch.float32 and tuple(img.shape) == (1, 3, 224, 224)
+        u8, f32 = P.policy_image(frame, 224)
+        assert np.array_equal(img.numpy(), f32), (H, W)
+        assert out["task"] == ["x"] and tuple(out["observation.state"].shape) == (1, 7)
